@@ -1,0 +1,357 @@
+"""CPU oracle for the TA3N hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this module.  The product package
+(``ta3n_b200``) never imports it and has no CPU fallback.
+
+What it is: a functional, eager-PyTorch (CPU, fp32 or fp64) restatement of the
+one code path of cmhungsteve/TA3N that this repo accelerates:
+
+    VideoModel.forward with frame_aggregation='trn-m', baseline_type='video',
+    add_fc=1, use_bn='none', ens_DA='none', share_params='Y',
+    use_attn in {'TransAttn','none'}, use_attn_frame in {'none','TransAttn'}
+
+plus the loss composition that main.py applies right after it.  Each function
+cites the reference file:line it follows (paths relative to /root/reference).
+
+Parity pinning: the reference ships no tests or golden vectors,
+so this oracle is pinned against the *live* reference, imported unmodified in
+the build container through ``oracle/ref_shims.py``:
+  * ``tests/test_oracle_vs_reference.py`` compares every output and every
+    parameter gradient of this file with the reference classes (skipped when
+    /root/reference is absent, e.g. on the GPU box);
+  * ``oracle/gen_golden.py`` ran the reference to produce ``tests/golden/*.npz``;
+    ``tests/test_oracle_golden.py`` checks this oracle against those fixtures
+    everywhere.
+
+The arithmetic itself lives in PyTorch (a third-party dependency of the
+reference, requirements.txt:98 pins torch==2.2.0; this image has 2.11.0); the
+oracle therefore uses the same ATen CPU ops in the same order as the reference
+so that its timing is a fair stand-in for "the reference's CPU path" where the
+Python reference itself cannot travel (the GPU box has no /root/reference).
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+FEATURE_DIM = 2048     # ResNet-101 pool5 width; models.py:125-126 reads fc.in_features
+NUM_BOTTLENECK = 256   # models.py:223
+INIT_STD = 1e-3        # models.py:128
+
+
+@dataclass(frozen=True)
+class PathConfig:
+    """The knobs of the hot path (constructor args of models.py:59-67 that matter here)."""
+    num_class: int = 12
+    num_segments: int = 5          # train_segments == val_segments for trn-m
+    fc_dim: int = 512
+    dropout_i: float = 0.5
+    dropout_v: float = 0.5
+    use_attn: str = "TransAttn"    # or 'none'
+    use_attn_frame: str = "none"   # or 'TransAttn'
+
+    @property
+    def shared_dim(self) -> int:   # models.py:129
+        return min(self.fc_dim, FEATURE_DIM)
+
+
+# ----------------------------------------------------------------------------
+# static relation tables                                     TRNmodule.py:30-41
+# ----------------------------------------------------------------------------
+def relation_tuples(num_frames: int, subsample: int = 3) -> List[List[Tuple[int, ...]]]:
+    """Frame tuples actually evaluated per scale, largest scale first.
+
+    TRNmodule.py:34   scales = [T, T-1, ..., 2]
+    TRNmodule.py:36-41 all lexicographic combinations per scale, min(3, N) kept
+    TRNmodule.py:60   the first (largest) scale uses combination 0 only
+    TRNmodule.py:71   evenly spaced pick: idx_k = ceil(k * N / n_sel)
+    """
+    chosen: List[List[Tuple[int, ...]]] = []
+    for pos, scale in enumerate(range(num_frames, 1, -1)):
+        combos = list(itertools.combinations(range(num_frames), scale))
+        if pos == 0:
+            chosen.append([combos[0]])
+            continue
+        n_sel = min(subsample, len(combos))
+        picks = [int(math.ceil(k * len(combos) / n_sel)) for k in range(n_sel)]
+        chosen.append([combos[i] for i in picks])
+    return chosen
+
+
+# ----------------------------------------------------------------------------
+# parameters                                   models.py:119-325 (_prepare_DA)
+# ----------------------------------------------------------------------------
+def _std_linear(n_in: int, n_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """nn.Linear followed by normal_(w, 0, 0.001), constant_(b, 0)   (models.py:141-143 etc.)."""
+    lin = torch.nn.Linear(n_in, n_out)          # consumes RNG exactly like the reference
+    torch.nn.init.normal_(lin.weight, 0, INIT_STD)
+    torch.nn.init.constant_(lin.bias, 0)
+    return lin.weight.detach(), lin.bias.detach()
+
+
+def _default_linear(n_in: int, n_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """nn.Linear with PyTorch's default init (TRNmodule.py:48-52, models.py:289-293)."""
+    lin = torch.nn.Linear(n_in, n_out)
+    return lin.weight.detach(), lin.bias.detach()
+
+
+def init_params(cfg: PathConfig, seed: Optional[int] = None) -> "OrderedDict[str, torch.Tensor]":
+    """Create the state_dict of the reference VideoModel for this path, in the
+    reference's construction order so the same seed yields the same values.
+
+    Order (models.py): :141 shared, :156 fc_feature_source, :161 fc_feature_domain,
+    :166 fc_classifier_source, :170 fc_classifier_domain, :224 TRN (TRNmodule.py:45-54),
+    :225-226 bn_trn_{S,T}, :258/:262 fc_feature_video_source{,_2}, :267 fc_feature_domain_video,
+    :272 fc_classifier_video_source, :281 fc_classifier_domain_video, :286-294 relation discs.
+    """
+    if seed is not None:
+        torch.manual_seed(seed)
+    Fd, H, C, T = cfg.shared_dim, NUM_BOTTLENECK, cfg.num_class, cfg.num_segments
+    p: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+
+    def put(name, wb):
+        p[name + ".weight"], p[name + ".bias"] = wb
+
+    put("fc_feature_shared_source", _std_linear(FEATURE_DIM, Fd))
+    put("fc_feature_source", _std_linear(Fd, Fd))               # registered, unused (App. C)
+    put("fc_feature_domain", _std_linear(Fd, Fd))
+    put("fc_classifier_source", _std_linear(Fd, C))             # executed, output dropped
+    put("fc_classifier_domain", _std_linear(Fd, 2))
+    for i, scale in enumerate(range(T, 1, -1)):
+        put(f"TRN.fc_fusion_scales.{i}.1", _default_linear(scale * Fd, H))
+    for dom in ("S", "T"):                                      # BatchNorm1d(256), unused here
+        p[f"bn_trn_{dom}.weight"] = torch.ones(H)
+        p[f"bn_trn_{dom}.bias"] = torch.zeros(H)
+        p[f"bn_trn_{dom}.running_mean"] = torch.zeros(H)
+        p[f"bn_trn_{dom}.running_var"] = torch.ones(H)
+        p[f"bn_trn_{dom}.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    put("fc_feature_video_source", _std_linear(H, H))           # unused
+    put("fc_feature_video_source_2", _std_linear(H, H))         # unused
+    put("fc_feature_domain_video", _std_linear(H, H))
+    put("fc_classifier_video_source", _std_linear(H, C))
+    put("fc_classifier_domain_video", _std_linear(H, 2))
+    for i in range(T - 1):
+        put(f"relation_domain_classifier_all.{i}.0", _default_linear(H, H))
+        put(f"relation_domain_classifier_all.{i}.2", _default_linear(H, 2))
+    return p
+
+
+USED_PARAM_PREFIXES = (
+    "fc_feature_shared_source", "fc_feature_domain.", "fc_classifier_domain.",
+    "TRN.", "fc_feature_domain_video", "fc_classifier_video_source",
+    "fc_classifier_domain_video", "relation_domain_classifier_all",
+)
+
+
+def used_param_names(params: Dict[str, torch.Tensor]) -> List[str]:
+    """Names of the parameters that receive gradients on this path."""
+    return [k for k in params
+            if k.startswith(USED_PARAM_PREFIXES) and params[k].dtype.is_floating_point]
+
+
+# ----------------------------------------------------------------------------
+# building blocks
+# ----------------------------------------------------------------------------
+class _FlipGrad(torch.autograd.Function):
+    """Gradient reversal: identity forward, -beta * g backward (models.py:20-29)."""
+
+    @staticmethod
+    def forward(ctx, x, beta):
+        ctx.beta = float(beta)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.neg() * ctx.beta, None
+
+
+def grad_reverse(x: torch.Tensor, beta: float) -> torch.Tensor:
+    return _FlipGrad.apply(x, beta)
+
+
+def entropy_attention(logits: torch.Tensor) -> torch.Tensor:
+    """w = 1 - H(softmax(logits)) along dim 1 (models.py:351-357)."""
+    q = F.softmax(logits, dim=1)
+    lq = F.log_softmax(logits, dim=1)
+    return 1 - torch.sum(-q * lq, 1)
+
+
+def _apply_dropout(x: torch.Tensor, p: float, train: bool, mask: Optional[torch.Tensor]) -> torch.Tensor:
+    """nn.Dropout semantics (models.py:133-134).  ``mask`` (0/1 keep mask, same shape)
+    overrides the RNG so that CUDA and oracle see the same drops."""
+    if not train or p <= 0.0:
+        return x
+    if mask is None:
+        return F.dropout(x, p, True)
+    return x * mask.to(x.dtype) * (1.0 / (1.0 - p))
+
+
+def trn_multiscale(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+                   tuples: List[List[Tuple[int, ...]]]) -> torch.Tensor:
+    """RelationModuleMultiScale.forward (TRNmodule.py:58-82).
+
+    x (N, T, F) -> (N, T-1, H);  out[:, i] = sum_r relu(W_i . concat_j relu(x[:, tau_ir[j]]) + b_i)
+    """
+    per_scale = []
+    for i, rels in enumerate(tuples):
+        acc = None
+        for tau in rels:
+            u = x[:, list(tau), :].reshape(x.size(0), -1)             # :60-61 / :75-76
+            a = F.relu(F.linear(F.relu(u), weights[i], biases[i]))    # :46-54 ReLU-Linear-ReLU
+            acc = a if acc is None else acc + a                        # :79
+        per_scale.append(acc.unsqueeze(1))
+    return torch.cat(per_scale, 1)                                     # :81
+
+
+def two_layer_disc(x: torch.Tensor, w1, b1, w2, b2, beta: float) -> torch.Tensor:
+    """GradReverse -> Linear -> ReLU -> Linear(->2) (models.py:456-470, 477-479)."""
+    h = F.relu(F.linear(grad_reverse(x, beta), w1, b1))
+    return F.linear(h, w2, b2)
+
+
+# ----------------------------------------------------------------------------
+# one domain through the path                            models.py:557-704
+# ----------------------------------------------------------------------------
+def _forward_domain(p: Dict[str, torch.Tensor], x: torch.Tensor, beta: Sequence[float], mu: float,
+                    cfg: PathConfig, train: bool, reverse: bool,
+                    mask_i: Optional[torch.Tensor], mask_v: Optional[torch.Tensor]):
+    T, Fd, H = cfg.num_segments, cfg.shared_dim, NUM_BOTTLENECK
+    R = T - 1
+    batch = x.size(0)
+    tuples = relation_tuples(T)
+
+    flat = x.reshape(-1, x.size(-1))                                                   # :557
+    feat = F.linear(flat, p["fc_feature_shared_source.weight"], p["fc_feature_shared_source.bias"])  # :565
+    feat = F.relu(feat)                                                                # :572
+    feat = _apply_dropout(feat, cfg.dropout_i, train, mask_i)                          # :574
+    feat_frames = feat.view(batch, T, Fd)                                              # :578
+
+    pred_frame = two_layer_disc(feat, p["fc_feature_domain.weight"], p["fc_feature_domain.bias"],
+                                p["fc_classifier_domain.weight"], p["fc_classifier_domain.bias"],
+                                beta[2])                                               # :606
+    if cfg.use_attn_frame != "none":                                                   # :612-614, :368-377
+        w_frame = entropy_attention(pred_frame)
+        feat = (w_frame.view(-1, 1) + 1) * feat
+
+    # fc_classifier_source (:617) is executed by the reference but its output is
+    # dropped for baseline_type='video' (:437-441); it has no effect on any output.
+
+    rel = trn_multiscale(feat.view(batch, T, Fd),
+                         [p[f"TRN.fc_fusion_scales.{i}.1.weight"] for i in range(R)],
+                         [p[f"TRN.fc_fusion_scales.{i}.1.bias"] for i in range(R)],
+                         tuples)                                                       # :635
+
+    pred_rel = torch.stack(
+        [two_layer_disc(rel[:, i, :],
+                        p[f"relation_domain_classifier_all.{i}.0.weight"],
+                        p[f"relation_domain_classifier_all.{i}.0.bias"],
+                        p[f"relation_domain_classifier_all.{i}.2.weight"],
+                        p[f"relation_domain_classifier_all.{i}.2.bias"], beta[0])
+         for i in range(R)], 1)                                                        # :472-488 -> (B,R,2)
+
+    if cfg.use_attn != "none":                                                         # :643-645, :379-388
+        w_rel = entropy_attention(pred_rel.reshape(-1, 2)).view(batch, R)
+        rel_att = (w_rel.unsqueeze(-1) + 1) * rel
+        attn = w_rel
+    else:                                                                              # :647
+        rel_att = rel
+        attn = rel[:, :, 0]
+
+    feat_video = rel_att.sum(1)                                                        # :651
+    vid = _apply_dropout(feat_video, cfg.dropout_v, train, mask_v)                     # :679
+    if reverse:                                                                        # :682-684
+        vid = grad_reverse(vid, mu)
+    pred_video = F.linear(vid, p["fc_classifier_video_source.weight"],
+                          p["fc_classifier_video_source.bias"])                        # :686
+    pred_dom_video = two_layer_disc(vid, p["fc_feature_domain_video.weight"],
+                                    p["fc_feature_domain_video.bias"],
+                                    p["fc_classifier_domain_video.weight"],
+                                    p["fc_classifier_domain_video.bias"], beta[1])     # :694
+
+    pred_domain = [pred_rel, pred_dom_video, pred_frame.view(batch, T, 2)]            # reversed list, :722
+    feats = [pred_video, feat_video, feat_frames]                                      # reversed list, :722
+    return attn, pred_video, pred_video, pred_domain, feats                            # :713 out_2 = out
+
+
+def forward(params: Dict[str, torch.Tensor], input_source: torch.Tensor, input_target: torch.Tensor,
+            beta: Sequence[float], mu: float, cfg: PathConfig, train: bool = True, reverse: bool = False,
+            masks: Optional[Dict[str, torch.Tensor]] = None):
+    """VideoModel.forward (models.py:545-722) -> the reference's 10-tuple.
+
+    ``masks`` may hold keep-masks 'i_source' (Bs*T,F), 'i_target', 'v_source' (Bs,H), 'v_target'.
+    """
+    masks = masks or {}
+    src = _forward_domain(params, input_source, beta, mu, cfg, train, reverse,
+                          masks.get("i_source"), masks.get("v_source"))
+    tgt = _forward_domain(params, input_target, beta, mu, cfg, train, reverse,
+                          masks.get("i_target"), masks.get("v_target"))
+    return src + tgt
+
+
+# ----------------------------------------------------------------------------
+# loss composition of the shipped script     main.py:446, 508-538, 559-562
+# ----------------------------------------------------------------------------
+def attentive_entropy(pred: torch.Tensor, pred_domain: torch.Tensor) -> torch.Tensor:
+    """loss.py:15-25."""
+    dq = F.softmax(pred_domain, dim=1)
+    dlq = F.log_softmax(pred_domain, dim=1)
+    weights = 1 + torch.sum(-dq * dlq, 1)
+    q = F.softmax(pred, dim=1)
+    lq = F.log_softmax(pred, dim=1)
+    return torch.mean(weights * torch.sum(-q * lq, 1))
+
+
+def compose_loss(outputs, label_source: torch.Tensor, gamma: float = 0.003,
+                 place_adv: Sequence[str] = ("Y", "Y", "Y"), use_attn: str = "TransAttn") -> torch.Tensor:
+    """use_target='uSv', adv_DA='RevGrad', add_loss_DA='attentive_entropy'.
+
+    main.py:446      class CE on source only
+    main.py:508-538  for l in (relation, video, frame): CE(cat(pred_S, pred_T), cat(0s, 1s))
+    main.py:559-562  + gamma * attentive_entropy(cat(out_S, out_T), pred_domain_all[1])
+                     (only when use_attn != 'none', main.py:559)
+    """
+    (_, out_s, _, pd_s, _, _, out_t, _, pd_t, _) = outputs
+    loss = F.cross_entropy(out_s, label_source)
+    stacked = []
+    for lvl, flag in enumerate(place_adv):
+        if flag != "Y":
+            continue
+        ps = pd_s[lvl].reshape(-1, 2)
+        pt = pd_t[lvl].reshape(-1, 2)
+        dom = torch.cat([torch.zeros(ps.size(0), dtype=torch.long),
+                         torch.ones(pt.size(0), dtype=torch.long)])
+        both = torch.cat([ps, pt], 0)
+        stacked.append(both)
+        loss = loss + F.cross_entropy(both, dom)
+    if use_attn != "none" and len(stacked) > 1:
+        loss = loss + gamma * attentive_entropy(torch.cat([out_s, out_t], 0), stacked[1])
+    return loss
+
+
+def train_step(params: Dict[str, torch.Tensor], xs, xt, labels, beta, cfg: PathConfig,
+               gamma: float = 0.003, train: bool = True, masks=None):
+    """forward + composed loss + backward; returns (loss, outputs, grads-by-name)."""
+    names = used_param_names(params)
+    leaves = {k: params[k].detach().clone().requires_grad_(True) for k in names}
+    live = dict(params)
+    live.update(leaves)
+    outs = forward(live, xs, xt, beta, 0.0, cfg, train=train, reverse=False, masks=masks)
+    loss = compose_loss(outs, labels, gamma, use_attn=cfg.use_attn)
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    return loss.detach(), outs, OrderedDict(zip(names, grads))
+
+
+def synthetic_batch(batch: int, cfg: PathConfig, seed: int = 4321, dtype=torch.float32):
+    """Synthetic (B,T,2048) N(0,1) features and labels arange(B) % C."""
+    g = torch.Generator().manual_seed(seed)
+    xs = torch.randn(batch, cfg.num_segments, FEATURE_DIM, generator=g).to(dtype)
+    xt = torch.randn(batch, cfg.num_segments, FEATURE_DIM, generator=g).to(dtype)
+    labels = torch.arange(batch) % cfg.num_class
+    return xs, xt, labels
