@@ -1,0 +1,184 @@
+/*
+ * ta3n_b200.h -- C ABI of libta3n_sm100.so: the B200 (sm_100a) implementation of the
+ * TA3N hot path (TRN-M relation aggregation + domain-attentive pooling + gradient-reversal
+ * discriminators inside VideoModel.forward of cmhungsteve/TA3N).
+ *
+ * The reference has no FFI: its "operator interface" for this path is the set of Python
+ * methods of models.py / TRNmodule.py that call ATen.  Each entry point below replaces one
+ * of those methods (cited as file:line, paths relative to the reference root) and is what a
+ * ctypes / pybind stub in the reference would bind.
+ *
+ * Conventions
+ *   - every tensor is fp32, row-major, contiguous unless a leading dimension is given;
+ *     all pointers are DEVICE pointers unless the name ends in _host;
+ *   - weights use the nn.Linear layout [out_features, in_features];
+ *   - the library allocates nothing and never synchronises: the caller passes outputs,
+ *     saved-for-backward buffers and a workspace (sizes from the *_workspace_bytes queries);
+ *     every call enqueues work on `stream` (a cudaStream_t) of the current device and is
+ *     CUDA-graph capturable;
+ *   - return value: 0 on success, a TA3N_ERR_* code otherwise (never throws/aborts);
+ *     ta3n_last_error() gives a thread-local message;
+ *   - "rows" M is the number of videos (source rows first, then target rows: weights are
+ *     shared between domains -- models.py:565-566 with share_params='Y' -- and no op on the
+ *     path mixes rows, so both domains go through one launch).
+ */
+#ifndef TA3N_B200_H_
+#define TA3N_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TA3N_ABI_VERSION 1
+
+enum {
+  TA3N_OK = 0,
+  TA3N_ERR_INVALID = 1,   /* bad argument (null pointer, unsupported size)           */
+  TA3N_ERR_WORKSPACE = 2, /* workspace too small                                      */
+  TA3N_ERR_CUDA = 3,      /* a CUDA runtime / driver call failed                      */
+  TA3N_ERR_UNSUPPORTED = 4
+};
+
+/* GEMM engines for the dense contractions. */
+enum {
+  TA3N_GEMM_FP32_SIMT = 0,   /* exact fp32 FFMA tiles (parity / debugging engine)     */
+  TA3N_GEMM_TF32_TCGEN05 = 1 /* tcgen05.mma kind::tf32, TMA-staged, TMEM accumulators */
+};
+
+typedef void* ta3n_stream_t; /* cudaStream_t */
+
+/* Relation table of RelationModuleMultiScale (TRNmodule.py:30-41, 66-71), host arrays:
+ *   n_scales            = T-1 (scale i uses scale_size[i] = T-i frames)
+ *   rel_count[i]        = relations evaluated for scale i (1 for i==0, else min(3, C(T,s)))
+ *   frames              = concatenation over scales i, relations r, of scale_size[i] frame ids
+ */
+typedef struct {
+  int num_frames;           /* T */
+  int n_scales;             /* R = T-1 */
+  const int* scale_size;    /* [n_scales] host */
+  const int* rel_count;     /* [n_scales] host */
+  const int* frames;        /* [sum_i rel_count[i]*scale_size[i]] host */
+} ta3n_relation_table;
+
+/* Dropout control.  keep==NULL and p>0 -> counter-based in-kernel RNG keyed by
+ * (seed, *step_dev) (step_dev may be NULL); keep!=NULL -> caller-provided 0/1 keep mask
+ * (uint8, same shape as the tensor it masks).  p<=0 -> no dropout.                       */
+typedef struct {
+  float p;
+  const uint8_t* keep;
+  uint64_t seed;
+  const uint64_t* step_dev;
+} ta3n_dropout;
+
+/* ---- library state ---------------------------------------------------------------- */
+int ta3n_abi_version(void);
+const char* ta3n_last_error(void);
+/* number of kernels this library has launched since load / last reset (all threads) */
+uint64_t ta3n_launch_count(void);
+void ta3n_reset_launch_count(void);
+/* select the GEMM engine used by subsequent calls (process-wide). */
+int ta3n_set_gemm_engine(int engine);
+int ta3n_get_gemm_engine(void);
+
+/* ---- shared frame layer: Dropout(ReLU(x W^T + b))  (models.py:565-575) ------------- */
+/* x_src [rows_src, D], x_tgt [rows_tgt, D] (rows = videos*T); feat [rows_src+rows_tgt, F] */
+int ta3n_shared_fc_fwd(const float* x_src, int rows_src, const float* x_tgt, int rows_tgt, int D,
+                       const float* W, const float* b, int F, const ta3n_dropout* drop,
+                       float* feat, ta3n_stream_t stream);
+size_t ta3n_shared_fc_bwd_workspace_bytes(int rows, int D, int F);
+/* dfeat [rows, F] is consumed (overwritten with d pre-activation). Inputs carry no grad
+ *  so only dW [F, D], db [F] are produced.                                   */
+int ta3n_shared_fc_bwd(const float* x_src, int rows_src, const float* x_tgt, int rows_tgt, int D,
+                       int F, const float* feat, float* dfeat, const float* g_feat_ext, float p,
+                       float* dW, float* db, void* workspace, size_t workspace_bytes,
+                       ta3n_stream_t stream);
+
+/* ---- GradReverse + two-layer domain discriminator ---------------------------------- */
+/* models.py:456-462 (frame level), :464-470 (video level):
+ *   logits = W2 relu(W1 GRL_beta(x) + b1) + b2,  x [rows, K], W1 [Kh, K], W2 [2, Kh]     */
+int ta3n_disc_fwd(const float* x, int rows, int K, int Kh, const float* W1, const float* b1,
+                  const float* W2, const float* b2, float* hidden, float* logits,
+                  ta3n_stream_t stream);
+size_t ta3n_disc_bwd_workspace_bytes(int rows, int K, int Kh);
+/* dx += -beta * dgrad (accumulate!=0) or dx = -beta * dgrad;  dx may be NULL.            */
+int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, const float* W2,
+                  const float* hidden, const float* g_logits, float beta, float* dx,
+                  int accumulate, float* dW1, float* db1, float* dW2, float* db2,
+                  void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
+/* stand-alone gradient reversal backward, models.py:27-29: out = -beta * g               */
+int ta3n_grl_bwd(const float* g, float beta, float* out, size_t n, ta3n_stream_t stream);
+
+/* ---- frame-level transferable attention (models.py:368-377, use_attn_frame) -------- */
+/* w = 1 - H(softmax(logits)); out = (w + 1) * feat;  logits [rows,2], feat [rows,F]      */
+int ta3n_frame_attn_fwd(const float* feat, const float* logits, int rows, int F, float* out,
+                        ta3n_stream_t stream);
+/* d_out [rows,F] is rewritten in place with d feat; g_logits [rows,2] += d w * dw/dlogits */
+int ta3n_frame_attn_bwd(const float* feat, const float* logits, int rows, int F, float* d_out,
+                        float* g_logits, ta3n_stream_t stream);
+
+/* ---- multi-scale temporal relation module (TRNmodule.py:58-82) --------------------- */
+/* x [M, T, F];  W_host[i] -> device [H, scale_size[i]*F];  b_host[i] -> device [H]
+ * act [n_rel_total, M, H] : relu'd relation activations (saved for backward)
+ * feat_rel [M, R, H]      : per-scale sums (the module output)
+ * relu_input != 0 applies the leading nn.ReLU of fc_fusion (TRNmodule.py:49) to x; callers
+ * that know x >= 0 (inside VideoModel: post-ReLU/dropout features) may pass 0.           */
+int ta3n_trn_fwd(const float* x, int M, int F, int H, const ta3n_relation_table* tab,
+                 const float* const* W_host, const float* const* b_host, int relu_input,
+                 float* act, float* feat_rel, ta3n_stream_t stream);
+size_t ta3n_trn_bwd_workspace_bytes(int M, int F, int H, const ta3n_relation_table* tab);
+/* d_feat_rel [M,R,H] -> dW_host[i] [H, s_i F], db_host[i] [H], dx [M,T,F] (dx may be NULL) */
+int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table* tab,
+                 const float* const* W_host, int relu_input, const float* act,
+                 const float* d_feat_rel, float* const* dW_host, float* const* db_host, float* dx,
+                 void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
+
+/* ---- relation discriminators + domain attention + pooling -------------------------- */
+/* models.py:472-488 (per-relation GRL + MLP), :351-357 (entropy attention), :379-388
+ * (re-weighting), :651-652 (sum over relations).
+ *   feat_rel [M,R,H]; W1_host[i] [H,H], b1_host[i] [H], W2_host[i] [2,H], b2_host[i] [2]
+ *   hidden [R,M,H] (saved), pred_rel [M,R,2], attn [M,R], feat_video [M,H]
+ * use_attn == 0 reproduces use_attn='none' (:647): plain sum, attn = feat_rel[:,:,0].    */
+int ta3n_relattn_fwd(const float* feat_rel, int M, int R, int H, const float* const* W1_host,
+                     const float* const* b1_host, const float* const* W2_host,
+                     const float* const* b2_host, int use_attn, float* hidden, float* pred_rel,
+                     float* attn, float* feat_video, ta3n_stream_t stream);
+size_t ta3n_relattn_bwd_workspace_bytes(int M, int R, int H);
+/* g_feat_video [M,H], g_pred_rel [M,R,2] (may be NULL), g_attn [M,R] (may be NULL)
+ * -> d_feat_rel [M,R,H] and the discriminator gradients; beta = beta[0].                 */
+int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* const* W1_host,
+                     const float* const* W2_host, int use_attn, const float* hidden,
+                     const float* pred_rel, const float* attn, const float* g_feat_video,
+                     const float* g_pred_rel, const float* g_attn, float beta,
+                     float* d_feat_rel, float* const* dW1_host, float* const* db1_host,
+                     float* const* dW2_host, float* const* db2_host, void* workspace,
+                     size_t workspace_bytes, ta3n_stream_t stream);
+
+/* ---- video head: Dropout -> [GRL_mu] -> Linear(H -> C)  (models.py:679-687) -------- */
+/* feat_video [M,H] -> dropped [M,H] (saved; equals feat_video when no dropout),
+ * pred [M,C].                                                                            */
+int ta3n_video_head_fwd(const float* feat_video, int M, int H, int C, const float* Wc,
+                        const float* bc, const ta3n_dropout* drop, float* dropped, float* pred,
+                        ta3n_stream_t stream);
+size_t ta3n_video_head_bwd_workspace_bytes(int M, int H, int C);
+/* g_pred [M,C] (may be NULL), d_dropped_extra [M,H] = gradient already accumulated on the
+ * dropped features by the video discriminator (may be NULL), g_feat_video_ext [M,H] (may be
+ * NULL).  grad_scale multiplies everything that flows through the optional GRL_mu
+ * (reverse ? -mu : 1).  Produces d_feat_video [M,H], dWc [C,H], dbc [C].                 */
+int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* Wc,
+                        const ta3n_dropout* drop, const float* g_pred,
+                        const float* d_dropped_extra, const float* g_feat_video_ext,
+                        float grad_scale, float* d_feat_video, float* dWc, float* dbc,
+                        void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
+
+/* ---- self test of the tensor-core GEMM engine (used by tests; device buffers) ------ */
+/* C[M,N] = A[M,K] * B[N,K]^T with the selected engine; A, B, C row-major fp32.           */
+int ta3n_gemm_tn(const float* A, const float* B, float* C, int M, int N, int K,
+                 ta3n_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TA3N_B200_H_ */

@@ -1,0 +1,124 @@
+"""ctypes binding of libta3n_sm100.so (the C ABI in include/ta3n_b200.h).
+
+There is no CPU fallback: if the shared library is missing this module raises, and every
+wrapper refuses tensors that are not CUDA fp32 contiguous.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+TA3N_GEMM_FP32_SIMT = 0
+TA3N_GEMM_TF32_TCGEN05 = 1
+
+
+class RelationTable(C.Structure):
+    _fields_ = [("num_frames", C.c_int), ("n_scales", C.c_int),
+                ("scale_size", C.POINTER(C.c_int)), ("rel_count", C.POINTER(C.c_int)),
+                ("frames", C.POINTER(C.c_int))]
+
+
+class Dropout(C.Structure):
+    _fields_ = [("p", C.c_float), ("keep", C.c_void_p), ("seed", C.c_uint64), ("step_dev", C.c_void_p)]
+
+
+_VP, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_PP = C.POINTER(C.c_void_p)
+_TAB = C.POINTER(RelationTable)
+_DRP = C.POINTER(Dropout)
+
+# name -> (restype, argtypes); mirrors include/ta3n_b200.h one to one
+SIGNATURES = {
+    "ta3n_abi_version": (_I, []),
+    "ta3n_last_error": (C.c_char_p, []),
+    "ta3n_launch_count": (C.c_uint64, []),
+    "ta3n_reset_launch_count": (None, []),
+    "ta3n_set_gemm_engine": (_I, [_I]),
+    "ta3n_get_gemm_engine": (_I, []),
+    "ta3n_shared_fc_fwd": (_I, [_VP, _I, _VP, _I, _I, _VP, _VP, _I, _DRP, _VP, _VP]),
+    "ta3n_shared_fc_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ta3n_shared_fc_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _VP, _VP, _VP, _F, _VP, _VP, _VP, _SZ, _VP]),
+    "ta3n_disc_fwd": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "ta3n_disc_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ta3n_disc_bwd": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _F, _VP, _I, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "ta3n_grl_bwd": (_I, [_VP, _F, _VP, _SZ, _VP]),
+    "ta3n_frame_attn_fwd": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
+    "ta3n_frame_attn_bwd": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
+    "ta3n_trn_fwd": (_I, [_VP, _I, _I, _I, _TAB, _PP, _PP, _I, _VP, _VP, _VP]),
+    "ta3n_trn_bwd_workspace_bytes": (_SZ, [_I, _I, _I, _TAB]),
+    "ta3n_trn_bwd": (_I, [_VP, _I, _I, _I, _TAB, _PP, _I, _VP, _VP, _PP, _PP, _VP, _VP, _SZ, _VP]),
+    "ta3n_relattn_fwd": (_I, [_VP, _I, _I, _I, _PP, _PP, _PP, _PP, _I, _VP, _VP, _VP, _VP, _VP]),
+    "ta3n_relattn_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ta3n_relattn_bwd": (_I, [_VP, _I, _I, _I, _PP, _PP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP,
+                              _PP, _PP, _PP, _PP, _VP, _SZ, _VP]),
+    "ta3n_video_head_fwd": (_I, [_VP, _I, _I, _I, _VP, _VP, _DRP, _VP, _VP, _VP]),
+    "ta3n_video_head_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ta3n_video_head_bwd": (_I, [_VP, _I, _I, _I, _VP, _DRP, _VP, _VP, _VP, _F, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "ta3n_gemm_tn": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class Ta3nError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            path = lib_path()
+            if not os.path.exists(path):
+                raise Ta3nError(
+                    f"{path} is missing: build it with `python -m ta3n_b200.build` "
+                    "(or __graft_entry__.build()). ta3n_b200 has no CPU / PyTorch fallback.")
+            lib = C.CDLL(path)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)   # AttributeError if the .so does not export the symbol
+                fn.restype = res
+                fn.argtypes = args
+            if lib.ta3n_abi_version() != 1:
+                raise Ta3nError("libta3n_sm100.so ABI version mismatch")
+            _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().ta3n_last_error()
+        raise Ta3nError(f"libta3n_sm100 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    return arr
+
+
+def set_gemm_engine(engine) -> None:
+    """'fp32' (exact SIMT tiles) or 'tf32' (tcgen05 tensor cores)."""
+    code = {"fp32": TA3N_GEMM_FP32_SIMT, "tf32": TA3N_GEMM_TF32_TCGEN05}.get(engine, engine)
+    check(load().ta3n_set_gemm_engine(int(code)))
+
+
+def get_gemm_engine() -> str:
+    return {0: "fp32", 1: "tf32"}[load().ta3n_get_gemm_engine()]
+
+
+def launch_count() -> int:
+    return int(load().ta3n_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().ta3n_reset_launch_count()

@@ -1,0 +1,131 @@
+// common.cuh -- error plumbing, launch accounting and small device helpers shared by every
+// translation unit of libta3n_sm100.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/ta3n_b200.h"
+
+namespace ta3n {
+
+// ---- error state ---------------------------------------------------------------------------
+inline char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define TA3N_REQUIRE(cond, msg)                                                         \
+  do {                                                                                   \
+    if (!(cond)) return ::ta3n::fail(TA3N_ERR_INVALID, "%s: requirement failed: " msg " (line %d)", \
+                                     __func__, (int)__LINE__);                           \
+  } while (0)
+
+#define TA3N_CUDA(expr)                                                                  \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return ::ta3n::fail(TA3N_ERR_CUDA, "CUDA error %s at line %d", cudaGetErrorString(_e), \
+                          (int)__LINE__);                                                \
+  } while (0)
+
+#define TA3N_TRY(expr)                 \
+  do {                                 \
+    int _rc = (expr);                  \
+    if (_rc != TA3N_OK) return _rc;    \
+  } while (0)
+
+// ---- launch accounting (bench.py reports gpu_launches from this) ----------------------------
+inline std::atomic<uint64_t>& launch_counter() {
+  static std::atomic<uint64_t> n{0};
+  return n;
+}
+
+inline int after_launch() {
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();  // launch-configuration errors only; never synchronises
+  if (e != cudaSuccess) return fail(TA3N_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return TA3N_OK;
+}
+
+inline std::atomic<int>& gemm_engine() {
+  static std::atomic<int> e{TA3N_GEMM_FP32_SIMT};
+  return e;
+}
+
+// ---- workspace carving ----------------------------------------------------------------------
+struct Arena {
+  char* base;
+  size_t size;
+  size_t used;
+  Arena(void* p, size_t n) : base(static_cast<char*>(p)), size(n), used(0) {}
+  static size_t round(size_t n) { return (n + 255) & ~size_t(255); }
+  // returns nullptr when exhausted (caller checks via ok())
+  float* floats(size_t n) {
+    size_t bytes = round(n * sizeof(float));
+    if (base == nullptr || used + bytes > size) {
+      used = size + 1;
+      return nullptr;
+    }
+    float* p = reinterpret_cast<float*>(base + used);
+    used += bytes;
+    return p;
+  }
+  bool ok() const { return used <= size; }
+};
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Counter-based keep decision for dropout: a stateless 64-bit mix of (seed, step, element).
+// Recomputable in backward from the same triple, so no mask has to be stored.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ bool rng_keep(uint64_t seed, uint64_t step, uint64_t idx, float p) {
+  uint64_t h = mix64(mix64(seed + 0x9E3779B97F4A7C15ull * (step + 1)) ^ (idx * 0xD6E8FEB86659FD93ull));
+  // top 24 bits -> uniform in [0,1)
+  float u = (float)(h >> 40) * (1.0f / 16777216.0f);
+  return u >= p;
+}
+
+// softmax over two logits -> q0,q1, entropy E and w = 1 - E   (models.py:351-357)
+struct Attn2 {
+  float q0, q1, lq0, lq1, ent, w;
+};
+__device__ __forceinline__ Attn2 attn_from_logits(float p0, float p1) {
+  Attn2 a;
+  float mx = fmaxf(p0, p1);
+  float e0 = expf(p0 - mx), e1 = expf(p1 - mx);
+  float s = e0 + e1;
+  float ls = logf(s);
+  a.lq0 = p0 - mx - ls;
+  a.lq1 = p1 - mx - ls;
+  a.q0 = e0 / s;
+  a.q1 = e1 / s;
+  a.ent = -(a.q0 * a.lq0 + a.q1 * a.lq1);
+  a.w = 1.0f - a.ent;
+  return a;
+}
+
+}  // namespace ta3n

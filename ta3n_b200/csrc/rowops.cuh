@@ -1,0 +1,374 @@
+// rowops.cuh -- the light (HBM-bound) kernels of the path: small heads, entropy attention and
+// pooling, ReLU/dropout masks, bias-gradient column sums.  All fp32, coalesced along the
+// feature dimension; warp-per-row where a row reduction is needed.
+#pragma once
+
+#include "common.cuh"
+
+namespace ta3n {
+
+constexpr int kMaxScales = 32;   // R = T-1 <= 32
+constexpr int kMaxRel = 96;      // relations evaluated (1 + 3*(R-1)) <= 96
+
+struct PtrTable {
+  const float* p[kMaxScales];
+};
+struct MutPtrTable {
+  float* p[kMaxScales];
+};
+struct RelMap {
+  int n_rel;
+  int n_scales;
+  int rel_begin[kMaxScales + 1];   // relations of scale i are [rel_begin[i], rel_begin[i+1])
+  unsigned char scale_of[kMaxRel];
+};
+
+inline unsigned blocks_for(size_t n, int threads) {
+  size_t b = (n + threads - 1) / threads;
+  if (b > 148u * 32u) b = 148u * 32u;   // grid-stride beyond 32 CTAs per SM
+  if (b == 0) b = 1;
+  return (unsigned)b;
+}
+
+// ---- feat_rel[m,i,:] = sum_r act[q(i,r)][m,:]                              TRNmodule.py:79 ----
+__global__ void __launch_bounds__(256) relsum_kernel(const float* __restrict__ act, float* __restrict__ feat_rel,
+                                                     int M, int H, const __grid_constant__ RelMap map) {
+  const int R = map.n_scales;
+  const size_t total = (size_t)M * R * H;
+  const size_t plane = (size_t)M * H;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int h = (int)(e % H);
+    const size_t mi = e / H;
+    const int i = (int)(mi % R);
+    const size_t m = mi / R;
+    float s = 0.f;
+    for (int q = map.rel_begin[i]; q < map.rel_begin[i + 1]; ++q) s += act[q * plane + m * H + h];
+    feat_rel[e] = s;
+  }
+}
+
+// ---- dZ[q][m,h] = d_feat_rel[m,i(q),h] * 1[act[q][m,h] > 0] ------------------------------------
+__global__ void __launch_bounds__(256) dz_kernel(const float* __restrict__ act, const float* __restrict__ d_feat_rel,
+                                                 float* __restrict__ dz, int M, int H,
+                                                 const __grid_constant__ RelMap map) {
+  const int R = map.n_scales;
+  const size_t plane = (size_t)M * H;
+  const size_t total = plane * map.n_rel;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(e / plane);
+    const size_t mh = e % plane;
+    const size_t m = mh / H;
+    const int h = (int)(mh % H);
+    const int i = map.scale_of[q];
+    dz[e] = act[e] > 0.f ? d_feat_rel[(m * R + i) * H + h] : 0.f;
+  }
+}
+
+// ---- small head: out[row, n] = <x[row,:], W[n,:]> + b[n], n < N2 (warp per row) -----------------
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ x, int ldx,
+                                                       const float* __restrict__ W, const float* __restrict__ b,
+                                                       float* __restrict__ out, int ldo, int rows, int K, int N2) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
+    const float* xr = x + (size_t)row * ldx;
+    for (int n = 0; n < N2; ++n) {
+      const float* wr = W + (size_t)n * K;
+      float s = 0.f;
+      for (int k = lane; k < K; k += 32) s = fmaf(xr[k], __ldg(wr + k), s);
+      s = warp_sum(s);
+      if (lane == 0) out[(size_t)row * ldo + n] = s + (b ? b[n] : 0.f);
+    }
+  }
+}
+
+// ---- out[row,k] = alpha * (sum_n g[row,n] W[n,k]) * 1[gate[row,k] > 0]  (+ out if accumulate) ----
+__global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restrict__ g, int N2,
+                                                            const float* __restrict__ W,
+                                                            const float* __restrict__ gate, float alpha,
+                                                            int accumulate, float* __restrict__ out, int rows, int K) {
+  const size_t total = (size_t)rows * K;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = e / K;
+    const int k = (int)(e % K);
+    float s = 0.f;
+    for (int n = 0; n < N2; ++n) s = fmaf(g[row * N2 + n], __ldg(W + (size_t)n * K + k), s);
+    s *= alpha;
+    if (gate && !(gate[e] > 0.f)) s = 0.f;
+    out[e] = accumulate ? out[e] + s : s;
+  }
+}
+
+// ---- relation heads + entropy attention + attentive pooling (warp per video) -------------------
+// models.py:479 (second Linear of each relation discriminator), :351-357, :379-388, :651-652
+__global__ void __launch_bounds__(256)
+relattn_fwd_kernel(const float* __restrict__ feat_rel, const float* __restrict__ hidden, int M, int R, int H,
+                   const __grid_constant__ PtrTable W2, const __grid_constant__ PtrTable b2, int use_attn,
+                   float* __restrict__ pred_rel, float* __restrict__ attn, float* __restrict__ feat_video) {
+  __shared__ float wsh[8][kMaxScales];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int m = blockIdx.x * warps_per_block + wib; m < M; m += gridDim.x * warps_per_block) {
+    for (int i = 0; i < R; ++i) {
+      const float* hr = hidden + ((size_t)i * M + m) * H;
+      const float* w0 = W2.p[i];
+      const float* w1 = w0 + H;
+      float s0 = 0.f, s1 = 0.f;
+      for (int h = lane; h < H; h += 32) {
+        float hv = hr[h];
+        s0 = fmaf(hv, __ldg(w0 + h), s0);
+        s1 = fmaf(hv, __ldg(w1 + h), s1);
+      }
+      s0 = warp_sum(s0) + b2.p[i][0];
+      s1 = warp_sum(s1) + b2.p[i][1];
+      float w;
+      if (use_attn) {
+        w = attn_from_logits(s0, s1).w;
+      } else {
+        w = 0.f;   // plain sum:  (w + 1) == 1
+      }
+      if (lane == 0) {
+        pred_rel[((size_t)m * R + i) * 2 + 0] = s0;
+        pred_rel[((size_t)m * R + i) * 2 + 1] = s1;
+        attn[(size_t)m * R + i] = use_attn ? w : feat_rel[((size_t)m * R + i) * H];   // :647 placeholder
+        wsh[wib][i] = w + 1.0f;
+      }
+    }
+    __syncwarp();
+    for (int h = lane; h < H; h += 32) {
+      float y = 0.f;
+      for (int i = 0; i < R; ++i) y = fmaf(wsh[wib][i], feat_rel[((size_t)m * R + i) * H + h], y);
+      feat_video[(size_t)m * H + h] = y;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- backward of the above up to the hidden layer (warp per video) -----------------------------
+//   dw_i   = <G[m], feat_rel[m,i]> + g_attn[m,i]
+//   Pt_ik  = g_pred[m,i,k] + dw_i * q_ik (log q_ik + E_i)
+//   dHid_i = (Pt_i0 W2_i[0,:] + Pt_i1 W2_i[1,:]) * 1[hidden_i > 0]
+__global__ void __launch_bounds__(256)
+relattn_bwd_pre_kernel(const float* __restrict__ feat_rel, const float* __restrict__ hidden,
+                       const float* __restrict__ pred_rel, const float* __restrict__ G,
+                       const float* __restrict__ g_pred, const float* __restrict__ g_attn, int M, int R, int H,
+                       const __grid_constant__ PtrTable W2, int use_attn, float* __restrict__ Pt,
+                       float* __restrict__ d_hidden) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int m = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M; m += gridDim.x * warps_per_block) {
+    for (int i = 0; i < R; ++i) {
+      float pt0 = g_pred ? g_pred[((size_t)m * R + i) * 2 + 0] : 0.f;
+      float pt1 = g_pred ? g_pred[((size_t)m * R + i) * 2 + 1] : 0.f;
+      if (use_attn) {
+        const float* fr = feat_rel + ((size_t)m * R + i) * H;
+        const float* gr = G + (size_t)m * H;
+        float dw = 0.f;
+        for (int h = lane; h < H; h += 32) dw = fmaf(gr[h], fr[h], dw);
+        dw = warp_sum(dw);
+        if (g_attn) dw += g_attn[(size_t)m * R + i];
+        Attn2 a = attn_from_logits(pred_rel[((size_t)m * R + i) * 2 + 0], pred_rel[((size_t)m * R + i) * 2 + 1]);
+        pt0 += dw * a.q0 * (a.lq0 + a.ent);
+        pt1 += dw * a.q1 * (a.lq1 + a.ent);
+      }
+      if (lane == 0) {
+        Pt[((size_t)m * R + i) * 2 + 0] = pt0;
+        Pt[((size_t)m * R + i) * 2 + 1] = pt1;
+      }
+      const float* w0 = W2.p[i];
+      const float* w1 = w0 + H;
+      const float* hr = hidden + ((size_t)i * M + m) * H;
+      float* dh = d_hidden + ((size_t)i * M + m) * H;
+      for (int h = lane; h < H; h += 32)
+        dh[h] = hr[h] > 0.f ? fmaf(pt0, __ldg(w0 + h), pt1 * __ldg(w1 + h)) : 0.f;
+    }
+  }
+}
+
+// d_feat_rel[m,i,0] += g_attn[m,i]   (use_attn='none' placeholder output, models.py:647)
+__global__ void attn_placeholder_bwd_kernel(const float* __restrict__ g_attn, float* __restrict__ d_feat_rel,
+                                            int M, int R, int H) {
+  const int total = M * R;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x)
+    d_feat_rel[(size_t)e * H] += g_attn[e];
+}
+
+// ---- frame-level attention                                         models.py:368-377 ----------
+__global__ void __launch_bounds__(256) frame_attn_fwd_kernel(const float* __restrict__ feat,
+                                                             const float* __restrict__ logits, int rows, int F,
+                                                             float* __restrict__ out) {
+  const size_t total = (size_t)rows * F;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = e / F;
+    const float w = attn_from_logits(logits[row * 2], logits[row * 2 + 1]).w;
+    out[e] = (w + 1.0f) * feat[e];
+  }
+}
+
+// warp per row: dw = <d_out, feat>; d_out *= (w+1); g_logits += dw * dw/dlogits
+__global__ void __launch_bounds__(256) frame_attn_bwd_kernel(const float* __restrict__ feat,
+                                                             const float* __restrict__ logits, int rows, int F,
+                                                             float* __restrict__ d_out, float* __restrict__ g_logits) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
+    const float* fr = feat + (size_t)row * F;
+    float* dr = d_out + (size_t)row * F;
+    const Attn2 a = attn_from_logits(logits[(size_t)row * 2], logits[(size_t)row * 2 + 1]);
+    float dw = 0.f;
+    for (int k = lane; k < F; k += 32) dw = fmaf(dr[k], fr[k], dw);
+    dw = warp_sum(dw);
+    const float sc = a.w + 1.0f;
+    for (int k = lane; k < F; k += 32) dr[k] *= sc;
+    if (lane == 0) {
+      g_logits[(size_t)row * 2 + 0] += dw * a.q0 * (a.lq0 + a.ent);
+      g_logits[(size_t)row * 2 + 1] += dw * a.q1 * (a.lq1 + a.ent);
+    }
+  }
+}
+
+// ---- dropout helpers -----------------------------------------------------------------------------
+struct DropArgs {
+  float p, scale;
+  const uint8_t* keep;
+  uint64_t seed;
+  const uint64_t* step_dev;
+  int mode;   // 0 none, 1 mask, 2 rng
+};
+inline DropArgs make_drop(const ta3n_dropout* d) {
+  DropArgs a;
+  memset(&a, 0, sizeof(a));
+  a.scale = 1.0f;
+  if (d && d->p > 0.0f) {
+    a.p = d->p;
+    a.scale = 1.0f / (1.0f - d->p);
+    a.keep = d->keep;
+    a.seed = d->seed;
+    a.step_dev = d->step_dev;
+    a.mode = d->keep ? 1 : 2;
+  }
+  return a;
+}
+__device__ __forceinline__ float drop_factor(const DropArgs& a, size_t e) {
+  if (a.mode == 0) return 1.0f;
+  bool k = (a.mode == 1) ? (a.keep[e] != 0) : rng_keep(a.seed, a.step_dev ? *a.step_dev : 0ull, e, a.p);
+  return k ? a.scale : 0.0f;
+}
+
+// dropped = y * keep / (1-p)                                               models.py:679-680
+__global__ void __launch_bounds__(256) video_drop_fwd_kernel(const float* __restrict__ y, float* __restrict__ out,
+                                                             size_t total, const DropArgs a) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
+    out[e] = y[e] * drop_factor(a, e);
+}
+
+// d_feat_video = ((g_pred Wc) + extra) * grad_scale * keep/(1-p) + g_ext
+__global__ void __launch_bounds__(256)
+video_head_bwd_kernel(const float* __restrict__ g_pred, int C, const float* __restrict__ Wc,
+                      const float* __restrict__ extra, const float* __restrict__ g_ext, float grad_scale,
+                      const DropArgs a, float* __restrict__ out, int M, int H) {
+  const size_t total = (size_t)M * H;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = e / H;
+    const int h = (int)(e % H);
+    float s = extra ? extra[e] : 0.f;
+    if (g_pred)
+      for (int c = 0; c < C; ++c) s = fmaf(g_pred[m * C + c], __ldg(Wc + (size_t)c * H + h), s);
+    s *= grad_scale * drop_factor(a, e);
+    if (g_ext) s += g_ext[e];
+    out[e] = s;
+  }
+}
+
+// d_pre = (d_feat + g_ext) * 1[feat > 0] * scale   (ReLU + dropout backward; feat>0 <=> kept & pre>0)
+__global__ void __launch_bounds__(256) dpre_kernel(const float* __restrict__ feat, float* __restrict__ d_feat,
+                                                   const float* __restrict__ g_ext, float scale, size_t total) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    float g = d_feat[e] + (g_ext ? g_ext[e] : 0.f);
+    d_feat[e] = feat[e] > 0.f ? g * scale : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) grl_bwd_kernel(const float* __restrict__ g, float beta, float* __restrict__ out,
+                                                      size_t n) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+    out[e] = -beta * g[e];
+}
+
+// ---- deterministic column sums (bias gradients) ------------------------------------------------
+struct ColsumJob {
+  const float* X[4];
+  int rows[4];
+  int nseg;
+  int ld;
+  int N;
+  float* out;
+};
+constexpr int kMaxColsumJobs = 40;
+struct ColsumTable {
+  int n_jobs;
+  ColsumJob job[kMaxColsumJobs];
+};
+
+// block = 32 columns x 32 row-stripes; grid = (ceil(maxN/32), n_jobs)
+__global__ void __launch_bounds__(1024) colsum_kernel(const __grid_constant__ ColsumTable tab) {
+  __shared__ float red[32][33];
+  const ColsumJob& j = tab.job[blockIdx.y];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  if (blockIdx.x * 32 >= j.N) return;
+  float s = 0.f;
+  if (n < j.N) {
+    for (int sg = 0; sg < j.nseg; ++sg) {
+      const float* X = j.X[sg];
+      for (int r = threadIdx.y; r < j.rows[sg]; r += 32) s += X[(size_t)r * j.ld + n];
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < j.N) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) t += red[y][threadIdx.x];
+    j.out[n] = t;
+  }
+}
+
+struct ColsumPlan {
+  std::vector<ColsumJob> jobs;
+  ColsumJob& add(float* out, int N, int ld) {
+    ColsumJob j;
+    memset(&j, 0, sizeof(j));
+    j.out = out;
+    j.N = N;
+    j.ld = ld;
+    jobs.push_back(j);
+    return jobs.back();
+  }
+  void seg(const float* X, int rows) {
+    ColsumJob& j = jobs.back();
+    if (rows <= 0) return;
+    j.X[j.nseg] = X;
+    j.rows[j.nseg] = rows;
+    j.nseg++;
+  }
+  int run(cudaStream_t stream) {
+    size_t i = 0;
+    while (i < jobs.size()) {
+      ColsumTable tab;
+      tab.n_jobs = 0;
+      int maxN = 0;
+      while (i < jobs.size() && tab.n_jobs < kMaxColsumJobs) {
+        tab.job[tab.n_jobs++] = jobs[i];
+        if (jobs[i].N > maxN) maxN = jobs[i].N;
+        ++i;
+      }
+      if (maxN == 0) continue;
+      dim3 grid((maxN + 31) / 32, tab.n_jobs), block(32, 32);
+      colsum_kernel<<<grid, block, 0, stream>>>(tab);
+      TA3N_TRY(after_launch());
+    }
+    return TA3N_OK;
+  }
+};
+
+}  // namespace ta3n

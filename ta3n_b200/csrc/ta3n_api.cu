@@ -1,0 +1,577 @@
+// ta3n_api.cu -- extern "C" entry points of libta3n_sm100.so (see include/ta3n_b200.h).
+// Every function only builds launch tables on the host and enqueues kernels on the caller's
+// stream: no allocation, no synchronisation, CUDA-graph capturable.
+#include "common.cuh"
+#include "seg_gemm.cuh"
+#include "rowops.cuh"
+#include "gemm_tcgen05.cuh"
+
+using namespace ta3n;
+
+namespace {
+
+struct RelLayout {
+  int T, R, n_rel, n_slots;
+  std::vector<int> scale_size, rel_count, rel_begin;   // per scale
+  std::vector<int> rel_scale;                          // per relation q
+  std::vector<int> slot_begin;                         // per relation q: offset into frames
+  const int* frames;
+};
+
+int parse_table(const ta3n_relation_table* tab, RelLayout* L) {
+  TA3N_REQUIRE(tab != nullptr, "relation table is null");
+  TA3N_REQUIRE(tab->num_frames >= 2 && tab->n_scales >= 1 && tab->n_scales <= kMaxScales, "bad table sizes");
+  TA3N_REQUIRE(tab->scale_size && tab->rel_count && tab->frames, "relation table arrays are null");
+  L->T = tab->num_frames;
+  L->R = tab->n_scales;
+  L->frames = tab->frames;
+  L->n_rel = 0;
+  L->n_slots = 0;
+  for (int i = 0; i < L->R; ++i) {
+    const int s = tab->scale_size[i], n = tab->rel_count[i];
+    TA3N_REQUIRE(s >= 1 && s <= L->T && n >= 1, "bad scale entry");
+    L->scale_size.push_back(s);
+    L->rel_count.push_back(n);
+    L->rel_begin.push_back(L->n_rel);
+    for (int r = 0; r < n; ++r) {
+      L->rel_scale.push_back(i);
+      L->slot_begin.push_back(L->n_slots);
+      for (int j = 0; j < s; ++j) {
+        const int t = tab->frames[L->n_slots + j];
+        TA3N_REQUIRE(t >= 0 && t < L->T, "frame id out of range");
+      }
+      L->n_slots += s;
+    }
+    L->n_rel += n;
+  }
+  L->rel_begin.push_back(L->n_rel);
+  TA3N_REQUIRE(L->n_rel <= kMaxRel, "too many relations");
+  return TA3N_OK;
+}
+
+RelMap make_relmap(const RelLayout& L) {
+  RelMap m;
+  memset(&m, 0, sizeof(m));
+  m.n_rel = L.n_rel;
+  m.n_scales = L.R;
+  for (int i = 0; i <= L.R; ++i) m.rel_begin[i] = L.rel_begin[i];
+  for (int q = 0; q < L.n_rel; ++q) m.scale_of[q] = (unsigned char)L.rel_scale[q];
+  return m;
+}
+
+void set_dropout_epilogue(Group& g, const DropArgs& d, const uint8_t* keep, int ldkeep, uint64_t rng_offset) {
+  if (d.mode == 0) return;
+  g.drop_scale = d.scale;
+  g.drop_p = d.p;
+  if (d.mode == 1) {
+    g.flags |= EPI_DROP_MASK;
+    g.keep = keep;
+    g.ldkeep = ldkeep;
+  } else {
+    g.flags |= EPI_DROP_RNG;
+    g.seed = d.seed;
+    g.step_dev = d.step_dev;
+    g.rng_offset = rng_offset;
+  }
+}
+
+inline cudaStream_t S(ta3n_stream_t s) { return static_cast<cudaStream_t>(s); }
+
+// Upper bound of the split-K partial buffers plan_splitk() may carve for `n_groups` outputs:
+// sum_g ksplit_g * M_g * N_g <= (target_ctas + tiles) * 64*64 <= 2 * 296 * 4096 floats.
+inline size_t splitk_bytes(int n_groups) {
+  return (size_t)2 * 296 * 4096 * sizeof(float) + (size_t)256 * (n_groups + 1) + 4096;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ta3n_abi_version(void) { return TA3N_ABI_VERSION; }
+const char* ta3n_last_error(void) { return last_error_buf(); }
+uint64_t ta3n_launch_count(void) { return launch_counter().load(); }
+void ta3n_reset_launch_count(void) { launch_counter().store(0); }
+int ta3n_set_gemm_engine(int engine) {
+  if (engine != TA3N_GEMM_FP32_SIMT && engine != TA3N_GEMM_TF32_TCGEN05)
+    return fail(TA3N_ERR_INVALID, "unknown GEMM engine %d", engine);
+  gemm_engine().store(engine);
+  return TA3N_OK;
+}
+int ta3n_get_gemm_engine(void) { return gemm_engine().load(); }
+
+// ------------------------------------------------------------------------------------------------
+// shared frame layer                                                        models.py:565-575
+// ------------------------------------------------------------------------------------------------
+int ta3n_shared_fc_fwd(const float* x_src, int rows_src, const float* x_tgt, int rows_tgt, int D,
+                       const float* W, const float* b, int F, const ta3n_dropout* drop, float* feat,
+                       ta3n_stream_t stream) {
+  TA3N_REQUIRE(rows_src >= 0 && rows_tgt >= 0 && D > 0 && F > 0, "bad sizes");
+  TA3N_REQUIRE(W && b && feat, "null pointer");
+  TA3N_REQUIRE((rows_src == 0 || x_src) && (rows_tgt == 0 || x_tgt), "null input");
+  const DropArgs d = make_drop(drop);
+  GemmPlan plan;
+  const float* xs[2] = {x_src, x_tgt};
+  const int rows[2] = {rows_src, rows_tgt};
+  size_t row0 = 0;
+  for (int dom = 0; dom < 2; ++dom) {
+    if (rows[dom] > 0) {
+      Group& g = plan.add_group(rows[dom], F, feat + row0 * F, F);
+      g.flags = EPI_BIAS | EPI_RELU;
+      g.bias = b;
+      set_dropout_epilogue(g, d, d.keep ? d.keep + row0 * F : nullptr, F, row0 * F);
+      plan.add_seg(xs[dom], D, W, D, D);
+    }
+    row0 += rows[dom];
+  }
+  return run_gemm(plan, S(stream));
+}
+
+size_t ta3n_shared_fc_bwd_workspace_bytes(int rows, int D, int F) {
+  (void)rows; (void)D; (void)F;
+  return splitk_bytes(1);
+}
+
+int ta3n_shared_fc_bwd(const float* x_src, int rows_src, const float* x_tgt, int rows_tgt, int D, int F,
+                       const float* feat, float* dfeat, const float* g_feat_ext, float p, float* dW,
+                       float* db, void* workspace, size_t workspace_bytes, ta3n_stream_t stream) {
+  TA3N_REQUIRE(rows_src >= 0 && rows_tgt >= 0 && D > 0 && F > 0, "bad sizes");
+  TA3N_REQUIRE(feat && dfeat && dW && db, "null pointer");
+  TA3N_REQUIRE(p >= 0.f && p < 1.f, "dropout p must be in [0,1)");
+  const int rows = rows_src + rows_tgt;
+  if (rows == 0) {
+    TA3N_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * F * D, S(stream)));
+    TA3N_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * F, S(stream)));
+    return TA3N_OK;
+  }
+  const size_t total = (size_t)rows * F;
+  dpre_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(feat, dfeat, g_feat_ext, 1.0f / (1.0f - p), total);
+  TA3N_TRY(after_launch());
+
+  Arena arena(workspace, workspace_bytes);
+  GemmPlan plan;
+  plan.a_kmaj = false;
+  plan.b_kmaj = false;
+  plan.add_group(F, D, dW, D);
+  if (rows_src > 0) plan.add_seg(dfeat, F, x_src, D, rows_src);
+  if (rows_tgt > 0) plan.add_seg(dfeat + (size_t)rows_src * F, F, x_tgt, D, rows_tgt);
+  TA3N_TRY(run_gemm(plan, S(stream), &arena));
+
+  ColsumPlan cs;
+  cs.add(db, F, F);
+  cs.seg(dfeat, rows);
+  return cs.run(S(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// GradReverse + two-layer discriminator                        models.py:456-470, 20-29
+// ------------------------------------------------------------------------------------------------
+int ta3n_disc_fwd(const float* x, int rows, int K, int Kh, const float* W1, const float* b1, const float* W2,
+                  const float* b2, float* hidden, float* logits, ta3n_stream_t stream) {
+  TA3N_REQUIRE(rows >= 0 && K > 0 && Kh > 0, "bad sizes");
+  if (rows == 0) return TA3N_OK;
+  TA3N_REQUIRE(x && W1 && b1 && W2 && b2 && hidden && logits, "null pointer");
+  GemmPlan plan;
+  Group& g = plan.add_group(rows, Kh, hidden, Kh);
+  g.flags = EPI_BIAS | EPI_RELU;
+  g.bias = b1;
+  plan.add_seg(x, K, W1, K, K);
+  TA3N_TRY(run_gemm(plan, S(stream)));
+  head_fwd_kernel<<<blocks_for((size_t)rows * 32, 256), 256, 0, S(stream)>>>(hidden, Kh, W2, b2, logits, 2, rows,
+                                                                             Kh, 2);
+  return after_launch();
+}
+
+size_t ta3n_disc_bwd_workspace_bytes(int rows, int K, int Kh) {
+  (void)K;
+  return Arena::round((size_t)rows * Kh * sizeof(float)) + splitk_bytes(2);
+}
+
+int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, const float* W2,
+                  const float* hidden, const float* g_logits, float beta, float* dx, int accumulate,
+                  float* dW1, float* db1, float* dW2, float* db2, void* workspace, size_t workspace_bytes,
+                  ta3n_stream_t stream) {
+  TA3N_REQUIRE(rows >= 0 && K > 0 && Kh > 0, "bad sizes");
+  TA3N_REQUIRE(dW1 && db1 && dW2 && db2, "null gradient pointer");
+  cudaStream_t st = S(stream);
+  if (rows == 0 || g_logits == nullptr) {
+    TA3N_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * Kh * K, st));
+    TA3N_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * Kh, st));
+    TA3N_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * 2 * Kh, st));
+    TA3N_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * 2, st));
+    if (dx && !accumulate && rows > 0) TA3N_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * rows * K, st));
+    return TA3N_OK;
+  }
+  TA3N_REQUIRE(x && W1 && W2 && hidden, "null pointer");
+  Arena arena(workspace, workspace_bytes);
+  float* dH = arena.floats((size_t)rows * Kh);
+  if (!dH) return fail(TA3N_ERR_WORKSPACE, "ta3n_disc_bwd: workspace too small (%zu bytes)", workspace_bytes);
+
+  // dH = (g_logits W2) * 1[hidden > 0]
+  head_bwd_data_kernel<<<blocks_for((size_t)rows * Kh, 256), 256, 0, st>>>(g_logits, 2, W2, hidden, 1.0f, 0, dH,
+                                                                           rows, Kh);
+  TA3N_TRY(after_launch());
+
+  {  // dW2 [2,Kh] = g_logits^T hidden ; dW1 [Kh,K] = dH^T x
+    GemmPlan plan;
+    plan.a_kmaj = false;
+    plan.b_kmaj = false;
+    plan.add_group(2, Kh, dW2, Kh);
+    plan.add_seg(g_logits, 2, hidden, Kh, rows);
+    plan.add_group(Kh, K, dW1, K);
+    plan.add_seg(dH, Kh, x, K, rows);
+    TA3N_TRY(run_gemm(plan, st, &arena));
+  }
+  {
+    ColsumPlan cs;
+    cs.add(db2, 2, 2);
+    cs.seg(g_logits, rows);
+    cs.add(db1, Kh, Kh);
+    cs.seg(dH, rows);
+    TA3N_TRY(cs.run(st));
+  }
+  if (dx) {  // dx (+)= -beta * dH W1
+    GemmPlan plan;
+    plan.a_kmaj = true;
+    plan.b_kmaj = false;
+    Group& g = plan.add_group(rows, K, dx, K);
+    g.alpha = -beta;
+    if (accumulate) g.flags |= EPI_ACCUM;
+    plan.add_seg(dH, Kh, W1, K, Kh);
+    TA3N_TRY(run_gemm(plan, st));
+  }
+  return TA3N_OK;
+}
+
+int ta3n_grl_bwd(const float* g, float beta, float* out, size_t n, ta3n_stream_t stream) {
+  if (n == 0) return TA3N_OK;
+  TA3N_REQUIRE(g && out, "null pointer");
+  grl_bwd_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(g, beta, out, n);
+  return after_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame-level attention                                                    models.py:368-377
+// ------------------------------------------------------------------------------------------------
+int ta3n_frame_attn_fwd(const float* feat, const float* logits, int rows, int F, float* out,
+                        ta3n_stream_t stream) {
+  TA3N_REQUIRE(rows >= 0 && F > 0, "bad sizes");
+  if (rows == 0) return TA3N_OK;
+  TA3N_REQUIRE(feat && logits && out, "null pointer");
+  frame_attn_fwd_kernel<<<blocks_for((size_t)rows * F, 256), 256, 0, S(stream)>>>(feat, logits, rows, F, out);
+  return after_launch();
+}
+
+int ta3n_frame_attn_bwd(const float* feat, const float* logits, int rows, int F, float* d_out, float* g_logits,
+                        ta3n_stream_t stream) {
+  TA3N_REQUIRE(rows >= 0 && F > 0, "bad sizes");
+  if (rows == 0) return TA3N_OK;
+  TA3N_REQUIRE(feat && logits && d_out && g_logits, "null pointer");
+  frame_attn_bwd_kernel<<<blocks_for((size_t)rows * 32, 256), 256, 0, S(stream)>>>(feat, logits, rows, F, d_out,
+                                                                                   g_logits);
+  return after_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-scale temporal relation module                                   TRNmodule.py:58-82
+// ------------------------------------------------------------------------------------------------
+int ta3n_trn_fwd(const float* x, int M, int F, int H, const ta3n_relation_table* tab,
+                 const float* const* W_host, const float* const* b_host, int relu_input, float* act,
+                 float* feat_rel, ta3n_stream_t stream) {
+  RelLayout L;
+  TA3N_TRY(parse_table(tab, &L));
+  TA3N_REQUIRE(M >= 0 && F > 0 && H > 0, "bad sizes");
+  if (M == 0) return TA3N_OK;
+  TA3N_REQUIRE(x && W_host && b_host && act && feat_rel, "null pointer");
+  const int ldx = L.T * F;
+  GemmPlan plan;
+  plan.load_flags = relu_input ? LD_RELU_A : 0;
+  for (int q = 0; q < L.n_rel; ++q) {
+    const int i = L.rel_scale[q], s = L.scale_size[i];
+    TA3N_REQUIRE(W_host[i] && b_host[i], "null weight pointer");
+    Group& g = plan.add_group(M, H, act + (size_t)q * M * H, H);
+    g.flags = EPI_BIAS | EPI_RELU;
+    g.bias = b_host[i];
+    for (int j = 0; j < s; ++j) {
+      const int t = L.frames[L.slot_begin[q] + j];
+      plan.add_seg(x + (size_t)t * F, ldx, W_host[i] + (size_t)j * F, s * F, F);
+    }
+  }
+  TA3N_TRY(run_gemm(plan, S(stream)));
+  const RelMap map = make_relmap(L);
+  relsum_kernel<<<blocks_for((size_t)M * L.R * H, 256), 256, 0, S(stream)>>>(act, feat_rel, M, H, map);
+  return after_launch();
+}
+
+size_t ta3n_trn_bwd_workspace_bytes(int M, int F, int H, const ta3n_relation_table* tab) {
+  RelLayout L;
+  if (parse_table(tab, &L) != TA3N_OK) return 0;
+  (void)F;
+  return Arena::round((size_t)L.n_rel * M * H * sizeof(float)) + splitk_bytes(L.n_slots);
+}
+
+int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table* tab,
+                 const float* const* W_host, int relu_input, const float* act, const float* d_feat_rel,
+                 float* const* dW_host, float* const* db_host, float* dx, void* workspace,
+                 size_t workspace_bytes, ta3n_stream_t stream) {
+  RelLayout L;
+  TA3N_TRY(parse_table(tab, &L));
+  TA3N_REQUIRE(M >= 0 && F > 0 && H > 0, "bad sizes");
+  TA3N_REQUIRE(dW_host && db_host, "null gradient tables");
+  cudaStream_t st = S(stream);
+  if (M == 0) {
+    for (int i = 0; i < L.R; ++i) {
+      TA3N_CUDA(cudaMemsetAsync(dW_host[i], 0, sizeof(float) * H * L.scale_size[i] * F, st));
+      TA3N_CUDA(cudaMemsetAsync(db_host[i], 0, sizeof(float) * H, st));
+    }
+    return TA3N_OK;
+  }
+  TA3N_REQUIRE(x && W_host && act && d_feat_rel, "null pointer");
+  const int ldx = L.T * F;
+  const size_t plane = (size_t)M * H;
+  Arena arena(workspace, workspace_bytes);
+  float* dz = arena.floats(plane * L.n_rel);
+  if (!dz) return fail(TA3N_ERR_WORKSPACE, "ta3n_trn_bwd: workspace too small (%zu bytes)", workspace_bytes);
+
+  const RelMap map = make_relmap(L);
+  dz_kernel<<<blocks_for(plane * L.n_rel, 256), 256, 0, st>>>(act, d_feat_rel, dz, M, H, map);
+  TA3N_TRY(after_launch());
+
+  {  // wgrad: dW_i[:, jF:(j+1)F] = sum_r dz_{i,r}^T x[:, tau_{i,r}[j], :]
+    GemmPlan plan;
+    plan.a_kmaj = false;
+    plan.b_kmaj = false;
+    plan.load_flags = relu_input ? LD_RELU_B : 0;
+    for (int i = 0; i < L.R; ++i) {
+      const int s = L.scale_size[i];
+      TA3N_REQUIRE(dW_host[i] && db_host[i], "null gradient pointer");
+      for (int j = 0; j < s; ++j) {
+        plan.add_group(H, F, dW_host[i] + (size_t)j * F, s * F);
+        for (int q = L.rel_begin[i]; q < L.rel_begin[i + 1]; ++q) {
+          const int t = L.frames[L.slot_begin[q] + j];
+          plan.add_seg(dz + q * plane, H, x + (size_t)t * F, ldx, M);
+        }
+      }
+    }
+    TA3N_TRY(run_gemm(plan, st, &arena));
+  }
+  {  // db_i = sum_r colsum(dz_{i,r})
+    ColsumPlan cs;
+    for (int i = 0; i < L.R; ++i) {
+      cs.add(db_host[i], H, H);
+      for (int q = L.rel_begin[i]; q < L.rel_begin[i + 1]; ++q) cs.seg(dz + q * plane, M);
+    }
+    TA3N_TRY(cs.run(st));
+  }
+  if (dx) {  // dgrad, deterministic per frame: dx[:, t, :] = sum_{(q,j): tau_q[j]=t} dz_q W_i[:, jF:(j+1)F]
+    GemmPlan plan;
+    plan.a_kmaj = true;
+    plan.b_kmaj = false;
+    std::vector<int> untouched;
+    for (int t = 0; t < L.T; ++t) {
+      bool any = false;
+      for (int q = 0; q < L.n_rel && !any; ++q)
+        for (int j = 0; j < L.scale_size[L.rel_scale[q]]; ++j)
+          if (L.frames[L.slot_begin[q] + j] == t) any = true;
+      if (!any) {
+        untouched.push_back(t);
+        continue;
+      }
+      Group& g = plan.add_group(M, F, dx + (size_t)t * F, ldx);
+      if (relu_input) {
+        g.flags |= EPI_GATE;
+        g.gate = x + (size_t)t * F;
+        g.ldgate = ldx;
+      }
+      for (int q = 0; q < L.n_rel; ++q) {
+        const int i = L.rel_scale[q], s = L.scale_size[i];
+        for (int j = 0; j < s; ++j)
+          if (L.frames[L.slot_begin[q] + j] == t) plan.add_seg(dz + q * plane, H, W_host[i] + (size_t)j * F, s * F, H);
+      }
+    }
+    for (int t : untouched)   // frames no relation reads get a zero gradient
+      TA3N_CUDA(cudaMemset2DAsync(dx + (size_t)t * F, sizeof(float) * ldx, 0, sizeof(float) * F, M, st));
+    TA3N_TRY(run_gemm(plan, st));
+  }
+  return TA3N_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// relation discriminators + attention + pooling      models.py:472-488, 351-357, 379-388, 651-652
+// ------------------------------------------------------------------------------------------------
+int ta3n_relattn_fwd(const float* feat_rel, int M, int R, int H, const float* const* W1_host,
+                     const float* const* b1_host, const float* const* W2_host, const float* const* b2_host,
+                     int use_attn, float* hidden, float* pred_rel, float* attn, float* feat_video,
+                     ta3n_stream_t stream) {
+  TA3N_REQUIRE(M >= 0 && R >= 1 && R <= kMaxScales && H > 0, "bad sizes");
+  if (M == 0) return TA3N_OK;
+  TA3N_REQUIRE(feat_rel && W1_host && b1_host && W2_host && b2_host && hidden && pred_rel && attn && feat_video,
+               "null pointer");
+  GemmPlan plan;
+  PtrTable w2, b2;
+  memset(&w2, 0, sizeof(w2));
+  memset(&b2, 0, sizeof(b2));
+  for (int i = 0; i < R; ++i) {
+    TA3N_REQUIRE(W1_host[i] && b1_host[i] && W2_host[i] && b2_host[i], "null weight pointer");
+    Group& g = plan.add_group(M, H, hidden + (size_t)i * M * H, H);
+    g.flags = EPI_BIAS | EPI_RELU;
+    g.bias = b1_host[i];
+    plan.add_seg(feat_rel + (size_t)i * H, R * H, W1_host[i], H, H);
+    w2.p[i] = W2_host[i];
+    b2.p[i] = b2_host[i];
+  }
+  TA3N_TRY(run_gemm(plan, S(stream)));
+  relattn_fwd_kernel<<<blocks_for((size_t)M * 32, 256), 256, 0, S(stream)>>>(feat_rel, hidden, M, R, H, w2, b2,
+                                                                             use_attn, pred_rel, attn, feat_video);
+  return after_launch();
+}
+
+size_t ta3n_relattn_bwd_workspace_bytes(int M, int R, int H) {
+  return Arena::round((size_t)M * R * 2 * sizeof(float)) + Arena::round((size_t)R * M * H * sizeof(float)) +
+         splitk_bytes(2 * R);
+}
+
+int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* const* W1_host,
+                     const float* const* W2_host, int use_attn, const float* hidden, const float* pred_rel,
+                     const float* attn, const float* g_feat_video, const float* g_pred_rel, const float* g_attn,
+                     float beta, float* d_feat_rel, float* const* dW1_host, float* const* db1_host,
+                     float* const* dW2_host, float* const* db2_host, void* workspace, size_t workspace_bytes,
+                     ta3n_stream_t stream) {
+  TA3N_REQUIRE(M >= 0 && R >= 1 && R <= kMaxScales && H > 0, "bad sizes");
+  TA3N_REQUIRE(dW1_host && db1_host && dW2_host && db2_host, "null gradient tables");
+  cudaStream_t st = S(stream);
+  if (M == 0) {
+    for (int i = 0; i < R; ++i) {
+      TA3N_CUDA(cudaMemsetAsync(dW1_host[i], 0, sizeof(float) * H * H, st));
+      TA3N_CUDA(cudaMemsetAsync(db1_host[i], 0, sizeof(float) * H, st));
+      TA3N_CUDA(cudaMemsetAsync(dW2_host[i], 0, sizeof(float) * 2 * H, st));
+      TA3N_CUDA(cudaMemsetAsync(db2_host[i], 0, sizeof(float) * 2, st));
+    }
+    return TA3N_OK;
+  }
+  TA3N_REQUIRE(feat_rel && W1_host && W2_host && hidden && pred_rel && attn && g_feat_video && d_feat_rel,
+               "null pointer");
+  Arena arena(workspace, workspace_bytes);
+  float* Pt = arena.floats((size_t)M * R * 2);
+  float* dHid = arena.floats((size_t)R * M * H);
+  if (!Pt || !dHid)
+    return fail(TA3N_ERR_WORKSPACE, "ta3n_relattn_bwd: workspace too small (%zu bytes)", workspace_bytes);
+
+  PtrTable w2;
+  memset(&w2, 0, sizeof(w2));
+  for (int i = 0; i < R; ++i) w2.p[i] = W2_host[i];
+  relattn_bwd_pre_kernel<<<blocks_for((size_t)M * 32, 256), 256, 0, st>>>(
+      feat_rel, hidden, pred_rel, g_feat_video, g_pred_rel, g_attn, M, R, H, w2, use_attn, Pt, dHid);
+  TA3N_TRY(after_launch());
+
+  {  // weight gradients of both layers of every relation discriminator
+    GemmPlan plan;
+    plan.a_kmaj = false;
+    plan.b_kmaj = false;
+    for (int i = 0; i < R; ++i) {
+      plan.add_group(2, H, dW2_host[i], H);
+      plan.add_seg(Pt + (size_t)i * 2, R * 2, hidden + (size_t)i * M * H, H, M);
+      plan.add_group(H, H, dW1_host[i], H);
+      plan.add_seg(dHid + (size_t)i * M * H, H, feat_rel + (size_t)i * H, R * H, M);
+    }
+    TA3N_TRY(run_gemm(plan, st, &arena));
+  }
+  {
+    ColsumPlan cs;
+    for (int i = 0; i < R; ++i) {
+      cs.add(db2_host[i], 2, R * 2);
+      cs.seg(Pt + (size_t)i * 2, M);
+      cs.add(db1_host[i], H, H);
+      cs.seg(dHid + (size_t)i * M * H, M);
+    }
+    TA3N_TRY(cs.run(st));
+  }
+  {  // d_feat_rel[:, i, :] = (w_i + 1) G - beta * dHid_i W1_i
+    GemmPlan plan;
+    plan.a_kmaj = true;
+    plan.b_kmaj = false;
+    for (int i = 0; i < R; ++i) {
+      Group& g = plan.add_group(M, H, d_feat_rel + (size_t)i * H, R * H);
+      g.alpha = -beta;
+      g.flags = EPI_ADDROW;
+      g.add = g_feat_video;
+      g.ldadd = H;
+      if (use_attn) {
+        g.rowscale = attn + i;
+        g.rs_stride = R;
+        g.rs_bias = 1.0f;
+      }
+      plan.add_seg(dHid + (size_t)i * M * H, H, W1_host[i], H, H);
+    }
+    TA3N_TRY(run_gemm(plan, st));
+  }
+  if (!use_attn && g_attn) {
+    attn_placeholder_bwd_kernel<<<blocks_for((size_t)M * R, 256), 256, 0, st>>>(g_attn, d_feat_rel, M, R, H);
+    TA3N_TRY(after_launch());
+  }
+  return TA3N_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// video head                                                                models.py:679-687
+// ------------------------------------------------------------------------------------------------
+int ta3n_video_head_fwd(const float* feat_video, int M, int H, int C, const float* Wc, const float* bc,
+                        const ta3n_dropout* drop, float* dropped, float* pred, ta3n_stream_t stream) {
+  TA3N_REQUIRE(M >= 0 && H > 0 && C > 0, "bad sizes");
+  if (M == 0) return TA3N_OK;
+  TA3N_REQUIRE(feat_video && Wc && bc && dropped && pred, "null pointer");
+  const DropArgs d = make_drop(drop);
+  video_drop_fwd_kernel<<<blocks_for((size_t)M * H, 256), 256, 0, S(stream)>>>(feat_video, dropped, (size_t)M * H, d);
+  TA3N_TRY(after_launch());
+  head_fwd_kernel<<<blocks_for((size_t)M * 32, 256), 256, 0, S(stream)>>>(dropped, H, Wc, bc, pred, C, M, H, C);
+  return after_launch();
+}
+
+size_t ta3n_video_head_bwd_workspace_bytes(int M, int H, int C) {
+  (void)M; (void)H; (void)C;
+  return splitk_bytes(1);
+}
+
+int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* Wc, const ta3n_dropout* drop,
+                        const float* g_pred, const float* d_dropped_extra, const float* g_feat_video_ext,
+                        float grad_scale, float* d_feat_video, float* dWc, float* dbc, void* workspace,
+                        size_t workspace_bytes, ta3n_stream_t stream) {
+  TA3N_REQUIRE(M >= 0 && H > 0 && C > 0, "bad sizes");
+  TA3N_REQUIRE(dWc && dbc, "null gradient pointer");
+  cudaStream_t st = S(stream);
+  if (M == 0 || g_pred == nullptr) {
+    TA3N_CUDA(cudaMemsetAsync(dWc, 0, sizeof(float) * C * H, st));
+    TA3N_CUDA(cudaMemsetAsync(dbc, 0, sizeof(float) * C, st));
+  }
+  if (M == 0) return TA3N_OK;
+  TA3N_REQUIRE(dropped && Wc && d_feat_video, "null pointer");
+  const DropArgs d = make_drop(drop);
+  video_head_bwd_kernel<<<blocks_for((size_t)M * H, 256), 256, 0, st>>>(g_pred, C, Wc, d_dropped_extra,
+                                                                         g_feat_video_ext, grad_scale, d,
+                                                                         d_feat_video, M, H);
+  TA3N_TRY(after_launch());
+  if (g_pred) {
+    Arena arena(workspace, workspace_bytes);
+    GemmPlan plan;
+    plan.a_kmaj = false;
+    plan.b_kmaj = false;
+    plan.add_group(C, H, dWc, H);
+    plan.add_seg(g_pred, C, dropped, H, M);
+    TA3N_TRY(run_gemm(plan, st, &arena));
+    ColsumPlan cs;
+    cs.add(dbc, C, C);
+    cs.seg(g_pred, M);
+    TA3N_TRY(cs.run(st));
+  }
+  return TA3N_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int ta3n_gemm_tn(const float* A, const float* B, float* C, int M, int N, int K, ta3n_stream_t stream) {
+  TA3N_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bad arguments");
+  GemmPlan plan;
+  plan.add_group(M, N, C, N);
+  plan.add_seg(A, K, B, K, K);
+  return run_gemm(plan, S(stream));
+}
+
+}  // extern "C"

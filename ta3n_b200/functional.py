@@ -1,0 +1,358 @@
+"""Autograd operators over the C ABI (include/ta3n_b200.h).
+
+Two operators:
+  * ``trn_multiscale``   -- RelationModuleMultiScale.forward (TRNmodule.py:58-82), stand-alone;
+  * ``video_path``       -- the whole trn-m branch of VideoModel.forward (models.py:557-704)
+                            as ONE autograd node: forward = 6 C calls, backward = 6 C calls in
+                            a fixed order, gradients accumulated inside the kernels (no autograd
+                            add / index_put / slice-backward launches).
+Tensors must be CUDA, fp32, contiguous; anything else raises (no CPU path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import math
+from dataclasses import dataclass, field
+from functools import lru_cache
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Dropout, RelationTable, check, ptr_array
+
+
+# ----------------------------------------------------------------------------------------------
+# relation table                                                        TRNmodule.py:30-41, 66-71
+# ----------------------------------------------------------------------------------------------
+class RelationSet:
+    """Host-side static description of the multi-scale relations for T frames."""
+
+    def __init__(self, num_frames: int, subsample: int = 3):
+        if num_frames < 2:
+            raise ValueError("TRN needs at least 2 frames")
+        self.num_frames = num_frames
+        self.scales = list(range(num_frames, 1, -1))                 # TRNmodule.py:34
+        self.tuples: List[List[Tuple[int, ...]]] = []
+        for pos, s in enumerate(self.scales):
+            combos = list(itertools.combinations(range(num_frames), s))   # TRNmodule.py:84-86
+            if pos == 0:
+                self.tuples.append([combos[0]])                       # TRNmodule.py:60
+            else:
+                n_sel = min(subsample, len(combos))                    # TRNmodule.py:41
+                self.tuples.append([combos[int(math.ceil(k * len(combos) / n_sel))]   # TRNmodule.py:71
+                                    for k in range(n_sel)])
+        self.n_rel = sum(len(r) for r in self.tuples)
+        self.n_slots = sum(len(t) for r in self.tuples for t in r)
+        flat = [f for r in self.tuples for t in r for f in t]
+        self._scale_size = (C.c_int * len(self.scales))(*self.scales)
+        self._rel_count = (C.c_int * len(self.scales))(*[len(r) for r in self.tuples])
+        self._frames = (C.c_int * len(flat))(*flat)
+        self.ctable = RelationTable(num_frames, len(self.scales), self._scale_size, self._rel_count, self._frames)
+
+    @property
+    def ref(self):
+        return C.byref(self.ctable)
+
+
+@lru_cache(maxsize=None)
+def relation_set(num_frames: int) -> RelationSet:
+    return RelationSet(num_frames)
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.Ta3nError(f"{name}: ta3n_b200 runs on CUDA tensors only (got {t.device}); there is no CPU path")
+    if t.dtype != torch.float32:
+        raise _lib.Ta3nError(f"{name}: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _ws(nbytes: int, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=like.device)
+
+
+@dataclass
+class DropSpec:
+    """Dropout control handed to the kernels.  keep: uint8 0/1 mask (parity runs) or None (in-kernel RNG)."""
+    p: float = 0.0
+    keep: Optional[torch.Tensor] = None
+    seed: int = 0
+    step: Optional[torch.Tensor] = None     # device int64 counter (graph-capture friendly), optional
+
+    def cstruct(self) -> Optional[Dropout]:
+        if self.p <= 0.0:
+            return None
+        if self.keep is not None:
+            if self.keep.dtype != torch.uint8 or not self.keep.is_cuda or not self.keep.is_contiguous():
+                raise _lib.Ta3nError("dropout keep mask must be a contiguous CUDA uint8 tensor")
+        return Dropout(float(self.p), _p(self.keep), int(self.seed) & (2 ** 64 - 1), _p(self.step))
+
+
+def _dref(d: Optional[Dropout]):
+    return None if d is None else C.byref(d)
+
+
+# ----------------------------------------------------------------------------------------------
+# stand-alone TRN operator
+# ----------------------------------------------------------------------------------------------
+class _TRNFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, relu_input: bool, *wb):
+        lib = _lib.load()
+        x = _chk(x, "x")
+        M, T, F = x.shape
+        rs = relation_set(T)
+        R = len(rs.scales)
+        Ws = [_chk(w, "weight") for w in wb[:R]]
+        bs = [_chk(b, "bias") for b in wb[R:]]
+        H = Ws[0].shape[0]
+        for i, s in enumerate(rs.scales):
+            if tuple(Ws[i].shape) != (H, s * F):
+                raise _lib.Ta3nError(f"TRN weight {i}: expected {(H, s * F)}, got {tuple(Ws[i].shape)}")
+        act = torch.empty(rs.n_rel, M, H, device=x.device, dtype=torch.float32)
+        feat_rel = torch.empty(M, R, H, device=x.device, dtype=torch.float32)
+        check(lib.ta3n_trn_fwd(_p(x), M, F, H, rs.ref, ptr_array([_p(w) for w in Ws]),
+                               ptr_array([_p(b) for b in bs]), int(relu_input), _p(act), _p(feat_rel), _stream()))
+        ctx.save_for_backward(x, act, *Ws)
+        ctx.meta = (M, T, F, H, bool(relu_input))
+        return feat_rel
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, act, *Ws = ctx.saved_tensors
+        M, T, F, H, relu_input = ctx.meta
+        rs = relation_set(T)
+        g = _chk(g, "grad")
+        dWs = [torch.empty_like(w) for w in Ws]
+        dbs = [torch.empty(H, device=x.device, dtype=torch.float32) for _ in Ws]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        ws = _ws(lib.ta3n_trn_bwd_workspace_bytes(M, F, H, rs.ref), x)
+        check(lib.ta3n_trn_bwd(_p(x), M, F, H, rs.ref, ptr_array([_p(w) for w in Ws]), int(relu_input), _p(act),
+                               _p(g), ptr_array([_p(t) for t in dWs]), ptr_array([_p(t) for t in dbs]), _p(dx),
+                               _p(ws), ws.numel(), _stream()))
+        return (dx, None, *dWs, *dbs)
+
+
+def trn_multiscale(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+                   relu_input: bool = True) -> torch.Tensor:
+    """(N,T,F) -> (N,T-1,H): multi-scale temporal relation features (TRNmodule.py:58-82)."""
+    return _TRNFunction.apply(x, relu_input, *weights, *biases)
+
+
+class _GradReverseFunction(torch.autograd.Function):
+    """models.py:20-29 -- identity forward, -beta * g backward (CUDA kernel ta3n_grl_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, beta):
+        ctx.beta = float(beta)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _chk(g, "grad")
+        out = torch.empty_like(g)
+        check(_lib.load().ta3n_grl_bwd(_p(g), ctx.beta, _p(out), g.numel(), _stream()))
+        return out, None
+
+
+# ----------------------------------------------------------------------------------------------
+# the fused path
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class PathSpec:
+    """Non-tensor arguments of one forward through the trn-m path."""
+    num_segments: int
+    beta: Tuple[float, float, float]          # [relation, video, frame]  (opts.py:58-59)
+    mu: float = 0.0
+    reverse: bool = False
+    use_attn: bool = True                     # 'TransAttn' vs 'none'
+    use_attn_frame: bool = False
+    drop_i: DropSpec = field(default_factory=DropSpec)
+    drop_v: DropSpec = field(default_factory=DropSpec)
+
+
+# parameter order expected by _VideoPathFunction (R = T-1):
+#   shared W,b | frame-disc W1,b1,W2,b2 | TRN W_0..W_{R-1} | TRN b_0..b_{R-1} |
+#   rel-disc W1_i | b1_i | W2_i | b2_i (each R long) | classifier W,b | video-disc W1,b1,W2,b2
+def _split_params(params, R):
+    it = iter(params)
+    take = lambda n: [next(it) for _ in range(n)]   # noqa: E731
+    shared = take(2)
+    fdisc = take(4)
+    trn_w, trn_b = take(R), take(R)
+    r_w1, r_b1, r_w2, r_b2 = take(R), take(R), take(R), take(R)
+    cls = take(2)
+    vdisc = take(4)
+    return shared, fdisc, trn_w, trn_b, r_w1, r_b1, r_w2, r_b2, cls, vdisc
+
+
+class _VideoPathFunction(torch.autograd.Function):
+    """VideoModel.forward, trn-m branch, source and target rows processed together.
+
+    Outputs (all for M = Bs + Bt rows, source rows first):
+      feat_fc (M,T,F) | pred_frame (M,T,2) | attn (M,R) | pred_rel (M,R,2) | feat_video (M,H) |
+      pred_video (M,C) | pred_dom_video (M,2)
+    """
+
+    @staticmethod
+    def forward(ctx, spec: PathSpec, xs, xt, *params):
+        lib = _lib.load()
+        st = _stream()
+        xs, xt = _chk(xs, "input_source"), _chk(xt, "input_target")
+        params = [_chk(p, "parameter") for p in params]
+        T = spec.num_segments
+        if xs.dim() != 3 or xt.dim() != 3 or xs.shape[1] != T or xt.shape[1] != T or xs.shape[2] != xt.shape[2]:
+            raise _lib.Ta3nError(f"inputs must be (B,{T},D); got {tuple(xs.shape)} and {tuple(xt.shape)}")
+        Bs, Bt, D = xs.shape[0], xt.shape[0], xs.shape[2]
+        M, R = Bs + Bt, T - 1
+        rs = relation_set(T)
+        (w_sh, b_sh), (w1f, b1f, w2f, b2f), trn_w, trn_b, r_w1, r_b1, r_w2, r_b2, (w_c, b_c), \
+            (w1v, b1v, w2v, b2v) = _split_params(params, R)
+        F, H, Cn = w_sh.shape[0], trn_w[0].shape[0], w_c.shape[0]
+        dev = xs.device
+        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)   # noqa: E731
+
+        d_i, d_v = spec.drop_i.cstruct(), spec.drop_v.cstruct()
+
+        # 1. shared layer  (models.py:565-575)
+        feat = new(M * T, F)
+        check(lib.ta3n_shared_fc_fwd(_p(xs), Bs * T, _p(xt), Bt * T, D, _p(w_sh), _p(b_sh), F, _dref(d_i),
+                                     _p(feat), st))
+        # 2. frame-level discriminator  (models.py:606-610)
+        hid_f, pred_frame = new(M * T, F), new(M * T, 2)
+        check(lib.ta3n_disc_fwd(_p(feat), M * T, F, F, _p(w1f), _p(b1f), _p(w2f), _p(b2f), _p(hid_f),
+                                _p(pred_frame), st))
+        # 2b. frame attention  (models.py:612-614)
+        if spec.use_attn_frame:
+            feat_in = new(M * T, F)
+            check(lib.ta3n_frame_attn_fwd(_p(feat), _p(pred_frame), M * T, F, _p(feat_in), st))
+        else:
+            feat_in = feat
+        # 3. TRN  (models.py:635-636).  feat_in >= 0 (post ReLU/dropout, attention factor > 0): the
+        #    leading nn.ReLU of fc_fusion is an identity in value and gradient -> relu_input=0.
+        act, feat_rel = new(rs.n_rel, M, H), new(M, R, H)
+        check(lib.ta3n_trn_fwd(_p(feat_in), M, F, H, rs.ref, ptr_array([_p(w) for w in trn_w]),
+                               ptr_array([_p(b) for b in trn_b]), 0, _p(act), _p(feat_rel), st))
+        # 4. relation discriminators + attention + pooling  (models.py:639-652)
+        hid_r, pred_rel, attn, feat_video = new(R, M, H), new(M, R, 2), new(M, R), new(M, H)
+        check(lib.ta3n_relattn_fwd(_p(feat_rel), M, R, H, ptr_array([_p(w) for w in r_w1]),
+                                   ptr_array([_p(b) for b in r_b1]), ptr_array([_p(w) for w in r_w2]),
+                                   ptr_array([_p(b) for b in r_b2]), int(spec.use_attn), _p(hid_r), _p(pred_rel),
+                                   _p(attn), _p(feat_video), st))
+        # 5. video head  (models.py:679-687)
+        dropped, pred_video = new(M, H), new(M, Cn)
+        check(lib.ta3n_video_head_fwd(_p(feat_video), M, H, Cn, _p(w_c), _p(b_c), _dref(d_v), _p(dropped),
+                                      _p(pred_video), st))
+        # 6. video-level discriminator  (models.py:694-698)
+        hid_v, pred_dom_video = new(M, H), new(M, 2)
+        check(lib.ta3n_disc_fwd(_p(dropped), M, H, H, _p(w1v), _p(b1v), _p(w2v), _p(b2v), _p(hid_v),
+                                _p(pred_dom_video), st))
+
+        ctx.spec = spec
+        ctx.dims = (Bs, Bt, D, T, F, H, Cn)
+        ctx.drop_keepalive = (spec.drop_i.keep, spec.drop_v.keep, spec.drop_i.step, spec.drop_v.step)
+        ctx.save_for_backward(xs, xt, feat, hid_f, pred_frame, feat_in, act, feat_rel, hid_r, pred_rel, attn,
+                              dropped, hid_v, *params)
+        ctx.set_materialize_grads(False)
+        return (feat.view(M, T, F), pred_frame.view(M, T, 2), attn, pred_rel, feat_video, pred_video,
+                pred_dom_video)
+
+    @staticmethod
+    def backward(ctx, g_feat, g_pred_frame, g_attn, g_pred_rel, g_feat_video, g_pred_video, g_pred_dom_video):
+        lib = _lib.load()
+        st = _stream()
+        spec: PathSpec = ctx.spec
+        Bs, Bt, D, T, F, H, Cn = ctx.dims
+        M, R = Bs + Bt, T - 1
+        rs = relation_set(T)
+        (xs, xt, feat, hid_f, pred_frame, feat_in, act, feat_rel, hid_r, pred_rel, attn, dropped, hid_v,
+         *params) = ctx.saved_tensors
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise _lib.Ta3nError("gradients w.r.t. the input features are not part of this path "
+                                 "(the reference's features carry no grad, SURVEY 3.3)")
+        (w_sh, b_sh), (w1f, b1f, w2f, b2f), trn_w, trn_b, r_w1, r_b1, r_w2, r_b2, (w_c, b_c), \
+            (w1v, b1v, w2v, b2v) = _split_params(params, R)
+        dev = xs.device
+        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)   # noqa: E731
+        like = lambda ts: [torch.empty_like(t) for t in ts]                          # noqa: E731
+        g_feat, g_pred_frame, g_attn, g_pred_rel, g_feat_video, g_pred_video, g_pred_dom_video = [
+            _chk(t, "grad") for t in (g_feat, g_pred_frame, g_attn, g_pred_rel, g_feat_video, g_pred_video,
+                                      g_pred_dom_video)]
+        d_v = spec.drop_v.cstruct()
+
+        # 6'. video discriminator: d_dropped = -beta1 * dgrad
+        dw1v, db1v, dw2v, db2v = like([w1v, b1v, w2v, b2v])
+        d_dropped = new(M, H)
+        ws = _ws(lib.ta3n_disc_bwd_workspace_bytes(M, H, H), xs)
+        check(lib.ta3n_disc_bwd(_p(dropped), M, H, H, _p(w1v), _p(w2v), _p(hid_v), _p(g_pred_dom_video),
+                                float(spec.beta[1]), _p(d_dropped), 0, _p(dw1v), _p(db1v), _p(dw2v), _p(db2v),
+                                _p(ws), ws.numel(), st))
+        # 5'. classifier + dropout_v (+ optional GRL_mu around both heads, models.py:682-684)
+        dw_c, db_c = like([w_c, b_c])
+        G = new(M, H)
+        ws = _ws(lib.ta3n_video_head_bwd_workspace_bytes(M, H, Cn), xs)
+        check(lib.ta3n_video_head_bwd(_p(dropped), M, H, Cn, _p(w_c), _dref(d_v), _p(g_pred_video), _p(d_dropped),
+                                      _p(g_feat_video), float(-spec.mu) if spec.reverse else 1.0, _p(G),
+                                      _p(dw_c), _p(db_c), _p(ws), ws.numel(), st))
+        # 4'. relation discriminators / attention (attention weights are NOT detached)
+        dr_w1, dr_b1, dr_w2, dr_b2 = like(r_w1), like(r_b1), like(r_w2), like(r_b2)
+        d_feat_rel = new(M, R, H)
+        ws = _ws(lib.ta3n_relattn_bwd_workspace_bytes(M, R, H), xs)
+        check(lib.ta3n_relattn_bwd(_p(feat_rel), M, R, H, ptr_array([_p(w) for w in r_w1]),
+                                   ptr_array([_p(w) for w in r_w2]), int(spec.use_attn), _p(hid_r), _p(pred_rel),
+                                   _p(attn), _p(G), _p(g_pred_rel), _p(g_attn), float(spec.beta[0]),
+                                   _p(d_feat_rel), ptr_array([_p(t) for t in dr_w1]),
+                                   ptr_array([_p(t) for t in dr_b1]), ptr_array([_p(t) for t in dr_w2]),
+                                   ptr_array([_p(t) for t in dr_b2]), _p(ws), ws.numel(), st))
+        # 3'. TRN
+        dtrn_w, dtrn_b = like(trn_w), like(trn_b)
+        d_feat = new(M * T, F)
+        ws = _ws(lib.ta3n_trn_bwd_workspace_bytes(M, F, H, rs.ref), xs)
+        check(lib.ta3n_trn_bwd(_p(feat_in), M, F, H, rs.ref, ptr_array([_p(w) for w in trn_w]), 0, _p(act),
+                               _p(d_feat_rel), ptr_array([_p(t) for t in dtrn_w]),
+                               ptr_array([_p(t) for t in dtrn_b]), _p(d_feat), _p(ws), ws.numel(), st))
+        # 2b'. frame attention
+        if g_pred_frame is not None:
+            g_pf = g_pred_frame.reshape(M * T, 2)
+            if spec.use_attn_frame:
+                g_pf = g_pf.clone()
+        else:
+            g_pf = torch.zeros(M * T, 2, device=dev, dtype=torch.float32) if spec.use_attn_frame else None
+        if spec.use_attn_frame:
+            check(lib.ta3n_frame_attn_bwd(_p(feat), _p(pred_frame), M * T, F, _p(d_feat), _p(g_pf), st))
+        # 2'. frame discriminator: d_feat += -beta2 * dgrad
+        dw1f, db1f, dw2f, db2f = like([w1f, b1f, w2f, b2f])
+        ws = _ws(lib.ta3n_disc_bwd_workspace_bytes(M * T, F, F), xs)
+        check(lib.ta3n_disc_bwd(_p(feat), M * T, F, F, _p(w1f), _p(w2f), _p(hid_f), _p(g_pf),
+                                float(spec.beta[2]), _p(d_feat), 1, _p(dw1f), _p(db1f), _p(dw2f), _p(db2f),
+                                _p(ws), ws.numel(), st))
+        # 1'. shared layer (wgrad only)
+        dw_sh, db_sh = like([w_sh, b_sh])
+        ws = _ws(lib.ta3n_shared_fc_bwd_workspace_bytes(M * T, D, F), xs)
+        g_feat_flat = None if g_feat is None else g_feat.reshape(M * T, F)
+        check(lib.ta3n_shared_fc_bwd(_p(xs), Bs * T, _p(xt), Bt * T, D, F, _p(feat), _p(d_feat), _p(g_feat_flat),
+                                     float(spec.drop_i.p), _p(dw_sh), _p(db_sh), _p(ws), ws.numel(), st))
+
+        grads = [dw_sh, db_sh, dw1f, db1f, dw2f, db2f, *dtrn_w, *dtrn_b, *dr_w1, *dr_b1, *dr_w2, *dr_b2,
+                 dw_c, db_c, dw1v, db1v, dw2v, db2v]
+        return (None, None, None, *grads)
+
+
+def video_path(spec: PathSpec, xs: torch.Tensor, xt: torch.Tensor, params: Sequence[torch.Tensor]):
+    return _VideoPathFunction.apply(spec, xs, xt, *params)

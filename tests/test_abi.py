@@ -1,0 +1,94 @@
+"""The C-ABI shared library loads and exports every symbol include/ta3n_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ta3n_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ta3n_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ta3n_b200 import build
+    build.build()                       # nvcc cross-compiles sm_100a without a GPU
+    from ta3n_b200 import _lib
+    return _lib.load()
+
+
+def test_header_and_binding_agree(lib):
+    from ta3n_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 20
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_every_declared_symbol_is_exported(lib):
+    raw = ctypes.CDLL(lib._name)
+    for name in declared_functions():
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+
+
+def test_abi_version_and_engine_switch(lib):
+    from ta3n_b200 import _lib
+    assert lib.ta3n_abi_version() == 1
+    _lib.set_gemm_engine("tf32")
+    assert _lib.get_gemm_engine() == "tf32"
+    _lib.set_gemm_engine("fp32")
+    assert _lib.get_gemm_engine() == "fp32"
+    assert lib.ta3n_set_gemm_engine(7) != 0
+    assert b"unknown GEMM engine" in lib.ta3n_last_error()
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    # null pointers / bad sizes are rejected on the host before any CUDA call
+    rc = lib.ta3n_disc_fwd(None, 4, 8, 8, None, None, None, None, None, None, None)
+    assert rc == 1
+    assert b"ta3n_disc_fwd" in lib.ta3n_last_error()
+    rc = lib.ta3n_gemm_tn(None, None, None, 0, 0, 0, None)
+    assert rc == 1
+
+
+def test_no_cpu_fallback_in_product_package():
+    """The product package never imports the oracle and refuses CPU tensors."""
+    import torch
+
+    from ta3n_b200 import Ta3nError
+    from ta3n_b200.models import VideoModel
+    pkg = os.path.join(ROOT, "ta3n_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("the oracle", ""), fn
+    m = VideoModel(5, "video", "trn-m", "RGB", train_segments=5, val_segments=5, fc_dim=64, verbose=False)
+    x = torch.zeros(2, 5, 2048)
+    with pytest.raises(Ta3nError):
+        m(x, x, [1, 1, 1], 0, True, False)     # model on CPU -> refuses
+
+
+def test_unsupported_options_raise():
+    from ta3n_b200.models import VideoModel
+    for kw in (dict(frame_aggregation="avgpool"), dict(use_bn="AdaBN"), dict(ens_DA="MCD"),
+               dict(share_params="N"), dict(use_attn="general"), dict(baseline_type="tsn")):
+        args = dict(num_class=5, baseline_type="video", frame_aggregation="trn-m", modality="RGB", verbose=False)
+        args.update(kw)
+        with pytest.raises(NotImplementedError):
+            VideoModel(**args)
+    with pytest.raises(ValueError):
+        VideoModel(5, "video", "trn-m", "RGB", add_fc=0, verbose=False)
+
+
+def test_relation_table_matches_survey_appendix_a():
+    from ta3n_b200.functional import relation_set
+    rs = relation_set(5)
+    assert rs.tuples[1] == [(0, 1, 2, 3), (0, 1, 3, 4), (1, 2, 3, 4)]
+    assert rs.tuples[3] == [(0, 1), (1, 2), (2, 3)]
+    assert (rs.n_rel, rs.n_slots) == (10, 32)
+    r9 = relation_set(9)
+    assert (r9.n_rel, r9.n_slots) == (22, 114)

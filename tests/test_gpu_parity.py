@@ -1,0 +1,301 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the CPU oracle and the golden vectors.
+
+Tolerances: normwise relative error per tensor.  1e-3 is the path's stated budget (north_star);
+the exact-fp32 engine is held to 2e-4 (accumulation-order noise only).
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import gen_golden
+from oracle import ta3n_oracle as orc
+from tests.golden_util import (TOL_PATH, assert_close, check_grads_against_golden,
+                               check_outputs_against_golden, load_golden, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["fp32", "tf32"]
+TOL = {"fp32": 2e-4, "tf32": TOL_PATH}
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(params=ENGINES)
+def engine(request):
+    import ta3n_b200
+    ta3n_b200.set_gemm_engine(request.param)
+    yield request.param
+    ta3n_b200.set_gemm_engine("fp32")
+
+
+def build_model(cfg: orc.PathConfig, params, train: bool):
+    from ta3n_b200.models import VideoModel
+    m = VideoModel(cfg.num_class, "video", "trn-m", "RGB", train_segments=cfg.num_segments,
+                   val_segments=cfg.num_segments, add_fc=1, fc_dim=cfg.fc_dim, dropout_i=cfg.dropout_i,
+                   dropout_v=cfg.dropout_v, partial_bn=False, use_bn="none", ens_DA="none",
+                   use_attn=cfg.use_attn, use_attn_frame=cfg.use_attn_frame, share_params="Y", verbose=False)
+    m.load_state_dict(params)
+    m = m.to(_dev())
+    m.train(train)
+    return m
+
+
+def cat_masks(masks):
+    if masks is None:
+        return None
+    return {"i": torch.cat([masks["i_source"], masks["i_target"]], 0).to(_dev()),
+            "v": torch.cat([masks["v_source"], masks["v_target"]], 0).to(_dev())}
+
+
+def run_cuda_step(model, xs, xt, labels, beta, gamma, masks=None):
+    from ta3n_b200.loss import ta3n_loss
+    model.zero_grad(set_to_none=True)
+    model.dropout_masks = cat_masks(masks)
+    outs = model(xs.to(_dev()), xt.to(_dev()), list(beta), 0, is_train=True, reverse=False)
+    loss = ta3n_loss(outs, labels.to(_dev()), gamma, use_attn=model.use_attn)
+    loss.backward()
+    grads = {k: (p.grad.detach().cpu() if p.grad is not None else None) for k, p in model.named_parameters()}
+    return loss.detach().cpu(), outs, grads
+
+
+def flat_outputs(outs):
+    return [outs[0], outs[1], *outs[3], *outs[4], outs[5], outs[6], *outs[8], *outs[9]]
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors (made by the unmodified reference, tests/golden/ta3n_golden.npz)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", list(gen_golden.CASES))
+def test_model_matches_reference_golden(case, engine):
+    z, meta = load_golden()
+    c = gen_golden.CASES[case]
+    cfg, xs, xt, labels, masks = gen_golden.case_inputs(c)
+    params = orc.init_params(cfg, seed=meta["model_seed"])
+    model = build_model(cfg, params, train=c["train"])
+    loss, outs, grads = run_cuda_step(model, xs, xt, labels, meta["beta"], meta["gamma"], masks)
+    tol = TOL[engine]
+    assert_close(loss, z[f"{case}/loss"], tol, "loss")
+    check_outputs_against_golden(z, case, outs, tol, meta["stride"])
+    used = meta["used_params"][case]
+    check_grads_against_golden(z, case, grads, used, tol, meta["stride"])
+    for name, g in grads.items():          # parameters the reference leaves without grad stay without
+        if name not in used:
+            assert g is None, name
+
+
+# ------------------------------------------------------------------------------------------------
+# live oracle at a mid size with non-degenerate (trained-like) weights
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,attn_frame,bs,bt", [(5, "none", 37, 21), (7, "TransAttn", 16, 16)])
+def test_model_matches_oracle_mid_size(T, attn_frame, bs, bt, engine):
+    cfg = orc.PathConfig(num_class=12, num_segments=T, fc_dim=512, dropout_i=0.5, dropout_v=0.5,
+                         use_attn="TransAttn", use_attn_frame=attn_frame)
+    params = orc.init_params(cfg, seed=99)
+    g = torch.Generator().manual_seed(5)
+    for k in params:                        # move away from the N(0, 1e-3) init: logits of O(1)
+        if params[k].dtype.is_floating_point and k.startswith(orc.USED_PARAM_PREFIXES) and "weight" in k:
+            params[k] = params[k] + 0.02 * torch.randn(params[k].shape, generator=g)
+    xs = torch.randn(bs, T, orc.FEATURE_DIM, generator=g)
+    xt = torch.randn(bt, T, orc.FEATURE_DIM, generator=g) + 0.3
+    labels = torch.arange(bs) % cfg.num_class
+    keep = lambda *s: (torch.rand(*s, generator=g) < 0.5).to(torch.uint8)   # noqa: E731
+    masks = {"i_source": keep(bs * T, 512), "i_target": keep(bt * T, 512),
+             "v_source": keep(bs, 256), "v_target": keep(bt, 256)}
+    beta = (0.75, 0.6, 0.5)
+    loss_o, outs_o, grads_o = orc.train_step(params, xs, xt, labels, beta, cfg, 0.003, train=True, masks=masks)
+    model = build_model(cfg, params, train=True)
+    loss, outs, grads = run_cuda_step(model, xs, xt, labels, beta, 0.003, masks)
+    tol = TOL[engine]
+    assert_close(loss, loss_o, tol, "loss")
+    for i, (a, b) in enumerate(zip(flat_outputs(outs), flat_outputs(outs_o))):
+        assert a.shape == b.shape
+        assert_close(a, b, tol, f"output {i}")
+    for name, go in grads_o.items():
+        assert_close(grads[name], go, tol * 2, f"grad {name}")
+
+
+# ------------------------------------------------------------------------------------------------
+# stand-alone RelationModuleMultiScale (negative inputs exercise the leading ReLU, TRNmodule.py:49)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,F,N", [(5, 64, 9), (3, 128, 70), (9, 32, 5), (2, 16, 3)])
+def test_trn_module_matches_oracle(T, F, N, engine):
+    from ta3n_b200.TRNmodule import RelationModuleMultiScale
+    torch.manual_seed(3)
+    mod = RelationModuleMultiScale(F, 256, T).to(_dev())
+    x = torch.randn(N, T, F)
+    ws = [s[1].weight.detach().cpu().clone().requires_grad_(True) for s in mod.fc_fusion_scales]
+    bs = [s[1].bias.detach().cpu().clone().requires_grad_(True) for s in mod.fc_fusion_scales]
+    xo = x.clone().requires_grad_(True)
+    ref = orc.trn_multiscale(xo, ws, bs, orc.relation_tuples(T))
+    gout = torch.randn(ref.shape)
+    ref.backward(gout)
+    xg = x.to(_dev()).requires_grad_(True)
+    out = mod(xg)
+    out.backward(gout.to(_dev()))
+    tol = TOL[engine]
+    assert_close(out, ref, tol, "trn fwd")
+    assert_close(xg.grad, xo.grad, tol * 2, "trn dx")
+    for i, seq in enumerate(mod.fc_fusion_scales):
+        assert_close(seq[1].weight.grad, ws[i].grad, tol * 2, f"trn dW{i}")
+        assert_close(seq[1].bias.grad, bs[i].grad, tol * 2, f"trn db{i}")
+
+
+def test_grad_reverse_matches_reference_semantics():
+    from ta3n_b200.models import GradReverse
+    x = torch.randn(33, 7, device=_dev(), requires_grad=True)
+    y = GradReverse.apply(x, 0.75)
+    assert torch.equal(y, x)
+    g = torch.randn_like(x)
+    y.backward(g)
+    assert torch.allclose(x.grad, -0.75 * g, rtol=0, atol=0)   # models.py:27-29: probe beta=0.75 -> -0.75
+
+
+# ------------------------------------------------------------------------------------------------
+# raw GEMM engine through the C ABI (ragged sizes hit every guard path)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (64, 64, 16), (130, 70, 50), (512, 256, 2560), (37, 256, 512),
+                                   (2560, 512, 2048)])
+def test_gemm_tn_matches_torch(M, N, K, engine):
+    from ta3n_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g).to(_dev())
+    B = torch.randn(N, K, generator=g).to(_dev())
+    Cm = torch.empty(M, N, device=_dev())
+    _lib.check(lib.ta3n_gemm_tn(A.data_ptr(), B.data_ptr(), Cm.data_ptr(), M, N, K,
+                                torch.cuda.current_stream().cuda_stream))
+    ref = (A.double() @ B.double().t()).float()
+    assert_close(Cm, ref, TOL[engine] , "gemm_tn")
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size (BASELINE cfg2: B=256,T=5,D=2048,C=12) size-independent properties
+# ------------------------------------------------------------------------------------------------
+def _cfg2_model(train=False):
+    cfg = orc.PathConfig(num_class=12, num_segments=5, fc_dim=512, dropout_i=0.5, dropout_v=0.5)
+    params = orc.init_params(cfg, seed=1234)
+    return cfg, params, build_model(cfg, params, train)
+
+
+def test_full_size_rows_are_independent_and_deterministic(engine):
+    """No op on the path mixes videos: a sub-batch gives the same rows; reruns are bit-identical."""
+    cfg, params, model = _cfg2_model(train=False)
+    xs, xt, _ = orc.synthetic_batch(256, cfg)
+    xs, xt = xs.to(_dev()), xt.to(_dev())
+    with torch.no_grad():
+        a = model(xs, xt, [0.75, 0.75, 0.5], 0, True, False)
+        b = model(xs, xt, [0.75, 0.75, 0.5], 0, True, False)
+        sub = model(xs[:64], xt[:40], [0.75, 0.75, 0.5], 0, True, False)
+    for u, v in zip(flat_outputs(a), flat_outputs(b)):
+        assert torch.equal(u, v)
+    fa, fs = flat_outputs(a), flat_outputs(sub)
+    half = len(fa) // 2
+    for i, (u, v) in enumerate(zip(fa, fs)):
+        n = 64 if i < half else 40
+        assert_close(v, u[:n], 1e-5 if engine == "fp32" else TOL_PATH, f"row independence output {i}")
+
+
+def test_full_size_matches_oracle_sample(engine):
+    """cfg2 forward on the GPU vs the CPU oracle on the same inputs (eval mode; ~1 s of CPU)."""
+    cfg, params, model = _cfg2_model(train=False)
+    xs, xt, labels = orc.synthetic_batch(256, cfg)
+    with torch.no_grad():
+        outs = model(xs.to(_dev()), xt.to(_dev()), [0.75, 0.75, 0.5], 0, True, False)
+        ref = orc.forward(params, xs, xt, [0.75, 0.75, 0.5], 0.0, cfg, train=False)
+    for i, (a, b) in enumerate(zip(flat_outputs(outs), flat_outputs(ref))):
+        assert_close(a, b, TOL[engine], f"cfg2 output {i}")
+
+
+def test_full_size_gradient_shards_sum_to_full_batch(engine):
+    """Data-parallel property (§8e): with mean losses and equal shards, the average of the two
+    half-batch gradients equals the full-batch gradient."""
+    from ta3n_b200.loss import ta3n_loss
+    cfg, params, model = _cfg2_model(train=False)
+    xs, xt, labels = orc.synthetic_batch(256, cfg)
+    xs, xt, labels = xs.to(_dev()), xt.to(_dev()), labels.to(_dev())
+
+    def grads_of(sl):
+        model.zero_grad(set_to_none=True)
+        outs = model(xs[sl], xt[sl], [0.75, 0.75, 0.5], 0, True, False)
+        ta3n_loss(outs, labels[sl], 0.003).backward()
+        return {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    full = grads_of(slice(0, 256))
+    h0, h1 = grads_of(slice(0, 128)), grads_of(slice(128, 256))
+    tol = 5e-4 if engine == "fp32" else 2 * TOL_PATH
+    for k in full:
+        assert_close(0.5 * (h0[k] + h1[k]), full[k], tol, f"shard-sum {k}")
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases
+# ------------------------------------------------------------------------------------------------
+def test_single_video_and_empty_target():
+    cfg = orc.PathConfig(num_class=5, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0)
+    params = orc.init_params(cfg, seed=1)
+    model = build_model(cfg, params, train=True)
+    xs = torch.randn(1, 5, orc.FEATURE_DIM)
+    xt = torch.randn(0, 5, orc.FEATURE_DIM)
+    outs = model(xs.to(_dev()), xt.to(_dev()), [1, 1, 1], 0, True, False)
+    ref = orc.forward(params, xs, xt, [1, 1, 1], 0.0, cfg, train=True)
+    for a, b in zip(flat_outputs(outs), flat_outputs(ref)):
+        assert a.shape == b.shape
+        if b.numel():
+            assert_close(a, b, 2e-4, "single video")
+    outs[1].sum().backward()
+    assert model.fc_feature_shared_source.weight.grad is not None
+
+
+def test_in_kernel_dropout_statistics_and_mask_consistency():
+    """Perf-mode dropout (counter-based RNG): keep rate ~ 1-p, scaling 1/(1-p), fresh mask per call,
+    and backward uses the same mask as forward (gradient is zero exactly where the feature is zero)."""
+    cfg = orc.PathConfig(num_class=12, num_segments=5, fc_dim=512, dropout_i=0.5, dropout_v=0.5)
+    params = orc.init_params(cfg, seed=1234)
+    model = build_model(cfg, params, train=True)
+    xs, xt, labels = orc.synthetic_batch(64, cfg)
+    o1 = model(xs.to(_dev()), xt.to(_dev()), [0.75, 0.75, 0.5], 0, True, False)
+    o2 = model(xs.to(_dev()), xt.to(_dev()), [0.75, 0.75, 0.5], 0, True, False)
+    f1, f2 = o1[4][2], o2[4][2]
+    model.eval()
+    with torch.no_grad():
+        fe = model(xs.to(_dev()), xt.to(_dev()), [0.75, 0.75, 0.5], 0, True, False)[4][2]
+    alive = fe > 0
+    kept = (f1 > 0) & alive
+    rate = kept.sum().item() / alive.sum().item()
+    assert abs(rate - 0.5) < 0.01, rate
+    assert torch.allclose(f1[kept], 2.0 * fe[kept], rtol=1e-6, atol=0)
+    assert not torch.equal(f1 > 0, f2 > 0)
+
+
+def test_reverse_flag_scales_trunk_gradient_by_minus_mu():
+    cfg = orc.PathConfig(num_class=12, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0)
+    params = orc.init_params(cfg, seed=4)
+    model = build_model(cfg, params, train=True)
+    xs, xt, labels = orc.synthetic_batch(8, cfg)
+
+    def run(cuda: bool, mu, reverse):
+        if cuda:
+            model.zero_grad(set_to_none=True)
+            outs = model(xs.to(_dev()), xt.to(_dev()), [0.75, 0.75, 0.5], mu, True, reverse)
+            (outs[1].sum() + outs[6].sum() + outs[3][1].sum()).backward()
+            return model.TRN.fc_fusion_scales[0][1].weight.grad.cpu(), model.fc_classifier_video_source.weight.grad.cpu()
+        leaves = {k: v.clone().requires_grad_(True) for k, v in params.items() if v.dtype.is_floating_point}
+        outs = orc.forward(leaves, xs, xt, [0.75, 0.75, 0.5], mu, cfg, train=True, reverse=reverse)
+        (outs[1].sum() + outs[6].sum() + outs[3][1].sum()).backward()
+        return leaves["TRN.fc_fusion_scales.0.1.weight"].grad, leaves["fc_classifier_video_source.weight"].grad
+
+    for mu, rev in [(0.0, False), (0.7, True), (0.0, True)]:
+        a, b = run(True, mu, rev), run(False, mu, rev)
+        for u, v in zip(a, b):
+            assert_close(u, v, 5e-4, f"reverse mu={mu} rev={rev}")
+
+
+def test_cpu_tensors_are_moved_not_computed_on_cpu():
+    from ta3n_b200 import _lib
+    from ta3n_b200 import functional as TF
+    with pytest.raises(_lib.Ta3nError):
+        TF.trn_multiscale(torch.randn(2, 5, 8), [torch.randn(256, s * 8) for s in (5, 4, 3, 2)],
+                          [torch.randn(256) for _ in range(4)])
