@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the TA3N hot path on B200 (metric of BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0
+
+One "step" = one paired mini-batch (B source + B target videos, T=5, D=2048) through
+VideoModel.forward (train mode, dropout 0.5/0.5), the composed loss of the shipped script
+(CE + 3 domain CEs + 0.003 * attentive entropy; main.py:446, 508-538, 559-562) and backward to all
+parameter gradients (+ the gradient all-reduce when N > 1).  clips per step = 2B per GPU.
+The optimizer is outside the metric (BASELINE.json: "fwd+bwd"); the e2e leg includes it.
+
+Prints ONE JSON line on rank 0 (schema: see the task contract).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BETA = (0.75, 0.75, 0.5)       # script_train_val.sh: beta 0.75 0.75 0.5
+GAMMA = 0.003
+H = 256
+D = 2048
+METRIC = "video-clips/sec fwd+bwd (B=256,T=5,D=2048)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="videos per domain per GPU")
+    ap.add_argument("--segments", type=int, default=5)
+    ap.add_argument("--classes", type=int, default=12)
+    ap.add_argument("--fc_dim", type=int, default=512)
+    ap.add_argument("--engine", default=os.environ.get("TA3N_ENGINE", "auto"), choices=["auto", "fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic traffic (fp32; every operand read once, every result written once) -- DESIGN.md §5
+# ------------------------------------------------------------------------------------------------
+def traffic_model(M, T, F, C):
+    """bytes per step for the whole path ("scope B") and per GEMM call site."""
+    from ta3n_b200.functional import relation_set
+    rs = relation_set(T)
+    R = T - 1
+    S = rs.n_slots
+    Wt = sum(s * F * H + H for s in rs.scales)
+    Wr = R * (H * H + 3 * H + 2)
+    f4 = 4.0
+    scope_a = f4 * (3 * M * T * F + 3 * Wt + 3 * Wr + 4 * M * R * H + 2 * (3 * M * R + M * H))
+    shared = 2 * M * T * D + 3 * (F * D + F)                       # x read fwd+wgrad, W read 2x, dW written
+    frame_disc = 3 * (F * F + 3 * F + 2) + 2 * M * T * F + 2 * M * T * F + 3 * M * T * 2
+    video = 3 * (H * H + 3 * H + 2 + C * H + C) + 4 * M * H + 3 * M * (C + 2)
+    scope_b = scope_a + f4 * (shared + frame_disc + video)
+    n_rel = rs.n_rel
+    sites = {
+        "shared_fc_fwd": f4 * (M * T * D + F * D + F + M * T * F),
+        "shared_fc_wgrad": f4 * (M * T * F + M * T * D + F * D),
+        "trn_fwd": f4 * (M * T * F + Wt + n_rel * M * H),
+        "trn_wgrad": f4 * (n_rel * M * H + M * T * F + Wt),
+        "trn_dgrad": f4 * (n_rel * M * H + Wt + M * T * F),
+        "disc_fwd": f4 * (M * T * F + F * F + F + M * T * F) + f4 * (M * H + H * H + H + M * H),
+        "disc_wgrad": f4 * (2 * M * T * F + F * F + M * T * 2 + 2 * F) + f4 * (2 * M * H + H * H + M * 2 + 2 * H),
+        "disc_dgrad": f4 * (M * T * F + F * F + 2 * M * T * F) + f4 * (M * H + H * H + M * H),
+        "relattn_fwd": f4 * (M * R * H + R * (H * H + H) + R * M * H),
+        "relattn_wgrad": f4 * (2 * R * M * H + R * H * H + R * M * 2 + R * 2 * H + R * M * H),
+        "relattn_dgrad": f4 * (R * M * H + R * H * H + M * H + M * R + M * R * H),
+    }
+    flops_b = 3 * (2 * M * S * F * H + R * (2 * M * H * H + 4 * M * H)) + \
+        3 * (2 * M * T * F * F + 4 * M * T * F + 2 * M * H * H + 4 * M * H + 2 * M * H * C) + 2 * (2 * M * T * D * F)
+    return {"scope_a": scope_a, "scope_b": scope_b, "sites": sites, "flops_b": flops_b}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                self.samples.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, smax, reasons, power = [], 0.0, set(), 0.0
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                smax = max(smax, float(s[1]))
+                power = max(power, float(s[2]))
+                for n, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax or None,
+                "power_w_max": power or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 0))), "measured"
+    return 6650.0, 1590.0, "fallback"        # B200_PROFILING.md fallback
+
+
+def pick_engine(requested):
+    import ta3n_b200
+    if requested == "auto":
+        requested = os.environ.get("TA3N_DEFAULT_ENGINE", "fp32")
+    ta3n_b200.set_gemm_engine(requested)
+    return requested
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(args, steps, warmup, budget_s=None):
+    import torch
+
+    from oracle import ta3n_oracle as orc          # checker / CPU baseline only (never the product path)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = orc.PathConfig(num_class=args.classes, num_segments=args.segments, fc_dim=args.fc_dim,
+                         dropout_i=0.5, dropout_v=0.5)
+    params = orc.init_params(cfg, seed=1234)
+    xs, xt, labels = orc.synthetic_batch(args.batch, cfg)
+    names = orc.used_param_names(params)
+    leaves = {k: params[k].clone().requires_grad_(True) for k in names}
+    live = dict(params)
+    live.update(leaves)
+
+    def step():
+        for v in leaves.values():
+            v.grad = None
+        outs = orc.forward(live, xs, xt, BETA, 0.0, cfg, train=True, reverse=False)
+        loss = orc.compose_loss(outs, labels, GAMMA)
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 3:
+            break
+    dt = time.perf_counter() - t0
+    return {"clips_per_s": done * 2 * args.batch / dt, "ms_per_step": 1e3 * dt / done, "steps": done, "cores": cores}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args, args.steps, args.warmup)
+    sample = (f"{r['steps']} full steps of the oracle port (eager PyTorch CPU restatement of the reference) at "
+              f"B={args.batch}+{args.batch}, T={args.segments}, D={D}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["clips_per_s"], "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1, "cpu"),
+        "cpu_baseline": {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": r["clips_per_s"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world, engine):
+    return {"workload": f"cfg2: B={args.batch} source + {args.batch} target videos per GPU, T={args.segments}, "
+                        f"D={D}, fc_dim={args.fc_dim}, {args.classes} classes, TRN-M + TransAttn + RevGrad "
+                        f"discriminators (frame/video/relation)",
+            "global_batch": 2 * args.batch * world, "per_gpu_clips": 2 * args.batch,
+            "step": "forward + composed loss + backward to all parameter gradients"
+                    + (" + flat NCCL gradient all-reduce" if world > 1 else ""),
+            "optimizer": "excluded from value (metric is fwd+bwd); included in e2e",
+            "dropout": "0.5/0.5, in-kernel counter RNG", "gemm_engine": engine,
+            "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) before every timed step"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import ta3n_b200
+    from ta3n_b200 import _lib
+    from ta3n_b200.loss import ta3n_loss
+    from ta3n_b200.models import VideoModel
+    from ta3n_b200.parallel import GradientBucket
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    engine = pick_engine(args.engine)
+
+    B, T, C, F = args.batch, args.segments, args.classes, min(args.fc_dim, D)
+    torch.manual_seed(1234)
+    model = VideoModel(C, "video", "trn-m", "RGB", train_segments=T, val_segments=T, add_fc=1, fc_dim=args.fc_dim,
+                       dropout_i=0.5, dropout_v=0.5, partial_bn=False, use_bn="none", ens_DA="none",
+                       use_attn="TransAttn", use_attn_frame="none", share_params="Y", verbose=False).to(dev).train()
+    bucket = GradientBucket(model.parameters())
+    opt = torch.optim.SGD(model.parameters(), 3e-2, momentum=0.9, weight_decay=1e-4, nesterov=True)
+
+    g = torch.Generator().manual_seed(4321 + rank)
+    xs_h = torch.randn(B, T, D, generator=g).pin_memory()
+    xt_h = torch.randn(B, T, D, generator=g).pin_memory()
+    lab_h = (torch.arange(B) % C).pin_memory()
+    xs, xt, labels = xs_h.to(dev), xt_h.to(dev), lab_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(a, b, y):
+        model.zero_grad(set_to_none=True)
+        outs = model(a, b, list(BETA), 0, is_train=True, reverse=False)
+        loss = ta3n_loss(outs, y, GAMMA)
+        loss.backward()
+        bucket.allreduce_mean()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(xs, xt, labels)
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- value: inputs resident in HBM, device-timed with CUDA events, L2 flushed before each step
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    _lib.reset_launch_count()
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record()
+        step(xs, xt, labels)
+        ev[k][1].record()
+    barrier()
+    launches = _lib.launch_count()
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([t_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms = float(t.item())
+    clocks = sampler.finish() if sampler else None
+
+    # ---- e2e: host (pinned) inputs -> public API -> loss on the host, optimizer step included
+    def e2e_step():
+        loss = step(xs_h, xt_h, lab_h.to(dev, non_blocking=True))     # VideoModel.forward does the H2D copies
+        opt.step()
+        return loss.item()                                            # D2H read of the step's result
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+
+    # ---- roofline: per-call-site device time (CUDA events inside the library, separate pass)
+    _lib.timing_enable(True)
+    barrier()
+    n_prof = min(args.steps, 10)
+    for k in range(n_prof):
+        flush.fill_(k & 0xFF)
+        step(xs, xt, labels)
+    torch.cuda.synchronize()
+    rep = _lib.timing_report()
+    _lib.timing_enable(False)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tf_peak, peak_kind = measured_peaks()
+    M = 2 * B
+    tm = traffic_model(M, T, F, C)
+    step_ms = t_ms / args.steps
+    total_site_ms = sum(ms for _, ms in rep.values()) or 1.0
+    dom = max((k for k in rep if k in tm["sites"]), key=lambda k: rep[k][1], default=None)
+    roof = None
+    if dom:
+        cnt, ms = rep[dom]
+        per_step_ms = ms / n_prof                      # all launches of this call site in one step
+        ach = tm["sites"][dom] / (per_step_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_step": tm["sites"][dom], "kernel_ms_per_step": per_step_ms,
+                "share_of_library_time": ms / total_site_ms, "launches_per_step": cnt / n_prof}
+    ach_b = tm["scope_b"] / (step_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": world * 2 * B * args.steps / (t_ms * 1e-3), "unit": "clips/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if engine == "fp32" else "tf32",
+        "data": "synthetic", "config": workload_config(args, world, engine),
+        "roofline": roof,
+        "roofline_step": {"bound": "hbm", "scope": "whole step (SURVEY 8d scope B)", "achieved": ach_b,
+                          "peak": hbm_peak, "unit": "GB/s", "frac": ach_b / hbm_peak,
+                          "algorithmic_bytes": tm["scope_b"], "algorithmic_flops": tm["flops_b"],
+                          "achieved_tflops": tm["flops_b"] / (step_ms * 1e-3) / 1e12, "peak_kind": peak_kind},
+        "kernel_ms_per_step": {k: round(v[1] / n_prof, 5) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])},
+        "e2e": {"value": world * 2 * B * args.steps / e2e_s, "unit": "clips/s",
+                "h2d_bytes_per_step": int(2 * B * T * D * 4 + B * 8), "d2h_bytes_per_step": 4,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "includes": "H2D of inputs, forward, loss, backward, "
+                "all-reduce, SGD step, D2H of the loss"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args, 1000, 2, budget_s=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "kind": "port",
+                                "ms_per_step": r["ms_per_step"],
+                                "sample": f"{r['steps']} full steps (B={B}+{B}) of the oracle port on the host "
+                                          f"cores, ~{args.cpu_seconds:.0f}s budget"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,11 @@ void ta3n_reset_launch_count(void);
 /* select the GEMM engine used by subsequent calls (process-wide). */
 int ta3n_set_gemm_engine(int engine);
 int ta3n_get_gemm_engine(void);
+/* Per-call-site device timing (CUDA events on the launching stream, eager mode only; not for use
+ * under graph capture).  ta3n_timing_report synchronises the recorded events, writes lines
+ * "label count total_ms\n" to buf, clears the registry and returns the bytes needed.           */
+void ta3n_timing_enable(int on);
+size_t ta3n_timing_report(char* buf, size_t buf_bytes);
 
 /* ---- shared frame layer: Dropout(ReLU(x W^T + b))  (models.py:565-575) ------------- */
 /* x_src [rows_src, D], x_tgt [rows_tgt, D] (rows = videos*T); feat [rows_src+rows_tgt, F] */

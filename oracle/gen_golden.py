@@ -82,14 +82,16 @@ def checksum(t: torch.Tensor) -> np.ndarray:
     return np.array([d.sum().item(), d.norm().item()])
 
 
-def run_reference(c):
+def run_reference(c, dtype=torch.float32):
     ref_models, _, ref_loss = ref_shims.load()
     cfg, xs, xt, labels, masks = case_inputs(c)
+    xs, xt = xs.to(dtype), xt.to(dtype)
     torch.manual_seed(MODEL_SEED)
     model = ref_models.VideoModel(c["C"], "video", "trn-m", "RGB", train_segments=c["T"], val_segments=c["T"],
                                   add_fc=1, fc_dim=c["F"], dropout_i=DROPOUT, dropout_v=DROPOUT,
                                   partial_bn=False, use_bn="none", ens_DA="none", use_attn=c["use_attn"],
                                   n_attn=1, use_attn_frame=c["attn_frame"], share_params="Y", verbose=False)
+    model = model.to(dtype)
     if c["train"]:
         model.train()
         model.dropout_i = ref_shims.InjectedDropout(DROPOUT, [masks["i_source"], masks["i_target"]])
@@ -122,9 +124,14 @@ def main():
             "torch": torch.__version__}
     for name, c in CASES.items():
         model, outs, loss, (xs, xt) = run_reference(c)
+        # the same reference in float64: |fp32 - fp64| is the reference's own rounding noise, stored
+        # per tensor so that tests can tell cancellation noise from real disagreement
+        model64, outs64, loss64, _ = run_reference(c, torch.float64)
+        grads64 = {n: p.grad for n, p in model64.named_parameters()}
         (attn_s, out_s, _, pd_s, feat_s, attn_t, out_t, _, pd_t, feat_t) = outs
         k = name + "/"
         blob[k + "loss"] = np.array(loss.item())
+        blob[k + "noise/loss"] = np.array(abs(loss.item() - loss64.item()))
         blob[k + "in_checksum"] = np.concatenate([checksum(xs), checksum(xt)])
         for dom, attn, out, pd, feat in (("s", attn_s, out_s, pd_s, feat_s), ("t", attn_t, out_t, pd_t, feat_t)):
             blob[k + f"attn_{dom}"] = attn.detach().numpy()
@@ -143,6 +150,9 @@ def main():
             used.append(pname)
             blob[k + "grad_norm/" + pname] = np.array(prm.grad.double().norm().item())
             blob[k + "grad_sample/" + pname] = sample(prm.grad)
+            blob[k + "grad_noise/" + pname] = np.array((prm.grad.double() - grads64[pname]).norm().item())
+            blob[k + "grad_sample_noise/" + pname] = np.array(
+                np.linalg.norm(sample(prm.grad) - sample(grads64[pname])))
         meta.setdefault("used_params", {})[name] = used
         print(f"{name}: loss={loss.item():.8f} used_params={len(used)}")
     blob["meta_json"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)

@@ -38,6 +38,8 @@ SIGNATURES = {
     "ta3n_reset_launch_count": (None, []),
     "ta3n_set_gemm_engine": (_I, [_I]),
     "ta3n_get_gemm_engine": (_I, []),
+    "ta3n_timing_enable": (None, [_I]),
+    "ta3n_timing_report": (_SZ, [C.c_char_p, _SZ]),
     "ta3n_shared_fc_fwd": (_I, [_VP, _I, _VP, _I, _I, _VP, _VP, _I, _DRP, _VP, _VP]),
     "ta3n_shared_fc_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ta3n_shared_fc_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _VP, _VP, _VP, _F, _VP, _VP, _VP, _SZ, _VP]),
@@ -122,3 +124,18 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     load().ta3n_reset_launch_count()
+
+
+def timing_enable(on: bool) -> None:
+    load().ta3n_timing_enable(int(bool(on)))
+
+
+def timing_report() -> dict:
+    """{label: (count, total_ms)} of the launches recorded since timing was enabled (synchronises)."""
+    buf = C.create_string_buffer(1 << 16)
+    load().ta3n_timing_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        label, count, ms = line.split()
+        out[label] = (int(count), float(ms))
+    return out

@@ -9,6 +9,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "../../include/ta3n_b200.h"
 
@@ -54,8 +57,56 @@ inline std::atomic<uint64_t>& launch_counter() {
   return n;
 }
 
+// ---- optional per-launch timing (CUDA events on the launching stream; eager mode only) --------
+// bench.py switches this on for a separate pass to attribute device time to each call site.
+struct TimingRegistry {
+  struct Rec {
+    const char* label;
+    cudaEvent_t a, b;
+  };
+  std::mutex mu;
+  std::atomic<bool> enabled{false};
+  std::vector<Rec> recs;
+};
+inline TimingRegistry& timing() {
+  static TimingRegistry t;
+  return t;
+}
+struct PendingTimer {
+  bool active = false;
+  cudaEvent_t stop = nullptr;
+  cudaStream_t stream = nullptr;
+};
+inline PendingTimer& pending_timer() {
+  static thread_local PendingTimer p;
+  return p;
+}
+
+// call right before a kernel launch
+inline void pre_launch(const char* label, cudaStream_t stream) {
+  TimingRegistry& t = timing();
+  if (!t.enabled.load(std::memory_order_relaxed)) return;
+  TimingRegistry::Rec r;
+  r.label = label;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, stream);
+  {
+    std::lock_guard<std::mutex> g(t.mu);
+    t.recs.push_back(r);
+  }
+  PendingTimer& p = pending_timer();
+  p.active = true;
+  p.stop = r.b;
+  p.stream = stream;
+}
+
 inline int after_launch() {
   launch_counter().fetch_add(1, std::memory_order_relaxed);
+  PendingTimer& p = pending_timer();
+  if (p.active) {
+    cudaEventRecord(p.stop, p.stream);
+    p.active = false;
+  }
   cudaError_t e = cudaGetLastError();  // launch-configuration errors only; never synchronises
   if (e != cudaSuccess) return fail(TA3N_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return TA3N_OK;

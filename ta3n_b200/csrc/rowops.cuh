@@ -364,6 +364,7 @@ struct ColsumPlan {
       }
       if (maxN == 0) continue;
       dim3 grid((maxN + 31) / 32, tab.n_jobs), block(32, 32);
+      pre_launch("colsum", stream);
       colsum_kernel<<<grid, block, 0, stream>>>(tab);
       TA3N_TRY(after_launch());
     }

@@ -303,6 +303,7 @@ struct GemmPlan {
   std::vector<Seg> segs;     // group.seg_begin indexes into this vector
   bool a_kmaj = true, b_kmaj = true;
   int load_flags = 0;
+  const char* label = "seg_gemm";   // call-site name used by the timing registry
 
   // add a group; its segments must be pushed right after with add_seg
   Group& add_group(int M, int N, float* C, int ldc) {
@@ -386,6 +387,7 @@ inline int launch_simt(const GemmPlan& plan, cudaStream_t stream) {
     tab.n_groups = ng;
     tab.total_tiles = tiles;
     if (tiles > 0) {
+      pre_launch(plan.label, stream);
       if (plan.a_kmaj && plan.b_kmaj)
         seg_gemm_simt_kernel<true, true><<<tiles, SG_THREADS, 0, stream>>>(tab);
       else if (plan.a_kmaj && !plan.b_kmaj)
@@ -397,6 +399,7 @@ inline int launch_simt(const GemmPlan& plan, cudaStream_t stream) {
       TA3N_TRY(after_launch());
       if (any_split) {
         dim3 grid(32, ng);
+        pre_launch("splitk_reduce", stream);
         splitk_reduce_kernel<<<grid, 256, 0, stream>>>(tab);
         TA3N_TRY(after_launch());
       }

@@ -99,6 +99,53 @@ int ta3n_set_gemm_engine(int engine) {
 }
 int ta3n_get_gemm_engine(void) { return gemm_engine().load(); }
 
+void ta3n_timing_enable(int on) { timing().enabled.store(on != 0); }
+
+// Synchronises the recorded events, aggregates device time per call-site label and writes lines
+// "label count total_ms\n" into buf.  Returns the number of bytes needed (excluding the NUL).
+size_t ta3n_timing_report(char* buf, size_t buf_bytes) {
+  TimingRegistry& t = timing();
+  std::vector<TimingRegistry::Rec> recs;
+  {
+    std::lock_guard<std::mutex> g(t.mu);
+    recs.swap(t.recs);
+  }
+  struct Agg {
+    const char* label;
+    int count;
+    double ms;
+  };
+  std::vector<Agg> agg;
+  for (auto& r : recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      bool found = false;
+      for (auto& a : agg)
+        if (strcmp(a.label, r.label) == 0) {
+          a.count++;
+          a.ms += ms;
+          found = true;
+          break;
+        }
+      if (!found) agg.push_back({r.label, 1, (double)ms});
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  std::string out;
+  char line[160];
+  for (auto& a : agg) {
+    snprintf(line, sizeof(line), "%s %d %.6f\n", a.label, a.count, a.ms);
+    out += line;
+  }
+  if (buf && buf_bytes > 0) {
+    size_t n = out.size() < buf_bytes - 1 ? out.size() : buf_bytes - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return out.size();
+}
+
 // ------------------------------------------------------------------------------------------------
 // shared frame layer                                                        models.py:565-575
 // ------------------------------------------------------------------------------------------------
@@ -110,6 +157,7 @@ int ta3n_shared_fc_fwd(const float* x_src, int rows_src, const float* x_tgt, int
   TA3N_REQUIRE((rows_src == 0 || x_src) && (rows_tgt == 0 || x_tgt), "null input");
   const DropArgs d = make_drop(drop);
   GemmPlan plan;
+    plan.label = "shared_fc_fwd";
   const float* xs[2] = {x_src, x_tgt};
   const int rows[2] = {rows_src, rows_tgt};
   size_t row0 = 0;
@@ -144,11 +192,13 @@ int ta3n_shared_fc_bwd(const float* x_src, int rows_src, const float* x_tgt, int
     return TA3N_OK;
   }
   const size_t total = (size_t)rows * F;
+  pre_launch("dpre", S(stream));
   dpre_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(feat, dfeat, g_feat_ext, 1.0f / (1.0f - p), total);
   TA3N_TRY(after_launch());
 
   Arena arena(workspace, workspace_bytes);
   GemmPlan plan;
+    plan.label = "shared_fc_wgrad";
   plan.a_kmaj = false;
   plan.b_kmaj = false;
   plan.add_group(F, D, dW, D);
@@ -171,11 +221,13 @@ int ta3n_disc_fwd(const float* x, int rows, int K, int Kh, const float* W1, cons
   if (rows == 0) return TA3N_OK;
   TA3N_REQUIRE(x && W1 && b1 && W2 && b2 && hidden && logits, "null pointer");
   GemmPlan plan;
+    plan.label = "disc_fwd";
   Group& g = plan.add_group(rows, Kh, hidden, Kh);
   g.flags = EPI_BIAS | EPI_RELU;
   g.bias = b1;
   plan.add_seg(x, K, W1, K, K);
   TA3N_TRY(run_gemm(plan, S(stream)));
+  pre_launch("head_fwd", S(stream));
   head_fwd_kernel<<<blocks_for((size_t)rows * 32, 256), 256, 0, S(stream)>>>(hidden, Kh, W2, b2, logits, 2, rows,
                                                                              Kh, 2);
   return after_launch();
@@ -207,12 +259,14 @@ int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, cons
   if (!dH) return fail(TA3N_ERR_WORKSPACE, "ta3n_disc_bwd: workspace too small (%zu bytes)", workspace_bytes);
 
   // dH = (g_logits W2) * 1[hidden > 0]
+  pre_launch("head_bwd_data", st);
   head_bwd_data_kernel<<<blocks_for((size_t)rows * Kh, 256), 256, 0, st>>>(g_logits, 2, W2, hidden, 1.0f, 0, dH,
                                                                            rows, Kh);
   TA3N_TRY(after_launch());
 
   {  // dW2 [2,Kh] = g_logits^T hidden ; dW1 [Kh,K] = dH^T x
     GemmPlan plan;
+    plan.label = "disc_wgrad";
     plan.a_kmaj = false;
     plan.b_kmaj = false;
     plan.add_group(2, Kh, dW2, Kh);
@@ -231,6 +285,7 @@ int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, cons
   }
   if (dx) {  // dx (+)= -beta * dH W1
     GemmPlan plan;
+    plan.label = "disc_dgrad";
     plan.a_kmaj = true;
     plan.b_kmaj = false;
     Group& g = plan.add_group(rows, K, dx, K);
@@ -245,6 +300,7 @@ int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, cons
 int ta3n_grl_bwd(const float* g, float beta, float* out, size_t n, ta3n_stream_t stream) {
   if (n == 0) return TA3N_OK;
   TA3N_REQUIRE(g && out, "null pointer");
+  pre_launch("grl_bwd", S(stream));
   grl_bwd_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(g, beta, out, n);
   return after_launch();
 }
@@ -257,6 +313,7 @@ int ta3n_frame_attn_fwd(const float* feat, const float* logits, int rows, int F,
   TA3N_REQUIRE(rows >= 0 && F > 0, "bad sizes");
   if (rows == 0) return TA3N_OK;
   TA3N_REQUIRE(feat && logits && out, "null pointer");
+  pre_launch("frame_attn_fwd", S(stream));
   frame_attn_fwd_kernel<<<blocks_for((size_t)rows * F, 256), 256, 0, S(stream)>>>(feat, logits, rows, F, out);
   return after_launch();
 }
@@ -266,6 +323,7 @@ int ta3n_frame_attn_bwd(const float* feat, const float* logits, int rows, int F,
   TA3N_REQUIRE(rows >= 0 && F > 0, "bad sizes");
   if (rows == 0) return TA3N_OK;
   TA3N_REQUIRE(feat && logits && d_out && g_logits, "null pointer");
+  pre_launch("frame_attn_bwd", S(stream));
   frame_attn_bwd_kernel<<<blocks_for((size_t)rows * 32, 256), 256, 0, S(stream)>>>(feat, logits, rows, F, d_out,
                                                                                    g_logits);
   return after_launch();
@@ -284,6 +342,7 @@ int ta3n_trn_fwd(const float* x, int M, int F, int H, const ta3n_relation_table*
   TA3N_REQUIRE(x && W_host && b_host && act && feat_rel, "null pointer");
   const int ldx = L.T * F;
   GemmPlan plan;
+    plan.label = "trn_fwd";
   plan.load_flags = relu_input ? LD_RELU_A : 0;
   for (int q = 0; q < L.n_rel; ++q) {
     const int i = L.rel_scale[q], s = L.scale_size[i];
@@ -298,6 +357,7 @@ int ta3n_trn_fwd(const float* x, int M, int F, int H, const ta3n_relation_table*
   }
   TA3N_TRY(run_gemm(plan, S(stream)));
   const RelMap map = make_relmap(L);
+  pre_launch("relsum", S(stream));
   relsum_kernel<<<blocks_for((size_t)M * L.R * H, 256), 256, 0, S(stream)>>>(act, feat_rel, M, H, map);
   return after_launch();
 }
@@ -333,11 +393,13 @@ int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table*
   if (!dz) return fail(TA3N_ERR_WORKSPACE, "ta3n_trn_bwd: workspace too small (%zu bytes)", workspace_bytes);
 
   const RelMap map = make_relmap(L);
+  pre_launch("dz", st);
   dz_kernel<<<blocks_for(plane * L.n_rel, 256), 256, 0, st>>>(act, d_feat_rel, dz, M, H, map);
   TA3N_TRY(after_launch());
 
   {  // wgrad: dW_i[:, jF:(j+1)F] = sum_r dz_{i,r}^T x[:, tau_{i,r}[j], :]
     GemmPlan plan;
+    plan.label = "trn_wgrad";
     plan.a_kmaj = false;
     plan.b_kmaj = false;
     plan.load_flags = relu_input ? LD_RELU_B : 0;
@@ -364,6 +426,7 @@ int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table*
   }
   if (dx) {  // dgrad, deterministic per frame: dx[:, t, :] = sum_{(q,j): tau_q[j]=t} dz_q W_i[:, jF:(j+1)F]
     GemmPlan plan;
+    plan.label = "trn_dgrad";
     plan.a_kmaj = true;
     plan.b_kmaj = false;
     std::vector<int> untouched;
@@ -407,6 +470,7 @@ int ta3n_relattn_fwd(const float* feat_rel, int M, int R, int H, const float* co
   TA3N_REQUIRE(feat_rel && W1_host && b1_host && W2_host && b2_host && hidden && pred_rel && attn && feat_video,
                "null pointer");
   GemmPlan plan;
+    plan.label = "relattn_fwd";
   PtrTable w2, b2;
   memset(&w2, 0, sizeof(w2));
   memset(&b2, 0, sizeof(b2));
@@ -420,6 +484,7 @@ int ta3n_relattn_fwd(const float* feat_rel, int M, int R, int H, const float* co
     b2.p[i] = b2_host[i];
   }
   TA3N_TRY(run_gemm(plan, S(stream)));
+  pre_launch("relattn_fwd", S(stream));
   relattn_fwd_kernel<<<blocks_for((size_t)M * 32, 256), 256, 0, S(stream)>>>(feat_rel, hidden, M, R, H, w2, b2,
                                                                              use_attn, pred_rel, attn, feat_video);
   return after_launch();
@@ -459,12 +524,14 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
   PtrTable w2;
   memset(&w2, 0, sizeof(w2));
   for (int i = 0; i < R; ++i) w2.p[i] = W2_host[i];
+  pre_launch("relattn_bwd_pre", st);
   relattn_bwd_pre_kernel<<<blocks_for((size_t)M * 32, 256), 256, 0, st>>>(
       feat_rel, hidden, pred_rel, g_feat_video, g_pred_rel, g_attn, M, R, H, w2, use_attn, Pt, dHid);
   TA3N_TRY(after_launch());
 
   {  // weight gradients of both layers of every relation discriminator
     GemmPlan plan;
+    plan.label = "relattn_wgrad";
     plan.a_kmaj = false;
     plan.b_kmaj = false;
     for (int i = 0; i < R; ++i) {
@@ -487,6 +554,7 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
   }
   {  // d_feat_rel[:, i, :] = (w_i + 1) G - beta * dHid_i W1_i
     GemmPlan plan;
+    plan.label = "relattn_dgrad";
     plan.a_kmaj = true;
     plan.b_kmaj = false;
     for (int i = 0; i < R; ++i) {
@@ -505,6 +573,7 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
     TA3N_TRY(run_gemm(plan, st));
   }
   if (!use_attn && g_attn) {
+    pre_launch("attn_placeholder_bwd", st);
     attn_placeholder_bwd_kernel<<<blocks_for((size_t)M * R, 256), 256, 0, st>>>(g_attn, d_feat_rel, M, R, H);
     TA3N_TRY(after_launch());
   }
@@ -520,8 +589,10 @@ int ta3n_video_head_fwd(const float* feat_video, int M, int H, int C, const floa
   if (M == 0) return TA3N_OK;
   TA3N_REQUIRE(feat_video && Wc && bc && dropped && pred, "null pointer");
   const DropArgs d = make_drop(drop);
+  pre_launch("video_drop_fwd", S(stream));
   video_drop_fwd_kernel<<<blocks_for((size_t)M * H, 256), 256, 0, S(stream)>>>(feat_video, dropped, (size_t)M * H, d);
   TA3N_TRY(after_launch());
+  pre_launch("head_fwd", S(stream));
   head_fwd_kernel<<<blocks_for((size_t)M * 32, 256), 256, 0, S(stream)>>>(dropped, H, Wc, bc, pred, C, M, H, C);
   return after_launch();
 }
@@ -545,6 +616,7 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
   if (M == 0) return TA3N_OK;
   TA3N_REQUIRE(dropped && Wc && d_feat_video, "null pointer");
   const DropArgs d = make_drop(drop);
+  pre_launch("video_head_bwd", st);
   video_head_bwd_kernel<<<blocks_for((size_t)M * H, 256), 256, 0, st>>>(g_pred, C, Wc, d_dropped_extra,
                                                                          g_feat_video_ext, grad_scale, d,
                                                                          d_feat_video, M, H);
@@ -552,6 +624,7 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
   if (g_pred) {
     Arena arena(workspace, workspace_bytes);
     GemmPlan plan;
+    plan.label = "video_head_wgrad";
     plan.a_kmaj = false;
     plan.b_kmaj = false;
     plan.add_group(C, H, dWc, H);
@@ -569,6 +642,7 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
 int ta3n_gemm_tn(const float* A, const float* B, float* C, int M, int N, int K, ta3n_stream_t stream) {
   TA3N_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bad arguments");
   GemmPlan plan;
+    plan.label = "gemm_tn";
   plan.add_group(M, N, C, N);
   plan.add_seg(A, K, B, K, K);
   return run_gemm(plan, S(stream));

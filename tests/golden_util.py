@@ -31,10 +31,24 @@ def rel_err(a, b) -> float:
     return num / den if den > 0 else num
 
 
-def assert_close(a, b, tol, what=""):
-    e = rel_err(a, b)
-    assert e <= tol, f"{what}: normwise rel err {e:.3e} > {tol:.1e}"
-    return e
+def abs_err(a, b) -> float:
+    a = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).detach().double().cpu().reshape(-1)
+    b = torch.as_tensor(np.asarray(b) if not torch.is_tensor(b) else b).detach().double().cpu().reshape(-1)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return (a - b).norm().item()
+
+
+def assert_close(a, b, tol, what="", noise=0.0):
+    """||a-b|| <= tol*||b|| + 8*noise, where ``noise`` is the reference's own fp32 rounding error
+    ||ref_fp32 - ref_fp64|| for this tensor (matters only for sums that cancel, e.g. the bias
+    gradients of the domain heads, whose source and target halves have opposite signs)."""
+    b_t = torch.as_tensor(np.asarray(b) if not torch.is_tensor(b) else b).detach().double().cpu()
+    d = abs_err(a, b)
+    den = b_t.norm().item()
+    bound = tol * den + 8.0 * float(noise)
+    assert d <= bound or (den == 0 and d == 0), \
+        f"{what}: ||diff||={d:.3e} > {tol:.1e}*||ref||({den:.3e}) + 8*noise({float(noise):.3e})"
+    return d / den if den > 0 else d
 
 
 def sample(t: torch.Tensor, stride: int):
@@ -68,9 +82,11 @@ def check_grads_against_golden(z, case: str, grads: dict, used: list, tol: float
         g = grads[name]
         assert g is not None, f"{case}: no grad for {name}"
         ref_norm = float(z[f"{case}/grad_norm/{name}"])
+        noise = float(z[f"{case}/grad_noise/{name}"])
         got_norm = g.detach().double().norm().item()
-        assert abs(got_norm - ref_norm) <= tol * max(ref_norm, 1e-30), \
-            f"{case}: grad norm {name}: {got_norm:.6e} vs {ref_norm:.6e}"
+        assert abs(got_norm - ref_norm) <= tol * ref_norm + 8 * noise, \
+            f"{case}: grad norm {name}: {got_norm:.6e} vs {ref_norm:.6e} (noise {noise:.2e})"
         worst = max(worst, assert_close(sample(g, stride), z[f"{case}/grad_sample/{name}"], tol * 4,
-                                        f"{case}:grad_sample:{name}"))
+                                        f"{case}:grad_sample:{name}",
+                                        noise=float(z[f"{case}/grad_sample_noise/{name}"])))
     return worst

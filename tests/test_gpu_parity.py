@@ -10,7 +10,7 @@ import torch
 
 from oracle import gen_golden
 from oracle import ta3n_oracle as orc
-from tests.golden_util import (TOL_PATH, assert_close, check_grads_against_golden,
+from tests.golden_util import (TOL_PATH, abs_err, assert_close, check_grads_against_golden,
                                check_outputs_against_golden, load_golden, rel_err)
 
 pytestmark = pytest.mark.gpu
@@ -65,6 +65,17 @@ def flat_outputs(outs):
     return [outs[0], outs[1], *outs[3], *outs[4], outs[5], outs[6], *outs[8], *outs[9]]
 
 
+def oracle_truth(params, xs, xt, labels, beta, cfg, gamma, train, masks):
+    """Oracle in fp64 (truth) and fp32; ||fp32 - fp64|| per tensor is the rounding-noise floor that
+    any fp32 implementation of the same math carries (large only where sums cancel)."""
+    p64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in params.items()}
+    l64, o64, g64 = orc.train_step(p64, xs.double(), xt.double(), labels, beta, cfg, gamma, train=train, masks=masks)
+    l32, o32, g32 = orc.train_step(params, xs, xt, labels, beta, cfg, gamma, train=train, masks=masks)
+    out_noise = [abs_err(a, b) for a, b in zip(flat_outputs(o32), flat_outputs(o64))]
+    grad_noise = {k: abs_err(g32[k], g64[k]) for k in g64}
+    return l64, o64, g64, abs(l32.item() - l64.item()), out_noise, grad_noise
+
+
 # ------------------------------------------------------------------------------------------------
 # golden vectors (made by the unmodified reference, tests/golden/ta3n_golden.npz)
 # ------------------------------------------------------------------------------------------------
@@ -105,16 +116,17 @@ def test_model_matches_oracle_mid_size(T, attn_frame, bs, bt, engine):
     masks = {"i_source": keep(bs * T, 512), "i_target": keep(bt * T, 512),
              "v_source": keep(bs, 256), "v_target": keep(bt, 256)}
     beta = (0.75, 0.6, 0.5)
-    loss_o, outs_o, grads_o = orc.train_step(params, xs, xt, labels, beta, cfg, 0.003, train=True, masks=masks)
+    loss_o, outs_o, grads_o, n_loss, n_out, n_grad = oracle_truth(params, xs, xt, labels, beta, cfg, 0.003,
+                                                                   True, masks)
     model = build_model(cfg, params, train=True)
     loss, outs, grads = run_cuda_step(model, xs, xt, labels, beta, 0.003, masks)
     tol = TOL[engine]
-    assert_close(loss, loss_o, tol, "loss")
+    assert_close(loss, loss_o, tol, "loss", noise=n_loss)
     for i, (a, b) in enumerate(zip(flat_outputs(outs), flat_outputs(outs_o))):
         assert a.shape == b.shape
-        assert_close(a, b, tol, f"output {i}")
+        assert_close(a, b, tol, f"output {i}", noise=n_out[i])
     for name, go in grads_o.items():
-        assert_close(grads[name], go, tol * 2, f"grad {name}")
+        assert_close(grads[name], go, tol * 2, f"grad {name}", noise=n_grad[name])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -126,12 +138,12 @@ def test_trn_module_matches_oracle(T, F, N, engine):
     torch.manual_seed(3)
     mod = RelationModuleMultiScale(F, 256, T).to(_dev())
     x = torch.randn(N, T, F)
-    ws = [s[1].weight.detach().cpu().clone().requires_grad_(True) for s in mod.fc_fusion_scales]
-    bs = [s[1].bias.detach().cpu().clone().requires_grad_(True) for s in mod.fc_fusion_scales]
-    xo = x.clone().requires_grad_(True)
+    ws = [s[1].weight.detach().cpu().double().requires_grad_(True) for s in mod.fc_fusion_scales]
+    bs = [s[1].bias.detach().cpu().double().requires_grad_(True) for s in mod.fc_fusion_scales]
+    xo = x.double().requires_grad_(True)
     ref = orc.trn_multiscale(xo, ws, bs, orc.relation_tuples(T))
     gout = torch.randn(ref.shape)
-    ref.backward(gout)
+    ref.backward(gout.double())
     xg = x.to(_dev()).requires_grad_(True)
     out = mod(xg)
     out.backward(gout.to(_dev()))
@@ -227,7 +239,8 @@ def test_full_size_gradient_shards_sum_to_full_batch(engine):
     h0, h1 = grads_of(slice(0, 128)), grads_of(slice(128, 256))
     tol = 5e-4 if engine == "fp32" else 2 * TOL_PATH
     for k in full:
-        assert_close(0.5 * (h0[k] + h1[k]), full[k], tol, f"shard-sum {k}")
+        # noise floor: the domain-head bias gradients are sums of opposite-sign halves (~1e-7 left)
+        assert_close(0.5 * (h0[k] + h1[k]), full[k], tol, f"shard-sum {k}", noise=2e-8)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -240,11 +253,16 @@ def test_single_video_and_empty_target():
     xs = torch.randn(1, 5, orc.FEATURE_DIM)
     xt = torch.randn(0, 5, orc.FEATURE_DIM)
     outs = model(xs.to(_dev()), xt.to(_dev()), [1, 1, 1], 0, True, False)
-    ref = orc.forward(params, xs, xt, [1, 1, 1], 0.0, cfg, train=True)
-    for a, b in zip(flat_outputs(outs), flat_outputs(ref)):
+    # the reference (and so the oracle) cannot reshape an empty batch; rows are independent, so the
+    # source half is checked against an oracle run with a stand-in target and the target half must be empty
+    ref = orc.forward(params, xs, xs, [1, 1, 1], 0.0, cfg, train=True)
+    fo, fr = flat_outputs(outs), flat_outputs(ref)
+    half = len(fo) // 2
+    for a, b in zip(fo[:half], fr[:half]):
         assert a.shape == b.shape
-        if b.numel():
-            assert_close(a, b, 2e-4, "single video")
+        assert_close(a, b, 2e-4, "single video")
+    for a, b in zip(fo[half:], fr[half:]):
+        assert a.shape[0] == 0 and a.shape[1:] == b.shape[1:]
     outs[1].sum().backward()
     assert model.fc_feature_shared_source.weight.grad is not None
 
@@ -282,15 +300,15 @@ def test_reverse_flag_scales_trunk_gradient_by_minus_mu():
             outs = model(xs.to(_dev()), xt.to(_dev()), [0.75, 0.75, 0.5], mu, True, reverse)
             (outs[1].sum() + outs[6].sum() + outs[3][1].sum()).backward()
             return model.TRN.fc_fusion_scales[0][1].weight.grad.cpu(), model.fc_classifier_video_source.weight.grad.cpu()
-        leaves = {k: v.clone().requires_grad_(True) for k, v in params.items() if v.dtype.is_floating_point}
-        outs = orc.forward(leaves, xs, xt, [0.75, 0.75, 0.5], mu, cfg, train=True, reverse=reverse)
+        leaves = {k: v.double().requires_grad_(True) for k, v in params.items() if v.dtype.is_floating_point}
+        outs = orc.forward(leaves, xs.double(), xt.double(), [0.75, 0.75, 0.5], mu, cfg, train=True, reverse=reverse)
         (outs[1].sum() + outs[6].sum() + outs[3][1].sum()).backward()
         return leaves["TRN.fc_fusion_scales.0.1.weight"].grad, leaves["fc_classifier_video_source.weight"].grad
 
     for mu, rev in [(0.0, False), (0.7, True), (0.0, True)]:
         a, b = run(True, mu, rev), run(False, mu, rev)
         for u, v in zip(a, b):
-            assert_close(u, v, 5e-4, f"reverse mu={mu} rev={rev}")
+            assert_close(u, v, 5e-4, f"reverse mu={mu} rev={rev}", noise=1e-9)
 
 
 def test_cpu_tensors_are_moved_not_computed_on_cpu():
