@@ -182,6 +182,11 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
 /* C[M,N] = A[M,K] * B[N,K]^T with the selected engine; A, B, C row-major fp32.           */
 int ta3n_gemm_tn(const float* A, const float* B, float* C, int M, int N, int K,
                  ta3n_stream_t stream);
+/* General form: a_kmajor ? A(m,k)=A[m*lda+k] : A(m,k)=A[k*lda+m];  b_kmajor ? B(k,n)=B[n*ldb+k] :
+ * B(k,n)=B[k*ldb+n].  workspace (optional) enables deterministic split-K.                 */
+int ta3n_gemm_ex(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor,
+                 float* C, int ldc, int M, int N, int K, void* workspace, size_t workspace_bytes,
+                 ta3n_stream_t stream);
 
 #ifdef __cplusplus
 }

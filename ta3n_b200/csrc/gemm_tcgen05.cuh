@@ -1,13 +1,498 @@
-// gemm_tcgen05.cuh -- tcgen05 (5th-gen tensor core) engine for the segmented grouped GEMM.
-// Placeholder until the engine lands: declines every plan so the SIMT engine runs it.
+// gemm_tcgen05.cuh -- 5th-generation tensor-core engine for the segmented grouped GEMM.
+//
+// One CTA per 128 x 128 output tile (2 CTAs resident per SM), warp-specialised:
+//   warp 0     : TMA producer  -- cp.async.bulk.tensor.2d into a 3-stage ring of 128B-swizzled tiles
+//   warp 1     : TMEM allocator + single-thread tcgen05.mma.kind::tf32 issuer (fp32 accum in TMEM)
+//   warps 2..5 : epilogue      -- tcgen05.ld (32 lanes x 32 columns), transpose through smem,
+//                                 fused epilogue (apply_epilogue) with coalesced 128 B row stores
+// Operands stay fp32 in HBM: kind::tf32 reads the fp32 bit patterns directly (10-bit mantissa,
+// fp32 range), so there is no conversion pass and no second copy of any tensor.
+// The "gather" of TRN frame tuples, the source/target split and the per-frame dgrad are all
+// expressed as TMA coordinates / tensor maps per K-segment: nothing is materialised.
+//
+// Both operand majors are supported through the UMMA smem descriptors:
+//   K-major  (A(m,k)=A[m*ld+k]) : one TMA box {32 k, 128 rows}   ; desc SBO=1024 B, +32 B per K=8 step
+//   MN-major (A(m,k)=A[k*ld+m]) : four TMA boxes {32 m, 32 k}    ; desc LBO=4096 B, SBO=1024 B, +1024 B per step
 #pragma once
+
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
 #include "seg_gemm.cuh"
 
 namespace ta3n {
-inline int run_gemm_tcgen05(const GemmPlan& plan, cudaStream_t stream, bool* handled) {
-  (void)plan;
-  (void)stream;
-  *handled = false;
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 16 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;   // + slack for 1024 B alignment
+constexpr int TC_TMEM_COLS = 128;
+constexpr int kMaxMaps = 64;
+
+struct alignas(64) TcMaps {
+  CUtensorMap m[kMaxMaps];
+};
+struct TcSegMaps {
+  unsigned char a[kMaxSegs];
+  unsigned char b[kMaxSegs];
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when every tcgen05 op issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns: lane i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a,b=TF32 [7,10)=[10,13)=2,
+// a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(bool a_kmaj, bool b_kmaj, int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_kmaj ? 0u : 1u) << 15) | ((b_kmaj ? 0u : 1u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------
+template <bool A_KMAJ, bool B_KMAJ>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant__ TcMaps maps,
+                   const __grid_constant__ TcSegMaps segmaps) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile decode (same scheme as the SIMT engine, 128x128 tiles) ----
+  const int tile = blockIdx.x;
+  int gi = 0;
+  for (int i = 1; i < tab.n_groups; ++i)
+    if (tile >= tab.g[i].tile_begin) gi = i;
+  const Group& g = tab.g[gi];
+  int local = tile - g.tile_begin;
+  const int per_split = g.tiles_m * g.tiles_n;
+  const int split = local / per_split;
+  local -= split * per_split;
+  const int m0 = (local / g.tiles_n) * TC_BM;
+  const int n0 = (local % g.tiles_n) * TC_BN;
+
+  int total_chunks = 0;
+  for (int s = 0; s < g.seg_count; ++s) total_chunks += (tab.s[g.seg_begin + s].len + TC_BK - 1) / TC_BK;
+  const int cps = (total_chunks + g.ksplit - 1) / g.ksplit;
+  const int c_begin = split * cps;
+  const int c_end = min(total_chunks, c_begin + cps);
+  const int n_iter = max(0, c_end - c_begin);
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, TC_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0 && n_iter > 0) {
+      int seg = 0, k0 = 0;
+      {
+        int skip = c_begin;
+        while (seg < g.seg_count) {
+          const int nch = (tab.s[g.seg_begin + seg].len + TC_BK - 1) / TC_BK;
+          if (skip < nch) {
+            k0 = skip * TC_BK;
+            break;
+          }
+          skip -= nch;
+          ++seg;
+        }
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int stage = it % TC_STAGES;
+        const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+        uint8_t* sA = smem + stage * TC_STAGE_BYTES;
+        uint8_t* sB = sA + TC_A_BYTES;
+        const CUtensorMap* ma = &maps.m[segmaps.a[g.seg_begin + seg]];
+        const CUtensorMap* mb = &maps.m[segmaps.b[g.seg_begin + seg]];
+        if (A_KMAJ) {
+          tma_load_2d(sA, ma, &full_bar[stage], k0, m0);
+        } else {
+#pragma unroll
+          for (int q = 0; q < TC_BM / 32; ++q) tma_load_2d(sA + q * 4096, ma, &full_bar[stage], m0 + 32 * q, k0);
+        }
+        if (B_KMAJ) {
+          tma_load_2d(sB, mb, &full_bar[stage], k0, n0);
+        } else {
+#pragma unroll
+          for (int q = 0; q < TC_BN / 32; ++q) tma_load_2d(sB + q * 4096, mb, &full_bar[stage], n0 + 32 * q, k0);
+        }
+        k0 += TC_BK;
+        if (k0 >= tab.s[g.seg_begin + seg].len) {
+          ++seg;
+          k0 = 0;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (one thread) ===========================
+    if (lane == 0 && n_iter > 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(A_KMAJ, B_KMAJ, TC_BM, TC_BN);
+      for (int it = 0; it < n_iter; ++it) {
+        const int stage = it % TC_STAGES;
+        const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * TC_STAGE_BYTES);
+        const uint32_t b_base = a_base + TC_A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+          const uint64_t adesc = A_KMAJ ? umma_desc(a_base + ks * 32, 16, 1024) : umma_desc(a_base + ks * 1024, 4096, 1024);
+          const uint64_t bdesc = B_KMAJ ? umma_desc(b_base + ks * 32, 16, 1024) : umma_desc(b_base + ks * 1024, 4096, 1024);
+          umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);   // releases the smem slot once these MMAs have read it
+      }
+      umma_commit(&tmem_full_bar);        // accumulator complete
+    }
+  } else {
+    // =========================== epilogue (4 warps, 32 TMEM lanes each) ===========================
+    const int lq = warp & 3;              // TMEM lane quarter this warp may access
+    float* stg = reinterpret_cast<float*>(smem) + lq * (32 * 33);   // pipeline smem is idle by now
+    if (n_iter > 0) {
+      mbar_wait(&tmem_full_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < TC_BN / 32; ++c) {
+      float v[32];
+      if (n_iter > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(c * 32), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+      __syncwarp();
+      const int n = n0 + c * 32 + lane;
+      if (n < g.N) {
+        for (int r = 0; r < 32; ++r) {
+          const int m = m0 + lq * 32 + r;
+          if (m >= g.M) break;
+          const float acc = stg[r * 33 + lane];
+          if (g.ksplit > 1)
+            g.partial[((size_t)split * g.M + m) * g.N + n] = acc;
+          else
+            g.C[(size_t)m * g.ldc + n] = apply_epilogue(g, m, n, acc);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled encode_fn() {
+  static PFN_encodeTiled fn = []() -> PFN_encodeTiled {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<PFN_encodeTiled>(p);
+  }();
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  long inner, outer, ld;
+  int box_inner, box_outer;
+  bool operator<(const MapKey& o) const {
+    return std::tie(ptr, inner, outer, ld, box_inner, box_outer) <
+           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer);
+  }
+};
+
+// fp32 2-D row-major tensor [outer, inner] with row pitch ld floats; 128B swizzle; OOB reads give zeros
+inline int encode_map(const MapKey& k, CUtensorMap* out) {
+  static thread_local std::map<MapKey, CUtensorMap> cache;
+  auto it = cache.find(k);
+  if (it != cache.end()) {
+    *out = it->second;
+    return TA3N_OK;
+  }
+  PFN_encodeTiled fn = encode_fn();
+  if (!fn) return fail(TA3N_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)k.inner, (cuuint64_t)k.outer};
+  cuuint64_t strides[1] = {(cuuint64_t)k.ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)k.box_inner, (cuuint32_t)k.box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(k.ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TA3N_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  if (cache.size() > 4096) cache.clear();
+  cache[k] = *out;
   return TA3N_OK;
 }
+
+inline bool tc_operand_ok(const float* p, int ld) {
+  return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && (ld % 4) == 0 && ld > 0;
+}
+
+// Is this group worth / able to run on the tensor-core engine?
+inline bool tc_group_ok(const GemmPlan& plan, const Group& g) {
+  if (plan.load_flags != 0) return false;                    // ReLU-on-load needs a register pass
+  if ((long)g.M * g.N < 64L * 64L) return false;             // tiny heads stay on the SIMT engine
+  if (g.seg_count > kMaxSegs) return false;
+  for (int i = 0; i < g.seg_count; ++i) {
+    const Seg& s = plan.segs[g.seg_begin + i];
+    if (!tc_operand_ok(s.A, s.lda) || !tc_operand_ok(s.B, s.ldb) || s.len <= 0) return false;
+  }
+  return true;
+}
+
+template <bool A_KMAJ, bool B_KMAJ>
+inline int tc_launch_one(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
+                         const char* label) {
+  static bool configured = false;
+  if (!configured) {
+    TA3N_CUDA(cudaFuncSetAttribute(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TC_SMEM_BYTES));
+    configured = true;
+  }
+  pre_launch(label, stream);
+  seg_gemm_tc_kernel<A_KMAJ, B_KMAJ><<<tab.total_tiles, TC_THREADS, TC_SMEM_BYTES, stream>>>(tab, maps, sm);
+  return after_launch();
+}
+
+// Launch `plan` (all groups eligible) on the tcgen05 engine.
+inline int launch_tc(const GemmPlan& plan, cudaStream_t stream) {
+  size_t gi = 0;
+  while (gi < plan.groups.size()) {
+    GemmTable tab;
+    TcMaps maps;
+    TcSegMaps sm;
+    memset(&tab, 0, sizeof(int) * 4);
+    memset(&sm, 0, sizeof(sm));
+    std::map<MapKey, int> local;
+    int ng = 0, ns = 0, tiles = 0, nmaps = 0;
+    bool any_split = false;
+    while (gi < plan.groups.size() && ng < kMaxGroups) {
+      const Group& src = plan.groups[gi];
+      if (ns + src.seg_count > kMaxSegs) break;
+      // tensor maps of this group's segments (deduplicated within the launch)
+      std::vector<std::pair<MapKey, MapKey>> keys;
+      int fresh = 0;
+      std::map<MapKey, int> trial = local;
+      for (int i = 0; i < src.seg_count; ++i) {
+        const Seg& s = plan.segs[src.seg_begin + i];
+        MapKey ka = plan.a_kmaj ? MapKey{s.A, s.len, src.M, s.lda, TC_BK, TC_BM} : MapKey{s.A, src.M, s.len, s.lda, 32, TC_BK};
+        MapKey kb = plan.b_kmaj ? MapKey{s.B, s.len, src.N, s.ldb, TC_BK, TC_BN} : MapKey{s.B, src.N, s.len, s.ldb, 32, TC_BK};
+        for (const MapKey& k : {ka, kb})
+          if (!trial.count(k)) trial[k] = nmaps + fresh++;
+        keys.push_back({ka, kb});
+      }
+      if (nmaps + fresh > kMaxMaps) {
+        if (ng == 0) return fail(TA3N_ERR_UNSUPPORTED, "tcgen05 GEMM: one group needs %d tensor maps", fresh);
+        break;
+      }
+      for (auto& kv : trial)
+        if (!local.count(kv.first)) {
+          TA3N_TRY(encode_map(kv.first, &maps.m[kv.second]));
+          local[kv.first] = kv.second;
+        }
+      nmaps += fresh;
+      Group g = src;
+      for (int i = 0; i < src.seg_count; ++i) {
+        tab.s[ns + i] = plan.segs[src.seg_begin + i];
+        sm.a[ns + i] = (unsigned char)local[keys[i].first];
+        sm.b[ns + i] = (unsigned char)local[keys[i].second];
+      }
+      g.seg_begin = ns;
+      ns += src.seg_count;
+      g.tiles_m = (g.M + TC_BM - 1) / TC_BM;
+      g.tiles_n = (g.N + TC_BN - 1) / TC_BN;
+      g.tile_begin = tiles;
+      tiles += g.tiles_m * g.tiles_n * g.ksplit;
+      any_split |= g.ksplit > 1;
+      tab.g[ng++] = g;
+      ++gi;
+    }
+    tab.n_groups = ng;
+    tab.total_tiles = tiles;
+    if (tiles > 0) {
+      if (plan.a_kmaj && plan.b_kmaj)
+        TA3N_TRY((tc_launch_one<true, true>(tab, maps, sm, stream, plan.label)));
+      else if (plan.a_kmaj && !plan.b_kmaj)
+        TA3N_TRY((tc_launch_one<true, false>(tab, maps, sm, stream, plan.label)));
+      else if (!plan.a_kmaj && !plan.b_kmaj)
+        TA3N_TRY((tc_launch_one<false, false>(tab, maps, sm, stream, plan.label)));
+      else
+        TA3N_TRY((tc_launch_one<false, true>(tab, maps, sm, stream, plan.label)));
+      if (any_split) {
+        dim3 grid(32, ng);
+        pre_launch("splitk_reduce", stream);
+        splitk_reduce_kernel<<<grid, 256, 0, stream>>>(tab);
+        TA3N_TRY(after_launch());
+      }
+    }
+  }
+  return TA3N_OK;
+}
+
+// Copy the groups `idx` of `plan` (with their segments) into a new plan.
+inline GemmPlan sub_plan(const GemmPlan& plan, const std::vector<int>& idx) {
+  GemmPlan out;
+  out.a_kmaj = plan.a_kmaj;
+  out.b_kmaj = plan.b_kmaj;
+  out.load_flags = plan.load_flags;
+  out.label = plan.label;
+  for (int i : idx) {
+    Group g = plan.groups[i];
+    const int b = g.seg_begin;
+    g.seg_begin = (int)out.segs.size();
+    for (int k = 0; k < g.seg_count; ++k) out.segs.push_back(plan.segs[b + k]);
+    out.groups.push_back(g);
+  }
+  return out;
+}
+
+// Run a plan.  With the tf32 engine selected, every group the tensor-core kernel can take runs
+// there; the rest (tiny heads, unaligned operands, ReLU-on-load) runs on the fp32 SIMT engine --
+// still CUDA, never the CPU.
+inline int run_gemm(GemmPlan& plan, cudaStream_t stream, Arena* splitk_arena = nullptr) {
+  if (plan.groups.empty()) return TA3N_OK;
+  for (auto& g : plan.groups)
+    if (g.M <= 0 || g.N <= 0 || g.seg_count <= 0)
+      return fail(TA3N_ERR_INVALID, "seg_gemm: empty group M=%d N=%d segs=%d", g.M, g.N, g.seg_count);
+  if (gemm_engine().load() == TA3N_GEMM_TF32_TCGEN05) {
+    std::vector<int> tc_idx, simt_idx;
+    for (int i = 0; i < (int)plan.groups.size(); ++i) (tc_group_ok(plan, plan.groups[i]) ? tc_idx : simt_idx).push_back(i);
+    if (!tc_idx.empty()) {
+      GemmPlan tc = sub_plan(plan, tc_idx);
+      plan_splitk(tc, splitk_arena, TC_BM, TC_BN, TC_BK, 4);
+      TA3N_TRY(launch_tc(tc, stream));
+    }
+    if (!simt_idx.empty()) {
+      GemmPlan rest = sub_plan(plan, simt_idx);
+      plan_splitk(rest, splitk_arena, SG_BM, SG_BN, SG_BK, 8);
+      TA3N_TRY(launch_simt(rest, stream));
+    }
+    return TA3N_OK;
+  }
+  plan_splitk(plan, splitk_arena, SG_BM, SG_BN, SG_BK, 8);
+  return launch_simt(plan, stream);
+}
+
 }  // namespace ta3n

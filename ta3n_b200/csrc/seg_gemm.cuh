@@ -335,20 +335,19 @@ struct GemmPlan {
   }
 };
 
-int run_gemm_tcgen05(const GemmPlan& plan, cudaStream_t stream, bool* handled);  // gemm_tcgen05.cuh
-
 // Choose a split-K factor for reduction-heavy, tile-poor problems (wgrads) and carve the partial
-// buffers out of `arena` (which may be null -> no split-K).
-inline void plan_splitk(GemmPlan& plan, Arena* arena, int target_ctas = 296) {
+// buffers out of `arena` (which may be null -> no split-K).  bm/bn/bk: tile shape of the engine.
+inline void plan_splitk(GemmPlan& plan, Arena* arena, int bm, int bn, int bk, int min_chunks,
+                        int target_ctas = 296) {
   if (!arena) return;
   long tiles = 0;
-  for (auto& g : plan.groups) tiles += (long)((g.M + SG_BM - 1) / SG_BM) * ((g.N + SG_BN - 1) / SG_BN);
+  for (auto& g : plan.groups) tiles += (long)((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn);
   if (tiles <= 0 || tiles >= target_ctas) return;
   for (auto& g : plan.groups) {
     long chunks = 0;
-    for (int i = 0; i < g.seg_count; ++i) chunks += (plan.segs[g.seg_begin + i].len + SG_BK - 1) / SG_BK;
+    for (int i = 0; i < g.seg_count; ++i) chunks += (plan.segs[g.seg_begin + i].len + bk - 1) / bk;
     int want = (int)((target_ctas + tiles - 1) / tiles);
-    int maxsplit = (int)(chunks / 8);  // at least 8 chunks (128 k) per split
+    int maxsplit = (int)(chunks / min_chunks);
     int ks = want < maxsplit ? want : maxsplit;
     if (ks > 16) ks = 16;
     if (ks < 2) continue;
@@ -406,22 +405,6 @@ inline int launch_simt(const GemmPlan& plan, cudaStream_t stream) {
     }
   }
   return TA3N_OK;
-}
-
-// Run a plan on the selected engine.  The tcgen05 engine declines (handled=false) shapes it
-// does not cover (tiny or unaligned problems); those run on the SIMT engine -- still CUDA, never CPU.
-inline int run_gemm(GemmPlan& plan, cudaStream_t stream, Arena* splitk_arena = nullptr) {
-  if (plan.groups.empty()) return TA3N_OK;
-  for (auto& g : plan.groups) {
-    if (g.M <= 0 || g.N <= 0) return fail(TA3N_ERR_INVALID, "seg_gemm: empty group M=%d N=%d", g.M, g.N);
-  }
-  if (gemm_engine().load() == TA3N_GEMM_TF32_TCGEN05) {
-    bool handled = false;
-    TA3N_TRY(run_gemm_tcgen05(plan, stream, &handled));
-    if (handled) return TA3N_OK;
-  }
-  plan_splitk(plan, splitk_arena);
-  return launch_simt(plan, stream);
 }
 
 }  // namespace ta3n

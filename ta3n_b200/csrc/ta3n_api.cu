@@ -648,4 +648,18 @@ int ta3n_gemm_tn(const float* A, const float* B, float* C, int M, int N, int K, 
   return run_gemm(plan, S(stream));
 }
 
+
+int ta3n_gemm_ex(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, float* C, int ldc,
+                 int M, int N, int K, void* workspace, size_t workspace_bytes, ta3n_stream_t stream) {
+  TA3N_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bad arguments");
+  Arena arena(workspace, workspace_bytes);
+  GemmPlan plan;
+  plan.label = "gemm_ex";
+  plan.a_kmaj = a_kmajor != 0;
+  plan.b_kmaj = b_kmajor != 0;
+  plan.add_group(M, N, C, ldc);
+  plan.add_seg(A, lda, B, ldb, K);
+  return run_gemm(plan, S(stream), workspace ? &arena : nullptr);
+}
+
 }  // extern "C"

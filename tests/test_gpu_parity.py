@@ -183,6 +183,40 @@ def test_gemm_tn_matches_torch(M, N, K, engine):
     assert_close(Cm, ref, TOL[engine] , "gemm_tn")
 
 
+@pytest.mark.parametrize("a_kmaj,b_kmaj", [(1, 1), (1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("M,N,K,pad,splitk", [(128, 128, 64, 0, False), (200, 136, 96, 8, False),
+                                              (512, 256, 1024, 0, False), (256, 512, 2560, 4, True),
+                                              (64, 2048, 512, 0, True), (1, 5, 3, 0, False)])
+def test_gemm_ex_all_operand_layouts(M, N, K, pad, splitk, a_kmaj, b_kmaj, engine):
+    """Forward (K-major x K-major), dgrad (K-major x N-major) and wgrad (M-major x N-major) operand
+    layouts of the segmented GEMM, with padded leading dimensions and ragged tile edges."""
+    from ta3n_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(K, N, generator=g)
+    ref = (A.double() @ B.double()).float()
+    dev = _dev()
+    if a_kmaj:
+        Abuf = torch.zeros(M, K + pad); Abuf[:, :K] = A; lda = K + pad
+    else:
+        Abuf = torch.zeros(K, M + pad); Abuf[:, :M] = A.t(); lda = M + pad
+    if b_kmaj:
+        Bbuf = torch.zeros(N, K + pad); Bbuf[:, :K] = B.t(); ldb = K + pad
+    else:
+        Bbuf = torch.zeros(K, N + pad); Bbuf[:, :N] = B; ldb = N + pad
+    Abuf, Bbuf = Abuf.to(dev), Bbuf.to(dev)
+    Cbuf = torch.full((M, N + pad), 7.0, device=dev)
+    ws = torch.empty(16 << 20, dtype=torch.uint8, device=dev) if splitk else None
+    _lib.check(lib.ta3n_gemm_ex(Abuf.data_ptr(), lda, a_kmaj, Bbuf.data_ptr(), ldb, b_kmaj, Cbuf.data_ptr(),
+                                N + pad, M, N, K, ws.data_ptr() if splitk else None,
+                                ws.numel() if splitk else 0, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert_close(Cbuf[:, :N], ref, TOL[engine], f"gemm_ex a_kmaj={a_kmaj} b_kmaj={b_kmaj}")
+    if pad:
+        assert torch.all(Cbuf[:, N:] == 7.0)        # padding columns untouched
+
+
 # ------------------------------------------------------------------------------------------------
 # full-size (BASELINE cfg2: B=256,T=5,D=2048,C=12) size-independent properties
 # ------------------------------------------------------------------------------------------------
