@@ -11,8 +11,12 @@
 // expressed as TMA coordinates / tensor maps per K-segment: nothing is materialised.
 //
 // Both operand majors are supported through the UMMA smem descriptors:
-//   K-major  (A(m,k)=A[m*ld+k]) : one TMA box {32 k, 128 rows}   ; desc SBO=1024 B, +32 B per K=8 step
-//   MN-major (A(m,k)=A[k*ld+m]) : four TMA boxes {32 m, 32 k}    ; desc LBO=4096 B, SBO=1024 B, +1024 B per step
+//   K-major  (A(m,k)=A[m*ld+k]) : one TMA box {32 k, 128 rows}, SWIZZLE_128B (16 B chunks);
+//                                 desc layout SW128, SBO=1024 B, +32 B per K=8 step
+//   MN-major (A(m,k)=A[k*ld+m]) : four TMA boxes {32 m, 32 k}, SWIZZLE_128B_ATOM_32B -- the only smem
+//                                 layout tcgen05 accepts for MN-major 32-bit operands (swizzle atom =
+//                                 4 k-rows x 128 B); desc layout SW128_BASE32B, LBO=4096 B (next 32 m),
+//                                 SBO=512 B (next 4 k-rows), +1024 B per K=8 step
 #pragma once
 
 #include <cuda.h>
@@ -120,16 +124,24 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// UMMA shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 |
+//   [61,64) layout: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout_type & 7u) << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t tile_base, int kstep) {
+  return umma_desc(tile_base + kstep * 32, 16, 1024, 2);
+}
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t tile_base, int kstep) {
+  return umma_desc(tile_base + kstep * 1024, 4096, 512, 1);
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a,b=TF32 [7,10)=[10,13)=2,
@@ -245,8 +257,8 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
         const uint32_t b_base = a_base + TC_A_BYTES;
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
-          const uint64_t adesc = A_KMAJ ? umma_desc(a_base + ks * 32, 16, 1024) : umma_desc(a_base + ks * 1024, 4096, 1024);
-          const uint64_t bdesc = B_KMAJ ? umma_desc(b_base + ks * 32, 16, 1024) : umma_desc(b_base + ks * 1024, 4096, 1024);
+          const uint64_t adesc = A_KMAJ ? umma_desc_kmajor(a_base, ks) : umma_desc_mnmajor(a_base, ks);
+          const uint64_t bdesc = B_KMAJ ? umma_desc_kmajor(b_base, ks) : umma_desc_mnmajor(b_base, ks);
           umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);   // releases the smem slot once these MMAs have read it
@@ -317,9 +329,10 @@ struct MapKey {
   const void* ptr;
   long inner, outer, ld;
   int box_inner, box_outer;
+  int atom32;   // 1: SWIZZLE_128B_ATOM_32B (MN-major operands), 0: SWIZZLE_128B
   bool operator<(const MapKey& o) const {
-    return std::tie(ptr, inner, outer, ld, box_inner, box_outer) <
-           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer);
+    return std::tie(ptr, inner, outer, ld, box_inner, box_outer, atom32) <
+           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer, o.atom32);
   }
 };
 
@@ -338,7 +351,9 @@ inline int encode_map(const MapKey& k, CUtensorMap* out) {
   cuuint32_t box[2] = {(cuuint32_t)k.box_inner, (cuuint32_t)k.box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(k.ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  k.atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TA3N_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
   if (cache.size() > 4096) cache.clear();
@@ -397,8 +412,10 @@ inline int launch_tc(const GemmPlan& plan, cudaStream_t stream) {
       std::map<MapKey, int> trial = local;
       for (int i = 0; i < src.seg_count; ++i) {
         const Seg& s = plan.segs[src.seg_begin + i];
-        MapKey ka = plan.a_kmaj ? MapKey{s.A, s.len, src.M, s.lda, TC_BK, TC_BM} : MapKey{s.A, src.M, s.len, s.lda, 32, TC_BK};
-        MapKey kb = plan.b_kmaj ? MapKey{s.B, s.len, src.N, s.ldb, TC_BK, TC_BN} : MapKey{s.B, src.N, s.len, s.ldb, 32, TC_BK};
+        MapKey ka = plan.a_kmaj ? MapKey{s.A, s.len, src.M, s.lda, TC_BK, TC_BM, 0}
+                                : MapKey{s.A, src.M, s.len, s.lda, 32, TC_BK, 1};
+        MapKey kb = plan.b_kmaj ? MapKey{s.B, s.len, src.N, s.ldb, TC_BK, TC_BN, 0}
+                                : MapKey{s.B, src.N, s.len, s.ldb, 32, TC_BK, 1};
         for (const MapKey& k : {ka, kb})
           if (!trial.count(k)) trial[k] = nmaps + fresh++;
         keys.push_back({ka, kb});
