@@ -178,6 +178,21 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
                         float grad_scale, float* d_feat_video, float* dWc, float* dbc,
                         void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
 
+/* ---- fused loss heads of the shipped training configuration ------------------------- */
+/* main.py:446 (class CE on the Bs source rows), main.py:508-538 (domain CE per level, labels
+ * 0 = source rows, 1 = target rows), main.py:559-562 + loss.py:15-25 (gamma * attentive entropy).
+ * flags: 1 relation-level adv, 2 video-level adv, 4 frame-level adv, 8 attentive entropy.
+ * Inputs are the (Bs+Bt)-row outputs of the path; labels [Bs] int64.  Writes the scalar loss and
+ * d loss / d logits of every head (zeros for disabled levels).                              */
+size_t ta3n_loss_workspace_bytes(int M);
+int ta3n_loss_fwd_bwd(const float* pred_video, const long long* labels, const float* pred_rel,
+                      const float* pred_dom_video, const float* pred_frame, int Bs, int Bt, int T,
+                      int R, int C, float gamma, int flags, float* loss, float* g_pred_video,
+                      float* g_pred_rel, float* g_pred_dom_video, float* g_pred_frame,
+                      void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
+/* *counter += 1 on the stream (dropout step counter for CUDA-graph replays). */
+int ta3n_counter_inc(uint64_t* counter, ta3n_stream_t stream);
+
 /* ---- self test of the tensor-core GEMM engine (used by tests; device buffers) ------ */
 /* C[M,N] = A[M,K] * B[N,K]^T with the selected engine; A, B, C row-major fp32.           */
 int ta3n_gemm_tn(const float* A, const float* B, float* C, int M, int N, int K,

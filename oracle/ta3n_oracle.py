@@ -193,26 +193,81 @@ def _apply_dropout(x: torch.Tensor, p: float, train: bool, mask: Optional[torch.
     return x * mask.to(x.dtype) * (1.0 / (1.0 - p))
 
 
+def _relu(x: torch.Tensor, gate: Optional[torch.Tensor]) -> torch.Tensor:
+    """ReLU, or -- when ``gate`` (0/1, same shape) is given -- the linear map x * gate.
+
+    Gates let a test evaluate the oracle *on a prescribed activation pattern*: a reduced-precision
+    forward (tf32) flips the sign of the ~1e-4 fraction of pre-activations that sit within rounding
+    error of zero; each flip changes a gradient entry by O(1), so gradients of the two networks differ
+    by ~sqrt(fraction) ~ 1e-2 even though every product is accurate to ~1e-4.  With the pattern pinned,
+    gradients must agree to rounding accuracy again."""
+    return F.relu(x) if gate is None else x * gate.to(x.dtype)
+
+
+def activation_pattern(params, xs, xt, beta, cfg: "PathConfig") -> Dict[str, torch.Tensor]:
+    """The ReLU on/off pattern of a plain (dropout-free) oracle forward, in the ``gates`` format
+    (M = Bs+Bt rows, source first) -- used to test the gate plumbing against itself."""
+    p = params
+    T, Fd, R = cfg.num_segments, cfg.shared_dim, cfg.num_segments - 1
+    tuples = relation_tuples(T)
+    x = torch.cat([xs, xt], 0)
+    M = x.size(0)
+    pre = F.linear(x.reshape(-1, x.size(-1)), p["fc_feature_shared_source.weight"], p["fc_feature_shared_source.bias"])
+    feat = F.relu(pre)
+    hf = F.linear(feat, p["fc_feature_domain.weight"], p["fc_feature_domain.bias"])
+    g = {"shared": pre > 0, "frame_disc": hf > 0}
+    if cfg.use_attn_frame != "none":
+        pf = F.linear(F.relu(hf), p["fc_classifier_domain.weight"], p["fc_classifier_domain.bias"])
+        feat = (entropy_attention(pf).view(-1, 1) + 1) * feat
+    f3 = feat.view(M, T, Fd)
+    trn, rel = [], []
+    for i, rels in enumerate(tuples):
+        acc = 0
+        for tau in rels:
+            z = F.linear(f3[:, list(tau), :].reshape(M, -1), p[f"TRN.fc_fusion_scales.{i}.1.weight"],
+                         p[f"TRN.fc_fusion_scales.{i}.1.bias"])
+            trn.append(z > 0)
+            acc = acc + F.relu(z)
+        rel.append(acc)
+    g["trn"] = trn
+    hr = [F.linear(rel[i], p[f"relation_domain_classifier_all.{i}.0.weight"],
+                   p[f"relation_domain_classifier_all.{i}.0.bias"]) for i in range(R)]
+    g["rel_disc"] = [h > 0 for h in hr]
+    relf = torch.stack(rel, 1)
+    if cfg.use_attn != "none":
+        pr = torch.stack([F.linear(F.relu(hr[i]), p[f"relation_domain_classifier_all.{i}.2.weight"],
+                                   p[f"relation_domain_classifier_all.{i}.2.bias"]) for i in range(R)], 1)
+        w = entropy_attention(pr.reshape(-1, 2)).view(M, R)
+        relf = (w.unsqueeze(-1) + 1) * relf
+    vid = relf.sum(1)
+    g["video_disc"] = F.linear(vid, p["fc_feature_domain_video.weight"], p["fc_feature_domain_video.bias"]) > 0
+    return g
+
+
 def trn_multiscale(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
-                   tuples: List[List[Tuple[int, ...]]]) -> torch.Tensor:
+                   tuples: List[List[Tuple[int, ...]]], gates: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
     """RelationModuleMultiScale.forward (TRNmodule.py:58-82).
 
     x (N, T, F) -> (N, T-1, H);  out[:, i] = sum_r relu(W_i . concat_j relu(x[:, tau_ir[j]]) + b_i)
+    ``gates`` (optional): one (N,H) 0/1 tensor per evaluated relation, see ``_relu``.
     """
     per_scale = []
+    q = 0
     for i, rels in enumerate(tuples):
         acc = None
         for tau in rels:
             u = x[:, list(tau), :].reshape(x.size(0), -1)             # :60-61 / :75-76
-            a = F.relu(F.linear(F.relu(u), weights[i], biases[i]))    # :46-54 ReLU-Linear-ReLU
+            a = _relu(F.linear(F.relu(u), weights[i], biases[i]),     # :46-54 ReLU-Linear-ReLU
+                      None if gates is None else gates[q])
+            q += 1
             acc = a if acc is None else acc + a                        # :79
         per_scale.append(acc.unsqueeze(1))
     return torch.cat(per_scale, 1)                                     # :81
 
 
-def two_layer_disc(x: torch.Tensor, w1, b1, w2, b2, beta: float) -> torch.Tensor:
+def two_layer_disc(x: torch.Tensor, w1, b1, w2, b2, beta: float, gate: Optional[torch.Tensor] = None) -> torch.Tensor:
     """GradReverse -> Linear -> ReLU -> Linear(->2) (models.py:456-470, 477-479)."""
-    h = F.relu(F.linear(grad_reverse(x, beta), w1, b1))
+    h = _relu(F.linear(grad_reverse(x, beta), w1, b1), gate)
     return F.linear(h, w2, b2)
 
 
@@ -221,21 +276,23 @@ def two_layer_disc(x: torch.Tensor, w1, b1, w2, b2, beta: float) -> torch.Tensor
 # ----------------------------------------------------------------------------
 def _forward_domain(p: Dict[str, torch.Tensor], x: torch.Tensor, beta: Sequence[float], mu: float,
                     cfg: PathConfig, train: bool, reverse: bool,
-                    mask_i: Optional[torch.Tensor], mask_v: Optional[torch.Tensor]):
+                    mask_i: Optional[torch.Tensor], mask_v: Optional[torch.Tensor],
+                    gates: Optional[Dict[str, torch.Tensor]] = None):
     T, Fd, H = cfg.num_segments, cfg.shared_dim, NUM_BOTTLENECK
     R = T - 1
     batch = x.size(0)
     tuples = relation_tuples(T)
+    gates = gates or {}
 
     flat = x.reshape(-1, x.size(-1))                                                   # :557
     feat = F.linear(flat, p["fc_feature_shared_source.weight"], p["fc_feature_shared_source.bias"])  # :565
-    feat = F.relu(feat)                                                                # :572
+    feat = _relu(feat, gates.get("shared"))                                            # :572
     feat = _apply_dropout(feat, cfg.dropout_i, train, mask_i)                          # :574
     feat_frames = feat.view(batch, T, Fd)                                              # :578
 
     pred_frame = two_layer_disc(feat, p["fc_feature_domain.weight"], p["fc_feature_domain.bias"],
                                 p["fc_classifier_domain.weight"], p["fc_classifier_domain.bias"],
-                                beta[2])                                               # :606
+                                beta[2], gates.get("frame_disc"))                      # :606
     if cfg.use_attn_frame != "none":                                                   # :612-614, :368-377
         w_frame = entropy_attention(pred_frame)
         feat = (w_frame.view(-1, 1) + 1) * feat
@@ -246,14 +303,15 @@ def _forward_domain(p: Dict[str, torch.Tensor], x: torch.Tensor, beta: Sequence[
     rel = trn_multiscale(feat.view(batch, T, Fd),
                          [p[f"TRN.fc_fusion_scales.{i}.1.weight"] for i in range(R)],
                          [p[f"TRN.fc_fusion_scales.{i}.1.bias"] for i in range(R)],
-                         tuples)                                                       # :635
+                         tuples, gates.get("trn"))                                     # :635
 
     pred_rel = torch.stack(
         [two_layer_disc(rel[:, i, :],
                         p[f"relation_domain_classifier_all.{i}.0.weight"],
                         p[f"relation_domain_classifier_all.{i}.0.bias"],
                         p[f"relation_domain_classifier_all.{i}.2.weight"],
-                        p[f"relation_domain_classifier_all.{i}.2.bias"], beta[0])
+                        p[f"relation_domain_classifier_all.{i}.2.bias"], beta[0],
+                        None if "rel_disc" not in gates else gates["rel_disc"][i])
          for i in range(R)], 1)                                                        # :472-488 -> (B,R,2)
 
     if cfg.use_attn != "none":                                                         # :643-645, :379-388
@@ -273,25 +331,44 @@ def _forward_domain(p: Dict[str, torch.Tensor], x: torch.Tensor, beta: Sequence[
     pred_dom_video = two_layer_disc(vid, p["fc_feature_domain_video.weight"],
                                     p["fc_feature_domain_video.bias"],
                                     p["fc_classifier_domain_video.weight"],
-                                    p["fc_classifier_domain_video.bias"], beta[1])     # :694
+                                    p["fc_classifier_domain_video.bias"], beta[1],
+                                    gates.get("video_disc"))                           # :694
 
     pred_domain = [pred_rel, pred_dom_video, pred_frame.view(batch, T, 2)]            # reversed list, :722
     feats = [pred_video, feat_video, feat_frames]                                      # reversed list, :722
     return attn, pred_video, pred_video, pred_domain, feats                            # :713 out_2 = out
 
 
+def split_gates(gates: Optional[Dict[str, torch.Tensor]], bs: int, T: int):
+    """Split activation-pattern gates given for M = Bs+Bt rows (source first) into per-domain dicts.
+    Keys: 'shared', 'frame_disc' (M*T,F); 'trn' (n_rel,M,H); 'rel_disc' (R,M,H); 'video_disc' (M,H)."""
+    if not gates:
+        return None, None
+    out = ({}, {})
+    for k, g in gates.items():
+        if k in ("shared", "frame_disc"):
+            out[0][k], out[1][k] = g[:bs * T], g[bs * T:]
+        elif k in ("trn", "rel_disc"):
+            out[0][k], out[1][k] = [t[:bs] for t in g], [t[bs:] for t in g]
+        else:
+            out[0][k], out[1][k] = g[:bs], g[bs:]
+    return out
+
+
 def forward(params: Dict[str, torch.Tensor], input_source: torch.Tensor, input_target: torch.Tensor,
             beta: Sequence[float], mu: float, cfg: PathConfig, train: bool = True, reverse: bool = False,
-            masks: Optional[Dict[str, torch.Tensor]] = None):
+            masks: Optional[Dict[str, torch.Tensor]] = None, gates: Optional[Dict[str, torch.Tensor]] = None):
     """VideoModel.forward (models.py:545-722) -> the reference's 10-tuple.
 
     ``masks`` may hold keep-masks 'i_source' (Bs*T,F), 'i_target', 'v_source' (Bs,H), 'v_target'.
+    ``gates`` pins the ReLU activation pattern (see ``_relu`` / ``split_gates``); default: real ReLUs.
     """
     masks = masks or {}
+    gs, gt = split_gates(gates, input_source.size(0), cfg.num_segments)
     src = _forward_domain(params, input_source, beta, mu, cfg, train, reverse,
-                          masks.get("i_source"), masks.get("v_source"))
+                          masks.get("i_source"), masks.get("v_source"), gs)
     tgt = _forward_domain(params, input_target, beta, mu, cfg, train, reverse,
-                          masks.get("i_target"), masks.get("v_target"))
+                          masks.get("i_target"), masks.get("v_target"), gt)
     return src + tgt
 
 
@@ -336,13 +413,13 @@ def compose_loss(outputs, label_source: torch.Tensor, gamma: float = 0.003,
 
 
 def train_step(params: Dict[str, torch.Tensor], xs, xt, labels, beta, cfg: PathConfig,
-               gamma: float = 0.003, train: bool = True, masks=None):
+               gamma: float = 0.003, train: bool = True, masks=None, gates=None):
     """forward + composed loss + backward; returns (loss, outputs, grads-by-name)."""
     names = used_param_names(params)
     leaves = {k: params[k].detach().clone().requires_grad_(True) for k in names}
     live = dict(params)
     live.update(leaves)
-    outs = forward(live, xs, xt, beta, 0.0, cfg, train=train, reverse=False, masks=masks)
+    outs = forward(live, xs, xt, beta, 0.0, cfg, train=train, reverse=False, masks=masks, gates=gates)
     loss = compose_loss(outs, labels, gamma, use_attn=cfg.use_attn)
     grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
     return loss.detach(), outs, OrderedDict(zip(names, grads))

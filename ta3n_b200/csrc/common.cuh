@@ -127,10 +127,7 @@ struct Arena {
   // returns nullptr when exhausted (caller checks via ok())
   float* floats(size_t n) {
     size_t bytes = round(n * sizeof(float));
-    if (base == nullptr || used + bytes > size) {
-      used = size + 1;
-      return nullptr;
-    }
+    if (base == nullptr || used + bytes > size) return nullptr;   // caller decides whether that is fatal
     float* p = reinterpret_cast<float*>(base + used);
     used += bytes;
     return p;

@@ -20,6 +20,7 @@
 #pragma once
 
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <map>
 #include <tuple>
@@ -350,7 +351,15 @@ inline int encode_map(const MapKey& k, CUtensorMap* out) {
   cuuint64_t strides[1] = {(cuuint64_t)k.ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)k.box_inner, (cuuint32_t)k.box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(k.ptr), dims, strides, box, estr,
+  // TFLOAT32: the TMA unit rounds fp32 -> tf32 (round to nearest) while filling shared memory, so the
+  // tensor core never sees the truncation bias (-2^-11 relative per operand) it would apply to raw fp32
+  // bit patterns.  TA3N_TMA_RAW_FP32=1 switches to the raw copy (kept to measure the difference).
+  static const bool raw = []() {
+    const char* e = getenv("TA3N_TMA_RAW_FP32");
+    return e && e[0] == '1';
+  }();
+  CUresult r = fn(out, raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
+                  const_cast<void*>(k.ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   k.atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

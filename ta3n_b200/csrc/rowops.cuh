@@ -295,6 +295,120 @@ __global__ void __launch_bounds__(256) grl_bwd_kernel(const float* __restrict__ 
     out[e] = -beta * g[e];
 }
 
+// ---- fused loss heads of the shipped configuration ----------------------------
+//   main.py:446      CE(out_source, label)                         mean over Bs
+//   main.py:508-538  CE(cat(pred_S, pred_T), cat(0s, 1s)) per level mean over the level's rows
+//   main.py:559-562  gamma * mean_m (1 + H(softmax(dom_video_m))) * H(softmax(out_m))   (loss.py:15-25)
+// One warp per video: writes d loss / d logits for every head and the video's loss contribution.
+enum : int { LOSS_ADV_REL = 1, LOSS_ADV_VIDEO = 2, LOSS_ADV_FRAME = 4, LOSS_ATT_ENT = 8 };
+
+__global__ void __launch_bounds__(256)
+loss_heads_kernel(const float* __restrict__ pred_video, const long long* __restrict__ labels,
+                  const float* __restrict__ pred_rel, const float* __restrict__ pred_dom,
+                  const float* __restrict__ pred_frame, int Bs, int M, int T, int R, int C, float gamma, int flags,
+                  float* __restrict__ g_video, float* __restrict__ g_rel, float* __restrict__ g_dom,
+                  float* __restrict__ g_frame, float* __restrict__ row_loss) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int m = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M; m += gridDim.x * warps_per_block) {
+    const int dom = m >= Bs ? 1 : 0;
+    float loss = 0.f;
+    // class logits: softmax statistics over C
+    const float* pv = pred_video + (size_t)m * C;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, pv[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += expf(pv[c] - mx);
+    se = warp_sum(se);
+    const float lse = logf(se);
+    float hc = 0.f;   // entropy of the class prediction
+    for (int c = lane; c < C; c += 32) {
+      const float lq = pv[c] - mx - lse;
+      hc -= expf(lq) * lq;
+    }
+    hc = warp_sum(hc);
+    // video-level domain logits
+    const Attn2 dv = attn_from_logits(pred_dom[(size_t)m * 2], pred_dom[(size_t)m * 2 + 1]);
+    const bool att = (flags & LOSS_ATT_ENT) != 0;
+    const float att_scale = att ? gamma / (float)M : 0.f;
+    const long long y = (m < Bs) ? labels[m] : -1;
+    for (int c = lane; c < C; c += 32) {
+      const float lq = pv[c] - mx - lse;
+      const float q = expf(lq);
+      float gq = 0.f;
+      if (m < Bs) gq = (q - (c == (int)y ? 1.f : 0.f)) / (float)Bs;
+      gq += att_scale * (1.f + dv.ent) * (-q * (lq + hc));
+      g_video[(size_t)m * C + c] = gq;
+      if (m < Bs && c == (int)y && lane == (c & 31)) loss += -lq / (float)Bs;
+    }
+    loss = warp_sum(loss);   // exactly one lane held the CE term
+    if (lane == 0) {
+      float l = loss + att_scale * (1.f + dv.ent) * hc;
+      float g0 = 0.f, g1 = 0.f;
+      if (flags & LOSS_ADV_VIDEO) {
+        l += -(dom ? dv.lq1 : dv.lq0) / (float)M;
+        g0 = (dv.q0 - (dom ? 0.f : 1.f)) / (float)M;
+        g1 = (dv.q1 - (dom ? 1.f : 0.f)) / (float)M;
+      }
+      g0 += att_scale * hc * (-dv.q0 * (dv.lq0 + dv.ent));
+      g1 += att_scale * hc * (-dv.q1 * (dv.lq1 + dv.ent));
+      g_dom[(size_t)m * 2] = g0;
+      g_dom[(size_t)m * 2 + 1] = g1;
+      loss = l;
+    }
+    // relation-level and frame-level domain logits: one lane per (relation | frame)
+    float extra = 0.f;
+    for (int i = lane; i < R; i += 32) {
+      const size_t o = ((size_t)m * R + i) * 2;
+      float g0 = 0.f, g1 = 0.f;
+      if (flags & LOSS_ADV_REL) {
+        const Attn2 a = attn_from_logits(pred_rel[o], pred_rel[o + 1]);
+        const float inv = 1.f / ((float)M * (float)R);
+        extra += -(dom ? a.lq1 : a.lq0) * inv;
+        g0 = (a.q0 - (dom ? 0.f : 1.f)) * inv;
+        g1 = (a.q1 - (dom ? 1.f : 0.f)) * inv;
+      }
+      g_rel[o] = g0;
+      g_rel[o + 1] = g1;
+    }
+    for (int t = lane; t < T; t += 32) {
+      const size_t o = ((size_t)m * T + t) * 2;
+      float g0 = 0.f, g1 = 0.f;
+      if (flags & LOSS_ADV_FRAME) {
+        const Attn2 a = attn_from_logits(pred_frame[o], pred_frame[o + 1]);
+        const float inv = 1.f / ((float)M * (float)T);
+        extra += -(dom ? a.lq1 : a.lq0) * inv;
+        g0 = (a.q0 - (dom ? 0.f : 1.f)) * inv;
+        g1 = (a.q1 - (dom ? 1.f : 0.f)) * inv;
+      }
+      g_frame[o] = g0;
+      g_frame[o + 1] = g1;
+    }
+    extra = warp_sum(extra);
+    if (lane == 0) row_loss[m] = loss + extra;
+  }
+}
+
+// deterministic sum of row_loss[0..M) -> out[0]  (single block, fixed tree)
+__global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ row_loss, int M,
+                                                           float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) s += row_loss[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[0] = t;
+  }
+}
+
+__global__ void counter_inc_kernel(unsigned long long* ctr) { ctr[0] += 1ull; }
+
 // ---- deterministic column sums (bias gradients) ------------------------------------------------
 struct ColsumJob {
   const float* X[4];

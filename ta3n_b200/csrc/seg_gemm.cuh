@@ -349,7 +349,7 @@ inline void plan_splitk(GemmPlan& plan, Arena* arena, int bm, int bn, int bk, in
     int want = (int)((target_ctas + tiles - 1) / tiles);
     int maxsplit = (int)(chunks / min_chunks);
     int ks = want < maxsplit ? want : maxsplit;
-    if (ks > 16) ks = 16;
+    if (ks > 8) ks = 8;
     if (ks < 2) continue;
     float* p = arena->floats((size_t)ks * g.M * g.N);
     if (!p) continue;  // not enough workspace: stay unsplit (still correct)

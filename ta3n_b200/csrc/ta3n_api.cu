@@ -78,9 +78,10 @@ void set_dropout_epilogue(Group& g, const DropArgs& d, const uint8_t* keep, int 
 inline cudaStream_t S(ta3n_stream_t s) { return static_cast<cudaStream_t>(s); }
 
 // Upper bound of the split-K partial buffers plan_splitk() may carve for `n_groups` outputs:
-// sum_g ksplit_g * M_g * N_g <= (target_ctas + tiles) * 64*64 <= 2 * 296 * 4096 floats.
+// sum_g ksplit_g * M_g * N_g <= (target_ctas + tiles) * tile_elems <= 2 * 296 * 128*128 floats
+// (tile_elems of the tensor-core engine; the SIMT engine's 64x64 tiles need a quarter of that).
 inline size_t splitk_bytes(int n_groups) {
-  return (size_t)2 * 296 * 4096 * sizeof(float) + (size_t)256 * (n_groups + 1) + 4096;
+  return (size_t)2 * 296 * 128 * 128 * sizeof(float) + (size_t)256 * (n_groups + 1) + 4096;
 }
 
 }  // namespace
@@ -636,6 +637,40 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
     TA3N_TRY(cs.run(st));
   }
   return TA3N_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused loss heads (main.py:446, 508-538, 559-562; loss.py:15-25)
+// ------------------------------------------------------------------------------------------------
+size_t ta3n_loss_workspace_bytes(int M) { return Arena::round((size_t)M * sizeof(float)) + 256; }
+
+int ta3n_loss_fwd_bwd(const float* pred_video, const long long* labels, const float* pred_rel,
+                      const float* pred_dom_video, const float* pred_frame, int Bs, int Bt, int T, int R, int C,
+                      float gamma, int flags, float* loss, float* g_pred_video, float* g_pred_rel,
+                      float* g_pred_dom_video, float* g_pred_frame, void* workspace, size_t workspace_bytes,
+                      ta3n_stream_t stream) {
+  TA3N_REQUIRE(Bs >= 1 && Bt >= 0 && T >= 1 && R >= 1 && C >= 1, "bad sizes");
+  TA3N_REQUIRE(pred_video && labels && pred_rel && pred_dom_video && pred_frame && loss, "null input");
+  TA3N_REQUIRE(g_pred_video && g_pred_rel && g_pred_dom_video && g_pred_frame, "null gradient output");
+  const int M = Bs + Bt;
+  Arena arena(workspace, workspace_bytes);
+  float* row_loss = arena.floats(M);
+  if (!row_loss) return fail(TA3N_ERR_WORKSPACE, "ta3n_loss_fwd_bwd: workspace too small (%zu bytes)", workspace_bytes);
+  pre_launch("loss_heads", S(stream));
+  loss_heads_kernel<<<blocks_for((size_t)M * 32, 256), 256, 0, S(stream)>>>(
+      pred_video, labels, pred_rel, pred_dom_video, pred_frame, Bs, M, T, R, C, gamma, flags, g_pred_video,
+      g_pred_rel, g_pred_dom_video, g_pred_frame, row_loss);
+  TA3N_TRY(after_launch());
+  pre_launch("loss_reduce", S(stream));
+  loss_reduce_kernel<<<1, 1024, 0, S(stream)>>>(row_loss, M, loss);
+  return after_launch();
+}
+
+int ta3n_counter_inc(uint64_t* counter, ta3n_stream_t stream) {
+  TA3N_REQUIRE(counter != nullptr, "null counter");
+  pre_launch("counter_inc", S(stream));
+  counter_inc_kernel<<<1, 1, 0, S(stream)>>>(reinterpret_cast<unsigned long long*>(counter));
+  return after_launch();
 }
 
 // ------------------------------------------------------------------------------------------------

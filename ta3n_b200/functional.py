@@ -202,8 +202,164 @@ def _split_params(params, R):
     return shared, fdisc, trn_w, trn_b, r_w1, r_b1, r_w2, r_b2, cls, vdisc
 
 
+class Buffers:
+    """Named scratch tensors.  ``persistent=False``: fresh torch.empty per request (autograd path, the
+    caching allocator recycles them).  ``persistent=True``: allocated once and reused on every call --
+    what a captured CUDA graph needs (fixed addresses)."""
+
+    def __init__(self, device, persistent: bool = False):
+        self.device = device
+        self.persistent = persistent
+        self.pool = {}
+
+    def get(self, name, *shape, dtype=torch.float32):
+        if not self.persistent:
+            return torch.empty(*shape, device=self.device, dtype=dtype)
+        t = self.pool.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(*shape, device=self.device, dtype=dtype)
+            self.pool[name] = t
+        return t
+
+    def workspace(self, name, nbytes):
+        return self.get("ws_" + name, max(int(nbytes), 256), dtype=torch.uint8)
+
+
+def path_forward(spec: PathSpec, xs, xt, params, bufs: Buffers):
+    """The six forward C calls of the path.  Returns (saved tensors dict, outputs tuple, dims)."""
+    lib = _lib.load()
+    st = _stream()
+    T = spec.num_segments
+    if xs.dim() != 3 or xt.dim() != 3 or xs.shape[1] != T or xt.shape[1] != T or xs.shape[2] != xt.shape[2]:
+        raise _lib.Ta3nError(f"inputs must be (B,{T},D); got {tuple(xs.shape)} and {tuple(xt.shape)}")
+    Bs, Bt, D = xs.shape[0], xt.shape[0], xs.shape[2]
+    M, R = Bs + Bt, T - 1
+    rs = relation_set(T)
+    (w_sh, b_sh), (w1f, b1f, w2f, b2f), trn_w, trn_b, r_w1, r_b1, r_w2, r_b2, (w_c, b_c), \
+        (w1v, b1v, w2v, b2v) = _split_params(params, R)
+    F, H, Cn = w_sh.shape[0], trn_w[0].shape[0], w_c.shape[0]
+    new = bufs.get
+    d_i, d_v = spec.drop_i.cstruct(), spec.drop_v.cstruct()
+
+    # 1. shared layer  (models.py:565-575)
+    feat = new("feat", M * T, F)
+    check(lib.ta3n_shared_fc_fwd(_p(xs), Bs * T, _p(xt), Bt * T, D, _p(w_sh), _p(b_sh), F, _dref(d_i),
+                                 _p(feat), st))
+    # 2. frame-level discriminator  (models.py:606-610)
+    hid_f, pred_frame = new("hid_f", M * T, F), new("pred_frame", M * T, 2)
+    check(lib.ta3n_disc_fwd(_p(feat), M * T, F, F, _p(w1f), _p(b1f), _p(w2f), _p(b2f), _p(hid_f),
+                            _p(pred_frame), st))
+    # 2b. frame attention  (models.py:612-614)
+    if spec.use_attn_frame:
+        feat_in = new("feat_in", M * T, F)
+        check(lib.ta3n_frame_attn_fwd(_p(feat), _p(pred_frame), M * T, F, _p(feat_in), st))
+    else:
+        feat_in = feat
+    # 3. TRN  (models.py:635-636).  feat_in >= 0 (post ReLU/dropout, attention factor > 0): the
+    #    leading nn.ReLU of fc_fusion is an identity in value and gradient -> relu_input=0.
+    act, feat_rel = new("act", rs.n_rel, M, H), new("feat_rel", M, R, H)
+    check(lib.ta3n_trn_fwd(_p(feat_in), M, F, H, rs.ref, ptr_array([_p(w) for w in trn_w]),
+                           ptr_array([_p(b) for b in trn_b]), 0, _p(act), _p(feat_rel), st))
+    # 4. relation discriminators + attention + pooling  (models.py:639-652)
+    hid_r, pred_rel = new("hid_r", R, M, H), new("pred_rel", M, R, 2)
+    attn, feat_video = new("attn", M, R), new("feat_video", M, H)
+    check(lib.ta3n_relattn_fwd(_p(feat_rel), M, R, H, ptr_array([_p(w) for w in r_w1]),
+                               ptr_array([_p(b) for b in r_b1]), ptr_array([_p(w) for w in r_w2]),
+                               ptr_array([_p(b) for b in r_b2]), int(spec.use_attn), _p(hid_r), _p(pred_rel),
+                               _p(attn), _p(feat_video), st))
+    # 5. video head  (models.py:679-687)
+    dropped, pred_video = new("dropped", M, H), new("pred_video", M, Cn)
+    check(lib.ta3n_video_head_fwd(_p(feat_video), M, H, Cn, _p(w_c), _p(b_c), _dref(d_v), _p(dropped),
+                                  _p(pred_video), st))
+    # 6. video-level discriminator  (models.py:694-698)
+    hid_v, pred_dom_video = new("hid_v", M, H), new("pred_dom_video", M, 2)
+    check(lib.ta3n_disc_fwd(_p(dropped), M, H, H, _p(w1v), _p(b1v), _p(w2v), _p(b2v), _p(hid_v),
+                            _p(pred_dom_video), st))
+
+    saved = dict(feat=feat, hid_f=hid_f, pred_frame=pred_frame, feat_in=feat_in, act=act, feat_rel=feat_rel,
+                 hid_r=hid_r, pred_rel=pred_rel, attn=attn, dropped=dropped, hid_v=hid_v)
+    outputs = (feat.view(M, T, F), pred_frame.view(M, T, 2), attn, pred_rel, feat_video, pred_video,
+               pred_dom_video)
+    return saved, outputs, (Bs, Bt, D, T, F, H, Cn)
+
+
+def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: Buffers):
+    """The backward C calls in their fixed order.  ``gin``: dict of incoming output gradients
+    (feat, pred_frame, attn, pred_rel, feat_video, pred_video, pred_dom_video; missing/None = zero).
+    ``gout``: list of tensors (same order as ``params``) that receive the parameter gradients."""
+    lib = _lib.load()
+    st = _stream()
+    Bs, Bt, D, T, F, H, Cn = dims
+    M, R = Bs + Bt, T - 1
+    rs = relation_set(T)
+    (w_sh, b_sh), (w1f, b1f, w2f, b2f), trn_w, trn_b, r_w1, r_b1, r_w2, r_b2, (w_c, b_c), \
+        (w1v, b1v, w2v, b2v) = _split_params(params, R)
+    (dw_sh, db_sh), (dw1f, db1f, dw2f, db2f), dtrn_w, dtrn_b, dr_w1, dr_b1, dr_w2, dr_b2, (dw_c, db_c), \
+        (dw1v, db1v, dw2v, db2v) = _split_params(gout, R)
+    g = lambda k: gin.get(k)   # noqa: E731
+    new, wsp = bufs.get, bufs.workspace
+    d_v = spec.drop_v.cstruct()
+    feat, hid_f, pred_frame, feat_in = saved["feat"], saved["hid_f"], saved["pred_frame"], saved["feat_in"]
+    act, feat_rel, hid_r, pred_rel = saved["act"], saved["feat_rel"], saved["hid_r"], saved["pred_rel"]
+    attn, dropped, hid_v = saved["attn"], saved["dropped"], saved["hid_v"]
+
+    # 6'. video discriminator: d_dropped = -beta1 * dgrad
+    d_dropped = new("d_dropped", M, H)
+    ws = wsp("disc_v", lib.ta3n_disc_bwd_workspace_bytes(M, H, H))
+    check(lib.ta3n_disc_bwd(_p(dropped), M, H, H, _p(w1v), _p(w2v), _p(hid_v), _p(g("pred_dom_video")),
+                            float(spec.beta[1]), _p(d_dropped), 0, _p(dw1v), _p(db1v), _p(dw2v), _p(db2v),
+                            _p(ws), ws.numel(), st))
+    # 5'. classifier + dropout_v (+ optional GRL_mu around both heads, models.py:682-684)
+    G = new("G", M, H)
+    ws = wsp("vhead", lib.ta3n_video_head_bwd_workspace_bytes(M, H, Cn))
+    check(lib.ta3n_video_head_bwd(_p(dropped), M, H, Cn, _p(w_c), _dref(d_v), _p(g("pred_video")), _p(d_dropped),
+                                  _p(g("feat_video")), float(-spec.mu) if spec.reverse else 1.0, _p(G),
+                                  _p(dw_c), _p(db_c), _p(ws), ws.numel(), st))
+    # 4'. relation discriminators / attention (attention weights are NOT detached, SURVEY 3.3)
+    d_feat_rel = new("d_feat_rel", M, R, H)
+    ws = wsp("relattn", lib.ta3n_relattn_bwd_workspace_bytes(M, R, H))
+    check(lib.ta3n_relattn_bwd(_p(feat_rel), M, R, H, ptr_array([_p(w) for w in r_w1]),
+                               ptr_array([_p(w) for w in r_w2]), int(spec.use_attn), _p(hid_r), _p(pred_rel),
+                               _p(attn), _p(G), _p(g("pred_rel")), _p(g("attn")), float(spec.beta[0]),
+                               _p(d_feat_rel), ptr_array([_p(t) for t in dr_w1]),
+                               ptr_array([_p(t) for t in dr_b1]), ptr_array([_p(t) for t in dr_w2]),
+                               ptr_array([_p(t) for t in dr_b2]), _p(ws), ws.numel(), st))
+    # 3'. TRN
+    d_feat = new("d_feat", M * T, F)
+    ws = wsp("trn", lib.ta3n_trn_bwd_workspace_bytes(M, F, H, rs.ref))
+    check(lib.ta3n_trn_bwd(_p(feat_in), M, F, H, rs.ref, ptr_array([_p(w) for w in trn_w]), 0, _p(act),
+                           _p(d_feat_rel), ptr_array([_p(t) for t in dtrn_w]),
+                           ptr_array([_p(t) for t in dtrn_b]), _p(d_feat), _p(ws), ws.numel(), st))
+    # 2b'. frame attention (needs a writable copy of the frame-logit gradient)
+    g_pf = g("pred_frame")
+    if g_pf is not None:
+        g_pf = g_pf.reshape(M * T, 2)
+    if spec.use_attn_frame:
+        acc = new("g_pf_acc", M * T, 2)
+        if g_pf is not None:
+            acc.copy_(g_pf)
+        else:
+            acc.zero_()
+        g_pf = acc
+        check(lib.ta3n_frame_attn_bwd(_p(feat), _p(pred_frame), M * T, F, _p(d_feat), _p(g_pf), st))
+    # 2'. frame discriminator: d_feat += -beta2 * dgrad
+    ws = wsp("disc_f", lib.ta3n_disc_bwd_workspace_bytes(M * T, F, F))
+    check(lib.ta3n_disc_bwd(_p(feat), M * T, F, F, _p(w1f), _p(w2f), _p(hid_f), _p(g_pf),
+                            float(spec.beta[2]), _p(d_feat), 1, _p(dw1f), _p(db1f), _p(dw2f), _p(db2f),
+                            _p(ws), ws.numel(), st))
+    # 1'. shared layer (wgrad only; the input features carry no gradient)
+    ws = wsp("shared", lib.ta3n_shared_fc_bwd_workspace_bytes(M * T, D, F))
+    g_feat = g("feat")
+    g_feat_flat = None if g_feat is None else g_feat.reshape(M * T, F)
+    check(lib.ta3n_shared_fc_bwd(_p(xs), Bs * T, _p(xt), Bt * T, D, F, _p(feat), _p(d_feat), _p(g_feat_flat),
+                                 float(spec.drop_i.p), _p(dw_sh), _p(db_sh), _p(ws), ws.numel(), st))
+
+
+_OUT_NAMES = ("feat", "pred_frame", "attn", "pred_rel", "feat_video", "pred_video", "pred_dom_video")
+
+
 class _VideoPathFunction(torch.autograd.Function):
-    """VideoModel.forward, trn-m branch, source and target rows processed together.
+    """VideoModel.forward, trn-m branch, source and target rows processed together, as ONE autograd node.
 
     Outputs (all for M = Bs + Bt rows, source rows first):
       feat_fc (M,T,F) | pred_frame (M,T,2) | attn (M,R) | pred_rel (M,R,2) | feat_video (M,H) |
@@ -212,146 +368,30 @@ class _VideoPathFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec: PathSpec, xs, xt, *params):
-        lib = _lib.load()
-        st = _stream()
         xs, xt = _chk(xs, "input_source"), _chk(xt, "input_target")
         params = [_chk(p, "parameter") for p in params]
-        T = spec.num_segments
-        if xs.dim() != 3 or xt.dim() != 3 or xs.shape[1] != T or xt.shape[1] != T or xs.shape[2] != xt.shape[2]:
-            raise _lib.Ta3nError(f"inputs must be (B,{T},D); got {tuple(xs.shape)} and {tuple(xt.shape)}")
-        Bs, Bt, D = xs.shape[0], xt.shape[0], xs.shape[2]
-        M, R = Bs + Bt, T - 1
-        rs = relation_set(T)
-        (w_sh, b_sh), (w1f, b1f, w2f, b2f), trn_w, trn_b, r_w1, r_b1, r_w2, r_b2, (w_c, b_c), \
-            (w1v, b1v, w2v, b2v) = _split_params(params, R)
-        F, H, Cn = w_sh.shape[0], trn_w[0].shape[0], w_c.shape[0]
-        dev = xs.device
-        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)   # noqa: E731
-
-        d_i, d_v = spec.drop_i.cstruct(), spec.drop_v.cstruct()
-
-        # 1. shared layer  (models.py:565-575)
-        feat = new(M * T, F)
-        check(lib.ta3n_shared_fc_fwd(_p(xs), Bs * T, _p(xt), Bt * T, D, _p(w_sh), _p(b_sh), F, _dref(d_i),
-                                     _p(feat), st))
-        # 2. frame-level discriminator  (models.py:606-610)
-        hid_f, pred_frame = new(M * T, F), new(M * T, 2)
-        check(lib.ta3n_disc_fwd(_p(feat), M * T, F, F, _p(w1f), _p(b1f), _p(w2f), _p(b2f), _p(hid_f),
-                                _p(pred_frame), st))
-        # 2b. frame attention  (models.py:612-614)
-        if spec.use_attn_frame:
-            feat_in = new(M * T, F)
-            check(lib.ta3n_frame_attn_fwd(_p(feat), _p(pred_frame), M * T, F, _p(feat_in), st))
-        else:
-            feat_in = feat
-        # 3. TRN  (models.py:635-636).  feat_in >= 0 (post ReLU/dropout, attention factor > 0): the
-        #    leading nn.ReLU of fc_fusion is an identity in value and gradient -> relu_input=0.
-        act, feat_rel = new(rs.n_rel, M, H), new(M, R, H)
-        check(lib.ta3n_trn_fwd(_p(feat_in), M, F, H, rs.ref, ptr_array([_p(w) for w in trn_w]),
-                               ptr_array([_p(b) for b in trn_b]), 0, _p(act), _p(feat_rel), st))
-        # 4. relation discriminators + attention + pooling  (models.py:639-652)
-        hid_r, pred_rel, attn, feat_video = new(R, M, H), new(M, R, 2), new(M, R), new(M, H)
-        check(lib.ta3n_relattn_fwd(_p(feat_rel), M, R, H, ptr_array([_p(w) for w in r_w1]),
-                                   ptr_array([_p(b) for b in r_b1]), ptr_array([_p(w) for w in r_w2]),
-                                   ptr_array([_p(b) for b in r_b2]), int(spec.use_attn), _p(hid_r), _p(pred_rel),
-                                   _p(attn), _p(feat_video), st))
-        # 5. video head  (models.py:679-687)
-        dropped, pred_video = new(M, H), new(M, Cn)
-        check(lib.ta3n_video_head_fwd(_p(feat_video), M, H, Cn, _p(w_c), _p(b_c), _dref(d_v), _p(dropped),
-                                      _p(pred_video), st))
-        # 6. video-level discriminator  (models.py:694-698)
-        hid_v, pred_dom_video = new(M, H), new(M, 2)
-        check(lib.ta3n_disc_fwd(_p(dropped), M, H, H, _p(w1v), _p(b1v), _p(w2v), _p(b2v), _p(hid_v),
-                                _p(pred_dom_video), st))
-
-        ctx.spec = spec
-        ctx.dims = (Bs, Bt, D, T, F, H, Cn)
+        saved, outputs, dims = path_forward(spec, xs, xt, params, Buffers(xs.device))
+        ctx.spec, ctx.dims = spec, dims
+        ctx.saved_names = list(saved)
         ctx.drop_keepalive = (spec.drop_i.keep, spec.drop_v.keep, spec.drop_i.step, spec.drop_v.step)
-        ctx.save_for_backward(xs, xt, feat, hid_f, pred_frame, feat_in, act, feat_rel, hid_r, pred_rel, attn,
-                              dropped, hid_v, *params)
+        ctx.save_for_backward(xs, xt, *[saved[k] for k in ctx.saved_names], *params)
         ctx.set_materialize_grads(False)
-        return (feat.view(M, T, F), pred_frame.view(M, T, 2), attn, pred_rel, feat_video, pred_video,
-                pred_dom_video)
+        return outputs
 
     @staticmethod
-    def backward(ctx, g_feat, g_pred_frame, g_attn, g_pred_rel, g_feat_video, g_pred_video, g_pred_dom_video):
-        lib = _lib.load()
-        st = _stream()
-        spec: PathSpec = ctx.spec
-        Bs, Bt, D, T, F, H, Cn = ctx.dims
-        M, R = Bs + Bt, T - 1
-        rs = relation_set(T)
-        (xs, xt, feat, hid_f, pred_frame, feat_in, act, feat_rel, hid_r, pred_rel, attn, dropped, hid_v,
-         *params) = ctx.saved_tensors
+    def backward(ctx, *grads):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             raise _lib.Ta3nError("gradients w.r.t. the input features are not part of this path "
                                  "(the reference's features carry no grad, SURVEY 3.3)")
-        (w_sh, b_sh), (w1f, b1f, w2f, b2f), trn_w, trn_b, r_w1, r_b1, r_w2, r_b2, (w_c, b_c), \
-            (w1v, b1v, w2v, b2v) = _split_params(params, R)
-        dev = xs.device
-        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)   # noqa: E731
-        like = lambda ts: [torch.empty_like(t) for t in ts]                          # noqa: E731
-        g_feat, g_pred_frame, g_attn, g_pred_rel, g_feat_video, g_pred_video, g_pred_dom_video = [
-            _chk(t, "grad") for t in (g_feat, g_pred_frame, g_attn, g_pred_rel, g_feat_video, g_pred_video,
-                                      g_pred_dom_video)]
-        d_v = spec.drop_v.cstruct()
-
-        # 6'. video discriminator: d_dropped = -beta1 * dgrad
-        dw1v, db1v, dw2v, db2v = like([w1v, b1v, w2v, b2v])
-        d_dropped = new(M, H)
-        ws = _ws(lib.ta3n_disc_bwd_workspace_bytes(M, H, H), xs)
-        check(lib.ta3n_disc_bwd(_p(dropped), M, H, H, _p(w1v), _p(w2v), _p(hid_v), _p(g_pred_dom_video),
-                                float(spec.beta[1]), _p(d_dropped), 0, _p(dw1v), _p(db1v), _p(dw2v), _p(db2v),
-                                _p(ws), ws.numel(), st))
-        # 5'. classifier + dropout_v (+ optional GRL_mu around both heads, models.py:682-684)
-        dw_c, db_c = like([w_c, b_c])
-        G = new(M, H)
-        ws = _ws(lib.ta3n_video_head_bwd_workspace_bytes(M, H, Cn), xs)
-        check(lib.ta3n_video_head_bwd(_p(dropped), M, H, Cn, _p(w_c), _dref(d_v), _p(g_pred_video), _p(d_dropped),
-                                      _p(g_feat_video), float(-spec.mu) if spec.reverse else 1.0, _p(G),
-                                      _p(dw_c), _p(db_c), _p(ws), ws.numel(), st))
-        # 4'. relation discriminators / attention (attention weights are NOT detached)
-        dr_w1, dr_b1, dr_w2, dr_b2 = like(r_w1), like(r_b1), like(r_w2), like(r_b2)
-        d_feat_rel = new(M, R, H)
-        ws = _ws(lib.ta3n_relattn_bwd_workspace_bytes(M, R, H), xs)
-        check(lib.ta3n_relattn_bwd(_p(feat_rel), M, R, H, ptr_array([_p(w) for w in r_w1]),
-                                   ptr_array([_p(w) for w in r_w2]), int(spec.use_attn), _p(hid_r), _p(pred_rel),
-                                   _p(attn), _p(G), _p(g_pred_rel), _p(g_attn), float(spec.beta[0]),
-                                   _p(d_feat_rel), ptr_array([_p(t) for t in dr_w1]),
-                                   ptr_array([_p(t) for t in dr_b1]), ptr_array([_p(t) for t in dr_w2]),
-                                   ptr_array([_p(t) for t in dr_b2]), _p(ws), ws.numel(), st))
-        # 3'. TRN
-        dtrn_w, dtrn_b = like(trn_w), like(trn_b)
-        d_feat = new(M * T, F)
-        ws = _ws(lib.ta3n_trn_bwd_workspace_bytes(M, F, H, rs.ref), xs)
-        check(lib.ta3n_trn_bwd(_p(feat_in), M, F, H, rs.ref, ptr_array([_p(w) for w in trn_w]), 0, _p(act),
-                               _p(d_feat_rel), ptr_array([_p(t) for t in dtrn_w]),
-                               ptr_array([_p(t) for t in dtrn_b]), _p(d_feat), _p(ws), ws.numel(), st))
-        # 2b'. frame attention
-        if g_pred_frame is not None:
-            g_pf = g_pred_frame.reshape(M * T, 2)
-            if spec.use_attn_frame:
-                g_pf = g_pf.clone()
-        else:
-            g_pf = torch.zeros(M * T, 2, device=dev, dtype=torch.float32) if spec.use_attn_frame else None
-        if spec.use_attn_frame:
-            check(lib.ta3n_frame_attn_bwd(_p(feat), _p(pred_frame), M * T, F, _p(d_feat), _p(g_pf), st))
-        # 2'. frame discriminator: d_feat += -beta2 * dgrad
-        dw1f, db1f, dw2f, db2f = like([w1f, b1f, w2f, b2f])
-        ws = _ws(lib.ta3n_disc_bwd_workspace_bytes(M * T, F, F), xs)
-        check(lib.ta3n_disc_bwd(_p(feat), M * T, F, F, _p(w1f), _p(w2f), _p(hid_f), _p(g_pf),
-                                float(spec.beta[2]), _p(d_feat), 1, _p(dw1f), _p(db1f), _p(dw2f), _p(db2f),
-                                _p(ws), ws.numel(), st))
-        # 1'. shared layer (wgrad only)
-        dw_sh, db_sh = like([w_sh, b_sh])
-        ws = _ws(lib.ta3n_shared_fc_bwd_workspace_bytes(M * T, D, F), xs)
-        g_feat_flat = None if g_feat is None else g_feat.reshape(M * T, F)
-        check(lib.ta3n_shared_fc_bwd(_p(xs), Bs * T, _p(xt), Bt * T, D, F, _p(feat), _p(d_feat), _p(g_feat_flat),
-                                     float(spec.drop_i.p), _p(dw_sh), _p(db_sh), _p(ws), ws.numel(), st))
-
-        grads = [dw_sh, db_sh, dw1f, db1f, dw2f, db2f, *dtrn_w, *dtrn_b, *dr_w1, *dr_b1, *dr_w2, *dr_b2,
-                 dw_c, db_c, dw1v, db1v, dw2v, db2v]
-        return (None, None, None, *grads)
+        tensors = ctx.saved_tensors
+        xs, xt = tensors[0], tensors[1]
+        n = len(ctx.saved_names)
+        saved = dict(zip(ctx.saved_names, tensors[2:2 + n]))
+        params = list(tensors[2 + n:])
+        gin = {k: _chk(g, "grad") for k, g in zip(_OUT_NAMES, grads) if g is not None}
+        gout = [torch.empty_like(p) for p in params]
+        path_backward(ctx.spec, ctx.dims, xs, xt, params, saved, gin, gout, Buffers(xs.device))
+        return (None, None, None, *gout)
 
 
 def video_path(spec: PathSpec, xs: torch.Tensor, xt: torch.Tensor, params: Sequence[torch.Tensor]):

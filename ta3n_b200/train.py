@@ -1,0 +1,136 @@
+"""Fused training step of the path: forward + loss heads + backward as a fixed sequence of C-ABI
+calls (no autograd graph, no torch ops), optionally captured in ONE CUDA graph.
+
+This is lines 418-576 of the reference's ``main.py`` for the shipped configuration
+(use_target='uSv', adv_DA='RevGrad', add_loss_DA='attentive_entropy'):
+    model(source, target, beta, mu, is_train=True, reverse=False)          main.py:418
+    CE + 3 domain CEs + gamma * attentive_entropy                          main.py:446, 508-538, 559-562
+    loss.backward()                                                        main.py:576
+Gradients land directly in a flat fp32 bucket whose views are installed as ``param.grad``, so a stock
+``torch.optim`` optimizer and ``clip_grad_norm_`` work unchanged, and data parallelism is one
+all-reduce over that bucket (parameters the path never uses keep ``grad=None``, as in the reference).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import functional as TF
+from ._lib import check
+
+_P = TF._p
+
+
+class TrainStep:
+    def __init__(self, model, batch_source: int, batch_target: int, beta: Sequence[float], gamma: float = 0.003,
+                 place_adv: Sequence[str] = ("Y", "Y", "Y"), add_loss_DA: str = "attentive_entropy",
+                 use_graph: bool = True, process_group=None, seed: int = 0x5EED):
+        if not model.training:
+            raise ValueError("TrainStep needs model.train() (dropout state is fixed at construction)")
+        self.model = model
+        self.params = model.path_parameters()
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise _lib.Ta3nError("TrainStep needs the model on a CUDA device; there is no CPU path")
+        self.device = dev
+        self.Bs, self.Bt = int(batch_source), int(batch_target)
+        self.T, self.D = model.train_segments, model.feature_dim
+        self.M, self.R = self.Bs + self.Bt, self.T - 1
+        self.C = model.fc_classifier_video_source.weight.shape[0]
+        self.gamma = float(gamma)
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.flags = (1 if place_adv[0] == "Y" else 0) | (2 if place_adv[1] == "Y" else 0) | \
+                     (4 if place_adv[2] == "Y" else 0)
+        if add_loss_DA == "attentive_entropy" and model.use_attn != "none":
+            if place_adv[0] != "Y" or place_adv[1] != "Y":
+                # main.py:560 indexes pred_domain_all[1], the video level only when both are on
+                raise NotImplementedError("attentive_entropy needs place_adv[0] == place_adv[1] == 'Y'")
+            self.flags |= 8
+
+        # flat gradient bucket; views installed as .grad
+        n = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.grad_views, off = [], 0
+        for p in self.params:
+            v = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            self.grad_views.append(v)
+            p.grad = v
+
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.xs = torch.zeros(self.Bs, self.T, self.D, **f32)
+        self.xt = torch.zeros(self.Bt, self.T, self.D, **f32)
+        self.labels = torch.zeros(self.Bs, device=dev, dtype=torch.int64)
+        self.loss = torch.zeros(1, **f32)
+        self.g_video = torch.zeros(self.M, self.C, **f32)
+        self.g_rel = torch.zeros(self.M, self.R, 2, **f32)
+        self.g_dom = torch.zeros(self.M, 2, **f32)
+        self.g_frame = torch.zeros(self.M * self.T, 2, **f32)
+        self.step_counter = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.bufs = TF.Buffers(dev, persistent=True)
+        self.loss_ws = self.bufs.workspace("loss", _lib.load().ta3n_loss_workspace_bytes(self.M))
+
+        di, dv = float(model.dropout_rate_i), float(model.dropout_rate_v)
+        self.spec = TF.PathSpec(
+            num_segments=self.T, beta=(float(beta[0]), float(beta[1]), float(beta[2])), mu=0.0, reverse=False,
+            use_attn=model.use_attn != "none", use_attn_frame=model.use_attn_frame != "none",
+            drop_i=TF.DropSpec(p=di, seed=seed, step=self.step_counter) if di > 0 else TF.DropSpec(),
+            drop_v=TF.DropSpec(p=dv, seed=seed ^ 0x9E3779B9, step=self.step_counter) if dv > 0 else TF.DropSpec())
+        self.outputs = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        if use_graph:
+            self._capture()
+
+    # -- the fixed launch sequence ---------------------------------------------------------------------
+    def _enqueue(self):
+        lib = _lib.load()
+        st = TF._stream()
+        check(lib.ta3n_counter_inc(_P(self.step_counter), st))          # fresh dropout masks per step
+        saved, outputs, dims = TF.path_forward(self.spec, self.xs, self.xt, self.params, self.bufs)
+        self.outputs = outputs
+        _, pred_frame, _, pred_rel, _, pred_video, pred_dom = outputs
+        check(lib.ta3n_loss_fwd_bwd(_P(pred_video), _P(self.labels), _P(pred_rel), _P(pred_dom), _P(pred_frame),
+                                    self.Bs, self.Bt, self.T, self.R, self.C, self.gamma, self.flags,
+                                    _P(self.loss), _P(self.g_video), _P(self.g_rel), _P(self.g_dom),
+                                    _P(self.g_frame), _P(self.loss_ws), self.loss_ws.numel(), st))
+        gin = {"pred_video": self.g_video, "pred_rel": self.g_rel, "pred_dom_video": self.g_dom,
+               "pred_frame": self.g_frame}
+        TF.path_backward(self.spec, dims, self.xs, self.xt, self.params, saved, gin, self.grad_views, self.bufs)
+
+    def _capture(self):
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._enqueue()                      # warm-up: sizes every buffer, sets kernel attributes
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue()
+        self.graph = g
+
+    # -- public API ------------------------------------------------------------------------------------
+    def load(self, source, target, labels):
+        """Copy one paired mini-batch (host or device tensors) into the step's static input buffers."""
+        self.xs.copy_(source.reshape(self.xs.shape), non_blocking=True)
+        self.xt.copy_(target.reshape(self.xt.shape), non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+
+    def run(self):
+        """forward + loss + backward (+ gradient all-reduce); returns the device loss tensor (1,)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat_grad.mul_(1.0 / self.world)
+        return self.loss
+
+    def __call__(self, source, target, labels):
+        self.load(source, target, labels)
+        return self.run()

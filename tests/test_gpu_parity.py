@@ -17,6 +17,13 @@ pytestmark = pytest.mark.gpu
 
 ENGINES = ["fp32", "tf32"]
 TOL = {"fp32": 2e-4, "tf32": TOL_PATH}
+# Gradients under the tf32 engine, compared with the fp64 network WITHOUT pinning the activation
+# pattern: every product is accurate to ~3e-4, but ~2e-4 of the ReLU units sit within rounding error
+# of zero and flip, and each flip moves a gradient entry by O(1) -> normwise ~sqrt(2e-4) ~ 1-2.5e-2
+# (measured, tools/parity_report.py).  Inherent to ANY reduced-precision forward (cuBLAS TF32 and bf16
+# included).  With the realised pattern pinned the gradients agree to 2e-3 again
+# (test_tf32_gradients_match_oracle_on_realised_activation_pattern).
+GRAD_TOL = {"fp32": 2 * 2e-4, "tf32": 5e-2}
 
 
 def _dev():
@@ -91,7 +98,7 @@ def test_model_matches_reference_golden(case, engine):
     assert_close(loss, z[f"{case}/loss"], tol, "loss")
     check_outputs_against_golden(z, case, outs, tol, meta["stride"])
     used = meta["used_params"][case]
-    check_grads_against_golden(z, case, grads, used, tol, meta["stride"])
+    check_grads_against_golden(z, case, grads, used, GRAD_TOL[engine] / 2, meta["stride"])
     for name, g in grads.items():          # parameters the reference leaves without grad stay without
         if name not in used:
             assert g is None, name
@@ -126,7 +133,53 @@ def test_model_matches_oracle_mid_size(T, attn_frame, bs, bt, engine):
         assert a.shape == b.shape
         assert_close(a, b, tol, f"output {i}", noise=n_out[i])
     for name, go in grads_o.items():
-        assert_close(grads[name], go, tol * 2, f"grad {name}", noise=n_grad[name])
+        assert_close(grads[name], go, GRAD_TOL[engine], f"grad {name}", noise=n_grad[name])
+
+
+@pytest.mark.parametrize("T,attn_frame,bs,bt", [(5, "none", 48, 40), (6, "TransAttn", 12, 20)])
+def test_tf32_gradients_match_oracle_on_realised_activation_pattern(T, attn_frame, bs, bt):
+    """tf32 engine: with the ReLU on/off pattern of the CUDA forward pinned in the fp64 oracle, loss and
+    every parameter gradient agree to 2e-3 -- i.e. the backward kernels are accurate; the 1-2 % seen
+    without pinning comes only from the handful of units whose pre-activation is within tf32 rounding
+    error of zero."""
+    import ta3n_b200
+    from ta3n_b200.train import TrainStep
+    ta3n_b200.set_gemm_engine("tf32")
+    try:
+        cfg = orc.PathConfig(num_class=12, num_segments=T, fc_dim=512, dropout_i=0.0, dropout_v=0.0,
+                             use_attn="TransAttn", use_attn_frame=attn_frame)
+        params = orc.init_params(cfg, seed=31)
+        g = torch.Generator().manual_seed(9)
+        for k in params:
+            if params[k].dtype.is_floating_point and k.startswith(orc.USED_PARAM_PREFIXES) and "weight" in k:
+                params[k] = params[k] + 0.02 * torch.randn(params[k].shape, generator=g)
+        xs = torch.randn(bs, T, orc.FEATURE_DIM, generator=g)
+        xt = torch.randn(bt, T, orc.FEATURE_DIM, generator=g) + 0.1
+        labels = torch.arange(bs) % cfg.num_class
+        beta = (0.75, 0.75, 0.5)
+        model = build_model(cfg, params, train=True)
+        step = TrainStep(model, bs, bt, beta, gamma=0.003, use_graph=False)
+        loss = step(xs, xt, labels)
+        torch.cuda.synchronize()
+        pool = step.bufs.pool
+        gates = {"shared": (pool["feat"] > 0).cpu(), "frame_disc": (pool["hid_f"] > 0).cpu(),
+                 "trn": [(a > 0).cpu() for a in pool["act"]], "rel_disc": [(h > 0).cpu() for h in pool["hid_r"]],
+                 "video_disc": (pool["hid_v"] > 0).cpu()}
+        p64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in params.items()}
+        plain = orc.activation_pattern(p64, xs.double(), xt.double(), beta, cfg)
+        flips = sum((a != b).sum().item() for a, b in zip(
+            [gates["shared"], gates["frame_disc"], *gates["trn"], *gates["rel_disc"], gates["video_disc"]],
+            [plain["shared"], plain["frame_disc"], *plain["trn"], *plain["rel_disc"], plain["video_disc"]]))
+        total = sum(t.numel() for t in [gates["shared"], gates["frame_disc"], *gates["trn"], *gates["rel_disc"],
+                                        gates["video_disc"]])
+        assert flips / total < 2e-3, (flips, total)           # a tiny fraction of units flips ...
+        l64, _, g64 = orc.train_step(p64, xs.double(), xt.double(), labels, beta, cfg, 0.003, train=True, gates=gates)
+        assert_close(loss.cpu()[0], l64, TOL_PATH, "loss (pinned pattern)")
+        named = dict(model.named_parameters())
+        for name, go in g64.items():                          # ... and with it pinned the gradients agree
+            assert_close(named[name].grad, go, 2e-3, f"grad {name} (pinned pattern)", noise=1e-9)
+    finally:
+        ta3n_b200.set_gemm_engine("fp32")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -149,10 +202,10 @@ def test_trn_module_matches_oracle(T, F, N, engine):
     out.backward(gout.to(_dev()))
     tol = TOL[engine]
     assert_close(out, ref, tol, "trn fwd")
-    assert_close(xg.grad, xo.grad, tol * 2, "trn dx")
+    assert_close(xg.grad, xo.grad, GRAD_TOL[engine], "trn dx")
     for i, seq in enumerate(mod.fc_fusion_scales):
-        assert_close(seq[1].weight.grad, ws[i].grad, tol * 2, f"trn dW{i}")
-        assert_close(seq[1].bias.grad, bs[i].grad, tol * 2, f"trn db{i}")
+        assert_close(seq[1].weight.grad, ws[i].grad, GRAD_TOL[engine], f"trn dW{i}")
+        assert_close(seq[1].bias.grad, bs[i].grad, GRAD_TOL[engine], f"trn db{i}")
 
 
 def test_grad_reverse_matches_reference_semantics():
@@ -271,7 +324,7 @@ def test_full_size_gradient_shards_sum_to_full_batch(engine):
 
     full = grads_of(slice(0, 256))
     h0, h1 = grads_of(slice(0, 128)), grads_of(slice(128, 256))
-    tol = 5e-4 if engine == "fp32" else 2 * TOL_PATH
+    tol = 5e-4 if engine == "fp32" else GRAD_TOL["tf32"]
     for k in full:
         # noise floor: the domain-head bias gradients are sums of opposite-sign halves (~1e-7 left)
         assert_close(0.5 * (h0[k] + h1[k]), full[k], tol, f"shard-sum {k}", noise=2e-8)
@@ -351,3 +404,56 @@ def test_cpu_tensors_are_moved_not_computed_on_cpu():
     with pytest.raises(_lib.Ta3nError):
         TF.trn_multiscale(torch.randn(2, 5, 8), [torch.randn(256, s * 8) for s in (5, 4, 3, 2)],
                           [torch.randn(256) for _ in range(4)])
+
+
+# ------------------------------------------------------------------------------------------------
+# fused loss heads and the fused / graph-captured training step
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("T,attn_frame,bs,bt,C", [(5, "none", 24, 24, 12), (4, "TransAttn", 9, 5, 30)])
+def test_fused_train_step_matches_oracle(T, attn_frame, bs, bt, C, use_graph, engine):
+    """TrainStep (forward + fused loss heads + backward, no autograd) vs the fp64 oracle's
+    loss and parameter gradients; dropout off so both see the same function."""
+    from ta3n_b200.train import TrainStep
+    cfg = orc.PathConfig(num_class=C, num_segments=T, fc_dim=512, dropout_i=0.0, dropout_v=0.0,
+                         use_attn="TransAttn", use_attn_frame=attn_frame)
+    params = orc.init_params(cfg, seed=21)
+    g = torch.Generator().manual_seed(8)
+    for k in params:
+        if params[k].dtype.is_floating_point and k.startswith(orc.USED_PARAM_PREFIXES) and "weight" in k:
+            params[k] = params[k] + 0.02 * torch.randn(params[k].shape, generator=g)
+    xs = torch.randn(bs, T, orc.FEATURE_DIM, generator=g)
+    xt = torch.randn(bt, T, orc.FEATURE_DIM, generator=g) - 0.2
+    labels = torch.arange(bs) % C
+    beta = (0.75, 0.6, 0.5)
+    loss_o, _, grads_o, n_loss, _, n_grad = oracle_truth(params, xs, xt, labels, beta, cfg, 0.003, True, None)
+    model = build_model(cfg, params, train=True)
+    step = TrainStep(model, bs, bt, beta, gamma=0.003, use_graph=use_graph)
+    for _ in range(2):                                       # replays are idempotent
+        loss = step(xs.pin_memory(), xt.pin_memory(), labels)
+    torch.cuda.synchronize()
+    tol = TOL[engine]
+    assert_close(loss.cpu()[0], loss_o, tol, "fused loss", noise=n_loss)
+    named = dict(model.named_parameters())
+    for name, go in grads_o.items():
+        assert named[name].grad is not None
+        assert_close(named[name].grad, go, GRAD_TOL[engine], f"fused grad {name}", noise=n_grad[name])
+    assert model.fc_feature_source.weight.grad is None       # off-path parameters stay untouched
+
+
+def test_fused_step_dropout_changes_every_replay():
+    from ta3n_b200.train import TrainStep
+    cfg = orc.PathConfig(num_class=12, num_segments=5, fc_dim=512, dropout_i=0.5, dropout_v=0.5)
+    params = orc.init_params(cfg, seed=1234)
+    model = build_model(cfg, params, train=True)
+    xs, xt, labels = orc.synthetic_batch(32, cfg)
+    step = TrainStep(model, 32, 32, (0.75, 0.75, 0.5), use_graph=True)
+    step.load(xs, xt, labels)
+    step.run()
+    f1 = step.outputs[0].clone()
+    step.run()
+    f2 = step.outputs[0].clone()
+    torch.cuda.synchronize()
+    assert not torch.equal(f1 > 0, f2 > 0)                  # the in-graph counter re-keys the RNG
+    keep = ((f1 > 0).float().mean() / ((f1 > 0) | (f2 > 0)).float().mean()).item()
+    assert 0.55 < keep < 0.8                                 # P(kept | kept in either) = 0.5/0.75

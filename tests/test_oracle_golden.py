@@ -51,3 +51,26 @@ def test_oracle_reproduces_reference_golden(case):
 def test_fingerprint_matches_survey_probe():
     # loss = 4.57745266 for the C=12 fingerprint config
     assert abs(float(Z["fingerprint_c12/loss"]) - 4.57745266) < 5e-7
+
+
+@pytest.mark.parametrize("attn_frame", ["none", "TransAttn"])
+def test_oracle_gates_reproduce_the_plain_run(attn_frame):
+    """Pinning the ReLU pattern to the pattern of the plain run must change nothing (gate plumbing)."""
+    cfg = orc.PathConfig(num_class=7, num_segments=4, fc_dim=64, dropout_i=0.0, dropout_v=0.0,
+                         use_attn_frame=attn_frame)
+    params = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in orc.init_params(cfg, seed=3).items()}
+    xs, xt, labels = orc.synthetic_batch(6, cfg, dtype=torch.float64)
+    xt = xt[:4]
+    beta = (0.75, 0.75, 0.5)
+    l0, _, g0 = orc.train_step(params, xs, xt, labels, beta, cfg, 0.003, train=True)
+    gates = orc.activation_pattern(params, xs, xt, beta, cfg)
+    l1, _, g1 = orc.train_step(params, xs, xt, labels, beta, cfg, 0.003, train=True, gates=gates)
+    assert abs(l0.item() - l1.item()) < 1e-12
+    for k in g0:
+        assert torch.allclose(g0[k], g1[k], rtol=1e-10, atol=1e-14), k
+    # flipping a handful of units changes gradients by far more than rounding: the sqrt(eps) effect
+    flipped = {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in gates.items()}
+    flipped["frame_disc"][0, :8] = ~flipped["frame_disc"][0, :8]
+    _, _, g2 = orc.train_step(params, xs, xt, labels, beta, cfg, 0.003, train=True, gates=flipped)
+    k = "fc_feature_domain.weight"
+    assert (g2[k] - g0[k]).norm() / g0[k].norm() > 1e-3
