@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--fc_dim", type=int, default=512)
     ap.add_argument("--engine", default=os.environ.get("TA3N_ENGINE", "auto"), choices=["auto", "fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -241,6 +242,7 @@ def workload_config(args, world, engine):
                         f"D={D}, fc_dim={args.fc_dim}, {args.classes} classes, TRN-M + TransAttn + RevGrad "
                         f"discriminators (frame/video/relation)",
             "global_batch": 2 * args.batch * world, "per_gpu_clips": 2 * args.batch,
+            "api": "ta3n_b200.train.TrainStep (forward + fused loss heads + backward, one CUDA graph)",
             "step": "forward + composed loss + backward to all parameter gradients"
                     + (" + flat NCCL gradient all-reduce" if world > 1 else ""),
             "optimizer": "excluded from value (metric is fwd+bwd); included in e2e",
@@ -257,7 +259,7 @@ def run_b200(args):
     from ta3n_b200 import _lib
     from ta3n_b200.loss import ta3n_loss
     from ta3n_b200.models import VideoModel
-    from ta3n_b200.parallel import GradientBucket
+    from ta3n_b200.train import TrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -275,23 +277,17 @@ def run_b200(args):
     model = VideoModel(C, "video", "trn-m", "RGB", train_segments=T, val_segments=T, add_fc=1, fc_dim=args.fc_dim,
                        dropout_i=0.5, dropout_v=0.5, partial_bn=False, use_bn="none", ens_DA="none",
                        use_attn="TransAttn", use_attn_frame="none", share_params="Y", verbose=False).to(dev).train()
-    bucket = GradientBucket(model.parameters())
     opt = torch.optim.SGD(model.parameters(), 3e-2, momentum=0.9, weight_decay=1e-4, nesterov=True)
 
     g = torch.Generator().manual_seed(4321 + rank)
     xs_h = torch.randn(B, T, D, generator=g).pin_memory()
     xt_h = torch.randn(B, T, D, generator=g).pin_memory()
     lab_h = (torch.arange(B) % C).pin_memory()
-    xs, xt, labels = xs_h.to(dev), xt_h.to(dev), lab_h.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step(a, b, y):
-        model.zero_grad(set_to_none=True)
-        outs = model(a, b, list(BETA), 0, is_train=True, reverse=False)
-        loss = ta3n_loss(outs, y, GAMMA)
-        loss.backward()
-        bucket.allreduce_mean()
-        return loss
+    # the public training-step API: forward + fused loss heads + backward in one CUDA graph
+    step = TrainStep(model, B, B, BETA, gamma=GAMMA, use_graph=not args.no_graph)
+    step.load(xs_h, xt_h, lab_h)
 
     def barrier():
         if world > 1:
@@ -299,7 +295,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        step(xs, xt, labels)
+        step.run()
     barrier()
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -309,15 +305,14 @@ def run_b200(args):
 
     # ---- value: inputs resident in HBM, device-timed with CUDA events, L2 flushed before each step
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    _lib.reset_launch_count()
     barrier()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
         ev[k][0].record()
-        step(xs, xt, labels)
+        step.run()
         ev[k][1].record()
     barrier()
-    launches = _lib.launch_count()
+    launches = step.launches_per_step * args.steps
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([t_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -327,9 +322,9 @@ def run_b200(args):
 
     # ---- e2e: host (pinned) inputs -> public API -> loss on the host, optimizer step included
     def e2e_step():
-        loss = step(xs_h, xt_h, lab_h.to(dev, non_blocking=True))     # VideoModel.forward does the H2D copies
+        loss = step(xs_h, xt_h, lab_h)        # H2D copies of this step's inputs + graph replay (+ all-reduce)
         opt.step()
-        return loss.item()                                            # D2H read of the step's result
+        return loss.item()                    # D2H read of the step's result
 
     for _ in range(3):
         e2e_step()
@@ -344,13 +339,35 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
 
-    # ---- roofline: per-call-site device time (CUDA events inside the library, separate pass)
+    # ---- the drop-in autograd API (VideoModel.forward + torch loss + backward), for reference
+    def autograd_step():
+        model.zero_grad(set_to_none=True)
+        outs = model(step.xs, step.xt, list(BETA), 0, is_train=True, reverse=False)
+        ta3n_loss(outs, step.labels, GAMMA).backward()
+
+    for _ in range(3):
+        autograd_step()
+    barrier()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for _ in range(args.steps):
+        autograd_step()
+    eb.record()
+    barrier()
+    autograd_ms = ea.elapsed_time(eb) / args.steps
+    for p_, v_ in zip(step.params, step.grad_views):
+        p_.grad = v_
+
+    # ---- roofline: per-call-site device time (CUDA events inside the library; eager pass, no graph)
+    eager = TrainStep(model, B, B, BETA, gamma=GAMMA, use_graph=False)
+    eager.load(xs_h, xt_h, lab_h)
+    eager.run()
     _lib.timing_enable(True)
     barrier()
     n_prof = min(args.steps, 10)
     for k in range(n_prof):
         flush.fill_(k & 0xFF)
-        step(xs, xt, labels)
+        eager.run()
     torch.cuda.synchronize()
     rep = _lib.timing_report()
     _lib.timing_enable(False)
@@ -393,7 +410,8 @@ def run_b200(args):
                 "h2d_bytes_per_step": int(2 * B * T * D * 4 + B * 8), "d2h_bytes_per_step": 4,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "includes": "H2D of inputs, forward, loss, backward, "
                 "all-reduce, SGD step, D2H of the loss"},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "launches_per_step": int(step.launches_per_step),
+        "cuda_graph": not args.no_graph, "autograd_api_ms_per_step": autograd_ms, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, 1000, 2, budget_s=args.cpu_seconds)

@@ -178,6 +178,15 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
                         float grad_scale, float* d_feat_video, float* dWc, float* dbc,
                         void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
 
+/* ---- deferred weight gradients (optional) ------------------------------------------- */
+/* Between begin and flush (same host thread) the *_bwd entry points above launch only their
+ * data-gradient chain; their weight-gradient GEMMs and bias column sums are collected and issued by
+ * the flush as one grouped launch per GEMM engine plus one column-sum launch.  The caller must keep
+ * every buffer those calls were given (workspaces included) alive and unmodified until the flush. */
+int ta3n_wgrad_defer_begin(void);
+size_t ta3n_wgrad_defer_workspace_bytes(void);
+int ta3n_wgrad_defer_flush(void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
+
 /* ---- fused loss heads of the shipped training configuration ------------------------- */
 /* main.py:446 (class CE on the Bs source rows), main.py:508-538 (domain CE per level, labels
  * 0 = source rows, 1 = target rows), main.py:559-562 + loss.py:15-25 (gamma * attentive entropy).

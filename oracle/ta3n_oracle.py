@@ -245,11 +245,15 @@ def activation_pattern(params, xs, xt, beta, cfg: "PathConfig") -> Dict[str, tor
 
 
 def trn_multiscale(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
-                   tuples: List[List[Tuple[int, ...]]], gates: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+                   tuples: List[List[Tuple[int, ...]]], gates: Optional[Sequence[torch.Tensor]] = None,
+                   input_relu: bool = True) -> torch.Tensor:
     """RelationModuleMultiScale.forward (TRNmodule.py:58-82).
 
     x (N, T, F) -> (N, T-1, H);  out[:, i] = sum_r relu(W_i . concat_j relu(x[:, tau_ir[j]]) + b_i)
     ``gates`` (optional): one (N,H) 0/1 tensor per evaluated relation, see ``_relu``.
+    ``input_relu=False`` drops the leading nn.ReLU (TRNmodule.py:49): inside VideoModel its input is the
+    already rectified shared feature, so it is an identity -- and when the shared layer's pattern is
+    pinned by a gate it must not re-decide the sign of the few units the gate kept at a tiny negative value.
     """
     per_scale = []
     q = 0
@@ -257,7 +261,7 @@ def trn_multiscale(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Seq
         acc = None
         for tau in rels:
             u = x[:, list(tau), :].reshape(x.size(0), -1)             # :60-61 / :75-76
-            a = _relu(F.linear(F.relu(u), weights[i], biases[i]),     # :46-54 ReLU-Linear-ReLU
+            a = _relu(F.linear(F.relu(u) if input_relu else u, weights[i], biases[i]),   # :46-54 ReLU-Linear-ReLU
                       None if gates is None else gates[q])
             q += 1
             acc = a if acc is None else acc + a                        # :79
@@ -303,7 +307,7 @@ def _forward_domain(p: Dict[str, torch.Tensor], x: torch.Tensor, beta: Sequence[
     rel = trn_multiscale(feat.view(batch, T, Fd),
                          [p[f"TRN.fc_fusion_scales.{i}.1.weight"] for i in range(R)],
                          [p[f"TRN.fc_fusion_scales.{i}.1.bias"] for i in range(R)],
-                         tuples, gates.get("trn"))                                     # :635
+                         tuples, gates.get("trn"), input_relu="shared" not in gates)   # :635
 
     pred_rel = torch.stack(
         [two_layer_disc(rel[:, i, :],

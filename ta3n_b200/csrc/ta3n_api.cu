@@ -84,9 +84,70 @@ inline size_t splitk_bytes(int n_groups) {
   return (size_t)2 * 296 * 128 * 128 * sizeof(float) + (size_t)256 * (n_groups + 1) + 4096;
 }
 
+// ---- deferred weight-gradient work ------------------------------------------------------------------
+// Between ta3n_wgrad_defer_begin() and ta3n_wgrad_defer_flush() the *_bwd entry points enqueue only
+// their data-gradient chain; their weight-gradient GEMMs (all M-major x N-major) and bias column sums
+// are collected here and issued by the flush as ONE grouped launch per engine + ONE column-sum launch.
+// The buffers they read (workspaces, saved activations) must stay alive and unmodified until the flush.
+struct DeferCtx {
+  bool active = false;
+  GemmPlan wgrad;
+  ColsumPlan cs;
+  void reset() {
+    wgrad = GemmPlan();
+    wgrad.a_kmaj = false;
+    wgrad.b_kmaj = false;
+    wgrad.label = "wgrad_all";
+    cs = ColsumPlan();
+  }
+};
+DeferCtx& defer_ctx() {
+  static thread_local DeferCtx c;
+  return c;
+}
+
+int submit_wgrad(GemmPlan& plan, cudaStream_t st, Arena* arena) {
+  DeferCtx& d = defer_ctx();
+  if (!d.active || plan.load_flags != 0) return run_gemm(plan, st, arena);
+  for (const Group& src : plan.groups) {
+    Group g = src;
+    g.seg_begin = (int)d.wgrad.segs.size();
+    for (int k = 0; k < src.seg_count; ++k) d.wgrad.segs.push_back(plan.segs[src.seg_begin + k]);
+    d.wgrad.groups.push_back(g);
+  }
+  return TA3N_OK;
+}
+
+int submit_colsum(ColsumPlan& cs, cudaStream_t st) {
+  DeferCtx& d = defer_ctx();
+  if (!d.active) return cs.run(st);
+  for (auto& j : cs.jobs) d.cs.jobs.push_back(j);
+  return TA3N_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int ta3n_wgrad_defer_begin(void) {
+  DeferCtx& d = defer_ctx();
+  d.reset();
+  d.active = true;
+  return TA3N_OK;
+}
+
+size_t ta3n_wgrad_defer_workspace_bytes(void) { return splitk_bytes(64); }
+
+int ta3n_wgrad_defer_flush(void* workspace, size_t workspace_bytes, ta3n_stream_t stream) {
+  DeferCtx& d = defer_ctx();
+  if (!d.active) return fail(TA3N_ERR_INVALID, "ta3n_wgrad_defer_flush without ta3n_wgrad_defer_begin");
+  d.active = false;
+  Arena arena(workspace, workspace_bytes);
+  int rc = run_gemm(d.wgrad, S(stream), workspace ? &arena : nullptr);
+  if (rc == TA3N_OK) rc = d.cs.run(S(stream));
+  d.reset();
+  return rc;
+}
 
 int ta3n_abi_version(void) { return TA3N_ABI_VERSION; }
 const char* ta3n_last_error(void) { return last_error_buf(); }
@@ -205,12 +266,12 @@ int ta3n_shared_fc_bwd(const float* x_src, int rows_src, const float* x_tgt, int
   plan.add_group(F, D, dW, D);
   if (rows_src > 0) plan.add_seg(dfeat, F, x_src, D, rows_src);
   if (rows_tgt > 0) plan.add_seg(dfeat + (size_t)rows_src * F, F, x_tgt, D, rows_tgt);
-  TA3N_TRY(run_gemm(plan, S(stream), &arena));
+  TA3N_TRY(submit_wgrad(plan, S(stream), &arena));
 
   ColsumPlan cs;
   cs.add(db, F, F);
   cs.seg(dfeat, rows);
-  return cs.run(S(stream));
+  return submit_colsum(cs, S(stream));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -274,7 +335,7 @@ int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, cons
     plan.add_seg(g_logits, 2, hidden, Kh, rows);
     plan.add_group(Kh, K, dW1, K);
     plan.add_seg(dH, Kh, x, K, rows);
-    TA3N_TRY(run_gemm(plan, st, &arena));
+    TA3N_TRY(submit_wgrad(plan, st, &arena));
   }
   {
     ColsumPlan cs;
@@ -282,7 +343,7 @@ int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, cons
     cs.seg(g_logits, rows);
     cs.add(db1, Kh, Kh);
     cs.seg(dH, rows);
-    TA3N_TRY(cs.run(st));
+    TA3N_TRY(submit_colsum(cs, st));
   }
   if (dx) {  // dx (+)= -beta * dH W1
     GemmPlan plan;
@@ -415,7 +476,7 @@ int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table*
         }
       }
     }
-    TA3N_TRY(run_gemm(plan, st, &arena));
+    TA3N_TRY(submit_wgrad(plan, st, &arena));
   }
   {  // db_i = sum_r colsum(dz_{i,r})
     ColsumPlan cs;
@@ -423,7 +484,7 @@ int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table*
       cs.add(db_host[i], H, H);
       for (int q = L.rel_begin[i]; q < L.rel_begin[i + 1]; ++q) cs.seg(dz + q * plane, M);
     }
-    TA3N_TRY(cs.run(st));
+    TA3N_TRY(submit_colsum(cs, st));
   }
   if (dx) {  // dgrad, deterministic per frame: dx[:, t, :] = sum_{(q,j): tau_q[j]=t} dz_q W_i[:, jF:(j+1)F]
     GemmPlan plan;
@@ -541,7 +602,7 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
       plan.add_group(H, H, dW1_host[i], H);
       plan.add_seg(dHid + (size_t)i * M * H, H, feat_rel + (size_t)i * H, R * H, M);
     }
-    TA3N_TRY(run_gemm(plan, st, &arena));
+    TA3N_TRY(submit_wgrad(plan, st, &arena));
   }
   {
     ColsumPlan cs;
@@ -551,7 +612,7 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
       cs.add(db1_host[i], H, H);
       cs.seg(dHid + (size_t)i * M * H, M);
     }
-    TA3N_TRY(cs.run(st));
+    TA3N_TRY(submit_colsum(cs, st));
   }
   {  // d_feat_rel[:, i, :] = (w_i + 1) G - beta * dHid_i W1_i
     GemmPlan plan;
@@ -630,11 +691,11 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
     plan.b_kmaj = false;
     plan.add_group(C, H, dWc, H);
     plan.add_seg(g_pred, C, dropped, H, M);
-    TA3N_TRY(run_gemm(plan, st, &arena));
+    TA3N_TRY(submit_wgrad(plan, st, &arena));
     ColsumPlan cs;
     cs.add(dbc, C, C);
     cs.seg(g_pred, M);
-    TA3N_TRY(cs.run(st));
+    TA3N_TRY(submit_colsum(cs, st));
   }
   return TA3N_OK;
 }

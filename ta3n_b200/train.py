@@ -81,6 +81,7 @@ class TrainStep:
             drop_i=TF.DropSpec(p=di, seed=seed, step=self.step_counter) if di > 0 else TF.DropSpec(),
             drop_v=TF.DropSpec(p=dv, seed=seed ^ 0x9E3779B9, step=self.step_counter) if dv > 0 else TF.DropSpec())
         self.outputs = None
+        self.launches_per_step = 0               # kernels of libta3n_sm100.so per step (counted at capture)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         if use_graph:
             self._capture()
@@ -99,13 +100,22 @@ class TrainStep:
                                     _P(self.g_frame), _P(self.loss_ws), self.loss_ws.numel(), st))
         gin = {"pred_video": self.g_video, "pred_rel": self.g_rel, "pred_dom_video": self.g_dom,
                "pred_frame": self.g_frame}
-        TF.path_backward(self.spec, dims, self.xs, self.xt, self.params, saved, gin, self.grad_views, self.bufs)
+        # data-gradient chain first; every weight-gradient GEMM / bias column sum of the step is deferred
+        # and issued as one grouped launch per engine at the end (buffers are persistent, so they stay valid)
+        check(lib.ta3n_wgrad_defer_begin())
+        try:
+            TF.path_backward(self.spec, dims, self.xs, self.xt, self.params, saved, gin, self.grad_views, self.bufs)
+        finally:
+            ws = self.bufs.workspace("wgrad_all", lib.ta3n_wgrad_defer_workspace_bytes())
+            check(lib.ta3n_wgrad_defer_flush(_P(ws), ws.numel(), st))
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
+            n0 = _lib.launch_count()
             self._enqueue()                      # warm-up: sizes every buffer, sets kernel attributes
+            self.launches_per_step = _lib.launch_count() - n0
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
@@ -125,7 +135,9 @@ class TrainStep:
         if self.graph is not None:
             self.graph.replay()
         else:
+            n0 = _lib.launch_count()
             self._enqueue()
+            self.launches_per_step = _lib.launch_count() - n0
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
             self.flat_grad.mul_(1.0 / self.world)

@@ -44,12 +44,34 @@ for eng in ("fp32", "tf32"):
         if n in g64:
             r["grad:" + n] = rel(p.grad, g64[n])
     res[eng] = r
+# tf32 engine again, but against the fp64 oracle evaluated ON THE ACTIVATION PATTERN the CUDA forward realised
+from ta3n_b200.train import TrainStep
+ta3n_b200.set_gemm_engine("tf32")
+m = VideoModel(12, "video", "trn-m", "RGB", train_segments=T, val_segments=T, fc_dim=512, dropout_i=0.0,
+               dropout_v=0.0, partial_bn=False, verbose=False)
+m.load_state_dict(params); m = m.to(dev).train()
+step = TrainStep(m, B, B, beta, gamma=0.003, use_graph=False)
+lossp = step(xs, xt, labels); torch.cuda.synchronize()
+pool = step.bufs.pool
+gates = {"shared": (pool["feat"] > 0).cpu(), "frame_disc": (pool["hid_f"] > 0).cpu(),
+         "trn": [(a > 0).cpu() for a in pool["act"]], "rel_disc": [(h > 0).cpu() for h in pool["hid_r"]],
+         "video_disc": (pool["hid_v"] > 0).cpu()}
+plain = orc.activation_pattern(p64, xs.double(), xt.double(), beta, cfg)
+lst = lambda g: [g["shared"], g["frame_disc"], *g["trn"], *g["rel_disc"], g["video_disc"]]
+flips = sum((a != b).sum().item() for a, b in zip(lst(gates), lst(plain))); total = sum(t.numel() for t in lst(gates))
+lp, op, gp = orc.train_step(p64, xs.double(), xt.double(), labels, beta, cfg, 0.003, train=True, gates=gates)
+pinned = {"loss": rel(lossp[0], lp)}
+for n, p in m.named_parameters():
+    if n in gp:
+        pinned["grad:" + n] = rel(p.grad, gp[n])
 ref = {"loss": rel(l32, l64)}
 for n, a, b in zip(names, flat(o32), flat(o64)):
     ref["out:" + n] = rel(a, b)
 for n in g64:
     ref["grad:" + n] = rel(g32[n], g64[n])
 print(f"# B={B}+{B} T={T} perturbed={os.environ.get('PERTURB','1')}  normwise rel err vs fp64 oracle")
-print(f"{'tensor':58s} {'cpu fp32':>10s} {'cuda fp32':>10s} {'cuda tf32':>10s}")
+print(f"# ReLU units whose on/off state differs between the tf32 CUDA forward and the fp64 oracle: {flips} of {total} ({flips/total:.2e})")
+print(f"{'tensor':58s} {'cpu fp32':>10s} {'cuda fp32':>10s} {'cuda tf32':>10s} {'tf32 pinned':>12s}")
 for k in res["fp32"]:
-    print(f"{k:58s} {ref[k]:10.2e} {res['fp32'][k]:10.2e} {res['tf32'][k]:10.2e}")
+    pin = f"{pinned[k]:12.2e}" if k in pinned else f"{'':>12s}"
+    print(f"{k:58s} {ref[k]:10.2e} {res['fp32'][k]:10.2e} {res['tf32'][k]:10.2e} {pin}")
