@@ -178,6 +178,14 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
                         float grad_scale, float* d_feat_video, float* dWc, float* dbc,
                         void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
 
+/* ---- forward batching (optional) ------------------------------------------------------ */
+/* Between begin and flush (same host thread) ta3n_disc_fwd and ta3n_trn_fwd only register their GEMMs;
+ * the flush issues them as ONE grouped launch followed by their light follow-up kernels.  Only calls
+ * whose inputs are already final may be batched together (e.g. the frame discriminator and the TRN,
+ * which both read the shared features when use_attn_frame == 'none').                                  */
+int ta3n_fwd_batch_begin(void);
+int ta3n_fwd_batch_flush(ta3n_stream_t stream);
+
 /* ---- deferred weight gradients (optional) ------------------------------------------- */
 /* Between begin and flush (same host thread) the *_bwd entry points above launch only their
  * data-gradient chain; their weight-gradient GEMMs and bias column sums are collected and issued by

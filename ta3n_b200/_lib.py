@@ -59,6 +59,8 @@ SIGNATURES = {
     "ta3n_video_head_fwd": (_I, [_VP, _I, _I, _I, _VP, _VP, _DRP, _VP, _VP, _VP]),
     "ta3n_video_head_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ta3n_video_head_bwd": (_I, [_VP, _I, _I, _I, _VP, _DRP, _VP, _VP, _VP, _F, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "ta3n_fwd_batch_begin": (_I, []),
+    "ta3n_fwd_batch_flush": (_I, [_VP]),
     "ta3n_wgrad_defer_begin": (_I, []),
     "ta3n_wgrad_defer_workspace_bytes": (_SZ, []),
     "ta3n_wgrad_defer_flush": (_I, [_VP, _SZ, _VP]),
@@ -79,7 +81,7 @@ class Ta3nError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    return os.environ.get("TA3N_LIB", _build.LIB_PATH)
 
 
 def load() -> C.CDLL:

@@ -35,7 +35,10 @@ constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 16 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;   // + slack for 1024 B alignment
 constexpr int TC_TMEM_COLS = 128;
-constexpr int kMaxMaps = 64;
+#ifndef TA3N_MAX_MAPS
+#define TA3N_MAX_MAPS 64
+#endif
+constexpr int kMaxMaps = TA3N_MAX_MAPS;
 
 struct alignas(64) TcMaps {
   CUtensorMap m[kMaxMaps];
@@ -156,7 +159,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(bool a_kmaj, bool b_kmaj,
 template <bool A_KMAJ, bool B_KMAJ>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant__ TcMaps maps,
-                   const __grid_constant__ TcSegMaps segmaps) {
+                   const __grid_constant__ TcSegMaps segmaps, const int dbg) {
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
@@ -166,12 +169,11 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- tile decode (same scheme as the SIMT engine, 128x128 tiles) ----
+  // ---- tile decode (same scheme as the SIMT engine, 128x128 tiles); group + segments staged in smem ----
+  __shared__ TileCtx ctx;
   const int tile = blockIdx.x;
-  int gi = 0;
-  for (int i = 1; i < tab.n_groups; ++i)
-    if (tile >= tab.g[i].tile_begin) gi = i;
-  const Group& g = tab.g[gi];
+  load_tile_ctx(tab, tile, &ctx, segmaps.a, segmaps.b);
+  const Group& g = ctx.g;
   int local = tile - g.tile_begin;
   const int per_split = g.tiles_m * g.tiles_n;
   const int split = local / per_split;
@@ -180,11 +182,13 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
   const int n0 = (local % g.tiles_n) * TC_BN;
 
   int total_chunks = 0;
-  for (int s = 0; s < g.seg_count; ++s) total_chunks += (tab.s[g.seg_begin + s].len + TC_BK - 1) / TC_BK;
+  for (int s = 0; s < g.seg_count; ++s) total_chunks += (ctx.seg[s].len + TC_BK - 1) / TC_BK;
   const int cps = (total_chunks + g.ksplit - 1) / g.ksplit;
   const int c_begin = split * cps;
   const int c_end = min(total_chunks, c_begin + cps);
-  const int n_iter = max(0, c_end - c_begin);
+  int n_iter = max(0, c_end - c_begin);
+  if (dbg & 4) n_iter = 0;       // debug: no TMA / MMA
+  if (dbg & 8) return;           // debug: nothing at all
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -195,11 +199,16 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
     mbar_init(&tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, TC_TMEM_COLS);
+  if (warp == 1 && !(dbg & 2)) tmem_alloc(&tmem_slot, TC_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (dbg & 16) {                // debug: setup + teardown only
+    __syncthreads();
+    if (warp == 1 && !(dbg & 2)) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    return;
+  }
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -208,7 +217,7 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
       {
         int skip = c_begin;
         while (seg < g.seg_count) {
-          const int nch = (tab.s[g.seg_begin + seg].len + TC_BK - 1) / TC_BK;
+          const int nch = (ctx.seg[seg].len + TC_BK - 1) / TC_BK;
           if (skip < nch) {
             k0 = skip * TC_BK;
             break;
@@ -224,8 +233,8 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
         mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
         uint8_t* sA = smem + stage * TC_STAGE_BYTES;
         uint8_t* sB = sA + TC_A_BYTES;
-        const CUtensorMap* ma = &maps.m[segmaps.a[g.seg_begin + seg]];
-        const CUtensorMap* mb = &maps.m[segmaps.b[g.seg_begin + seg]];
+        const CUtensorMap* ma = &maps.m[ctx.seg[seg].amap];
+        const CUtensorMap* mb = &maps.m[ctx.seg[seg].bmap];
         if (A_KMAJ) {
           tma_load_2d(sA, ma, &full_bar[stage], k0, m0);
         } else {
@@ -239,7 +248,7 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
           for (int q = 0; q < TC_BN / 32; ++q) tma_load_2d(sB + q * 4096, mb, &full_bar[stage], n0 + 32 * q, k0);
         }
         k0 += TC_BK;
-        if (k0 >= tab.s[g.seg_begin + seg].len) {
+        if (k0 >= ctx.seg[seg].len) {
           ++seg;
           k0 = 0;
         }
@@ -287,7 +296,7 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
       for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
       __syncwarp();
       const int n = n0 + c * 32 + lane;
-      if (n < g.N) {
+      if (n < g.N && !(dbg & 1)) {
         for (int r = 0; r < 32; ++r) {
           const int m = m0 + lq * 32 + r;
           if (m >= g.M) break;
@@ -304,7 +313,7 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 1 && !(dbg & 2)) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
@@ -395,8 +404,12 @@ inline int tc_launch_one(const GemmTable& tab, const TcMaps& maps, const TcSegMa
                                    TC_SMEM_BYTES));
     configured = true;
   }
+  static const int dbg = []() {
+    const char* e = getenv("TA3N_TC_DEBUG");
+    return e ? atoi(e) : 0;
+  }();
   pre_launch(label, stream);
-  seg_gemm_tc_kernel<A_KMAJ, B_KMAJ><<<tab.total_tiles, TC_THREADS, TC_SMEM_BYTES, stream>>>(tab, maps, sm);
+  seg_gemm_tc_kernel<A_KMAJ, B_KMAJ><<<tab.total_tiles, TC_THREADS, TC_SMEM_BYTES, stream>>>(tab, maps, sm, dbg);
   return after_launch();
 }
 
@@ -467,7 +480,7 @@ inline int launch_tc(const GemmPlan& plan, cudaStream_t stream) {
       else
         TA3N_TRY((tc_launch_one<false, true>(tab, maps, sm, stream, plan.label)));
       if (any_split) {
-        dim3 grid(32, ng);
+        dim3 grid(splitk_reduce_blocks(tab), ng);
         pre_launch("splitk_reduce", stream);
         splitk_reduce_kernel<<<grid, 256, 0, stream>>>(tab);
         TA3N_TRY(after_launch());

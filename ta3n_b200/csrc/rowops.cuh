@@ -427,7 +427,14 @@ struct ColsumTable {
 // block = 32 columns x 32 row-stripes; grid = (ceil(maxN/32), n_jobs)
 __global__ void __launch_bounds__(1024) colsum_kernel(const __grid_constant__ ColsumTable tab) {
   __shared__ float red[32][33];
-  const ColsumJob& j = tab.job[blockIdx.y];
+  __shared__ ColsumJob j;   // staged: run-time indexed kernel parameters are slow generic loads
+  {
+    const int* src = reinterpret_cast<const int*>(&tab.job[blockIdx.y]);
+    int* dst = reinterpret_cast<int*>(&j);
+    const int t = threadIdx.y * 32 + threadIdx.x;
+    if (t < (int)(sizeof(ColsumJob) / sizeof(int))) dst[t] = src[t];
+    __syncthreads();
+  }
   const int n = blockIdx.x * 32 + threadIdx.x;
   if (blockIdx.x * 32 >= j.N) return;
   float s = 0.f;

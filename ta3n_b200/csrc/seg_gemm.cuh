@@ -23,8 +23,14 @@
 
 namespace ta3n {
 
-constexpr int kMaxGroups = 48;
-constexpr int kMaxSegs = 128;
+#ifndef TA3N_MAX_GROUPS
+#define TA3N_MAX_GROUPS 48
+#endif
+#ifndef TA3N_MAX_SEGS
+#define TA3N_MAX_SEGS 128
+#endif
+constexpr int kMaxGroups = TA3N_MAX_GROUPS;
+constexpr int kMaxSegs = TA3N_MAX_SEGS;
 
 enum : int {
   EPI_BIAS = 1,        // v += bias[n]
@@ -107,6 +113,58 @@ __device__ __forceinline__ float apply_epilogue(const Group& g, int m, int n, fl
   return v;
 }
 
+// ---- per-CTA tile context ------------------------------------------------------------------------
+// The launch tables live in kernel-parameter space; indexing them with run-time indices makes every
+// field access a ~300-cycle generic load.  Each CTA therefore copies ITS group and the lengths /
+// operand bases of that group's segments into shared memory once (one parallel round of loads) and
+// works from there.
+struct SegLite {
+  const float* A;
+  const float* B;
+  int len, lda, ldb;
+  unsigned short amap, bmap;   // tensor-map slots (tcgen05 engine only)
+};
+constexpr int kCtxMaxSegs = kMaxSegs;
+
+struct TileCtx {
+  Group g;
+  SegLite seg[kCtxMaxSegs];
+  int gi;
+};
+
+// Find the group owning `tile` (groups are sorted by tile_begin) with one parallel probe per warp,
+// then stage it.  Must be called by all threads of the CTA; ends with __syncthreads().
+__device__ __forceinline__ void load_tile_ctx(const GemmTable& tab, int tile, TileCtx* ctx,
+                                              const unsigned char* amap, const unsigned char* bmap) {
+  if (threadIdx.x < 32) {
+    int best = 0;
+    for (int i = threadIdx.x; i < tab.n_groups; i += 32)
+      if (tile >= tab.g[i].tile_begin) best = max(best, i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (threadIdx.x == 0) ctx->gi = best;
+  }
+  __syncthreads();
+  const int gi = ctx->gi;
+  const int* src = reinterpret_cast<const int*>(&tab.g[gi]);
+  int* dst = reinterpret_cast<int*>(&ctx->g);
+  for (int i = threadIdx.x; i < (int)(sizeof(Group) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+  const int sb = tab.g[gi].seg_begin, sc = tab.g[gi].seg_count;
+  for (int i = threadIdx.x; i < sc; i += blockDim.x) {
+    const Seg& s = tab.s[sb + i];
+    SegLite l;
+    l.A = s.A;
+    l.B = s.B;
+    l.len = s.len;
+    l.lda = s.lda;
+    l.ldb = s.ldb;
+    l.amap = amap ? amap[sb + i] : 0;
+    l.bmap = bmap ? bmap[sb + i] : 0;
+    ctx->seg[i] = l;
+  }
+  __syncthreads();
+}
+
 // =============================================================================================
 // exact-fp32 SIMT engine: 64x64x16 tiles, 256 threads, 4x4 register micro-tile, double-buffered
 // =============================================================================================
@@ -173,12 +231,11 @@ seg_gemm_simt_kernel(const __grid_constant__ GemmTable tab) {
   __shared__ __align__(16) float As[2][SG_BK][SG_BM + SG_PAD];
   __shared__ __align__(16) float Bs[2][SG_BK][SG_BN + SG_PAD];
 
+  __shared__ TileCtx ctx;
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
-  int gi = 0;
-  for (int i = 1; i < tab.n_groups; ++i)
-    if (tile >= tab.g[i].tile_begin) gi = i;
-  const Group& g = tab.g[gi];
+  load_tile_ctx(tab, tile, &ctx, nullptr, nullptr);
+  const Group& g = ctx.g;
   int local = tile - g.tile_begin;
   const int per_split = g.tiles_m * g.tiles_n;
   const int split = local / per_split;
@@ -188,7 +245,7 @@ seg_gemm_simt_kernel(const __grid_constant__ GemmTable tab) {
 
   // chunk range of this split over the concatenated K of all segments
   int total_chunks = 0;
-  for (int s = 0; s < g.seg_count; ++s) total_chunks += (tab.s[g.seg_begin + s].len + SG_BK - 1) / SG_BK;
+  for (int s = 0; s < g.seg_count; ++s) total_chunks += (ctx.seg[s].len + SG_BK - 1) / SG_BK;
   const int cps = (total_chunks + g.ksplit - 1) / g.ksplit;
   const int c_begin = split * cps;
   const int c_end = min(total_chunks, c_begin + cps);
@@ -207,7 +264,7 @@ seg_gemm_simt_kernel(const __grid_constant__ GemmTable tab) {
   {
     int skip = c_begin;
     while (seg < g.seg_count) {
-      int nch = (tab.s[g.seg_begin + seg].len + SG_BK - 1) / SG_BK;
+      int nch = (ctx.seg[seg].len + SG_BK - 1) / SG_BK;
       if (skip < nch) {
         k0 = skip * SG_BK;
         break;
@@ -221,7 +278,7 @@ seg_gemm_simt_kernel(const __grid_constant__ GemmTable tab) {
   if (n_iter > 0) {
     float4 ra, rb;
     {
-      const Seg& sg = tab.s[g.seg_begin + seg];
+      const SegLite& sg = ctx.seg[seg];
       ra = fetch_operand<A_KMAJ>(sg.A, sg.lda, m0, g.M, k0, sg.len, tid, reluA);
       rb = fetch_operand<B_KMAJ>(sg.B, sg.ldb, n0, g.N, k0, sg.len, tid, reluB);
     }
@@ -235,11 +292,11 @@ seg_gemm_simt_kernel(const __grid_constant__ GemmTable tab) {
       const bool has_next = (it + 1 < n_iter);
       if (has_next) {
         k0 += SG_BK;
-        if (k0 >= tab.s[g.seg_begin + seg].len) {
+        if (k0 >= ctx.seg[seg].len) {
           ++seg;
           k0 = 0;
         }
-        const Seg& sg = tab.s[g.seg_begin + seg];
+        const SegLite& sg = ctx.seg[seg];
         ra = fetch_operand<A_KMAJ>(sg.A, sg.lda, m0, g.M, k0, sg.len, tid, reluA);
         rb = fetch_operand<B_KMAJ>(sg.B, sg.ldb, n0, g.N, k0, sg.len, tid, reluB);
       }
@@ -284,7 +341,13 @@ seg_gemm_simt_kernel(const __grid_constant__ GemmTable tab) {
 // deterministic split-K reduction + epilogue: one thread per output element of every group
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ GemmTable tab) {
   // blockIdx.y = group, blockIdx.x strides over the elements
-  const Group& g = tab.g[blockIdx.y];
+  __shared__ Group g;
+  {
+    const int* src = reinterpret_cast<const int*>(&tab.g[blockIdx.y]);
+    int* dst = reinterpret_cast<int*>(&g);
+    for (int i = threadIdx.x; i < (int)(sizeof(Group) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
   if (g.ksplit <= 1) return;
   const size_t total = (size_t)g.M * g.N;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -293,6 +356,15 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
     const int m = (int)(e / g.N), n = (int)(e % g.N);
     g.C[(size_t)m * g.ldc + n] = apply_epilogue(g, m, n, s);
   }
+}
+
+inline unsigned splitk_reduce_blocks(const GemmTable& tab) {
+  size_t mx = 0;
+  for (int i = 0; i < tab.n_groups; ++i)
+    if (tab.g[i].ksplit > 1 && (size_t)tab.g[i].M * tab.g[i].N > mx) mx = (size_t)tab.g[i].M * tab.g[i].N;
+  size_t b = (mx + 255) / 256;
+  if (b > 512) b = 512;
+  return (unsigned)(b ? b : 1);
 }
 
 // =============================================================================================
@@ -338,15 +410,15 @@ struct GemmPlan {
 // Choose a split-K factor for reduction-heavy, tile-poor problems (wgrads) and carve the partial
 // buffers out of `arena` (which may be null -> no split-K).  bm/bn/bk: tile shape of the engine.
 inline void plan_splitk(GemmPlan& plan, Arena* arena, int bm, int bn, int bk, int min_chunks,
-                        int target_ctas = 296) {
+                        int target_ctas = 148) {
   if (!arena) return;
   long tiles = 0;
   for (auto& g : plan.groups) tiles += (long)((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn);
-  if (tiles <= 0 || tiles >= target_ctas) return;
+  if (tiles <= 0 || 2 * tiles > target_ctas) return;   // already (at least half) a wave: partials cost more than they buy
   for (auto& g : plan.groups) {
     long chunks = 0;
     for (int i = 0; i < g.seg_count; ++i) chunks += (plan.segs[g.seg_begin + i].len + bk - 1) / bk;
-    int want = (int)((target_ctas + tiles - 1) / tiles);
+    int want = (int)(target_ctas / tiles);
     int maxsplit = (int)(chunks / min_chunks);
     int ks = want < maxsplit ? want : maxsplit;
     if (ks > 8) ks = 8;
@@ -397,7 +469,7 @@ inline int launch_simt(const GemmPlan& plan, cudaStream_t stream) {
         seg_gemm_simt_kernel<false, true><<<tiles, SG_THREADS, 0, stream>>>(tab);
       TA3N_TRY(after_launch());
       if (any_split) {
-        dim3 grid(32, ng);
+        dim3 grid(splitk_reduce_blocks(tab), ng);
         pre_launch("splitk_reduce", stream);
         splitk_reduce_kernel<<<grid, 256, 0, stream>>>(tab);
         TA3N_TRY(after_launch());

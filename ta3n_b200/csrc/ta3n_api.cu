@@ -6,6 +6,8 @@
 #include "rowops.cuh"
 #include "gemm_tcgen05.cuh"
 
+#include <functional>
+
 using namespace ta3n;
 
 namespace {
@@ -118,6 +120,40 @@ int submit_wgrad(GemmPlan& plan, cudaStream_t st, Arena* arena) {
   return TA3N_OK;
 }
 
+// Forward-side batching: independent K-major x K-major GEMMs (frame discriminator hidden layer and the TRN
+// relation GEMMs both read the shared features) collected into one grouped launch; the light kernels that
+// consume their outputs run right after it, in submission order.
+struct FwdBatch {
+  bool active = false;
+  GemmPlan plan;
+  std::vector<std::function<int(cudaStream_t)>> post;
+  void reset() {
+    plan = GemmPlan();
+    plan.label = "fwd_batch";
+    post.clear();
+  }
+};
+FwdBatch& fwd_batch() {
+  static thread_local FwdBatch b;
+  return b;
+}
+
+int submit_fwd(GemmPlan& plan, cudaStream_t st, std::function<int(cudaStream_t)> post) {
+  FwdBatch& b = fwd_batch();
+  if (!b.active || plan.load_flags != 0 || !plan.a_kmaj || !plan.b_kmaj) {
+    TA3N_TRY(run_gemm(plan, st));
+    return post(st);
+  }
+  for (const Group& src : plan.groups) {
+    Group g = src;
+    g.seg_begin = (int)b.plan.segs.size();
+    for (int k = 0; k < src.seg_count; ++k) b.plan.segs.push_back(plan.segs[src.seg_begin + k]);
+    b.plan.groups.push_back(g);
+  }
+  b.post.push_back(std::move(post));
+  return TA3N_OK;
+}
+
 int submit_colsum(ColsumPlan& cs, cudaStream_t st) {
   DeferCtx& d = defer_ctx();
   if (!d.active) return cs.run(st);
@@ -128,6 +164,24 @@ int submit_colsum(ColsumPlan& cs, cudaStream_t st) {
 }  // namespace
 
 extern "C" {
+
+int ta3n_fwd_batch_begin(void) {
+  FwdBatch& b = fwd_batch();
+  b.reset();
+  b.active = true;
+  return TA3N_OK;
+}
+
+int ta3n_fwd_batch_flush(ta3n_stream_t stream) {
+  FwdBatch& b = fwd_batch();
+  if (!b.active) return fail(TA3N_ERR_INVALID, "ta3n_fwd_batch_flush without ta3n_fwd_batch_begin");
+  b.active = false;
+  int rc = run_gemm(b.plan, S(stream));
+  for (auto& f : b.post)
+    if (rc == TA3N_OK) rc = f(S(stream));
+  b.reset();
+  return rc;
+}
 
 int ta3n_wgrad_defer_begin(void) {
   DeferCtx& d = defer_ctx();
@@ -288,11 +342,11 @@ int ta3n_disc_fwd(const float* x, int rows, int K, int Kh, const float* W1, cons
   g.flags = EPI_BIAS | EPI_RELU;
   g.bias = b1;
   plan.add_seg(x, K, W1, K, K);
-  TA3N_TRY(run_gemm(plan, S(stream)));
-  pre_launch("head_fwd", S(stream));
-  head_fwd_kernel<<<blocks_for((size_t)rows * 32, 256), 256, 0, S(stream)>>>(hidden, Kh, W2, b2, logits, 2, rows,
-                                                                             Kh, 2);
-  return after_launch();
+  return submit_fwd(plan, S(stream), [=](cudaStream_t st) -> int {
+    pre_launch("head_fwd", st);
+    head_fwd_kernel<<<blocks_for((size_t)rows * 32, 256), 256, 0, st>>>(hidden, Kh, W2, b2, logits, 2, rows, Kh, 2);
+    return after_launch();
+  });
 }
 
 size_t ta3n_disc_bwd_workspace_bytes(int rows, int K, int Kh) {
@@ -417,11 +471,13 @@ int ta3n_trn_fwd(const float* x, int M, int F, int H, const ta3n_relation_table*
       plan.add_seg(x + (size_t)t * F, ldx, W_host[i] + (size_t)j * F, s * F, F);
     }
   }
-  TA3N_TRY(run_gemm(plan, S(stream)));
   const RelMap map = make_relmap(L);
-  pre_launch("relsum", S(stream));
-  relsum_kernel<<<blocks_for((size_t)M * L.R * H, 256), 256, 0, S(stream)>>>(act, feat_rel, M, H, map);
-  return after_launch();
+  const int R = L.R;
+  return submit_fwd(plan, S(stream), [=](cudaStream_t st) -> int {
+    pre_launch("relsum", st);
+    relsum_kernel<<<blocks_for((size_t)M * R * H, 256), 256, 0, st>>>(act, feat_rel, M, H, map);
+    return after_launch();
+  });
 }
 
 size_t ta3n_trn_bwd_workspace_bytes(int M, int F, int H, const ta3n_relation_table* tab) {

@@ -225,8 +225,10 @@ class Buffers:
         return self.get("ws_" + name, max(int(nbytes), 256), dtype=torch.uint8)
 
 
-def path_forward(spec: PathSpec, xs, xt, params, bufs: Buffers):
-    """The six forward C calls of the path.  Returns (saved tensors dict, outputs tuple, dims)."""
+def path_forward(spec: PathSpec, xs, xt, params, bufs: Buffers, batch_gemms: bool = False):
+    """The six forward C calls of the path.  Returns (saved tensors dict, outputs tuple, dims).
+    ``batch_gemms``: issue the frame-discriminator and TRN GEMMs (both read the shared features) as one
+    grouped launch (ta3n_fwd_batch_*); not applicable with frame attention, where TRN reads its output."""
     lib = _lib.load()
     st = _stream()
     T = spec.num_segments
@@ -247,6 +249,9 @@ def path_forward(spec: PathSpec, xs, xt, params, bufs: Buffers):
                                  _p(feat), st))
     # 2. frame-level discriminator  (models.py:606-610)
     hid_f, pred_frame = new("hid_f", M * T, F), new("pred_frame", M * T, 2)
+    batched = batch_gemms and not spec.use_attn_frame
+    if batched:
+        check(lib.ta3n_fwd_batch_begin())
     check(lib.ta3n_disc_fwd(_p(feat), M * T, F, F, _p(w1f), _p(b1f), _p(w2f), _p(b2f), _p(hid_f),
                             _p(pred_frame), st))
     # 2b. frame attention  (models.py:612-614)
@@ -260,6 +265,8 @@ def path_forward(spec: PathSpec, xs, xt, params, bufs: Buffers):
     act, feat_rel = new("act", rs.n_rel, M, H), new("feat_rel", M, R, H)
     check(lib.ta3n_trn_fwd(_p(feat_in), M, F, H, rs.ref, ptr_array([_p(w) for w in trn_w]),
                            ptr_array([_p(b) for b in trn_b]), 0, _p(act), _p(feat_rel), st))
+    if batched:
+        check(lib.ta3n_fwd_batch_flush(st))
     # 4. relation discriminators + attention + pooling  (models.py:639-652)
     hid_r, pred_rel = new("hid_r", R, M, H), new("pred_rel", M, R, 2)
     attn, feat_video = new("attn", M, R), new("feat_video", M, H)

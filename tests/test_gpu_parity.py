@@ -142,8 +142,7 @@ def test_model_matches_oracle_mid_size(T, attn_frame, bs, bt, engine):
 @pytest.mark.parametrize("T,attn_frame,bs,bt", [(5, "none", 48, 40), (6, "TransAttn", 12, 20)])
 def test_tf32_gradients_match_oracle_on_realised_activation_pattern(T, attn_frame, bs, bt):
     """tf32 engine: with the ReLU on/off pattern of the CUDA forward pinned in the fp64 oracle, the loss
-    agrees to 1e-3 and every parameter gradient to 1e-2 (chain of ~10 tf32 GEMMs, each ~3e-4; measured
-    values in profiles/r1_parity_report.txt) -- the extra 1-2.5 % seen without pinning comes only from the
+    agrees to 1e-3 and every parameter gradient to 3e-3 (measured <= 5e-4 at cfg2, profiles/r1_parity_report.txt) -- the extra 1-2.5 % seen without pinning comes only from the
     handful of units whose pre-activation is within tf32 rounding error of zero."""
     import ta3n_b200
     from ta3n_b200.train import TrainStep
@@ -181,7 +180,7 @@ def test_tf32_gradients_match_oracle_on_realised_activation_pattern(T, attn_fram
         assert_close(loss.cpu()[0], l64, TOL_PATH, "loss (pinned pattern)")
         named = dict(model.named_parameters())
         for name, go in g64.items():                          # ... and with it pinned the gradients agree
-            assert_close(named[name].grad, go, 1e-2, f"grad {name} (pinned pattern)",
+            assert_close(named[name].grad, go, 3e-3, f"grad {name} (pinned pattern)",
                          noise=abs_err(g32[name], go) * NOISE_SCALE["tf32"])
     finally:
         ta3n_b200.set_gemm_engine("fp32")
