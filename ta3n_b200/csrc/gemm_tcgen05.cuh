@@ -3,8 +3,9 @@
 // One CTA per 128 x 128 output tile (2 CTAs resident per SM), warp-specialised:
 //   warp 0     : TMA producer  -- cp.async.bulk.tensor.2d into a 3-stage ring of 128B-swizzled tiles
 //   warp 1     : TMEM allocator + single-thread tcgen05.mma.kind::tf32 issuer (fp32 accum in TMEM)
-//   warps 2..5 : epilogue      -- tcgen05.ld (32 lanes x 32 columns), transpose through smem,
-//                                 fused epilogue (apply_epilogue) with coalesced 128 B row stores
+//   warps 2..5 : epilogue      -- tcgen05.ld (32 lanes x 32 columns: one accumulator row per lane),
+//                                 fused epilogue (apply_epilogue) in registers, 16 B stores covering
+//                                 each 128 B line of the output row completely
 // Operands stay fp32 in HBM: kind::tf32 reads the fp32 bit patterns directly (10-bit mantissa,
 // fp32 range), so there is no conversion pass and no second copy of any tensor.
 // The "gather" of TRN frame tuples, the source/target split and the per-frame dgrad are all
@@ -29,11 +30,14 @@
 
 namespace ta3n {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_THREADS = 192;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 16 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;   // + slack for 1024 B alignment
+// Two pipeline depths: 3 stages (97 KB, two CTAs per SM: one CTA's epilogue overlaps the other's main
+// loop) for grids beyond a wave; 6 stages (193 KB, one CTA per SM, twice the bytes in flight per CTA)
+// for the sub-wave grids of this workload, where a CTA is alone on its SM and TMA latency-bound.
+constexpr int tc_smem_bytes(int stages) { return stages * TC_STAGE_BYTES + 1024; }   // + 1024 B alignment slack
 constexpr int TC_TMEM_COLS = 128;
 #ifndef TA3N_MAX_MAPS
 #define TA3N_MAX_MAPS 64
@@ -156,8 +160,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(bool a_kmaj, bool b_kmaj,
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------
-template <bool A_KMAJ, bool B_KMAJ>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+template <bool A_KMAJ, bool B_KMAJ, int TC_STAGES>
+__global__ void __launch_bounds__(TC_THREADS, TC_STAGES <= 3 ? 2 : 1)
 seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant__ TcMaps maps,
                    const __grid_constant__ TcSegMaps segmaps, const int dbg) {
   extern __shared__ uint8_t tc_smem_raw[];
@@ -277,8 +281,14 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
     }
   } else {
     // =========================== epilogue (4 warps, 32 TMEM lanes each) ===========================
+    // Lane i of warp lq owns accumulator row 32*lq + i; tcgen05.ld hands it 32 consecutive columns, which
+    // it finishes (fused epilogue) and writes as 8 x 16 B stores: every 128 B line of C is written whole.
     const int lq = warp & 3;              // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(smem) + lq * (32 * 33);   // pipeline smem is idle by now
+    const Group e = ctx.g;                // register copy: no reloads behind the global stores
+    const int m = m0 + lq * 32 + lane;
+    const bool split_out = e.ksplit > 1;
+    float* const obase = split_out ? e.partial + (size_t)split * e.M * e.N : e.C;
+    const int ldo = split_out ? e.N : e.ldc;
     if (n_iter > 0) {
       mbar_wait(&tmem_full_bar, 0);
       tc_fence_after();
@@ -286,28 +296,35 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
 #pragma unroll 1
     for (int c = 0; c < TC_BN / 32; ++c) {
       float v[32];
-      if (n_iter > 0) {
+      if (n_iter > 0 && !(dbg & 128)) {
         tmem_ld_32x32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(c * 32), v);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
+      const int nb = n0 + c * 32;
+      if (m < e.M && nb < e.N && !(dbg & 1) && (!(dbg & 32) || lane == 0)) {
+        float* orow = obase + (size_t)m * ldo + nb;
+        if (dbg & 64) {
+          orow[0] = v[0];
+          continue;
+        }
+        if (!split_out && !(dbg & 256)) {
+          TA3N_EPI_DISPATCH(e.flags, {
+            _Pragma("unroll") for (int j = 0; j < 32; ++j)
+              if (nb + j < e.N) v[j] = epilogue_t<EPI_F>(e, m, nb + j, v[j]);
+          })
+        }
+        if (nb + 32 <= e.N && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
-      __syncwarp();
-      const int n = n0 + c * 32 + lane;
-      if (n < g.N && !(dbg & 1)) {
-        for (int r = 0; r < 32; ++r) {
-          const int m = m0 + lq * 32 + r;
-          if (m >= g.M) break;
-          const float acc = stg[r * 33 + lane];
-          if (g.ksplit > 1)
-            g.partial[((size_t)split * g.M + m) * g.N + n] = acc;
-          else
-            g.C[(size_t)m * g.ldc + n] = apply_epilogue(g, m, n, acc);
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < e.N) orow[j] = v[j];
         }
       }
-      __syncwarp();
     }
   }
 
@@ -395,13 +412,13 @@ inline bool tc_group_ok(const GemmPlan& plan, const Group& g) {
   return true;
 }
 
-template <bool A_KMAJ, bool B_KMAJ>
-inline int tc_launch_one(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
-                         const char* label) {
+template <bool A_KMAJ, bool B_KMAJ, int STAGES>
+inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
+                            const char* label) {
   static bool configured = false;
   if (!configured) {
-    TA3N_CUDA(cudaFuncSetAttribute(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   TC_SMEM_BYTES));
+    TA3N_CUDA(cudaFuncSetAttribute(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(STAGES)));
     configured = true;
   }
   static const int dbg = []() {
@@ -409,8 +426,21 @@ inline int tc_launch_one(const GemmTable& tab, const TcMaps& maps, const TcSegMa
     return e ? atoi(e) : 0;
   }();
   pre_launch(label, stream);
-  seg_gemm_tc_kernel<A_KMAJ, B_KMAJ><<<tab.total_tiles, TC_THREADS, TC_SMEM_BYTES, stream>>>(tab, maps, sm, dbg);
+  seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES><<<tab.total_tiles, TC_THREADS, tc_smem_bytes(STAGES), stream>>>(
+      tab, maps, sm, dbg);
   return after_launch();
+}
+
+template <bool A_KMAJ, bool B_KMAJ>
+inline int tc_launch_one(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
+                         const char* label) {
+  static const int force = []() {
+    const char* e = getenv("TA3N_TC_STAGES");
+    return e ? atoi(e) : 0;
+  }();
+  const bool deep = force ? force > 3 : tab.total_tiles <= 148;
+  return deep ? tc_launch_stages<A_KMAJ, B_KMAJ, 6>(tab, maps, sm, stream, label)
+              : tc_launch_stages<A_KMAJ, B_KMAJ, 3>(tab, maps, sm, stream, label);
 }
 
 // Launch `plan` (all groups eligible) on the tcgen05 engine.

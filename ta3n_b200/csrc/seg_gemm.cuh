@@ -94,9 +94,14 @@ inline Group make_group() {
 }
 
 // ---- epilogue (shared by the SIMT engine, the split-K reducer and the tcgen05 engine) --------
-__device__ __forceinline__ float apply_epilogue(const Group& g, int m, int n, float acc) {
+// F >= 0: flag set known at compile time (dead branches -- notably the 64-bit RNG mixing -- vanish);
+// F < 0 : generic, flags read at run time.  The kernels dispatch the common sets to the specialised
+// instantiations: evaluated per output element, the generic form costs ~100 issued instructions even when
+// every feature is off, which was 80 % of the run time of a small GEMM tile.
+template <int F>
+__device__ __forceinline__ float epilogue_t(const Group& g, int m, int n, float acc) {
+  const int f = (F >= 0) ? F : g.flags;
   float v = g.alpha * acc;
-  const int f = g.flags;
   if (f & EPI_BIAS) v += g.bias[n];
   if (f & EPI_RELU) v = fmaxf(v, 0.0f);
   if (f & EPI_DROP_MASK) v = g.keep[(size_t)m * g.ldkeep + n] ? v * g.drop_scale : 0.0f;
@@ -112,6 +117,21 @@ __device__ __forceinline__ float apply_epilogue(const Group& g, int m, int n, fl
   if (f & EPI_ACCUM) v += g.C[(size_t)m * g.ldc + n];
   return v;
 }
+
+__device__ __forceinline__ float apply_epilogue(const Group& g, int m, int n, float acc) {
+  return epilogue_t<-1>(g, m, n, acc);
+}
+
+// Call `body(tag)` with tag = std::integral_constant<int, F> for the flag set of `flags`.
+#define TA3N_EPI_DISPATCH(flags, ...)                                              \
+  switch (flags) {                                                                  \
+    case 0: { constexpr int EPI_F = 0; __VA_ARGS__; } break;                               \
+    case (EPI_BIAS | EPI_RELU): { constexpr int EPI_F = EPI_BIAS | EPI_RELU; __VA_ARGS__; } break; \
+    case (EPI_BIAS | EPI_RELU | EPI_DROP_RNG): { constexpr int EPI_F = EPI_BIAS | EPI_RELU | EPI_DROP_RNG; __VA_ARGS__; } break; \
+    case EPI_ADDROW: { constexpr int EPI_F = EPI_ADDROW; __VA_ARGS__; } break;              \
+    case EPI_ACCUM: { constexpr int EPI_F = EPI_ACCUM; __VA_ARGS__; } break;                \
+    default: { constexpr int EPI_F = -1; __VA_ARGS__; } break;                              \
+  }
 
 // ---- per-CTA tile context ------------------------------------------------------------------------
 // The launch tables live in kernel-parameter space; indexing them with run-time indices makes every
@@ -321,20 +341,29 @@ seg_gemm_simt_kernel(const __grid_constant__ GemmTable tab) {
   }
 
   const int ty = tid >> 4, tx = tid & 15;
+  const Group e = ctx.g;   // register copy: no reloads behind the global stores
+  if (e.ksplit > 1) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= g.M) continue;
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m >= e.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n >= g.N) continue;
-      if (g.ksplit > 1) {
-        g.partial[((size_t)split * g.M + m) * g.N + n] = acc[i][j];
-      } else {
-        g.C[(size_t)m * g.ldc + n] = apply_epilogue(g, m, n, acc[i][j]);
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (n < e.N) e.partial[((size_t)split * e.M + m) * e.N + n] = acc[i][j];
       }
     }
+  } else {
+    TA3N_EPI_DISPATCH(e.flags, {
+      _Pragma("unroll") for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= e.M) continue;
+        _Pragma("unroll") for (int j = 0; j < 4; ++j) {
+          const int n = n0 + tx * 4 + j;
+          if (n < e.N) e.C[(size_t)m * e.ldc + n] = epilogue_t<EPI_F>(e, m, n, acc[i][j]);
+        }
+      }
+    })
   }
 }
 
@@ -350,12 +379,15 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
   }
   if (g.ksplit <= 1) return;
   const size_t total = (size_t)g.M * g.N;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < g.ksplit; ++k) s += g.partial[(size_t)k * total + e];
-    const int m = (int)(e / g.N), n = (int)(e % g.N);
-    g.C[(size_t)m * g.ldc + n] = apply_epilogue(g, m, n, s);
-  }
+  const Group gr = g;
+  TA3N_EPI_DISPATCH(gr.flags, {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < gr.ksplit; ++k) s += gr.partial[(size_t)k * total + e];
+      const int m = (int)(e / gr.N), n = (int)(e % gr.N);
+      gr.C[(size_t)m * gr.ldc + n] = epilogue_t<EPI_F>(gr, m, n, s);
+    }
+  })
 }
 
 inline unsigned splitk_reduce_blocks(const GemmTable& tab) {
