@@ -68,18 +68,22 @@ def traffic_model(M, T, F, C):
     video = 3 * (H * H + 3 * H + 2 + C * H + C) + 4 * M * H + 3 * M * (C + 2)
     scope_b = scope_a + f4 * (shared + frame_disc + video)
     n_rel = rs.n_rel
-    sites = {
+    frame_fwd = M * T * F + F * F + F + M * T * F          # frame-disc hidden GEMM: feat, W1, b1 -> hidden
+    video_fwd = M * H + H * H + H + M * H
+    w_shared = M * T * F + M * T * D + F * D               # d_pre, x -> dW
+    w_trn = n_rel * M * H + M * T * F + Wt
+    w_frame = 2 * M * T * F + F * F + M * T * 2 + 2 * F
+    w_video = 2 * M * H + H * H + M * 2 + 2 * H + M * C + M * H + C * H
+    w_rel = 2 * R * M * H + R * H * H + R * M * 2 + R * 2 * H + R * M * H
+    sites = {   # algorithmic bytes of ONE launch of each GEMM call site of the TrainStep launch sequence
         "shared_fc_fwd": f4 * (M * T * D + F * D + F + M * T * F),
-        "shared_fc_wgrad": f4 * (M * T * F + M * T * D + F * D),
-        "trn_fwd": f4 * (M * T * F + Wt + n_rel * M * H),
-        "trn_wgrad": f4 * (n_rel * M * H + M * T * F + Wt),
-        "trn_dgrad": f4 * (n_rel * M * H + Wt + M * T * F),
-        "disc_fwd": f4 * (M * T * F + F * F + F + M * T * F) + f4 * (M * H + H * H + H + M * H),
-        "disc_wgrad": f4 * (2 * M * T * F + F * F + M * T * 2 + 2 * F) + f4 * (2 * M * H + H * H + M * 2 + 2 * H),
-        "disc_dgrad": f4 * (M * T * F + F * F + 2 * M * T * F) + f4 * (M * H + H * H + M * H),
+        "fwd_batch": f4 * (frame_fwd + M * T * F + Wt + n_rel * M * H),      # frame-disc hidden + TRN relations
         "relattn_fwd": f4 * (M * R * H + R * (H * H + H) + R * M * H),
-        "relattn_wgrad": f4 * (2 * R * M * H + R * H * H + R * M * 2 + R * 2 * H + R * M * H),
+        "disc_fwd": f4 * video_fwd,
+        "disc_dgrad": f4 * (M * T * F + F * F + 2 * M * T * F) + f4 * (M * H + H * H + M * H),   # 2 launches
         "relattn_dgrad": f4 * (R * M * H + R * H * H + M * H + M * R + M * R * H),
+        "trn_dgrad": f4 * (n_rel * M * H + Wt + M * T * F),
+        "wgrad_all": f4 * (w_shared + w_trn + w_frame + w_video + w_rel),    # every weight gradient of the step
     }
     flops_b = 3 * (2 * M * S * F * H + R * (2 * M * H * H + 4 * M * H)) + \
         3 * (2 * M * T * F * F + 4 * M * T * F + 2 * M * H * H + 4 * M * H + 2 * M * H * C) + 2 * (2 * M * T * D * F)

@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <map>
 #include <tuple>
 
@@ -175,7 +176,10 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
 
   // ---- tile decode (same scheme as the SIMT engine, 128x128 tiles); group + segments staged in smem ----
   __shared__ TileCtx ctx;
-  const int tile = blockIdx.x;
+  // Groups arrive sorted by K (longest first).  CTAs beyond the first wave of 148 take tiles from the END
+  // of the list, so the SM that received the longest tile gets the shortest one as its second resident CTA.
+  int tile = blockIdx.x;
+  if (tile >= 148) tile = tab.total_tiles - 1 - (tile - 148);
   load_tile_ctx(tab, tile, &ctx, segmaps.a, segmaps.b);
   const Group& g = ctx.g;
   int local = tile - g.tile_begin;
@@ -443,8 +447,33 @@ inline int tc_launch_one(const GemmTable& tab, const TcMaps& maps, const TcSegMa
               : tc_launch_stages<A_KMAJ, B_KMAJ, 3>(tab, maps, sm, stream, label);
 }
 
+// Copy the groups `idx` of `plan` (with their segments) into a new plan.
+inline GemmPlan sub_plan(const GemmPlan& plan, const std::vector<int>& idx) {
+  GemmPlan out;
+  out.a_kmaj = plan.a_kmaj;
+  out.b_kmaj = plan.b_kmaj;
+  out.load_flags = plan.load_flags;
+  out.label = plan.label;
+  for (int i : idx) {
+    Group g = plan.groups[i];
+    const int b = g.seg_begin;
+    g.seg_begin = (int)out.segs.size();
+    for (int k = 0; k < g.seg_count; ++k) out.segs.push_back(plan.segs[b + k]);
+    out.groups.push_back(g);
+  }
+  return out;
+}
+
 // Launch `plan` (all groups eligible) on the tcgen05 engine.
-inline int launch_tc(const GemmPlan& plan, cudaStream_t stream) {
+inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
+  // longest-K groups first (see the tile remap in the kernel): LPT-style balance of the tensor pipe
+  std::vector<int> order(plan_in.groups.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return plan_in.k_total(plan_in.groups[a]) / plan_in.groups[a].ksplit >
+           plan_in.k_total(plan_in.groups[b]) / plan_in.groups[b].ksplit;
+  });
+  const GemmPlan plan = sub_plan(plan_in, order);
   size_t gi = 0;
   while (gi < plan.groups.size()) {
     GemmTable tab;
@@ -518,23 +547,6 @@ inline int launch_tc(const GemmPlan& plan, cudaStream_t stream) {
     }
   }
   return TA3N_OK;
-}
-
-// Copy the groups `idx` of `plan` (with their segments) into a new plan.
-inline GemmPlan sub_plan(const GemmPlan& plan, const std::vector<int>& idx) {
-  GemmPlan out;
-  out.a_kmaj = plan.a_kmaj;
-  out.b_kmaj = plan.b_kmaj;
-  out.load_flags = plan.load_flags;
-  out.label = plan.label;
-  for (int i : idx) {
-    Group g = plan.groups[i];
-    const int b = g.seg_begin;
-    g.seg_begin = (int)out.segs.size();
-    for (int k = 0; k < g.seg_count; ++k) out.segs.push_back(plan.segs[b + k]);
-    out.groups.push_back(g);
-  }
-  return out;
 }
 
 // Run a plan.  With the tf32 engine selected, every group the tensor-core kernel can take runs

@@ -409,84 +409,172 @@ __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restri
 
 __global__ void counter_inc_kernel(unsigned long long* ctr) { ctr[0] += 1ull; }
 
-// ---- deterministic column sums (bias gradients) ------------------------------------------------
-struct ColsumJob {
+// ---- deterministic (weighted) column sums: bias gradients and the skinny head weight gradients ----
+//   out[k*ldo + n] = sum_seg sum_r  P_seg[r*ldp + k] * X_seg[r*ld + n]      k < N2 <= 32, n < N
+// P == nullptr -> N2 = 1 with unit weights (a plain column sum = a bias gradient).  The N2 x N outputs of
+// the two-logit / C-logit heads (dW2 [2,H], dWc [C,H]) are tall-skinny reductions over the rows; as GEMM
+// tiles they would be 98 % padding.  Two stages (row splits -> fixed-order sum) keep it deterministic.
+struct WColsumJob {
   const float* X[4];
+  const float* P[4];
   int rows[4];
   int nseg;
-  int ld;
-  int N;
+  int ld, ldp;
+  int N, N2;
+  int ldo;
   float* out;
+  float* partial;   // [splits, N2, N]
 };
-constexpr int kMaxColsumJobs = 40;
-struct ColsumTable {
+constexpr int kMaxWColsumJobs = 40;
+constexpr int kWColsumSplits = 16;
+struct WColsumTable {
   int n_jobs;
-  ColsumJob job[kMaxColsumJobs];
+  WColsumJob job[kMaxWColsumJobs];
 };
 
-// block = 32 columns x 32 row-stripes; grid = (ceil(maxN/32), n_jobs)
-__global__ void __launch_bounds__(1024) colsum_kernel(const __grid_constant__ ColsumTable tab) {
-  __shared__ float red[32][33];
-  __shared__ ColsumJob j;   // staged: run-time indexed kernel parameters are slow generic loads
+// stage 1: grid (ceil(maxN/32), n_jobs, splits), block (32, 8)
+template <int KMAX>
+__device__ __forceinline__ void wcolsum_body(const WColsumJob& j, float (*red)[33]) {
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int split = blockIdx.z, nsplit = gridDim.z;
+  float acc[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  if (n < j.N) {
+    for (int sg = 0; sg < j.nseg; ++sg) {
+      const float* X = j.X[sg];
+      const float* P = j.P[sg];
+      const int rows = j.rows[sg];
+      const int per = (rows + nsplit - 1) / nsplit;
+      const int r1 = min(rows, (split + 1) * per);
+      for (int r = split * per + threadIdx.y; r < r1; r += 8) {
+        const float x = X[(size_t)r * j.ld + n];
+        if (P == nullptr) {
+          acc[0] += x;
+        } else {
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k)
+            if (k < j.N2) acc[k] = fmaf(__ldg(P + (size_t)r * j.ldp + k), x, acc[k]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k >= j.N2) break;
+    red[threadIdx.y][threadIdx.x] = acc[k];
+    __syncthreads();
+    if (threadIdx.y == 0 && n < j.N) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+      j.partial[((size_t)split * j.N2 + k) * j.N + n] = t;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) wcolsum_stage1_kernel(const __grid_constant__ WColsumTable tab) {
+  __shared__ float red[8][33];
+  __shared__ WColsumJob j;   // staged: run-time indexed kernel parameters are slow generic loads
   {
     const int* src = reinterpret_cast<const int*>(&tab.job[blockIdx.y]);
     int* dst = reinterpret_cast<int*>(&j);
     const int t = threadIdx.y * 32 + threadIdx.x;
-    if (t < (int)(sizeof(ColsumJob) / sizeof(int))) dst[t] = src[t];
+    if (t < (int)(sizeof(WColsumJob) / sizeof(int))) dst[t] = src[t];
     __syncthreads();
   }
-  const int n = blockIdx.x * 32 + threadIdx.x;
   if (blockIdx.x * 32 >= j.N) return;
-  float s = 0.f;
-  if (n < j.N) {
-    for (int sg = 0; sg < j.nseg; ++sg) {
-      const float* X = j.X[sg];
-      for (int r = threadIdx.y; r < j.rows[sg]; r += 32) s += X[(size_t)r * j.ld + n];
-    }
+  if (j.N2 <= 1)
+    wcolsum_body<1>(j, red);
+  else if (j.N2 <= 2)
+    wcolsum_body<2>(j, red);
+  else if (j.N2 <= 16)
+    wcolsum_body<16>(j, red);
+  else
+    wcolsum_body<32>(j, red);
+}
+
+// stage 2: out[k, n] = sum_split partial[split, k, n]; grid (blocks, n_jobs)
+__global__ void __launch_bounds__(256) wcolsum_stage2_kernel(const __grid_constant__ WColsumTable tab, int nsplit) {
+  __shared__ WColsumJob j;
+  {
+    const int* src = reinterpret_cast<const int*>(&tab.job[blockIdx.y]);
+    int* dst = reinterpret_cast<int*>(&j);
+    if (threadIdx.x < (int)(sizeof(WColsumJob) / sizeof(int))) dst[threadIdx.x] = src[threadIdx.x];
+    __syncthreads();
   }
-  red[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && n < j.N) {
-    float t = 0.f;
-#pragma unroll
-    for (int y = 0; y < 32; ++y) t += red[y][threadIdx.x];
-    j.out[n] = t;
+  const int total = j.N2 * j.N;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) s += j.partial[(size_t)sp * total + e];
+    j.out[(size_t)(e / j.N) * j.ldo + (e % j.N)] = s;
   }
 }
 
 struct ColsumPlan {
-  std::vector<ColsumJob> jobs;
-  ColsumJob& add(float* out, int N, int ld) {
-    ColsumJob j;
+  std::vector<WColsumJob> jobs;
+  // plain column sum of X (N columns, leading dimension ld) -> out[N]
+  WColsumJob& add(float* out, int N, int ld) {
+    WColsumJob j;
     memset(&j, 0, sizeof(j));
     j.out = out;
     j.N = N;
     j.ld = ld;
+    j.N2 = 1;
+    j.ldo = N;
     jobs.push_back(j);
     return jobs.back();
   }
-  void seg(const float* X, int rows) {
-    ColsumJob& j = jobs.back();
+  // weighted: out[k*ldo + n] = sum_r P[r*ldp + k] X[r*ld + n]
+  WColsumJob& add_weighted(float* out, int ldo, int N2, int N, int ld, int ldp) {
+    WColsumJob& j = add(out, N, ld);
+    j.N2 = N2;
+    j.ldo = ldo;
+    j.ldp = ldp;
+    return j;
+  }
+  void seg(const float* X, int rows, const float* P = nullptr) {
+    WColsumJob& j = jobs.back();
     if (rows <= 0) return;
     j.X[j.nseg] = X;
+    j.P[j.nseg] = P;
     j.rows[j.nseg] = rows;
     j.nseg++;
   }
-  int run(cudaStream_t stream) {
+  static size_t workspace_bytes(size_t total_out_elems) {
+    return Arena::round(total_out_elems * kWColsumSplits * sizeof(float)) + 256 * (size_t)kMaxWColsumJobs;
+  }
+  // Needs arena space for the stage-1 partials (kWColsumSplits x outputs).
+  int run(cudaStream_t stream, Arena* arena) {
     size_t i = 0;
     while (i < jobs.size()) {
-      ColsumTable tab;
+      WColsumTable tab;
       tab.n_jobs = 0;
-      int maxN = 0;
-      while (i < jobs.size() && tab.n_jobs < kMaxColsumJobs) {
-        tab.job[tab.n_jobs++] = jobs[i];
-        if (jobs[i].N > maxN) maxN = jobs[i].N;
+      int maxN = 0, maxOut = 0;
+      while (i < jobs.size() && tab.n_jobs < kMaxWColsumJobs) {
+        WColsumJob j = jobs[i];
+        if (j.nseg == 0) {   // nothing to sum: the gradient is zero
+          for (int k = 0; k < j.N2; ++k)
+            TA3N_CUDA(cudaMemsetAsync(j.out + (size_t)k * j.ldo, 0, sizeof(float) * j.N, stream));
+          ++i;
+          continue;
+        }
+        j.partial = arena ? arena->floats((size_t)kWColsumSplits * j.N2 * j.N) : nullptr;
+        if (!j.partial) return fail(TA3N_ERR_WORKSPACE, "column-sum workspace too small");
+        tab.job[tab.n_jobs++] = j;
+        if (j.N > maxN) maxN = j.N;
+        if (j.N * j.N2 > maxOut) maxOut = j.N * j.N2;
         ++i;
       }
-      if (maxN == 0) continue;
-      dim3 grid((maxN + 31) / 32, tab.n_jobs), block(32, 32);
-      pre_launch("colsum", stream);
-      colsum_kernel<<<grid, block, 0, stream>>>(tab);
+      if (tab.n_jobs == 0) continue;
+      dim3 grid((maxN + 31) / 32, tab.n_jobs, kWColsumSplits), block(32, 8);
+      pre_launch("wcolsum", stream);
+      wcolsum_stage1_kernel<<<grid, block, 0, stream>>>(tab);
+      TA3N_TRY(after_launch());
+      dim3 grid2((maxOut + 255) / 256, tab.n_jobs);
+      pre_launch("wcolsum_reduce", stream);
+      wcolsum_stage2_kernel<<<grid2, 256, 0, stream>>>(tab, kWColsumSplits);
       TA3N_TRY(after_launch());
     }
     return TA3N_OK;

@@ -154,12 +154,15 @@ int submit_fwd(GemmPlan& plan, cudaStream_t st, std::function<int(cudaStream_t)>
   return TA3N_OK;
 }
 
-int submit_colsum(ColsumPlan& cs, cudaStream_t st) {
+int submit_colsum(ColsumPlan& cs, cudaStream_t st, Arena* arena) {
   DeferCtx& d = defer_ctx();
-  if (!d.active) return cs.run(st);
+  if (!d.active) return cs.run(st, arena);
   for (auto& j : cs.jobs) d.cs.jobs.push_back(j);
   return TA3N_OK;
 }
+
+// workspace of the (weighted) column sums producing `out_elems` gradient values
+inline size_t colsum_bytes(size_t out_elems) { return ColsumPlan::workspace_bytes(out_elems); }
 
 }  // namespace
 
@@ -190,15 +193,15 @@ int ta3n_wgrad_defer_begin(void) {
   return TA3N_OK;
 }
 
-size_t ta3n_wgrad_defer_workspace_bytes(void) { return splitk_bytes(64); }
+size_t ta3n_wgrad_defer_workspace_bytes(void) { return splitk_bytes(64) + colsum_bytes((size_t)1 << 20); }
 
 int ta3n_wgrad_defer_flush(void* workspace, size_t workspace_bytes, ta3n_stream_t stream) {
   DeferCtx& d = defer_ctx();
   if (!d.active) return fail(TA3N_ERR_INVALID, "ta3n_wgrad_defer_flush without ta3n_wgrad_defer_begin");
   d.active = false;
   Arena arena(workspace, workspace_bytes);
-  int rc = run_gemm(d.wgrad, S(stream), workspace ? &arena : nullptr);
-  if (rc == TA3N_OK) rc = d.cs.run(S(stream));
+  int rc = d.cs.run(S(stream), &arena);   // first: its partials are small and must fit
+  if (rc == TA3N_OK) rc = run_gemm(d.wgrad, S(stream), workspace ? &arena : nullptr);
   d.reset();
   return rc;
 }
@@ -291,8 +294,8 @@ int ta3n_shared_fc_fwd(const float* x_src, int rows_src, const float* x_tgt, int
 }
 
 size_t ta3n_shared_fc_bwd_workspace_bytes(int rows, int D, int F) {
-  (void)rows; (void)D; (void)F;
-  return splitk_bytes(1);
+  (void)rows; (void)D;
+  return splitk_bytes(1) + colsum_bytes(F);
 }
 
 int ta3n_shared_fc_bwd(const float* x_src, int rows_src, const float* x_tgt, int rows_tgt, int D, int F,
@@ -325,7 +328,7 @@ int ta3n_shared_fc_bwd(const float* x_src, int rows_src, const float* x_tgt, int
   ColsumPlan cs;
   cs.add(db, F, F);
   cs.seg(dfeat, rows);
-  return submit_colsum(cs, S(stream));
+  return submit_colsum(cs, S(stream), &arena);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -351,7 +354,7 @@ int ta3n_disc_fwd(const float* x, int rows, int K, int Kh, const float* W1, cons
 
 size_t ta3n_disc_bwd_workspace_bytes(int rows, int K, int Kh) {
   (void)K;
-  return Arena::round((size_t)rows * Kh * sizeof(float)) + splitk_bytes(2);
+  return Arena::round((size_t)rows * Kh * sizeof(float)) + splitk_bytes(2) + colsum_bytes((size_t)3 * Kh + 2);
 }
 
 int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, const float* W2,
@@ -380,24 +383,24 @@ int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, cons
                                                                            rows, Kh);
   TA3N_TRY(after_launch());
 
-  {  // dW2 [2,Kh] = g_logits^T hidden ; dW1 [Kh,K] = dH^T x
-    GemmPlan plan;
-    plan.label = "disc_wgrad";
-    plan.a_kmaj = false;
-    plan.b_kmaj = false;
-    plan.add_group(2, Kh, dW2, Kh);
-    plan.add_seg(g_logits, 2, hidden, Kh, rows);
-    plan.add_group(Kh, K, dW1, K);
-    plan.add_seg(dH, Kh, x, K, rows);
-    TA3N_TRY(submit_wgrad(plan, st, &arena));
-  }
-  {
+  {  // dW2 [2,Kh] = g_logits^T hidden (skinny: weighted column sum), db2, db1
     ColsumPlan cs;
+    cs.add_weighted(dW2, Kh, 2, Kh, Kh, 2);
+    cs.seg(hidden, rows, g_logits);
     cs.add(db2, 2, 2);
     cs.seg(g_logits, rows);
     cs.add(db1, Kh, Kh);
     cs.seg(dH, rows);
-    TA3N_TRY(submit_colsum(cs, st));
+    TA3N_TRY(submit_colsum(cs, st, &arena));
+  }
+  {  // dW1 [Kh,K] = dH^T x
+    GemmPlan plan;
+    plan.label = "disc_wgrad";
+    plan.a_kmaj = false;
+    plan.b_kmaj = false;
+    plan.add_group(Kh, K, dW1, K);
+    plan.add_seg(dH, Kh, x, K, rows);
+    TA3N_TRY(submit_wgrad(plan, st, &arena));
   }
   if (dx) {  // dx (+)= -beta * dH W1
     GemmPlan plan;
@@ -484,7 +487,8 @@ size_t ta3n_trn_bwd_workspace_bytes(int M, int F, int H, const ta3n_relation_tab
   RelLayout L;
   if (parse_table(tab, &L) != TA3N_OK) return 0;
   (void)F;
-  return Arena::round((size_t)L.n_rel * M * H * sizeof(float)) + splitk_bytes(L.n_slots);
+  return Arena::round((size_t)L.n_rel * M * H * sizeof(float)) + splitk_bytes(L.n_slots) +
+         colsum_bytes((size_t)L.R * H);
 }
 
 int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table* tab,
@@ -540,7 +544,7 @@ int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table*
       cs.add(db_host[i], H, H);
       for (int q = L.rel_begin[i]; q < L.rel_begin[i + 1]; ++q) cs.seg(dz + q * plane, M);
     }
-    TA3N_TRY(submit_colsum(cs, st));
+    TA3N_TRY(submit_colsum(cs, st, &arena));
   }
   if (dx) {  // dgrad, deterministic per frame: dx[:, t, :] = sum_{(q,j): tau_q[j]=t} dz_q W_i[:, jF:(j+1)F]
     GemmPlan plan;
@@ -610,7 +614,7 @@ int ta3n_relattn_fwd(const float* feat_rel, int M, int R, int H, const float* co
 
 size_t ta3n_relattn_bwd_workspace_bytes(int M, int R, int H) {
   return Arena::round((size_t)M * R * 2 * sizeof(float)) + Arena::round((size_t)R * M * H * sizeof(float)) +
-         splitk_bytes(2 * R);
+         splitk_bytes(2 * R) + colsum_bytes((size_t)R * (3 * H + 2));
 }
 
 int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* const* W1_host,
@@ -653,8 +657,6 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
     plan.a_kmaj = false;
     plan.b_kmaj = false;
     for (int i = 0; i < R; ++i) {
-      plan.add_group(2, H, dW2_host[i], H);
-      plan.add_seg(Pt + (size_t)i * 2, R * 2, hidden + (size_t)i * M * H, H, M);
       plan.add_group(H, H, dW1_host[i], H);
       plan.add_seg(dHid + (size_t)i * M * H, H, feat_rel + (size_t)i * H, R * H, M);
     }
@@ -663,12 +665,14 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
   {
     ColsumPlan cs;
     for (int i = 0; i < R; ++i) {
+      cs.add_weighted(dW2_host[i], H, 2, H, H, R * 2);           // dW2_i [2,H] = Pt_i^T hidden_i
+      cs.seg(hidden + (size_t)i * M * H, M, Pt + (size_t)i * 2);
       cs.add(db2_host[i], 2, R * 2);
       cs.seg(Pt + (size_t)i * 2, M);
       cs.add(db1_host[i], H, H);
       cs.seg(dHid + (size_t)i * M * H, M);
     }
-    TA3N_TRY(submit_colsum(cs, st));
+    TA3N_TRY(submit_colsum(cs, st, &arena));
   }
   {  // d_feat_rel[:, i, :] = (w_i + 1) G - beta * dHid_i W1_i
     GemmPlan plan;
@@ -716,8 +720,8 @@ int ta3n_video_head_fwd(const float* feat_video, int M, int H, int C, const floa
 }
 
 size_t ta3n_video_head_bwd_workspace_bytes(int M, int H, int C) {
-  (void)M; (void)H; (void)C;
-  return splitk_bytes(1);
+  (void)M;
+  return splitk_bytes(1) + colsum_bytes((size_t)C * (H + 1));
 }
 
 int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* Wc, const ta3n_dropout* drop,
@@ -741,17 +745,26 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
   TA3N_TRY(after_launch());
   if (g_pred) {
     Arena arena(workspace, workspace_bytes);
-    GemmPlan plan;
-    plan.label = "video_head_wgrad";
-    plan.a_kmaj = false;
-    plan.b_kmaj = false;
-    plan.add_group(C, H, dWc, H);
-    plan.add_seg(g_pred, C, dropped, H, M);
-    TA3N_TRY(submit_wgrad(plan, st, &arena));
-    ColsumPlan cs;
-    cs.add(dbc, C, C);
-    cs.seg(g_pred, M);
-    TA3N_TRY(submit_colsum(cs, st));
+    if (C <= 32) {   // dWc [C,H] = g_pred^T dropped: skinny -> weighted column sum
+      ColsumPlan cs;
+      cs.add_weighted(dWc, H, C, H, H, C);
+      cs.seg(dropped, M, g_pred);
+      cs.add(dbc, C, C);
+      cs.seg(g_pred, M);
+      TA3N_TRY(submit_colsum(cs, st, &arena));
+    } else {
+      GemmPlan plan;
+      plan.label = "video_head_wgrad";
+      plan.a_kmaj = false;
+      plan.b_kmaj = false;
+      plan.add_group(C, H, dWc, H);
+      plan.add_seg(g_pred, C, dropped, H, M);
+      TA3N_TRY(submit_wgrad(plan, st, &arena));
+      ColsumPlan cs;
+      cs.add(dbc, C, C);
+      cs.seg(g_pred, M);
+      TA3N_TRY(submit_colsum(cs, st, &arena));
+    }
   }
   return TA3N_OK;
 }
