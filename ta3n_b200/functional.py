@@ -290,10 +290,13 @@ def path_forward(spec: PathSpec, xs, xt, params, bufs: Buffers, batch_gemms: boo
     return saved, outputs, (Bs, Bt, D, T, F, H, Cn)
 
 
-def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: Buffers):
+def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: Buffers, stage_done=None):
     """The backward C calls in their fixed order.  ``gin``: dict of incoming output gradients
     (feat, pred_frame, attn, pred_rel, feat_video, pred_video, pred_dom_video; missing/None = zero).
-    ``gout``: list of tensors (same order as ``params``) that receive the parameter gradients."""
+    ``gout``: list of tensors (same order as ``params``) that receive the parameter gradients.
+    ``stage_done(name)`` (optional) is called after each module's calls ('video', 'relation', 'trn',
+    'frame', 'shared') -- TrainStep uses it to issue the deferred weight-gradient work on a second stream."""
+    stage_done = stage_done or (lambda name: None)
     lib = _lib.load()
     st = _stream()
     Bs, Bt, D, T, F, H, Cn = dims
@@ -322,6 +325,7 @@ def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: 
     check(lib.ta3n_video_head_bwd(_p(dropped), M, H, Cn, _p(w_c), _dref(d_v), _p(g("pred_video")), _p(d_dropped),
                                   _p(g("feat_video")), float(-spec.mu) if spec.reverse else 1.0, _p(G),
                                   _p(dw_c), _p(db_c), _p(ws), ws.numel(), st))
+    stage_done("video")
     # 4'. relation discriminators / attention (attention weights are NOT detached)
     d_feat_rel = new("d_feat_rel", M, R, H)
     ws = wsp("relattn", lib.ta3n_relattn_bwd_workspace_bytes(M, R, H))
@@ -331,12 +335,14 @@ def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: 
                                _p(d_feat_rel), ptr_array([_p(t) for t in dr_w1]),
                                ptr_array([_p(t) for t in dr_b1]), ptr_array([_p(t) for t in dr_w2]),
                                ptr_array([_p(t) for t in dr_b2]), _p(ws), ws.numel(), st))
+    stage_done("relation")
     # 3'. TRN
     d_feat = new("d_feat", M * T, F)
     ws = wsp("trn", lib.ta3n_trn_bwd_workspace_bytes(M, F, H, rs.ref))
     check(lib.ta3n_trn_bwd(_p(feat_in), M, F, H, rs.ref, ptr_array([_p(w) for w in trn_w]), 0, _p(act),
                            _p(d_feat_rel), ptr_array([_p(t) for t in dtrn_w]),
                            ptr_array([_p(t) for t in dtrn_b]), _p(d_feat), _p(ws), ws.numel(), st))
+    stage_done("trn")
     # 2b'. frame attention (needs a writable copy of the frame-logit gradient)
     g_pf = g("pred_frame")
     if g_pf is not None:
@@ -354,12 +360,14 @@ def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: 
     check(lib.ta3n_disc_bwd(_p(feat), M * T, F, F, _p(w1f), _p(w2f), _p(hid_f), _p(g_pf),
                             float(spec.beta[2]), _p(d_feat), 1, _p(dw1f), _p(db1f), _p(dw2f), _p(db2f),
                             _p(ws), ws.numel(), st))
+    stage_done("frame")
     # 1'. shared layer (wgrad only; the input features carry no gradient)
     ws = wsp("shared", lib.ta3n_shared_fc_bwd_workspace_bytes(M * T, D, F))
     g_feat = g("feat")
     g_feat_flat = None if g_feat is None else g_feat.reshape(M * T, F)
     check(lib.ta3n_shared_fc_bwd(_p(xs), Bs * T, _p(xt), Bt * T, D, F, _p(feat), _p(d_feat), _p(g_feat_flat),
                                  float(spec.drop_i.p), _p(dw_sh), _p(db_sh), _p(ws), ws.numel(), st))
+    stage_done("shared")
 
 
 _OUT_NAMES = ("feat", "pred_frame", "attn", "pred_rel", "feat_video", "pred_video", "pred_dom_video")

@@ -27,7 +27,7 @@ _P = TF._p
 class TrainStep:
     def __init__(self, model, batch_source: int, batch_target: int, beta: Sequence[float], gamma: float = 0.003,
                  place_adv: Sequence[str] = ("Y", "Y", "Y"), add_loss_DA: str = "attentive_entropy",
-                 use_graph: bool = True, process_group=None, seed: int = 0x5EED):
+                 use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False, overlap_wgrad: bool = True):
         if not model.training:
             raise ValueError("TrainStep needs model.train() (dropout state is fixed at construction)")
         self.model = model
@@ -62,9 +62,15 @@ class TrainStep:
             p.grad = v
 
         f32 = dict(device=dev, dtype=torch.float32)
-        self.xs = torch.zeros(self.Bs, self.T, self.D, **f32)
-        self.xt = torch.zeros(self.Bt, self.T, self.D, **f32)
-        self.labels = torch.zeros(self.Bs, device=dev, dtype=torch.int64)
+        # input slots: one, or two for prefetching the next mini-batch while this one computes
+        self.n_slots = 2 if double_buffer else 1
+        self.slots = [(torch.zeros(self.Bs, self.T, self.D, **f32), torch.zeros(self.Bt, self.T, self.D, **f32),
+                       torch.zeros(self.Bs, device=dev, dtype=torch.int64)) for _ in range(self.n_slots)]
+        self.active = 0
+        self.xs, self.xt, self.labels = self.slots[0]
+        self.copy_stream = torch.cuda.Stream(device=dev) if double_buffer else None
+        self.ready = [None] * self.n_slots          # event: slot filled
+        self.consumed = [None] * self.n_slots       # event: last step that read the slot has finished
         self.loss = torch.zeros(1, **f32)
         self.g_video = torch.zeros(self.M, self.C, **f32)
         self.g_rel = torch.zeros(self.M, self.R, 2, **f32)
@@ -81,10 +87,18 @@ class TrainStep:
             drop_i=TF.DropSpec(p=di, seed=seed, step=self.step_counter) if di > 0 else TF.DropSpec(),
             drop_v=TF.DropSpec(p=dv, seed=seed ^ 0x9E3779B9, step=self.step_counter) if dv > 0 else TF.DropSpec())
         self.outputs = None
+        self.overlap_wgrad = bool(overlap_wgrad)
+        self.side_stream = torch.cuda.Stream(device=dev) if self.overlap_wgrad else None
         self.launches_per_step = 0               # kernels of libta3n_sm100.so per step (counted at capture)
+        self.graphs = [None] * self.n_slots      # one captured graph per input slot
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         if use_graph:
-            self._capture()
+            for slot in range(self.n_slots):
+                self.xs, self.xt, self.labels = self.slots[slot]
+                self._capture()
+                self.graphs[slot] = self.graph
+            self.xs, self.xt, self.labels = self.slots[0]
+            self.graph = self.graphs[0]
 
     # -- the fixed launch sequence ---------------------------------------------------------------------
     def _enqueue(self):
@@ -100,14 +114,33 @@ class TrainStep:
                                     _P(self.g_frame), _P(self.loss_ws), self.loss_ws.numel(), st))
         gin = {"pred_video": self.g_video, "pred_rel": self.g_rel, "pred_dom_video": self.g_dom,
                "pred_frame": self.g_frame}
-        # data-gradient chain first; every weight-gradient GEMM / bias column sum of the step is deferred
-        # and issued as one grouped launch per engine at the end (buffers are persistent, so they stay valid)
+        # The data-gradient chain (sub-wave GEMMs + row kernels, each waiting for the previous one) runs on the
+        # main stream; the weight-gradient GEMMs / bias sums it leaves behind are deferred and issued in three
+        # grouped batches on a SECOND stream as soon as their inputs exist, filling the SMs the chain leaves idle
+        # (buffers and workspaces are persistent and distinct per batch, so nothing is overwritten under them).
+        main = torch.cuda.current_stream()
+        side = self.side_stream
+        flush_after = {"relation": 0, "trn": 1, "shared": 2} if self.overlap_wgrad else {"shared": 2}
+
+        def stage_done(name):
+            if name not in flush_after:
+                return
+            ws = self.bufs.workspace(f"wgrad_{flush_after[name]}", lib.ta3n_wgrad_defer_workspace_bytes())
+            if self.overlap_wgrad:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                check(lib.ta3n_wgrad_defer_flush(_P(ws), ws.numel(), side.cuda_stream))
+            else:
+                check(lib.ta3n_wgrad_defer_flush(_P(ws), ws.numel(), st))
+            if name != "shared":
+                check(lib.ta3n_wgrad_defer_begin())
+
         check(lib.ta3n_wgrad_defer_begin())
-        try:
-            TF.path_backward(self.spec, dims, self.xs, self.xt, self.params, saved, gin, self.grad_views, self.bufs)
-        finally:
-            ws = self.bufs.workspace("wgrad_all", lib.ta3n_wgrad_defer_workspace_bytes())
-            check(lib.ta3n_wgrad_defer_flush(_P(ws), ws.numel(), st))
+        TF.path_backward(self.spec, dims, self.xs, self.xt, self.params, saved, gin, self.grad_views, self.bufs,
+                         stage_done=stage_done)
+        if self.overlap_wgrad:
+            main.wait_stream(side)            # join
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)
@@ -125,10 +158,36 @@ class TrainStep:
 
     # -- public API ------------------------------------------------------------------------------------
     def load(self, source, target, labels):
-        """Copy one paired mini-batch (host or device tensors) into the step's static input buffers."""
+        """Copy one paired mini-batch (host or device tensors) into the ACTIVE input slot (compute stream)."""
         self.xs.copy_(source.reshape(self.xs.shape), non_blocking=True)
         self.xt.copy_(target.reshape(self.xt.shape), non_blocking=True)
         self.labels.copy_(labels, non_blocking=True)
+
+    def prefetch(self, source, target, labels):
+        """double_buffer=True: copy the NEXT mini-batch into the inactive slot on the copy stream, overlapping
+        the step that is running; call ``swap()`` before the ``run()`` that should consume it."""
+        if self.n_slots < 2:
+            raise ValueError("prefetch needs TrainStep(double_buffer=True)")
+        nxt = 1 - self.active
+        xs, xt, lab = self.slots[nxt]
+        with torch.cuda.stream(self.copy_stream):
+            if self.consumed[nxt] is not None:
+                self.copy_stream.wait_event(self.consumed[nxt])      # do not overwrite inputs still being read
+            xs.copy_(source.reshape(xs.shape), non_blocking=True)
+            xt.copy_(target.reshape(xt.shape), non_blocking=True)
+            lab.copy_(labels, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.ready[nxt] = ev
+
+    def swap(self):
+        """Make the prefetched slot the active one (the compute stream waits for its copies)."""
+        self.active = 1 - self.active
+        self.xs, self.xt, self.labels = self.slots[self.active]
+        self.graph = self.graphs[self.active]
+        if self.ready[self.active] is not None:
+            torch.cuda.current_stream().wait_event(self.ready[self.active])
+            self.ready[self.active] = None
 
     def run(self):
         """forward + loss + backward (+ gradient all-reduce); returns the device loss tensor (1,)."""
@@ -138,6 +197,10 @@ class TrainStep:
             n0 = _lib.launch_count()
             self._enqueue()
             self.launches_per_step = _lib.launch_count() - n0
+        if self.n_slots > 1:
+            ev = torch.cuda.Event()
+            ev.record()
+            self.consumed[self.active] = ev
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
             self.flat_grad.mul_(1.0 / self.world)

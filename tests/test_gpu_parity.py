@@ -462,3 +462,30 @@ def test_fused_step_dropout_changes_every_replay():
     assert not torch.equal(f1 > 0, f2 > 0)                  # the in-graph counter re-keys the RNG
     keep = ((f1 > 0).float().mean() / ((f1 > 0) | (f2 > 0)).float().mean()).item()
     assert 0.55 < keep < 0.8                                 # P(kept | kept in either) = 0.5/0.75
+
+
+def test_prefetched_inputs_give_the_same_step():
+    """double_buffer=True: the batch copied on the copy stream while the previous step runs is the one
+    the next run() consumes; losses equal those of the plain load()+run() path, bit for bit."""
+    from ta3n_b200.train import TrainStep
+    cfg = orc.PathConfig(num_class=12, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0)
+    params = orc.init_params(cfg, seed=1234)
+    model = build_model(cfg, params, train=True)
+    batches = []
+    for seed in (1, 2, 3):
+        xs, xt, labels = orc.synthetic_batch(16, cfg, seed=seed)
+        batches.append((xs.pin_memory(), xt.pin_memory(), labels.pin_memory()))
+    plain = TrainStep(model, 16, 16, (0.75, 0.75, 0.5), use_graph=True)
+    want = [plain(*b).clone() for b in batches]
+    pipe = TrainStep(model, 16, 16, (0.75, 0.75, 0.5), use_graph=True, double_buffer=True)
+    got = []
+    pipe.prefetch(*batches[0])
+    for k in range(3):
+        pipe.swap()
+        if k + 1 < 3:
+            pipe.prefetch(*batches[k + 1])
+        got.append(pipe.run().clone())
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert not torch.equal(want[0], want[1])
