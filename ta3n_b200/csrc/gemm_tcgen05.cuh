@@ -314,10 +314,8 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
           continue;
         }
         if (!split_out && !(dbg & 256)) {
-          TA3N_EPI_DISPATCH(e.flags, {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j)
-              if (nb + j < e.N) v[j] = epilogue_t<EPI_F>(e, m, nb + j, v[j]);
-          })
+          const int nvalid = min(32, e.N - nb);
+          TA3N_EPI_DISPATCH(e.flags, { epilogue_row32<EPI_F>(e, m, nb, nvalid, v); })
         }
         if (nb + 32 <= e.N && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
 #pragma unroll

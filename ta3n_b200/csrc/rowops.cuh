@@ -65,21 +65,50 @@ __global__ void __launch_bounds__(256) dz_kernel(const float* __restrict__ act, 
 }
 
 // ---- small head: out[row, n] = <x[row,:], W[n,:]> + b[n], n < N2 (warp per row) -----------------
-__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ x, int ldx,
+// W (N2 x K, a few KB) is staged in shared memory by the whole block with all loads in flight at once; a
+// warp then keeps its row of x in registers and produces the N2 logits from on-chip data only.  (The first
+// version re-read W through L1 inside the n loop: N2 dependent round trips per row.)
+constexpr int kHeadMaxK = 1024;   // x row held in registers: K/32 values per lane
+__global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__ x, int ldx,
                                                        const float* __restrict__ W, const float* __restrict__ b,
-                                                       float* __restrict__ out, int ldo, int rows, int K, int N2) {
+                                                       float* __restrict__ out, int ldo, int rows, int K, int N2,
+                                                       int w_in_smem) {
+  extern __shared__ float head_ws[];
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  if (w_in_smem) {
+    for (int i = threadIdx.x; i < N2 * K; i += blockDim.x) head_ws[i] = __ldg(W + i);
+    __syncthreads();
+  }
+  const float* Wp = w_in_smem ? head_ws : W;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
     const float* xr = x + (size_t)row * ldx;
+    float xv[kHeadMaxK / 32];
+#pragma unroll
+    for (int i = 0; i < kHeadMaxK / 32; ++i) xv[i] = (lane + 32 * i < K) ? xr[lane + 32 * i] : 0.f;
     for (int n = 0; n < N2; ++n) {
-      const float* wr = W + (size_t)n * K;
+      const float* wr = Wp + (size_t)n * K;
       float s = 0.f;
-      for (int k = lane; k < K; k += 32) s = fmaf(xr[k], __ldg(wr + k), s);
+#pragma unroll
+      for (int i = 0; i < kHeadMaxK / 32; ++i)
+        if (lane + 32 * i < K) s = fmaf(xv[i], wr[lane + 32 * i], s);
       s = warp_sum(s);
       if (lane == 0) out[(size_t)row * ldo + n] = s + (b ? b[n] : 0.f);
     }
   }
+}
+
+inline int launch_head_fwd(const float* x, int ldx, const float* W, const float* b, float* out, int ldo, int rows,
+                           int K, int N2, cudaStream_t st) {
+  if (K > kHeadMaxK) return fail(TA3N_ERR_UNSUPPORTED, "head_fwd: K=%d > %d", K, kHeadMaxK);
+  const size_t wbytes = (size_t)N2 * K * sizeof(float);
+  const int in_smem = wbytes <= 48 * 1024 ? 1 : 0;
+  size_t blocks = ((size_t)rows + 3) / 4;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks == 0) blocks = 1;
+  pre_launch("head_fwd", st);
+  head_fwd_kernel<<<(unsigned)blocks, 128, in_smem ? wbytes : 0, st>>>(x, ldx, W, b, out, ldo, rows, K, N2, in_smem);
+  return after_launch();
 }
 
 // ---- out[row,k] = alpha * (sum_n g[row,n] W[n,k]) * 1[gate[row,k] > 0]  (+ out if accumulate) ----
@@ -99,89 +128,80 @@ __global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restr
   }
 }
 
-// ---- relation heads + entropy attention + attentive pooling (warp per video) -------------------
+// ---- relation heads + entropy attention + attentive pooling (block per video, warp per relation) ---
 // models.py:479 (second Linear of each relation discriminator), :351-357, :379-388, :651-652
-__global__ void __launch_bounds__(256)
+constexpr int kRelWarps = 8;
+__global__ void __launch_bounds__(kRelWarps * 32)
 relattn_fwd_kernel(const float* __restrict__ feat_rel, const float* __restrict__ hidden, int M, int R, int H,
                    const __grid_constant__ PtrTable W2, const __grid_constant__ PtrTable b2, int use_attn,
                    float* __restrict__ pred_rel, float* __restrict__ attn, float* __restrict__ feat_video) {
-  __shared__ float wsh[8][kMaxScales];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int warps_per_block = blockDim.x >> 5;
-  for (int m = blockIdx.x * warps_per_block + wib; m < M; m += gridDim.x * warps_per_block) {
-    for (int i = 0; i < R; ++i) {
-      const float* hr = hidden + ((size_t)i * M + m) * H;
-      const float* w0 = W2.p[i];
-      const float* w1 = w0 + H;
-      float s0 = 0.f, s1 = 0.f;
-      for (int h = lane; h < H; h += 32) {
-        float hv = hr[h];
-        s0 = fmaf(hv, __ldg(w0 + h), s0);
-        s1 = fmaf(hv, __ldg(w1 + h), s1);
-      }
-      s0 = warp_sum(s0) + b2.p[i][0];
-      s1 = warp_sum(s1) + b2.p[i][1];
-      float w;
-      if (use_attn) {
-        w = attn_from_logits(s0, s1).w;
-      } else {
-        w = 0.f;   // plain sum:  (w + 1) == 1
-      }
-      if (lane == 0) {
-        pred_rel[((size_t)m * R + i) * 2 + 0] = s0;
-        pred_rel[((size_t)m * R + i) * 2 + 1] = s1;
-        attn[(size_t)m * R + i] = use_attn ? w : feat_rel[((size_t)m * R + i) * H];   // :647 placeholder
-        wsh[wib][i] = w + 1.0f;
-      }
-    }
-    __syncwarp();
+  __shared__ float wsh[kMaxScales];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int m = blockIdx.x;
+  for (int i = warp; i < R; i += nwarp) {
+    const float* hr = hidden + ((size_t)i * M + m) * H;
+    const float* w0 = W2.p[i];
+    const float* w1 = w0 + H;
+    float s0 = 0.f, s1 = 0.f;
     for (int h = lane; h < H; h += 32) {
-      float y = 0.f;
-      for (int i = 0; i < R; ++i) y = fmaf(wsh[wib][i], feat_rel[((size_t)m * R + i) * H + h], y);
-      feat_video[(size_t)m * H + h] = y;
+      const float hv = hr[h];
+      s0 = fmaf(hv, __ldg(w0 + h), s0);
+      s1 = fmaf(hv, __ldg(w1 + h), s1);
     }
-    __syncwarp();
+    s0 = warp_sum(s0) + b2.p[i][0];
+    s1 = warp_sum(s1) + b2.p[i][1];
+    const float w = use_attn ? attn_from_logits(s0, s1).w : 0.f;   // 'none': plain sum, (w + 1) == 1
+    if (lane == 0) {
+      pred_rel[((size_t)m * R + i) * 2 + 0] = s0;
+      pred_rel[((size_t)m * R + i) * 2 + 1] = s1;
+      attn[(size_t)m * R + i] = use_attn ? w : feat_rel[((size_t)m * R + i) * H];   // :647 placeholder
+      wsh[i] = w + 1.0f;
+    }
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float y = 0.f;
+    for (int i = 0; i < R; ++i) y = fmaf(wsh[i], feat_rel[((size_t)m * R + i) * H + h], y);
+    feat_video[(size_t)m * H + h] = y;
   }
 }
 
-// ---- backward of the above up to the hidden layer (warp per video) -----------------------------
+// ---- backward of the above up to the hidden layer (block per video, warp per relation) ----------
 //   dw_i   = <G[m], feat_rel[m,i]> + g_attn[m,i]
 //   Pt_ik  = g_pred[m,i,k] + dw_i * q_ik (log q_ik + E_i)
 //   dHid_i = (Pt_i0 W2_i[0,:] + Pt_i1 W2_i[1,:]) * 1[hidden_i > 0]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kRelWarps * 32)
 relattn_bwd_pre_kernel(const float* __restrict__ feat_rel, const float* __restrict__ hidden,
                        const float* __restrict__ pred_rel, const float* __restrict__ G,
                        const float* __restrict__ g_pred, const float* __restrict__ g_attn, int M, int R, int H,
                        const __grid_constant__ PtrTable W2, int use_attn, float* __restrict__ Pt,
                        float* __restrict__ d_hidden) {
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  for (int m = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M; m += gridDim.x * warps_per_block) {
-    for (int i = 0; i < R; ++i) {
-      float pt0 = g_pred ? g_pred[((size_t)m * R + i) * 2 + 0] : 0.f;
-      float pt1 = g_pred ? g_pred[((size_t)m * R + i) * 2 + 1] : 0.f;
-      if (use_attn) {
-        const float* fr = feat_rel + ((size_t)m * R + i) * H;
-        const float* gr = G + (size_t)m * H;
-        float dw = 0.f;
-        for (int h = lane; h < H; h += 32) dw = fmaf(gr[h], fr[h], dw);
-        dw = warp_sum(dw);
-        if (g_attn) dw += g_attn[(size_t)m * R + i];
-        Attn2 a = attn_from_logits(pred_rel[((size_t)m * R + i) * 2 + 0], pred_rel[((size_t)m * R + i) * 2 + 1]);
-        pt0 += dw * a.q0 * (a.lq0 + a.ent);
-        pt1 += dw * a.q1 * (a.lq1 + a.ent);
-      }
-      if (lane == 0) {
-        Pt[((size_t)m * R + i) * 2 + 0] = pt0;
-        Pt[((size_t)m * R + i) * 2 + 1] = pt1;
-      }
-      const float* w0 = W2.p[i];
-      const float* w1 = w0 + H;
-      const float* hr = hidden + ((size_t)i * M + m) * H;
-      float* dh = d_hidden + ((size_t)i * M + m) * H;
-      for (int h = lane; h < H; h += 32)
-        dh[h] = hr[h] > 0.f ? fmaf(pt0, __ldg(w0 + h), pt1 * __ldg(w1 + h)) : 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int m = blockIdx.x;
+  for (int i = warp; i < R; i += nwarp) {
+    float pt0 = g_pred ? g_pred[((size_t)m * R + i) * 2 + 0] : 0.f;
+    float pt1 = g_pred ? g_pred[((size_t)m * R + i) * 2 + 1] : 0.f;
+    if (use_attn) {
+      const float* fr = feat_rel + ((size_t)m * R + i) * H;
+      const float* gr = G + (size_t)m * H;
+      float dw = 0.f;
+      for (int h = lane; h < H; h += 32) dw = fmaf(gr[h], fr[h], dw);
+      dw = warp_sum(dw);
+      if (g_attn) dw += g_attn[(size_t)m * R + i];
+      const Attn2 a = attn_from_logits(pred_rel[((size_t)m * R + i) * 2 + 0], pred_rel[((size_t)m * R + i) * 2 + 1]);
+      pt0 += dw * a.q0 * (a.lq0 + a.ent);
+      pt1 += dw * a.q1 * (a.lq1 + a.ent);
     }
+    if (lane == 0) {
+      Pt[((size_t)m * R + i) * 2 + 0] = pt0;
+      Pt[((size_t)m * R + i) * 2 + 1] = pt1;
+    }
+    const float* w0 = W2.p[i];
+    const float* w1 = w0 + H;
+    const float* hr = hidden + ((size_t)i * M + m) * H;
+    float* dh = d_hidden + ((size_t)i * M + m) * H;
+    for (int h = lane; h < H; h += 32)
+      dh[h] = hr[h] > 0.f ? fmaf(pt0, __ldg(w0 + h), pt1 * __ldg(w1 + h)) : 0.f;
   }
 }
 

@@ -122,6 +122,71 @@ __device__ __forceinline__ float apply_epilogue(const Group& g, int m, int n, fl
   return epilogue_t<-1>(g, m, n, acc);
 }
 
+// 32 consecutive floats p[0..31] of one row -> registers; 16 B vector loads when possible
+__device__ __forceinline__ void load_row32(const float* p, int nvalid, float (&r)[32]) {
+  if (nvalid >= 32 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p + j);
+      r[j] = t.x;
+      r[j + 1] = t.y;
+      r[j + 2] = t.z;
+      r[j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = j < nvalid ? p[j] : 0.f;
+  }
+}
+
+// The same epilogue applied to a 32-column segment (m, nb..nb+31) held by one thread (tcgen05 engine: one
+// accumulator row per lane).  Auxiliary operands (bias, add, gate, C) are fetched as whole 128 B row pieces
+// with vector loads up front instead of one dependent scalar load per element.
+template <int F>
+__device__ __forceinline__ void epilogue_row32(const Group& g, int m, int nb, int nvalid, float (&v)[32]) {
+  const int f = (F >= 0) ? F : g.flags;
+  float aux[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
+  if (f & EPI_BIAS) {
+    load_row32(g.bias + nb, nvalid, aux);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += aux[j];
+  }
+  if (f & EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (f & EPI_DROP_MASK) {
+    const uint8_t* k = g.keep + (size_t)m * g.ldkeep + nb;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) v[j] = k[j] ? v[j] * g.drop_scale : 0.0f;
+  }
+  if (f & EPI_DROP_RNG) {
+    const uint64_t step = g.step_dev ? *g.step_dev : 0ull;
+    const uint64_t base = g.rng_offset + (uint64_t)m * (uint64_t)g.N + (uint64_t)nb;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = rng_keep(g.seed, step, base + j, g.drop_p) ? v[j] * g.drop_scale : 0.0f;
+  }
+  if (f & EPI_ADDROW) {
+    const float rs = g.rowscale ? g.rowscale[(size_t)m * g.rs_stride] + g.rs_bias : 1.0f;
+    load_row32(g.add + (size_t)m * g.ldadd + nb, nvalid, aux);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaf(rs, aux[j], v[j]);
+  }
+  if (f & EPI_GATE) {
+    load_row32(g.gate + (size_t)m * g.ldgate + nb, nvalid, aux);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = aux[j] > 0.0f ? v[j] : 0.0f;
+  }
+  if (f & EPI_ACCUM) {
+    load_row32(g.C + (size_t)m * g.ldc + nb, nvalid, aux);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += aux[j];
+  }
+}
+
 // Call `body(tag)` with tag = std::integral_constant<int, F> for the flag set of `flags`.
 #define TA3N_EPI_DISPATCH(flags, ...)                                              \
   switch (flags) {                                                                  \

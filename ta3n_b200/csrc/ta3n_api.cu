@@ -346,9 +346,7 @@ int ta3n_disc_fwd(const float* x, int rows, int K, int Kh, const float* W1, cons
   g.bias = b1;
   plan.add_seg(x, K, W1, K, K);
   return submit_fwd(plan, S(stream), [=](cudaStream_t st) -> int {
-    pre_launch("head_fwd", st);
-    head_fwd_kernel<<<blocks_for((size_t)rows * 32, 256), 256, 0, st>>>(hidden, Kh, W2, b2, logits, 2, rows, Kh, 2);
-    return after_launch();
+    return launch_head_fwd(hidden, Kh, W2, b2, logits, 2, rows, Kh, 2, st);
   });
 }
 
@@ -607,8 +605,9 @@ int ta3n_relattn_fwd(const float* feat_rel, int M, int R, int H, const float* co
   }
   TA3N_TRY(run_gemm(plan, S(stream)));
   pre_launch("relattn_fwd", S(stream));
-  relattn_fwd_kernel<<<blocks_for((size_t)M * 32, 256), 256, 0, S(stream)>>>(feat_rel, hidden, M, R, H, w2, b2,
-                                                                             use_attn, pred_rel, attn, feat_video);
+  const int rel_threads = 32 * (R < kRelWarps ? R : kRelWarps);
+  relattn_fwd_kernel<<<M, rel_threads, 0, S(stream)>>>(feat_rel, hidden, M, R, H, w2, b2, use_attn, pred_rel, attn,
+                                                       feat_video);
   return after_launch();
 }
 
@@ -647,7 +646,7 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
   memset(&w2, 0, sizeof(w2));
   for (int i = 0; i < R; ++i) w2.p[i] = W2_host[i];
   pre_launch("relattn_bwd_pre", st);
-  relattn_bwd_pre_kernel<<<blocks_for((size_t)M * 32, 256), 256, 0, st>>>(
+  relattn_bwd_pre_kernel<<<M, 32 * (R < kRelWarps ? R : kRelWarps), 0, st>>>(
       feat_rel, hidden, pred_rel, g_feat_video, g_pred_rel, g_attn, M, R, H, w2, use_attn, Pt, dHid);
   TA3N_TRY(after_launch());
 
@@ -714,9 +713,7 @@ int ta3n_video_head_fwd(const float* feat_video, int M, int H, int C, const floa
   pre_launch("video_drop_fwd", S(stream));
   video_drop_fwd_kernel<<<blocks_for((size_t)M * H, 256), 256, 0, S(stream)>>>(feat_video, dropped, (size_t)M * H, d);
   TA3N_TRY(after_launch());
-  pre_launch("head_fwd", S(stream));
-  head_fwd_kernel<<<blocks_for((size_t)M * 32, 256), 256, 0, S(stream)>>>(dropped, H, Wc, bc, pred, C, M, H, C);
-  return after_launch();
+  return launch_head_fwd(dropped, H, Wc, bc, pred, C, M, H, C, S(stream));
 }
 
 size_t ta3n_video_head_bwd_workspace_bytes(int M, int H, int C) {

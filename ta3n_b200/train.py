@@ -27,7 +27,7 @@ _P = TF._p
 class TrainStep:
     def __init__(self, model, batch_source: int, batch_target: int, beta: Sequence[float], gamma: float = 0.003,
                  place_adv: Sequence[str] = ("Y", "Y", "Y"), add_loss_DA: str = "attentive_entropy",
-                 use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False, overlap_wgrad: bool = True):
+                 use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False, overlap_wgrad: bool = False):
         if not model.training:
             raise ValueError("TrainStep needs model.train() (dropout state is fixed at construction)")
         self.model = model
