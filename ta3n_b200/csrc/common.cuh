@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -117,6 +118,40 @@ inline std::atomic<int>& gemm_engine() {
   return e;
 }
 
+// ---- kernel launch with programmatic dependent launch (PDL) ---------------------------------------
+// Every kernel starts with pdl_wait() (griddepcontrol.wait: the previous kernel in the stream has completed
+// and its writes are visible) after whatever set-up needs no device data, then allows ITS dependents to be
+// scheduled.  With the launch attribute below, kernel k+1's CTAs are placed on idle SMs and run their
+// prologue (parameter staging, barrier init, TMEM allocation) while kernel k is still computing -- the
+// step is a chain of ~26 short, mostly sub-wave kernels, so launch latency and prologues are on the
+// critical path.  TA3N_PDL=0 disables the attribute (the device-side instructions are then no-ops).
+inline bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("TA3N_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in after_launch()
+}
+
 // ---- workspace carving ----------------------------------------------------------------------
 struct Arena {
   char* base;
@@ -136,6 +171,12 @@ struct Arena {
 };
 
 // ---- device helpers -------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

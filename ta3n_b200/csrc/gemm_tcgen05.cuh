@@ -212,6 +212,9 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // Everything above touched only kernel parameters, shared memory and TMEM: it overlaps the previous
+  // kernel of the stream.  From here on operands produced by that kernel are read.
+  pdl_wait();
   if (dbg & 16) {                // debug: setup + teardown only
     __syncthreads();
     if (warp == 1 && !(dbg & 2)) tmem_dealloc(tmem_base, TC_TMEM_COLS);
@@ -428,7 +431,7 @@ inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSe
     return e ? atoi(e) : 0;
   }();
   pre_launch(label, stream);
-  seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES><<<tab.total_tiles, TC_THREADS, tc_smem_bytes(STAGES), stream>>>(
+  launch_kernel(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES>, tab.total_tiles, TC_THREADS, tc_smem_bytes(STAGES), stream, 
       tab, maps, sm, dbg);
   return after_launch();
 }
@@ -539,7 +542,7 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
       if (any_split) {
         dim3 grid(splitk_reduce_blocks(tab), ng);
         pre_launch("splitk_reduce", stream);
-        splitk_reduce_kernel<<<grid, 256, 0, stream>>>(tab);
+        launch_kernel(splitk_reduce_kernel, grid, 256, 0, stream, tab);
         TA3N_TRY(after_launch());
       }
     }

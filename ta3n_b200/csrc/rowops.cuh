@@ -33,6 +33,7 @@ inline unsigned blocks_for(size_t n, int threads) {
 // ---- feat_rel[m,i,:] = sum_r act[q(i,r)][m,:]                              TRNmodule.py:79 ----
 __global__ void __launch_bounds__(256) relsum_kernel(const float* __restrict__ act, float* __restrict__ feat_rel,
                                                      int M, int H, const __grid_constant__ RelMap map) {
+  pdl_wait();
   const int R = map.n_scales;
   const size_t total = (size_t)M * R * H;
   const size_t plane = (size_t)M * H;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(256) relsum_kernel(const float* __restrict__ a
 __global__ void __launch_bounds__(256) dz_kernel(const float* __restrict__ act, const float* __restrict__ d_feat_rel,
                                                  float* __restrict__ dz, int M, int H,
                                                  const __grid_constant__ RelMap map) {
+  pdl_wait();
   const int R = map.n_scales;
   const size_t plane = (size_t)M * H;
   const size_t total = plane * map.n_rel;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ W, const float* __restrict__ b,
                                                        float* __restrict__ out, int ldo, int rows, int K, int N2,
                                                        int w_in_smem) {
+  pdl_wait();
   extern __shared__ float head_ws[];
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
@@ -83,31 +86,40 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__
   const float* Wp = w_in_smem ? head_ws : W;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
     const float* xr = x + (size_t)row * ldx;
-    float xv[kHeadMaxK / 32];
+    if (K <= kHeadMaxK) {
+      float xv[kHeadMaxK / 32];
 #pragma unroll
-    for (int i = 0; i < kHeadMaxK / 32; ++i) xv[i] = (lane + 32 * i < K) ? xr[lane + 32 * i] : 0.f;
-    for (int n = 0; n < N2; ++n) {
-      const float* wr = Wp + (size_t)n * K;
-      float s = 0.f;
+      for (int i = 0; i < kHeadMaxK / 32; ++i) xv[i] = (lane + 32 * i < K) ? xr[lane + 32 * i] : 0.f;
+      for (int n = 0; n < N2; ++n) {
+        const float* wr = Wp + (size_t)n * K;
+        float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < kHeadMaxK / 32; ++i)
-        if (lane + 32 * i < K) s = fmaf(xv[i], wr[lane + 32 * i], s);
-      s = warp_sum(s);
-      if (lane == 0) out[(size_t)row * ldo + n] = s + (b ? b[n] : 0.f);
+        for (int i = 0; i < kHeadMaxK / 32; ++i)
+          if (lane + 32 * i < K) s = fmaf(xv[i], wr[lane + 32 * i], s);
+        s = warp_sum(s);
+        if (lane == 0) out[(size_t)row * ldo + n] = s + (b ? b[n] : 0.f);
+      }
+    } else {   // very wide rows (fc_dim >= 2048): stream x from L1/L2
+      for (int n = 0; n < N2; ++n) {
+        const float* wr = Wp + (size_t)n * K;
+        float s = 0.f;
+        for (int k = lane; k < K; k += 32) s = fmaf(xr[k], wr[k], s);
+        s = warp_sum(s);
+        if (lane == 0) out[(size_t)row * ldo + n] = s + (b ? b[n] : 0.f);
+      }
     }
   }
 }
 
 inline int launch_head_fwd(const float* x, int ldx, const float* W, const float* b, float* out, int ldo, int rows,
                            int K, int N2, cudaStream_t st) {
-  if (K > kHeadMaxK) return fail(TA3N_ERR_UNSUPPORTED, "head_fwd: K=%d > %d", K, kHeadMaxK);
   const size_t wbytes = (size_t)N2 * K * sizeof(float);
   const int in_smem = wbytes <= 48 * 1024 ? 1 : 0;
   size_t blocks = ((size_t)rows + 3) / 4;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks == 0) blocks = 1;
   pre_launch("head_fwd", st);
-  head_fwd_kernel<<<(unsigned)blocks, 128, in_smem ? wbytes : 0, st>>>(x, ldx, W, b, out, ldo, rows, K, N2, in_smem);
+  launch_kernel(head_fwd_kernel, (unsigned)blocks, 128, in_smem ? wbytes : 0, st, x, ldx, W, b, out, ldo, rows, K, N2, in_smem);
   return after_launch();
 }
 
@@ -116,6 +128,7 @@ __global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restr
                                                             const float* __restrict__ W,
                                                             const float* __restrict__ gate, float alpha,
                                                             int accumulate, float* __restrict__ out, int rows, int K) {
+  pdl_wait();
   const size_t total = (size_t)rows * K;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const size_t row = e / K;
@@ -135,6 +148,7 @@ __global__ void __launch_bounds__(kRelWarps * 32)
 relattn_fwd_kernel(const float* __restrict__ feat_rel, const float* __restrict__ hidden, int M, int R, int H,
                    const __grid_constant__ PtrTable W2, const __grid_constant__ PtrTable b2, int use_attn,
                    float* __restrict__ pred_rel, float* __restrict__ attn, float* __restrict__ feat_video) {
+  pdl_wait();
   __shared__ float wsh[kMaxScales];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int m = blockIdx.x;
@@ -176,6 +190,7 @@ relattn_bwd_pre_kernel(const float* __restrict__ feat_rel, const float* __restri
                        const float* __restrict__ g_pred, const float* __restrict__ g_attn, int M, int R, int H,
                        const __grid_constant__ PtrTable W2, int use_attn, float* __restrict__ Pt,
                        float* __restrict__ d_hidden) {
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int m = blockIdx.x;
   for (int i = warp; i < R; i += nwarp) {
@@ -208,6 +223,7 @@ relattn_bwd_pre_kernel(const float* __restrict__ feat_rel, const float* __restri
 // d_feat_rel[m,i,0] += g_attn[m,i]   (use_attn='none' placeholder output, models.py:647)
 __global__ void attn_placeholder_bwd_kernel(const float* __restrict__ g_attn, float* __restrict__ d_feat_rel,
                                             int M, int R, int H) {
+  pdl_wait();
   const int total = M * R;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x)
     d_feat_rel[(size_t)e * H] += g_attn[e];
@@ -217,6 +233,7 @@ __global__ void attn_placeholder_bwd_kernel(const float* __restrict__ g_attn, fl
 __global__ void __launch_bounds__(256) frame_attn_fwd_kernel(const float* __restrict__ feat,
                                                              const float* __restrict__ logits, int rows, int F,
                                                              float* __restrict__ out) {
+  pdl_wait();
   const size_t total = (size_t)rows * F;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const size_t row = e / F;
@@ -229,6 +246,7 @@ __global__ void __launch_bounds__(256) frame_attn_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) frame_attn_bwd_kernel(const float* __restrict__ feat,
                                                              const float* __restrict__ logits, int rows, int F,
                                                              float* __restrict__ d_out, float* __restrict__ g_logits) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
@@ -278,6 +296,7 @@ __device__ __forceinline__ float drop_factor(const DropArgs& a, size_t e) {
 // dropped = y * keep / (1-p)                                               models.py:679-680
 __global__ void __launch_bounds__(256) video_drop_fwd_kernel(const float* __restrict__ y, float* __restrict__ out,
                                                              size_t total, const DropArgs a) {
+  pdl_wait();
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
     out[e] = y[e] * drop_factor(a, e);
 }
@@ -287,6 +306,7 @@ __global__ void __launch_bounds__(256)
 video_head_bwd_kernel(const float* __restrict__ g_pred, int C, const float* __restrict__ Wc,
                       const float* __restrict__ extra, const float* __restrict__ g_ext, float grad_scale,
                       const DropArgs a, float* __restrict__ out, int M, int H) {
+  pdl_wait();
   const size_t total = (size_t)M * H;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const size_t m = e / H;
@@ -303,6 +323,7 @@ video_head_bwd_kernel(const float* __restrict__ g_pred, int C, const float* __re
 // d_pre = (d_feat + g_ext) * 1[feat > 0] * scale   (ReLU + dropout backward; feat>0 <=> kept & pre>0)
 __global__ void __launch_bounds__(256) dpre_kernel(const float* __restrict__ feat, float* __restrict__ d_feat,
                                                    const float* __restrict__ g_ext, float scale, size_t total) {
+  pdl_wait();
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     float g = d_feat[e] + (g_ext ? g_ext[e] : 0.f);
     d_feat[e] = feat[e] > 0.f ? g * scale : 0.f;
@@ -311,6 +332,7 @@ __global__ void __launch_bounds__(256) dpre_kernel(const float* __restrict__ fea
 
 __global__ void __launch_bounds__(256) grl_bwd_kernel(const float* __restrict__ g, float beta, float* __restrict__ out,
                                                       size_t n) {
+  pdl_wait();
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
     out[e] = -beta * g[e];
 }
@@ -328,6 +350,7 @@ loss_heads_kernel(const float* __restrict__ pred_video, const long long* __restr
                   const float* __restrict__ pred_frame, int Bs, int M, int T, int R, int C, float gamma, int flags,
                   float* __restrict__ g_video, float* __restrict__ g_rel, float* __restrict__ g_dom,
                   float* __restrict__ g_frame, float* __restrict__ row_loss) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int m = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M; m += gridDim.x * warps_per_block) {
@@ -414,6 +437,7 @@ loss_heads_kernel(const float* __restrict__ pred_video, const long long* __restr
 // deterministic sum of row_loss[0..M) -> out[0]  (single block, fixed tree)
 __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ row_loss, int M,
                                                            float* __restrict__ out) {
+  pdl_wait();
   __shared__ float red[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < M; i += blockDim.x) s += row_loss[i];
@@ -427,7 +451,8 @@ __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restri
   }
 }
 
-__global__ void counter_inc_kernel(unsigned long long* ctr) { ctr[0] += 1ull; }
+__global__ void counter_inc_kernel(unsigned long long* ctr) {
+  pdl_wait(); ctr[0] += 1ull; }
 
 // ---- deterministic (weighted) column sums: bias gradients and the skinny head weight gradients ----
 //   out[k*ldo + n] = sum_seg sum_r  P_seg[r*ldp + k] * X_seg[r*ld + n]      k < N2 <= 32, n < N
@@ -467,7 +492,25 @@ __device__ __forceinline__ void wcolsum_body(const WColsumJob& j, float (*red)[3
       const int rows = j.rows[sg];
       const int per = (rows + nsplit - 1) / nsplit;
       const int r1 = min(rows, (split + 1) * per);
-      for (int r = split * per + threadIdx.y; r < r1; r += 8) {
+      int r = split * per + threadIdx.y;
+      // four independent rows in flight per thread (the loads, not the adds, bound this kernel)
+      for (; r + 24 < r1; r += 32) {
+        const float x0 = X[(size_t)r * j.ld + n], x1 = X[(size_t)(r + 8) * j.ld + n];
+        const float x2 = X[(size_t)(r + 16) * j.ld + n], x3 = X[(size_t)(r + 24) * j.ld + n];
+        if (P == nullptr) {
+          acc[0] += (x0 + x1) + (x2 + x3);
+        } else {
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k)
+            if (k < j.N2) {
+              acc[k] = fmaf(__ldg(P + (size_t)r * j.ldp + k), x0, acc[k]);
+              acc[k] = fmaf(__ldg(P + (size_t)(r + 8) * j.ldp + k), x1, acc[k]);
+              acc[k] = fmaf(__ldg(P + (size_t)(r + 16) * j.ldp + k), x2, acc[k]);
+              acc[k] = fmaf(__ldg(P + (size_t)(r + 24) * j.ldp + k), x3, acc[k]);
+            }
+        }
+      }
+      for (; r < r1; r += 8) {
         const float x = X[(size_t)r * j.ld + n];
         if (P == nullptr) {
           acc[0] += x;
@@ -495,6 +538,7 @@ __device__ __forceinline__ void wcolsum_body(const WColsumJob& j, float (*red)[3
 }
 
 __global__ void __launch_bounds__(256) wcolsum_stage1_kernel(const __grid_constant__ WColsumTable tab) {
+  pdl_wait();
   __shared__ float red[8][33];
   __shared__ WColsumJob j;   // staged: run-time indexed kernel parameters are slow generic loads
   {
@@ -517,6 +561,7 @@ __global__ void __launch_bounds__(256) wcolsum_stage1_kernel(const __grid_consta
 
 // stage 2: out[k, n] = sum_split partial[split, k, n]; grid (blocks, n_jobs)
 __global__ void __launch_bounds__(256) wcolsum_stage2_kernel(const __grid_constant__ WColsumTable tab, int nsplit) {
+  pdl_wait();
   __shared__ WColsumJob j;
   {
     const int* src = reinterpret_cast<const int*>(&tab.job[blockIdx.y]);
@@ -590,11 +635,11 @@ struct ColsumPlan {
       if (tab.n_jobs == 0) continue;
       dim3 grid((maxN + 31) / 32, tab.n_jobs, kWColsumSplits), block(32, 8);
       pre_launch("wcolsum", stream);
-      wcolsum_stage1_kernel<<<grid, block, 0, stream>>>(tab);
+      launch_kernel(wcolsum_stage1_kernel, grid, block, 0, stream, tab);
       TA3N_TRY(after_launch());
       dim3 grid2((maxOut + 255) / 256, tab.n_jobs);
       pre_launch("wcolsum_reduce", stream);
-      wcolsum_stage2_kernel<<<grid2, 256, 0, stream>>>(tab, kWColsumSplits);
+      launch_kernel(wcolsum_stage2_kernel, grid2, 256, 0, stream, tab, kWColsumSplits);
       TA3N_TRY(after_launch());
     }
     return TA3N_OK;

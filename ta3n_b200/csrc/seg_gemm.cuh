@@ -320,6 +320,7 @@ seg_gemm_simt_kernel(const __grid_constant__ GemmTable tab) {
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
   load_tile_ctx(tab, tile, &ctx, nullptr, nullptr);
+  pdl_wait();   // parameters staged; operands of the previous kernel are read from here on
   const Group& g = ctx.g;
   int local = tile - g.tile_begin;
   const int per_split = g.tiles_m * g.tiles_n;
@@ -434,6 +435,7 @@ seg_gemm_simt_kernel(const __grid_constant__ GemmTable tab) {
 
 // deterministic split-K reduction + epilogue: one thread per output element of every group
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ GemmTable tab) {
+  pdl_wait();
   // blockIdx.y = group, blockIdx.x strides over the elements
   __shared__ Group g;
   {
@@ -557,18 +559,18 @@ inline int launch_simt(const GemmPlan& plan, cudaStream_t stream) {
     if (tiles > 0) {
       pre_launch(plan.label, stream);
       if (plan.a_kmaj && plan.b_kmaj)
-        seg_gemm_simt_kernel<true, true><<<tiles, SG_THREADS, 0, stream>>>(tab);
+        launch_kernel(seg_gemm_simt_kernel<true, true>, tiles, SG_THREADS, 0, stream, tab);
       else if (plan.a_kmaj && !plan.b_kmaj)
-        seg_gemm_simt_kernel<true, false><<<tiles, SG_THREADS, 0, stream>>>(tab);
+        launch_kernel(seg_gemm_simt_kernel<true, false>, tiles, SG_THREADS, 0, stream, tab);
       else if (!plan.a_kmaj && !plan.b_kmaj)
-        seg_gemm_simt_kernel<false, false><<<tiles, SG_THREADS, 0, stream>>>(tab);
+        launch_kernel(seg_gemm_simt_kernel<false, false>, tiles, SG_THREADS, 0, stream, tab);
       else
-        seg_gemm_simt_kernel<false, true><<<tiles, SG_THREADS, 0, stream>>>(tab);
+        launch_kernel(seg_gemm_simt_kernel<false, true>, tiles, SG_THREADS, 0, stream, tab);
       TA3N_TRY(after_launch());
       if (any_split) {
         dim3 grid(splitk_reduce_blocks(tab), ng);
         pre_launch("splitk_reduce", stream);
-        splitk_reduce_kernel<<<grid, 256, 0, stream>>>(tab);
+        launch_kernel(splitk_reduce_kernel, grid, 256, 0, stream, tab);
         TA3N_TRY(after_launch());
       }
     }

@@ -312,7 +312,7 @@ int ta3n_shared_fc_bwd(const float* x_src, int rows_src, const float* x_tgt, int
   }
   const size_t total = (size_t)rows * F;
   pre_launch("dpre", S(stream));
-  dpre_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(feat, dfeat, g_feat_ext, 1.0f / (1.0f - p), total);
+  launch_kernel(dpre_kernel, blocks_for(total, 256), 256, 0, S(stream), feat, dfeat, g_feat_ext, 1.0f / (1.0f - p), total);
   TA3N_TRY(after_launch());
 
   Arena arena(workspace, workspace_bytes);
@@ -377,7 +377,7 @@ int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, cons
 
   // dH = (g_logits W2) * 1[hidden > 0]
   pre_launch("head_bwd_data", st);
-  head_bwd_data_kernel<<<blocks_for((size_t)rows * Kh, 256), 256, 0, st>>>(g_logits, 2, W2, hidden, 1.0f, 0, dH,
+  launch_kernel(head_bwd_data_kernel, blocks_for((size_t)rows * Kh, 256), 256, 0, st, g_logits, 2, W2, hidden, 1.0f, 0, dH,
                                                                            rows, Kh);
   TA3N_TRY(after_launch());
 
@@ -418,7 +418,7 @@ int ta3n_grl_bwd(const float* g, float beta, float* out, size_t n, ta3n_stream_t
   if (n == 0) return TA3N_OK;
   TA3N_REQUIRE(g && out, "null pointer");
   pre_launch("grl_bwd", S(stream));
-  grl_bwd_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(g, beta, out, n);
+  launch_kernel(grl_bwd_kernel, blocks_for(n, 256), 256, 0, S(stream), g, beta, out, n);
   return after_launch();
 }
 
@@ -431,7 +431,7 @@ int ta3n_frame_attn_fwd(const float* feat, const float* logits, int rows, int F,
   if (rows == 0) return TA3N_OK;
   TA3N_REQUIRE(feat && logits && out, "null pointer");
   pre_launch("frame_attn_fwd", S(stream));
-  frame_attn_fwd_kernel<<<blocks_for((size_t)rows * F, 256), 256, 0, S(stream)>>>(feat, logits, rows, F, out);
+  launch_kernel(frame_attn_fwd_kernel, blocks_for((size_t)rows * F, 256), 256, 0, S(stream), feat, logits, rows, F, out);
   return after_launch();
 }
 
@@ -441,7 +441,7 @@ int ta3n_frame_attn_bwd(const float* feat, const float* logits, int rows, int F,
   if (rows == 0) return TA3N_OK;
   TA3N_REQUIRE(feat && logits && d_out && g_logits, "null pointer");
   pre_launch("frame_attn_bwd", S(stream));
-  frame_attn_bwd_kernel<<<blocks_for((size_t)rows * 32, 256), 256, 0, S(stream)>>>(feat, logits, rows, F, d_out,
+  launch_kernel(frame_attn_bwd_kernel, blocks_for((size_t)rows * 32, 256), 256, 0, S(stream), feat, logits, rows, F, d_out,
                                                                                    g_logits);
   return after_launch();
 }
@@ -476,7 +476,7 @@ int ta3n_trn_fwd(const float* x, int M, int F, int H, const ta3n_relation_table*
   const int R = L.R;
   return submit_fwd(plan, S(stream), [=](cudaStream_t st) -> int {
     pre_launch("relsum", st);
-    relsum_kernel<<<blocks_for((size_t)M * R * H, 256), 256, 0, st>>>(act, feat_rel, M, H, map);
+    launch_kernel(relsum_kernel, blocks_for((size_t)M * R * H, 256), 256, 0, st, act, feat_rel, M, H, map);
     return after_launch();
   });
 }
@@ -514,7 +514,7 @@ int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table*
 
   const RelMap map = make_relmap(L);
   pre_launch("dz", st);
-  dz_kernel<<<blocks_for(plane * L.n_rel, 256), 256, 0, st>>>(act, d_feat_rel, dz, M, H, map);
+  launch_kernel(dz_kernel, blocks_for(plane * L.n_rel, 256), 256, 0, st, act, d_feat_rel, dz, M, H, map);
   TA3N_TRY(after_launch());
 
   {  // wgrad: dW_i[:, jF:(j+1)F] = sum_r dz_{i,r}^T x[:, tau_{i,r}[j], :]
@@ -606,7 +606,7 @@ int ta3n_relattn_fwd(const float* feat_rel, int M, int R, int H, const float* co
   TA3N_TRY(run_gemm(plan, S(stream)));
   pre_launch("relattn_fwd", S(stream));
   const int rel_threads = 32 * (R < kRelWarps ? R : kRelWarps);
-  relattn_fwd_kernel<<<M, rel_threads, 0, S(stream)>>>(feat_rel, hidden, M, R, H, w2, b2, use_attn, pred_rel, attn,
+  launch_kernel(relattn_fwd_kernel, M, rel_threads, 0, S(stream), feat_rel, hidden, M, R, H, w2, b2, use_attn, pred_rel, attn,
                                                        feat_video);
   return after_launch();
 }
@@ -646,7 +646,7 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
   memset(&w2, 0, sizeof(w2));
   for (int i = 0; i < R; ++i) w2.p[i] = W2_host[i];
   pre_launch("relattn_bwd_pre", st);
-  relattn_bwd_pre_kernel<<<M, 32 * (R < kRelWarps ? R : kRelWarps), 0, st>>>(
+  launch_kernel(relattn_bwd_pre_kernel, M, 32 * (R < kRelWarps ? R : kRelWarps), 0, st, 
       feat_rel, hidden, pred_rel, g_feat_video, g_pred_rel, g_attn, M, R, H, w2, use_attn, Pt, dHid);
   TA3N_TRY(after_launch());
 
@@ -695,7 +695,7 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
   }
   if (!use_attn && g_attn) {
     pre_launch("attn_placeholder_bwd", st);
-    attn_placeholder_bwd_kernel<<<blocks_for((size_t)M * R, 256), 256, 0, st>>>(g_attn, d_feat_rel, M, R, H);
+    launch_kernel(attn_placeholder_bwd_kernel, blocks_for((size_t)M * R, 256), 256, 0, st, g_attn, d_feat_rel, M, R, H);
     TA3N_TRY(after_launch());
   }
   return TA3N_OK;
@@ -711,7 +711,7 @@ int ta3n_video_head_fwd(const float* feat_video, int M, int H, int C, const floa
   TA3N_REQUIRE(feat_video && Wc && bc && dropped && pred, "null pointer");
   const DropArgs d = make_drop(drop);
   pre_launch("video_drop_fwd", S(stream));
-  video_drop_fwd_kernel<<<blocks_for((size_t)M * H, 256), 256, 0, S(stream)>>>(feat_video, dropped, (size_t)M * H, d);
+  launch_kernel(video_drop_fwd_kernel, blocks_for((size_t)M * H, 256), 256, 0, S(stream), feat_video, dropped, (size_t)M * H, d);
   TA3N_TRY(after_launch());
   return launch_head_fwd(dropped, H, Wc, bc, pred, C, M, H, C, S(stream));
 }
@@ -736,7 +736,7 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
   TA3N_REQUIRE(dropped && Wc && d_feat_video, "null pointer");
   const DropArgs d = make_drop(drop);
   pre_launch("video_head_bwd", st);
-  video_head_bwd_kernel<<<blocks_for((size_t)M * H, 256), 256, 0, st>>>(g_pred, C, Wc, d_dropped_extra,
+  launch_kernel(video_head_bwd_kernel, blocks_for((size_t)M * H, 256), 256, 0, st, g_pred, C, Wc, d_dropped_extra,
                                                                          g_feat_video_ext, grad_scale, d,
                                                                          d_feat_video, M, H);
   TA3N_TRY(after_launch());
@@ -784,19 +784,19 @@ int ta3n_loss_fwd_bwd(const float* pred_video, const long long* labels, const fl
   float* row_loss = arena.floats(M);
   if (!row_loss) return fail(TA3N_ERR_WORKSPACE, "ta3n_loss_fwd_bwd: workspace too small (%zu bytes)", workspace_bytes);
   pre_launch("loss_heads", S(stream));
-  loss_heads_kernel<<<blocks_for((size_t)M * 32, 256), 256, 0, S(stream)>>>(
+  launch_kernel(loss_heads_kernel, blocks_for((size_t)M * 32, 256), 256, 0, S(stream), 
       pred_video, labels, pred_rel, pred_dom_video, pred_frame, Bs, M, T, R, C, gamma, flags, g_pred_video,
       g_pred_rel, g_pred_dom_video, g_pred_frame, row_loss);
   TA3N_TRY(after_launch());
   pre_launch("loss_reduce", S(stream));
-  loss_reduce_kernel<<<1, 1024, 0, S(stream)>>>(row_loss, M, loss);
+  launch_kernel(loss_reduce_kernel, 1, 1024, 0, S(stream), row_loss, M, loss);
   return after_launch();
 }
 
 int ta3n_counter_inc(uint64_t* counter, ta3n_stream_t stream) {
   TA3N_REQUIRE(counter != nullptr, "null counter");
   pre_launch("counter_inc", S(stream));
-  counter_inc_kernel<<<1, 1, 0, S(stream)>>>(reinterpret_cast<unsigned long long*>(counter));
+  launch_kernel(counter_inc_kernel, 1, 1, 0, S(stream), reinterpret_cast<unsigned long long*>(counter));
   return after_launch();
 }
 

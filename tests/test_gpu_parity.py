@@ -489,3 +489,26 @@ def test_prefetched_inputs_give_the_same_step():
     for a, b in zip(got, want):
         assert torch.equal(a, b)
     assert not torch.equal(want[0], want[1])
+
+
+def test_config3_t9_frame_attention_full_size(engine):
+    """BASELINE config 3: B=128, T=9 (scales 9..2, 22 relations, 114 frame slots), use_attn_frame='TransAttn'.
+    Forward vs the oracle at full size; the fused TrainStep loss equals the autograd-API loss."""
+    from ta3n_b200.loss import ta3n_loss
+    from ta3n_b200.train import TrainStep
+    cfg = orc.PathConfig(num_class=12, num_segments=9, fc_dim=512, dropout_i=0.0, dropout_v=0.0,
+                         use_attn="TransAttn", use_attn_frame="TransAttn")
+    params = orc.init_params(cfg, seed=1234)
+    xs, xt, labels = orc.synthetic_batch(128, cfg)
+    model = build_model(cfg, params, train=True)
+    outs = model(xs.to(_dev()), xt.to(_dev()), [0.75, 0.75, 0.5], 0, True, False)
+    loss_api = ta3n_loss(outs, labels.to(_dev()), 0.003)
+    with torch.no_grad():
+        ref = orc.forward(params, xs, xt, [0.75, 0.75, 0.5], 0.0, cfg, train=True)
+    for i, (a, b) in enumerate(zip(flat_outputs(outs), flat_outputs(ref))):
+        assert a.shape == b.shape
+        assert_close(a, b, TOL[engine], f"cfg3 output {i}")
+    step = TrainStep(model, 128, 128, (0.75, 0.75, 0.5), gamma=0.003, use_graph=True)
+    loss_fused = step(xs, xt, labels)
+    torch.cuda.synchronize()
+    assert_close(loss_fused[0], loss_api, 1e-5 if engine == "fp32" else TOL_PATH, "cfg3 fused loss")
