@@ -134,11 +134,12 @@ int ta3n_trn_fwd(const float* x, int M, int F, int H, const ta3n_relation_table*
                  const float* const* W_host, const float* const* b_host, int relu_input,
                  float* act, float* feat_rel, ta3n_stream_t stream);
 size_t ta3n_trn_bwd_workspace_bytes(int M, int F, int H, const ta3n_relation_table* tab);
-/* d_feat_rel [M,R,H] -> dW_host[i] [H, s_i F], db_host[i] [H], dx [M,T,F] (dx may be NULL) */
+/* d_feat_rel [M,R,H] -> dW_host[i] [H, s_i F], db_host[i] [H], dx [M,T,F] (dx may be NULL);
+ * accumulate_dx != 0: dx += ... (lets an independent branch, e.g. the frame discriminator, write dx first) */
 int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table* tab,
                  const float* const* W_host, int relu_input, const float* act,
                  const float* d_feat_rel, float* const* dW_host, float* const* db_host, float* dx,
-                 void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
+                 int accumulate_dx, void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
 
 /* ---- relation discriminators + domain attention + pooling -------------------------- */
 /* models.py:472-488 (per-relation GRL + MLP), :351-357 (entropy attention), :379-388

@@ -51,7 +51,7 @@ SIGNATURES = {
     "ta3n_frame_attn_bwd": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
     "ta3n_trn_fwd": (_I, [_VP, _I, _I, _I, _TAB, _PP, _PP, _I, _VP, _VP, _VP]),
     "ta3n_trn_bwd_workspace_bytes": (_SZ, [_I, _I, _I, _TAB]),
-    "ta3n_trn_bwd": (_I, [_VP, _I, _I, _I, _TAB, _PP, _I, _VP, _VP, _PP, _PP, _VP, _VP, _SZ, _VP]),
+    "ta3n_trn_bwd": (_I, [_VP, _I, _I, _I, _TAB, _PP, _I, _VP, _VP, _PP, _PP, _VP, _I, _VP, _SZ, _VP]),
     "ta3n_relattn_fwd": (_I, [_VP, _I, _I, _I, _PP, _PP, _PP, _PP, _I, _VP, _VP, _VP, _VP, _VP]),
     "ta3n_relattn_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ta3n_relattn_bwd": (_I, [_VP, _I, _I, _I, _PP, _PP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP,

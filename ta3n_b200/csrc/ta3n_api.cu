@@ -491,7 +491,7 @@ size_t ta3n_trn_bwd_workspace_bytes(int M, int F, int H, const ta3n_relation_tab
 
 int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table* tab,
                  const float* const* W_host, int relu_input, const float* act, const float* d_feat_rel,
-                 float* const* dW_host, float* const* db_host, float* dx, void* workspace,
+                 float* const* dW_host, float* const* db_host, float* dx, int accumulate_dx, void* workspace,
                  size_t workspace_bytes, ta3n_stream_t stream) {
   RelLayout L;
   TA3N_TRY(parse_table(tab, &L));
@@ -565,14 +565,16 @@ int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table*
         g.gate = x + (size_t)t * F;
         g.ldgate = ldx;
       }
+      if (accumulate_dx) g.flags |= EPI_ACCUM;
       for (int q = 0; q < L.n_rel; ++q) {
         const int i = L.rel_scale[q], s = L.scale_size[i];
         for (int j = 0; j < s; ++j)
           if (L.frames[L.slot_begin[q] + j] == t) plan.add_seg(dz + q * plane, H, W_host[i] + (size_t)j * F, s * F, H);
       }
     }
-    for (int t : untouched)   // frames no relation reads get a zero gradient
-      TA3N_CUDA(cudaMemset2DAsync(dx + (size_t)t * F, sizeof(float) * ldx, 0, sizeof(float) * F, M, st));
+    if (!accumulate_dx)
+      for (int t : untouched)   // frames no relation reads get a zero gradient
+        TA3N_CUDA(cudaMemset2DAsync(dx + (size_t)t * F, sizeof(float) * ldx, 0, sizeof(float) * F, M, st));
     TA3N_TRY(run_gemm(plan, st));
   }
   return TA3N_OK;

@@ -144,7 +144,7 @@ class _TRNFunction(torch.autograd.Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         ws = _ws(lib.ta3n_trn_bwd_workspace_bytes(M, F, H, rs.ref), x)
         check(lib.ta3n_trn_bwd(_p(x), M, F, H, rs.ref, ptr_array([_p(w) for w in Ws]), int(relu_input), _p(act),
-                               _p(g), ptr_array([_p(t) for t in dWs]), ptr_array([_p(t) for t in dbs]), _p(dx),
+                               _p(g), ptr_array([_p(t) for t in dWs]), ptr_array([_p(t) for t in dbs]), _p(dx), 0,
                                _p(ws), ws.numel(), _stream()))
         return (dx, None, *dWs, *dbs)
 
@@ -290,13 +290,18 @@ def path_forward(spec: PathSpec, xs, xt, params, bufs: Buffers, batch_gemms: boo
     return saved, outputs, (Bs, Bt, D, T, F, H, Cn)
 
 
-def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: Buffers, stage_done=None):
+def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: Buffers, stage_done=None,
+                  side_stream=None):
     """The backward C calls in their fixed order.  ``gin``: dict of incoming output gradients
     (feat, pred_frame, attn, pred_rel, feat_video, pred_video, pred_dom_video; missing/None = zero).
     ``gout``: list of tensors (same order as ``params``) that receive the parameter gradients.
     ``stage_done(name)`` (optional) is called after each module's calls ('video', 'relation', 'trn',
-    'frame', 'shared') -- TrainStep uses it to issue the deferred weight-gradient work on a second stream."""
+    'frame', 'shared') -- TrainStep uses it to issue the deferred weight-gradient work on a second stream.
+    ``side_stream`` (optional, no frame attention): the frame-discriminator backward depends only on the loss
+    and on forward activations, so it runs on that stream concurrently with the video -> relation chain and
+    WRITES d_feat; the TRN dgrad then accumulates into it."""
     stage_done = stage_done or (lambda name: None)
+    frame_parallel = side_stream is not None and not spec.use_attn_frame
     lib = _lib.load()
     st = _stream()
     Bs, Bt, D, T, F, H, Cn = dims
@@ -312,6 +317,26 @@ def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: 
     feat, hid_f, pred_frame, feat_in = saved["feat"], saved["hid_f"], saved["pred_frame"], saved["feat_in"]
     act, feat_rel, hid_r, pred_rel = saved["act"], saved["feat_rel"], saved["hid_r"], saved["pred_rel"]
     attn, dropped, hid_v = saved["attn"], saved["dropped"], saved["hid_v"]
+    d_feat = new("d_feat", M * T, F)
+    g_pf = g("pred_frame")
+    if g_pf is not None:
+        g_pf = g_pf.reshape(M * T, 2)
+
+    def frame_disc_bwd(stream_handle, accumulate):
+        ws_f = wsp("disc_f", lib.ta3n_disc_bwd_workspace_bytes(M * T, F, F))
+        check(lib.ta3n_disc_bwd(_p(feat), M * T, F, F, _p(w1f), _p(w2f), _p(hid_f), _p(g_pf),
+                                float(spec.beta[2]), _p(d_feat), accumulate, _p(dw1f), _p(db1f), _p(dw2f), _p(db2f),
+                                _p(ws_f), ws_f.numel(), stream_handle))
+
+    frame_done = None
+    if frame_parallel:
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side_stream.wait_event(fork)
+        frame_disc_bwd(side_stream.cuda_stream, 0)          # d_feat = -beta2 * dgrad   (store)
+        frame_done = torch.cuda.Event()
+        frame_done.record(side_stream)
 
     # 6'. video discriminator: d_dropped = -beta1 * dgrad
     d_dropped = new("d_dropped", M, H)
@@ -337,16 +362,15 @@ def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: 
                                ptr_array([_p(t) for t in dr_b2]), _p(ws), ws.numel(), st))
     stage_done("relation")
     # 3'. TRN
-    d_feat = new("d_feat", M * T, F)
+    if frame_done is not None:
+        torch.cuda.current_stream().wait_event(frame_done)  # join: d_feat holds the frame-branch gradient
     ws = wsp("trn", lib.ta3n_trn_bwd_workspace_bytes(M, F, H, rs.ref))
     check(lib.ta3n_trn_bwd(_p(feat_in), M, F, H, rs.ref, ptr_array([_p(w) for w in trn_w]), 0, _p(act),
                            _p(d_feat_rel), ptr_array([_p(t) for t in dtrn_w]),
-                           ptr_array([_p(t) for t in dtrn_b]), _p(d_feat), _p(ws), ws.numel(), st))
+                           ptr_array([_p(t) for t in dtrn_b]), _p(d_feat), 1 if frame_parallel else 0,
+                           _p(ws), ws.numel(), st))
     stage_done("trn")
     # 2b'. frame attention (needs a writable copy of the frame-logit gradient)
-    g_pf = g("pred_frame")
-    if g_pf is not None:
-        g_pf = g_pf.reshape(M * T, 2)
     if spec.use_attn_frame:
         acc = new("g_pf_acc", M * T, 2)
         if g_pf is not None:
@@ -355,11 +379,9 @@ def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: 
             acc.zero_()
         g_pf = acc
         check(lib.ta3n_frame_attn_bwd(_p(feat), _p(pred_frame), M * T, F, _p(d_feat), _p(g_pf), st))
-    # 2'. frame discriminator: d_feat += -beta2 * dgrad
-    ws = wsp("disc_f", lib.ta3n_disc_bwd_workspace_bytes(M * T, F, F))
-    check(lib.ta3n_disc_bwd(_p(feat), M * T, F, F, _p(w1f), _p(w2f), _p(hid_f), _p(g_pf),
-                            float(spec.beta[2]), _p(d_feat), 1, _p(dw1f), _p(db1f), _p(dw2f), _p(db2f),
-                            _p(ws), ws.numel(), st))
+    # 2'. frame discriminator: d_feat += -beta2 * dgrad   (unless it already ran as the parallel branch)
+    if not frame_parallel:
+        frame_disc_bwd(st, 1)
     stage_done("frame")
     # 1'. shared layer (wgrad only; the input features carry no gradient)
     ws = wsp("shared", lib.ta3n_shared_fc_bwd_workspace_bytes(M * T, D, F))

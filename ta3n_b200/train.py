@@ -27,7 +27,8 @@ _P = TF._p
 class TrainStep:
     def __init__(self, model, batch_source: int, batch_target: int, beta: Sequence[float], gamma: float = 0.003,
                  place_adv: Sequence[str] = ("Y", "Y", "Y"), add_loss_DA: str = "attentive_entropy",
-                 use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False, overlap_wgrad: bool = False):
+                 use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False, overlap_wgrad: bool = False,
+                 parallel_branches: bool = True):
         if not model.training:
             raise ValueError("TrainStep needs model.train() (dropout state is fixed at construction)")
         self.model = model
@@ -87,6 +88,7 @@ class TrainStep:
             drop_i=TF.DropSpec(p=di, seed=seed, step=self.step_counter) if di > 0 else TF.DropSpec(),
             drop_v=TF.DropSpec(p=dv, seed=seed ^ 0x9E3779B9, step=self.step_counter) if dv > 0 else TF.DropSpec())
         self.outputs = None
+        self.branch_stream = torch.cuda.Stream(device=dev) if parallel_branches else None
         self.overlap_wgrad = bool(overlap_wgrad)
         self.side_stream = torch.cuda.Stream(device=dev) if self.overlap_wgrad else None
         self.launches_per_step = 0               # kernels of libta3n_sm100.so per step (counted at capture)
@@ -138,7 +140,7 @@ class TrainStep:
 
         check(lib.ta3n_wgrad_defer_begin())
         TF.path_backward(self.spec, dims, self.xs, self.xt, self.params, saved, gin, self.grad_views, self.bufs,
-                         stage_done=stage_done)
+                         stage_done=stage_done, side_stream=self.branch_stream)
         if self.overlap_wgrad:
             main.wait_stream(side)            # join
 
