@@ -25,10 +25,15 @@ _P = TF._p
 
 
 class TrainStep:
+    """Options ``overlap_wgrad`` / ``parallel_branches`` put independent parts of the backward on forked streams
+    inside the captured graph.  Measured on B200 (tools/concurrency_probe.py): forked sub-wave tcgen05 GEMM nodes
+    of one graph do not overlap (49.9 us forked vs 50.4 us sequential for two 80-tile launches), so both are off
+    by default; they stay available and tested for correctness."""
+
     def __init__(self, model, batch_source: int, batch_target: int, beta: Sequence[float], gamma: float = 0.003,
                  place_adv: Sequence[str] = ("Y", "Y", "Y"), add_loss_DA: str = "attentive_entropy",
                  use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False, overlap_wgrad: bool = False,
-                 parallel_branches: bool = True):
+                 parallel_branches: bool = False):
         if not model.training:
             raise ValueError("TrainStep needs model.train() (dropout state is fixed at construction)")
         self.model = model

@@ -446,6 +446,23 @@ def test_fused_train_step_matches_oracle(T, attn_frame, bs, bt, C, use_graph, en
     assert model.fc_feature_source.weight.grad is None       # off-path parameters stay untouched
 
 
+def test_fused_step_stream_options_do_not_change_results():
+    """overlap_wgrad / parallel_branches only re-order independent work across forked streams."""
+    from ta3n_b200.train import TrainStep
+    cfg = orc.PathConfig(num_class=12, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0)
+    params = orc.init_params(cfg, seed=1234)
+    model = build_model(cfg, params, train=True)
+    xs, xt, labels = orc.synthetic_batch(40, cfg)
+    base = TrainStep(model, 40, 40, (0.75, 0.75, 0.5), use_graph=True)
+    l0 = base(xs, xt, labels).clone()
+    g0 = base.flat_grad.clone()
+    alt = TrainStep(model, 40, 40, (0.75, 0.75, 0.5), use_graph=True, overlap_wgrad=True, parallel_branches=True)
+    l1 = alt(xs, xt, labels).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(l0, l1)
+    assert_close(alt.flat_grad, g0, 1e-6, "gradients with forked streams")
+
+
 def test_fused_step_dropout_changes_every_replay():
     from ta3n_b200.train import TrainStep
     cfg = orc.PathConfig(num_class=12, num_segments=5, fc_dim=512, dropout_i=0.5, dropout_v=0.5)
