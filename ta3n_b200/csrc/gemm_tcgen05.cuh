@@ -31,7 +31,10 @@
 
 namespace ta3n {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
+// warps 0,1 = TMA / MMA; then 4 epilogue warps (3-stage variant: two CTAs share an SM's registers) or 8
+// (6-stage variant, one CTA per SM: two warps per TMEM lane quarter, each finishing half of the columns)
+__host__ __device__ constexpr int tc_threads(int stages) { return stages <= 3 ? 192 : 320; }
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 16 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
@@ -82,6 +85,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
@@ -162,7 +172,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(bool a_kmaj, bool b_kmaj,
 
 // ---- the kernel -------------------------------------------------------------------------------------
 template <bool A_KMAJ, bool B_KMAJ, int TC_STAGES>
-__global__ void __launch_bounds__(TC_THREADS, TC_STAGES <= 3 ? 2 : 1)
+__global__ void __launch_bounds__(tc_threads(TC_STAGES), TC_STAGES <= 3 ? 2 : 1)
 seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant__ TcMaps maps,
                    const __grid_constant__ TcSegMaps segmaps, const int dbg) {
   extern __shared__ uint8_t tc_smem_raw[];
@@ -246,14 +256,21 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
         uint8_t* sB = sA + TC_A_BYTES;
         const CUtensorMap* ma = &maps.m[ctx.seg[seg].amap];
         const CUtensorMap* mb = &maps.m[ctx.seg[seg].bmap];
+        // MN-major tiles are four [32 k-rows][32 floats] slabs, one per group of 32 m (or n).  When the operand's
+        // MN extent is a multiple of 32 a rank-3 tensor map {32 floats, k rows, groups of 32} fetches all four with
+        // ONE instruction (the lone producer thread is issue-bound: ~50 cycles per TMA, 8 per chunk otherwise).
         if (A_KMAJ) {
           tma_load_2d(sA, ma, &full_bar[stage], k0, m0);
+        } else if (tab.pad_ & 1) {
+          tma_load_3d(sA, ma, &full_bar[stage], 0, k0, m0 >> 5);
         } else {
 #pragma unroll
           for (int q = 0; q < TC_BM / 32; ++q) tma_load_2d(sA + q * 4096, ma, &full_bar[stage], m0 + 32 * q, k0);
         }
         if (B_KMAJ) {
           tma_load_2d(sB, mb, &full_bar[stage], k0, n0);
+        } else if (tab.pad_ & 2) {
+          tma_load_3d(sB, mb, &full_bar[stage], 0, k0, n0 >> 5);
         } else {
 #pragma unroll
           for (int q = 0; q < TC_BN / 32; ++q) tma_load_2d(sB + q * 4096, mb, &full_bar[stage], n0 + 32 * q, k0);
@@ -300,8 +317,11 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
       mbar_wait(&tmem_full_bar, 0);
       tc_fence_after();
     }
+    constexpr int kEpiWarps = tc_threads(TC_STAGES) / 32 - 2;
+    constexpr int kColChunks = (TC_BN / 32) * 4 / kEpiWarps;      // column chunks of 32 per warp: 4 or 2
+    const int c0 = ((warp - 2) / 4) * kColChunks;
 #pragma unroll 1
-    for (int c = 0; c < TC_BN / 32; ++c) {
+    for (int c = c0; c < c0 + kColChunks; ++c) {
       float v[32];
       if (n_iter > 0 && !(dbg & 128)) {
         tmem_ld_32x32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(c * 32), v);
@@ -362,9 +382,10 @@ struct MapKey {
   long inner, outer, ld;
   int box_inner, box_outer;
   int atom32;   // 1: SWIZZLE_128B_ATOM_32B (MN-major operands), 0: SWIZZLE_128B
+  int rank3;    // 1: MN-major operand as {32 floats, outer rows, inner/32 groups}, box {32, box_outer, 4}
   bool operator<(const MapKey& o) const {
-    return std::tie(ptr, inner, outer, ld, box_inner, box_outer, atom32) <
-           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer, o.atom32);
+    return std::tie(ptr, inner, outer, ld, box_inner, box_outer, atom32, rank3) <
+           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer, o.atom32, o.rank3);
   }
 };
 
@@ -378,10 +399,14 @@ inline int encode_map(const MapKey& k, CUtensorMap* out) {
   }
   PFN_encodeTiled fn = encode_fn();
   if (!fn) return fail(TA3N_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {(cuuint64_t)k.inner, (cuuint64_t)k.outer};
-  cuuint64_t strides[1] = {(cuuint64_t)k.ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)k.box_inner, (cuuint32_t)k.box_outer};
-  cuuint32_t estr[2] = {1, 1};
+  cuuint64_t dims[3] = {(cuuint64_t)k.inner, (cuuint64_t)k.outer, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)k.ld * sizeof(float), 128};
+  cuuint32_t box[3] = {(cuuint32_t)k.box_inner, (cuuint32_t)k.box_outer, 4};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (k.rank3) {
+    dims[0] = 32;
+    dims[2] = (cuuint64_t)(k.inner / 32);
+  }
   // TFLOAT32: the TMA unit rounds fp32 -> tf32 (round to nearest) while filling shared memory, so the
   // tensor core never sees the truncation bias (-2^-11 relative per operand) it would apply to raw fp32
   // bit patterns.  TA3N_TMA_RAW_FP32=1 switches to the raw copy (kept to measure the difference).
@@ -389,7 +414,7 @@ inline int encode_map(const MapKey& k, CUtensorMap* out) {
     const char* e = getenv("TA3N_TMA_RAW_FP32");
     return e && e[0] == '1';
   }();
-  CUresult r = fn(out, raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
+  CUresult r = fn(out, raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, k.rank3 ? 3 : 2,
                   const_cast<void*>(k.ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   k.atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -431,7 +456,7 @@ inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSe
     return e ? atoi(e) : 0;
   }();
   pre_launch(label, stream);
-  launch_kernel(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES>, tab.total_tiles, TC_THREADS, tc_smem_bytes(STAGES), stream, 
+  launch_kernel(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES>, tab.total_tiles, tc_threads(STAGES), tc_smem_bytes(STAGES), stream, 
       tab, maps, sm, dbg);
   return after_launch();
 }
@@ -475,6 +500,16 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
            plan_in.k_total(plan_in.groups[b]) / plan_in.groups[b].ksplit;
   });
   const GemmPlan plan = sub_plan(plan_in, order);
+  // rank-3 maps for MN-major operands whose MN extent is a multiple of 32 in every group of the plan
+  static const bool allow3d = []() {
+    const char* e = getenv("TA3N_TMA_3D");
+    return !(e && e[0] == '0');
+  }();
+  bool a3d = !plan.a_kmaj && allow3d, b3d = !plan.b_kmaj && allow3d;
+  for (const Group& g : plan.groups) {
+    if (g.M % 32 != 0) a3d = false;
+    if (g.N % 32 != 0) b3d = false;
+  }
   size_t gi = 0;
   while (gi < plan.groups.size()) {
     GemmTable tab;
@@ -494,10 +529,10 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
       std::map<MapKey, int> trial = local;
       for (int i = 0; i < src.seg_count; ++i) {
         const Seg& s = plan.segs[src.seg_begin + i];
-        MapKey ka = plan.a_kmaj ? MapKey{s.A, s.len, src.M, s.lda, TC_BK, TC_BM, 0}
-                                : MapKey{s.A, src.M, s.len, s.lda, 32, TC_BK, 1};
-        MapKey kb = plan.b_kmaj ? MapKey{s.B, s.len, src.N, s.ldb, TC_BK, TC_BN, 0}
-                                : MapKey{s.B, src.N, s.len, s.ldb, 32, TC_BK, 1};
+        MapKey ka = plan.a_kmaj ? MapKey{s.A, s.len, src.M, s.lda, TC_BK, TC_BM, 0, 0}
+                                : MapKey{s.A, src.M, s.len, s.lda, 32, TC_BK, 1, a3d ? 1 : 0};
+        MapKey kb = plan.b_kmaj ? MapKey{s.B, s.len, src.N, s.ldb, TC_BK, TC_BN, 0, 0}
+                                : MapKey{s.B, src.N, s.len, s.ldb, 32, TC_BK, 1, b3d ? 1 : 0};
         for (const MapKey& k : {ka, kb})
           if (!trial.count(k)) trial[k] = nmaps + fresh++;
         keys.push_back({ka, kb});
@@ -530,6 +565,7 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
     }
     tab.n_groups = ng;
     tab.total_tiles = tiles;
+    tab.pad_ = (a3d ? 1 : 0) | (b3d ? 2 : 0);
     if (tiles > 0) {
       if (plan.a_kmaj && plan.b_kmaj)
         TA3N_TRY((tc_launch_one<true, true>(tab, maps, sm, stream, plan.label)));

@@ -66,6 +66,34 @@ __global__ void __launch_bounds__(256) dz_kernel(const float* __restrict__ act, 
   }
 }
 
+// ---- dropout helpers -----------------------------------------------------------------------------
+struct DropArgs {
+  float p, scale;
+  const uint8_t* keep;
+  uint64_t seed;
+  const uint64_t* step_dev;
+  int mode;   // 0 none, 1 mask, 2 rng
+};
+inline DropArgs make_drop(const ta3n_dropout* d) {
+  DropArgs a;
+  memset(&a, 0, sizeof(a));
+  a.scale = 1.0f;
+  if (d && d->p > 0.0f) {
+    a.p = d->p;
+    a.scale = 1.0f / (1.0f - d->p);
+    a.keep = d->keep;
+    a.seed = d->seed;
+    a.step_dev = d->step_dev;
+    a.mode = d->keep ? 1 : 2;
+  }
+  return a;
+}
+__device__ __forceinline__ float drop_factor(const DropArgs& a, size_t e) {
+  if (a.mode == 0) return 1.0f;
+  bool k = (a.mode == 1) ? (a.keep[e] != 0) : rng_keep(a.seed, a.step_dev ? *a.step_dev : 0ull, e, a.p);
+  return k ? a.scale : 0.0f;
+}
+
 // ---- small head: out[row, n] = <x[row,:], W[n,:]> + b[n], n < N2 (warp per row) -----------------
 // W (N2 x K, a few KB) is staged in shared memory by the whole block with all loads in flight at once; a
 // warp then keeps its row of x in registers and produces the N2 logits from on-chip data only.  (The first
@@ -74,7 +102,7 @@ constexpr int kHeadMaxK = 1024;   // x row held in registers: K/32 values per la
 __global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__ x, int ldx,
                                                        const float* __restrict__ W, const float* __restrict__ b,
                                                        float* __restrict__ out, int ldo, int rows, int K, int N2,
-                                                       int w_in_smem) {
+                                                       int w_in_smem, const DropArgs drop, float* __restrict__ x_out) {
   pdl_wait();
   extern __shared__ float head_ws[];
   const int lane = threadIdx.x & 31;
@@ -90,6 +118,15 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__
       float xv[kHeadMaxK / 32];
 #pragma unroll
       for (int i = 0; i < kHeadMaxK / 32; ++i) xv[i] = (lane + 32 * i < K) ? xr[lane + 32 * i] : 0.f;
+      if (x_out) {   // fused Dropout in front of the head (models.py:679-680): x_out = x * keep / (1-p)
+#pragma unroll
+        for (int i = 0; i < kHeadMaxK / 32; ++i)
+          if (lane + 32 * i < K) {
+            const size_t e = (size_t)row * K + lane + 32 * i;
+            xv[i] *= drop_factor(drop, e);
+            x_out[e] = xv[i];
+          }
+      }
       for (int n = 0; n < N2; ++n) {
         const float* wr = Wp + (size_t)n * K;
         float s = 0.f;
@@ -100,6 +137,11 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__
         if (lane == 0) out[(size_t)row * ldo + n] = s + (b ? b[n] : 0.f);
       }
     } else {   // very wide rows (fc_dim >= 2048): stream x from L1/L2
+      if (x_out) {
+        for (int k = lane; k < K; k += 32) x_out[(size_t)row * K + k] = xr[k] * drop_factor(drop, (size_t)row * K + k);
+        __syncwarp();
+        xr = x_out + (size_t)row * K;
+      }
       for (int n = 0; n < N2; ++n) {
         const float* wr = Wp + (size_t)n * K;
         float s = 0.f;
@@ -112,14 +154,18 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__
 }
 
 inline int launch_head_fwd(const float* x, int ldx, const float* W, const float* b, float* out, int ldo, int rows,
-                           int K, int N2, cudaStream_t st) {
+                           int K, int N2, cudaStream_t st, const DropArgs* drop = nullptr, float* x_out = nullptr) {
+  DropArgs d;
+  memset(&d, 0, sizeof(d));
+  d.scale = 1.0f;
+  if (drop) d = *drop;
   const size_t wbytes = (size_t)N2 * K * sizeof(float);
   const int in_smem = wbytes <= 48 * 1024 ? 1 : 0;
   size_t blocks = ((size_t)rows + 3) / 4;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks == 0) blocks = 1;
   pre_launch("head_fwd", st);
-  launch_kernel(head_fwd_kernel, (unsigned)blocks, 128, in_smem ? wbytes : 0, st, x, ldx, W, b, out, ldo, rows, K, N2, in_smem);
+  launch_kernel(head_fwd_kernel, (unsigned)blocks, 128, in_smem ? wbytes : 0, st, x, ldx, W, b, out, ldo, rows, K, N2, in_smem, d, x_out);
   return after_launch();
 }
 
@@ -263,34 +309,6 @@ __global__ void __launch_bounds__(256) frame_attn_bwd_kernel(const float* __rest
       g_logits[(size_t)row * 2 + 1] += dw * a.q1 * (a.lq1 + a.ent);
     }
   }
-}
-
-// ---- dropout helpers -----------------------------------------------------------------------------
-struct DropArgs {
-  float p, scale;
-  const uint8_t* keep;
-  uint64_t seed;
-  const uint64_t* step_dev;
-  int mode;   // 0 none, 1 mask, 2 rng
-};
-inline DropArgs make_drop(const ta3n_dropout* d) {
-  DropArgs a;
-  memset(&a, 0, sizeof(a));
-  a.scale = 1.0f;
-  if (d && d->p > 0.0f) {
-    a.p = d->p;
-    a.scale = 1.0f / (1.0f - d->p);
-    a.keep = d->keep;
-    a.seed = d->seed;
-    a.step_dev = d->step_dev;
-    a.mode = d->keep ? 1 : 2;
-  }
-  return a;
-}
-__device__ __forceinline__ float drop_factor(const DropArgs& a, size_t e) {
-  if (a.mode == 0) return 1.0f;
-  bool k = (a.mode == 1) ? (a.keep[e] != 0) : rng_keep(a.seed, a.step_dev ? *a.step_dev : 0ull, e, a.p);
-  return k ? a.scale : 0.0f;
 }
 
 // dropped = y * keep / (1-p)                                               models.py:679-680

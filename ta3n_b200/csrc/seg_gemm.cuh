@@ -513,7 +513,9 @@ inline void plan_splitk(GemmPlan& plan, Arena* arena, int bm, int bn, int bk, in
   if (!arena) return;
   long tiles = 0;
   for (auto& g : plan.groups) tiles += (long)((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn);
-  if (tiles <= 0 || 2 * tiles > target_ctas) return;   // already (at least half) a wave: partials cost more than they buy
+  // At least half a wave already: partials + the reduce pass cost more than they buy (measured: splitting only
+  // the long-K outliers of the merged weight-gradient launch made the step 17 % slower).
+  if (tiles <= 0 || 2 * tiles > target_ctas) return;
   for (auto& g : plan.groups) {
     long chunks = 0;
     for (int i = 0; i < g.seg_count; ++i) chunks += (plan.segs[g.seg_begin + i].len + bk - 1) / bk;

@@ -712,10 +712,9 @@ int ta3n_video_head_fwd(const float* feat_video, int M, int H, int C, const floa
   if (M == 0) return TA3N_OK;
   TA3N_REQUIRE(feat_video && Wc && bc && dropped && pred, "null pointer");
   const DropArgs d = make_drop(drop);
-  pre_launch("video_drop_fwd", S(stream));
-  launch_kernel(video_drop_fwd_kernel, blocks_for((size_t)M * H, 256), 256, 0, S(stream), feat_video, dropped, (size_t)M * H, d);
-  TA3N_TRY(after_launch());
-  return launch_head_fwd(dropped, H, Wc, bc, pred, C, M, H, C, S(stream));
+  // one kernel: Dropout (writes `dropped`, needed by the video discriminator and by backward) + Linear(H -> C)
+  TA3N_REQUIRE(feat_video != dropped, "dropped must not alias feat_video");
+  return launch_head_fwd(feat_video, H, Wc, bc, pred, C, M, H, C, S(stream), &d, dropped);
 }
 
 size_t ta3n_video_head_bwd_workspace_bytes(int M, int H, int C) {
