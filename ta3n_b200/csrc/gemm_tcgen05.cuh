@@ -295,6 +295,7 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
         const uint32_t b_base = a_base + TC_A_BYTES;
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
+          if ((dbg & 512) && ks > 0) break;   // debug: 1 of 4 MMAs (timing experiments only, wrong results)
           const uint64_t adesc = A_KMAJ ? umma_desc_kmajor(a_base, ks) : umma_desc_mnmajor(a_base, ks);
           const uint64_t bdesc = B_KMAJ ? umma_desc_kmajor(b_base, ks) : umma_desc_mnmajor(b_base, ks);
           umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
