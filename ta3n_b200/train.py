@@ -1,5 +1,5 @@
 """Fused training step of the path: forward + loss heads + backward as a fixed sequence of C-ABI
-calls (no autograd graph, no torch ops), optionally captured in ONE CUDA graph.
+calls (no autograd graph, no torch ops), captured in CUDA graphs.
 
 This is lines 418-576 of the reference's ``main.py`` for the shipped configuration
 (use_target='uSv', adv_DA='RevGrad', add_loss_DA='attentive_entropy'):
@@ -7,12 +7,18 @@ This is lines 418-576 of the reference's ``main.py`` for the shipped configurati
     CE + 3 domain CEs + gamma * attentive_entropy                          main.py:446, 508-538, 559-562
     loss.backward()                                                        main.py:576
 Gradients land directly in a flat fp32 bucket whose views are installed as ``param.grad``, so a stock
-``torch.optim`` optimizer and ``clip_grad_norm_`` work unchanged, and data parallelism is one
-all-reduce over that bucket (parameters the path never uses keep ``grad=None``, as in the reference).
+``torch.optim`` optimizer and ``clip_grad_norm_`` work unchanged (parameters the path never uses keep
+``grad=None``, as in the reference).
+
+Data parallelism (one process per GPU, videos sharded, weights replicated) replaces the reference's
+``nn.DataParallel`` (main.py:79) by NCCL all-reduces over that bucket.  With more than one rank the step is
+captured as TWO graphs split where the backward has produced the gradients of the video / relation / TRN
+layers (62 % of the bytes): their all-reduce runs on NCCL's stream while the second graph (frame
+discriminator + shared layer backward) computes; only the second, smaller all-reduce is exposed.
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -22,6 +28,7 @@ from . import functional as TF
 from ._lib import check
 
 _P = TF._p
+_N_LATE = 6     # path_parameters()[0:6] = shared layer W,b + frame discriminator W1,b1,W2,b2: produced last
 
 
 class TrainStep:
@@ -32,8 +39,9 @@ class TrainStep:
 
     def __init__(self, model, batch_source: int, batch_target: int, beta: Sequence[float], gamma: float = 0.003,
                  place_adv: Sequence[str] = ("Y", "Y", "Y"), add_loss_DA: str = "attentive_entropy",
-                 use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False, overlap_wgrad: bool = False,
-                 parallel_branches: bool = False):
+                 use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False,
+                 overlap_wgrad: bool = False, parallel_branches: bool = False,
+                 overlap_allreduce: Optional[bool] = None):
         if not model.training:
             raise ValueError("TrainStep needs model.train() (dropout state is fixed at construction)")
         self.model = model
@@ -56,16 +64,27 @@ class TrainStep:
                 # main.py:560 indexes pred_domain_all[1], the video level only when both are on
                 raise NotImplementedError("attentive_entropy needs place_adv[0] == place_adv[1] == 'Y'")
             self.flags |= 8
+        # split the step in two graphs around the first gradient bucket only when there is something to overlap
+        self.split = (self.world > 1) if overlap_allreduce is None else bool(overlap_allreduce)
+        if model.use_attn_frame != "none":
+            self.split = False     # frame attention couples the TRN and frame-discriminator gradients
 
-        # flat gradient bucket; views installed as .grad
+        # flat gradient bucket, laid out in the order the backward finishes the gradients:
+        #   [ video head, video disc, relation discs, TRN | frame disc, shared layer ]
+        # views are installed as .grad
         n = sum(p.numel() for p in self.params)
         self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.grad_views, off = [], 0
-        for p in self.params:
-            v = self.flat_grad[off:off + p.numel()].view_as(p)
+        self.grad_views: List[Optional[torch.Tensor]] = [None] * len(self.params)
+        off = 0
+        for idx in list(range(_N_LATE, len(self.params))) + list(range(_N_LATE)):
+            p = self.params[idx]
+            self.grad_views[idx] = self.flat_grad[off:off + p.numel()].view_as(p)
             off += p.numel()
-            self.grad_views.append(v)
-            p.grad = v
+            if idx == len(self.params) - 1:
+                self.early_numel = off
+            p.grad = self.grad_views[idx]
+        self.bucket_early = self.flat_grad[:self.early_numel]
+        self.bucket_late = self.flat_grad[self.early_numel:]
 
         f32 = dict(device=dev, dtype=torch.float32)
         # input slots: one, or two for prefetching the next mini-batch while this one computes
@@ -97,18 +116,18 @@ class TrainStep:
         self.overlap_wgrad = bool(overlap_wgrad)
         self.side_stream = torch.cuda.Stream(device=dev) if self.overlap_wgrad else None
         self.launches_per_step = 0               # kernels of libta3n_sm100.so per step (counted at capture)
-        self.graphs = [None] * self.n_slots      # one captured graph per input slot
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.use_graph = bool(use_graph)
+        self.graphs = [None] * self.n_slots      # per input slot: (graph_a, graph_b or None)
         if use_graph:
             for slot in range(self.n_slots):
                 self.xs, self.xt, self.labels = self.slots[slot]
-                self._capture()
-                self.graphs[slot] = self.graph
+                self.graphs[slot] = self._capture()
             self.xs, self.xt, self.labels = self.slots[0]
-            self.graph = self.graphs[0]
 
     # -- the fixed launch sequence ---------------------------------------------------------------------
-    def _enqueue(self):
+    def _enqueue(self, at_split=None):
+        """Enqueue the whole step on the current stream.  ``at_split()`` (optional) is called at the point
+        where the early gradient bucket is complete (after the TRN stage's deferred weight gradients)."""
         lib = _lib.load()
         st = TF._stream()
         check(lib.ta3n_counter_inc(_P(self.step_counter), st))          # fresh dropout masks per step
@@ -121,13 +140,17 @@ class TrainStep:
                                     _P(self.g_frame), _P(self.loss_ws), self.loss_ws.numel(), st))
         gin = {"pred_video": self.g_video, "pred_rel": self.g_rel, "pred_dom_video": self.g_dom,
                "pred_frame": self.g_frame}
-        # The data-gradient chain (sub-wave GEMMs + row kernels, each waiting for the previous one) runs on the
-        # main stream; the weight-gradient GEMMs / bias sums it leaves behind are deferred and issued in three
-        # grouped batches on a SECOND stream as soon as their inputs exist, filling the SMs the chain leaves idle
-        # (buffers and workspaces are persistent and distinct per batch, so nothing is overwritten under them).
+        # The data-gradient chain runs first; the weight-gradient GEMMs / bias sums it leaves behind are deferred
+        # and issued as grouped launches (buffers and workspaces are persistent, so they stay valid):
+        #   one batch at the end, or -- split mode -- one after the TRN stage (early bucket) and one at the end.
         main = torch.cuda.current_stream()
         side = self.side_stream
-        flush_after = {"relation": 0, "trn": 1, "shared": 2} if self.overlap_wgrad else {"shared": 2}
+        if self.overlap_wgrad:
+            flush_after = {"relation": 0, "trn": 1, "shared": 2}
+        elif at_split is not None:
+            flush_after = {"trn": 0, "shared": 1}
+        else:
+            flush_after = {"shared": 0}
 
         def stage_done(name):
             if name not in flush_after:
@@ -139,7 +162,9 @@ class TrainStep:
                 side.wait_event(ev)
                 check(lib.ta3n_wgrad_defer_flush(_P(ws), ws.numel(), side.cuda_stream))
             else:
-                check(lib.ta3n_wgrad_defer_flush(_P(ws), ws.numel(), st))
+                check(lib.ta3n_wgrad_defer_flush(_P(ws), ws.numel(), TF._stream()))
+            if name == "trn" and at_split is not None:
+                at_split()
             if name != "shared":
                 check(lib.ta3n_wgrad_defer_begin())
 
@@ -154,14 +179,31 @@ class TrainStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             n0 = _lib.launch_count()
-            self._enqueue()                      # warm-up: sizes every buffer, sets kernel attributes
+            self._enqueue(at_split=(lambda: None) if self.split else None)   # warm-up: sizes every buffer
             self.launches_per_step = _lib.launch_count() - n0
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._enqueue()
-        self.graph = g
+        if not self.split:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            return (g, None)
+        # two graphs: [forward .. TRN stage + early weight gradients] | [frame discriminator + shared layer]
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=self.device)
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            ga.capture_begin()
+
+            def cut():
+                ga.capture_end()
+                gb.capture_begin(pool=ga.pool())
+
+            self._enqueue(at_split=cut)
+            gb.capture_end()
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
+        return (ga, gb)
 
     # -- public API ------------------------------------------------------------------------------------
     def load(self, source, target, labels):
@@ -191,15 +233,24 @@ class TrainStep:
         """Make the prefetched slot the active one (the compute stream waits for its copies)."""
         self.active = 1 - self.active
         self.xs, self.xt, self.labels = self.slots[self.active]
-        self.graph = self.graphs[self.active]
         if self.ready[self.active] is not None:
             torch.cuda.current_stream().wait_event(self.ready[self.active])
             self.ready[self.active] = None
 
+    def _allreduce(self, t, async_op=False):
+        # AVG = sum * 1/world inside NCCL: mean of the equal-sized shards' gradients = global-batch gradient
+        return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+
     def run(self):
         """forward + loss + backward (+ gradient all-reduce); returns the device loss tensor (1,)."""
-        if self.graph is not None:
-            self.graph.replay()
+        pending = None
+        if self.use_graph:
+            ga, gb = self.graphs[self.active]
+            ga.replay()
+            if gb is not None:
+                if self.world > 1:
+                    pending = self._allreduce(self.bucket_early, async_op=True)   # overlaps graph b
+                gb.replay()
         else:
             n0 = _lib.launch_count()
             self._enqueue()
@@ -209,8 +260,11 @@ class TrainStep:
             ev.record()
             self.consumed[self.active] = ev
         if self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat_grad.mul_(1.0 / self.world)
+            if pending is not None:
+                self._allreduce(self.bucket_late)
+                pending.wait()
+            else:
+                self._allreduce(self.flat_grad)
         return self.loss
 
     def __call__(self, source, target, labels):

@@ -461,6 +461,16 @@ def test_fused_step_stream_options_do_not_change_results():
     torch.cuda.synchronize()
     assert torch.equal(l0, l1)
     assert_close(alt.flat_grad, g0, 1e-6, "gradients with forked streams")
+    # two-graph split used to overlap the early-bucket all-reduce under data parallelism
+    split = TrainStep(model, 40, 40, (0.75, 0.75, 0.5), use_graph=True, overlap_allreduce=True)
+    assert split.graphs[0][1] is not None
+    l2 = split(xs, xt, labels).clone()
+    l2 = split(xs, xt, labels).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(l0, l2)
+    assert_close(split.flat_grad, g0, 1e-6, "gradients with the split graphs")
+    n_late = sum(p.numel() for p in split.params[:6])
+    assert split.bucket_late.numel() == n_late and split.bucket_early.numel() + n_late == split.flat_grad.numel()
 
 
 def test_fused_step_dropout_changes_every_replay():
