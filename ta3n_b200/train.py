@@ -41,7 +41,7 @@ class TrainStep:
                  place_adv: Sequence[str] = ("Y", "Y", "Y"), add_loss_DA: str = "attentive_entropy",
                  use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False,
                  overlap_wgrad: bool = False, parallel_branches: bool = False,
-                 overlap_allreduce: Optional[bool] = None):
+                 overlap_allreduce: Optional[bool] = None, graph_collectives: Optional[bool] = None):
         if not model.training:
             raise ValueError("TrainStep needs model.train() (dropout state is fixed at construction)")
         self.model = model
@@ -68,6 +68,10 @@ class TrainStep:
         self.split = (self.world > 1) if overlap_allreduce is None else bool(overlap_allreduce)
         if model.use_attn_frame != "none":
             self.split = False     # frame attention couples the TRN and frame-discriminator gradients
+        # data parallel: try to capture the two NCCL all-reduces INSIDE the step's graph (no host launch gaps,
+        # the early one overlaps the rest of the backward); fall back to two graphs + eager collectives
+        self.graph_collectives = (self.world > 1) if graph_collectives is None else bool(graph_collectives)
+        self.collectives_captured = False
 
         # flat gradient bucket, laid out in the order the backward finishes the gradients:
         #   [ video head, video disc, relation discs, TRN | frame disc, shared layer ]
@@ -174,15 +178,38 @@ class TrainStep:
         if self.overlap_wgrad:
             main.wait_stream(side)            # join
 
+    def _enqueue_with_collectives(self):
+        """The step with both gradient all-reduces issued in place (early bucket as soon as it is complete)."""
+        pending = []
+        self._enqueue(at_split=lambda: pending.append(self._allreduce(self.bucket_early, async_op=True)))
+        self._allreduce(self.bucket_late)
+        for w in pending:
+            w.wait()
+
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             n0 = _lib.launch_count()
-            self._enqueue(at_split=(lambda: None) if self.split else None)   # warm-up: sizes every buffer
+            if self.world > 1 and self.split:
+                self._enqueue_with_collectives()       # warm-up incl. NCCL communicator set-up
+            else:
+                self._enqueue(at_split=(lambda: None) if self.split else None)   # warm-up: sizes every buffer
             self.launches_per_step = _lib.launch_count() - n0
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if self.world > 1 and self.split and self.graph_collectives:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_with_collectives()
+                self.collectives_captured = True
+                return (g, None)
+            except Exception as e:      # NCCL capture not possible here: eager collectives between two graphs
+                import warnings
+                warnings.warn(f"ta3n_b200: NCCL capture failed ({type(e).__name__}: {e}); using split graphs")
+                self.collectives_captured = False
+                torch.cuda.synchronize()
         if not self.split:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -259,7 +286,7 @@ class TrainStep:
             ev = torch.cuda.Event()
             ev.record()
             self.consumed[self.active] = ev
-        if self.world > 1:
+        if self.world > 1 and not (self.use_graph and self.collectives_captured):
             if pending is not None:
                 self._allreduce(self.bucket_late)
                 pending.wait()

@@ -1,0 +1,86 @@
+"""Data-parallel TrainStep on 2 GPUs (NCCL): the averaged shard gradients equal the single-GPU gradients of
+the global batch.  Needs >= 2 CUDA devices; skipped on single-GPU boxes."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ta3n_oracle as orc
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")]
+
+B_LOCAL = 32
+
+
+def _cfg():
+    return orc.PathConfig(num_class=12, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0)
+
+
+def _build(dev):
+    from ta3n_b200.models import VideoModel
+    cfg = _cfg()
+    m = VideoModel(cfg.num_class, "video", "trn-m", "RGB", train_segments=5, val_segments=5, fc_dim=512,
+                   dropout_i=0.0, dropout_v=0.0, partial_bn=False, verbose=False)
+    m.load_state_dict(orc.init_params(cfg, seed=1234))
+    return m.to(dev).train()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import ta3n_b200
+        from ta3n_b200.parallel import shard_rows
+        from ta3n_b200.train import TrainStep
+        ta3n_b200.set_gemm_engine("fp32")          # exact engine: the comparison below is about the collective
+        xs, xt, labels = orc.synthetic_batch(world * B_LOCAL, _cfg())
+        sl = shard_rows(world * B_LOCAL, rank, world)
+        model = _build(dev)
+        step = TrainStep(model, B_LOCAL, B_LOCAL, (0.75, 0.75, 0.5), gamma=0.0, use_graph=True)   # split graphs
+        assert step.graphs[0][1] is not None
+        for _ in range(2):
+            step(xs[sl], xt[sl], labels[sl])
+        torch.cuda.synchronize()
+        if rank == 0:
+            q.put(step.flat_grad.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_trainstep_matches_global_batch():
+    import ta3n_b200
+    from ta3n_b200.train import TrainStep
+    ta3n_b200.set_gemm_engine("fp32")
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = torch.from_numpy(q.get(timeout=300))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    dev = torch.device("cuda", 0)
+    xs, xt, labels = orc.synthetic_batch(world * B_LOCAL, _cfg())
+    model = _build(dev)
+    # gamma=0: every loss term is a plain mean over rows, so mean-of-shard-means == global mean exactly
+    ref = TrainStep(model, world * B_LOCAL, world * B_LOCAL, (0.75, 0.75, 0.5), gamma=0.0, use_graph=True,
+                    overlap_allreduce=True)          # same bucket layout as the 2-rank run
+    ref(xs, xt, labels)
+    torch.cuda.synchronize()
+    want = ref.flat_grad.cpu()
+    err = ((got.double() - want.double()).norm() / want.double().norm()).item()
+    assert err < 1e-4, err          # fp32 summation order only
