@@ -393,6 +393,8 @@ def run_b200(args):
         dist.barrier()
     if rank != 0:
         if world > 1:
+            del step, pipe, eager
+            torch.cuda.synchronize()
             dist.destroy_process_group()
         return
 
@@ -448,6 +450,8 @@ def run_b200(args):
                                           f"cores, ~{args.cpu_seconds:.0f}s budget"}
     print_json(line)
     if world > 1:
+        del step, pipe, eager
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

@@ -68,9 +68,11 @@ class TrainStep:
         self.split = (self.world > 1) if overlap_allreduce is None else bool(overlap_allreduce)
         if model.use_attn_frame != "none":
             self.split = False     # frame attention couples the TRN and frame-discriminator gradients
-        # data parallel: try to capture the two NCCL all-reduces INSIDE the step's graph (no host launch gaps,
-        # the early one overlaps the rest of the backward); fall back to two graphs + eager collectives
-        self.graph_collectives = (self.world > 1) if graph_collectives is None else bool(graph_collectives)
+        # graph_collectives=True captures the two NCCL all-reduces INSIDE the step's graph.  It works and is
+        # marginally faster (N=2: 0.371 vs 0.378 ms/step) but process-group teardown then hangs while the graphs
+        # are alive (observed on torch 2.11 / NCCL 2.28), so it is opt-in; the default is two graphs with the
+        # early bucket's all-reduce issued eagerly between them (overlapping the second graph).
+        self.graph_collectives = False if graph_collectives is None else bool(graph_collectives)
         self.collectives_captured = False
 
         # flat gradient bucket, laid out in the order the backward finishes the gradients:
