@@ -323,7 +323,6 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_ms = float(t.item())
-    clocks = sampler.finish() if sampler else None
 
     # ---- e2e: host (pinned) inputs -> public API -> loss on the host, optimizer step included.
     # Every step's inputs are copied H2D inside the timed region; the copy of step k+1 is issued on a copy
@@ -355,6 +354,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
+    clocks = sampler.finish() if sampler else None     # sampled across both timed regions (value and e2e)
 
     # ---- the drop-in autograd API (VideoModel.forward + torch loss + backward), for reference
     def autograd_step():
