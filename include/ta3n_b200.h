@@ -211,6 +211,20 @@ int ta3n_loss_fwd_bwd(const float* pred_video, const long long* labels, const fl
 /* *counter += 1 on the stream (dropout step counter for CUDA-graph replays). */
 int ta3n_counter_inc(uint64_t* counter, ta3n_stream_t stream);
 
+/* ---- optimizer step ---------------------------------------------------- */
+/* main.py:578-581 clip_grad_norm_(parameters, max_norm) followed by main.py:83/583
+ * torch.optim.SGD(lr, momentum, weight_decay, nesterov=True).step(), over FLAT fp32 buffers of n
+ * elements (params, grads, momentum buffers in the same order; momentum zero-initialised):
+ *     coef = min(1, max_norm / (||g||_2 + 1e-6))        (max_norm <= 0: no clipping, coef = 1)
+ *     d = coef*g + weight_decay*p;  m = momentum*m + d;  p -= lr * (d + momentum*m)
+ * lr is read from device memory (*lr_dev) so a per-step schedule (main.py:800-802) replays inside a
+ * CUDA graph.  stats (optional, 2 floats) receives {||g||_2, coef}.  Two launches; deterministic.  */
+size_t ta3n_sgd_workspace_bytes(void);
+int ta3n_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf, long long n,
+                           const float* lr_dev, float momentum, float weight_decay, float max_norm,
+                           void* workspace, size_t workspace_bytes, float* stats,
+                           ta3n_stream_t stream);
+
 /* ---- self test of the tensor-core GEMM engine (used by tests; device buffers) ------ */
 /* C[M,N] = A[M,K] * B[N,K]^T with the selected engine; A, B, C row-major fp32.           */
 int ta3n_gemm_tn(const float* A, const float* B, float* C, int M, int N, int K,

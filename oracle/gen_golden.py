@@ -82,6 +82,26 @@ def checksum(t: torch.Tensor) -> np.ndarray:
     return np.array([d.sum().item(), d.norm().item()])
 
 
+def reference_loss(outs, labels, use_attn="TransAttn"):
+    """Loss composition exactly as main.py:446, 508-538, 559-562 (uSv + RevGrad + attentive_entropy), on the
+    reference's own 10-tuple, using the reference's loss.py."""
+    _, _, ref_loss = ref_shims.load()
+    (attn_s, out_s, _, pd_s, feat_s, attn_t, out_t, _, pd_t, feat_t) = outs
+    ce = torch.nn.CrossEntropyLoss()
+    loss = ce(out_s, labels)
+    pred_domain_all = []
+    for l in range(3):
+        ps = pd_s[l].view(-1, pd_s[l].size()[-1])
+        pt = pd_t[l].view(-1, pd_t[l].size()[-1])
+        dom = torch.cat((torch.zeros(ps.size(0)).long(), torch.ones(pt.size(0)).long()), 0)
+        pred = torch.cat((ps, pt), 0)
+        pred_domain_all.append(pred)
+        loss = loss + ce(pred, dom)
+    if use_attn != "none":
+        loss = loss + GAMMA * ref_loss.attentive_entropy(torch.cat((out_s, out_t), 0), pred_domain_all[1])
+    return loss
+
+
 def run_reference(c, dtype=torch.float32):
     ref_models, _, ref_loss = ref_shims.load()
     cfg, xs, xt, labels, masks = case_inputs(c)
@@ -99,20 +119,7 @@ def run_reference(c, dtype=torch.float32):
     else:
         model.eval()
     outs = model(xs, xt, list(BETA), 0, is_train=True, reverse=False)
-    # loss composition exactly as main.py:446, 508-538, 559-562 (uSv + RevGrad + attentive_entropy)
-    (attn_s, out_s, _, pd_s, feat_s, attn_t, out_t, _, pd_t, feat_t) = outs
-    ce = torch.nn.CrossEntropyLoss()
-    loss = ce(out_s, labels)
-    pred_domain_all = []
-    for l in range(3):
-        ps = pd_s[l].view(-1, pd_s[l].size()[-1])
-        pt = pd_t[l].view(-1, pd_t[l].size()[-1])
-        dom = torch.cat((torch.zeros(ps.size(0)).long(), torch.ones(pt.size(0)).long()), 0)
-        pred = torch.cat((ps, pt), 0)
-        pred_domain_all.append(pred)
-        loss = loss + ce(pred, dom)
-    if c["use_attn"] != "none":
-        loss = loss + GAMMA * ref_loss.attentive_entropy(torch.cat((out_s, out_t), 0), pred_domain_all[1])
+    loss = reference_loss(outs, labels, c["use_attn"])
     loss.backward()
     return model, outs, loss, (xs, xt)
 

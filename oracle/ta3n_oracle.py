@@ -436,3 +436,53 @@ def synthetic_batch(batch: int, cfg: PathConfig, seed: int = 4321, dtype=torch.f
     xt = torch.randn(batch, cfg.num_segments, FEATURE_DIM, generator=g).to(dtype)
     labels = torch.arange(batch) % cfg.num_class
     return xs, xt, labels
+
+
+# ---- the optimizer step that follows loss.backward() ------------------------------------
+def clip_grad_norm(grads: Dict[str, torch.Tensor], max_norm: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``clip_grad_norm_(model.parameters(), args.clip_gradient)`` of main.py:578-581 restated on a dict of
+    gradients (in place).  torch.nn.utils.clip_grad_norm_: total = ||(||g_i||_2)_i||_2,
+    coef = clamp(max_norm / (total + 1e-6), max=1), g_i *= coef.  Returns (total_norm, coef)."""
+    total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g) for g in grads.values()]))
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    for g in grads.values():
+        g.mul_(coef)
+    return total, coef
+
+
+def sgd_nesterov_step(params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor],
+                      bufs: Dict[str, torch.Tensor], lr: float, momentum: float = 0.9,
+                      weight_decay: float = 1e-4) -> None:
+    """``torch.optim.SGD(params, lr, momentum, weight_decay, nesterov=True).step()`` (main.py:83, 583), in
+    place on ``params`` / ``bufs``.  Only parameters that received a gradient are touched (SGD skips
+    ``grad is None``).  The first step of torch clones d into the buffer; a zero-initialised buffer gives the
+    same value (momentum*0 + d)."""
+    for k, g in grads.items():
+        d = g.add(params[k], alpha=weight_decay)
+        buf = bufs.setdefault(k, torch.zeros_like(d))
+        buf.mul_(momentum).add_(d)
+        params[k].add_(d.add(buf, alpha=momentum), alpha=-lr)
+
+
+def lr_dann(lr0: float, p: float) -> float:
+    """adjust_learning_rate_dann, main.py:800-802 (p = progress in [0, 1], main.py:349)."""
+    return lr0 / (1.0 + 10.0 * p) ** 0.75
+
+
+def beta_dann(p: float) -> float:
+    """main.py:350: the value that replaces negative entries of --beta."""
+    return 2.0 / (1.0 + math.exp(-10.0 * p)) - 1.0
+
+
+def train_iteration(params, bufs, xs, xt, labels, beta, cfg: PathConfig, lr: float, gamma: float = 0.003,
+                    momentum: float = 0.9, weight_decay: float = 1e-4, clip_gradient: Optional[float] = 20.0,
+                    train: bool = True, masks=None, gates=None):
+    """One full iteration of main.py:418-583: train_step, clip, SGD-Nesterov.  Updates params/bufs in place;
+    returns (loss, total_norm or None)."""
+    loss, _, grads = train_step(params, xs, xt, labels, beta, cfg, gamma, train=train, masks=masks, gates=gates)
+    grads = OrderedDict((k, g.clone()) for k, g in grads.items() if g is not None)
+    total = None
+    if clip_gradient is not None:
+        total, _ = clip_grad_norm(grads, clip_gradient)
+    sgd_nesterov_step(params, grads, bufs, lr, momentum, weight_decay)
+    return loss, total

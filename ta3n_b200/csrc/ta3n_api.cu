@@ -5,6 +5,7 @@
 #include "seg_gemm.cuh"
 #include "rowops.cuh"
 #include "gemm_tcgen05.cuh"
+#include "optim.cuh"
 
 #include <functional>
 
@@ -798,6 +799,32 @@ int ta3n_counter_inc(uint64_t* counter, ta3n_stream_t stream) {
   TA3N_REQUIRE(counter != nullptr, "null counter");
   pre_launch("counter_inc", S(stream));
   launch_kernel(counter_inc_kernel, 1, 1, 0, S(stream), reinterpret_cast<unsigned long long*>(counter));
+  return after_launch();
+}
+
+// ---- optimizer step: clip_grad_norm_ + SGD-Nesterov over flat buffers (main.py:83, 578-583) ----
+size_t ta3n_sgd_workspace_bytes(void) { return Arena::round(kSqnormBlocks * sizeof(float)); }
+
+int ta3n_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf, long long n, const float* lr_dev,
+                           float momentum, float weight_decay, float max_norm, void* workspace,
+                           size_t workspace_bytes, float* stats, ta3n_stream_t stream) {
+  TA3N_REQUIRE(params && grads && momentum_buf && lr_dev && n > 0, "bad arguments");
+  TA3N_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
+                 reinterpret_cast<uintptr_t>(momentum_buf)) & 15) == 0, "flat buffers must be 16-byte aligned");
+  TA3N_REQUIRE(momentum >= 0.f && weight_decay >= 0.f, "negative momentum / weight decay");
+  float* partial = nullptr;
+  if (max_norm > 0.f) {
+    TA3N_REQUIRE(workspace != nullptr && workspace_bytes >= ta3n_sgd_workspace_bytes(), "workspace too small");
+    partial = static_cast<float*>(workspace);
+    pre_launch("sqnorm", S(stream));
+    launch_kernel(sqnorm_partial_kernel, kSqnormBlocks, kOptThreads, 0, S(stream), grads, n, partial);
+    TA3N_TRY(after_launch());
+  }
+  long long n4 = (n + 3) / 4;
+  int blocks = static_cast<int>(std::min<long long>((n4 + kOptThreads - 1) / kOptThreads, 148 * 8));
+  pre_launch("sgd_nesterov", S(stream));
+  launch_kernel(sgd_nesterov_kernel, blocks, kOptThreads, 0, S(stream), params, grads, momentum_buf, n, lr_dev,
+                momentum, weight_decay, max_norm, static_cast<const float*>(partial), kSqnormBlocks, stats);
   return after_launch();
 }
 

@@ -18,6 +18,7 @@ discriminator + shared layer backward) computes; only the second, smaller all-re
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
 import torch
@@ -29,6 +30,57 @@ from ._lib import check
 
 _P = TF._p
 _N_LATE = 6     # path_parameters()[0:6] = shared layer W,b + frame discriminator W1,b1,W2,b2: produced last
+_ALIGN = 64     # floats: every tensor of a flat buffer starts 256-byte aligned (vector stores, TMA operands)
+
+
+@dataclass
+class SGDNesterov:
+    """``torch.optim.SGD(model.parameters(), lr, momentum, weight_decay, nesterov=True)`` (main.py:83) preceded
+    by ``clip_grad_norm_(model.parameters(), clip_gradient)`` (main.py:578-581; None = no clipping), run as two
+    kernels over the flat parameter / gradient / momentum buffers (C ABI ``ta3n_sgd_nesterov_step``)."""
+    lr: float
+    momentum: float = 0.9
+    weight_decay: float = 1e-4
+    clip_gradient: Optional[float] = 20.0
+
+
+def lr_dann(lr0: float, p: float) -> float:
+    """adjust_learning_rate_dann (main.py:800-802): p = training progress in [0, 1] (main.py:349)."""
+    return lr0 / (1.0 + 10.0 * p) ** 0.75
+
+
+def bucket_layout(params):
+    """Order and offsets (in floats) of the path's tensors inside a flat buffer: the order in which the
+    backward finishes their gradients, [video head, video disc, relation discs, TRN | frame disc, shared layer],
+    every slot padded to ``_ALIGN`` floats.  Returns (order, offsets-by-index, total, early_total)."""
+    order = list(range(_N_LATE, len(params))) + list(range(_N_LATE))
+    offs, off, early = {}, 0, 0
+    for idx in order:
+        offs[idx] = off
+        off += -(-params[idx].numel() // _ALIGN) * _ALIGN
+        if idx == len(params) - 1:
+            early = off
+    return order, offs, off, early
+
+
+def flatten_parameters(model) -> torch.Tensor:
+    """Re-point the ``.data`` of the path's parameters at views of ONE flat fp32 buffer (bucket_layout order), so
+    that the optimizer is a single pass over contiguous memory.  Values are preserved; idempotent.  The
+    Parameter objects (and hence state_dict / load_state_dict / checkpoints) are unchanged."""
+    params = model.path_parameters()
+    order, offs, total, _ = bucket_layout(params)
+    flat = getattr(model, "_ta3n_flat_params", None)
+    if (flat is not None and flat.numel() == total and flat.device == params[0].device and
+            all(params[i].data_ptr() == flat.data_ptr() + 4 * offs[i] for i in order)):
+        return flat
+    flat = torch.zeros(total, device=params[0].device, dtype=torch.float32)
+    for idx in order:
+        prm = params[idx]
+        view = flat[offs[idx]:offs[idx] + prm.numel()].view_as(prm)
+        view.copy_(prm.data)
+        prm.data = view
+    object.__setattr__(model, "_ta3n_flat_params", flat)
+    return flat
 
 
 class TrainStep:
@@ -41,7 +93,8 @@ class TrainStep:
                  place_adv: Sequence[str] = ("Y", "Y", "Y"), add_loss_DA: str = "attentive_entropy",
                  use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False,
                  overlap_wgrad: bool = False, parallel_branches: bool = False,
-                 overlap_allreduce: Optional[bool] = None, graph_collectives: Optional[bool] = None):
+                 overlap_allreduce: Optional[bool] = None, graph_collectives: Optional[bool] = None,
+                 optimizer: Optional[SGDNesterov] = None):
         if not model.training:
             raise ValueError("TrainStep needs model.train() (dropout state is fixed at construction)")
         self.model = model
@@ -77,20 +130,27 @@ class TrainStep:
 
         # flat gradient bucket, laid out in the order the backward finishes the gradients:
         #   [ video head, video disc, relation discs, TRN | frame disc, shared layer ]
-        # views are installed as .grad
-        n = sum(p.numel() for p in self.params)
+        # views are installed as .grad; the parameters live in a twin flat buffer (same offsets)
+        self.flat_param = flatten_parameters(model)
+        order, offs, n, self.early_numel = bucket_layout(self.params)
         self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
         self.grad_views: List[Optional[torch.Tensor]] = [None] * len(self.params)
-        off = 0
-        for idx in list(range(_N_LATE, len(self.params))) + list(range(_N_LATE)):
+        for idx in order:
             p = self.params[idx]
-            self.grad_views[idx] = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
-            if idx == len(self.params) - 1:
-                self.early_numel = off
+            self.grad_views[idx] = self.flat_grad[offs[idx]:offs[idx] + p.numel()].view_as(p)
             p.grad = self.grad_views[idx]
         self.bucket_early = self.flat_grad[:self.early_numel]
         self.bucket_late = self.flat_grad[self.early_numel:]
+
+        # optimizer state: momentum buffers, device-resident learning rate, {norm, coef} stats
+        self.opt = optimizer
+        if optimizer is not None:
+            self.momentum_buf = torch.zeros_like(self.flat_grad)
+            self.lr_dev = torch.full((1,), float(optimizer.lr), device=dev, dtype=torch.float32)
+            self._lr_host = torch.full((1,), float(optimizer.lr), dtype=torch.float32).pin_memory()
+            self.grad_stats = torch.zeros(2, device=dev, dtype=torch.float32)     # [total_norm, clip_coef]
+            self.opt_ws = torch.zeros(max(1, _lib.load().ta3n_sgd_workspace_bytes() // 4), device=dev,
+                                      dtype=torch.float32)
 
         f32 = dict(device=dev, dtype=torch.float32)
         # input slots: one, or two for prefetching the next mini-batch while this one computes
@@ -131,9 +191,26 @@ class TrainStep:
             self.xs, self.xt, self.labels = self.slots[0]
 
     # -- the fixed launch sequence ---------------------------------------------------------------------
-    def _enqueue(self, at_split=None):
+    def _enqueue_optimizer(self):
+        """clip_grad_norm_ + SGD-Nesterov over the flat buffers (main.py:578-583): two launches."""
+        o = self.opt
+        clip = float(o.clip_gradient) if o.clip_gradient is not None else 0.0
+        check(_lib.load().ta3n_sgd_nesterov_step(
+            _P(self.flat_param), _P(self.flat_grad), _P(self.momentum_buf), self.flat_grad.numel(),
+            _P(self.lr_dev), float(o.momentum), float(o.weight_decay), clip, _P(self.opt_ws),
+            self.opt_ws.numel() * 4, _P(self.grad_stats), TF._stream()))
+
+    def set_lr(self, lr: float):
+        """Per-step learning-rate schedules (main.py:800-802): one 4-byte async copy, no re-capture."""
+        self._lr_host[0] = float(lr)
+        self.lr_dev.copy_(self._lr_host, non_blocking=True)
+        self.opt.lr = float(lr)
+
+    def _enqueue(self, at_split=None, optimizer=False):
         """Enqueue the whole step on the current stream.  ``at_split()`` (optional) is called at the point
-        where the early gradient bucket is complete (after the TRN stage's deferred weight gradients)."""
+        where the early gradient bucket is complete (after the TRN stage's deferred weight gradients).
+        ``optimizer``: append the optimizer step (single-rank sequences; with several ranks it follows the
+        all-reduce instead)."""
         lib = _lib.load()
         st = TF._stream()
         check(lib.ta3n_counter_inc(_P(self.step_counter), st))          # fresh dropout masks per step
@@ -179,14 +256,18 @@ class TrainStep:
                          stage_done=stage_done, side_stream=self.branch_stream)
         if self.overlap_wgrad:
             main.wait_stream(side)            # join
+        if optimizer and self.opt is not None:
+            self._enqueue_optimizer()
 
-    def _enqueue_with_collectives(self):
+    def _enqueue_with_collectives(self, optimizer=False):
         """The step with both gradient all-reduces issued in place (early bucket as soon as it is complete)."""
         pending = []
         self._enqueue(at_split=lambda: pending.append(self._allreduce(self.bucket_early, async_op=True)))
         self._allreduce(self.bucket_late)
         for w in pending:
             w.wait()
+        if optimizer and self.opt is not None:
+            self._enqueue_optimizer()
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)
@@ -197,14 +278,16 @@ class TrainStep:
                 self._enqueue_with_collectives()       # warm-up incl. NCCL communicator set-up
             else:
                 self._enqueue(at_split=(lambda: None) if self.split else None)   # warm-up: sizes every buffer
-            self.launches_per_step = _lib.launch_count() - n0
+            self.launches_per_step = _lib.launch_count() - n0        # warm-up never applies the optimizer
+            if self.opt is not None:
+                self.launches_per_step += 2 if self.opt.clip_gradient is not None else 1
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         if self.world > 1 and self.split and self.graph_collectives:
             try:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._enqueue_with_collectives()
+                    self._enqueue_with_collectives(optimizer=True)
                 self.collectives_captured = True
                 return (g, None)
             except Exception as e:      # NCCL capture not possible here: eager collectives between two graphs
@@ -212,10 +295,11 @@ class TrainStep:
                 warnings.warn(f"ta3n_b200: NCCL capture failed ({type(e).__name__}: {e}); using split graphs")
                 self.collectives_captured = False
                 torch.cuda.synchronize()
+        inline = self.world == 1          # single rank: the optimizer is part of the (last) graph
         if not self.split:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._enqueue()
+                self._enqueue(optimizer=inline)
             return (g, None)
         # two graphs: [forward .. TRN stage + early weight gradients] | [frame discriminator + shared layer]
         ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -228,7 +312,7 @@ class TrainStep:
                 ga.capture_end()
                 gb.capture_begin(pool=ga.pool())
 
-            self._enqueue(at_split=cut)
+            self._enqueue(at_split=cut, optimizer=inline)
             gb.capture_end()
         torch.cuda.current_stream().wait_stream(cap)
         torch.cuda.synchronize()
@@ -271,8 +355,10 @@ class TrainStep:
         return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
 
     def run(self):
-        """forward + loss + backward (+ gradient all-reduce); returns the device loss tensor (1,)."""
+        """forward + loss + backward (+ gradient all-reduce) (+ optimizer step when configured); returns the
+        device loss tensor (1,)."""
         pending = None
+        opt_done = self.opt is None
         if self.use_graph:
             ga, gb = self.graphs[self.active]
             ga.replay()
@@ -280,10 +366,12 @@ class TrainStep:
                 if self.world > 1:
                     pending = self._allreduce(self.bucket_early, async_op=True)   # overlaps graph b
                 gb.replay()
+            opt_done = opt_done or self.world == 1 or self.collectives_captured
         else:
             n0 = _lib.launch_count()
-            self._enqueue()
+            self._enqueue(optimizer=self.world == 1)
             self.launches_per_step = _lib.launch_count() - n0
+            opt_done = opt_done or self.world == 1
         if self.n_slots > 1:
             ev = torch.cuda.Event()
             ev.record()
@@ -294,6 +382,8 @@ class TrainStep:
                 pending.wait()
             else:
                 self._allreduce(self.flat_grad)
+        if not opt_done:
+            self._enqueue_optimizer()             # after the all-reduce: every rank applies the same update
         return self.loss
 
     def __call__(self, source, target, labels):

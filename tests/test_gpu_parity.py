@@ -5,6 +5,8 @@ the exact-fp32 engine is held to 2e-4 (accumulation-order noise only).
 """
 import os
 
+from collections import OrderedDict
+
 import pytest
 import torch
 
@@ -469,8 +471,95 @@ def test_fused_step_stream_options_do_not_change_results():
     torch.cuda.synchronize()
     assert torch.equal(l0, l2)
     assert_close(split.flat_grad, g0, 1e-6, "gradients with the split graphs")
-    n_late = sum(p.numel() for p in split.params[:6])
+    n_late = sum(-(-p.numel() // 64) * 64 for p in split.params[:6])      # slots are padded to 64 floats
     assert split.bucket_late.numel() == n_late and split.bucket_early.numel() + n_late == split.flat_grad.numel()
+    for prm, view in zip(split.params, split.grad_views):
+        assert view.data_ptr() % 256 == 0 and prm.data_ptr() % 256 == 0    # vector stores / TMA operands
+
+
+@pytest.mark.parametrize("n,max_norm", [(1000003, 0.5), (4096, 0.0), (7, 1e9)])
+def test_sgd_nesterov_kernel_matches_torch_optim(n, max_norm):
+    """ta3n_sgd_nesterov_step vs torch.optim.SGD(nesterov) + clip_grad_norm_ (main.py:83, 578-583) on flat
+    buffers, three steps with a changing learning rate; n deliberately not a multiple of 4."""
+    from ta3n_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(n)
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([ref], 0.1, momentum=0.9, weight_decay=1e-3, nesterov=True)
+    p = p0.to(_dev())
+    m = torch.zeros(n, device=_dev())
+    lr = torch.zeros(1, device=_dev())
+    stats = torch.zeros(2, device=_dev())
+    ws = torch.zeros(lib.ta3n_sgd_workspace_bytes() // 4, device=_dev())
+    for it in range(3):
+        grad = torch.randn(n, generator=g) * (1.0 + it)
+        lr_it = 0.1 / (1 + it)
+        for grp in opt.param_groups:
+            grp["lr"] = lr_it
+        ref.grad = grad.clone()
+        norm_ref = grad.norm()
+        if max_norm > 0:
+            norm_ref = torch.nn.utils.clip_grad_norm_([ref], max_norm)
+        opt.step()
+        lr.fill_(lr_it)
+        gd = grad.to(_dev())
+        _lib.check(lib.ta3n_sgd_nesterov_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), n, lr.data_ptr(), 0.9, 1e-3,
+                                              max_norm, ws.data_ptr(), ws.numel() * 4, stats.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        if max_norm > 0:
+            # torch's fp32 vector norm itself carries ~1e-5 of accumulation error at 1e6 elements; the kernel's
+            # two-stage fixed-order sum is held to the fp64 value
+            assert_close(stats[0].cpu(), norm_ref, 5e-5, "total norm vs torch fp32")
+            assert_close(stats[0].cpu(), grad.double().norm(), 2e-6, "total norm vs fp64")
+            assert abs(float(stats[1]) - min(1.0, max_norm / (float(norm_ref) + 1e-6))) < 5e-5
+    assert_close(p.cpu(), ref.detach(), 1e-6, "parameters after 3 steps")
+    assert_close(m.cpu(), opt.state[ref]["momentum_buffer"], 1e-6, "momentum buffer")
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("clip", [0.02, None])
+def test_fused_train_iteration_matches_oracle(clip, use_graph, engine):
+    """TrainStep(optimizer=SGDNesterov) = main.py:418-583 (forward, loss, backward, clip_grad_norm_, SGD-Nesterov
+    step, DANN learning rate): three iterations against oracle.train_iteration (fp64), compared on the parameter
+    UPDATES.  C=5 and ragged batches make the flat-buffer slots unaligned before padding."""
+    from ta3n_b200.train import SGDNesterov, TrainStep, lr_dann
+    cfg = orc.PathConfig(num_class=5, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0)
+    params = orc.init_params(cfg, seed=33)
+    g = torch.Generator().manual_seed(9)
+    for k in params:
+        if params[k].dtype.is_floating_point and k.startswith(orc.USED_PARAM_PREFIXES) and "weight" in k:
+            params[k] = params[k] + 0.02 * torch.randn(params[k].shape, generator=g)
+    bs, bt = 12, 7
+    xs = torch.randn(bs, 5, orc.FEATURE_DIM, generator=g)
+    xt = torch.randn(bt, 5, orc.FEATURE_DIM, generator=g) - 0.2
+    labels = torch.arange(bs) % 5
+    beta, lr0 = (0.75, 0.75, 0.5), 0.05
+    model = build_model(cfg, params, train=True)
+    step = TrainStep(model, bs, bt, beta, gamma=0.003, use_graph=use_graph,
+                     optimizer=SGDNesterov(lr=lr0, momentum=0.9, weight_decay=1e-4, clip_gradient=clip))
+    p64 = OrderedDict((k, v.double() if v.dtype.is_floating_point else v) for k, v in params.items())
+    bufs = {}
+    for it in range(3):
+        lr = lr_dann(lr0, it / 3.0)
+        assert abs(lr - orc.lr_dann(lr0, it / 3.0)) < 1e-15
+        step.set_lr(lr)
+        loss = step(xs.pin_memory(), xt.pin_memory(), labels)
+        loss_o, total_o = orc.train_iteration(p64, bufs, xs.double(), xt.double(), labels, beta, cfg, lr, 0.003,
+                                              clip_gradient=clip, train=True)
+        torch.cuda.synchronize()
+        assert_close(loss.cpu()[0], loss_o, 20 * TOL[engine], f"loss at iteration {it}")
+        if clip is not None:
+            assert float(total_o) > clip                      # clipping is active in this test
+            assert_close(step.grad_stats[0].cpu(), total_o, GRAD_TOL[engine], f"gradient norm at iteration {it}")
+    named = dict(model.named_parameters())
+    for name in orc.used_param_names(params):
+        delta = named[name].detach().cpu().double() - params[name].double()
+        delta_o = p64[name] - params[name].double()
+        assert_close(delta, delta_o, max(GRAD_TOL[engine], 2e-3), f"update of {name}")
+    # parameters the path never uses are not touched (SGD skips grad=None)
+    assert torch.equal(model.fc_feature_source.weight.detach().cpu(), params["fc_feature_source.weight"])
 
 
 def test_fused_step_dropout_changes_every_replay():

@@ -1,4 +1,6 @@
 """Pin the oracle against the LIVE reference (build container only)."""
+from collections import OrderedDict
+
 import pytest
 import torch
 
@@ -42,3 +44,35 @@ def test_reference_state_dict_keys_match_oracle_init():
     for k in sd:
         assert sd[k].shape == p[k].shape, k
         assert torch.equal(sd[k], p[k]), k
+
+
+def test_oracle_train_iteration_equals_reference_loop():
+    """main.py:418-583 on the live reference (model forward, loss, backward, clip_grad_norm_, SGD-Nesterov step,
+    DANN learning-rate schedule) against oracle.train_iteration, three iterations."""
+    from torch.nn.utils import clip_grad_norm_
+    c = gen_golden.CASES["cfg1_small_c5"]
+    model, _, _, _ = gen_golden.run_reference(c)
+    model.zero_grad(set_to_none=True)
+    cfg, xs, xt, labels, masks = gen_golden.case_inputs(c)
+    params = OrderedDict((k, v.detach().clone()) for k, v in model.state_dict().items())
+    bufs = {}
+    lr0 = 3e-2
+    opt = torch.optim.SGD(model.parameters(), lr0, momentum=0.9, weight_decay=1e-4, nesterov=True)   # main.py:83
+    for it in range(3):
+        p = it / 3.0
+        lr = orc.lr_dann(lr0, p)
+        for gparam in opt.param_groups:
+            gparam["lr"] = lr0 / (1. + 10 * p) ** 0.75                                              # main.py:800-802
+        outs = model(xs, xt, list(gen_golden.BETA), 0, is_train=True, reverse=False)
+        loss_ref = gen_golden.reference_loss(outs, labels)
+        opt.zero_grad()
+        loss_ref.backward()
+        norm_ref = clip_grad_norm_(model.parameters(), 0.05)      # small max_norm so that clipping is active
+        opt.step()
+        loss, total = orc.train_iteration(params, bufs, xs, xt, labels, gen_golden.BETA, cfg, lr, gen_golden.GAMMA,
+                                          clip_gradient=0.05, train=c["train"], masks=masks)
+        assert_close(loss, loss_ref.detach(), TOL_FP32, f"loss it{it}")
+        assert_close(total, norm_ref, 1e-5, f"total_norm it{it}")
+        assert float(norm_ref) > 0.05
+    for name, prm in model.named_parameters():
+        assert_close(params[name], prm.detach(), 1e-6, f"param {name}")
