@@ -252,7 +252,9 @@ def workload_config(args, world, engine):
                     + (" + flat NCCL gradient all-reduce" if world > 1 else ""),
             "optimizer": "excluded from value (metric is fwd+bwd); included in e2e",
             "dropout": "0.5/0.5, in-kernel counter RNG", "gemm_engine": engine,
-            "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) before every timed step"}
+            "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) before every timed step",
+            "timing": "CUDA events around each step on the launching stream; steps enqueued behind a 20 ms "
+                      "device-side spin so host launch gaps are outside the events"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -310,6 +312,10 @@ def run_b200(args):
     # ---- value: inputs resident in HBM, device-timed with CUDA events, L2 flushed before each step
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    # Park the GPU (~20 ms spin) while the host enqueues the first steps: the events then bracket device time
+    # only, not the gaps a busy host leaves between a flush and the following graph launch (observed on a shared
+    # box: 0.29 -> 0.38 ms/step with identical per-kernel times).
+    torch.cuda._sleep(int(20e-3 * 1.9e9))
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
         ev[k][0].record()
@@ -413,7 +419,11 @@ def run_b200(args):
     tm = traffic_model(M, T, F, C)
     step_ms = t_ms / args.steps
     total_site_ms = sum(ms for _, ms in rep.values()) or 1.0
-    dom = max((k for k in rep if k in tm["sites"]), key=lambda k: rep[k][1], default=None)
+    # dominant GEMM call site; sites within 3 % of the slowest are ranked by their algorithmic bytes (the merged
+    # weight-gradient launch and the forward batch are that close and would otherwise swap between runs)
+    cand = [k for k in rep if k in tm["sites"]]
+    t_max = max((rep[k][1] for k in cand), default=0.0)
+    dom = max((k for k in cand if rep[k][1] >= 0.97 * t_max), key=lambda k: tm["sites"][k], default=None)
     roof = None
     if dom:
         cnt, ms = rep[dom]

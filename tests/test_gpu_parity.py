@@ -479,13 +479,14 @@ def test_fused_step_stream_options_do_not_change_results():
 
 @pytest.mark.parametrize("n,max_norm", [(1000003, 0.5), (4096, 0.0), (7, 1e9)])
 def test_sgd_nesterov_kernel_matches_torch_optim(n, max_norm):
-    """ta3n_sgd_nesterov_step vs torch.optim.SGD(nesterov) + clip_grad_norm_ (main.py:83, 578-583) on flat
-    buffers, three steps with a changing learning rate; n deliberately not a multiple of 4."""
+    """ta3n_sgd_nesterov_step vs torch.optim.SGD(nesterov) + clip_grad_norm_ (main.py:83, 578-583) run in fp64 on
+    the same flat buffers, three steps with a changing learning rate; n deliberately not a multiple of 4.
+    (Against torch in fp32 the clip coefficient itself differs by ~1e-5: torch's fp32 norm of 1e6 elements.)"""
     from ta3n_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(n)
     p0 = torch.randn(n, generator=g)
-    ref = torch.nn.Parameter(p0.clone())
+    ref = torch.nn.Parameter(p0.double())
     opt = torch.optim.SGD([ref], 0.1, momentum=0.9, weight_decay=1e-3, nesterov=True)
     p = p0.to(_dev())
     m = torch.zeros(n, device=_dev())
@@ -497,8 +498,8 @@ def test_sgd_nesterov_kernel_matches_torch_optim(n, max_norm):
         lr_it = 0.1 / (1 + it)
         for grp in opt.param_groups:
             grp["lr"] = lr_it
-        ref.grad = grad.clone()
-        norm_ref = grad.norm()
+        ref.grad = grad.double()
+        norm_ref = grad.double().norm()
         if max_norm > 0:
             norm_ref = torch.nn.utils.clip_grad_norm_([ref], max_norm)
         opt.step()
@@ -509,21 +510,19 @@ def test_sgd_nesterov_kernel_matches_torch_optim(n, max_norm):
                                               torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         if max_norm > 0:
-            # torch's fp32 vector norm itself carries ~1e-5 of accumulation error at 1e6 elements; the kernel's
-            # two-stage fixed-order sum is held to the fp64 value
-            assert_close(stats[0].cpu(), norm_ref, 5e-5, "total norm vs torch fp32")
-            assert_close(stats[0].cpu(), grad.double().norm(), 2e-6, "total norm vs fp64")
-            assert abs(float(stats[1]) - min(1.0, max_norm / (float(norm_ref) + 1e-6))) < 5e-5
+            assert_close(stats[0].cpu(), norm_ref, 2e-6, "total norm")
+            assert abs(float(stats[1]) - min(1.0, max_norm / (float(norm_ref) + 1e-6))) < 1e-6 * max(1.0, float(stats[1]))
     assert_close(p.cpu(), ref.detach(), 1e-6, "parameters after 3 steps")
     assert_close(m.cpu(), opt.state[ref]["momentum_buffer"], 1e-6, "momentum buffer")
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
-@pytest.mark.parametrize("clip", [0.02, None])
+@pytest.mark.parametrize("clip", [10.0, None])
 def test_fused_train_iteration_matches_oracle(clip, use_graph, engine):
     """TrainStep(optimizer=SGDNesterov) = main.py:418-583 (forward, loss, backward, clip_grad_norm_, SGD-Nesterov
     step, DANN learning rate): three iterations against oracle.train_iteration (fp64), compared on the parameter
-    UPDATES.  C=5 and ragged batches make the flat-buffer slots unaligned before padding."""
+    UPDATES.  C=5 and ragged batches make the flat-buffer slots unaligned before padding.  The gradient norm is
+    ~32, 15, 12 over the three iterations, so clip=10 is active throughout."""
     from ta3n_b200.train import SGDNesterov, TrainStep, lr_dann
     cfg = orc.PathConfig(num_class=5, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0)
     params = orc.init_params(cfg, seed=33)
@@ -535,7 +534,8 @@ def test_fused_train_iteration_matches_oracle(clip, use_graph, engine):
     xs = torch.randn(bs, 5, orc.FEATURE_DIM, generator=g)
     xt = torch.randn(bt, 5, orc.FEATURE_DIM, generator=g) - 0.2
     labels = torch.arange(bs) % 5
-    beta, lr0 = (0.75, 0.75, 0.5), 0.05
+    beta, lr0 = (0.75, 0.75, 0.5), 0.002
+    _, _, _, _, _, n_grad = oracle_truth(params, xs, xt, labels, beta, cfg, 0.003, True, None)
     model = build_model(cfg, params, train=True)
     step = TrainStep(model, bs, bt, beta, gamma=0.003, use_graph=use_graph,
                      optimizer=SGDNesterov(lr=lr0, momentum=0.9, weight_decay=1e-4, clip_gradient=clip))
@@ -549,15 +549,19 @@ def test_fused_train_iteration_matches_oracle(clip, use_graph, engine):
         loss_o, total_o = orc.train_iteration(p64, bufs, xs.double(), xt.double(), labels, beta, cfg, lr, 0.003,
                                               clip_gradient=clip, train=True)
         torch.cuda.synchronize()
-        assert_close(loss.cpu()[0], loss_o, 20 * TOL[engine], f"loss at iteration {it}")
+        assert_close(loss.cpu()[0], loss_o, (1 + 10 * it) * TOL[engine], f"loss at iteration {it}")
         if clip is not None:
             assert float(total_o) > clip                      # clipping is active in this test
+            assert float(step.grad_stats[1]) < 1.0
             assert_close(step.grad_stats[0].cpu(), total_o, GRAD_TOL[engine], f"gradient norm at iteration {it}")
     named = dict(model.named_parameters())
     for name in orc.used_param_names(params):
         delta = named[name].detach().cpu().double() - params[name].double()
         delta_o = p64[name] - params[name].double()
-        assert_close(delta, delta_o, max(GRAD_TOL[engine], 2e-3), f"update of {name}")
+        # noise floors: fp32 storage of the parameter (3 roundings at eps * |p|) and the cancellation noise of
+        # the bias gradients of the domain heads (oracle fp32 vs fp64), carried through lr * (1 + momentum terms)
+        noise = 3 * 6e-8 * params[name].double().norm().item() + 6 * lr0 * n_grad[name] * NOISE_SCALE[engine]
+        assert_close(delta, delta_o, max(GRAD_TOL[engine], 1e-3), f"update of {name}", noise=noise)
     # parameters the path never uses are not touched (SGD skips grad=None)
     assert torch.equal(model.fc_feature_source.weight.detach().cpu(), params["fc_feature_source.weight"])
 

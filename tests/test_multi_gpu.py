@@ -1,5 +1,6 @@
 """Data-parallel TrainStep on 2 GPUs (NCCL): the averaged shard gradients equal the single-GPU gradients of
-the global batch.  Needs >= 2 CUDA devices; skipped on single-GPU boxes."""
+the global batch, and with an optimizer configured every rank applies the update of the global batch (the
+reference's nn.DataParallel semantics, main.py:79, 576-583).  Needs >= 2 CUDA devices; skipped otherwise."""
 import os
 import socket
 
@@ -43,7 +44,7 @@ def _worker(rank, world, port, q):
     try:
         import ta3n_b200
         from ta3n_b200.parallel import shard_rows
-        from ta3n_b200.train import TrainStep
+        from ta3n_b200.train import SGDNesterov, TrainStep
         ta3n_b200.set_gemm_engine("fp32")          # exact engine: the comparison below is about the collective
         xs, xt, labels = orc.synthetic_batch(world * B_LOCAL, _cfg())
         sl = shard_rows(world * B_LOCAL, rank, world)
@@ -55,13 +56,26 @@ def _worker(rank, world, port, q):
         torch.cuda.synchronize()
         if rank == 0:
             q.put(step.flat_grad.cpu().numpy())
+        # the same with the fused optimizer: 3 iterations, then all ranks must hold identical parameters
+        model2 = _build(dev)
+        opt_step = TrainStep(model2, B_LOCAL, B_LOCAL, (0.75, 0.75, 0.5), gamma=0.0, use_graph=True,
+                             optimizer=SGDNesterov(lr=0.05, clip_gradient=0.02))
+        for _ in range(3):
+            opt_step(xs[sl], xt[sl], labels[sl])
+        torch.cuda.synchronize()
+        mine = opt_step.flat_param.clone()
+        other = mine.clone()
+        dist.broadcast(other, src=0)
+        assert torch.equal(mine, other), "ranks diverged after the optimizer step"
+        if rank == 0:
+            q.put(opt_step.flat_param.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
 
 def test_two_gpu_trainstep_matches_global_batch():
     import ta3n_b200
-    from ta3n_b200.train import TrainStep
+    from ta3n_b200.train import SGDNesterov, TrainStep, flatten_parameters
     ta3n_b200.set_gemm_engine("fp32")
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
@@ -70,6 +84,7 @@ def test_two_gpu_trainstep_matches_global_batch():
     for p in procs:
         p.start()
     got = torch.from_numpy(q.get(timeout=300))
+    got_param = torch.from_numpy(q.get(timeout=300))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -84,3 +99,16 @@ def test_two_gpu_trainstep_matches_global_batch():
     want = ref.flat_grad.cpu()
     err = ((got.double() - want.double()).norm() / want.double().norm()).item()
     assert err < 1e-4, err          # fp32 summation order only
+    # optimizer: 3 iterations on the global batch on one GPU == 3 data-parallel iterations
+    model2 = _build(dev)
+    p0 = flatten_parameters(model2).clone()                    # initial values in bucket order
+    ref2 = TrainStep(model2, world * B_LOCAL, world * B_LOCAL, (0.75, 0.75, 0.5), gamma=0.0, use_graph=True,
+                     overlap_allreduce=True, optimizer=SGDNesterov(lr=0.05, clip_gradient=0.02))
+    for _ in range(3):
+        ref2(xs, xt, labels)
+    torch.cuda.synchronize()
+    assert float(ref2.grad_stats[1]) < 1.0                      # clipping was active
+    want_delta = (ref2.flat_param - p0).double().cpu()
+    got_delta = got_param.double() - p0.double().cpu()
+    err = ((got_delta - want_delta).norm() / want_delta.norm()).item()
+    assert err < 1e-3, err
