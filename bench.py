@@ -339,17 +339,28 @@ def run_b200(args):
                      optimizer=SGDNesterov(lr=3e-2, momentum=0.9, weight_decay=1e-4, clip_gradient=20.0))
     host_batches = [(xs_h, xt_h, lab_h), (xt_h, xs_h, lab_h)]      # two distinct pinned batches, alternated
 
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_loop(n):
+        """Every step: H2D of its inputs (prefetched one step ahead), the fused iteration, D2H of its loss.  The
+        host reads the loss of step k-1 while step k runs (as a logging training loop does), so a slow host
+        does not drain the device queue."""
         pipe.prefetch(*host_batches[0])
         last = None
         for k in range(n):
             pipe.swap()                                   # consume the prefetched slot
             pipe.prefetch(*host_batches[(k + 1) & 1])     # H2D of the next step's inputs, overlapped
             loss = pipe.run()                             # fwd + loss + bwd (+ all-reduce) + clip + SGD step
-            last = loss.item()                            # D2H read of this step's result
-        return last
+            loss_host[k & 1].copy_(loss, non_blocking=True)      # D2H of this step's result
+            loss_ready[k & 1].record()
+            if k > 0:
+                loss_ready[(k - 1) & 1].synchronize()
+                last = float(loss_host[(k - 1) & 1][0])
+        loss_ready[(n - 1) & 1].synchronize()
+        return float(loss_host[(n - 1) & 1][0]) if n > 0 else last
 
-    e2e_loop(3)
+    e2e_loop(6)
     barrier()
     t0 = time.perf_counter()
     e2e_loop(args.steps)
@@ -461,7 +472,7 @@ def run_b200(args):
                 "optimizer_launches_per_step": 2,
                 "includes": "H2D of every step's inputs (pinned host -> device, prefetched one step ahead on a "
                 "copy stream), forward, loss, backward, all-reduce, clip_grad_norm + SGD-Nesterov step (fused "
-                "kernels of this library), D2H of the loss"},
+                "kernels of this library), D2H of every step's loss (read by the host one step behind)"},
         "gpu_launches": int(launches), "launches_per_step": int(step.launches_per_step),
         "cuda_graph": not args.no_graph, "autograd_api_ms_per_step": autograd_ms, "clocks": clocks,
     }
