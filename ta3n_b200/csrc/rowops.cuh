@@ -66,6 +66,52 @@ __global__ void __launch_bounds__(256) dz_kernel(const float* __restrict__ act, 
   }
 }
 
+// ---- 16-byte variants of the two kernels above (H % 4 == 0, 16 B aligned buffers, < 2^31 float4s): one thread
+// per 4 consecutive h shares the index arithmetic (32-bit), and the relation tables are read from shared
+// memory -- run-time indexed kernel parameters are ~300-cycle generic loads on the critical path.
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__global__ void __launch_bounds__(256) relsum_v4_kernel(const float4* __restrict__ act, float4* __restrict__ feat_rel,
+                                                        int M, int H4, const __grid_constant__ RelMap map) {
+  __shared__ int rb[kMaxScales + 1];
+  const int R = map.n_scales;
+  if (threadIdx.x <= R) rb[threadIdx.x] = map.rel_begin[threadIdx.x];
+  __syncthreads();
+  pdl_wait();
+  const unsigned total = (unsigned)M * R * H4, plane = (unsigned)M * H4;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const unsigned mi = e / H4, h = e - mi * H4;
+    const unsigned m = mi / R, i = mi - m * R;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = rb[i]; q < rb[i + 1]; ++q) {
+      const float4 a = act[q * plane + m * H4 + h];
+      s.x += a.x;
+      s.y += a.y;
+      s.z += a.z;
+      s.w += a.w;
+    }
+    feat_rel[e] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) dz_v4_kernel(const float4* __restrict__ act, const float4* __restrict__ d_feat_rel,
+                                                    float4* __restrict__ dz, int M, int H4,
+                                                    const __grid_constant__ RelMap map) {
+  __shared__ unsigned char so[kMaxRel];
+  for (int q = threadIdx.x; q < map.n_rel; q += blockDim.x) so[q] = map.scale_of[q];
+  __syncthreads();
+  pdl_wait();
+  const unsigned R = map.n_scales;
+  const unsigned plane = (unsigned)M * H4, total = plane * map.n_rel;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const unsigned q = e / plane, mh = e - q * plane;
+    const unsigned m = mh / H4, h = mh - m * H4;
+    const float4 a = act[e];
+    const float4 g = d_feat_rel[(m * R + so[q]) * H4 + h];
+    dz[e] = make_float4(a.x > 0.f ? g.x : 0.f, a.y > 0.f ? g.y : 0.f, a.z > 0.f ? g.z : 0.f, a.w > 0.f ? g.w : 0.f);
+  }
+}
+
 // ---- dropout helpers -----------------------------------------------------------------------------
 struct DropArgs {
   float p, scale;
@@ -184,6 +230,60 @@ __global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restr
     s *= alpha;
     if (gate && !(gate[e] > 0.f)) s = 0.f;
     out[e] = accumulate ? out[e] + s : s;
+  }
+}
+
+// 16-byte variant (K % 4 == 0, aligned buffers, rows*K/4 < 2^31, N2 <= 32)
+__global__ void __launch_bounds__(256) head_bwd_data_v4_kernel(const float* __restrict__ g, int N2,
+                                                               const float4* __restrict__ W,
+                                                               const float4* __restrict__ gate, float alpha,
+                                                               int accumulate, float4* __restrict__ out, int rows,
+                                                               int K4) {
+  pdl_wait();
+  const unsigned total = (unsigned)rows * K4;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const unsigned row = e / K4, k = e - row * K4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = 0; n < N2; ++n) {
+      const float gv = g[row * N2 + n];
+      const float4 w = __ldg(W + (size_t)n * K4 + k);
+      s.x = fmaf(gv, w.x, s.x);
+      s.y = fmaf(gv, w.y, s.y);
+      s.z = fmaf(gv, w.z, s.z);
+      s.w = fmaf(gv, w.w, s.w);
+    }
+    s.x *= alpha;
+    s.y *= alpha;
+    s.z *= alpha;
+    s.w *= alpha;
+    if (gate) {
+      const float4 t = gate[e];
+      if (!(t.x > 0.f)) s.x = 0.f;
+      if (!(t.y > 0.f)) s.y = 0.f;
+      if (!(t.z > 0.f)) s.z = 0.f;
+      if (!(t.w > 0.f)) s.w = 0.f;
+    }
+    if (accumulate) {
+      const float4 o = out[e];
+      s.x += o.x;
+      s.y += o.y;
+      s.z += o.z;
+      s.w += o.w;
+    }
+    out[e] = s;
+  }
+}
+
+inline void launch_head_bwd_data(const float* g, int N2, const float* W, const float* gate, float alpha, int accumulate,
+                                 float* out, int rows, int K, cudaStream_t st) {
+  const size_t total = (size_t)rows * K;
+  if (K % 4 == 0 && aligned16(W) && aligned16(out) && (!gate || aligned16(gate)) && total / 4 < (1ull << 31)) {
+    launch_kernel(head_bwd_data_v4_kernel, blocks_for(total / 4, 256), 256, 0, st, g, N2,
+                  reinterpret_cast<const float4*>(W), reinterpret_cast<const float4*>(gate), alpha, accumulate,
+                  reinterpret_cast<float4*>(out), rows, K / 4);
+  } else {
+    launch_kernel(head_bwd_data_kernel, blocks_for(total, 256), 256, 0, st, g, N2, W, gate, alpha, accumulate, out,
+                  rows, K);
   }
 }
 
@@ -348,6 +448,34 @@ __global__ void __launch_bounds__(256) dpre_kernel(const float* __restrict__ fea
   }
 }
 
+__global__ void __launch_bounds__(256) dpre_v4_kernel(const float4* __restrict__ feat, float4* __restrict__ d_feat,
+                                                      const float4* __restrict__ g_ext, float scale, unsigned total4) {
+  pdl_wait();
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += gridDim.x * blockDim.x) {
+    float4 g = d_feat[e];
+    if (g_ext) {
+      const float4 x = g_ext[e];
+      g.x += x.x;
+      g.y += x.y;
+      g.z += x.z;
+      g.w += x.w;
+    }
+    const float4 f = feat[e];
+    d_feat[e] = make_float4(f.x > 0.f ? g.x * scale : 0.f, f.y > 0.f ? g.y * scale : 0.f,
+                            f.z > 0.f ? g.z * scale : 0.f, f.w > 0.f ? g.w * scale : 0.f);
+  }
+}
+
+inline void launch_dpre(const float* feat, float* d_feat, const float* g_ext, float scale, size_t total, cudaStream_t st) {
+  if (total % 4 == 0 && aligned16(feat) && aligned16(d_feat) && (!g_ext || aligned16(g_ext)) && total / 4 < (1ull << 31)) {
+    launch_kernel(dpre_v4_kernel, blocks_for(total / 4, 256), 256, 0, st, reinterpret_cast<const float4*>(feat),
+                  reinterpret_cast<float4*>(d_feat), reinterpret_cast<const float4*>(g_ext), scale,
+                  (unsigned)(total / 4));
+  } else {
+    launch_kernel(dpre_kernel, blocks_for(total, 256), 256, 0, st, feat, d_feat, g_ext, scale, total);
+  }
+}
+
 __global__ void __launch_bounds__(256) grl_bwd_kernel(const float* __restrict__ g, float beta, float* __restrict__ out,
                                                       size_t n) {
   pdl_wait();
@@ -469,6 +597,8 @@ __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restri
   }
 }
 
+// The counter advances at the START of a step: the video head's backward re-derives its dropout mask from the
+// same counter value the forward used (rowops: video_head_bwd_kernel), so it must not move in between.
 __global__ void counter_inc_kernel(unsigned long long* ctr) {
   pdl_wait(); ctr[0] += 1ull; }
 
@@ -477,6 +607,9 @@ __global__ void counter_inc_kernel(unsigned long long* ctr) {
 // P == nullptr -> N2 = 1 with unit weights (a plain column sum = a bias gradient).  The N2 x N outputs of
 // the two-logit / C-logit heads (dW2 [2,H], dWc [C,H]) are tall-skinny reductions over the rows; as GEMM
 // tiles they would be 98 % padding.  Two stages (row splits -> fixed-order sum) keep it deterministic.
+// A block covers 128 columns x one row split: each thread owns 4 consecutive columns (one 16 B load per row,
+// a warp reads 512 contiguous bytes) and keeps 4 rows in flight; the 8 warps of the block take rows r, r+1, ..
+// The number of row splits is per job (tall inputs get more), so every block has 2-3 iterations of work.
 struct WColsumJob {
   const float* X[4];
   const float* P[4];
@@ -485,24 +618,46 @@ struct WColsumJob {
   int ld, ldp;
   int N, N2;
   int ldo;
+  int nsplit;       // row splits of this job (<= kWColsumMaxSplits)
+  int vec4;         // 1: N % 4 == 0, ld % 4 == 0 and every X 16-byte aligned -> float4 path
   float* out;
-  float* partial;   // [splits, N2, N]
+  float* partial;   // [nsplit, N2, N]
 };
 constexpr int kMaxWColsumJobs = 40;
-constexpr int kWColsumSplits = 16;
+constexpr int kWColsumMaxSplits = 32;
 struct WColsumTable {
   int n_jobs;
   WColsumJob job[kMaxWColsumJobs];
 };
 
-// stage 1: grid (ceil(maxN/32), n_jobs, splits), block (32, 8)
-template <int KMAX>
-__device__ __forceinline__ void wcolsum_body(const WColsumJob& j, float (*red)[33]) {
-  const int n = blockIdx.x * 32 + threadIdx.x;
-  const int split = blockIdx.z, nsplit = gridDim.z;
-  float acc[KMAX];
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_fma(float4& a, float p, const float4& x) {
+  a.x = fmaf(p, x.x, a.x);
+  a.y = fmaf(p, x.y, a.y);
+  a.z = fmaf(p, x.z, a.z);
+  a.w = fmaf(p, x.w, a.w);
+}
+
+// stage 1: grid (ceil(maxN/128), n_jobs, max splits), block (32, 8)
+// One pass handles the weight columns k0 .. k0+KMAX-1 (KMAX <= 4 keeps the kernel at ~64 registers; the C-logit
+// classifier head takes ceil(C/4) passes over its small, L2-resident input).
+template <int KMAX, bool VEC>
+__device__ __forceinline__ void wcolsum_body(const WColsumJob& j, float4 (*red)[33], const int k0) {
+  const int n = blockIdx.x * 128 + threadIdx.x * 4;
+  const int split = blockIdx.z, nsplit = j.nsplit;
+  float4 acc[KMAX];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  for (int k = 0; k < KMAX; ++k) acc[k] = f4_zero();
+  auto ldx = [&](const float* X, int r) -> float4 {
+    const float* q = X + (size_t)r * j.ld + n;
+    if (VEC) return *reinterpret_cast<const float4*>(q);
+    float4 v = f4_zero();
+    if (n < j.N) v.x = q[0];
+    if (n + 1 < j.N) v.y = q[1];
+    if (n + 2 < j.N) v.z = q[2];
+    if (n + 3 < j.N) v.w = q[3];
+    return v;
+  };
   if (n < j.N) {
     for (int sg = 0; sg < j.nseg; ++sg) {
       const float* X = j.X[sg];
@@ -513,43 +668,62 @@ __device__ __forceinline__ void wcolsum_body(const WColsumJob& j, float (*red)[3
       int r = split * per + threadIdx.y;
       // four independent rows in flight per thread (the loads, not the adds, bound this kernel)
       for (; r + 24 < r1; r += 32) {
-        const float x0 = X[(size_t)r * j.ld + n], x1 = X[(size_t)(r + 8) * j.ld + n];
-        const float x2 = X[(size_t)(r + 16) * j.ld + n], x3 = X[(size_t)(r + 24) * j.ld + n];
+        const float4 x0 = ldx(X, r), x1 = ldx(X, r + 8), x2 = ldx(X, r + 16), x3 = ldx(X, r + 24);
         if (P == nullptr) {
-          acc[0] += (x0 + x1) + (x2 + x3);
+          acc[0].x += (x0.x + x1.x) + (x2.x + x3.x);
+          acc[0].y += (x0.y + x1.y) + (x2.y + x3.y);
+          acc[0].z += (x0.z + x1.z) + (x2.z + x3.z);
+          acc[0].w += (x0.w + x1.w) + (x2.w + x3.w);
         } else {
 #pragma unroll
           for (int k = 0; k < KMAX; ++k)
-            if (k < j.N2) {
-              acc[k] = fmaf(__ldg(P + (size_t)r * j.ldp + k), x0, acc[k]);
-              acc[k] = fmaf(__ldg(P + (size_t)(r + 8) * j.ldp + k), x1, acc[k]);
-              acc[k] = fmaf(__ldg(P + (size_t)(r + 16) * j.ldp + k), x2, acc[k]);
-              acc[k] = fmaf(__ldg(P + (size_t)(r + 24) * j.ldp + k), x3, acc[k]);
+            if (k0 + k < j.N2) {
+              f4_fma(acc[k], __ldg(P + (size_t)r * j.ldp + k0 + k), x0);
+              f4_fma(acc[k], __ldg(P + (size_t)(r + 8) * j.ldp + k0 + k), x1);
+              f4_fma(acc[k], __ldg(P + (size_t)(r + 16) * j.ldp + k0 + k), x2);
+              f4_fma(acc[k], __ldg(P + (size_t)(r + 24) * j.ldp + k0 + k), x3);
             }
         }
       }
       for (; r < r1; r += 8) {
-        const float x = X[(size_t)r * j.ld + n];
+        const float4 x = ldx(X, r);
         if (P == nullptr) {
-          acc[0] += x;
+          acc[0].x += x.x;
+          acc[0].y += x.y;
+          acc[0].z += x.z;
+          acc[0].w += x.w;
         } else {
 #pragma unroll
           for (int k = 0; k < KMAX; ++k)
-            if (k < j.N2) acc[k] = fmaf(__ldg(P + (size_t)r * j.ldp + k), x, acc[k]);
+            if (k0 + k < j.N2) f4_fma(acc[k], __ldg(P + (size_t)r * j.ldp + k0 + k), x);
         }
       }
     }
   }
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
-    if (k >= j.N2) break;
+    if (k0 + k >= j.N2) break;
     red[threadIdx.y][threadIdx.x] = acc[k];
     __syncthreads();
     if (threadIdx.y == 0 && n < j.N) {
-      float t = 0.f;
+      float4 t = f4_zero();
 #pragma unroll
-      for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
-      j.partial[((size_t)split * j.N2 + k) * j.N + n] = t;
+      for (int y = 0; y < 8; ++y) {
+        const float4 v = red[y][threadIdx.x];
+        t.x += v.x;
+        t.y += v.y;
+        t.z += v.z;
+        t.w += v.w;
+      }
+      float* o = j.partial + ((size_t)split * j.N2 + k0 + k) * j.N + n;
+      if (VEC) {
+        *reinterpret_cast<float4*>(o) = t;      // partial rows are 16 B aligned when N % 4 == 0
+      } else {
+        o[0] = t.x;
+        if (n + 1 < j.N) o[1] = t.y;
+        if (n + 2 < j.N) o[2] = t.z;
+        if (n + 3 < j.N) o[3] = t.w;
+      }
     }
     __syncthreads();
   }
@@ -557,7 +731,7 @@ __device__ __forceinline__ void wcolsum_body(const WColsumJob& j, float (*red)[3
 
 __global__ void __launch_bounds__(256) wcolsum_stage1_kernel(const __grid_constant__ WColsumTable tab) {
   pdl_wait();
-  __shared__ float red[8][33];
+  __shared__ float4 red[8][33];
   __shared__ WColsumJob j;   // staged: run-time indexed kernel parameters are slow generic loads
   {
     const int* src = reinterpret_cast<const int*>(&tab.job[blockIdx.y]);
@@ -566,19 +740,28 @@ __global__ void __launch_bounds__(256) wcolsum_stage1_kernel(const __grid_consta
     if (t < (int)(sizeof(WColsumJob) / sizeof(int))) dst[t] = src[t];
     __syncthreads();
   }
-  if (blockIdx.x * 32 >= j.N) return;
-  if (j.N2 <= 1)
-    wcolsum_body<1>(j, red);
-  else if (j.N2 <= 2)
-    wcolsum_body<2>(j, red);
-  else if (j.N2 <= 16)
-    wcolsum_body<16>(j, red);
-  else
-    wcolsum_body<32>(j, red);
+  if (blockIdx.x * 128 >= j.N || (int)blockIdx.z >= j.nsplit) return;
+  if (j.vec4) {
+    if (j.N2 <= 1) {
+      wcolsum_body<1, true>(j, red, 0);
+    } else if (j.N2 <= 2) {
+      wcolsum_body<2, true>(j, red, 0);
+    } else {
+      for (int k0 = 0; k0 < j.N2; k0 += 4) wcolsum_body<4, true>(j, red, k0);
+    }
+  } else {
+    if (j.N2 <= 1) {
+      wcolsum_body<1, false>(j, red, 0);
+    } else if (j.N2 <= 2) {
+      wcolsum_body<2, false>(j, red, 0);
+    } else {
+      for (int k0 = 0; k0 < j.N2; k0 += 4) wcolsum_body<4, false>(j, red, k0);
+    }
+  }
 }
 
 // stage 2: out[k, n] = sum_split partial[split, k, n]; grid (blocks, n_jobs)
-__global__ void __launch_bounds__(256) wcolsum_stage2_kernel(const __grid_constant__ WColsumTable tab, int nsplit) {
+__global__ void __launch_bounds__(256) wcolsum_stage2_kernel(const __grid_constant__ WColsumTable tab) {
   pdl_wait();
   __shared__ WColsumJob j;
   {
@@ -590,7 +773,7 @@ __global__ void __launch_bounds__(256) wcolsum_stage2_kernel(const __grid_consta
   const int total = j.N2 * j.N;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     float s = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) s += j.partial[(size_t)sp * total + e];
+    for (int sp = 0; sp < j.nsplit; ++sp) s += j.partial[(size_t)sp * total + e];
     j.out[(size_t)(e / j.N) * j.ldo + (e % j.N)] = s;
   }
 }
@@ -626,15 +809,15 @@ struct ColsumPlan {
     j.nseg++;
   }
   static size_t workspace_bytes(size_t total_out_elems) {
-    return Arena::round(total_out_elems * kWColsumSplits * sizeof(float)) + 256 * (size_t)kMaxWColsumJobs;
+    return Arena::round(total_out_elems * kWColsumMaxSplits * sizeof(float)) + 256 * (size_t)kMaxWColsumJobs;
   }
-  // Needs arena space for the stage-1 partials (kWColsumSplits x outputs).
+  // Needs arena space for the stage-1 partials (row splits x outputs).
   int run(cudaStream_t stream, Arena* arena) {
     size_t i = 0;
     while (i < jobs.size()) {
       WColsumTable tab;
       tab.n_jobs = 0;
-      int maxN = 0, maxOut = 0;
+      int maxN = 0, maxOut = 0, maxSplit = 1;
       while (i < jobs.size() && tab.n_jobs < kMaxWColsumJobs) {
         WColsumJob j = jobs[i];
         if (j.nseg == 0) {   // nothing to sum: the gradient is zero
@@ -643,21 +826,31 @@ struct ColsumPlan {
           ++i;
           continue;
         }
-        j.partial = arena ? arena->floats((size_t)kWColsumSplits * j.N2 * j.N) : nullptr;
+        // row splits: ~64 rows of the tallest segment per block (8 rows per thread), 4 ... 32
+        int tall = 0;
+        bool vec = (j.N % 4 == 0) && (j.ld % 4 == 0);
+        for (int q = 0; q < j.nseg; ++q) {
+          if (j.rows[q] > tall) tall = j.rows[q];
+          if (reinterpret_cast<uintptr_t>(j.X[q]) & 15u) vec = false;
+        }
+        j.nsplit = std::min(kWColsumMaxSplits, std::max(4, (tall * j.nseg + 63) / 64));
+        j.vec4 = vec ? 1 : 0;
+        j.partial = arena ? arena->floats((size_t)j.nsplit * j.N2 * j.N) : nullptr;
         if (!j.partial) return fail(TA3N_ERR_WORKSPACE, "column-sum workspace too small");
+        if (j.nsplit > maxSplit) maxSplit = j.nsplit;
         tab.job[tab.n_jobs++] = j;
         if (j.N > maxN) maxN = j.N;
         if (j.N * j.N2 > maxOut) maxOut = j.N * j.N2;
         ++i;
       }
       if (tab.n_jobs == 0) continue;
-      dim3 grid((maxN + 31) / 32, tab.n_jobs, kWColsumSplits), block(32, 8);
+      dim3 grid((maxN + 127) / 128, tab.n_jobs, maxSplit), block(32, 8);
       pre_launch("wcolsum", stream);
       launch_kernel(wcolsum_stage1_kernel, grid, block, 0, stream, tab);
       TA3N_TRY(after_launch());
       dim3 grid2((maxOut + 255) / 256, tab.n_jobs);
       pre_launch("wcolsum_reduce", stream);
-      launch_kernel(wcolsum_stage2_kernel, grid2, 256, 0, stream, tab, kWColsumSplits);
+      launch_kernel(wcolsum_stage2_kernel, grid2, 256, 0, stream, tab);
       TA3N_TRY(after_launch());
     }
     return TA3N_OK;

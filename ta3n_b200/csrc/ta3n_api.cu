@@ -194,7 +194,7 @@ int ta3n_wgrad_defer_begin(void) {
   return TA3N_OK;
 }
 
-size_t ta3n_wgrad_defer_workspace_bytes(void) { return splitk_bytes(64) + colsum_bytes((size_t)1 << 20); }
+size_t ta3n_wgrad_defer_workspace_bytes(void) { return splitk_bytes(64) + colsum_bytes((size_t)1 << 18); }
 
 int ta3n_wgrad_defer_flush(void* workspace, size_t workspace_bytes, ta3n_stream_t stream) {
   DeferCtx& d = defer_ctx();
@@ -313,7 +313,7 @@ int ta3n_shared_fc_bwd(const float* x_src, int rows_src, const float* x_tgt, int
   }
   const size_t total = (size_t)rows * F;
   pre_launch("dpre", S(stream));
-  launch_kernel(dpre_kernel, blocks_for(total, 256), 256, 0, S(stream), feat, dfeat, g_feat_ext, 1.0f / (1.0f - p), total);
+  launch_dpre(feat, dfeat, g_feat_ext, 1.0f / (1.0f - p), total, S(stream));
   TA3N_TRY(after_launch());
 
   Arena arena(workspace, workspace_bytes);
@@ -378,8 +378,7 @@ int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, cons
 
   // dH = (g_logits W2) * 1[hidden > 0]
   pre_launch("head_bwd_data", st);
-  launch_kernel(head_bwd_data_kernel, blocks_for((size_t)rows * Kh, 256), 256, 0, st, g_logits, 2, W2, hidden, 1.0f, 0, dH,
-                                                                           rows, Kh);
+  launch_head_bwd_data(g_logits, 2, W2, hidden, 1.0f, 0, dH, rows, Kh, st);
   TA3N_TRY(after_launch());
 
   {  // dW2 [2,Kh] = g_logits^T hidden (skinny: weighted column sum), db2, db1
@@ -475,9 +474,14 @@ int ta3n_trn_fwd(const float* x, int M, int F, int H, const ta3n_relation_table*
   }
   const RelMap map = make_relmap(L);
   const int R = L.R;
+  const size_t act_f4 = (size_t)M * L.n_rel * (H / 4);      // the largest float4 index the kernel forms
   return submit_fwd(plan, S(stream), [=](cudaStream_t st) -> int {
     pre_launch("relsum", st);
-    launch_kernel(relsum_kernel, blocks_for((size_t)M * R * H, 256), 256, 0, st, act, feat_rel, M, H, map);
+    if (H % 4 == 0 && aligned16(act) && aligned16(feat_rel) && act_f4 < (1ull << 31))
+      launch_kernel(relsum_v4_kernel, blocks_for((size_t)M * R * (H / 4), 256), 256, 0, st,
+                    reinterpret_cast<const float4*>(act), reinterpret_cast<float4*>(feat_rel), M, H / 4, map);
+    else
+      launch_kernel(relsum_kernel, blocks_for((size_t)M * R * H, 256), 256, 0, st, act, feat_rel, M, H, map);
     return after_launch();
   });
 }
@@ -515,7 +519,11 @@ int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table*
 
   const RelMap map = make_relmap(L);
   pre_launch("dz", st);
-  launch_kernel(dz_kernel, blocks_for(plane * L.n_rel, 256), 256, 0, st, act, d_feat_rel, dz, M, H, map);
+  if (H % 4 == 0 && aligned16(act) && aligned16(d_feat_rel) && aligned16(dz) && plane * L.n_rel / 4 < (1ull << 31))
+    launch_kernel(dz_v4_kernel, blocks_for(plane * L.n_rel / 4, 256), 256, 0, st, reinterpret_cast<const float4*>(act),
+                  reinterpret_cast<const float4*>(d_feat_rel), reinterpret_cast<float4*>(dz), M, H / 4, map);
+  else
+    launch_kernel(dz_kernel, blocks_for(plane * L.n_rel, 256), 256, 0, st, act, d_feat_rel, dz, M, H, map);
   TA3N_TRY(after_launch());
 
   {  // wgrad: dW_i[:, jF:(j+1)F] = sum_r dz_{i,r}^T x[:, tau_{i,r}[j], :]
