@@ -173,14 +173,21 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__
             x_out[e] = xv[i];
           }
       }
-      for (int n = 0; n < N2; ++n) {
-        const float* wr = Wp + (size_t)n * K;
-        float s = 0.f;
+      // Logits in chunks of 32: lane n ends up holding logit n0 + n, the bias is read once per chunk, not per
+      // logit (a dependent L2 round trip inside the loop was the longest part of the C-logit head)
+      for (int n0 = 0; n0 < N2; n0 += 32) {
+        const int nn = min(32, N2 - n0);
+        float res = (b && lane < nn) ? b[n0 + lane] : 0.f;
+        for (int n = 0; n < nn; ++n) {
+          const float* wr = Wp + (size_t)(n0 + n) * K;
+          float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < kHeadMaxK / 32; ++i)
-          if (lane + 32 * i < K) s = fmaf(xv[i], wr[lane + 32 * i], s);
-        s = warp_sum(s);
-        if (lane == 0) out[(size_t)row * ldo + n] = s + (b ? b[n] : 0.f);
+          for (int i = 0; i < kHeadMaxK / 32; ++i)
+            if (lane + 32 * i < K) s = fmaf(xv[i], wr[lane + 32 * i], s);
+          s = warp_sum(s);
+          if (lane == n) res += s;
+        }
+        if (lane < nn) out[(size_t)row * ldo + n0 + lane] = res;
       }
     } else {   // very wide rows (fc_dim >= 2048): stream x from L1/L2
       if (x_out) {
@@ -760,7 +767,9 @@ __global__ void __launch_bounds__(256) wcolsum_stage1_kernel(const __grid_consta
   }
 }
 
-// stage 2: out[k, n] = sum_split partial[split, k, n]; grid (blocks, n_jobs)
+// stage 2: out[k, n] = sum_split partial[split, k, n]; grid (blocks, n_jobs), one thread per output, eight
+// splits in flight per thread in a fixed order (one dependent load per split was 10 us at 32 splits; a warp per
+// output with a shuffle tree was slower still: 9600 mostly idle blocks each staging its job).
 __global__ void __launch_bounds__(256) wcolsum_stage2_kernel(const __grid_constant__ WColsumTable tab) {
   pdl_wait();
   __shared__ WColsumJob j;
@@ -771,9 +780,18 @@ __global__ void __launch_bounds__(256) wcolsum_stage2_kernel(const __grid_consta
     __syncthreads();
   }
   const int total = j.N2 * j.N;
+  const int nsplit = j.nsplit;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const float* p = j.partial + e;
     float s = 0.f;
-    for (int sp = 0; sp < j.nsplit; ++sp) s += j.partial[(size_t)sp * total + e];
+    int sp = 0;
+    for (; sp + 8 <= nsplit; sp += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = p[(size_t)(sp + i) * total];
+      s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    for (; sp < nsplit; ++sp) s += p[(size_t)sp * total];
     j.out[(size_t)(e / j.N) * j.ldo + (e % j.N)] = s;
   }
 }

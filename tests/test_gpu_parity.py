@@ -416,7 +416,8 @@ def test_cpu_tensors_are_moved_not_computed_on_cpu():
 # fused loss heads and the fused / graph-captured training step
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("use_graph", [False, True])
-@pytest.mark.parametrize("T,attn_frame,bs,bt,C", [(5, "none", 24, 24, 12), (4, "TransAttn", 9, 5, 30)])
+@pytest.mark.parametrize("T,attn_frame,bs,bt,C", [(5, "none", 24, 24, 12), (4, "TransAttn", 9, 5, 30),
+                                                   (3, "none", 60, 11, 51)])     # C > 32: chunked class head
 def test_fused_train_step_matches_oracle(T, attn_frame, bs, bt, C, use_graph, engine):
     """TrainStep (forward + fused loss heads + backward, no autograd) vs the fp64 oracle's
     loss and parameter gradients; dropout off so both see the same function."""
