@@ -64,6 +64,18 @@ def load():
     return ref_models, ref_trn, ref_loss
 
 
+def load_dataset():
+    """Return the reference's `dataset` module (dataset.py needs only the colorama stub)."""
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    load()                                   # installs the colorama stub and sys.path entry
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ta3n_reference_dataset", os.path.join(REFERENCE_ROOT, "dataset.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 import torch as _torch  # noqa: E402
 
 
