@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TA3N_ABI_VERSION 1
+#define TA3N_ABI_VERSION 2
 
 enum {
   TA3N_OK = 0,
@@ -201,11 +201,15 @@ int ta3n_wgrad_defer_flush(void* workspace, size_t workspace_bytes, ta3n_stream_
  * 0 = source rows, 1 = target rows), main.py:559-562 + loss.py:15-25 (gamma * attentive entropy).
  * flags: 1 relation-level adv, 2 video-level adv, 4 frame-level adv, 8 attentive entropy.
  * Inputs are the (Bs+Bt)-row outputs of the path; labels [Bs] int64.  Writes the scalar loss and
- * d loss / d logits of every head (zeros for disabled levels).                              */
+ * d loss / d logits of every head (zeros for disabled levels).
+ * valid_rows (device, optional): {real source rows, real target rows} when the batch is the
+ * zero-padded last one of an epoch (main.py:354-372 pads, main.py:421-422 slices the padding off
+ * before the loss): padded rows get zero loss / gradient, means run over the real rows only.   */
 size_t ta3n_loss_workspace_bytes(int M);
 int ta3n_loss_fwd_bwd(const float* pred_video, const long long* labels, const float* pred_rel,
                       const float* pred_dom_video, const float* pred_frame, int Bs, int Bt, int T,
-                      int R, int C, float gamma, int flags, float* loss, float* g_pred_video,
+                      int R, int C, float gamma, int flags, const int* valid_rows, float* loss,
+                      float* g_pred_video,
                       float* g_pred_rel, float* g_pred_dom_video, float* g_pred_frame,
                       void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
 /* *counter += 1 on the stream (dropout step counter for CUDA-graph replays). */

@@ -65,7 +65,7 @@ SIGNATURES = {
     "ta3n_wgrad_defer_workspace_bytes": (_SZ, []),
     "ta3n_wgrad_defer_flush": (_I, [_VP, _SZ, _VP]),
     "ta3n_loss_workspace_bytes": (_SZ, [_I]),
-    "ta3n_loss_fwd_bwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _F, _I, _VP, _VP, _VP, _VP, _VP,
+    "ta3n_loss_fwd_bwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _F, _I, _VP, _VP, _VP, _VP, _VP, _VP,
                                _VP, _SZ, _VP]),
     "ta3n_counter_inc": (_I, [_VP, _VP]),
     "ta3n_sgd_workspace_bytes": (_SZ, []),
@@ -103,7 +103,7 @@ def load() -> C.CDLL:
                 fn = getattr(lib, name)   # AttributeError if the .so does not export the symbol
                 fn.restype = res
                 fn.argtypes = args
-            if lib.ta3n_abi_version() != 1:
+            if lib.ta3n_abi_version() != 2:
                 raise Ta3nError("libta3n_sm100.so ABI version mismatch")
             _lib = lib
     return _lib

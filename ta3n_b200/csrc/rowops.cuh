@@ -501,13 +501,27 @@ __global__ void __launch_bounds__(256)
 loss_heads_kernel(const float* __restrict__ pred_video, const long long* __restrict__ labels,
                   const float* __restrict__ pred_rel, const float* __restrict__ pred_dom,
                   const float* __restrict__ pred_frame, int Bs, int M, int T, int R, int C, float gamma, int flags,
-                  float* __restrict__ g_video, float* __restrict__ g_rel, float* __restrict__ g_dom,
-                  float* __restrict__ g_frame, float* __restrict__ row_loss) {
+                  const int* __restrict__ valid_rows, float* __restrict__ g_video, float* __restrict__ g_rel,
+                  float* __restrict__ g_dom, float* __restrict__ g_frame, float* __restrict__ row_loss) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  // valid_rows = {real source rows, real target rows} of a zero-padded last mini-batch (main.py:354-372 pads,
+  // main.py:421-422 "ignore dummy tensors" slices the padding off again before any loss): padded rows get zero
+  // loss and zero gradient, and every mean runs over the real rows only.
+  const int vs = valid_rows ? min(valid_rows[0], Bs) : Bs;
+  const int vt = valid_rows ? min(valid_rows[1], M - Bs) : M - Bs;
+  const float n_src = (float)max(vs, 1), n_all = (float)max(vs + vt, 1);
   for (int m = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M; m += gridDim.x * warps_per_block) {
     const int dom = m >= Bs ? 1 : 0;
+    if (dom ? (m - Bs >= vt) : (m >= vs)) {   // padding row
+      for (int c = lane; c < C; c += 32) g_video[(size_t)m * C + c] = 0.f;
+      for (int i = lane; i < 2 * R; i += 32) g_rel[(size_t)m * R * 2 + i] = 0.f;
+      for (int t = lane; t < 2 * T; t += 32) g_frame[(size_t)m * T * 2 + t] = 0.f;
+      if (lane < 2) g_dom[(size_t)m * 2 + lane] = 0.f;
+      if (lane == 0) row_loss[m] = 0.f;
+      continue;
+    }
     float loss = 0.f;
     // class logits: softmax statistics over C
     const float* pv = pred_video + (size_t)m * C;
@@ -528,25 +542,25 @@ loss_heads_kernel(const float* __restrict__ pred_video, const long long* __restr
     // video-level domain logits
     const Attn2 dv = attn_from_logits(pred_dom[(size_t)m * 2], pred_dom[(size_t)m * 2 + 1]);
     const bool att = (flags & LOSS_ATT_ENT) != 0;
-    const float att_scale = att ? gamma / (float)M : 0.f;
+    const float att_scale = att ? gamma / n_all : 0.f;
     const long long y = (m < Bs) ? labels[m] : -1;
     for (int c = lane; c < C; c += 32) {
       const float lq = pv[c] - mx - lse;
       const float q = expf(lq);
       float gq = 0.f;
-      if (m < Bs) gq = (q - (c == (int)y ? 1.f : 0.f)) / (float)Bs;
+      if (m < Bs) gq = (q - (c == (int)y ? 1.f : 0.f)) / n_src;
       gq += att_scale * (1.f + dv.ent) * (-q * (lq + hc));
       g_video[(size_t)m * C + c] = gq;
-      if (m < Bs && c == (int)y && lane == (c & 31)) loss += -lq / (float)Bs;
+      if (m < Bs && c == (int)y && lane == (c & 31)) loss += -lq / n_src;
     }
     loss = warp_sum(loss);   // exactly one lane held the CE term
     if (lane == 0) {
       float l = loss + att_scale * (1.f + dv.ent) * hc;
       float g0 = 0.f, g1 = 0.f;
       if (flags & LOSS_ADV_VIDEO) {
-        l += -(dom ? dv.lq1 : dv.lq0) / (float)M;
-        g0 = (dv.q0 - (dom ? 0.f : 1.f)) / (float)M;
-        g1 = (dv.q1 - (dom ? 1.f : 0.f)) / (float)M;
+        l += -(dom ? dv.lq1 : dv.lq0) / n_all;
+        g0 = (dv.q0 - (dom ? 0.f : 1.f)) / n_all;
+        g1 = (dv.q1 - (dom ? 1.f : 0.f)) / n_all;
       }
       g0 += att_scale * hc * (-dv.q0 * (dv.lq0 + dv.ent));
       g1 += att_scale * hc * (-dv.q1 * (dv.lq1 + dv.ent));
@@ -561,7 +575,7 @@ loss_heads_kernel(const float* __restrict__ pred_video, const long long* __restr
       float g0 = 0.f, g1 = 0.f;
       if (flags & LOSS_ADV_REL) {
         const Attn2 a = attn_from_logits(pred_rel[o], pred_rel[o + 1]);
-        const float inv = 1.f / ((float)M * (float)R);
+        const float inv = 1.f / (n_all * (float)R);
         extra += -(dom ? a.lq1 : a.lq0) * inv;
         g0 = (a.q0 - (dom ? 0.f : 1.f)) * inv;
         g1 = (a.q1 - (dom ? 1.f : 0.f)) * inv;
@@ -574,7 +588,7 @@ loss_heads_kernel(const float* __restrict__ pred_video, const long long* __restr
       float g0 = 0.f, g1 = 0.f;
       if (flags & LOSS_ADV_FRAME) {
         const Attn2 a = attn_from_logits(pred_frame[o], pred_frame[o + 1]);
-        const float inv = 1.f / ((float)M * (float)T);
+        const float inv = 1.f / (n_all * (float)T);
         extra += -(dom ? a.lq1 : a.lq0) * inv;
         g0 = (a.q0 - (dom ? 0.f : 1.f)) * inv;
         g1 = (a.q1 - (dom ? 1.f : 0.f)) * inv;

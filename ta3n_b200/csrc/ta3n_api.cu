@@ -783,9 +783,9 @@ size_t ta3n_loss_workspace_bytes(int M) { return Arena::round((size_t)M * sizeof
 
 int ta3n_loss_fwd_bwd(const float* pred_video, const long long* labels, const float* pred_rel,
                       const float* pred_dom_video, const float* pred_frame, int Bs, int Bt, int T, int R, int C,
-                      float gamma, int flags, float* loss, float* g_pred_video, float* g_pred_rel,
-                      float* g_pred_dom_video, float* g_pred_frame, void* workspace, size_t workspace_bytes,
-                      ta3n_stream_t stream) {
+                      float gamma, int flags, const int* valid_rows, float* loss, float* g_pred_video,
+                      float* g_pred_rel, float* g_pred_dom_video, float* g_pred_frame, void* workspace,
+                      size_t workspace_bytes, ta3n_stream_t stream) {
   TA3N_REQUIRE(Bs >= 1 && Bt >= 0 && T >= 1 && R >= 1 && C >= 1, "bad sizes");
   TA3N_REQUIRE(pred_video && labels && pred_rel && pred_dom_video && pred_frame && loss, "null input");
   TA3N_REQUIRE(g_pred_video && g_pred_rel && g_pred_dom_video && g_pred_frame, "null gradient output");
@@ -795,8 +795,8 @@ int ta3n_loss_fwd_bwd(const float* pred_video, const long long* labels, const fl
   if (!row_loss) return fail(TA3N_ERR_WORKSPACE, "ta3n_loss_fwd_bwd: workspace too small (%zu bytes)", workspace_bytes);
   pre_launch("loss_heads", S(stream));
   launch_kernel(loss_heads_kernel, blocks_for((size_t)M * 32, 256), 256, 0, S(stream), 
-      pred_video, labels, pred_rel, pred_dom_video, pred_frame, Bs, M, T, R, C, gamma, flags, g_pred_video,
-      g_pred_rel, g_pred_dom_video, g_pred_frame, row_loss);
+      pred_video, labels, pred_rel, pred_dom_video, pred_frame, Bs, M, T, R, C, gamma, flags, valid_rows,
+      g_pred_video, g_pred_rel, g_pred_dom_video, g_pred_frame, row_loss);
   TA3N_TRY(after_launch());
   pre_launch("loss_reduce", S(stream));
   launch_kernel(loss_reduce_kernel, 1, 1024, 0, S(stream), row_loss, M, loss);

@@ -155,10 +155,14 @@ class TrainStep:
         f32 = dict(device=dev, dtype=torch.float32)
         # input slots: one, or two for prefetching the next mini-batch while this one computes
         self.n_slots = 2 if double_buffer else 1
+        # per slot: source features, target features, source labels, {real source rows, real target rows}
         self.slots = [(torch.zeros(self.Bs, self.T, self.D, **f32), torch.zeros(self.Bt, self.T, self.D, **f32),
-                       torch.zeros(self.Bs, device=dev, dtype=torch.int64)) for _ in range(self.n_slots)]
+                       torch.zeros(self.Bs, device=dev, dtype=torch.int64),
+                       torch.tensor([self.Bs, self.Bt], device=dev, dtype=torch.int32)) for _ in range(self.n_slots)]
+        self._valid_host = [torch.tensor([self.Bs, self.Bt], dtype=torch.int32).pin_memory()
+                            for _ in range(self.n_slots)]
         self.active = 0
-        self.xs, self.xt, self.labels = self.slots[0]
+        self.xs, self.xt, self.labels, self.valid = self.slots[0]
         self.copy_stream = torch.cuda.Stream(device=dev) if double_buffer else None
         self.ready = [None] * self.n_slots          # event: slot filled
         self.consumed = [None] * self.n_slots       # event: last step that read the slot has finished
@@ -186,9 +190,9 @@ class TrainStep:
         self.graphs = [None] * self.n_slots      # per input slot: (graph_a, graph_b or None)
         if use_graph:
             for slot in range(self.n_slots):
-                self.xs, self.xt, self.labels = self.slots[slot]
+                self.xs, self.xt, self.labels, self.valid = self.slots[slot]
                 self.graphs[slot] = self._capture()
-            self.xs, self.xt, self.labels = self.slots[0]
+            self.xs, self.xt, self.labels, self.valid = self.slots[0]
 
     # -- the fixed launch sequence ---------------------------------------------------------------------
     def _enqueue_optimizer(self):
@@ -219,7 +223,7 @@ class TrainStep:
         _, pred_frame, _, pred_rel, _, pred_video, pred_dom = outputs
         check(lib.ta3n_loss_fwd_bwd(_P(pred_video), _P(self.labels), _P(pred_rel), _P(pred_dom), _P(pred_frame),
                                     self.Bs, self.Bt, self.T, self.R, self.C, self.gamma, self.flags,
-                                    _P(self.loss), _P(self.g_video), _P(self.g_rel), _P(self.g_dom),
+                                    _P(self.valid), _P(self.loss), _P(self.g_video), _P(self.g_rel), _P(self.g_dom),
                                     _P(self.g_frame), _P(self.loss_ws), self.loss_ws.numel(), st))
         gin = {"pred_video": self.g_video, "pred_rel": self.g_rel, "pred_dom_video": self.g_dom,
                "pred_frame": self.g_frame}
@@ -319,11 +323,30 @@ class TrainStep:
         return (ga, gb)
 
     # -- public API ------------------------------------------------------------------------------------
+    def _fill(self, slot, source, target, labels):
+        """Copy a paired mini-batch into input slot `slot` on the current stream.  Fewer than (Bs, Bt) rows --
+        the last batch of an epoch -- are padded the way main.py:354-372 does and masked out of every loss term
+        the way main.py:421-422 does (the rows are simply left as they were: rows are independent and the
+        padded ones receive zero gradient)."""
+        xs, xt, lab, valid = self.slots[slot]
+        ns, nt = int(source.shape[0]), int(target.shape[0])
+        if not (1 <= ns <= self.Bs and 0 <= nt <= self.Bt) or labels.shape[0] != ns:
+            raise ValueError(f"batch of {ns}+{nt} videos / {labels.shape[0]} labels does not fit TrainStep({self.Bs}, {self.Bt})")
+        xs[:ns].copy_(source.reshape((ns,) + tuple(xs.shape[1:])), non_blocking=True)
+        if nt:
+            xt[:nt].copy_(target.reshape((nt,) + tuple(xt.shape[1:])), non_blocking=True)
+        lab[:ns].copy_(labels, non_blocking=True)
+        host = self._valid_host[slot]
+        if (int(host[0]), int(host[1])) != (ns, nt):
+            # the pinned pair must not change while an earlier async copy of it may be pending; the batch size
+            # changes once per epoch, so a stream synchronisation here costs nothing measurable
+            torch.cuda.current_stream().synchronize()
+            host[0], host[1] = ns, nt
+            valid.copy_(host, non_blocking=True)
+
     def load(self, source, target, labels):
         """Copy one paired mini-batch (host or device tensors) into the ACTIVE input slot (compute stream)."""
-        self.xs.copy_(source.reshape(self.xs.shape), non_blocking=True)
-        self.xt.copy_(target.reshape(self.xt.shape), non_blocking=True)
-        self.labels.copy_(labels, non_blocking=True)
+        self._fill(self.active, source, target, labels)
 
     def prefetch(self, source, target, labels):
         """double_buffer=True: copy the NEXT mini-batch into the inactive slot on the copy stream, overlapping
@@ -331,13 +354,10 @@ class TrainStep:
         if self.n_slots < 2:
             raise ValueError("prefetch needs TrainStep(double_buffer=True)")
         nxt = 1 - self.active
-        xs, xt, lab = self.slots[nxt]
         with torch.cuda.stream(self.copy_stream):
             if self.consumed[nxt] is not None:
                 self.copy_stream.wait_event(self.consumed[nxt])      # do not overwrite inputs still being read
-            xs.copy_(source.reshape(xs.shape), non_blocking=True)
-            xt.copy_(target.reshape(xt.shape), non_blocking=True)
-            lab.copy_(labels, non_blocking=True)
+            self._fill(nxt, source, target, labels)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         self.ready[nxt] = ev
@@ -345,7 +365,7 @@ class TrainStep:
     def swap(self):
         """Make the prefetched slot the active one (the compute stream waits for its copies)."""
         self.active = 1 - self.active
-        self.xs, self.xt, self.labels = self.slots[self.active]
+        self.xs, self.xt, self.labels, self.valid = self.slots[self.active]
         if self.ready[self.active] is not None:
             torch.cuda.current_stream().wait_event(self.ready[self.active])
             self.ready[self.active] = None

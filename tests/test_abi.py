@@ -38,7 +38,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_abi_version_and_engine_switch(lib):
     from ta3n_b200 import _lib
-    assert lib.ta3n_abi_version() == 1
+    assert lib.ta3n_abi_version() == 2
     _lib.set_gemm_engine("tf32")
     assert _lib.get_gemm_engine() == "tf32"
     _lib.set_gemm_engine("fp32")

@@ -567,6 +567,50 @@ def test_fused_train_iteration_matches_oracle(clip, use_graph, engine):
     assert torch.equal(model.fc_feature_source.weight.detach().cpu(), params["fc_feature_source.weight"])
 
 
+@pytest.mark.parametrize("double_buffer", [False, True])
+def test_fused_step_short_last_batch_is_masked_like_the_reference(double_buffer, engine):
+    """The last mini-batch of an epoch has fewer videos; main.py:354-372 zero-pads it to the full size and
+    main.py:421-422 drops the padded rows again before any loss.  TrainStep keeps its captured shapes, leaves the
+    unused rows as they were and masks them in the loss kernel: loss and gradients must equal the oracle run on
+    the real rows only, and a following full batch must be unaffected."""
+    from ta3n_b200.train import TrainStep
+    cfg = orc.PathConfig(num_class=12, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0)
+    params = orc.init_params(cfg, seed=5)
+    g = torch.Generator().manual_seed(15)
+    for k in params:
+        if params[k].dtype.is_floating_point and k.startswith(orc.USED_PARAM_PREFIXES) and "weight" in k:
+            params[k] = params[k] + 0.02 * torch.randn(params[k].shape, generator=g)
+    Bs, Bt = 16, 12
+    xs = torch.randn(Bs, 5, orc.FEATURE_DIM, generator=g)
+    xt = torch.randn(Bt, 5, orc.FEATURE_DIM, generator=g) - 0.2
+    labels = torch.arange(Bs) % 12
+    beta = (0.75, 0.75, 0.5)
+    model = build_model(cfg, params, train=True)
+    step = TrainStep(model, Bs, Bt, beta, gamma=0.003, use_graph=True, double_buffer=double_buffer)
+
+    def run(a, b, lab):
+        if double_buffer:
+            step.prefetch(a.pin_memory(), b.pin_memory(), lab)
+            step.swap()
+            loss = step.run()
+        else:
+            loss = step(a.pin_memory(), b.pin_memory(), lab)
+        torch.cuda.synchronize()
+        return loss.cpu()[0].clone(), {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters()
+                                       if p.grad is not None}
+
+    for ns, nt in [(Bs, Bt), (5, 3), (Bs, Bt), (16, 1)]:
+        loss, grads = run(xs[:ns], xt[:nt], labels[:ns])
+        loss_o, _, grads_o, n_loss, _, n_grad = oracle_truth(params, xs[:ns], xt[:nt], labels[:ns], beta, cfg, 0.003,
+                                                             True, None)
+        assert_close(loss, loss_o, TOL[engine], f"loss with {ns}+{nt} real rows", noise=n_loss)
+        for name, go in grads_o.items():
+            assert_close(grads[name], go, GRAD_TOL[engine], f"grad {name} with {ns}+{nt} real rows",
+                         noise=n_grad[name] * NOISE_SCALE[engine])
+    with pytest.raises(ValueError):
+        step.load(xs, xt[:nt], labels[:3])
+
+
 def test_fused_step_dropout_changes_every_replay():
     from ta3n_b200.train import TrainStep
     cfg = orc.PathConfig(num_class=12, num_segments=5, fc_dim=512, dropout_i=0.5, dropout_v=0.5)
