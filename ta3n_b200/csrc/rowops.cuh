@@ -418,14 +418,6 @@ __global__ void __launch_bounds__(256) frame_attn_bwd_kernel(const float* __rest
   }
 }
 
-// dropped = y * keep / (1-p)                                               models.py:679-680
-__global__ void __launch_bounds__(256) video_drop_fwd_kernel(const float* __restrict__ y, float* __restrict__ out,
-                                                             size_t total, const DropArgs a) {
-  pdl_wait();
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
-    out[e] = y[e] * drop_factor(a, e);
-}
-
 // d_feat_video = ((g_pred Wc) + extra) * grad_scale * keep/(1-p) + g_ext
 __global__ void __launch_bounds__(256)
 video_head_bwd_kernel(const float* __restrict__ g_pred, int C, const float* __restrict__ Wc,
