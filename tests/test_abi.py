@@ -54,6 +54,15 @@ def test_argument_validation_needs_no_gpu(lib):
     assert b"ta3n_disc_fwd" in lib.ta3n_last_error()
     rc = lib.ta3n_gemm_tn(None, None, None, 0, 0, 0, None)
     assert rc == 1
+    # optimizer entry: null buffers, then buffers that are not 16-byte aligned
+    assert lib.ta3n_sgd_nesterov_step(None, None, None, 10, None, 0.9, 1e-4, 20.0, None, 0, None, None) == 1
+    assert lib.ta3n_sgd_nesterov_step(4, 16, 32, 10, 64, 0.9, 1e-4, 0.0, None, 0, None, None) == 1
+    assert b"16-byte aligned" in lib.ta3n_last_error()
+    assert lib.ta3n_sgd_nesterov_step(16, 32, 48, 10, 64, -0.1, 1e-4, 0.0, None, 0, None, None) == 1
+    assert lib.ta3n_sgd_workspace_bytes() >= 296 * 4
+    # loss heads: a class count / batch of zero is rejected before anything is launched
+    assert lib.ta3n_loss_fwd_bwd(None, None, None, None, None, 0, 0, 5, 4, 12, 0.003, 15, None, None, None, None,
+                                 None, None, None, 0, None) == 1
 
 
 def test_no_cpu_fallback_in_product_package():
