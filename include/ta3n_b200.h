@@ -183,9 +183,11 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
 /* Between begin and flush (same host thread) ta3n_disc_fwd and ta3n_trn_fwd only register their GEMMs;
  * the flush issues them as ONE grouped launch followed by their light follow-up kernels.  Only calls
  * whose inputs are already final may be batched together (e.g. the frame discriminator and the TRN,
- * which both read the shared features when use_attn_frame == 'none').                                  */
+ * which both read the shared features when use_attn_frame == 'none').  The workspace (optional, may be
+ * NULL / 0) is only used by the experimental balanced split-K of the grouped launch.                    */
 int ta3n_fwd_batch_begin(void);
-int ta3n_fwd_batch_flush(ta3n_stream_t stream);
+size_t ta3n_fwd_batch_workspace_bytes(void);
+int ta3n_fwd_batch_flush(void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
 
 /* ---- deferred weight gradients (optional) ------------------------------------------- */
 /* Between begin and flush (same host thread) the *_bwd entry points above launch only their

@@ -60,7 +60,8 @@ SIGNATURES = {
     "ta3n_video_head_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ta3n_video_head_bwd": (_I, [_VP, _I, _I, _I, _VP, _DRP, _VP, _VP, _VP, _F, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "ta3n_fwd_batch_begin": (_I, []),
-    "ta3n_fwd_batch_flush": (_I, [_VP]),
+    "ta3n_fwd_batch_workspace_bytes": (_SZ, []),
+    "ta3n_fwd_batch_flush": (_I, [_VP, _SZ, _VP]),
     "ta3n_wgrad_defer_begin": (_I, []),
     "ta3n_wgrad_defer_workspace_bytes": (_SZ, []),
     "ta3n_wgrad_defer_flush": (_I, [_VP, _SZ, _VP]),

@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <tuple>
 
@@ -171,10 +172,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(bool a_kmaj, bool b_kmaj,
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------
-template <bool A_KMAJ, bool B_KMAJ, int TC_STAGES>
+// FIXUP (experimental, TA3N_FIXUP_SPLITK=1): groups with fix_slot >= 0 fold their split-K partials inside this
+// kernel instead of a reduce pass.  Splits 0 .. ksplit-2 of a tile write their raw accumulators to `partial` and
+// bump the tile's arrival counter (release); the LAST split acquires the counter after its own K range, adds the
+// partials in a fixed order in its register epilogue, runs the fused epilogue and resets the counter for the next
+// launch.  Nobody but the last split ever waits, and the host only plans such launches when every CTA is resident
+// at once (<= 256 CTAs at two per SM), so the wait cannot starve the blocks it waits for; a bounded spin turns
+// any violation of that assumption into a trap instead of a hang.
+template <bool A_KMAJ, bool B_KMAJ, int TC_STAGES, bool FIXUP>
 __global__ void __launch_bounds__(tc_threads(TC_STAGES), TC_STAGES <= 3 ? 2 : 1)
 seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant__ TcMaps maps,
-                   const __grid_constant__ TcSegMaps segmaps, const int dbg) {
+                   const __grid_constant__ TcSegMaps segmaps, const int dbg, int* __restrict__ fix_flags) {
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
@@ -311,12 +319,28 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
     const int lq = warp & 3;              // TMEM lane quarter this warp may access
     const Group e = ctx.g;                // register copy: no reloads behind the global stores
     const int m = m0 + lq * 32 + lane;
-    const bool split_out = e.ksplit > 1;
+    const bool fix = FIXUP && e.ksplit > 1 && e.fix_slot >= 0;
+    const bool owner = fix && split == e.ksplit - 1;
+    const bool split_out = e.ksplit > 1 && !owner;
     float* const obase = split_out ? e.partial + (size_t)split * e.M * e.N : e.C;
     const int ldo = split_out ? e.N : e.ldc;
+    int* const flag = fix ? fix_flags + e.fix_slot + local : nullptr;
     if (n_iter > 0) {
       mbar_wait(&tmem_full_bar, 0);
       tc_fence_after();
+    }
+    if (FIXUP && owner) {
+      // wait until every other split of this tile has stored its partial (they are resident and never wait)
+      if (lane == 0) {
+        int seen = 0;
+        for (unsigned spin = 0; ; ++spin) {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+          if (seen >= e.ksplit - 1) break;
+          if (spin > (1u << 24)) __trap();
+          __nanosleep(128);
+        }
+      }
+      __syncwarp();
     }
     constexpr int kEpiWarps = tc_threads(TC_STAGES) / 32 - 2;
     constexpr int kColChunks = (TC_BN / 32) * 4 / kEpiWarps;      // column chunks of 32 per warp: 4 or 2
@@ -337,6 +361,26 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
           orow[0] = v[0];
           continue;
         }
+        if (FIXUP && owner) {      // raw partial sums of the other splits, fixed order, straight from L2
+          const int nvalid = min(32, e.N - nb);
+          for (int sp = 0; sp < e.ksplit - 1; ++sp) {
+            const float* pr = e.partial + (size_t)sp * e.M * e.N + (size_t)m * e.N + nb;
+            if (nvalid >= 32 && (reinterpret_cast<uintptr_t>(pr) & 15u) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(pr + j));
+                v[j] += t.x;
+                v[j + 1] += t.y;
+                v[j + 2] += t.z;
+                v[j + 3] += t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) v[j] += __ldcg(pr + j);
+            }
+          }
+        }
         if (!split_out && !(dbg & 256)) {
           const int nvalid = min(32, e.N - nb);
           TA3N_EPI_DISPATCH(e.flags, { epilogue_row32<EPI_F>(e, m, nb, nvalid, v); })
@@ -350,6 +394,17 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
           for (int j = 0; j < 32; ++j)
             if (nb + j < e.N) orow[j] = v[j];
         }
+      }
+    }
+    if (FIXUP && fix) {
+      // all epilogue warps have issued their stores -> one thread publishes (or, for the owner, re-arms) the counter
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"((tc_threads(TC_STAGES) / 32 - 2) * 32) : "memory");
+      if (warp == 2 && lane == 0) {
+        if (owner)
+          *reinterpret_cast<volatile int*>(flag) = 0;
+        else
+          asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flag) : "memory");
       }
     }
   }
@@ -443,12 +498,12 @@ inline bool tc_group_ok(const GemmPlan& plan, const Group& g) {
   return true;
 }
 
-template <bool A_KMAJ, bool B_KMAJ, int STAGES>
+template <bool A_KMAJ, bool B_KMAJ, int STAGES, bool FIXUP>
 inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
-                            const char* label) {
+                            const char* label, int* fix_flags) {
   static bool configured = false;
   if (!configured) {
-    TA3N_CUDA(cudaFuncSetAttribute(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES>,
+    TA3N_CUDA(cudaFuncSetAttribute(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES, FIXUP>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(STAGES)));
     configured = true;
   }
@@ -457,21 +512,121 @@ inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSe
     return e ? atoi(e) : 0;
   }();
   pre_launch(label, stream);
-  launch_kernel(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES>, tab.total_tiles, tc_threads(STAGES), tc_smem_bytes(STAGES), stream, 
-      tab, maps, sm, dbg);
+  launch_kernel(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES, FIXUP>, tab.total_tiles, tc_threads(STAGES),
+                tc_smem_bytes(STAGES), stream, tab, maps, sm, dbg, fix_flags);
   return after_launch();
 }
 
 template <bool A_KMAJ, bool B_KMAJ>
 inline int tc_launch_one(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
-                         const char* label) {
+                         const char* label, int* fix_flags) {
   static const int force = []() {
     const char* e = getenv("TA3N_TC_STAGES");
     return e ? atoi(e) : 0;
   }();
   const bool deep = force ? force > 3 : tab.total_tiles <= 148;
-  return deep ? tc_launch_stages<A_KMAJ, B_KMAJ, 6>(tab, maps, sm, stream, label)
-              : tc_launch_stages<A_KMAJ, B_KMAJ, 3>(tab, maps, sm, stream, label);
+  if (fix_flags != nullptr)
+    return deep ? tc_launch_stages<A_KMAJ, B_KMAJ, 6, true>(tab, maps, sm, stream, label, fix_flags)
+                : tc_launch_stages<A_KMAJ, B_KMAJ, 3, true>(tab, maps, sm, stream, label, fix_flags);
+  return deep ? tc_launch_stages<A_KMAJ, B_KMAJ, 6, false>(tab, maps, sm, stream, label, nullptr)
+              : tc_launch_stages<A_KMAJ, B_KMAJ, 3, false>(tab, maps, sm, stream, label, nullptr);
+}
+
+// ---- experimental: in-kernel split-K fix-up (TA3N_FIXUP_SPLITK=1) -----------------------------------------
+inline bool fixup_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("TA3N_FIXUP_SPLITK");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
+// Arrival counters: one int per split output tile, zero between launches (the owner re-arms its counter).  The
+// buffer belongs to the library (one per device, allocated on first use OUTSIDE stream capture -- during capture
+// an unallocated buffer simply disables the fix-up for that call); launches take consecutive slots from a ring.
+constexpr int kFixFlagSlots = 1 << 16;
+inline int* fix_flags_take(int n, cudaStream_t stream, int* slot) {
+  struct Dev {
+    int* base = nullptr;
+    unsigned next = 0;
+  };
+  static std::mutex mu;
+  static std::map<int, Dev> devs;
+  if (n <= 0 || n > kFixFlagSlots / 4) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  Dev& d = devs[dev];
+  if (!d.base) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+    int* p = nullptr;
+    if (cudaMalloc(&p, sizeof(int) * kFixFlagSlots) != cudaSuccess) return nullptr;
+    if (cudaMemset(p, 0, sizeof(int) * kFixFlagSlots) != cudaSuccess) {
+      cudaFree(p);
+      return nullptr;
+    }
+    d.base = p;
+  }
+  if (d.next + (unsigned)n > (unsigned)kFixFlagSlots) d.next = 0;
+  *slot = (int)d.next;
+  d.next += (unsigned)n;
+  return d.base;
+}
+
+// Modelled makespan (in 32-wide K slabs) of a launch: CTAs in launch order, each to the least loaded of 148 SMs;
+// an SM's fill bandwidth is shared by its resident CTAs, so loads add up.
+inline long tc_makespan(const std::vector<long>& cta_slabs) {
+  std::vector<long> sm(148, 0);
+  std::vector<long> sorted = cta_slabs;
+  std::sort(sorted.begin(), sorted.end(), std::greater<long>());
+  for (long c : sorted) *std::min_element(sm.begin(), sm.end()) += c;
+  return *std::max_element(sm.begin(), sm.end());
+}
+
+// Choose per-group split factors that shorten the modelled makespan of a launch whose tiles are few and uneven
+// (the critical tile of the forward batch is 80 slabs against 36 per SM on average).  Only with the fix-up: a
+// separate reduce pass costs more than this saves.
+inline void plan_balance_splitk(GemmPlan& plan, Arena* arena) {
+  if (!arena) return;
+  const int ng = (int)plan.groups.size();
+  std::vector<long> tiles(ng), slabs(ng);
+  long total = 0;
+  for (int i = 0; i < ng; ++i) {
+    const Group& g = plan.groups[i];
+    if (g.ksplit > 1) return;   // already planned
+    tiles[i] = (long)((g.M + TC_BM - 1) / TC_BM) * ((g.N + TC_BN - 1) / TC_BN);
+    slabs[i] = 0;
+    for (int k = 0; k < g.seg_count; ++k) slabs[i] += (plan.segs[g.seg_begin + k].len + TC_BK - 1) / TC_BK;
+    total += tiles[i] * slabs[i];
+  }
+  auto model = [&](const std::vector<int>& ks) {
+    std::vector<long> ctas;
+    for (int i = 0; i < ng; ++i)
+      for (long t = 0; t < tiles[i] * ks[i]; ++t) ctas.push_back((slabs[i] + ks[i] - 1) / ks[i] + 2);   // +2: fix-up
+    return tc_makespan(ctas);
+  };
+  std::vector<int> ks(ng, 1);
+  const long before = model(ks);
+  const long target = std::max<long>(12, (long)(1.15 * (double)total / 148.0));
+  long n_ctas = 0;
+  for (int i = 0; i < ng; ++i) {
+    int want = (int)((slabs[i] + target - 1) / target);
+    want = std::min(want, 4);
+    while (want > 1 && slabs[i] / want < 8) --want;
+    ks[i] = std::max(want, 1);
+    n_ctas += tiles[i] * ks[i];
+  }
+  if (n_ctas > 256) return;                                    // every CTA resident at once, with headroom
+  if (model(ks) * 100 > before * 85) return;                   // needs >= 15 % shorter critical path
+  for (int i = 0; i < ng; ++i) {
+    if (ks[i] < 2) continue;
+    Group& g = plan.groups[i];
+    float* p = arena->floats((size_t)ks[i] * g.M * g.N);   // ksplit planes: the reduce pass stays a valid fallback
+    if (!p) continue;
+    g.ksplit = ks[i];
+    g.partial = p;
+  }
 }
 
 // Copy the groups `idx` of `plan` (with their segments) into a new plan.
@@ -492,7 +647,7 @@ inline GemmPlan sub_plan(const GemmPlan& plan, const std::vector<int>& idx) {
 }
 
 // Launch `plan` (all groups eligible) on the tcgen05 engine.
-inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
+inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool fixup = false) {
   // longest-K groups first (see the tile remap in the kernel): LPT-style balance of the tensor pipe
   std::vector<int> order(plan_in.groups.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
@@ -519,7 +674,7 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
     memset(&tab, 0, sizeof(int) * 4);
     memset(&sm, 0, sizeof(sm));
     std::map<MapKey, int> local;
-    int ng = 0, ns = 0, tiles = 0, nmaps = 0;
+    int ng = 0, ns = 0, tiles = 0, nmaps = 0, fix_tiles = 0;
     bool any_split = false;
     while (gi < plan.groups.size() && ng < kMaxGroups) {
       const Group& src = plan.groups[gi];
@@ -560,22 +715,36 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
       g.tiles_n = (g.N + TC_BN - 1) / TC_BN;
       g.tile_begin = tiles;
       tiles += g.tiles_m * g.tiles_n * g.ksplit;
-      any_split |= g.ksplit > 1;
+      g.fix_slot = -1;
+      if (g.ksplit > 1 && fixup) {
+        g.fix_slot = fix_tiles;                 // relative; rebased below once the ring slots are known
+        fix_tiles += g.tiles_m * g.tiles_n;
+      }
       tab.g[ng++] = g;
       ++gi;
     }
+    // arrival counters for the fix-up groups; without them (first use inside a stream capture) the groups fall
+    // back to the separate reduce pass
+    int* fix_flags = nullptr;
+    if (fix_tiles > 0) {
+      int slot0 = 0;
+      fix_flags = fix_flags_take(fix_tiles, stream, &slot0);
+      for (int i = 0; i < ng; ++i)
+        if (tab.g[i].fix_slot >= 0) tab.g[i].fix_slot = fix_flags ? tab.g[i].fix_slot + slot0 : -1;
+    }
+    for (int i = 0; i < ng; ++i) any_split |= tab.g[i].ksplit > 1 && tab.g[i].fix_slot < 0;
     tab.n_groups = ng;
     tab.total_tiles = tiles;
     tab.pad_ = (a3d ? 1 : 0) | (b3d ? 2 : 0);
     if (tiles > 0) {
       if (plan.a_kmaj && plan.b_kmaj)
-        TA3N_TRY((tc_launch_one<true, true>(tab, maps, sm, stream, plan.label)));
+        TA3N_TRY((tc_launch_one<true, true>(tab, maps, sm, stream, plan.label, fix_flags)));
       else if (plan.a_kmaj && !plan.b_kmaj)
-        TA3N_TRY((tc_launch_one<true, false>(tab, maps, sm, stream, plan.label)));
+        TA3N_TRY((tc_launch_one<true, false>(tab, maps, sm, stream, plan.label, fix_flags)));
       else if (!plan.a_kmaj && !plan.b_kmaj)
-        TA3N_TRY((tc_launch_one<false, false>(tab, maps, sm, stream, plan.label)));
+        TA3N_TRY((tc_launch_one<false, false>(tab, maps, sm, stream, plan.label, fix_flags)));
       else
-        TA3N_TRY((tc_launch_one<false, true>(tab, maps, sm, stream, plan.label)));
+        TA3N_TRY((tc_launch_one<false, true>(tab, maps, sm, stream, plan.label, fix_flags)));
       if (any_split) {
         dim3 grid(splitk_reduce_blocks(tab), ng);
         pre_launch("splitk_reduce", stream);
@@ -601,7 +770,12 @@ inline int run_gemm(GemmPlan& plan, cudaStream_t stream, Arena* splitk_arena = n
     if (!tc_idx.empty()) {
       GemmPlan tc = sub_plan(plan, tc_idx);
       plan_splitk(tc, splitk_arena, TC_BM, TC_BN, TC_BK, 4);
-      TA3N_TRY(launch_tc(tc, stream));
+      bool fixup = false;
+      if (fixup_enabled() && splitk_arena) {
+        plan_balance_splitk(tc, splitk_arena);      // no-op when plan_splitk already split something
+        for (const Group& g : tc.groups) fixup |= g.ksplit > 1;
+      }
+      TA3N_TRY(launch_tc(tc, stream, fixup));
     }
     if (!simt_idx.empty()) {
       GemmPlan rest = sub_plan(plan, simt_idx);

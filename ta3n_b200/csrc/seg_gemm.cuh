@@ -63,6 +63,8 @@ struct Group {
   float drop_scale, drop_p;
   float rs_bias;
   int ldkeep, ldadd, rs_stride, ldgate;
+  int fix_slot;     // >= 0: split-K partials are folded in by the LAST split of each tile inside the GEMM kernel
+  int pad2_;        //       (arrival counters fix_flags[fix_slot + tile]); -1: separate reduce kernel
   float* C;
   float* partial;   // [ksplit, M, N] when ksplit > 1
   const float* bias;
@@ -90,6 +92,7 @@ inline Group make_group() {
   memset(&g, 0, sizeof(g));
   g.alpha = 1.0f;
   g.ksplit = 1;
+  g.fix_slot = -1;
   return g;
 }
 
@@ -444,7 +447,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
     for (int i = threadIdx.x; i < (int)(sizeof(Group) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
     __syncthreads();
   }
-  if (g.ksplit <= 1) return;
+  if (g.ksplit <= 1 || g.fix_slot >= 0) return;
   const size_t total = (size_t)g.M * g.N;
   const Group gr = g;
   TA3N_EPI_DISPATCH(gr.flags, {
@@ -460,7 +463,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
 inline unsigned splitk_reduce_blocks(const GemmTable& tab) {
   size_t mx = 0;
   for (int i = 0; i < tab.n_groups; ++i)
-    if (tab.g[i].ksplit > 1 && (size_t)tab.g[i].M * tab.g[i].N > mx) mx = (size_t)tab.g[i].M * tab.g[i].N;
+    if (tab.g[i].ksplit > 1 && tab.g[i].fix_slot < 0 && (size_t)tab.g[i].M * tab.g[i].N > mx)
+      mx = (size_t)tab.g[i].M * tab.g[i].N;
   size_t b = (mx + 255) / 256;
   if (b > 512) b = 512;
   return (unsigned)(b ? b : 1);

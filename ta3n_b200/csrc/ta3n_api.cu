@@ -176,11 +176,15 @@ int ta3n_fwd_batch_begin(void) {
   return TA3N_OK;
 }
 
-int ta3n_fwd_batch_flush(ta3n_stream_t stream) {
+size_t ta3n_fwd_batch_workspace_bytes(void) { return fixup_enabled() ? splitk_bytes(64) : 0; }
+
+int ta3n_fwd_batch_flush(void* workspace, size_t workspace_bytes, ta3n_stream_t stream) {
   FwdBatch& b = fwd_batch();
   if (!b.active) return fail(TA3N_ERR_INVALID, "ta3n_fwd_batch_flush without ta3n_fwd_batch_begin");
   b.active = false;
-  int rc = run_gemm(b.plan, S(stream));
+  // The workspace only feeds the experimental balanced split-K; the default launch plan is the unsplit one.
+  Arena arena(workspace, workspace_bytes);
+  int rc = run_gemm(b.plan, S(stream), (workspace && fixup_enabled()) ? &arena : nullptr);
   for (auto& f : b.post)
     if (rc == TA3N_OK) rc = f(S(stream));
   b.reset();

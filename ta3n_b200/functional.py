@@ -266,7 +266,8 @@ def path_forward(spec: PathSpec, xs, xt, params, bufs: Buffers, batch_gemms: boo
     check(lib.ta3n_trn_fwd(_p(feat_in), M, F, H, rs.ref, ptr_array([_p(w) for w in trn_w]),
                            ptr_array([_p(b) for b in trn_b]), 0, _p(act), _p(feat_rel), st))
     if batched:
-        check(lib.ta3n_fwd_batch_flush(st))
+        ws = bufs.workspace("fwd_batch", lib.ta3n_fwd_batch_workspace_bytes())
+        check(lib.ta3n_fwd_batch_flush(_p(ws), ws.numel(), st))
     # 4. relation discriminators + attention + pooling  (models.py:639-652)
     hid_r, pred_rel = new("hid_r", R, M, H), new("pred_rel", M, R, 2)
     attn, feat_video = new("attn", M, R), new("feat_video", M, H)
