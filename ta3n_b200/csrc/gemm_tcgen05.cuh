@@ -336,7 +336,7 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
         for (unsigned spin = 0; ; ++spin) {
           asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
           if (seen >= e.ksplit - 1) break;
-          if (spin > (1u << 24)) __trap();
+          if (spin > (1u << 22)) __trap();      // seconds: a protocol error becomes a trap, not a hung device
           __nanosleep(128);
         }
       }
