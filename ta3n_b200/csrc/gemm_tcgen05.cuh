@@ -95,6 +95,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a tile (no shared-memory destination, no barrier): warms the line ahead of the real load
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -255,7 +263,43 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
           ++seg;
         }
       }
+      // Experimental (TA3N_L2_PREFETCH=<slabs>, default 0 = off): TMA prefetch into L2 `pf` slabs ahead of the
+      // loads.  The first GEMMs of a step read inputs and weights that are cold in L2 (HBM latency ~2x an L2 hit)
+      // with only TC_STAGES slabs in flight per SM; an L2 prefetch needs no shared memory, so it can run far ahead.
+      const int pf = (dbg >> 16) & 0xff;
+      int pseg = seg, pk0 = k0, pleft = 0;
+      if (pf > 0) {
+        pleft = n_iter;
+        for (int a = 0; a < pf && pleft > 0; ++a) {      // skip the first pf slabs: the real loads fetch those
+          --pleft;
+          pk0 += TC_BK;
+          if (pk0 >= ctx.seg[pseg].len) {
+            ++pseg;
+            pk0 = 0;
+          }
+        }
+      }
       for (int it = 0; it < n_iter; ++it) {
+        if (pleft > 0) {
+          const CUtensorMap* pa = &maps.m[ctx.seg[pseg].amap];
+          const CUtensorMap* pb = &maps.m[ctx.seg[pseg].bmap];
+          if (A_KMAJ) {
+            tma_prefetch_2d(pa, pk0, m0);
+          } else if (tab.pad_ & 1) {
+            tma_prefetch_3d(pa, 0, pk0, m0 >> 5);
+          }
+          if (B_KMAJ) {
+            tma_prefetch_2d(pb, pk0, n0);
+          } else if (tab.pad_ & 2) {
+            tma_prefetch_3d(pb, 0, pk0, n0 >> 5);
+          }
+          --pleft;
+          pk0 += TC_BK;
+          if (pk0 >= ctx.seg[pseg].len) {
+            ++pseg;
+            pk0 = 0;
+          }
+        }
         const int stage = it % TC_STAGES;
         const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -509,7 +553,10 @@ inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSe
   }
   static const int dbg = []() {
     const char* e = getenv("TA3N_TC_DEBUG");
-    return e ? atoi(e) : 0;
+    const char* p = getenv("TA3N_L2_PREFETCH");          // experimental: L2 prefetch distance in K slabs (0 = off)
+    int pf = p ? atoi(p) : 0;
+    pf = pf < 0 ? 0 : (pf > 255 ? 255 : pf);
+    return ((e ? atoi(e) : 0) & 0xffff) | (pf << 16);
   }();
   pre_launch(label, stream);
   launch_kernel(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES, FIXUP>, tab.total_tiles, tc_threads(STAGES),

@@ -1,9 +1,13 @@
 #!/bin/bash
-# A/B of the experimental in-kernel split-K fix-up on the GPU box:
+# A/B of the experimental knobs: in-kernel split-K fix-up, TMA L2 prefetch distance.
 #   gpurun --timeout 600 -- 'bash tools/fixup_bench.sh'
 set -u
 for v in 0 1; do
   TA3N_FIXUP_SPLITK=$v timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('fixup=$v', round(d['ms_per_step'],4), 'ms/step', {k: d['kernel_ms_per_step'][k] for k in ('fwd_batch','shared_fc_fwd','trn_dgrad','wgrad_all','disc_dgrad','disc_fwd','relattn_fwd','relattn_dgrad','splitk_reduce') if k in d['kernel_ms_per_step']})"
+done
+for pf in 8 16 32; do
+  TA3N_L2_PREFETCH=$pf timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('l2_prefetch=$pf', round(d['ms_per_step'],4), 'ms/step', {k: d['kernel_ms_per_step'][k] for k in ('fwd_batch','shared_fc_fwd','trn_dgrad','wgrad_all') if k in d['kernel_ms_per_step']})"
 done
 TA3N_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_experimental.py -m gpu -q 2>&1 | tail -5
