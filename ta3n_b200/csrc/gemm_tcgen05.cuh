@@ -234,6 +234,15 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1 && !(dbg & 2)) tmem_alloc(&tmem_slot, TC_TMEM_COLS);
+  if (warp == 0 && (dbg & (1 << 24))) {
+    // Experimental (TA3N_DESC_PREFETCH=1, default off): the tensor maps are kernel parameters, so their
+    // descriptors can be pulled into the TMA unit's cache here, under the previous kernel's tail, instead of
+    // stalling the first load of every segment.
+    for (int sgi = lane; sgi < g.seg_count; sgi += 32) {
+      tma_prefetch_desc(&maps.m[ctx.seg[sgi].amap]);
+      tma_prefetch_desc(&maps.m[ctx.seg[sgi].bmap]);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -556,7 +565,8 @@ inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSe
     const char* p = getenv("TA3N_L2_PREFETCH");          // experimental: L2 prefetch distance in K slabs (0 = off)
     int pf = p ? atoi(p) : 0;
     pf = pf < 0 ? 0 : (pf > 255 ? 255 : pf);
-    return ((e ? atoi(e) : 0) & 0xffff) | (pf << 16);
+    const char* d = getenv("TA3N_DESC_PREFETCH");        // experimental: prefetch tensor-map descriptors in the prologue
+    return ((e ? atoi(e) : 0) & 0xffff) | (pf << 16) | ((d && d[0] == '1') ? (1 << 24) : 0);
   }();
   pre_launch(label, stream);
   launch_kernel(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES, FIXUP>, tab.total_tiles, tc_threads(STAGES),
