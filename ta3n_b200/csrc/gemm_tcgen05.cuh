@@ -543,6 +543,13 @@ inline bool tc_operand_ok(const float* p, int ld) {
 inline bool tc_group_ok(const GemmPlan& plan, const Group& g) {
   if (plan.load_flags != 0) return false;                    // ReLU-on-load needs a register pass
   if ((long)g.M * g.N < 64L * 64L) return false;             // tiny heads stay on the SIMT engine
+  // Experimental (TA3N_SIMT_MAX_MNK=<M*N*K>, default 0 = off): a tcgen05 launch costs ~7 us before its first MMA
+  // retires (ncu: 8-slab launches), more than an fp32 SIMT pass over a 512x256x256 discriminator layer.
+  static const double simt_below = []() {
+    const char* e = getenv("TA3N_SIMT_MAX_MNK");
+    return e ? atof(e) : 0.0;
+  }();
+  if (simt_below > 0.0 && (double)g.M * g.N * (double)plan.k_total(g) <= simt_below) return false;
   if (g.seg_count > kMaxSegs) return false;
   for (int i = 0; i < g.seg_count; ++i) {
     const Seg& s = plan.segs[g.seg_begin + i];
