@@ -1,7 +1,8 @@
 """Opt-in checks of experimental kernels (not part of the default GPU suite: set TA3N_EXPERIMENTAL=1).
 
-TA3N_FIXUP_SPLITK=1 switches the tcgen05 GEMM launches to in-kernel split-K fix-up with balanced per-group split
-factors.  The flag is read once per process, so the parity tests run in a child process."""
+Knobs: TA3N_FIXUP_SPLITK=1 in-kernel split-K fix-up with balanced per-group split
+factors; TA3N_L2_PREFETCH=<slabs> TMA L2 prefetch distance; TA3N_DESC_PREFETCH=1 tensor-map descriptor prefetch;
+TA3N_SIMT_MAX_MNK=<M*N*K> small GEMMs on the fp32 SIMT engine."""
 import os
 import subprocess
 import sys
@@ -14,8 +15,15 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("TA3N_EXPERIMENTAL") != "1", reason="experimental kernels are opt-in")]
 
 
-def test_parity_suite_with_inkernel_splitk_fixup():
-    env = dict(os.environ, TA3N_FIXUP_SPLITK="1")
+KNOBS = [{"TA3N_FIXUP_SPLITK": "1"}, {"TA3N_L2_PREFETCH": "16"}, {"TA3N_DESC_PREFETCH": "1"},
+         {"TA3N_SIMT_MAX_MNK": "40000000"},
+         {"TA3N_FIXUP_SPLITK": "1", "TA3N_L2_PREFETCH": "16", "TA3N_DESC_PREFETCH": "1", "TA3N_SIMT_MAX_MNK": "40000000"}]
+
+
+@pytest.mark.parametrize("knobs", KNOBS, ids=lambda k: "+".join(sorted(k)))
+def test_parity_suite_under_experimental_knobs(knobs):
+    """The knobs are read once per process, so the parity tests run in a child process."""
+    env = dict(os.environ, **knobs)
     env.pop("TA3N_EXPERIMENTAL", None)
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x", "-k",
                         "gemm_ex or golden or fused_train or full_size or mid_size"],
