@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--segments", type=int, default=5)
     ap.add_argument("--classes", type=int, default=12)
     ap.add_argument("--fc_dim", type=int, default=512)
-    ap.add_argument("--engine", default=os.environ.get("TA3N_ENGINE", "auto"), choices=["auto", "fp32", "tf32"])
+    ap.add_argument("--engine", default=os.environ.get("TA3N_ENGINE", "auto"), choices=["auto", "fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline sample")
@@ -456,7 +456,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": world * 2 * B * args.steps / (t_ms * 1e-3), "unit": "clips/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if engine == "fp32" else "tf32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3"}.get(engine, "tf32"),
         "data": "synthetic", "config": workload_config(args, world, engine),
         "roofline": roof,
         "roofline_step": {"bound": "hbm", "scope": "whole step (SURVEY 8d scope B)", "achieved": ach_b,

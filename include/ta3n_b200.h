@@ -45,7 +45,9 @@ enum {
 /* GEMM engines for the dense contractions. */
 enum {
   TA3N_GEMM_FP32_SIMT = 0,   /* exact fp32 FFMA tiles (parity / debugging engine)     */
-  TA3N_GEMM_TF32_TCGEN05 = 1 /* tcgen05.mma kind::tf32, TMA-staged, TMEM accumulators */
+  TA3N_GEMM_TF32_TCGEN05 = 1, /* tcgen05.mma kind::tf32, TMA-staged, TMEM accumulators */
+  TA3N_GEMM_TF32X3_TCGEN05 = 2 /* EXPERIMENTAL: same pipeline, three tf32 MMAs per step on hi/lo operand
+                                   splits -> fp32-grade products at unchanged operand traffic */
 };
 
 typedef void* ta3n_stream_t; /* cudaStream_t */

@@ -43,6 +43,10 @@ constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 // loop) for grids beyond a wave; 6 stages (193 KB, one CTA per SM, twice the bytes in flight per CTA)
 // for the sub-wave grids of this workload, where a CTA is alone on its SM and TMA latency-bound.
 constexpr int tc_smem_bytes(int stages) { return stages * TC_STAGE_BYTES + 1024; }   // + 1024 B alignment slack
+// X3 ("tf32x3", experimental engine 2): fp32-grade products from three tf32 MMAs per K step.  A stage then also
+// holds the low-order halves of both operand tiles (64 KB), three stages, one CTA per SM, 8 helper/epilogue warps.
+constexpr int TC_X3_STAGES = 3;
+constexpr int tc_x3_smem_bytes() { return TC_X3_STAGES * 2 * TC_STAGE_BYTES + 1024; }
 constexpr int TC_TMEM_COLS = 128;
 #ifndef TA3N_MAX_MAPS
 #define TA3N_MAX_MAPS 64
@@ -78,6 +82,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -179,6 +186,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(bool a_kmaj, bool b_kmaj,
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// a - trunc_tf32(a): what the tensor core drops when it reads raw fp32 bits (0 for inf / nan, which the leading
+// product already propagates)
+__device__ __forceinline__ float tf32_low(float a) {
+  const uint32_t u = __float_as_uint(a);
+  return (u & 0x7f800000u) == 0x7f800000u ? 0.f : a - __uint_as_float(u & 0xffffe000u);
+}
+
 // ---- the kernel -------------------------------------------------------------------------------------
 // FIXUP (experimental, TA3N_FIXUP_SPLITK=1): groups with fix_slot >= 0 fold their split-K partials inside this
 // kernel instead of a reduce pass.  Splits 0 .. ksplit-2 of a tile write their raw accumulators to `partial` and
@@ -187,13 +201,23 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(bool a_kmaj, bool b_kmaj,
 // launch.  Nobody but the last split ever waits, and the host only plans such launches when every CTA is resident
 // at once (<= 256 CTAs at two per SM), so the wait cannot starve the blocks it waits for; a bounded spin turns
 // any violation of that assumption into a trap instead of a hang.
-template <bool A_KMAJ, bool B_KMAJ, int TC_STAGES, bool FIXUP>
-__global__ void __launch_bounds__(tc_threads(TC_STAGES), TC_STAGES <= 3 ? 2 : 1)
+//
+// X3 (experimental engine "tf32x3"): the tensor maps deliver RAW fp32 bits; the tensor core reads only the top 19
+// bits of an operand, i.e. hi = trunc_tf32(a).  The helper warps (idle during the main loop otherwise) compute
+// lo = a - hi (exact in fp32) for both tiles of a stage into a second pair of buffers, and the MMA thread issues
+// A*B + A*B_lo + A_lo*B per K step: relative error ~3 * 2^-20 per product instead of 2^-11, at unchanged operand
+// traffic -- the main loop is bound by the fill bandwidth, the tensor pipe is 26 % busy with one MMA per step.
+template <bool A_KMAJ, bool B_KMAJ, int TC_STAGES, bool FIXUP, bool X3 = false>
+__global__ void __launch_bounds__(X3 ? 320 : tc_threads(TC_STAGES), (X3 || TC_STAGES > 3) ? 1 : 2)
 seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant__ TcMaps maps,
                    const __grid_constant__ TcSegMaps segmaps, const int dbg, int* __restrict__ fix_flags) {
+  static_assert(!X3 || (TC_STAGES == TC_X3_STAGES && !FIXUP), "tf32x3 variant: 3 stages, no fix-up");
+  constexpr int kThreads = X3 ? 320 : tc_threads(TC_STAGES);
+  constexpr int kStageStride = X3 ? 2 * TC_STAGE_BYTES : TC_STAGE_BYTES;
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
+  __shared__ __align__(8) uint64_t split_bar[TC_STAGES];     // X3: low-order tiles of the stage are ready
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_slot;
 
@@ -229,6 +253,7 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], kThreads / 32 - 2);      // one arrival per helper warp (X3 only)
     }
     mbar_init(&tmem_full_bar, 1);
     fence_barrier_init();
@@ -313,7 +338,7 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
         const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-        uint8_t* sA = smem + stage * TC_STAGE_BYTES;
+        uint8_t* sA = smem + stage * kStageStride;
         uint8_t* sB = sA + TC_A_BYTES;
         const CUtensorMap* ma = &maps.m[ctx.seg[seg].amap];
         const CUtensorMap* mb = &maps.m[ctx.seg[seg].bmap];
@@ -350,16 +375,26 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
       for (int it = 0; it < n_iter; ++it) {
         const int stage = it % TC_STAGES;
         const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(X3 ? &split_bar[stage] : &full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * TC_STAGE_BYTES);
+        const uint32_t a_base = smem_u32(smem + stage * kStageStride);
         const uint32_t b_base = a_base + TC_A_BYTES;
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
           if ((dbg & 512) && ks > 0) break;   // debug: 1 of 4 MMAs (timing experiments only, wrong results)
           const uint64_t adesc = A_KMAJ ? umma_desc_kmajor(a_base, ks) : umma_desc_mnmajor(a_base, ks);
           const uint64_t bdesc = B_KMAJ ? umma_desc_kmajor(b_base, ks) : umma_desc_mnmajor(b_base, ks);
-          umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          if (X3) {
+            // small terms first, then the leading product; the low-order tiles sit TC_STAGE_BYTES above their tiles
+            const uint32_t al = a_base + TC_STAGE_BYTES, bl = b_base + TC_STAGE_BYTES;
+            const uint64_t aldesc = A_KMAJ ? umma_desc_kmajor(al, ks) : umma_desc_mnmajor(al, ks);
+            const uint64_t bldesc = B_KMAJ ? umma_desc_kmajor(bl, ks) : umma_desc_mnmajor(bl, ks);
+            umma_tf32(tmem_base, adesc, bldesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32(tmem_base, aldesc, bdesc, idesc, 1u);
+            umma_tf32(tmem_base, adesc, bdesc, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[stage]);   // releases the smem slot once these MMAs have read it
       }
@@ -369,6 +404,27 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
     // =========================== epilogue (4 warps, 32 TMEM lanes each) ===========================
     // Lane i of warp lq owns accumulator row 32*lq + i; tcgen05.ld hands it 32 consecutive columns, which
     // it finishes (fused epilogue) and writes as 8 x 16 B stores: every 128 B line of C is written whole.
+    if (X3 && n_iter > 0) {
+      // ---- tf32x3 helper role: lo = a - trunc_tf32(a) for the A and B tiles of every stage (elementwise, so the
+      // swizzled layout is irrelevant), written TC_STAGE_BYTES above the tiles with the same layout
+      constexpr int kHelpers = kThreads - 64;
+      const int ht = threadIdx.x - 64;
+      for (int it = 0; it < n_iter; ++it) {
+        const int stage = it % TC_STAGES;
+        const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
+        mbar_wait(&full_bar[stage], phase);
+        float4* tile = reinterpret_cast<float4*>(smem + stage * kStageStride);
+        float4* low = reinterpret_cast<float4*>(smem + stage * kStageStride + TC_STAGE_BYTES);
+#pragma unroll
+        for (int i = ht; i < TC_STAGE_BYTES / 16; i += kHelpers) {
+          const float4 a = tile[i];
+          low[i] = make_float4(tf32_low(a.x), tf32_low(a.y), tf32_low(a.z), tf32_low(a.w));
+        }
+        fence_proxy_async();              // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[stage]);
+      }
+    }
     const int lq = warp & 3;              // TMEM lane quarter this warp may access
     const Group e = ctx.g;                // register copy: no reloads behind the global stores
     const int m = m0 + lq * 32 + lane;
@@ -395,7 +451,7 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
       }
       __syncwarp();
     }
-    constexpr int kEpiWarps = tc_threads(TC_STAGES) / 32 - 2;
+    constexpr int kEpiWarps = kThreads / 32 - 2;
     constexpr int kColChunks = (TC_BN / 32) * 4 / kEpiWarps;      // column chunks of 32 per warp: 4 or 2
     const int c0 = ((warp - 2) / 4) * kColChunks;
 #pragma unroll 1
@@ -452,7 +508,7 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
     if (FIXUP && fix) {
       // all epilogue warps have issued their stores -> one thread publishes (or, for the owner, re-arms) the counter
       __threadfence();
-      asm volatile("bar.sync 1, %0;" ::"n"((tc_threads(TC_STAGES) / 32 - 2) * 32) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"((kThreads / 32 - 2) * 32) : "memory");
       if (warp == 2 && lane == 0) {
         if (owner)
           *reinterpret_cast<volatile int*>(flag) = 0;
@@ -492,9 +548,10 @@ struct MapKey {
   int box_inner, box_outer;
   int atom32;   // 1: SWIZZLE_128B_ATOM_32B (MN-major operands), 0: SWIZZLE_128B
   int rank3;    // 1: MN-major operand as {32 floats, outer rows, inner/32 groups}, box {32, box_outer, 4}
+  int raw;      // 1: FLOAT32 map (bits as stored; tf32x3 engine), 0: TFLOAT32 (TMA rounds to nearest tf32)
   bool operator<(const MapKey& o) const {
-    return std::tie(ptr, inner, outer, ld, box_inner, box_outer, atom32, rank3) <
-           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer, o.atom32, o.rank3);
+    return std::tie(ptr, inner, outer, ld, box_inner, box_outer, atom32, rank3, raw) <
+           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer, o.atom32, o.rank3, o.raw);
   }
 };
 
@@ -523,7 +580,7 @@ inline int encode_map(const MapKey& k, CUtensorMap* out) {
     const char* e = getenv("TA3N_TMA_RAW_FP32");
     return e && e[0] == '1';
   }();
-  CUresult r = fn(out, raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, k.rank3 ? 3 : 2,
+  CUresult r = fn(out, (raw || k.raw) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, k.rank3 ? 3 : 2,
                   const_cast<void*>(k.ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   k.atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -581,9 +638,25 @@ inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSe
   return after_launch();
 }
 
+// tf32x3 engine: 3 stages of 64 KB, 320 threads, one CTA per SM
+template <bool A_KMAJ, bool B_KMAJ>
+inline int tc_launch_x3(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
+                        const char* label) {
+  auto kernel = seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, TC_X3_STAGES, false, true>;
+  static bool configured = false;
+  if (!configured) {
+    TA3N_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_x3_smem_bytes()));
+    configured = true;
+  }
+  pre_launch(label, stream);
+  launch_kernel(kernel, tab.total_tiles, 320, tc_x3_smem_bytes(), stream, tab, maps, sm, 0, static_cast<int*>(nullptr));
+  return after_launch();
+}
+
 template <bool A_KMAJ, bool B_KMAJ>
 inline int tc_launch_one(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
-                         const char* label, int* fix_flags) {
+                         const char* label, int* fix_flags, bool x3 = false) {
+  if (x3) return tc_launch_x3<A_KMAJ, B_KMAJ>(tab, maps, sm, stream, label);
   static const int force = []() {
     const char* e = getenv("TA3N_TC_STAGES");
     return e ? atoi(e) : 0;
@@ -711,7 +784,7 @@ inline GemmPlan sub_plan(const GemmPlan& plan, const std::vector<int>& idx) {
 }
 
 // Launch `plan` (all groups eligible) on the tcgen05 engine.
-inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool fixup = false) {
+inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool fixup = false, bool x3 = false) {
   // longest-K groups first (see the tile remap in the kernel): LPT-style balance of the tensor pipe
   std::vector<int> order(plan_in.groups.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
@@ -749,10 +822,11 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool fixup = 
       std::map<MapKey, int> trial = local;
       for (int i = 0; i < src.seg_count; ++i) {
         const Seg& s = plan.segs[src.seg_begin + i];
-        MapKey ka = plan.a_kmaj ? MapKey{s.A, s.len, src.M, s.lda, TC_BK, TC_BM, 0, 0}
-                                : MapKey{s.A, src.M, s.len, s.lda, 32, TC_BK, 1, a3d ? 1 : 0};
-        MapKey kb = plan.b_kmaj ? MapKey{s.B, s.len, src.N, s.ldb, TC_BK, TC_BN, 0, 0}
-                                : MapKey{s.B, src.N, s.len, s.ldb, 32, TC_BK, 1, b3d ? 1 : 0};
+        const int raw = x3 ? 1 : 0;
+        MapKey ka = plan.a_kmaj ? MapKey{s.A, s.len, src.M, s.lda, TC_BK, TC_BM, 0, 0, raw}
+                                : MapKey{s.A, src.M, s.len, s.lda, 32, TC_BK, 1, a3d ? 1 : 0, raw};
+        MapKey kb = plan.b_kmaj ? MapKey{s.B, s.len, src.N, s.ldb, TC_BK, TC_BN, 0, 0, raw}
+                                : MapKey{s.B, src.N, s.len, s.ldb, 32, TC_BK, 1, b3d ? 1 : 0, raw};
         for (const MapKey& k : {ka, kb})
           if (!trial.count(k)) trial[k] = nmaps + fresh++;
         keys.push_back({ka, kb});
@@ -802,13 +876,13 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool fixup = 
     tab.pad_ = (a3d ? 1 : 0) | (b3d ? 2 : 0);
     if (tiles > 0) {
       if (plan.a_kmaj && plan.b_kmaj)
-        TA3N_TRY((tc_launch_one<true, true>(tab, maps, sm, stream, plan.label, fix_flags)));
+        TA3N_TRY((tc_launch_one<true, true>(tab, maps, sm, stream, plan.label, fix_flags, x3)));
       else if (plan.a_kmaj && !plan.b_kmaj)
-        TA3N_TRY((tc_launch_one<true, false>(tab, maps, sm, stream, plan.label, fix_flags)));
+        TA3N_TRY((tc_launch_one<true, false>(tab, maps, sm, stream, plan.label, fix_flags, x3)));
       else if (!plan.a_kmaj && !plan.b_kmaj)
-        TA3N_TRY((tc_launch_one<false, false>(tab, maps, sm, stream, plan.label, fix_flags)));
+        TA3N_TRY((tc_launch_one<false, false>(tab, maps, sm, stream, plan.label, fix_flags, x3)));
       else
-        TA3N_TRY((tc_launch_one<false, true>(tab, maps, sm, stream, plan.label, fix_flags)));
+        TA3N_TRY((tc_launch_one<false, true>(tab, maps, sm, stream, plan.label, fix_flags, x3)));
       if (any_split) {
         dim3 grid(splitk_reduce_blocks(tab), ng);
         pre_launch("splitk_reduce", stream);
@@ -828,18 +902,20 @@ inline int run_gemm(GemmPlan& plan, cudaStream_t stream, Arena* splitk_arena = n
   for (auto& g : plan.groups)
     if (g.M <= 0 || g.N <= 0 || g.seg_count <= 0)
       return fail(TA3N_ERR_INVALID, "seg_gemm: empty group M=%d N=%d segs=%d", g.M, g.N, g.seg_count);
-  if (gemm_engine().load() == TA3N_GEMM_TF32_TCGEN05) {
+  const int engine = gemm_engine().load();
+  if (engine == TA3N_GEMM_TF32_TCGEN05 || engine == TA3N_GEMM_TF32X3_TCGEN05) {
+    const bool x3 = engine == TA3N_GEMM_TF32X3_TCGEN05;
     std::vector<int> tc_idx, simt_idx;
     for (int i = 0; i < (int)plan.groups.size(); ++i) (tc_group_ok(plan, plan.groups[i]) ? tc_idx : simt_idx).push_back(i);
     if (!tc_idx.empty()) {
       GemmPlan tc = sub_plan(plan, tc_idx);
       plan_splitk(tc, splitk_arena, TC_BM, TC_BN, TC_BK, 4);
       bool fixup = false;
-      if (fixup_enabled() && splitk_arena) {
+      if (!x3 && fixup_enabled() && splitk_arena) {
         plan_balance_splitk(tc, splitk_arena);      // no-op when plan_splitk already split something
         for (const Group& g : tc.groups) fixup |= g.ksplit > 1;
       }
-      TA3N_TRY(launch_tc(tc, stream, fixup));
+      TA3N_TRY(launch_tc(tc, stream, fixup, x3));
     }
     if (!simt_idx.empty()) {
       GemmPlan rest = sub_plan(plan, simt_idx);

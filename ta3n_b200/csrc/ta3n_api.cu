@@ -216,7 +216,7 @@ const char* ta3n_last_error(void) { return last_error_buf(); }
 uint64_t ta3n_launch_count(void) { return launch_counter().load(); }
 void ta3n_reset_launch_count(void) { launch_counter().store(0); }
 int ta3n_set_gemm_engine(int engine) {
-  if (engine != TA3N_GEMM_FP32_SIMT && engine != TA3N_GEMM_TF32_TCGEN05)
+  if (engine != TA3N_GEMM_FP32_SIMT && engine != TA3N_GEMM_TF32_TCGEN05 && engine != TA3N_GEMM_TF32X3_TCGEN05)
     return fail(TA3N_ERR_INVALID, "unknown GEMM engine %d", engine);
   gemm_engine().store(engine);
   return TA3N_OK;

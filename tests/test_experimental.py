@@ -2,7 +2,8 @@
 
 Knobs: TA3N_FIXUP_SPLITK=1 in-kernel split-K fix-up with balanced per-group split
 factors; TA3N_L2_PREFETCH=<slabs> TMA L2 prefetch distance; TA3N_DESC_PREFETCH=1 tensor-map descriptor prefetch;
-TA3N_SIMT_MAX_MNK=<M*N*K> small GEMMs on the fp32 SIMT engine."""
+TA3N_SIMT_MAX_MNK=<M*N*K> small GEMMs on the fp32 SIMT engine; TA3N_TEST_TF32X3=1 adds the experimental 'tf32x3'
+engine (three tf32 MMAs per step on hi/lo operand splits) to the engines the parity tests run, at the fp32 tolerances."""
 import os
 import subprocess
 import sys
@@ -16,7 +17,7 @@ pytestmark = [pytest.mark.gpu,
 
 
 KNOBS = [{"TA3N_FIXUP_SPLITK": "1"}, {"TA3N_L2_PREFETCH": "16"}, {"TA3N_DESC_PREFETCH": "1"},
-         {"TA3N_SIMT_MAX_MNK": "40000000"},
+         {"TA3N_SIMT_MAX_MNK": "40000000"}, {"TA3N_TEST_TF32X3": "1"},
          {"TA3N_FIXUP_SPLITK": "1", "TA3N_L2_PREFETCH": "16", "TA3N_DESC_PREFETCH": "1", "TA3N_SIMT_MAX_MNK": "40000000"}]
 
 

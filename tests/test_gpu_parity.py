@@ -19,16 +19,19 @@ pytestmark = pytest.mark.gpu
 
 ENGINES = ["fp32", "tf32"]
 TOL = {"fp32": 2e-4, "tf32": TOL_PATH}
+if os.environ.get("TA3N_TEST_TF32X3") == "1":     # experimental engine: held to the fp32 bounds
+    ENGINES.append("tf32x3")
+    TOL["tf32x3"] = 2e-4
 # Gradients under the tf32 engine, compared with the fp64 network WITHOUT pinning the activation
 # pattern: every product is accurate to ~3e-4, but ~2e-4 of the ReLU units sit within rounding error
 # of zero and flip, and each flip moves a gradient entry by O(1) -> normwise ~sqrt(2e-4) ~ 1-2.5e-2
 # (measured, tools/parity_report.py).  Inherent to ANY reduced-precision forward (cuBLAS TF32 and bf16
 # included).  With the realised pattern pinned the gradients agree to 2e-3 again
 # (test_tf32_gradients_match_oracle_on_realised_activation_pattern).
-GRAD_TOL = {"fp32": 2 * 2e-4, "tf32": 5e-2}
+GRAD_TOL = {"fp32": 2 * 2e-4, "tf32": 5e-2, "tf32x3": 2 * 2e-4}
 # Rounding-noise floor of sums that cancel (bias gradients of the domain heads): measured as
 # ||ref_fp32 - ref_fp64|| for the fp32 engine; tf32 carries 13 fewer mantissa bits.
-NOISE_SCALE = {"fp32": 1.0, "tf32": 2.0 ** 13}
+NOISE_SCALE = {"fp32": 1.0, "tf32": 2.0 ** 13, "tf32x3": 8.0}
 
 
 def _dev():

@@ -6,6 +6,8 @@ for v in 0 1; do
   TA3N_FIXUP_SPLITK=$v timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('fixup=$v', round(d['ms_per_step'],4), 'ms/step', {k: d['kernel_ms_per_step'][k] for k in ('fwd_batch','shared_fc_fwd','trn_dgrad','wgrad_all','disc_dgrad','disc_fwd','relattn_fwd','relattn_dgrad','splitk_reduce') if k in d['kernel_ms_per_step']})"
 done
+timeout 200 python bench.py --engine tf32x3 --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('engine=tf32x3', round(d['ms_per_step'],4), 'ms/step', {k: d['kernel_ms_per_step'][k] for k in ('fwd_batch','shared_fc_fwd','trn_dgrad','wgrad_all') if k in d['kernel_ms_per_step']})"
 TA3N_DESC_PREFETCH=1 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('desc_prefetch=1', round(d['ms_per_step'],4), 'ms/step')"
 for mnk in 40000000; do      # the 512x256x256 layers: video + relation discriminators, fwd and dgrad
