@@ -243,6 +243,12 @@ int ta3n_gemm_ex(const float* A, int lda, int a_kmajor, const float* B, int ldb,
                  float* C, int ldc, int M, int N, int K, void* workspace, size_t workspace_bytes,
                  ta3n_stream_t stream);
 
+/* Host-only: the split-K balance model of the experimental in-kernel fix-up.  n groups with
+ * tiles[i] output tiles of slabs[i] 32-wide K slabs each -> split factor per group in ksplit[i] (all 1 when
+ * splitting does not shorten the modelled critical path by >= 15 % or would exceed one resident wave).
+ * Returns the modelled makespan (slabs) of the returned plan.  No CUDA call; usable without a GPU.          */
+long long ta3n_debug_balance_splitk(int n, const long long* tiles, const long long* slabs, int* ksplit);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,8 @@ SIGNATURES = {
     "ta3n_loss_fwd_bwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _F, _I, _VP, _VP, _VP, _VP, _VP, _VP,
                                _VP, _SZ, _VP]),
     "ta3n_counter_inc": (_I, [_VP, _VP]),
+    "ta3n_debug_balance_splitk": (C.c_longlong, [_I, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                                 C.POINTER(C.c_int)]),
     "ta3n_sgd_workspace_bytes": (_SZ, []),
     "ta3n_sgd_nesterov_step": (_I, [_VP, _VP, _VP, C.c_longlong, _VP, _F, _F, _F, _VP, _SZ, _VP, _VP]),
     "ta3n_gemm_tn": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP]),

@@ -722,40 +722,57 @@ inline long tc_makespan(const std::vector<long>& cta_slabs) {
 }
 
 // Choose per-group split factors that shorten the modelled makespan of a launch whose tiles are few and uneven
-// (the critical tile of the forward batch is 80 slabs against 36 per SM on average).  Only with the fix-up: a
-// separate reduce pass costs more than this saves.
-inline void plan_balance_splitk(GemmPlan& plan, Arena* arena) {
-  if (!arena) return;
-  const int ng = (int)plan.groups.size();
-  std::vector<long> tiles(ng), slabs(ng);
+// (the critical tile of the forward batch is 80 slabs against 36 per SM on average).  Pure host logic: `tiles[i]`
+// output tiles of `slabs[i]` K slabs each -> split factor per group (all 1 when splitting is not worth it).
+inline std::vector<int> balance_split_factors(const std::vector<long>& tiles, const std::vector<long>& slabs) {
+  const int ng = (int)tiles.size();
   long total = 0;
-  for (int i = 0; i < ng; ++i) {
-    const Group& g = plan.groups[i];
-    if (g.ksplit > 1) return;   // already planned
-    tiles[i] = (long)((g.M + TC_BM - 1) / TC_BM) * ((g.N + TC_BN - 1) / TC_BN);
-    slabs[i] = 0;
-    for (int k = 0; k < g.seg_count; ++k) slabs[i] += (plan.segs[g.seg_begin + k].len + TC_BK - 1) / TC_BK;
-    total += tiles[i] * slabs[i];
-  }
+  for (int i = 0; i < ng; ++i) total += tiles[i] * slabs[i];
   auto model = [&](const std::vector<int>& ks) {
     std::vector<long> ctas;
     for (int i = 0; i < ng; ++i)
       for (long t = 0; t < tiles[i] * ks[i]; ++t) ctas.push_back((slabs[i] + ks[i] - 1) / ks[i] + 2);   // +2: fix-up
     return tc_makespan(ctas);
   };
-  std::vector<int> ks(ng, 1);
-  const long before = model(ks);
+  std::vector<int> ones(ng, 1), best(ng, 1);
+  const long before = model(ones);
+  long best_span = before;
   const long target = std::max<long>(12, (long)(1.15 * (double)total / 148.0));
-  long n_ctas = 0;
-  for (int i = 0; i < ng; ++i) {
-    int want = (int)((slabs[i] + target - 1) / target);
-    want = std::min(want, 4);
-    while (want > 1 && slabs[i] / want < 8) --want;
-    ks[i] = std::max(want, 1);
-    n_ctas += tiles[i] * ks[i];
+  for (int bump = 0; bump <= 1; ++bump) {          // the even-load split, and one step finer (80 tiles: 3 beats 2)
+    std::vector<int> ks(ng, 1);
+    long n_ctas = 0;
+    for (int i = 0; i < ng; ++i) {
+      int want = (int)((slabs[i] + target - 1) / target);
+      if (want > 1 || bump) want += bump;
+      want = std::min(want, 4);
+      while (want > 1 && slabs[i] / want < 8) --want;
+      ks[i] = std::max(want, 1);
+      n_ctas += tiles[i] * ks[i];
+    }
+    if (n_ctas > 256) continue;                                // every CTA resident at once, with headroom
+    const long span = model(ks);
+    if (span < best_span) {
+      best_span = span;
+      best = ks;
+    }
   }
-  if (n_ctas > 256) return;                                    // every CTA resident at once, with headroom
-  if (model(ks) * 100 > before * 85) return;                   // needs >= 15 % shorter critical path
+  if (best_span * 100 > before * 85) return ones;              // needs >= 15 % shorter critical path
+  return best;
+}
+
+// Only with the fix-up: a separate reduce pass costs more than the balance saves.
+inline void plan_balance_splitk(GemmPlan& plan, Arena* arena) {
+  if (!arena) return;
+  const int ng = (int)plan.groups.size();
+  std::vector<long> tiles(ng), slabs(ng);
+  for (int i = 0; i < ng; ++i) {
+    const Group& g = plan.groups[i];
+    if (g.ksplit > 1) return;   // already planned
+    tiles[i] = (long)((g.M + TC_BM - 1) / TC_BM) * ((g.N + TC_BN - 1) / TC_BN);
+    slabs[i] = 0;
+    for (int k = 0; k < g.seg_count; ++k) slabs[i] += (plan.segs[g.seg_begin + k].len + TC_BK - 1) / TC_BK;
+  }
+  const std::vector<int> ks = balance_split_factors(tiles, slabs);
   for (int i = 0; i < ng; ++i) {
     if (ks[i] < 2) continue;
     Group& g = plan.groups[i];

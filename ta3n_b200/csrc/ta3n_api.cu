@@ -814,6 +814,18 @@ int ta3n_counter_inc(uint64_t* counter, ta3n_stream_t stream) {
   return after_launch();
 }
 
+long long ta3n_debug_balance_splitk(int n, const long long* tiles, const long long* slabs, int* ksplit) {
+  if (n <= 0 || !tiles || !slabs || !ksplit) return -1;
+  std::vector<long> t(tiles, tiles + n), s(slabs, slabs + n);
+  const std::vector<int> ks = balance_split_factors(t, s);
+  std::vector<long> ctas;
+  for (int i = 0; i < n; ++i) {
+    ksplit[i] = ks[i];
+    for (long c = 0; c < t[i] * ks[i]; ++c) ctas.push_back((s[i] + ks[i] - 1) / ks[i] + (ks[i] > 1 ? 2 : 0));
+  }
+  return tc_makespan(ctas);
+}
+
 // ---- optimizer step: clip_grad_norm_ + SGD-Nesterov over flat buffers (main.py:83, 578-583) ----
 size_t ta3n_sgd_workspace_bytes(void) { return Arena::round(kSqnormBlocks * sizeof(float)); }
 
