@@ -18,4 +18,5 @@ for pf in 8 16 32; do
   TA3N_L2_PREFETCH=$pf timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('l2_prefetch=$pf', round(d['ms_per_step'],4), 'ms/step', {k: d['kernel_ms_per_step'][k] for k in ('fwd_batch','shared_fc_fwd','trn_dgrad','wgrad_all') if k in d['kernel_ms_per_step']})"
 done
+X3=1 timeout 120 python tools/parity_report.py 256 5 2>&1 | tail -50
 TA3N_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_experimental.py -m gpu -q 2>&1 | tail -5

@@ -1,5 +1,6 @@
 """Print normwise relative errors (vs the fp64 CPU oracle) of every output and parameter gradient
-of the CUDA path, per GEMM engine.  Run on a GPU box:  python tools/parity_report.py [B] [T]"""
+of the CUDA path, per GEMM engine.  Run on a GPU box:  python tools/parity_report.py [B] [T]
+X3=1 adds a column for the experimental 'tf32x3' engine."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -30,7 +31,8 @@ def rel(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
 res = {}
-for eng in ("fp32", "tf32"):
+X3 = os.environ.get("X3", "0") == "1"
+for eng in ("fp32", "tf32") + (("tf32x3",) if X3 else ()):
     ta3n_b200.set_gemm_engine(eng)
     m = VideoModel(12, "video", "trn-m", "RGB", train_segments=T, val_segments=T, fc_dim=512, dropout_i=0.0,
                    dropout_v=0.0, partial_bn=False, verbose=False)
@@ -71,7 +73,8 @@ for n in g64:
     ref["grad:" + n] = rel(g32[n], g64[n])
 print(f"# B={B}+{B} T={T} perturbed={os.environ.get('PERTURB','1')}  normwise rel err vs fp64 oracle")
 print(f"# ReLU units whose on/off state differs between the tf32 CUDA forward and the fp64 oracle: {flips} of {total} ({flips/total:.2e})")
-print(f"{'tensor':58s} {'cpu fp32':>10s} {'cuda fp32':>10s} {'cuda tf32':>10s} {'tf32 pinned':>12s}")
+print(f"{'tensor':58s} {'cpu fp32':>10s} {'cuda fp32':>10s} {'cuda tf32':>10s} {'tf32 pinned':>12s}" + (f" {'cuda tf32x3':>12s}" if X3 else ""))
 for k in res["fp32"]:
     pin = f"{pinned[k]:12.2e}" if k in pinned else f"{'':>12s}"
-    print(f"{k:58s} {ref[k]:10.2e} {res['fp32'][k]:10.2e} {res['tf32'][k]:10.2e} {pin}")
+    x3 = f" {res['tf32x3'][k]:12.2e}" if X3 else ""
+    print(f"{k:58s} {ref[k]:10.2e} {res['fp32'][k]:10.2e} {res['tf32'][k]:10.2e} {pin}{x3}")
