@@ -2,7 +2,7 @@
 """bench.py -- throughput of the TA3N hot path on B200 (metric of BASELINE.json).
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path through the C ABI)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0
+    python bench.py --impl reference --gpus N --steps K ...  # the unmodified reference on the host cores, rank 0
 
 One "step" = one paired mini-batch (B source + B target videos, T=5, D=2048) through
 VideoModel.forward (train mode, dropout 0.5/0.5), the composed loss of the shipped script
@@ -157,7 +157,8 @@ def pick_engine(requested):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU implementation of the path (oracle port) on the host cores
+# reference arm: the reference's own CPU implementation of the path on the host cores (unmodified classes from
+# the oracle/_ref snapshot; the oracle port only if that snapshot is missing)
 # ------------------------------------------------------------------------------------------------
 def host_cores() -> int:
     """Cores this process may really use: affinity mask and cgroup CPU quota, not os.cpu_count()."""
@@ -171,11 +172,47 @@ def host_cores() -> int:
     return max(1, n)
 
 
-def cpu_reference_run(args, steps, warmup, budget_s=None):
-    import torch
+def _reference_step_fn(args):
+    """One training step (forward + composed loss + backward) of the UNMODIFIED reference classes on CPU:
+    models.VideoModel / TRNmodule / loss.attentive_entropy imported through oracle/ref_shims.py from
+    /root/reference (build container) or from the oracle/_ref snapshot made by oracle/build_ref.py (GPU box).
+    Protocol of BASELINE.md section 2.  Returns (step, kind) or (None, why)."""
+    try:
+        import torch
+
+        from oracle import gen_golden, ref_shims
+        if ref_shims.models_root() is None:
+            return None, "no reference modules (oracle/_ref snapshot missing)"
+        ref_models, _, _ = ref_shims.load()
+        torch.manual_seed(1234)
+        model = ref_models.VideoModel(args.classes, "video", "trn-m", "RGB", train_segments=args.segments,
+                                      val_segments=args.segments, add_fc=1, fc_dim=args.fc_dim, dropout_i=0.5,
+                                      dropout_v=0.5, partial_bn=False, use_bn="none", ens_DA="none",
+                                      use_attn="TransAttn", n_attn=1, use_attn_frame="none", share_params="Y",
+                                      verbose=False)
+        model.train()
+        g = torch.Generator().manual_seed(4321)
+        xs = torch.randn(args.batch, args.segments, D, generator=g)
+        xt = torch.randn(args.batch, args.segments, D, generator=g)
+        labels = torch.arange(args.batch) % args.classes
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            outs = model(xs, xt, list(BETA), 0, is_train=True, reverse=False)        # main.py:418
+            loss = gen_golden.reference_loss(outs, labels)                           # main.py:446, 508-538, 559-562
+            loss.backward()                                                          # main.py:576
+            return loss
+
+        step()
+        return step, "reference"
+    except Exception as e:      # the port below is the documented fallback; say why
+        return None, f"{type(e).__name__}: {e}"
+
+
+def _port_step_fn(args):
+    import torch  # noqa: F401
 
     from oracle import ta3n_oracle as orc          # checker / CPU baseline only (never the product path)
-    avail = host_cores()
     cfg = orc.PathConfig(num_class=args.classes, num_segments=args.segments, fc_dim=args.fc_dim,
                          dropout_i=0.5, dropout_v=0.5)
     params = orc.init_params(cfg, seed=1234)
@@ -192,6 +229,19 @@ def cpu_reference_run(args, steps, warmup, budget_s=None):
         loss = orc.compose_loss(outs, labels, GAMMA)
         loss.backward()
         return loss
+
+    return step
+
+
+def cpu_reference_run(args, steps, warmup, budget_s=None):
+    import torch
+
+    avail = host_cores()
+    step, kind = _reference_step_fn(args)
+    why_port = None
+    if step is None:
+        why_port, kind = kind, "port"
+        step = _port_step_fn(args)
 
     # "all the host threads it can use": eager PyTorch stops scaling (and can collapse) well before
     # 100+ threads on these small GEMMs, so time one step per candidate count and keep the fastest.
@@ -218,8 +268,10 @@ def cpu_reference_run(args, steps, warmup, budget_s=None):
         if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 3:
             break
     dt = time.perf_counter() - t0
+    what = ("the UNMODIFIED reference classes (models.VideoModel + TRNmodule + loss.py via oracle/ref_shims.py)"
+            if kind == "reference" else "the oracle port (eager PyTorch CPU restatement of the reference)")
     return {"clips_per_s": done * 2 * args.batch / dt, "ms_per_step": 1e3 * dt / done, "steps": done,
-            "cores": cores, "cores_available": avail}
+            "cores": cores, "cores_available": avail, "kind": kind, "what": what, "why_port": why_port}
 
 
 def run_reference(args):
@@ -227,15 +279,15 @@ def run_reference(args):
     if rank != 0:
         return
     r = cpu_reference_run(args, args.steps, args.warmup)
-    sample = (f"{r['steps']} full steps of the oracle port (eager PyTorch CPU restatement of the reference) at "
-              f"B={args.batch}+{args.batch}, T={args.segments}, D={D}")
+    sample = (f"{r['steps']} full steps of {r['what']} at B={args.batch}+{args.batch}, T={args.segments}, D={D}, "
+              f"train mode, dropout 0.5/0.5, forward + composed loss + backward")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["clips_per_s"], "unit": "clips/s", "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1, "cpu"),
+        "config": workload_config(args, 1, "cpu"), "gemm_engine": "cpu fp32 (ATen/MKL)",
         "cpu_baseline": {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "cores_available": r["cores_available"],
-                         "kind": "port", "sample": sample},
+                         "kind": r["kind"], "sample": sample, "why_port": r["why_port"]},
         "e2e": {"value": r["clips_per_s"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -251,7 +303,7 @@ def workload_config(args, world, engine):
             "step": "forward + composed loss + backward to all parameter gradients"
                     + (" + flat NCCL gradient all-reduce" if world > 1 else ""),
             "optimizer": "excluded from value (metric is fwd+bwd); included in e2e",
-            "dropout": "0.5/0.5, in-kernel counter RNG", "gemm_engine": engine,
+            "dropout": "0.5/0.5 (product arm: in-kernel counter RNG; reference arm: nn.Dropout)",
             "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) before every timed step",
             "timing": "CUDA events around each step on the launching stream; steps enqueued behind a 20 ms "
                       "device-side spin so host launch gaps are outside the events"}
@@ -457,7 +509,7 @@ def run_b200(args):
         "metric": METRIC, "value": world * 2 * B * args.steps / (t_ms * 1e-3), "unit": "clips/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3"}.get(engine, "tf32"),
-        "data": "synthetic", "config": workload_config(args, world, engine),
+        "data": "synthetic", "config": workload_config(args, world, engine), "gemm_engine": engine,
         "roofline": roof,
         "roofline_step": {"bound": "hbm", "scope": "whole step (SURVEY 8d scope B)", "achieved": ach_b,
                           "peak": hbm_peak, "unit": "GB/s", "frac": ach_b / hbm_peak,
@@ -479,9 +531,9 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, 1000, 2, budget_s=args.cpu_seconds)
         line["cpu_baseline"] = {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"],
-                                "cores_available": r["cores_available"], "kind": "port",
-                                "ms_per_step": r["ms_per_step"],
-                                "sample": f"{r['steps']} full steps (B={B}+{B}) of the oracle port on the host "
+                                "cores_available": r["cores_available"], "kind": r["kind"],
+                                "ms_per_step": r["ms_per_step"], "why_port": r["why_port"],
+                                "sample": f"{r['steps']} full steps (B={B}+{B}) of {r['what']} on the host "
                                           f"cores, ~{args.cpu_seconds:.0f}s budget"}
     print_json(line)
     if world > 1:

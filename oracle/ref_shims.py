@@ -19,16 +19,37 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("TA3N_REFERENCE_ROOT", "/root/reference")
+# byte copies of models.py / TRNmodule.py / loss.py made by oracle/build_ref.py in the build container
+# (git-ignored, shipped to the GPU box like a built .so) -- used where /root/reference does not exist
+SNAPSHOT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ta3n_ref_modules.zip")
 
 
 def available() -> bool:
+    """The full reference tree (models + dataset + ...) is present: build container only."""
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "models.py"))
+
+
+def models_root():
+    """sys.path entry holding the unmodified models.py / TRNmodule.py / loss.py: the reference tree, else the
+    oracle/_ref archive (zipimport), else None."""
+    if all(os.path.isfile(os.path.join(REFERENCE_ROOT, f)) for f in ("models.py", "TRNmodule.py", "loss.py")):
+        return REFERENCE_ROOT
+    if os.path.isfile(SNAPSHOT_ROOT):
+        import zipfile
+        try:
+            with zipfile.ZipFile(SNAPSHOT_ROOT) as z:
+                if all(f in z.namelist() for f in ("models.py", "TRNmodule.py", "loss.py")):
+                    return SNAPSHOT_ROOT
+        except zipfile.BadZipFile:
+            pass
+    return None
 
 
 def load():
     """Return the reference's (models, TRNmodule, loss) modules."""
-    if not available():
-        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    root = models_root()
+    if root is None:
+        raise RuntimeError(f"reference modules found neither at {REFERENCE_ROOT} nor at {SNAPSHOT_ROOT}")
     import torch
     import torchvision
 
@@ -50,10 +71,10 @@ def load():
 
     torchvision.models.resnet101 = lambda *a, **k: _HeadOnly()
 
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     saved = {k: sys.modules.pop(k) for k in ("models", "TRNmodule", "loss") if k in sys.modules
-             and not getattr(sys.modules[k], "__file__", "").startswith(REFERENCE_ROOT)}
+             and not (getattr(sys.modules[k], "__file__", "") or "").startswith(root)}
     try:
         import TRNmodule as ref_trn     # noqa: E402
         import loss as ref_loss         # noqa: E402
