@@ -45,9 +45,7 @@ enum {
 /* GEMM engines for the dense contractions. */
 enum {
   TA3N_GEMM_FP32_SIMT = 0,   /* exact fp32 FFMA tiles (parity / debugging engine)     */
-  TA3N_GEMM_TF32_TCGEN05 = 1, /* tcgen05.mma kind::tf32, TMA-staged, TMEM accumulators */
-  TA3N_GEMM_TF32X3_TCGEN05 = 2 /* EXPERIMENTAL: same pipeline, three tf32 MMAs per step on hi/lo operand
-                                   splits -> fp32-grade products at unchanged operand traffic */
+  TA3N_GEMM_TF32_TCGEN05 = 1 /* tcgen05.mma kind::tf32, TMA-staged, TMEM accumulators (the default) */
 };
 
 typedef void* ta3n_stream_t; /* cudaStream_t */
@@ -185,8 +183,8 @@ int ta3n_video_head_bwd(const float* dropped, int M, int H, int C, const float* 
 /* Between begin and flush (same host thread) ta3n_disc_fwd and ta3n_trn_fwd only register their GEMMs;
  * the flush issues them as ONE grouped launch followed by their light follow-up kernels.  Only calls
  * whose inputs are already final may be batched together (e.g. the frame discriminator and the TRN,
- * which both read the shared features when use_attn_frame == 'none').  The workspace (optional, may be
- * NULL / 0) is only used by the experimental balanced split-K of the grouped launch.                    */
+ * which both read the shared features when use_attn_frame == 'none').  The workspace arguments are reserved
+ * (may be NULL / 0).                                                                                     */
 int ta3n_fwd_batch_begin(void);
 size_t ta3n_fwd_batch_workspace_bytes(void);
 int ta3n_fwd_batch_flush(void* workspace, size_t workspace_bytes, ta3n_stream_t stream);
@@ -219,6 +217,104 @@ int ta3n_loss_fwd_bwd(const float* pred_video, const long long* labels, const fl
 /* *counter += 1 on the stream (dropout step counter for CUDA-graph replays). */
 int ta3n_counter_inc(uint64_t* counter, ta3n_stream_t stream);
 
+/* ---- the fused training step (SURVEY 8a rows a1-a13 + 8f row n1 in one launch) ---------------------------- */
+/* main.py:418 (model forward, models.py:545-722 trn-m branch), main.py:446, 508-538, 559-562 (composed loss:
+ * class CE + domain CE per adversarial level + gamma * attentive entropy, loss.py:15-25) and main.py:576
+ * (backward to every parameter gradient) for one paired mini-batch, use_attn_frame == 'none'.
+ *
+ * Everything is described once by a ta3n_step_desc (device pointers unless noted).  Two executors give
+ * bit-identical results:
+ *   ta3n_step_run_phased : one launch per dependency level -- 6 grouped tcgen05 GEMM launches, 1 fused per-video
+ *                          row kernel, 2 column-sum launches (9 launches; the round-1 sequence had 25);
+ *   ta3n_step_build + ta3n_step_run : the same work as ONE persistent kernel (one CTA per SM) that pulls GEMM
+ *                          tiles / row tasks / column-sum tasks from a queue and synchronises them through arrival
+ *                          counters in global memory (csrc/step_kernel.cuh) -- plus one memset node for the counters.
+ * Both are CUDA-graph capturable (ta3n_step_build itself is not: it copies the task graph to the device).        */
+typedef struct {
+  int Bs, Bt;                 /* source / target videos of the mini-batch (M = Bs + Bt rows, source first)         */
+  int T, D, F, H, C;          /* frames per video, input width, shared width (fc_dim), bottleneck (256), classes    */
+  int use_attn;               /* 1: use_attn='TransAttn', 0: 'none' (models.py:646-648)                             */
+  int loss_flags;             /* as ta3n_loss_fwd_bwd: 1 relation / 2 video / 4 frame adversarial CE, 8 attentive entropy */
+  float gamma;                /* weight of the attentive entropy (main.py:561)                                      */
+  float domain_weight[2];     /* criterion_domain weights (main.py:165-167); {1, 1} = unweighted                    */
+  const float* class_weight;  /* [C] criterion weights (main.py:160-163, 204) or NULL                               */
+  const float* beta_dev;      /* [3] {relation, video, frame} GRL coefficients in DEVICE memory, so that the per-step
+                                 DANN schedule (main.py:350-352) replays inside a captured graph                     */
+  const ta3n_relation_table* tab;
+  /* inputs */
+  const float* x_src;         /* [Bs, T, D] */
+  const float* x_tgt;         /* [Bt, T, D] */
+  const long long* labels;    /* [Bs] */
+  const int* valid_rows;      /* {real source rows, real target rows} or NULL (see ta3n_loss_fwd_bwd)               */
+  ta3n_dropout drop_i, drop_v;/* dropout of the shared layer / of the video features (p <= 0: none)                 */
+  /* parameters and their gradients; *_host are HOST arrays of R = T-1 device pointers                               */
+  const float *W_sh, *b_sh;                 /* fc_feature_shared_source   [F, D], [F]                                */
+  const float *W1f, *b1f, *W2f, *b2f;       /* fc_feature_domain [F, F], fc_classifier_domain [2, F]                 */
+  const float* const* W_trn_host;           /* TRN.fc_fusion_scales[i][1] [H, (T-i) F]                               */
+  const float* const* b_trn_host;
+  const float* const* W1r_host;             /* relation_domain_classifier_all[i][0] [H, H], [i][2] [2, H]            */
+  const float* const* b1r_host;
+  const float* const* W2r_host;
+  const float* const* b2r_host;
+  const float *Wc, *bc;                     /* fc_classifier_video_source [C, H]                                     */
+  const float *W1v, *b1v, *W2v, *b2v;       /* fc_feature_domain_video [H, H], fc_classifier_domain_video [2, H]     */
+  float *dW_sh, *db_sh, *dW1f, *db1f, *dW2f, *db2f;
+  float* const* dW_trn_host;
+  float* const* db_trn_host;
+  float* const* dW1r_host;
+  float* const* db1r_host;
+  float* const* dW2r_host;
+  float* const* db2r_host;
+  float *dWc, *dbc, *dW1v, *db1v, *dW2v, *db2v;
+  /* outputs / saved activations (caller-provided, M = Bs + Bt rows)                                                  */
+  float* feat;                /* [M*T, F]   shared features (post ReLU / dropout)                                    */
+  float* hid_f;               /* [M*T, F]   frame-discriminator hidden layer                                         */
+  float* pred_frame;          /* [M*T, 2]                                                                            */
+  float* act;                 /* [n_rel, M, H] relation activations                                                  */
+  float* feat_rel;            /* [M, R, H]                                                                           */
+  float* hid_r;               /* [R, M, H]  relation-discriminator hidden layers                                     */
+  float* pred_rel;            /* [M, R, 2]                                                                           */
+  float* attn;                /* [M, R]                                                                              */
+  float* feat_video;          /* [M, H]                                                                              */
+  float* dropped;             /* [M, H]                                                                              */
+  float* pred_video;          /* [M, C]                                                                              */
+  float* hid_v;               /* [M, H]                                                                              */
+  float* pred_dom;            /* [M, 2]                                                                              */
+  float* loss;                /* [1]                                                                                 */
+  uint64_t* step_counter;     /* optional: += 1 at the END of the step (dropout RNG key of the next replay)          */
+  void* workspace;            /* ta3n_step_workspace_bytes(desc) bytes of scratch                                    */
+  size_t workspace_bytes;
+} ta3n_step_desc;
+
+#define TA3N_STEP_HANDLE_BYTES 256
+size_t ta3n_step_workspace_bytes(const ta3n_step_desc* desc);
+int ta3n_step_run_phased(const ta3n_step_desc* desc, ta3n_stream_t stream);
+size_t ta3n_step_plan_bytes(const ta3n_step_desc* desc);
+/* Builds the task graph for `desc` (pointers are baked in) into plan_dev (device, ta3n_step_plan_bytes(desc) bytes;
+ * synchronous copy) and fills handle_host (HOST memory, TA3N_STEP_HANDLE_BYTES bytes) for ta3n_step_run.           */
+int ta3n_step_build(const ta3n_step_desc* desc, void* plan_dev, size_t plan_bytes, void* handle_host);
+int ta3n_step_run(const void* handle_host, ta3n_stream_t stream);
+/* Host-only summary of the task graph of `desc` (counts per task type, arrival counters, K slabs, and the number of
+ * waits that earlier tasks cannot satisfy -- must be 0: the deadlock-freedom invariant).  No CUDA call.            */
+size_t ta3n_step_describe(const ta3n_step_desc* desc, char* buf, size_t buf_bytes);
+/* Optional per-task trace: trace_dev (device, n_tasks * 4 uint64) receives {SM id, scheduled, accumulator ready, done}
+ * (globaltimer ns) of every task of the following runs; NULL switches it off.  tools/step_trace.py reads it.        */
+int ta3n_step_set_trace(void* handle_host, unsigned long long* trace_dev);
+/* number of tasks / arrival counters of a built plan (diagnostics) */
+int ta3n_step_info(const void* handle_host, int* n_tasks, int* n_counters, int* n_gemm_tiles);
+
+/* ---- gradient all-reduce over NVLink / NVSwitch peer memory (replaces nn.DataParallel's reduce, main.py:79) */
+/* In-place MEAN over the `world` ranks of one node of n floats (n % 4 == 0) that live at the same offset of a symmetric,
+ * peer-mapped allocation on every rank.  peer_bufs_host / peer_flags_host: HOST arrays of `world` device pointers -- this
+ * process's mappings of every rank's buffer / flag array ([rank] = the local one); flag arrays hold
+ * ta3n_allreduce_flag_bytes(world) bytes, zero-initialised once.  multicast_buf: the NVSwitch multicast mapping of the
+ * buffer (the switch reduces in flight: multimem.ld_reduce / multimem.st) or NULL (peer loads / stores).  *seq_dev: a
+ * device counter with the same value on every rank that has INCREASED since the previous call (the train step's step
+ * counter).  One kernel, two-shot, deterministic, bit-identical results on all ranks, CUDA-graph capturable.        */
+size_t ta3n_allreduce_flag_bytes(int world);
+int ta3n_allreduce_mean(float* const* peer_bufs_host, float* multicast_buf, uint32_t* const* peer_flags_host,
+                        const uint64_t* seq_dev, int rank, int world, long long n, ta3n_stream_t stream);
+
 /* ---- optimizer step ---------------------------------------------------- */
 /* main.py:578-581 clip_grad_norm_(parameters, max_norm) followed by main.py:83/583
  * torch.optim.SGD(lr, momentum, weight_decay, nesterov=True).step(), over FLAT fp32 buffers of n
@@ -242,12 +338,6 @@ int ta3n_gemm_tn(const float* A, const float* B, float* C, int M, int N, int K,
 int ta3n_gemm_ex(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor,
                  float* C, int ldc, int M, int N, int K, void* workspace, size_t workspace_bytes,
                  ta3n_stream_t stream);
-
-/* Host-only: the split-K balance model of the experimental in-kernel fix-up.  n groups with
- * tiles[i] output tiles of slabs[i] 32-wide K slabs each -> split factor per group in ksplit[i] (all 1 when
- * splitting does not shorten the modelled critical path by >= 15 % or would exceed one resident wave).
- * Returns the modelled makespan (slabs) of the returned plan.  No CUDA call; usable without a GPU.          */
-long long ta3n_debug_balance_splitk(int n, const long long* tiles, const long long* slabs, int* ksplit);
 
 #ifdef __cplusplus
 }

@@ -390,16 +390,22 @@ def attentive_entropy(pred: torch.Tensor, pred_domain: torch.Tensor) -> torch.Te
 
 
 def compose_loss(outputs, label_source: torch.Tensor, gamma: float = 0.003,
-                 place_adv: Sequence[str] = ("Y", "Y", "Y"), use_attn: str = "TransAttn") -> torch.Tensor:
+                 place_adv: Sequence[str] = ("Y", "Y", "Y"), use_attn: str = "TransAttn",
+                 class_weight: Optional[torch.Tensor] = None,
+                 domain_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
     """use_target='uSv', adv_DA='RevGrad', add_loss_DA='attentive_entropy'.
 
+    main.py:160-167  weight_source_class (--weighted_class_loss) / weight_domain_loss (--weighted_class_loss_DA)
+    main.py:204-205  criterion = CrossEntropyLoss(weight=weight_source_class), criterion_domain = ...(weight_domain_loss)
     main.py:446      class CE on source only
     main.py:508-538  for l in (relation, video, frame): CE(cat(pred_S, pred_T), cat(0s, 1s))
     main.py:559-562  + gamma * attentive_entropy(cat(out_S, out_T), pred_domain_all[1])
                      (only when use_attn != 'none', main.py:559)
     """
     (_, out_s, _, pd_s, _, _, out_t, _, pd_t, _) = outputs
-    loss = F.cross_entropy(out_s, label_source)
+    cw = None if class_weight is None else class_weight.to(out_s.dtype)
+    dw = None if domain_weight is None else torch.as_tensor(domain_weight).to(out_s.dtype)
+    loss = F.cross_entropy(out_s, label_source, weight=cw)
     stacked = []
     for lvl, flag in enumerate(place_adv):
         if flag != "Y":
@@ -410,21 +416,23 @@ def compose_loss(outputs, label_source: torch.Tensor, gamma: float = 0.003,
                          torch.ones(pt.size(0), dtype=torch.long)])
         both = torch.cat([ps, pt], 0)
         stacked.append(both)
-        loss = loss + F.cross_entropy(both, dom)
+        loss = loss + F.cross_entropy(both, dom, weight=dw)
     if use_attn != "none" and len(stacked) > 1:
         loss = loss + gamma * attentive_entropy(torch.cat([out_s, out_t], 0), stacked[1])
     return loss
 
 
 def train_step(params: Dict[str, torch.Tensor], xs, xt, labels, beta, cfg: PathConfig,
-               gamma: float = 0.003, train: bool = True, masks=None, gates=None):
+               gamma: float = 0.003, train: bool = True, masks=None, gates=None, class_weight=None,
+               domain_weight=None):
     """forward + composed loss + backward; returns (loss, outputs, grads-by-name)."""
     names = used_param_names(params)
     leaves = {k: params[k].detach().clone().requires_grad_(True) for k in names}
     live = dict(params)
     live.update(leaves)
     outs = forward(live, xs, xt, beta, 0.0, cfg, train=train, reverse=False, masks=masks, gates=gates)
-    loss = compose_loss(outs, labels, gamma, use_attn=cfg.use_attn)
+    loss = compose_loss(outs, labels, gamma, use_attn=cfg.use_attn, class_weight=class_weight,
+                        domain_weight=domain_weight)
     grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
     return loss.detach(), outs, OrderedDict(zip(names, grads))
 

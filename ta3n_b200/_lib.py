@@ -13,7 +13,6 @@ from . import build as _build
 
 TA3N_GEMM_FP32_SIMT = 0
 TA3N_GEMM_TF32_TCGEN05 = 1
-TA3N_GEMM_TF32X3_TCGEN05 = 2     # experimental
 
 
 class RelationTable(C.Structure):
@@ -25,6 +24,30 @@ class RelationTable(C.Structure):
 class Dropout(C.Structure):
     _fields_ = [("p", C.c_float), ("keep", C.c_void_p), ("seed", C.c_uint64), ("step_dev", C.c_void_p)]
 
+
+class StepDesc(C.Structure):
+    """ta3n_step_desc of include/ta3n_b200.h (same field order)."""
+    _fields_ = (
+        [(n, C.c_int) for n in ("Bs", "Bt", "T", "D", "F", "H", "C", "use_attn", "loss_flags")] +
+        [("gamma", C.c_float), ("domain_weight", C.c_float * 2), ("class_weight", C.c_void_p),
+         ("beta_dev", C.c_void_p), ("tab", C.POINTER(RelationTable)),
+         ("x_src", C.c_void_p), ("x_tgt", C.c_void_p), ("labels", C.c_void_p), ("valid_rows", C.c_void_p),
+         ("drop_i", Dropout), ("drop_v", Dropout)] +
+        [(n, C.c_void_p) for n in ("W_sh", "b_sh", "W1f", "b1f", "W2f", "b2f")] +
+        [(n, C.POINTER(C.c_void_p)) for n in ("W_trn_host", "b_trn_host", "W1r_host", "b1r_host", "W2r_host",
+                                              "b2r_host")] +
+        [(n, C.c_void_p) for n in ("Wc", "bc", "W1v", "b1v", "W2v", "b2v")] +
+        [(n, C.c_void_p) for n in ("dW_sh", "db_sh", "dW1f", "db1f", "dW2f", "db2f")] +
+        [(n, C.POINTER(C.c_void_p)) for n in ("dW_trn_host", "db_trn_host", "dW1r_host", "db1r_host", "dW2r_host",
+                                              "db2r_host")] +
+        [(n, C.c_void_p) for n in ("dWc", "dbc", "dW1v", "db1v", "dW2v", "db2v")] +
+        [(n, C.c_void_p) for n in ("feat", "hid_f", "pred_frame", "act", "feat_rel", "hid_r", "pred_rel", "attn",
+                                   "feat_video", "dropped", "pred_video", "hid_v", "pred_dom", "loss",
+                                   "step_counter", "workspace")] +
+        [("workspace_bytes", C.c_size_t)])
+
+
+STEP_HANDLE_BYTES = 256
 
 _VP, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _PP = C.POINTER(C.c_void_p)
@@ -70,8 +93,16 @@ SIGNATURES = {
     "ta3n_loss_fwd_bwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _F, _I, _VP, _VP, _VP, _VP, _VP, _VP,
                                _VP, _SZ, _VP]),
     "ta3n_counter_inc": (_I, [_VP, _VP]),
-    "ta3n_debug_balance_splitk": (C.c_longlong, [_I, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
-                                                 C.POINTER(C.c_int)]),
+    "ta3n_step_workspace_bytes": (_SZ, [C.POINTER(StepDesc)]),
+    "ta3n_step_run_phased": (_I, [C.POINTER(StepDesc), _VP]),
+    "ta3n_step_plan_bytes": (_SZ, [C.POINTER(StepDesc)]),
+    "ta3n_step_build": (_I, [C.POINTER(StepDesc), _VP, _SZ, _VP]),
+    "ta3n_step_run": (_I, [_VP, _VP]),
+    "ta3n_step_describe": (_SZ, [C.POINTER(StepDesc), C.c_char_p, _SZ]),
+    "ta3n_step_set_trace": (_I, [_VP, _VP]),
+    "ta3n_step_info": (_I, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ta3n_allreduce_flag_bytes": (_SZ, [_I]),
+    "ta3n_allreduce_mean": (_I, [_PP, _VP, _PP, _VP, _I, _I, C.c_longlong, _VP]),
     "ta3n_sgd_workspace_bytes": (_SZ, []),
     "ta3n_sgd_nesterov_step": (_I, [_VP, _VP, _VP, C.c_longlong, _VP, _F, _F, _F, _VP, _SZ, _VP, _VP]),
     "ta3n_gemm_tn": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP]),
@@ -125,15 +156,13 @@ def ptr_array(ptrs):
 
 
 def set_gemm_engine(engine) -> None:
-    """'fp32' (exact SIMT tiles), 'tf32' (tcgen05 tensor cores) or 'tf32x3' (experimental: three tf32 MMAs per
-    step on hi/lo operand splits, fp32-grade products)."""
-    code = {"fp32": TA3N_GEMM_FP32_SIMT, "tf32": TA3N_GEMM_TF32_TCGEN05,
-            "tf32x3": TA3N_GEMM_TF32X3_TCGEN05}.get(engine, engine)
+    """'tf32' (tcgen05 tensor cores; the library default) or 'fp32' (exact SIMT tiles)."""
+    code = {"fp32": TA3N_GEMM_FP32_SIMT, "tf32": TA3N_GEMM_TF32_TCGEN05}.get(engine, engine)
     check(load().ta3n_set_gemm_engine(int(code)))
 
 
 def get_gemm_engine() -> str:
-    return {0: "fp32", 1: "tf32", 2: "tf32x3"}[load().ta3n_get_gemm_engine()]
+    return {0: "fp32", 1: "tf32"}[load().ta3n_get_gemm_engine()]
 
 
 def launch_count() -> int:

@@ -10,7 +10,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libta3n_sm100.so")
 SOURCES = ["ta3n_api.cu"]
-HEADERS = ["common.cuh", "seg_gemm.cuh", "rowops.cuh", "gemm_tcgen05.cuh",
+HEADERS = ["common.cuh", "seg_gemm.cuh", "rowops.cuh", "gemm_tcgen05.cuh", "optim.cuh", "step_rows.cuh",
+           "step_kernel.cuh", "step_plan.cuh", "allreduce.cuh",
            os.path.join("..", "..", "include", "ta3n_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

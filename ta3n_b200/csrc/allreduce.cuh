@@ -1,0 +1,109 @@
+// allreduce.cuh -- in-place mean all-reduce of the flat gradient bucket over NVLink / NVSwitch peer memory, written
+// for the one collective of the path (the gradients of the used parameters, 13.9 MB at cfg2; replaces the
+// reduce-to-GPU-0 of nn.DataParallel, main.py:79).
+//
+// The bucket lives in a SYMMETRIC allocation (same size on every rank of the node, peer-mapped; optionally also
+// mapped through an NVSwitch multicast object).  Two-shot algorithm, one kernel, no host involvement:
+//   barrier 0 : every rank's bucket is complete (flags written into the peers' flag arrays with release stores);
+//   rank r owns slice r of the bucket: it reads that slice from every rank and sums it in rank order --
+//               multimem.ld_reduce (the switch adds the 8 copies in flight, NVLS) when a multicast mapping exists,
+//               peer loads otherwise -- scales by 1/world and writes the result into every rank's bucket
+//               (multimem.st / peer stores);
+//   barrier 1 : every slice has landed everywhere -> the kernel may complete, the optimizer kernel reads the mean.
+// Every slice is summed by exactly one rank and broadcast, so all ranks hold bit-identical gradients; the order of the
+// sum is fixed (rank order / switch order), so reruns are bit-identical too.  The kernel is CUDA-graph capturable
+// (plain device pointers), which NCCL collectives were not in practice (round 1: process-group teardown hang).
+#pragma once
+
+#include "common.cuh"
+
+namespace ta3n {
+
+constexpr int kArMaxWorld = 16;
+constexpr int kArBlocks = 64;
+constexpr int kArThreads = 1024;
+
+struct ArPeers {
+  float* buf[kArMaxWorld];          // peer mappings of the bucket ([rank] = local)
+  unsigned* flags[kArMaxWorld];     // peer mappings of the flag arrays: [2][kArBlocks][world] uint32 each
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+// all blocks `b` of all ranks meet: slot = (phase, b); one flag per source rank
+__device__ __forceinline__ void ar_barrier(const ArPeers& P, int rank, int world, int phase, unsigned seq) {
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    const int p = threadIdx.x;
+    const size_t slot = ((size_t)phase * kArBlocks + blockIdx.x) * world;
+    st_release_sys(P.flags[p] + slot + rank, seq);
+    unsigned spins = 0;
+    while ((int)(ld_acquire_sys(P.flags[rank] + slot + p) - seq) < 0) {
+      __nanosleep(32);
+      if (++spins > (1u << 25)) __trap();     // a missing peer becomes an error, not a hung GPU
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kArThreads, 1)
+allreduce_mean_kernel(const __grid_constant__ ArPeers P, float* __restrict__ mc, const unsigned long long* __restrict__ seq_dev,
+                      const int rank, const int world, const size_t n4, const float scale) {
+  pdl_wait();
+  const unsigned seq = (unsigned)seq_dev[0];
+  ar_barrier(P, rank, world, 0, seq);
+  const size_t s0 = n4 * (size_t)rank / world, s1 = n4 * (size_t)(rank + 1) / world;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (mc != nullptr) {
+    for (size_t i = s0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += stride) {
+      float4 v = multimem_ld_reduce_add(mc + 4 * i);
+      v.x *= scale;
+      v.y *= scale;
+      v.z *= scale;
+      v.w *= scale;
+      multimem_st(mc + 4 * i, v);
+    }
+  } else {
+    for (size_t i = s0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += stride) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int p = 0; p < world; ++p) {       // fixed rank order; `world` independent loads in flight
+        const float4 x = __ldcg(reinterpret_cast<const float4*>(P.buf[p]) + i);
+        acc.x += x.x;
+        acc.y += x.y;
+        acc.z += x.z;
+        acc.w += x.w;
+      }
+      acc.x *= scale;
+      acc.y *= scale;
+      acc.z *= scale;
+      acc.w *= scale;
+#pragma unroll 8
+      for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(P.buf[p])[i] = acc;
+    }
+  }
+  ar_barrier(P, rank, world, 1, seq);
+}
+
+}  // namespace ta3n

@@ -43,11 +43,7 @@ constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 // loop) for grids beyond a wave; 6 stages (193 KB, one CTA per SM, twice the bytes in flight per CTA)
 // for the sub-wave grids of this workload, where a CTA is alone on its SM and TMA latency-bound.
 constexpr int tc_smem_bytes(int stages) { return stages * TC_STAGE_BYTES + 1024; }   // + 1024 B alignment slack
-// X3 ("tf32x3", experimental engine 2): fp32-grade products from three tf32 MMAs per K step.  A stage then also
-// holds the low-order halves of both operand tiles (64 KB), three stages, one CTA per SM, 8 helper/epilogue warps.
-constexpr int TC_X3_STAGES = 3;
-constexpr int tc_x3_smem_bytes() { return TC_X3_STAGES * 2 * TC_STAGE_BYTES + 1024; }
-constexpr int TC_TMEM_COLS = 128;
+constexpr int TC_TMEM_COLS = 128;      // per-launch kernel: one accumulator; the step kernel allocates two
 #ifndef TA3N_MAX_MAPS
 #define TA3N_MAX_MAPS 64
 #endif
@@ -186,50 +182,214 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(bool a_kmaj, bool b_kmaj,
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// a - trunc_tf32(a): what the tensor core drops when it reads raw fp32 bits (0 for inf / nan, which the leading
-// product already propagates)
-__device__ __forceinline__ float tf32_low(float a) {
-  const uint32_t u = __float_as_uint(a);
-  return (u & 0x7f800000u) == 0x7f800000u ? 0.f : a - __uint_as_float(u & 0xffffe000u);
+// ---- one output tile, by warp role ---------------------------------------------------------------------
+// Shared by the per-launch kernel below (one tile per CTA, all roles in lockstep) and by the persistent step kernel
+// (step_kernel.cuh), where the three roles run their own loops over the task queue: the producer and the MMA issuer
+// of tile t+1 work while the epilogue warps still drain tile t (two TMEM accumulator buffers).
+// The operand ring barriers are initialised once per CTA; each role keeps its own running slab count.
+struct TcShared {
+  uint64_t full_bar[6];
+  uint64_t empty_bar[6];
+  uint64_t tmem_full_bar[2];
+  uint64_t tmem_empty_bar[2];
+  uint32_t tmem_slot;
+};
+
+template <int TC_STAGES>
+__device__ __forceinline__ void tc_pipe_init(TcShared* sh, int epi_warps) {
+  for (int s = 0; s < TC_STAGES; ++s) {
+    mbar_init(&sh->full_bar[s], 1);
+    mbar_init(&sh->empty_bar[s], 1);
+  }
+  for (int a = 0; a < 2; ++a) {
+    mbar_init(&sh->tmem_full_bar[a], 1);
+    mbar_init(&sh->tmem_empty_bar[a], epi_warps);
+  }
+  fence_barrier_init();
 }
 
-// ---- the kernel -------------------------------------------------------------------------------------
-// FIXUP (experimental, TA3N_FIXUP_SPLITK=1): groups with fix_slot >= 0 fold their split-K partials inside this
-// kernel instead of a reduce pass.  Splits 0 .. ksplit-2 of a tile write their raw accumulators to `partial` and
-// bump the tile's arrival counter (release); the LAST split acquires the counter after its own K range, adds the
-// partials in a fixed order in its register epilogue, runs the fused epilogue and resets the counter for the next
-// launch.  Nobody but the last split ever waits, and the host only plans such launches when every CTA is resident
-// at once (<= 256 CTAs at two per SM), so the wait cannot starve the blocks it waits for; a bounded spin turns
-// any violation of that assumption into a trap instead of a hang.
-//
-// X3 (experimental engine "tf32x3"): the tensor maps deliver RAW fp32 bits; the tensor core reads only the top 19
-// bits of an operand, i.e. hi = trunc_tf32(a).  The helper warps (idle during the main loop otherwise) compute
-// lo = a - hi (exact in fp32) for both tiles of a stage into a second pair of buffers, and the MMA thread issues
-// A*B + A*B_lo + A_lo*B per K step: relative error ~3 * 2^-20 per product instead of 2^-11, at unchanged operand
-// traffic -- the main loop is bound by the fill bandwidth, the tensor pipe is 26 % busy with one MMA per step.
-template <bool A_KMAJ, bool B_KMAJ, int TC_STAGES, bool FIXUP, bool X3 = false>
-__global__ void __launch_bounds__(X3 ? 320 : tc_threads(TC_STAGES), (X3 || TC_STAGES > 3) ? 1 : 2)
-seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant__ TcMaps maps,
-                   const __grid_constant__ TcSegMaps segmaps, const int dbg, int* __restrict__ fix_flags) {
-  static_assert(!X3 || (TC_STAGES == TC_X3_STAGES && !FIXUP), "tf32x3 variant: 3 stages, no fix-up");
-  constexpr int kThreads = X3 ? 320 : tc_threads(TC_STAGES);
-  constexpr int kStageStride = X3 ? 2 * TC_STAGE_BYTES : TC_STAGE_BYTES;
-  extern __shared__ uint8_t tc_smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
-  __shared__ __align__(8) uint64_t split_bar[TC_STAGES];     // X3: low-order tiles of the stage are ready
-  __shared__ __align__(8) uint64_t tmem_full_bar;
-  __shared__ uint32_t tmem_slot;
+// What a tile of a split-K group does with its accumulator:
+//   TILE_FINAL   : fused epilogue -> C                       (ksplit == 1)
+//   TILE_PARTIAL : raw accumulator -> partial[split]         (separate reduce pass, or an owner tile below)
+//   TILE_OWNER   : adds partial[0 .. ksplit-2] in a fixed order, then fused epilogue -> C.  The caller guarantees
+//                  those partials are complete and visible (step kernel: task dependency).
+enum : int { TILE_FINAL = 0, TILE_PARTIAL = 1, TILE_OWNER = 2 };
 
+// TMA producer (ONE thread): the n_iter K slabs [c_begin, c_begin + n_iter) of tile (m0, n0) into the ring.
+// `slabs` = slabs this CTA has pushed so far (advanced by the caller).
+template <int TC_STAGES>
+__device__ __forceinline__ void tc_produce(const TileCtx& ctx, const CUtensorMap* __restrict__ maps, const bool a_kmaj,
+                                           const bool b_kmaj, const int pad_flags, const int m0, const int n0,
+                                           const int c_begin, const int n_iter, uint8_t* smem, TcShared* sh,
+                                           const uint32_t slabs) {
+  const Group& g = ctx.g;
+  int seg = 0, k0 = 0;
+  {
+    int skip = c_begin;
+    while (seg < g.seg_count) {
+      const int nch = (ctx.seg[seg].len + TC_BK - 1) / TC_BK;
+      if (skip < nch) {
+        k0 = skip * TC_BK;
+        break;
+      }
+      skip -= nch;
+      ++seg;
+    }
+  }
+  for (int it = 0; it < n_iter; ++it) {
+    const uint32_t gl = slabs + (uint32_t)it;
+    const int stage = (int)(gl % TC_STAGES);
+    const uint32_t phase = (gl / TC_STAGES) & 1u;
+    mbar_wait(&sh->empty_bar[stage], phase ^ 1u);
+    mbar_expect_tx(&sh->full_bar[stage], TC_STAGE_BYTES);
+    uint8_t* sA = smem + stage * TC_STAGE_BYTES;
+    uint8_t* sB = sA + TC_A_BYTES;
+    const CUtensorMap* ma = &maps[ctx.seg[seg].amap];
+    const CUtensorMap* mb = &maps[ctx.seg[seg].bmap];
+    // MN-major tiles are four [32 k-rows][32 floats] slabs, one per group of 32 m (or n).  When the operand's
+    // MN extent is a multiple of 32 a rank-3 tensor map {32 floats, k rows, groups of 32} fetches all four with
+    // ONE instruction (the lone producer thread is issue-bound: ~50 cycles per TMA, 8 per chunk otherwise).
+    if (a_kmaj) {
+      tma_load_2d(sA, ma, &sh->full_bar[stage], k0, m0);
+    } else if (pad_flags & 1) {
+      tma_load_3d(sA, ma, &sh->full_bar[stage], 0, k0, m0 >> 5);
+    } else {
+#pragma unroll
+      for (int q = 0; q < TC_BM / 32; ++q) tma_load_2d(sA + q * 4096, ma, &sh->full_bar[stage], m0 + 32 * q, k0);
+    }
+    if (b_kmaj) {
+      tma_load_2d(sB, mb, &sh->full_bar[stage], k0, n0);
+    } else if (pad_flags & 2) {
+      tma_load_3d(sB, mb, &sh->full_bar[stage], 0, k0, n0 >> 5);
+    } else {
+#pragma unroll
+      for (int q = 0; q < TC_BN / 32; ++q) tma_load_2d(sB + q * 4096, mb, &sh->full_bar[stage], n0 + 32 * q, k0);
+    }
+    k0 += TC_BK;
+    if (k0 >= ctx.seg[seg].len) {
+      ++seg;
+      k0 = 0;
+    }
+  }
+}
+
+// MMA issuer (ONE thread): accumulates the n_iter slabs into TMEM buffer `acc` (columns acc*128 ..).
+template <int TC_STAGES>
+__device__ __forceinline__ void tc_mma(const bool a_kmaj, const bool b_kmaj, const int n_iter, uint8_t* smem, TcShared* sh,
+                                       const uint32_t tmem_base, const int acc, const uint32_t slabs) {
+  const uint32_t idesc = umma_idesc_tf32(a_kmaj, b_kmaj, TC_BM, TC_BN);
+  const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
+  for (int it = 0; it < n_iter; ++it) {
+    const uint32_t gl = slabs + (uint32_t)it;
+    const int stage = (int)(gl % TC_STAGES);
+    const uint32_t phase = (gl / TC_STAGES) & 1u;
+    mbar_wait(&sh->full_bar[stage], phase);
+    tc_fence_after();
+    const uint32_t a_base = smem_u32(smem + stage * TC_STAGE_BYTES);
+    const uint32_t b_base = a_base + TC_A_BYTES;
+#pragma unroll
+    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+      const uint64_t adesc = a_kmaj ? umma_desc_kmajor(a_base, ks) : umma_desc_mnmajor(a_base, ks);
+      const uint64_t bdesc = b_kmaj ? umma_desc_kmajor(b_base, ks) : umma_desc_mnmajor(b_base, ks);
+      umma_tf32(tmem_d, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+    }
+    umma_commit(&sh->empty_bar[stage]);   // releases the smem slot once these MMAs have read it
+  }
+  umma_commit(&sh->tmem_full_bar[acc]);   // accumulator complete
+}
+
+// Epilogue (kEpiWarps warps; `ew` = this warp's index among them, 0-based; warp id % 4 must equal (ew + 2) % 4, i.e.
+// the epilogue warps are warps 2 .. 2 + kEpiWarps - 1 of the CTA).  Lane i of a warp owns accumulator row 32*lq + i;
+// tcgen05.ld hands it 32 consecutive columns, which it finishes (fused epilogue) and writes as 8 x 16 B stores:
+// every 128 B line of C is written whole.  The caller has waited for tmem_full.
+template <int kEpiWarps>
+__device__ __forceinline__ void tc_epilogue(const TileCtx& ctx, const int m0, const int n0, const int split,
+                                            const int n_iter, const int mode, const uint32_t tmem_base, const int acc,
+                                            const int ew) {
+  const int lane = threadIdx.x & 31;
+  const int lq = (ew + 2) & 3;          // TMEM lane quarter this warp may access
+  const Group e = ctx.g;                // register copy: no reloads behind the global stores
+  const int m = m0 + lq * 32 + lane;
+  const bool split_out = mode == TILE_PARTIAL;
+  float* const obase = split_out ? e.partial + (size_t)split * e.M * e.N : e.C;
+  const int ldo = split_out ? e.N : e.ldc;
+  constexpr int kColChunks = (TC_BN / 32) * 4 / kEpiWarps;      // column chunks of 32 per warp: 4 or 2
+  const int c0 = (ew / 4) * kColChunks;
+#pragma unroll 1
+  for (int c = c0; c < c0 + kColChunks; ++c) {
+    float v[32];
+    if (n_iter > 0) {
+      tmem_ld_32x32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32), v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    const int nb = n0 + c * 32;
+    if (m < e.M && nb < e.N) {
+      float* orow = obase + (size_t)m * ldo + nb;
+      const int nvalid = min(32, e.N - nb);
+      if (mode == TILE_OWNER) {      // raw partial sums of the other splits, fixed order, straight from L2
+        for (int sp = 0; sp < e.ksplit - 1; ++sp) {
+          const float* pr = e.partial + (size_t)sp * e.M * e.N + (size_t)m * e.N + nb;
+          if (nvalid >= 32 && (reinterpret_cast<uintptr_t>(pr) & 15u) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldcg(reinterpret_cast<const float4*>(pr + j));
+              v[j] += t.x;
+              v[j + 1] += t.y;
+              v[j + 2] += t.z;
+              v[j + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) v[j] += __ldcg(pr + j);
+          }
+        }
+      }
+      if (!split_out) {
+        TA3N_EPI_DISPATCH(e.flags, { epilogue_row32<EPI_F>(e, m, nb, nvalid, v); })
+      }
+      if (nb + 32 <= e.N && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < e.N) orow[j] = v[j];
+      }
+    }
+  }
+  tc_fence_before();                    // TMEM reads ordered before whatever lets the next MMA reuse the buffer
+}
+
+// chunk range [c_begin, c_begin + n_iter) of split `split` of the group staged in ctx
+__device__ __forceinline__ void tc_chunk_range(const TileCtx& ctx, int split, int* c_begin, int* n_iter) {
+  const Group& g = ctx.g;
+  int total_chunks = 0;
+  for (int s = 0; s < g.seg_count; ++s) total_chunks += (ctx.seg[s].len + TC_BK - 1) / TC_BK;
+  const int cps = (total_chunks + g.ksplit - 1) / g.ksplit;
+  *c_begin = split * cps;
+  *n_iter = max(0, min(total_chunks, *c_begin + cps) - *c_begin);
+}
+
+// ---- the per-launch kernel: one tile per CTA ---------------------------------------------------------
+template <bool A_KMAJ, bool B_KMAJ, int TC_STAGES>
+__global__ void __launch_bounds__(tc_threads(TC_STAGES), TC_STAGES > 3 ? 1 : 2)
+seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant__ TcMaps maps,
+                   const __grid_constant__ TcSegMaps segmaps, const int first_wave) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  __shared__ __align__(8) TcShared sh;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- tile decode (same scheme as the SIMT engine, 128x128 tiles); group + segments staged in smem ----
   __shared__ TileCtx ctx;
-  // Groups arrive sorted by K (longest first).  CTAs beyond the first wave of 148 take tiles from the END
+  // Groups arrive sorted by K (longest first).  CTAs beyond the first wave (one per SM) take tiles from the END
   // of the list, so the SM that received the longest tile gets the shortest one as its second resident CTA.
   int tile = blockIdx.x;
-  if (tile >= 148) tile = tab.total_tiles - 1 - (tile - 148);
+  if (tile >= first_wave) tile = tab.total_tiles - 1 - (tile - first_wave);
   load_tile_ctx(tab, tile, &ctx, segmaps.a, segmaps.b);
   const Group& g = ctx.g;
   int local = tile - g.tile_begin;
@@ -238,289 +398,36 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
   local -= split * per_split;
   const int m0 = (local / g.tiles_n) * TC_BM;
   const int n0 = (local % g.tiles_n) * TC_BN;
-
-  int total_chunks = 0;
-  for (int s = 0; s < g.seg_count; ++s) total_chunks += (ctx.seg[s].len + TC_BK - 1) / TC_BK;
-  const int cps = (total_chunks + g.ksplit - 1) / g.ksplit;
-  const int c_begin = split * cps;
-  const int c_end = min(total_chunks, c_begin + cps);
-  int n_iter = max(0, c_end - c_begin);
-  if (dbg & 4) n_iter = 0;       // debug: no TMA / MMA
-  if (dbg & 8) return;           // debug: nothing at all
+  int c_begin, n_iter;
+  tc_chunk_range(ctx, split, &c_begin, &n_iter);
 
   // ---- one-time setup ----
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-      mbar_init(&split_bar[s], kThreads / 32 - 2);      // one arrival per helper warp (X3 only)
-    }
-    mbar_init(&tmem_full_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1 && !(dbg & 2)) tmem_alloc(&tmem_slot, TC_TMEM_COLS);
-  if (warp == 0 && (dbg & (1 << 24))) {
-    // Experimental (TA3N_DESC_PREFETCH=1, default off): the tensor maps are kernel parameters, so their
-    // descriptors can be pulled into the TMA unit's cache here, under the previous kernel's tail, instead of
-    // stalling the first load of every segment.
-    for (int sgi = lane; sgi < g.seg_count; sgi += 32) {
-      tma_prefetch_desc(&maps.m[ctx.seg[sgi].amap]);
-      tma_prefetch_desc(&maps.m[ctx.seg[sgi].bmap]);
-    }
-  }
+  constexpr int kEpiWarps = tc_threads(TC_STAGES) / 32 - 2;
+  if (warp == 0 && lane == 0) tc_pipe_init<TC_STAGES>(&sh, kEpiWarps);
+  if (warp == 1) tmem_alloc(&sh.tmem_slot, TC_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = sh.tmem_slot;
   // Everything above touched only kernel parameters, shared memory and TMEM: it overlaps the previous
   // kernel of the stream.  From here on operands produced by that kernel are read.
   pdl_wait();
-  if (dbg & 16) {                // debug: setup + teardown only
-    __syncthreads();
-    if (warp == 1 && !(dbg & 2)) tmem_dealloc(tmem_base, TC_TMEM_COLS);
-    return;
-  }
 
+  const int mode = g.ksplit > 1 ? TILE_PARTIAL : TILE_FINAL;
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0 && n_iter > 0) {
-      int seg = 0, k0 = 0;
-      {
-        int skip = c_begin;
-        while (seg < g.seg_count) {
-          const int nch = (ctx.seg[seg].len + TC_BK - 1) / TC_BK;
-          if (skip < nch) {
-            k0 = skip * TC_BK;
-            break;
-          }
-          skip -= nch;
-          ++seg;
-        }
-      }
-      // Experimental (TA3N_L2_PREFETCH=<slabs>, default 0 = off): TMA prefetch into L2 `pf` slabs ahead of the
-      // loads.  The first GEMMs of a step read inputs and weights that are cold in L2 (HBM latency ~2x an L2 hit)
-      // with only TC_STAGES slabs in flight per SM; an L2 prefetch needs no shared memory, so it can run far ahead.
-      const int pf = (dbg >> 16) & 0xff;
-      int pseg = seg, pk0 = k0, pleft = 0;
-      if (pf > 0) {
-        pleft = n_iter;
-        for (int a = 0; a < pf && pleft > 0; ++a) {      // skip the first pf slabs: the real loads fetch those
-          --pleft;
-          pk0 += TC_BK;
-          if (pk0 >= ctx.seg[pseg].len) {
-            ++pseg;
-            pk0 = 0;
-          }
-        }
-      }
-      for (int it = 0; it < n_iter; ++it) {
-        if (pleft > 0) {
-          const CUtensorMap* pa = &maps.m[ctx.seg[pseg].amap];
-          const CUtensorMap* pb = &maps.m[ctx.seg[pseg].bmap];
-          if (A_KMAJ) {
-            tma_prefetch_2d(pa, pk0, m0);
-          } else if (tab.pad_ & 1) {
-            tma_prefetch_3d(pa, 0, pk0, m0 >> 5);
-          }
-          if (B_KMAJ) {
-            tma_prefetch_2d(pb, pk0, n0);
-          } else if (tab.pad_ & 2) {
-            tma_prefetch_3d(pb, 0, pk0, n0 >> 5);
-          }
-          --pleft;
-          pk0 += TC_BK;
-          if (pk0 >= ctx.seg[pseg].len) {
-            ++pseg;
-            pk0 = 0;
-          }
-        }
-        const int stage = it % TC_STAGES;
-        const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-        uint8_t* sA = smem + stage * kStageStride;
-        uint8_t* sB = sA + TC_A_BYTES;
-        const CUtensorMap* ma = &maps.m[ctx.seg[seg].amap];
-        const CUtensorMap* mb = &maps.m[ctx.seg[seg].bmap];
-        // MN-major tiles are four [32 k-rows][32 floats] slabs, one per group of 32 m (or n).  When the operand's
-        // MN extent is a multiple of 32 a rank-3 tensor map {32 floats, k rows, groups of 32} fetches all four with
-        // ONE instruction (the lone producer thread is issue-bound: ~50 cycles per TMA, 8 per chunk otherwise).
-        if (A_KMAJ) {
-          tma_load_2d(sA, ma, &full_bar[stage], k0, m0);
-        } else if (tab.pad_ & 1) {
-          tma_load_3d(sA, ma, &full_bar[stage], 0, k0, m0 >> 5);
-        } else {
-#pragma unroll
-          for (int q = 0; q < TC_BM / 32; ++q) tma_load_2d(sA + q * 4096, ma, &full_bar[stage], m0 + 32 * q, k0);
-        }
-        if (B_KMAJ) {
-          tma_load_2d(sB, mb, &full_bar[stage], k0, n0);
-        } else if (tab.pad_ & 2) {
-          tma_load_3d(sB, mb, &full_bar[stage], 0, k0, n0 >> 5);
-        } else {
-#pragma unroll
-          for (int q = 0; q < TC_BN / 32; ++q) tma_load_2d(sB + q * 4096, mb, &full_bar[stage], n0 + 32 * q, k0);
-        }
-        k0 += TC_BK;
-        if (k0 >= ctx.seg[seg].len) {
-          ++seg;
-          k0 = 0;
-        }
-      }
-    }
+    if (lane == 0 && n_iter > 0) tc_produce<TC_STAGES>(ctx, maps.m, A_KMAJ, B_KMAJ, tab.pad_, m0, n0, c_begin, n_iter, smem, &sh, 0u);
   } else if (warp == 1) {
-    // =========================== MMA issuer (one thread) ===========================
-    if (lane == 0 && n_iter > 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(A_KMAJ, B_KMAJ, TC_BM, TC_BN);
-      for (int it = 0; it < n_iter; ++it) {
-        const int stage = it % TC_STAGES;
-        const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
-        mbar_wait(X3 ? &split_bar[stage] : &full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * kStageStride);
-        const uint32_t b_base = a_base + TC_A_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < TC_BK / 8; ++ks) {
-          if ((dbg & 512) && ks > 0) break;   // debug: 1 of 4 MMAs (timing experiments only, wrong results)
-          const uint64_t adesc = A_KMAJ ? umma_desc_kmajor(a_base, ks) : umma_desc_mnmajor(a_base, ks);
-          const uint64_t bdesc = B_KMAJ ? umma_desc_kmajor(b_base, ks) : umma_desc_mnmajor(b_base, ks);
-          if (X3) {
-            // small terms first, then the leading product; the low-order tiles sit TC_STAGE_BYTES above their tiles
-            const uint32_t al = a_base + TC_STAGE_BYTES, bl = b_base + TC_STAGE_BYTES;
-            const uint64_t aldesc = A_KMAJ ? umma_desc_kmajor(al, ks) : umma_desc_mnmajor(al, ks);
-            const uint64_t bldesc = B_KMAJ ? umma_desc_kmajor(bl, ks) : umma_desc_mnmajor(bl, ks);
-            umma_tf32(tmem_base, adesc, bldesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-            umma_tf32(tmem_base, aldesc, bdesc, idesc, 1u);
-            umma_tf32(tmem_base, adesc, bdesc, idesc, 1u);
-          } else {
-            umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(&empty_bar[stage]);   // releases the smem slot once these MMAs have read it
-      }
-      umma_commit(&tmem_full_bar);        // accumulator complete
-    }
+    if (lane == 0 && n_iter > 0) tc_mma<TC_STAGES>(A_KMAJ, B_KMAJ, n_iter, smem, &sh, tmem_base, 0, 0u);
   } else {
-    // =========================== epilogue (4 warps, 32 TMEM lanes each) ===========================
-    // Lane i of warp lq owns accumulator row 32*lq + i; tcgen05.ld hands it 32 consecutive columns, which
-    // it finishes (fused epilogue) and writes as 8 x 16 B stores: every 128 B line of C is written whole.
-    if (X3 && n_iter > 0) {
-      // ---- tf32x3 helper role: lo = a - trunc_tf32(a) for the A and B tiles of every stage (elementwise, so the
-      // swizzled layout is irrelevant), written TC_STAGE_BYTES above the tiles with the same layout
-      constexpr int kHelpers = kThreads - 64;
-      const int ht = threadIdx.x - 64;
-      for (int it = 0; it < n_iter; ++it) {
-        const int stage = it % TC_STAGES;
-        const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
-        mbar_wait(&full_bar[stage], phase);
-        float4* tile = reinterpret_cast<float4*>(smem + stage * kStageStride);
-        float4* low = reinterpret_cast<float4*>(smem + stage * kStageStride + TC_STAGE_BYTES);
-#pragma unroll
-        for (int i = ht; i < TC_STAGE_BYTES / 16; i += kHelpers) {
-          const float4 a = tile[i];
-          low[i] = make_float4(tf32_low(a.x), tf32_low(a.y), tf32_low(a.z), tf32_low(a.w));
-        }
-        fence_proxy_async();              // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&split_bar[stage]);
-      }
-    }
-    const int lq = warp & 3;              // TMEM lane quarter this warp may access
-    const Group e = ctx.g;                // register copy: no reloads behind the global stores
-    const int m = m0 + lq * 32 + lane;
-    const bool fix = FIXUP && e.ksplit > 1 && e.fix_slot >= 0;
-    const bool owner = fix && split == e.ksplit - 1;
-    const bool split_out = e.ksplit > 1 && !owner;
-    float* const obase = split_out ? e.partial + (size_t)split * e.M * e.N : e.C;
-    const int ldo = split_out ? e.N : e.ldc;
-    int* const flag = fix ? fix_flags + e.fix_slot + local : nullptr;
     if (n_iter > 0) {
-      mbar_wait(&tmem_full_bar, 0);
+      mbar_wait(&sh.tmem_full_bar[0], 0u);
       tc_fence_after();
     }
-    if (FIXUP && owner) {
-      // wait until every other split of this tile has stored its partial (they are resident and never wait)
-      if (lane == 0) {
-        int seen = 0;
-        for (unsigned spin = 0; ; ++spin) {
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-          if (seen >= e.ksplit - 1) break;
-          if (spin > (1u << 22)) __trap();      // seconds: a protocol error becomes a trap, not a hung device
-          __nanosleep(128);
-        }
-      }
-      __syncwarp();
-    }
-    constexpr int kEpiWarps = kThreads / 32 - 2;
-    constexpr int kColChunks = (TC_BN / 32) * 4 / kEpiWarps;      // column chunks of 32 per warp: 4 or 2
-    const int c0 = ((warp - 2) / 4) * kColChunks;
-#pragma unroll 1
-    for (int c = c0; c < c0 + kColChunks; ++c) {
-      float v[32];
-      if (n_iter > 0 && !(dbg & 128)) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(c * 32), v);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-      const int nb = n0 + c * 32;
-      if (m < e.M && nb < e.N && !(dbg & 1) && (!(dbg & 32) || lane == 0)) {
-        float* orow = obase + (size_t)m * ldo + nb;
-        if (dbg & 64) {
-          orow[0] = v[0];
-          continue;
-        }
-        if (FIXUP && owner) {      // raw partial sums of the other splits, fixed order, straight from L2
-          const int nvalid = min(32, e.N - nb);
-          for (int sp = 0; sp < e.ksplit - 1; ++sp) {
-            const float* pr = e.partial + (size_t)sp * e.M * e.N + (size_t)m * e.N + nb;
-            if (nvalid >= 32 && (reinterpret_cast<uintptr_t>(pr) & 15u) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 t = __ldcg(reinterpret_cast<const float4*>(pr + j));
-                v[j] += t.x;
-                v[j + 1] += t.y;
-                v[j + 2] += t.z;
-                v[j + 3] += t.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) v[j] += __ldcg(pr + j);
-            }
-          }
-        }
-        if (!split_out && !(dbg & 256)) {
-          const int nvalid = min(32, e.N - nb);
-          TA3N_EPI_DISPATCH(e.flags, { epilogue_row32<EPI_F>(e, m, nb, nvalid, v); })
-        }
-        if (nb + 32 <= e.N && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < e.N) orow[j] = v[j];
-        }
-      }
-    }
-    if (FIXUP && fix) {
-      // all epilogue warps have issued their stores -> one thread publishes (or, for the owner, re-arms) the counter
-      __threadfence();
-      asm volatile("bar.sync 1, %0;" ::"n"((kThreads / 32 - 2) * 32) : "memory");
-      if (warp == 2 && lane == 0) {
-        if (owner)
-          *reinterpret_cast<volatile int*>(flag) = 0;
-        else
-          asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flag) : "memory");
-      }
-    }
+    tc_epilogue<kEpiWarps>(ctx, m0, n0, split, n_iter, mode, tmem_base, 0, warp - 2);
   }
-
   tc_fence_before();
   __syncthreads();
-  if (warp == 1 && !(dbg & 2)) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
@@ -542,16 +449,44 @@ inline PFN_encodeTiled encode_fn() {
   return fn;
 }
 
+// Per-device facts and one-time kernel configuration.  cudaFuncSetAttribute is per DEVICE (a process may drive
+// several GPUs, e.g. one host thread per replica as nn.DataParallel does -- main.py:79), so the bookkeeping is
+// keyed by device ordinal and guarded by a mutex.
+struct DeviceInfo {
+  int sm_count = 0;
+  bool configured[8] = {false, false, false, false, false, false, false, false};
+  bool step_configured = false;      // step_kernel.cuh kernels (ta3n_api.cu)
+};
+inline std::mutex& device_mu() {
+  static std::mutex mu;
+  return mu;
+}
+inline DeviceInfo* device_info() {      // call with device_mu() held
+  static std::map<int, DeviceInfo> devs;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  DeviceInfo& d = devs[dev];
+  if (d.sm_count == 0) {
+    if (cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.sm_count <= 0)
+      d.sm_count = 148;
+  }
+  return &d;
+}
+inline int device_sm_count() {
+  std::lock_guard<std::mutex> lock(device_mu());
+  DeviceInfo* d = device_info();
+  return d ? d->sm_count : 148;
+}
+
 struct MapKey {
   const void* ptr;
   long inner, outer, ld;
   int box_inner, box_outer;
   int atom32;   // 1: SWIZZLE_128B_ATOM_32B (MN-major operands), 0: SWIZZLE_128B
   int rank3;    // 1: MN-major operand as {32 floats, outer rows, inner/32 groups}, box {32, box_outer, 4}
-  int raw;      // 1: FLOAT32 map (bits as stored; tf32x3 engine), 0: TFLOAT32 (TMA rounds to nearest tf32)
   bool operator<(const MapKey& o) const {
-    return std::tie(ptr, inner, outer, ld, box_inner, box_outer, atom32, rank3, raw) <
-           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer, o.atom32, o.rank3, o.raw);
+    return std::tie(ptr, inner, outer, ld, box_inner, box_outer, atom32, rank3) <
+           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer, o.atom32, o.rank3);
   }
 };
 
@@ -575,12 +510,8 @@ inline int encode_map(const MapKey& k, CUtensorMap* out) {
   }
   // TFLOAT32: the TMA unit rounds fp32 -> tf32 (round to nearest) while filling shared memory, so the
   // tensor core never sees the truncation bias (-2^-11 relative per operand) it would apply to raw fp32
-  // bit patterns.  TA3N_TMA_RAW_FP32=1 switches to the raw copy (kept to measure the difference).
-  static const bool raw = []() {
-    const char* e = getenv("TA3N_TMA_RAW_FP32");
-    return e && e[0] == '1';
-  }();
-  CUresult r = fn(out, (raw || k.raw) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, k.rank3 ? 3 : 2,
+  // bit patterns (measured in round 1: a -7e-4 bias per GEMM with FLOAT32 maps).
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, k.rank3 ? 3 : 2,
                   const_cast<void*>(k.ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   k.atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -600,13 +531,6 @@ inline bool tc_operand_ok(const float* p, int ld) {
 inline bool tc_group_ok(const GemmPlan& plan, const Group& g) {
   if (plan.load_flags != 0) return false;                    // ReLU-on-load needs a register pass
   if ((long)g.M * g.N < 64L * 64L) return false;             // tiny heads stay on the SIMT engine
-  // Experimental (TA3N_SIMT_MAX_MNK=<M*N*K>, default 0 = off): a tcgen05 launch costs ~7 us before its first MMA
-  // retires (ncu: 8-slab launches), more than an fp32 SIMT pass over a 512x256x256 discriminator layer.
-  static const double simt_below = []() {
-    const char* e = getenv("TA3N_SIMT_MAX_MNK");
-    return e ? atof(e) : 0.0;
-  }();
-  if (simt_below > 0.0 && (double)g.M * g.N * (double)plan.k_total(g) <= simt_below) return false;
   if (g.seg_count > kMaxSegs) return false;
   for (int i = 0; i < g.seg_count; ++i) {
     const Seg& s = plan.segs[g.seg_begin + i];
@@ -615,172 +539,41 @@ inline bool tc_group_ok(const GemmPlan& plan, const Group& g) {
   return true;
 }
 
-template <bool A_KMAJ, bool B_KMAJ, int STAGES, bool FIXUP>
-inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
-                            const char* label, int* fix_flags) {
-  static bool configured = false;
-  if (!configured) {
-    TA3N_CUDA(cudaFuncSetAttribute(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES, FIXUP>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(STAGES)));
-    configured = true;
-  }
-  static const int dbg = []() {
-    const char* e = getenv("TA3N_TC_DEBUG");
-    const char* p = getenv("TA3N_L2_PREFETCH");          // experimental: L2 prefetch distance in K slabs (0 = off)
-    int pf = p ? atoi(p) : 0;
-    pf = pf < 0 ? 0 : (pf > 255 ? 255 : pf);
-    const char* d = getenv("TA3N_DESC_PREFETCH");        // experimental: prefetch tensor-map descriptors in the prologue
-    return ((e ? atoi(e) : 0) & 0xffff) | (pf << 16) | ((d && d[0] == '1') ? (1 << 24) : 0);
-  }();
-  pre_launch(label, stream);
-  launch_kernel(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES, FIXUP>, tab.total_tiles, tc_threads(STAGES),
-                tc_smem_bytes(STAGES), stream, tab, maps, sm, dbg, fix_flags);
-  return after_launch();
+// tensor-map keys of one segment of a group (shared by the per-launch and the step-kernel planners)
+inline void tc_seg_keys(const Seg& s, const Group& g, bool a_kmaj, bool b_kmaj, bool a3d, bool b3d, MapKey* ka,
+                        MapKey* kb) {
+  *ka = a_kmaj ? MapKey{s.A, s.len, g.M, s.lda, TC_BK, TC_BM, 0, 0} : MapKey{s.A, g.M, s.len, s.lda, 32, TC_BK, 1, a3d ? 1 : 0};
+  *kb = b_kmaj ? MapKey{s.B, s.len, g.N, s.ldb, TC_BK, TC_BN, 0, 0} : MapKey{s.B, g.N, s.len, s.ldb, 32, TC_BK, 1, b3d ? 1 : 0};
 }
 
-// tf32x3 engine: 3 stages of 64 KB, 320 threads, one CTA per SM
-template <bool A_KMAJ, bool B_KMAJ>
-inline int tc_launch_x3(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
-                        const char* label) {
-  auto kernel = seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, TC_X3_STAGES, false, true>;
-  static bool configured = false;
-  if (!configured) {
-    TA3N_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_x3_smem_bytes()));
-    configured = true;
+template <bool A_KMAJ, bool B_KMAJ, int STAGES>
+inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
+                            const char* label) {
+  constexpr int slot = (A_KMAJ ? 0 : 1) + (B_KMAJ ? 0 : 2) + (STAGES > 3 ? 4 : 0);
+  int first_wave = 148;
+  {
+    std::lock_guard<std::mutex> lock(device_mu());
+    DeviceInfo* d = device_info();
+    if (!d) return fail(TA3N_ERR_CUDA, "cudaGetDevice failed");
+    if (!d->configured[slot]) {
+      TA3N_CUDA(cudaFuncSetAttribute(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(STAGES)));
+      d->configured[slot] = true;
+    }
+    first_wave = d->sm_count;
   }
   pre_launch(label, stream);
-  launch_kernel(kernel, tab.total_tiles, 320, tc_x3_smem_bytes(), stream, tab, maps, sm, 0, static_cast<int*>(nullptr));
+  launch_kernel(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES>, tab.total_tiles, tc_threads(STAGES),
+                tc_smem_bytes(STAGES), stream, tab, maps, sm, first_wave);
   return after_launch();
 }
 
 template <bool A_KMAJ, bool B_KMAJ>
 inline int tc_launch_one(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream,
-                         const char* label, int* fix_flags, bool x3 = false) {
-  if (x3) return tc_launch_x3<A_KMAJ, B_KMAJ>(tab, maps, sm, stream, label);
-  static const int force = []() {
-    const char* e = getenv("TA3N_TC_STAGES");
-    return e ? atoi(e) : 0;
-  }();
-  const bool deep = force ? force > 3 : tab.total_tiles <= 148;
-  if (fix_flags != nullptr)
-    return deep ? tc_launch_stages<A_KMAJ, B_KMAJ, 6, true>(tab, maps, sm, stream, label, fix_flags)
-                : tc_launch_stages<A_KMAJ, B_KMAJ, 3, true>(tab, maps, sm, stream, label, fix_flags);
-  return deep ? tc_launch_stages<A_KMAJ, B_KMAJ, 6, false>(tab, maps, sm, stream, label, nullptr)
-              : tc_launch_stages<A_KMAJ, B_KMAJ, 3, false>(tab, maps, sm, stream, label, nullptr);
-}
-
-// ---- experimental: in-kernel split-K fix-up (TA3N_FIXUP_SPLITK=1) -----------------------------------------
-inline bool fixup_enabled() {
-  static const bool on = []() {
-    const char* e = getenv("TA3N_FIXUP_SPLITK");
-    return e && e[0] == '1';
-  }();
-  return on;
-}
-
-// Arrival counters: one int per split output tile, zero between launches (the owner re-arms its counter).  The
-// buffer belongs to the library (one per device, allocated on first use OUTSIDE stream capture -- during capture
-// an unallocated buffer simply disables the fix-up for that call); launches take consecutive slots from a ring.
-constexpr int kFixFlagSlots = 1 << 16;
-inline int* fix_flags_take(int n, cudaStream_t stream, int* slot) {
-  struct Dev {
-    int* base = nullptr;
-    unsigned next = 0;
-  };
-  static std::mutex mu;
-  static std::map<int, Dev> devs;
-  if (n <= 0 || n > kFixFlagSlots / 4) return nullptr;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  std::lock_guard<std::mutex> lock(mu);
-  Dev& d = devs[dev];
-  if (!d.base) {
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
-    int* p = nullptr;
-    if (cudaMalloc(&p, sizeof(int) * kFixFlagSlots) != cudaSuccess) return nullptr;
-    if (cudaMemset(p, 0, sizeof(int) * kFixFlagSlots) != cudaSuccess) {
-      cudaFree(p);
-      return nullptr;
-    }
-    d.base = p;
-  }
-  if (d.next + (unsigned)n > (unsigned)kFixFlagSlots) d.next = 0;
-  *slot = (int)d.next;
-  d.next += (unsigned)n;
-  return d.base;
-}
-
-// Modelled makespan (in 32-wide K slabs) of a launch: CTAs in launch order, each to the least loaded of 148 SMs;
-// an SM's fill bandwidth is shared by its resident CTAs, so loads add up.
-inline long tc_makespan(const std::vector<long>& cta_slabs) {
-  std::vector<long> sm(148, 0);
-  std::vector<long> sorted = cta_slabs;
-  std::sort(sorted.begin(), sorted.end(), std::greater<long>());
-  for (long c : sorted) *std::min_element(sm.begin(), sm.end()) += c;
-  return *std::max_element(sm.begin(), sm.end());
-}
-
-// Choose per-group split factors that shorten the modelled makespan of a launch whose tiles are few and uneven
-// (the critical tile of the forward batch is 80 slabs against 36 per SM on average).  Pure host logic: `tiles[i]`
-// output tiles of `slabs[i]` K slabs each -> split factor per group (all 1 when splitting is not worth it).
-inline std::vector<int> balance_split_factors(const std::vector<long>& tiles, const std::vector<long>& slabs) {
-  const int ng = (int)tiles.size();
-  long total = 0;
-  for (int i = 0; i < ng; ++i) total += tiles[i] * slabs[i];
-  auto model = [&](const std::vector<int>& ks) {
-    std::vector<long> ctas;
-    for (int i = 0; i < ng; ++i)
-      for (long t = 0; t < tiles[i] * ks[i]; ++t) ctas.push_back((slabs[i] + ks[i] - 1) / ks[i] + 2);   // +2: fix-up
-    return tc_makespan(ctas);
-  };
-  std::vector<int> ones(ng, 1), best(ng, 1);
-  const long before = model(ones);
-  long best_span = before;
-  const long target = std::max<long>(12, (long)(1.15 * (double)total / 148.0));
-  for (int bump = 0; bump <= 1; ++bump) {          // the even-load split, and one step finer (80 tiles: 3 beats 2)
-    std::vector<int> ks(ng, 1);
-    long n_ctas = 0;
-    for (int i = 0; i < ng; ++i) {
-      int want = (int)((slabs[i] + target - 1) / target);
-      if (want > 1 || bump) want += bump;
-      want = std::min(want, 4);
-      while (want > 1 && slabs[i] / want < 8) --want;
-      ks[i] = std::max(want, 1);
-      n_ctas += tiles[i] * ks[i];
-    }
-    if (n_ctas > 256) continue;                                // every CTA resident at once, with headroom
-    const long span = model(ks);
-    if (span < best_span) {
-      best_span = span;
-      best = ks;
-    }
-  }
-  if (best_span * 100 > before * 85) return ones;              // needs >= 15 % shorter critical path
-  return best;
-}
-
-// Only with the fix-up: a separate reduce pass costs more than the balance saves.
-inline void plan_balance_splitk(GemmPlan& plan, Arena* arena) {
-  if (!arena) return;
-  const int ng = (int)plan.groups.size();
-  std::vector<long> tiles(ng), slabs(ng);
-  for (int i = 0; i < ng; ++i) {
-    const Group& g = plan.groups[i];
-    if (g.ksplit > 1) return;   // already planned
-    tiles[i] = (long)((g.M + TC_BM - 1) / TC_BM) * ((g.N + TC_BN - 1) / TC_BN);
-    slabs[i] = 0;
-    for (int k = 0; k < g.seg_count; ++k) slabs[i] += (plan.segs[g.seg_begin + k].len + TC_BK - 1) / TC_BK;
-  }
-  const std::vector<int> ks = balance_split_factors(tiles, slabs);
-  for (int i = 0; i < ng; ++i) {
-    if (ks[i] < 2) continue;
-    Group& g = plan.groups[i];
-    float* p = arena->floats((size_t)ks[i] * g.M * g.N);   // ksplit planes: the reduce pass stays a valid fallback
-    if (!p) continue;
-    g.ksplit = ks[i];
-    g.partial = p;
-  }
+                         const char* label) {
+  // 6 stages / one CTA per SM for grids within a wave, 3 stages / two CTAs per SM beyond
+  return tab.total_tiles <= device_sm_count() ? tc_launch_stages<A_KMAJ, B_KMAJ, 6>(tab, maps, sm, stream, label)
+                                              : tc_launch_stages<A_KMAJ, B_KMAJ, 3>(tab, maps, sm, stream, label);
 }
 
 // Copy the groups `idx` of `plan` (with their segments) into a new plan.
@@ -800,8 +593,18 @@ inline GemmPlan sub_plan(const GemmPlan& plan, const std::vector<int>& idx) {
   return out;
 }
 
+// rank-3 maps for MN-major operands whose MN extent is a multiple of 32 in every group of the plan
+inline void tc_rank3_flags(const GemmPlan& plan, bool* a3d, bool* b3d) {
+  *a3d = !plan.a_kmaj;
+  *b3d = !plan.b_kmaj;
+  for (const Group& g : plan.groups) {
+    if (g.M % 32 != 0) *a3d = false;
+    if (g.N % 32 != 0) *b3d = false;
+  }
+}
+
 // Launch `plan` (all groups eligible) on the tcgen05 engine.
-inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool fixup = false, bool x3 = false) {
+inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
   // longest-K groups first (see the tile remap in the kernel): LPT-style balance of the tensor pipe
   std::vector<int> order(plan_in.groups.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
@@ -810,16 +613,8 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool fixup = 
            plan_in.k_total(plan_in.groups[b]) / plan_in.groups[b].ksplit;
   });
   const GemmPlan plan = sub_plan(plan_in, order);
-  // rank-3 maps for MN-major operands whose MN extent is a multiple of 32 in every group of the plan
-  static const bool allow3d = []() {
-    const char* e = getenv("TA3N_TMA_3D");
-    return !(e && e[0] == '0');
-  }();
-  bool a3d = !plan.a_kmaj && allow3d, b3d = !plan.b_kmaj && allow3d;
-  for (const Group& g : plan.groups) {
-    if (g.M % 32 != 0) a3d = false;
-    if (g.N % 32 != 0) b3d = false;
-  }
+  bool a3d, b3d;
+  tc_rank3_flags(plan, &a3d, &b3d);
   size_t gi = 0;
   while (gi < plan.groups.size()) {
     GemmTable tab;
@@ -828,7 +623,7 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool fixup = 
     memset(&tab, 0, sizeof(int) * 4);
     memset(&sm, 0, sizeof(sm));
     std::map<MapKey, int> local;
-    int ng = 0, ns = 0, tiles = 0, nmaps = 0, fix_tiles = 0;
+    int ng = 0, ns = 0, tiles = 0, nmaps = 0;
     bool any_split = false;
     while (gi < plan.groups.size() && ng < kMaxGroups) {
       const Group& src = plan.groups[gi];
@@ -838,12 +633,8 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool fixup = 
       int fresh = 0;
       std::map<MapKey, int> trial = local;
       for (int i = 0; i < src.seg_count; ++i) {
-        const Seg& s = plan.segs[src.seg_begin + i];
-        const int raw = x3 ? 1 : 0;
-        MapKey ka = plan.a_kmaj ? MapKey{s.A, s.len, src.M, s.lda, TC_BK, TC_BM, 0, 0, raw}
-                                : MapKey{s.A, src.M, s.len, s.lda, 32, TC_BK, 1, a3d ? 1 : 0, raw};
-        MapKey kb = plan.b_kmaj ? MapKey{s.B, s.len, src.N, s.ldb, TC_BK, TC_BN, 0, 0, raw}
-                                : MapKey{s.B, src.N, s.len, s.ldb, 32, TC_BK, 1, b3d ? 1 : 0, raw};
+        MapKey ka, kb;
+        tc_seg_keys(plan.segs[src.seg_begin + i], src, plan.a_kmaj, plan.b_kmaj, a3d, b3d, &ka, &kb);
         for (const MapKey& k : {ka, kb})
           if (!trial.count(k)) trial[k] = nmaps + fresh++;
         keys.push_back({ka, kb});
@@ -871,35 +662,22 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool fixup = 
       g.tile_begin = tiles;
       tiles += g.tiles_m * g.tiles_n * g.ksplit;
       g.fix_slot = -1;
-      if (g.ksplit > 1 && fixup) {
-        g.fix_slot = fix_tiles;                 // relative; rebased below once the ring slots are known
-        fix_tiles += g.tiles_m * g.tiles_n;
-      }
+      any_split |= g.ksplit > 1;
       tab.g[ng++] = g;
       ++gi;
     }
-    // arrival counters for the fix-up groups; without them (first use inside a stream capture) the groups fall
-    // back to the separate reduce pass
-    int* fix_flags = nullptr;
-    if (fix_tiles > 0) {
-      int slot0 = 0;
-      fix_flags = fix_flags_take(fix_tiles, stream, &slot0);
-      for (int i = 0; i < ng; ++i)
-        if (tab.g[i].fix_slot >= 0) tab.g[i].fix_slot = fix_flags ? tab.g[i].fix_slot + slot0 : -1;
-    }
-    for (int i = 0; i < ng; ++i) any_split |= tab.g[i].ksplit > 1 && tab.g[i].fix_slot < 0;
     tab.n_groups = ng;
     tab.total_tiles = tiles;
     tab.pad_ = (a3d ? 1 : 0) | (b3d ? 2 : 0);
     if (tiles > 0) {
       if (plan.a_kmaj && plan.b_kmaj)
-        TA3N_TRY((tc_launch_one<true, true>(tab, maps, sm, stream, plan.label, fix_flags, x3)));
+        TA3N_TRY((tc_launch_one<true, true>(tab, maps, sm, stream, plan.label)));
       else if (plan.a_kmaj && !plan.b_kmaj)
-        TA3N_TRY((tc_launch_one<true, false>(tab, maps, sm, stream, plan.label, fix_flags, x3)));
+        TA3N_TRY((tc_launch_one<true, false>(tab, maps, sm, stream, plan.label)));
       else if (!plan.a_kmaj && !plan.b_kmaj)
-        TA3N_TRY((tc_launch_one<false, false>(tab, maps, sm, stream, plan.label, fix_flags, x3)));
+        TA3N_TRY((tc_launch_one<false, false>(tab, maps, sm, stream, plan.label)));
       else
-        TA3N_TRY((tc_launch_one<false, true>(tab, maps, sm, stream, plan.label, fix_flags, x3)));
+        TA3N_TRY((tc_launch_one<false, true>(tab, maps, sm, stream, plan.label)));
       if (any_split) {
         dim3 grid(splitk_reduce_blocks(tab), ng);
         pre_launch("splitk_reduce", stream);
@@ -920,19 +698,13 @@ inline int run_gemm(GemmPlan& plan, cudaStream_t stream, Arena* splitk_arena = n
     if (g.M <= 0 || g.N <= 0 || g.seg_count <= 0)
       return fail(TA3N_ERR_INVALID, "seg_gemm: empty group M=%d N=%d segs=%d", g.M, g.N, g.seg_count);
   const int engine = gemm_engine().load();
-  if (engine == TA3N_GEMM_TF32_TCGEN05 || engine == TA3N_GEMM_TF32X3_TCGEN05) {
-    const bool x3 = engine == TA3N_GEMM_TF32X3_TCGEN05;
+  if (engine == TA3N_GEMM_TF32_TCGEN05) {
     std::vector<int> tc_idx, simt_idx;
     for (int i = 0; i < (int)plan.groups.size(); ++i) (tc_group_ok(plan, plan.groups[i]) ? tc_idx : simt_idx).push_back(i);
     if (!tc_idx.empty()) {
       GemmPlan tc = sub_plan(plan, tc_idx);
       plan_splitk(tc, splitk_arena, TC_BM, TC_BN, TC_BK, 4);
-      bool fixup = false;
-      if (!x3 && fixup_enabled() && splitk_arena) {
-        plan_balance_splitk(tc, splitk_arena);      // no-op when plan_splitk already split something
-        for (const Group& g : tc.groups) fixup |= g.ksplit > 1;
-      }
-      TA3N_TRY(launch_tc(tc, stream, fixup, x3));
+      TA3N_TRY(launch_tc(tc, stream));
     }
     if (!simt_idx.empty()) {
       GemmPlan rest = sub_plan(plan, simt_idx);

@@ -39,7 +39,11 @@ enum : int {
   EPI_DROP_RNG = 8,    // same with the counter-based RNG
   EPI_ADDROW = 16,     // v += (rowscale ? rowscale[m*rs_stride] + rs_bias : 1) * add[m*ldadd + n]
   EPI_GATE = 32,       // v = gate[m*ldgate + n] > 0 ? v : 0
-  EPI_ACCUM = 64       // v += C[m,n]
+  EPI_ACCUM = 64,      // v += C[m,n]
+  EPI_DPRE = 128,      // LAST: v = gate[m*ldgate + n] > 0 ? v * drop_scale : 0   (ReLU + dropout backward of the shared
+                       //       layer folded into the data-gradient GEMM that completes d_feat; rowops dpre_kernel)
+  EPI_MULTI = 256      // additionally store v * 1[multi_gate[q][m*ldmulti + n] > 0] to multi_out[q], q < n_multi
+                       //       (d_feat_rel -> the dZ planes of every relation of the scale; rowops dz_kernel)
 };
 enum : int { LD_RELU_A = 1, LD_RELU_B = 2 };
 
@@ -75,6 +79,10 @@ struct Group {
   const uint64_t* step_dev;
   uint64_t seed;
   uint64_t rng_offset;  // added to the element index m*N+n (keeps source/target streams apart)
+  const float* alpha_dev;       // optional: alpha *= *alpha_dev (device-resident GRL coefficient, main.py:350-352)
+  float* multi_out[3];          // EPI_MULTI
+  const float* multi_gate[3];
+  int n_multi, ldmulti;
 };
 
 struct GemmTable {
@@ -104,7 +112,7 @@ inline Group make_group() {
 template <int F>
 __device__ __forceinline__ float epilogue_t(const Group& g, int m, int n, float acc) {
   const int f = (F >= 0) ? F : g.flags;
-  float v = g.alpha * acc;
+  float v = (g.alpha_dev ? g.alpha * __ldg(g.alpha_dev) : g.alpha) * acc;
   if (f & EPI_BIAS) v += g.bias[n];
   if (f & EPI_RELU) v = fmaxf(v, 0.0f);
   if (f & EPI_DROP_MASK) v = g.keep[(size_t)m * g.ldkeep + n] ? v * g.drop_scale : 0.0f;
@@ -118,6 +126,13 @@ __device__ __forceinline__ float epilogue_t(const Group& g, int m, int n, float 
   }
   if (f & EPI_GATE) v = g.gate[(size_t)m * g.ldgate + n] > 0.0f ? v : 0.0f;
   if (f & EPI_ACCUM) v += g.C[(size_t)m * g.ldc + n];
+  if (f & EPI_DPRE) v = g.gate[(size_t)m * g.ldgate + n] > 0.0f ? v * g.drop_scale : 0.0f;
+  if (f & EPI_MULTI) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q)      // constant indices: the Group copy stays in registers
+      if (q < g.n_multi)
+        g.multi_out[q][(size_t)m * g.ldmulti + n] = g.multi_gate[q][(size_t)m * g.ldmulti + n] > 0.0f ? v : 0.0f;
+  }
   return v;
 }
 
@@ -125,12 +140,14 @@ __device__ __forceinline__ float apply_epilogue(const Group& g, int m, int n, fl
   return epilogue_t<-1>(g, m, n, acc);
 }
 
-// 32 consecutive floats p[0..31] of one row -> registers; 16 B vector loads when possible
+// 32 consecutive floats p[0..31] of one row -> registers; 16 B vector loads when possible.  ld.global.cg: read at L2
+// (no reuse in L1 anyway), so that inside the persistent step kernel data written by another SM earlier in the SAME
+// launch is never served from a stale L1 line.
 __device__ __forceinline__ void load_row32(const float* p, int nvalid, float (&r)[32]) {
   if (nvalid >= 32 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(p + j);
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(p + j));
       r[j] = t.x;
       r[j + 1] = t.y;
       r[j + 2] = t.z;
@@ -138,7 +155,7 @@ __device__ __forceinline__ void load_row32(const float* p, int nvalid, float (&r
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] = j < nvalid ? p[j] : 0.f;
+    for (int j = 0; j < 32; ++j) r[j] = j < nvalid ? __ldcg(p + j) : 0.f;
   }
 }
 
@@ -149,8 +166,9 @@ template <int F>
 __device__ __forceinline__ void epilogue_row32(const Group& g, int m, int nb, int nvalid, float (&v)[32]) {
   const int f = (F >= 0) ? F : g.flags;
   float aux[32];
+  const float alpha = g.alpha_dev ? g.alpha * __ldg(g.alpha_dev) : g.alpha;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
+  for (int j = 0; j < 32; ++j) v[j] *= alpha;
   if (f & EPI_BIAS) {
     load_row32(g.bias + nb, nvalid, aux);
 #pragma unroll
@@ -173,7 +191,7 @@ __device__ __forceinline__ void epilogue_row32(const Group& g, int m, int nb, in
     for (int j = 0; j < 32; ++j) v[j] = rng_keep(g.seed, step, base + j, g.drop_p) ? v[j] * g.drop_scale : 0.0f;
   }
   if (f & EPI_ADDROW) {
-    const float rs = g.rowscale ? g.rowscale[(size_t)m * g.rs_stride] + g.rs_bias : 1.0f;
+    const float rs = g.rowscale ? __ldcg(g.rowscale + (size_t)m * g.rs_stride) + g.rs_bias : 1.0f;
     load_row32(g.add + (size_t)m * g.ldadd + nb, nvalid, aux);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaf(rs, aux[j], v[j]);
@@ -188,6 +206,29 @@ __device__ __forceinline__ void epilogue_row32(const Group& g, int m, int nb, in
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += aux[j];
   }
+  if (f & EPI_DPRE) {
+    load_row32(g.gate + (size_t)m * g.ldgate + nb, nvalid, aux);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = aux[j] > 0.0f ? v[j] * g.drop_scale : 0.0f;
+  }
+  if (f & EPI_MULTI) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {      // constant indices: the Group copy stays in registers
+      if (q >= g.n_multi) break;
+      load_row32(g.multi_gate[q] + (size_t)m * g.ldmulti + nb, nvalid, aux);
+      float* o = g.multi_out[q] + (size_t)m * g.ldmulti + nb;
+      if (nvalid >= 32 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(o + j) = make_float4(aux[j] > 0.f ? v[j] : 0.f, aux[j + 1] > 0.f ? v[j + 1] : 0.f,
+                                                          aux[j + 2] > 0.f ? v[j + 2] : 0.f, aux[j + 3] > 0.f ? v[j + 3] : 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) o[j] = aux[j] > 0.f ? v[j] : 0.f;
+      }
+    }
+  }
 }
 
 // Call `body(tag)` with tag = std::integral_constant<int, F> for the flag set of `flags`.
@@ -198,6 +239,8 @@ __device__ __forceinline__ void epilogue_row32(const Group& g, int m, int nb, in
     case (EPI_BIAS | EPI_RELU | EPI_DROP_RNG): { constexpr int EPI_F = EPI_BIAS | EPI_RELU | EPI_DROP_RNG; __VA_ARGS__; } break; \
     case EPI_ADDROW: { constexpr int EPI_F = EPI_ADDROW; __VA_ARGS__; } break;              \
     case EPI_ACCUM: { constexpr int EPI_F = EPI_ACCUM; __VA_ARGS__; } break;                \
+    case (EPI_ACCUM | EPI_DPRE): { constexpr int EPI_F = EPI_ACCUM | EPI_DPRE; __VA_ARGS__; } break; \
+    case (EPI_ADDROW | EPI_MULTI): { constexpr int EPI_F = EPI_ADDROW | EPI_MULTI; __VA_ARGS__; } break; \
     default: { constexpr int EPI_F = -1; __VA_ARGS__; } break;                              \
   }
 

@@ -1,0 +1,323 @@
+// step_kernel.cuh -- the fused training step of the path as ONE persistent kernel.
+//
+// main.py:418-576 for the shipped configuration (forward of VideoModel.forward models.py:545-722, the composed loss,
+// backward to every parameter gradient) is a static graph of ~900 small tasks: 128x128 tcgen05 GEMM tiles
+// (gemm_tcgen05.cuh::tc_tile), per-video row tasks and column-sum tasks (step_rows.cuh).  Run as separate launches
+// (round 1: 25 kernels, every one sub-wave) the step is the SUM of per-launch critical paths plus a drain and a
+// pipeline fill at every kernel boundary: 0.27 ms for 20 us of HBM traffic.  Here one CTA per SM pulls tasks from a
+// queue in a fixed priority order; a task waits on arrival counters of the tasks that produce its inputs (release /
+// acquire through global memory), so
+//   * dependent stages overlap at 128-row granularity instead of at kernel boundaries,
+//   * the weight-gradient tiles and column sums (a third of the work, needed by nobody until the end of the step)
+//     fill the SMs the latency-bound forward / data-gradient chain leaves idle,
+//   * split-K tiles are folded by an "owner" tile that depends on its partial tiles -- deterministic, no reduce pass.
+// Deadlock freedom: tasks are taken in queue order and only ever wait for tasks EARLIER in the queue, each of which
+// has been taken by a resident CTA that never waits on a later task; so the lowest-numbered unfinished task can always
+// run, whatever number of CTAs is resident.  A bounded spin turns any violation into a trap instead of a hang.
+// Results do not depend on which CTA runs a task: every output element is produced by exactly one task with a fixed
+// summation order -> bit-identical reruns.
+#pragma once
+
+#include "gemm_tcgen05.cuh"
+#include "step_rows.cuh"
+
+namespace ta3n {
+
+constexpr int kStepThreads = 352;     // warp 0 TMA producer, 1 MMA issuer, 2..9 epilogue / row tasks, 10 scheduler
+constexpr int kStepStages = 5;        // operand ring: 5 x 32 KB
+constexpr int kStepSlots = 3;         // tasks a CTA holds at once (scheduled ahead of the one being finished)
+constexpr int kStepScratchBytes = 40 * 1024;      // shared memory of the row tasks (outside the operand ring)
+constexpr int kStepSmemBytes = kStepStages * TC_STAGE_BYTES + kStepScratchBytes + 1024;
+constexpr int kStepTmemCols = 256;    // two 128-column accumulators
+
+enum : int { TASK_GEMM = 0, TASK_TAIL = 1, TASK_COLSUM_PART = 2, TASK_COLSUM_REDUCE = 3, TASK_FINISH = 4, TASK_STOP = 5 };
+
+struct StepTask {
+  int type;
+  int group;              // GEMM: group index; COLSUM_*: job index
+  int m0, n0;             // GEMM: tile origin; TAIL: first video, video count; COLSUM_PART: column block, row split
+  int split, mode;        // GEMM: split index, TILE_* mode
+  int wait_begin[2], wait_end[2], wait_val[2];     // wait until counters[i] >= val for i in [begin, end)
+  int signal;             // counter bumped on completion (-1: none)
+  int signal2;            // second counter (the stage total; -1: none)
+};
+static_assert(sizeof(StepTask) % 4 == 0 && sizeof(StepTask) / 4 <= 32, "staged by one warp");
+
+struct StepGroup {
+  Group g;
+  int a_kmaj, b_kmaj, pad_flags, seg_begin;
+};
+
+struct StepHeader {
+  int n_tasks, n_counters, n_groups, n_jobs;
+  const StepTask* tasks;
+  const StepGroup* groups;
+  const SegLite* segs;
+  const CUtensorMap* maps;
+  const WColsumJob* jobs;
+  const TailArgs* tail;
+  int* counters;                 // [n_counters]; counters[n_counters - 1] is the queue cursor
+  unsigned long long* step_counter;   // dropout step counter, advanced by the FINISH task (may be null)
+  unsigned long long* trace;     // optional [n_tasks][4]: {sm id, scheduled, accumulator ready, done} (globaltimer ns)
+  int tail_videos;               // videos per row task
+  int pad_;
+};
+
+struct StepSlot {                // one scheduled task: descriptor + (GEMM) the group and its segments
+  StepTask task;
+  int index;                     // position in the queue (trace)
+  int flags;                     // a_kmaj | b_kmaj << 1 | pad_flags << 2
+  int c_begin, n_iter;
+  TileCtx ctx;
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned sm_id() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %smid;" : "=r"(v));
+  return v;
+}
+
+__global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid_constant__ StepHeader hd) {
+  extern __shared__ uint8_t step_smem_raw[];
+  __shared__ __align__(8) TcShared sh;
+  __shared__ __align__(8) uint64_t slot_full[kStepSlots];
+  __shared__ __align__(8) uint64_t slot_empty[kStepSlots];
+  __shared__ StepSlot slots[kStepSlots];
+  __shared__ TailArgs tail;
+  __shared__ WColsumJob job;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(step_smem_raw) + 1023) & ~uintptr_t(1023));
+  float* scratch = reinterpret_cast<float*>(smem + kStepStages * TC_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
+  int* const cursor = hd.counters + hd.n_counters - 1;
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    tc_pipe_init<kStepStages>(&sh, 8);
+    for (int s = 0; s < kStepSlots; ++s) {
+      mbar_init(&slot_full[s], 1);
+      mbar_init(&slot_empty[s], 10);       // producer + MMA issuer + 8 epilogue warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&sh.tmem_slot, kStepTmemCols);
+  for (int i = tid; i < (int)(sizeof(TailArgs) / sizeof(int)); i += kStepThreads)
+    reinterpret_cast<int*>(&tail)[i] = reinterpret_cast<const int*>(hd.tail)[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh.tmem_slot;
+  // (no griddepcontrol here: the kernel is launched with plain stream ordering behind the memset of its counters,
+  //  and must not release its dependents before it has finished)
+
+  if (warp == 10) {
+    // =========================== scheduler: take tasks, stage them, wait for their inputs ===========================
+    for (uint32_t k = 0;; ++k) {
+      const int s = (int)(k % kStepSlots);
+      mbar_wait(&slot_empty[s], ((k / kStepSlots) & 1u) ^ 1u);
+      StepSlot& sl = slots[s];
+      int t = 0;
+      if (lane == 0) t = atomicAdd(cursor, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= hd.n_tasks) {
+        if (lane == 0) {
+          sl.task.type = TASK_STOP;
+          mbar_arrive(&slot_full[s]);
+        }
+        break;
+      }
+      if (lane < (int)(sizeof(StepTask) / sizeof(int)))
+        reinterpret_cast<int*>(&sl.task)[lane] = __ldg(reinterpret_cast<const int*>(hd.tasks + t) + lane);
+      __syncwarp();
+      const int type = sl.task.type;
+      if (type == TASK_GEMM) {
+        const StepGroup* sg = hd.groups + sl.task.group;
+        for (int i = lane; i < (int)(sizeof(Group) / sizeof(int)); i += 32)
+          reinterpret_cast<int*>(&sl.ctx.g)[i] = __ldg(reinterpret_cast<const int*>(&sg->g) + i);
+        const int sb = __ldg(&sg->seg_begin), sc = __ldg(&sg->g.seg_count);
+        for (int i = lane; i < sc; i += 32) sl.ctx.seg[i] = hd.segs[sb + i];
+        __syncwarp();
+        if (lane == 0) {
+          sl.flags = (__ldg(&sg->a_kmaj) ? 1 : 0) | (__ldg(&sg->b_kmaj) ? 2 : 0) | (__ldg(&sg->pad_flags) << 2);
+          int c_begin, n_iter;
+          tc_chunk_range(sl.ctx, sl.task.split, &c_begin, &n_iter);
+          sl.c_begin = c_begin;
+          sl.n_iter = n_iter;
+        }
+      }
+      if (lane == 0) sl.index = t;
+      // dependencies: every lane polls its own counters of the two ranges (acquire)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int val = sl.task.wait_val[r];
+        for (int c = sl.task.wait_begin[r] + lane; c < sl.task.wait_end[r]; c += 32) {
+          unsigned spins = 0;
+          while (ld_acquire(hd.counters + c) < val) {
+            __nanosleep(40);
+            if (++spins > (1u << 25)) __trap();        // ~ seconds: a scheduling bug becomes an error, not a hung GPU
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        mbar_arrive(&slot_full[s]);
+      }
+    }
+  } else if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t slabs = 0;
+      for (uint32_t k = 0;; ++k) {
+        const int s = (int)(k % kStepSlots);
+        mbar_wait(&slot_full[s], (k / kStepSlots) & 1u);
+        const StepSlot& sl = slots[s];
+        const int type = sl.task.type;
+        if (type == TASK_STOP) break;
+        if (type == TASK_GEMM && sl.n_iter > 0) {
+          fence_proxy_async_all();                       // operands written by other SMs' generic stores -> TMA reads
+          tc_produce<kStepStages>(sl.ctx, hd.maps, (sl.flags & 1) != 0, (sl.flags & 2) != 0, sl.flags >> 2, sl.task.m0,
+                                  sl.task.n0, sl.c_begin, sl.n_iter, smem, &sh, slabs);
+          slabs += (uint32_t)sl.n_iter;
+        }
+        mbar_arrive(&slot_empty[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      uint32_t slabs = 0, tiles = 0;
+      for (uint32_t k = 0;; ++k) {
+        const int s = (int)(k % kStepSlots);
+        mbar_wait(&slot_full[s], (k / kStepSlots) & 1u);
+        const StepSlot& sl = slots[s];
+        const int type = sl.task.type;
+        if (type == TASK_STOP) break;
+        if (type == TASK_GEMM && sl.n_iter > 0) {
+          const int acc = (int)(tiles & 1u);
+          mbar_wait(&sh.tmem_empty_bar[acc], ((tiles >> 1) & 1u) ^ 1u);      // the epilogue has drained this buffer
+          tc_fence_after();
+          tc_mma<kStepStages>((sl.flags & 1) != 0, (sl.flags & 2) != 0, sl.n_iter, smem, &sh, tmem_base, acc, slabs);
+          slabs += (uint32_t)sl.n_iter;
+          ++tiles;
+        }
+        mbar_arrive(&slot_empty[s]);
+      }
+    }
+  } else {
+    // =========================== epilogue / row warps (2..9) ===========================
+    const int ew = warp - 2;
+    const int rt = tid - 64;
+    uint32_t tiles = 0;
+    for (uint32_t k = 0;; ++k) {
+      const int s = (int)(k % kStepSlots);
+      mbar_wait(&slot_full[s], (k / kStepSlots) & 1u);
+      const StepSlot& sl = slots[s];
+      const int type = sl.task.type;
+      if (type == TASK_STOP) break;
+      unsigned long long t_sched = 0, t_acc = 0;
+      if (hd.trace && rt == 0) t_sched = global_ns();
+      if (type == TASK_GEMM) {
+        const int acc = (int)(tiles & 1u);
+        if (sl.n_iter > 0) {
+          mbar_wait(&sh.tmem_full_bar[acc], (tiles >> 1) & 1u);
+          tc_fence_after();
+        }
+        if (hd.trace && rt == 0) t_acc = global_ns();
+        tc_epilogue<8>(sl.ctx, sl.task.m0, sl.task.n0, sl.task.split, sl.n_iter, sl.task.mode, tmem_base, acc, ew);
+        if (sl.n_iter > 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sh.tmem_empty_bar[acc]);      // this warp's TMEM reads are done
+          ++tiles;
+        }
+      } else if (type == TASK_TAIL) {
+        tail_task(tail, sl.task.m0, sl.task.n0, hd.tail_videos, scratch, rt);
+      } else if (type == TASK_COLSUM_PART || type == TASK_COLSUM_REDUCE) {
+        for (int i = rt; i < (int)(sizeof(WColsumJob) / sizeof(int)); i += kRowThreads)
+          reinterpret_cast<int*>(&job)[i] = __ldg(reinterpret_cast<const int*>(hd.jobs + sl.task.group) + i);
+        row_sync();
+        if (type == TASK_COLSUM_PART)
+          colsum_part_task(job, scratch, sl.task.m0, sl.task.n0, rt);
+        else
+          colsum_reduce_task(job, rt);
+      } else if (type == TASK_FINISH) {
+        if (rt == 0 && hd.step_counter) hd.step_counter[0] += 1ull;
+      }
+      // ---- completion: every store of the task issued -> release its arrival counters ----
+      const int sig = sl.task.signal, sig2 = sl.task.signal2, index = sl.index;
+      const unsigned long long tag = ((unsigned long long)type << 16) | ((unsigned long long)(unsigned)sl.task.group << 24) |
+                                     ((unsigned long long)sl.task.mode << 48) | ((unsigned long long)(unsigned)sl.n_iter << 52);
+      __threadfence();
+      row_sync();
+      if (rt == 0) {
+        if (sig >= 0 || sig2 >= 0) {
+          fence_proxy_async_all();
+          if (sig >= 0) red_release(hd.counters + sig, 1);
+          if (sig2 >= 0) red_release(hd.counters + sig2, 1);
+        }
+        if (hd.trace) {
+          unsigned long long* tr = hd.trace + (size_t)index * 4;
+          tr[0] = (unsigned long long)sm_id() | tag;
+          tr[1] = t_sched;
+          tr[2] = t_acc;
+          tr[3] = global_ns();
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_empty[s]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kStepTmemCols);
+  }
+}
+
+// ---- stand-alone row kernels of the phased executor --------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads) tail_kernel(const __grid_constant__ TailArgs a) {
+  extern __shared__ __align__(16) float tail_sm[];
+  pdl_wait();
+  const int v0 = blockIdx.x * kTailVideos;
+  const int nv = min(kTailVideos, a.M - v0);
+  if (nv > 0) tail_task(a, v0, nv, kTailVideos, tail_sm, threadIdx.x);
+}
+
+// column sums of the phased executor: the same task functions, (job, column block, row split) from the block index
+__global__ void __launch_bounds__(kRowThreads) step_colsum_part_kernel(const __grid_constant__ WColsumTable tab) {
+  __shared__ __align__(16) float red_sm[8 * 33 * 4];
+  __shared__ WColsumJob j;
+  pdl_wait();
+  for (int i = threadIdx.x; i < (int)(sizeof(WColsumJob) / sizeof(int)); i += kRowThreads)
+    reinterpret_cast<int*>(&j)[i] = reinterpret_cast<const int*>(&tab.job[blockIdx.y])[i];
+  __syncthreads();
+  colsum_part_task(j, red_sm, blockIdx.x, blockIdx.z, threadIdx.x);
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+step_colsum_reduce_kernel(const __grid_constant__ WColsumTable tab, unsigned long long* step_counter) {
+  __shared__ WColsumJob j;
+  pdl_wait();
+  for (int i = threadIdx.x; i < (int)(sizeof(WColsumJob) / sizeof(int)); i += kRowThreads)
+    reinterpret_cast<int*>(&j)[i] = reinterpret_cast<const int*>(&tab.job[blockIdx.x])[i];
+  __syncthreads();
+  colsum_reduce_task(j, threadIdx.x);
+  if (step_counter && blockIdx.x == 0 && threadIdx.x == 0) step_counter[0] += 1ull;   // last launch of the step
+}
+
+}  // namespace ta3n

@@ -6,6 +6,8 @@
 #include "rowops.cuh"
 #include "gemm_tcgen05.cuh"
 #include "optim.cuh"
+#include "step_plan.cuh"
+#include "allreduce.cuh"
 
 #include <functional>
 
@@ -176,15 +178,15 @@ int ta3n_fwd_batch_begin(void) {
   return TA3N_OK;
 }
 
-size_t ta3n_fwd_batch_workspace_bytes(void) { return fixup_enabled() ? splitk_bytes(64) : 0; }
+size_t ta3n_fwd_batch_workspace_bytes(void) { return 0; }
 
 int ta3n_fwd_batch_flush(void* workspace, size_t workspace_bytes, ta3n_stream_t stream) {
   FwdBatch& b = fwd_batch();
   if (!b.active) return fail(TA3N_ERR_INVALID, "ta3n_fwd_batch_flush without ta3n_fwd_batch_begin");
   b.active = false;
-  // The workspace only feeds the experimental balanced split-K; the default launch plan is the unsplit one.
-  Arena arena(workspace, workspace_bytes);
-  int rc = run_gemm(b.plan, S(stream), (workspace && fixup_enabled()) ? &arena : nullptr);
+  (void)workspace;      // reserved: the forward batch is launched unsplit (more than half a wave of tiles)
+  (void)workspace_bytes;
+  int rc = run_gemm(b.plan, S(stream), nullptr);
   for (auto& f : b.post)
     if (rc == TA3N_OK) rc = f(S(stream));
   b.reset();
@@ -216,7 +218,7 @@ const char* ta3n_last_error(void) { return last_error_buf(); }
 uint64_t ta3n_launch_count(void) { return launch_counter().load(); }
 void ta3n_reset_launch_count(void) { launch_counter().store(0); }
 int ta3n_set_gemm_engine(int engine) {
-  if (engine != TA3N_GEMM_FP32_SIMT && engine != TA3N_GEMM_TF32_TCGEN05 && engine != TA3N_GEMM_TF32X3_TCGEN05)
+  if (engine != TA3N_GEMM_FP32_SIMT && engine != TA3N_GEMM_TF32_TCGEN05)
     return fail(TA3N_ERR_INVALID, "unknown GEMM engine %d", engine);
   gemm_engine().store(engine);
   return TA3N_OK;
@@ -814,16 +816,263 @@ int ta3n_counter_inc(uint64_t* counter, ta3n_stream_t stream) {
   return after_launch();
 }
 
-long long ta3n_debug_balance_splitk(int n, const long long* tiles, const long long* slabs, int* ksplit) {
-  if (n <= 0 || !tiles || !slabs || !ksplit) return -1;
-  std::vector<long> t(tiles, tiles + n), s(slabs, slabs + n);
-  const std::vector<int> ks = balance_split_factors(t, s);
-  std::vector<long> ctas;
-  for (int i = 0; i < n; ++i) {
-    ksplit[i] = ks[i];
-    for (long c = 0; c < t[i] * ks[i]; ++c) ctas.push_back((s[i] + ks[i] - 1) / ks[i] + (ks[i] > 1 ? 2 : 0));
+// ------------------------------------------------------------------------------------------------
+// the fused training step (include/ta3n_b200.h: ta3n_step_*)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kStepMagic = 0x7A3B5700;
+
+int step_kernel_config(int* sm_count) {          // per-device opt-in of the large dynamic shared memory
+  std::lock_guard<std::mutex> lock(device_mu());
+  DeviceInfo* d = device_info();
+  if (!d) return fail(TA3N_ERR_CUDA, "cudaGetDevice failed");
+  if (!d->step_configured) {
+    TA3N_CUDA(cudaFuncSetAttribute(ta3n_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBytes));
+    TA3N_CUDA(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    d->step_configured = true;
   }
-  return tc_makespan(ctas);
+  *sm_count = d->sm_count;
+  return TA3N_OK;
+}
+
+}  // namespace
+
+size_t ta3n_step_workspace_bytes(const ta3n_step_desc* desc) {
+  StepProgram P;
+  if (build_step_program(desc, &P, /*dry=*/true) != TA3N_OK) return 0;
+  BuiltPlan B;
+  if (build_task_graph(P, device_sm_count(), nullptr, 0, &B) != TA3N_OK) return 0;
+  // column-sum partials of the phased executor use the same job preparation -> covered by partial_floats
+  return P.scratch_bytes + Arena::round(B.partial_floats * sizeof(float)) + 4096;
+}
+
+int ta3n_step_run_phased(const ta3n_step_desc* desc, ta3n_stream_t stream) {
+  StepProgram P;
+  TA3N_TRY(build_step_program(desc, &P));
+  cudaStream_t st = S(stream);
+  int sm_count = 148;
+  TA3N_TRY(step_kernel_config(&sm_count));
+  TA3N_TRY(run_gemm(P.g1, st));
+  TA3N_TRY(run_gemm(P.g2, st));
+  TA3N_TRY(run_gemm(P.g3, st));
+  {
+    const int n_tail = (P.M + kTailVideos - 1) / kTailVideos;
+    const size_t smem = (size_t)tail_smem_floats(kTailVideos, P.L.R, desc->H, desc->T, desc->C) * sizeof(float);
+    TA3N_REQUIRE(smem <= 160 * 1024, "row task: shared memory (T, C too large)");
+    pre_launch("step_tail", st);
+    launch_kernel(tail_kernel, n_tail, kRowThreads, smem, st, P.tail);
+    TA3N_TRY(after_launch());
+  }
+  TA3N_TRY(run_gemm(P.g5, st));
+  TA3N_TRY(run_gemm(P.g6, st));
+  TA3N_TRY(run_gemm(P.g7, st));
+  // column sums: parts, then the fixed-order reduction (which also advances the dropout step counter)
+  Arena arena(static_cast<char*>(desc->workspace) + P.scratch_bytes, desc->workspace_bytes - P.scratch_bytes);
+  size_t i = 0;
+  bool counter_done = desc->step_counter == nullptr;
+  while (i < P.jobs.size()) {
+    WColsumTable tab;
+    tab.n_jobs = 0;
+    int max_cb = 1, max_split = 1;
+    while (i < P.jobs.size() && tab.n_jobs < kMaxWColsumJobs) {
+      WColsumJob j = P.jobs[i].job;
+      step_prepare_job(&j);
+      j.partial = arena.floats((size_t)j.nsplit * j.N2 * j.N);
+      if (!j.partial) return fail(TA3N_ERR_WORKSPACE, "fused step: column-sum workspace too small");
+      max_cb = std::max(max_cb, (j.N + 127) / 128);
+      max_split = std::max(max_split, j.nsplit);
+      tab.job[tab.n_jobs++] = j;
+      ++i;
+    }
+    pre_launch("step_colsum", st);
+    launch_kernel(step_colsum_part_kernel, dim3(max_cb, tab.n_jobs, max_split), kRowThreads, 0, st, tab);
+    TA3N_TRY(after_launch());
+    const bool last = i >= P.jobs.size();
+    pre_launch("step_colsum_reduce", st);
+    launch_kernel(step_colsum_reduce_kernel, tab.n_jobs, kRowThreads, 0, st, tab,
+                  reinterpret_cast<unsigned long long*>((last && !counter_done) ? desc->step_counter : nullptr));
+    TA3N_TRY(after_launch());
+    if (last) counter_done = true;
+  }
+  return TA3N_OK;
+}
+
+namespace {
+struct PlanLayout {
+  size_t tasks, groups, segs, maps, jobs, tail, counters, total;
+};
+PlanLayout plan_layout(const BuiltPlan& B) {
+  PlanLayout l;
+  size_t off = 0;
+  auto put = [&](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~size_t(255);
+    return at;
+  };
+  l.maps = put(B.maps.size() * sizeof(CUtensorMap));
+  l.tasks = put(B.tasks.size() * sizeof(StepTask));
+  l.groups = put(B.groups.size() * sizeof(StepGroup));
+  l.segs = put(B.segs.size() * sizeof(SegLite));
+  l.jobs = put(B.jobs.size() * sizeof(WColsumJob));
+  l.tail = put(sizeof(TailArgs));
+  l.counters = put((size_t)B.n_counters * sizeof(int));
+  l.total = off;
+  return l;
+}
+}  // namespace
+
+size_t ta3n_step_plan_bytes(const ta3n_step_desc* desc) {
+  StepProgram P;
+  if (build_step_program(desc, &P, /*dry=*/true) != TA3N_OK) return 0;
+  BuiltPlan B;
+  if (build_task_graph(P, device_sm_count(), nullptr, 0, &B) != TA3N_OK) return 0;
+  return plan_layout(B).total + 1024;
+}
+
+int ta3n_step_build(const ta3n_step_desc* desc, void* plan_dev, size_t plan_bytes, void* handle_host) {
+  TA3N_REQUIRE(plan_dev != nullptr && handle_host != nullptr, "null plan / handle");
+  TA3N_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 255u) == 0, "plan buffer must be 256-byte aligned");
+  StepProgram P;
+  TA3N_TRY(build_step_program(desc, &P));
+  int sm_count = 148;
+  TA3N_TRY(step_kernel_config(&sm_count));
+  BuiltPlan B;
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(desc->workspace) + P.scratch_bytes);
+  const size_t partial_cap = (desc->workspace_bytes - P.scratch_bytes) / sizeof(float);
+  TA3N_TRY(build_task_graph(P, sm_count, partial, partial_cap, &B));
+  const PlanLayout l = plan_layout(B);
+  if (l.total > plan_bytes) return fail(TA3N_ERR_WORKSPACE, "ta3n_step_build: plan buffer too small (%zu < %zu)", plan_bytes, l.total);
+  std::vector<char> host(l.total, 0);
+  memcpy(host.data() + l.maps, B.maps.data(), B.maps.size() * sizeof(CUtensorMap));
+  memcpy(host.data() + l.tasks, B.tasks.data(), B.tasks.size() * sizeof(StepTask));
+  memcpy(host.data() + l.groups, B.groups.data(), B.groups.size() * sizeof(StepGroup));
+  memcpy(host.data() + l.segs, B.segs.data(), B.segs.size() * sizeof(SegLite));
+  memcpy(host.data() + l.jobs, B.jobs.data(), B.jobs.size() * sizeof(WColsumJob));
+  memcpy(host.data() + l.tail, &P.tail, sizeof(TailArgs));
+  TA3N_CUDA(cudaMemcpy(plan_dev, host.data(), l.total, cudaMemcpyHostToDevice));
+  char* base = static_cast<char*>(plan_dev);
+  StepHandle h;
+  memset(&h, 0, sizeof(h));
+  h.hd.n_tasks = (int)B.tasks.size();
+  h.hd.n_counters = B.n_counters;
+  h.hd.n_groups = (int)B.groups.size();
+  h.hd.n_jobs = (int)B.jobs.size();
+  h.hd.tasks = reinterpret_cast<const StepTask*>(base + l.tasks);
+  h.hd.groups = reinterpret_cast<const StepGroup*>(base + l.groups);
+  h.hd.segs = reinterpret_cast<const SegLite*>(base + l.segs);
+  h.hd.maps = reinterpret_cast<const CUtensorMap*>(base + l.maps);
+  h.hd.jobs = reinterpret_cast<const WColsumJob*>(base + l.jobs);
+  h.hd.tail = reinterpret_cast<const TailArgs*>(base + l.tail);
+  h.hd.counters = reinterpret_cast<int*>(base + l.counters);
+  h.hd.step_counter = reinterpret_cast<unsigned long long*>(desc->step_counter);
+  h.hd.tail_videos = B.tail_videos;
+  h.magic = kStepMagic;
+  h.n_gemm_tiles = B.n_gemm_tiles;
+  h.smem_bytes = kStepSmemBytes;
+  h.grid = sm_count;
+  memset(handle_host, 0, TA3N_STEP_HANDLE_BYTES);
+  memcpy(handle_host, &h, sizeof(h));
+  return TA3N_OK;
+}
+
+int ta3n_step_run(const void* handle_host, ta3n_stream_t stream) {
+  TA3N_REQUIRE(handle_host != nullptr, "null handle");
+  StepHandle h;
+  memcpy(&h, handle_host, sizeof(h));
+  TA3N_REQUIRE(h.magic == kStepMagic, "not a handle filled by ta3n_step_build");
+  cudaStream_t st = S(stream);
+  TA3N_CUDA(cudaMemsetAsync(h.hd.counters, 0, (size_t)h.hd.n_counters * sizeof(int), st));
+  pre_launch("step_kernel", st);
+  ta3n_step_kernel<<<h.grid, kStepThreads, h.smem_bytes, st>>>(h.hd);
+  return after_launch();
+}
+
+// Host-only description of the task graph the fused step would run for `desc` (no CUDA call; pointers in desc only
+// need to be non-null): "tasks T gemm_tiles G tail R colsum_parts P colsum_reduces Q counters N maps K slabs S".
+size_t ta3n_step_describe(const ta3n_step_desc* desc, char* buf, size_t buf_bytes) {
+  StepProgram P;
+  if (build_step_program(desc, &P, /*dry=*/true) != TA3N_OK) return 0;
+  BuiltPlan B;
+  if (build_task_graph(P, 148, nullptr, 0, &B) != TA3N_OK) return 0;
+  int n_type[5] = {0, 0, 0, 0, 0};
+  long slabs = 0;
+  int bad_order = 0;
+  std::vector<int> signalled_before(B.n_counters, 0);
+  for (size_t i = 0; i < B.tasks.size(); ++i) {
+    const StepTask& t = B.tasks[i];
+    n_type[t.type]++;
+    if (t.type == TASK_GEMM) {
+      const StepGroup& sg = B.groups[t.group];
+      int n = 0;
+      for (int k = 0; k < sg.g.seg_count; ++k) n += (B.segs[sg.seg_begin + k].len + TC_BK - 1) / TC_BK;
+      slabs += (n + sg.g.ksplit - 1) / sg.g.ksplit;
+    }
+    // every wait must be satisfiable by signals of EARLIER tasks (the deadlock-freedom invariant)
+    for (int r = 0; r < 2; ++r)
+      for (int c = t.wait_begin[r]; c < t.wait_end[r]; ++c)
+        if (c < 0 || c >= B.n_counters - 1 || signalled_before[c] < t.wait_val[r]) ++bad_order;
+    if (t.signal >= 0) signalled_before[t.signal]++;
+  }
+  char line[512];
+  snprintf(line, sizeof(line),
+           "tasks %zu gemm_tiles %d tail %d colsum_parts %d colsum_reduces %d counters %d maps %zu groups %zu slabs %ld "
+           "partial_floats %zu unsatisfiable_waits %d",
+           B.tasks.size(), n_type[TASK_GEMM], n_type[TASK_TAIL], n_type[TASK_COLSUM_PART], n_type[TASK_COLSUM_REDUCE],
+           B.n_counters, B.maps.size(), B.groups.size(), slabs, B.partial_floats, bad_order);
+  const size_t n = strlen(line);
+  if (buf && buf_bytes > 0) {
+    const size_t c = n < buf_bytes - 1 ? n : buf_bytes - 1;
+    memcpy(buf, line, c);
+    buf[c] = 0;
+  }
+  return n;
+}
+
+int ta3n_step_set_trace(void* handle_host, unsigned long long* trace_dev) {
+  TA3N_REQUIRE(handle_host != nullptr, "null handle");
+  StepHandle h;
+  memcpy(&h, handle_host, sizeof(h));
+  TA3N_REQUIRE(h.magic == kStepMagic, "not a handle filled by ta3n_step_build");
+  h.hd.trace = trace_dev;
+  memcpy(handle_host, &h, sizeof(h));
+  return TA3N_OK;
+}
+
+int ta3n_step_info(const void* handle_host, int* n_tasks, int* n_counters, int* n_gemm_tiles) {
+  TA3N_REQUIRE(handle_host != nullptr, "null handle");
+  StepHandle h;
+  memcpy(&h, handle_host, sizeof(h));
+  TA3N_REQUIRE(h.magic == kStepMagic, "not a handle filled by ta3n_step_build");
+  if (n_tasks) *n_tasks = h.hd.n_tasks;
+  if (n_counters) *n_counters = h.hd.n_counters;
+  if (n_gemm_tiles) *n_gemm_tiles = h.n_gemm_tiles;
+  return TA3N_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gradient all-reduce over peer / multicast memory (csrc/allreduce.cuh)
+// ------------------------------------------------------------------------------------------------
+size_t ta3n_allreduce_flag_bytes(int world) { return (size_t)2 * kArBlocks * (world > 0 ? world : 1) * sizeof(unsigned); }
+
+int ta3n_allreduce_mean(float* const* peer_bufs_host, float* multicast_buf, uint32_t* const* peer_flags_host,
+                        const uint64_t* seq_dev, int rank, int world, long long n, ta3n_stream_t stream) {
+  TA3N_REQUIRE(peer_bufs_host && peer_flags_host && seq_dev, "null argument");
+  TA3N_REQUIRE(world >= 1 && world <= kArMaxWorld && rank >= 0 && rank < world, "bad rank / world size");
+  TA3N_REQUIRE(n > 0 && n % 4 == 0, "element count must be a positive multiple of 4");
+  ArPeers P;
+  memset(&P, 0, sizeof(P));
+  for (int p = 0; p < world; ++p) {
+    TA3N_REQUIRE(peer_bufs_host[p] && peer_flags_host[p], "null peer pointer");
+    TA3N_REQUIRE((reinterpret_cast<uintptr_t>(peer_bufs_host[p]) & 15u) == 0, "buffers must be 16-byte aligned");
+    P.buf[p] = peer_bufs_host[p];
+    P.flags[p] = reinterpret_cast<unsigned*>(peer_flags_host[p]);
+  }
+  TA3N_REQUIRE((reinterpret_cast<uintptr_t>(multicast_buf) & 15u) == 0, "multicast mapping must be 16-byte aligned");
+  pre_launch("allreduce_mean", S(stream));
+  launch_kernel(allreduce_mean_kernel, kArBlocks, kArThreads, 0, S(stream), P, multicast_buf,
+                reinterpret_cast<const unsigned long long*>(seq_dev), rank, world, (size_t)(n / 4), 1.0f / (float)world);
+  return after_launch();
 }
 
 // ---- optimizer step: clip_grad_norm_ + SGD-Nesterov over flat buffers (main.py:83, 578-583) ----

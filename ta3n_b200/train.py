@@ -18,6 +18,8 @@ discriminator + shared layer backward) computes; only the second, smaller all-re
 """
 from __future__ import annotations
 
+import ctypes as C
+import math
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -47,6 +49,11 @@ class SGDNesterov:
 def lr_dann(lr0: float, p: float) -> float:
     """adjust_learning_rate_dann (main.py:800-802): p = training progress in [0, 1] (main.py:349)."""
     return lr0 / (1.0 + 10.0 * p) ** 0.75
+
+
+def beta_dann(p: float) -> float:
+    """main.py:351: the DANN schedule of the GRL coefficient; replaces every NEGATIVE entry of --beta (main.py:352)."""
+    return 2.0 / (1.0 + math.exp(-10.0 * p)) - 1.0
 
 
 def bucket_layout(params):
@@ -94,7 +101,19 @@ class TrainStep:
                  use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False,
                  overlap_wgrad: bool = False, parallel_branches: bool = False,
                  overlap_allreduce: Optional[bool] = None, graph_collectives: Optional[bool] = None,
-                 optimizer: Optional[SGDNesterov] = None):
+                 optimizer: Optional[SGDNesterov] = None, mode: Optional[str] = None,
+                 class_weight: Optional[torch.Tensor] = None, domain_weight: Sequence[float] = (1.0, 1.0),
+                 allreduce: Optional[str] = None):
+        """mode: 'fused' (default when the model has no frame attention) = the whole forward + loss + backward as ONE
+        persistent kernel (C ABI ta3n_step_build / ta3n_step_run); 'phased' = the same work as 9 launches
+        (ta3n_step_run_phased); 'legacy' = the round-1 per-operator sequence (25 launches; the only mode that
+        supports use_attn_frame).  class_weight / domain_weight: the weights of criterion / criterion_domain
+        (main.py:160-167, 204-205; fused and phased modes).  A negative beta entry selects the DANN schedule for that
+        level (main.py:350-352): call set_progress(p) every step.
+        allreduce (world > 1): 'peer' = this library's one-kernel all-reduce over NVLink peer / NVSwitch multicast
+        memory (csrc/allreduce.cuh; the gradient bucket then lives in symmetric memory and the whole iteration --
+        step, all-reduce, optimizer -- is one CUDA graph), 'nccl' = torch.distributed all_reduce between graphs;
+        default: 'peer' in fused / phased mode when symmetric memory can be set up, else 'nccl'."""
         if not model.training:
             raise ValueError("TrainStep needs model.train() (dropout state is fixed at construction)")
         self.model = model
@@ -118,8 +137,27 @@ class TrainStep:
                 raise NotImplementedError("attentive_entropy needs place_adv[0] == place_adv[1] == 'Y'")
             self.flags |= 8
         # split the step in two graphs around the first gradient bucket only when there is something to overlap
+        if mode is None:
+            # the fused kernel is a tcgen05 kernel; with the exact fp32 engine selected the same step runs phased
+            # (its grouped GEMM launches honour the engine), so engine-parametrised callers get what they selected
+            mode = "legacy" if model.use_attn_frame != "none" else \
+                ("fused" if _lib.get_gemm_engine() == "tf32" else "phased")
+        if mode not in ("fused", "phased", "legacy"):
+            raise ValueError(f"unknown TrainStep mode {mode!r}")
+        if mode != "legacy" and model.use_attn_frame != "none":
+            raise NotImplementedError("the fused step does not cover use_attn_frame; use mode='legacy'")
+        if mode != "legacy" and (overlap_wgrad or parallel_branches or overlap_allreduce or graph_collectives):
+            raise ValueError("overlap_wgrad / parallel_branches / overlap_allreduce / graph_collectives are options "
+                             "of mode='legacy' (the fused step is a single kernel)")
+        self.mode = mode
+        self.beta_spec = [float(b) for b in beta]
+        if mode == "legacy" and any(b < 0 for b in self.beta_spec):
+            raise ValueError("negative beta (= DANN schedule, main.py:350-352) needs mode='fused' or 'phased': the "
+                             "legacy sequence bakes beta into the captured graph")
+        if class_weight is not None and mode == "legacy":
+            raise ValueError("class_weight needs mode='fused' or 'phased'")
         self.split = (self.world > 1) if overlap_allreduce is None else bool(overlap_allreduce)
-        if model.use_attn_frame != "none":
+        if model.use_attn_frame != "none" or mode != "legacy":
             self.split = False     # frame attention couples the TRN and frame-discriminator gradients
         # graph_collectives=True captures the two NCCL all-reduces INSIDE the step's graph.  It works and is
         # marginally faster (N=2: 0.371 vs 0.378 ms/step) but process-group teardown then hangs while the graphs
@@ -133,7 +171,7 @@ class TrainStep:
         # views are installed as .grad; the parameters live in a twin flat buffer (same offsets)
         self.flat_param = flatten_parameters(model)
         order, offs, n, self.early_numel = bucket_layout(self.params)
-        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_grad = self._alloc_gradient_bucket(n, allreduce)
         self.grad_views: List[Optional[torch.Tensor]] = [None] * len(self.params)
         for idx in order:
             p = self.params[idx]
@@ -176,8 +214,19 @@ class TrainStep:
         self.loss_ws = self.bufs.workspace("loss", _lib.load().ta3n_loss_workspace_bytes(self.M))
 
         di, dv = float(model.dropout_rate_i), float(model.dropout_rate_v)
+        # independent dropout masks per data-parallel rank, like the reference's DataParallel replicas
+        rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        seed = (int(seed) ^ (rank * 0x9E3779B97F4A7C15)) & (2 ** 63 - 1)
+        # GRL coefficients in device memory (fused / phased): rescheduled per step without re-capturing
+        self.beta_dev = torch.tensor([max(b, 0.0) for b in self.beta_spec], device=dev, dtype=torch.float32)
+        self._beta_host = torch.tensor([max(b, 0.0) for b in self.beta_spec], dtype=torch.float32).pin_memory()
+        self.class_weight = None if class_weight is None else \
+            class_weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if self.class_weight is not None and self.class_weight.numel() != self.C:
+            raise ValueError("class_weight must have one entry per class")
+        self.domain_weight = (float(domain_weight[0]), float(domain_weight[1]))
         self.spec = TF.PathSpec(
-            num_segments=self.T, beta=(float(beta[0]), float(beta[1]), float(beta[2])), mu=0.0, reverse=False,
+            num_segments=self.T, beta=tuple(max(b, 0.0) for b in self.beta_spec), mu=0.0, reverse=False,
             use_attn=model.use_attn != "none", use_attn_frame=model.use_attn_frame != "none",
             drop_i=TF.DropSpec(p=di, seed=seed, step=self.step_counter) if di > 0 else TF.DropSpec(),
             drop_v=TF.DropSpec(p=dv, seed=seed ^ 0x9E3779B9, step=self.step_counter) if dv > 0 else TF.DropSpec())
@@ -188,11 +237,175 @@ class TrainStep:
         self.launches_per_step = 0               # kernels of libta3n_sm100.so per step (counted at capture)
         self.use_graph = bool(use_graph)
         self.graphs = [None] * self.n_slots      # per input slot: (graph_a, graph_b or None)
+        self.step_descs = [None] * self.n_slots  # fused / phased: ta3n_step_desc per input slot (+ keep-alives)
+        self.step_handles = [None] * self.n_slots
+        if self.mode != "legacy":
+            for slot in range(self.n_slots):
+                self._build_step(slot)
         if use_graph:
             for slot in range(self.n_slots):
+                self.active = slot
                 self.xs, self.xt, self.labels, self.valid = self.slots[slot]
                 self.graphs[slot] = self._capture()
+            self.active = 0
             self.xs, self.xt, self.labels, self.valid = self.slots[0]
+
+    # -- gradient bucket / all-reduce ------------------------------------------------------------------
+    def _alloc_gradient_bucket(self, n, allreduce):
+        """The flat gradient bucket.  With several ranks it is allocated in SYMMETRIC memory (same size on every rank,
+        peer-mapped over NVLink, multicast-mapped through the NVSwitch when available) so that the library's own
+        all-reduce kernel can read and write every rank's copy (ta3n_allreduce_mean)."""
+        import os
+        self.ar = None
+        want = allreduce or os.environ.get("TA3N_ALLREDUCE") or ("peer" if self.mode != "legacy" else "nccl")
+        if want not in ("peer", "nccl"):
+            raise ValueError(f"allreduce must be 'peer' or 'nccl', got {want!r}")
+        if self.world == 1 or want == "nccl":
+            return torch.zeros(n, device=self.device, dtype=torch.float32)
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else dist.group.WORLD
+            lib = _lib.load()
+            flat = symm.empty(n, dtype=torch.float32, device=self.device)
+            flat.zero_()
+            hdl = symm.rendezvous(flat, group)
+            flags = symm.empty(lib.ta3n_allreduce_flag_bytes(self.world) // 4, dtype=torch.int32, device=self.device)
+            flags.zero_()
+            fh = symm.rendezvous(flags, group)
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)              # every rank's flags are zero before anybody signals
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            if os.environ.get("TA3N_ALLREDUCE_NO_MULTICAST") == "1":
+                mc = 0
+            self.ar = dict(bufs=[int(p) for p in hdl.buffer_ptrs], flags=[int(p) for p in fh.buffer_ptrs],
+                           mc=mc, rank=int(hdl.rank), world=int(hdl.world_size), keep=(flat, flags, hdl, fh))
+            return flat
+        except Exception as e:      # no symmetric memory on this system / build: NCCL between graphs
+            if allreduce == "peer":
+                raise
+            import warnings
+            warnings.warn(f"ta3n_b200: symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL")
+            self.ar = None
+            return torch.zeros(n, device=self.device, dtype=torch.float32)
+
+    def _enqueue_allreduce(self):
+        """Mean of the gradient bucket over the ranks on the current stream (graph-capturable)."""
+        a = self.ar
+        check(_lib.load().ta3n_allreduce_mean(
+            _lib.ptr_array(a["bufs"]), a["mc"] or None, _lib.ptr_array(a["flags"]), _P(self.step_counter),
+            a["rank"], a["world"], self.flat_grad.numel(), TF._stream()))
+
+    # -- the fused step (C ABI ta3n_step_*) ------------------------------------------------------------
+    def _build_step(self, slot):
+        """Describe the step for input slot `slot` (ta3n_step_desc) and, in fused mode, build its task graph."""
+        lib = _lib.load()
+        xs, xt, labels, valid = self.slots[slot]
+        R, M, T = self.R, self.M, self.T
+        (w_sh, b_sh), (w1f, b1f, w2f, b2f), trn_w, trn_b, r_w1, r_b1, r_w2, r_b2, (w_c, b_c), \
+            (w1v, b1v, w2v, b2v) = TF._split_params(self.params, R)
+        (dw_sh, db_sh), (dw1f, db1f, dw2f, db2f), dtrn_w, dtrn_b, dr_w1, dr_b1, dr_w2, dr_b2, (dw_c, db_c), \
+            (dw1v, db1v, dw2v, db2v) = TF._split_params(self.grad_views, R)
+        F, H = w_sh.shape[0], trn_w[0].shape[0]
+        rs = TF.relation_set(T)
+        new = self.bufs.get
+        bufs = dict(feat=new("feat", M * T, F), hid_f=new("hid_f", M * T, F), pred_frame=new("pred_frame", M * T, 2),
+                    act=new("act", rs.n_rel, M, H), feat_rel=new("feat_rel", M, R, H), hid_r=new("hid_r", R, M, H),
+                    pred_rel=new("pred_rel", M, R, 2), attn=new("attn", M, R), feat_video=new("feat_video", M, H),
+                    dropped=new("dropped", M, H), pred_video=new("pred_video", M, self.C), hid_v=new("hid_v", M, H),
+                    pred_dom=new("pred_dom_video", M, 2))
+        d = _lib.StepDesc()
+        d.Bs, d.Bt, d.T, d.D, d.F, d.H, d.C = self.Bs, self.Bt, T, self.D, F, H, self.C
+        d.use_attn = int(self.spec.use_attn)
+        d.loss_flags = self.flags
+        d.gamma = self.gamma
+        d.domain_weight[0], d.domain_weight[1] = self.domain_weight
+        d.class_weight = _P(self.class_weight)
+        d.beta_dev = _P(self.beta_dev)
+        d.tab = C.pointer(rs.ctable)
+        d.x_src, d.x_tgt, d.labels, d.valid_rows = _P(xs), _P(xt), _P(labels), _P(valid)
+        di, dv = self.spec.drop_i.cstruct(), self.spec.drop_v.cstruct()
+        if di is not None:
+            d.drop_i = di
+        if dv is not None:
+            d.drop_v = dv
+        keep = []          # host pointer arrays must outlive every call that reads the descriptor
+
+        def arr(ts):
+            a = _lib.ptr_array([_P(t) for t in ts])
+            keep.append(a)
+            return a
+
+        d.W_sh, d.b_sh, d.W1f, d.b1f, d.W2f, d.b2f = map(_P, (w_sh, b_sh, w1f, b1f, w2f, b2f))
+        d.W_trn_host, d.b_trn_host = arr(trn_w), arr(trn_b)
+        d.W1r_host, d.b1r_host, d.W2r_host, d.b2r_host = arr(r_w1), arr(r_b1), arr(r_w2), arr(r_b2)
+        d.Wc, d.bc, d.W1v, d.b1v, d.W2v, d.b2v = map(_P, (w_c, b_c, w1v, b1v, w2v, b2v))
+        d.dW_sh, d.db_sh, d.dW1f, d.db1f, d.dW2f, d.db2f = map(_P, (dw_sh, db_sh, dw1f, db1f, dw2f, db2f))
+        d.dW_trn_host, d.db_trn_host = arr(dtrn_w), arr(dtrn_b)
+        d.dW1r_host, d.db1r_host, d.dW2r_host, d.db2r_host = arr(dr_w1), arr(dr_b1), arr(dr_w2), arr(dr_b2)
+        d.dWc, d.dbc, d.dW1v, d.db1v, d.dW2v, d.db2v = map(_P, (dw_c, db_c, dw1v, db1v, dw2v, db2v))
+        for k, t in bufs.items():
+            setattr(d, k, _P(t))
+        d.loss = _P(self.loss)
+        d.step_counter = _P(self.step_counter)
+        ws_bytes = lib.ta3n_step_workspace_bytes(C.byref(d))
+        if ws_bytes == 0:
+            raise _lib.Ta3nError("ta3n_step_workspace_bytes: " + (lib.ta3n_last_error() or b"?").decode())
+        ws = self.bufs.workspace("step", ws_bytes)          # shared by the input slots (they never run concurrently)
+        d.workspace, d.workspace_bytes = _P(ws), ws.numel()
+        self.step_descs[slot] = (d, keep, rs)
+        self.step_bufs = bufs
+        if self.mode == "fused":
+            plan = self.bufs.workspace(f"step_plan{slot}", lib.ta3n_step_plan_bytes(C.byref(d)))
+            handle = C.create_string_buffer(_lib.STEP_HANDLE_BYTES)
+            check(lib.ta3n_step_build(C.byref(d), _P(plan), plan.numel(), handle))
+            self.step_handles[slot] = handle
+        self.outputs = (bufs["feat"].view(M, T, F), bufs["pred_frame"].view(M, T, 2), bufs["attn"], bufs["pred_rel"],
+                        bufs["feat_video"], bufs["pred_video"], bufs["pred_dom"])
+
+    def step_info(self):
+        """(tasks, arrival counters, GEMM tiles) of the fused step's task graph."""
+        n = [C.c_int(), C.c_int(), C.c_int()]
+        check(_lib.load().ta3n_step_info(self.step_handles[self.active], *[C.byref(x) for x in n]))
+        return tuple(x.value for x in n)
+
+    def trace(self, enable: bool = True):
+        """Fused mode, eager or before capture: record {SM, scheduled, accumulator ready, done} per task of the step
+        kernel (ta3n_step_set_trace).  Returns the device tensor (n_tasks, 4) int64 the kernel fills."""
+        lib = _lib.load()
+        n_tasks = self.step_info()[0]
+        if not hasattr(self, "_trace_buf"):
+            self._trace_buf = torch.zeros(n_tasks, 4, device=self.device, dtype=torch.int64)
+        for h in self.step_handles:
+            if h is not None:
+                check(lib.ta3n_step_set_trace(h, _P(self._trace_buf) if enable else None))
+        return self._trace_buf
+
+    def set_beta(self, beta: Sequence[float]):
+        """New GRL coefficients {relation, video, frame} for the following steps (fused / phased modes): one
+        12-byte async copy, no re-capture."""
+        if self.mode == "legacy":
+            raise ValueError("set_beta needs mode='fused' or 'phased'")
+        for i in range(3):
+            self._beta_host[i] = float(beta[i])
+        self.beta_dev.copy_(self._beta_host, non_blocking=True)
+
+    def set_progress(self, p: float, lr0: Optional[float] = None):
+        """Per-step schedules of main.py for training progress p in [0, 1] (main.py:349): every NEGATIVE entry of
+        the configured beta takes the DANN value 2/(1+exp(-10p))-1 (main.py:350-352); with lr0 the learning rate
+        follows adjust_learning_rate_dann (main.py:800-802)."""
+        if any(b < 0 for b in self.beta_spec):
+            bd = beta_dann(p)
+            self.set_beta([bd if b < 0 else b for b in self.beta_spec])
+        if lr0 is not None:
+            self.set_lr(lr_dann(lr0, p))
+
+    def install_grads(self):
+        """(Re-)install the flat-bucket views as ``param.grad``.  ``optimizer.zero_grad()`` (set_to_none=True by
+        default) or another TrainStep / autograd backward on the same model detaches them; run() re-installs them,
+        so a stock ``zero_grad(); step.run(); optimizer.step()`` loop sees the gradients this step wrote."""
+        for p, view in zip(self.params, self.grad_views):
+            if view is not None and p.grad is not view:
+                p.grad = view
 
     # -- the fixed launch sequence ---------------------------------------------------------------------
     def _enqueue_optimizer(self):
@@ -206,6 +419,8 @@ class TrainStep:
 
     def set_lr(self, lr: float):
         """Per-step learning-rate schedules (main.py:800-802): one 4-byte async copy, no re-capture."""
+        if self.opt is None:
+            raise ValueError("set_lr needs TrainStep(optimizer=SGDNesterov(...))")
         self._lr_host[0] = float(lr)
         self.lr_dev.copy_(self._lr_host, non_blocking=True)
         self.opt.lr = float(lr)
@@ -217,6 +432,16 @@ class TrainStep:
         all-reduce instead)."""
         lib = _lib.load()
         st = TF._stream()
+        if self.mode != "legacy":
+            if self.mode == "fused":
+                check(lib.ta3n_step_run(self.step_handles[self.active], st))
+            else:
+                check(lib.ta3n_step_run_phased(C.byref(self.step_descs[self.active][0]), st))
+            if self.ar is not None:
+                self._enqueue_allreduce()         # same stream, same graph: step -> all-reduce -> optimizer
+            if optimizer and self.opt is not None:
+                self._enqueue_optimizer()
+            return
         check(lib.ta3n_counter_inc(_P(self.step_counter), st))          # fresh dropout masks per step
         saved, outputs, dims = TF.path_forward(self.spec, self.xs, self.xt, self.params, self.bufs, batch_gemms=True)
         self.outputs = outputs
@@ -251,6 +476,8 @@ class TrainStep:
             else:
                 check(lib.ta3n_wgrad_defer_flush(_P(ws), ws.numel(), TF._stream()))
             if name == "trn" and at_split is not None:
+                if self.overlap_wgrad:
+                    main.wait_stream(side)        # the early bucket must be complete before it is all-reduced / cut
                 at_split()
             if name != "shared":
                 check(lib.ta3n_wgrad_defer_begin())
@@ -299,7 +526,8 @@ class TrainStep:
                 warnings.warn(f"ta3n_b200: NCCL capture failed ({type(e).__name__}: {e}); using split graphs")
                 self.collectives_captured = False
                 torch.cuda.synchronize()
-        inline = self.world == 1          # single rank: the optimizer is part of the (last) graph
+        # single rank, or the library's own all-reduce inside the graph: the optimizer is part of the (last) graph
+        inline = self.world == 1 or self.ar is not None
         if not self.split:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -386,17 +614,17 @@ class TrainStep:
                 if self.world > 1:
                     pending = self._allreduce(self.bucket_early, async_op=True)   # overlaps graph b
                 gb.replay()
-            opt_done = opt_done or self.world == 1 or self.collectives_captured
+            opt_done = opt_done or self.world == 1 or self.collectives_captured or self.ar is not None
         else:
             n0 = _lib.launch_count()
-            self._enqueue(optimizer=self.world == 1)
+            self._enqueue(optimizer=self.world == 1 or self.ar is not None)
             self.launches_per_step = _lib.launch_count() - n0
-            opt_done = opt_done or self.world == 1
+            opt_done = opt_done or self.world == 1 or self.ar is not None
         if self.n_slots > 1:
             ev = torch.cuda.Event()
             ev.record()
             self.consumed[self.active] = ev
-        if self.world > 1 and not (self.use_graph and self.collectives_captured):
+        if self.world > 1 and self.ar is None and not (self.use_graph and self.collectives_captured):
             if pending is not None:
                 self._allreduce(self.bucket_late)
                 pending.wait()
@@ -404,6 +632,7 @@ class TrainStep:
                 self._allreduce(self.flat_grad)
         if not opt_done:
             self._enqueue_optimizer()             # after the all-reduce: every rank applies the same update
+        self.install_grads()
         return self.loss
 
     def __call__(self, source, target, labels):

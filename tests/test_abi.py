@@ -45,6 +45,7 @@ def test_abi_version_and_engine_switch(lib):
     assert _lib.get_gemm_engine() == "fp32"
     assert lib.ta3n_set_gemm_engine(7) != 0
     assert b"unknown GEMM engine" in lib.ta3n_last_error()
+    _lib.set_gemm_engine("tf32")          # the library default
 
 
 def test_argument_validation_needs_no_gpu(lib):
@@ -103,29 +104,3 @@ def test_relation_table_matches_survey_appendix_a():
     assert (r9.n_rel, r9.n_slots) == (22, 114)
 
 
-def test_split_k_balance_model_on_the_benchmark_launches(lib):
-    """Host logic of the experimental in-kernel split-K fix-up, no GPU needed."""
-    import ctypes as C
-
-    def plan(groups):
-        n = len(groups)
-        tiles = (C.c_longlong * n)(*[g[0] for g in groups])
-        slabs = (C.c_longlong * n)(*[g[1] for g in groups])
-        ks = (C.c_int * n)()
-        span = lib.ta3n_debug_balance_splitk(n, tiles, slabs, ks)
-        return list(ks), span
-
-    # forward batch at cfg2: frame discriminator (80 tiles x 16 slabs) + TRN scales 5,4,4,4,3,3,3,2,2,2 (8 tiles each)
-    fwd = [(80, 16), (8, 80)] + [(8, 64)] * 3 + [(8, 48)] * 3 + [(8, 32)] * 3
-    ks, span = plan(fwd)
-    assert ks[0] == 1 and ks[1] == 2 and ks[2:5] == [2, 2, 2] and ks[8:] == [1, 1, 1]
-    assert sum(t * k for (t, _), k in zip(fwd, ks)) <= 256          # one resident wave
-    assert span <= 0.7 * 80                                         # critical path 80 slabs -> <= 56
-    # a homogeneous 80-tile launch (shared layer forward): splitting by two only doubles up 12 SMs (68 > 64 slabs),
-    # by three shortens the critical path to two 24-slab CTAs per SM
-    ks, span = plan([(80, 64)])
-    assert ks == [3] and span <= 48
-    # an already wave-filling launch is left alone as well
-    assert plan([(148, 40)])[0] == [1]
-    # short K: never split below 8 slabs per CTA
-    assert plan([(4, 12), (4, 100)])[0][0] == 1

@@ -76,3 +76,27 @@ def test_oracle_train_iteration_equals_reference_loop():
         assert float(norm_ref) > 0.05
     for name, prm in model.named_parameters():
         assert_close(params[name], prm.detach(), 1e-6, f"param {name}")
+
+
+def test_weighted_losses_match_the_reference_criteria():
+    """main.py:160-167, 204-205: criterion / criterion_domain with class / domain weights, on the live reference's
+    outputs, against oracle.compose_loss(class_weight=, domain_weight=)."""
+    c = gen_golden.CASES["ragged_6_3"]
+    model, outs_ref, _, _ = gen_golden.run_reference(c)
+    cfg, xs, xt, labels, masks = gen_golden.case_inputs(c)
+    cw = 1.0 / torch.tensor([0.05, 0.2, 0.1, 0.05, 0.1, 0.05, 0.05, 0.1, 0.1, 0.05, 0.1, 0.05])
+    dw = torch.tensor([1.0 / 300, 1.0 / 170])
+    criterion = torch.nn.CrossEntropyLoss(weight=cw)                 # main.py:204
+    criterion_domain = torch.nn.CrossEntropyLoss(weight=dw)          # main.py:205
+    (_, out_s, _, pd_s, _, _, out_t, _, pd_t, _) = outs_ref
+    ref = criterion(out_s, labels)                                   # main.py:446
+    alls = []
+    for lvl in range(3):                                             # main.py:513-536
+        ps, pt = pd_s[lvl].view(-1, 2), pd_t[lvl].view(-1, 2)
+        dom = torch.cat((torch.zeros(ps.size(0)).long(), torch.ones(pt.size(0)).long()), 0)
+        alls.append(torch.cat((ps, pt), 0))
+        ref = ref + criterion_domain(alls[-1], dom)
+    _, _, ref_loss = ref_shims.load()
+    ref = ref + gen_golden.GAMMA * ref_loss.attentive_entropy(torch.cat((out_s, out_t), 0), alls[1])
+    got = orc.compose_loss(outs_ref, labels, gen_golden.GAMMA, class_weight=cw, domain_weight=dw)
+    assert_close(got.detach(), ref.detach(), 1e-6, "weighted loss")

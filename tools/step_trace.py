@@ -1,0 +1,69 @@
+"""Where does the time of the fused step kernel go?  Runs TrainStep(mode='fused') eagerly with the per-task trace on
+and prints, per task kind, count / busy time, the wall span of each stage and SM utilisation.
+    python tools/step_trace.py [B] [T] [C]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ta3n_b200  # noqa: E402
+from ta3n_b200.models import VideoModel  # noqa: E402
+from ta3n_b200.train import TrainStep  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+Cn = int(sys.argv[3]) if len(sys.argv) > 3 else 12
+dev = torch.device("cuda:0")
+ta3n_b200.set_gemm_engine("tf32")
+torch.manual_seed(1234)
+m = VideoModel(Cn, "video", "trn-m", "RGB", train_segments=T, val_segments=T, add_fc=1, fc_dim=512, dropout_i=0.5,
+               dropout_v=0.5, partial_bn=False, use_bn="none", ens_DA="none", use_attn="TransAttn",
+               use_attn_frame="none", share_params="Y", verbose=False).to(dev).train()
+g = torch.Generator().manual_seed(4321)
+xs, xt = torch.randn(B, T, 2048, generator=g), torch.randn(B, T, 2048, generator=g)
+labels = torch.arange(B) % Cn
+step = TrainStep(m, B, B, (0.75, 0.75, 0.5), gamma=0.003, use_graph=False, mode="fused")
+step.load(xs, xt, labels)
+for _ in range(3):
+    step.run()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+tr = step.trace(True)
+flush.fill_(1)
+step.run()
+torch.cuda.synchronize()
+t = tr.cpu()
+tag, sched, acc, done = t[:, 0], t[:, 1], t[:, 2], t[:, 3]
+sm = tag & 0xFFFF
+typ = (tag >> 16) & 0xFF
+grp = (tag >> 24) & 0xFFFFFF
+mode = (tag >> 48) & 0xF
+nit = (tag >> 52) & 0xFFF
+t0 = int(sched[sched > 0].min())
+span = (int(done.max()) - t0) / 1e3
+print(f"tasks {len(t)}  span {span:.1f} us  SMs used {len(set(sm.tolist()))}")
+names = {0: "gemm", 1: "tail", 2: "colsum_part", 3: "colsum_reduce", 4: "finish"}
+busy_total = 0.0
+for k, nm in names.items():
+    sel = typ == k
+    if sel.sum() == 0:
+        continue
+    dur = (done[sel] - sched[sel]).double() / 1e3
+    busy_total += float(dur.sum())
+    extra = ""
+    if k == 0:
+        ml = (acc[sel] - sched[sel]).double() / 1e3
+        ep = (done[sel] - acc[sel]).double() / 1e3
+        extra = f"  wait-for-accumulator avg {ml.mean():.2f} us  epilogue avg {ep.mean():.2f} us  slabs {int(nit[sel].sum())}"
+    print(f"  {nm:14s} n={int(sel.sum()):5d}  busy {dur.sum():9.1f} us  avg {dur.mean():6.2f}  max {dur.max():6.2f}{extra}")
+print(f"  epilogue-warp busy fraction: {busy_total / (span * len(set(sm.tolist()))):.2f}")
+# per GEMM group: when did it start / end (relative), tiles, avg duration
+print("  group  tiles  slabs/tile  first_start  last_end   avg_dur (us)")
+for gidx in sorted(set(grp[typ == 0].tolist())):
+    sel = (typ == 0) & (grp == gidx)
+    print(f"  {gidx:5d}  {int(sel.sum()):5d}  {float(nit[sel].double().mean()):9.1f}  {(int(sched[sel].min()) - t0) / 1e3:10.1f}  "
+          f"{(int(done[sel].max()) - t0) / 1e3:9.1f}  {float((done[sel] - sched[sel]).double().mean()) / 1e3:8.2f}")
+for k in (1, 2, 3):
+    sel = typ == k
+    if sel.sum():
+        print(f"  {names[k]:14s} first_start {(int(sched[sel].min()) - t0) / 1e3:8.1f}  last_end {(int(done[sel].max()) - t0) / 1e3:8.1f}")
