@@ -300,6 +300,8 @@ size_t ta3n_step_describe(const ta3n_step_desc* desc, char* buf, size_t buf_byte
 /* Optional per-task trace: trace_dev (device, n_tasks * 4 uint64) receives {SM id, scheduled, accumulator ready, done}
  * (globaltimer ns) of every task of the following runs; NULL switches it off.  tools/step_trace.py reads it.        */
 int ta3n_step_set_trace(void* handle_host, unsigned long long* trace_dev);
+/* development: the stand-alone row kernel of ta3n_step_run_phased writes 16 phase timestamps per task to dev_buf (NULL: off) */
+void ta3n_debug_set_tail_trace(unsigned long long* dev_buf);
 /* number of tasks / arrival counters of a built plan (diagnostics) */
 int ta3n_step_info(const void* handle_host, int* n_tasks, int* n_counters, int* n_gemm_tiles);
 

@@ -328,23 +328,20 @@ __device__ __forceinline__ void tc_epilogue(const TileCtx& ctx, const int m0, co
     if (m < e.M && nb < e.N) {
       float* orow = obase + (size_t)m * ldo + nb;
       const int nvalid = min(32, e.N - nb);
-      if (mode == TILE_OWNER) {      // raw partial sums of the other splits, fixed order, straight from L2
-        for (int sp = 0; sp < e.ksplit - 1; ++sp) {
-          const float* pr = e.partial + (size_t)sp * e.M * e.N + (size_t)m * e.N + nb;
-          if (nvalid >= 32 && (reinterpret_cast<uintptr_t>(pr) & 15u) == 0) {
+      if (mode == TILE_OWNER) {      // raw partial sums of the other splits, two in flight, added in split order
+        float pr[2][32];
+        load_row32(e.partial + (size_t)m * e.N + nb, nvalid, pr[0]);
+        if (e.ksplit > 2) load_row32(e.partial + (size_t)e.M * e.N + (size_t)m * e.N + nb, nvalid, pr[1]);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 t = __ldcg(reinterpret_cast<const float4*>(pr + j));
-              v[j] += t.x;
-              v[j + 1] += t.y;
-              v[j + 2] += t.z;
-              v[j + 3] += t.w;
-            }
-          } else {
+        for (int j = 0; j < 32; ++j) v[j] += pr[0][j];
+        if (e.ksplit > 2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) v[j] += __ldcg(pr + j);
-          }
+          for (int j = 0; j < 32; ++j) v[j] += pr[1][j];
+        }
+        for (int sp = 2; sp < e.ksplit - 1; ++sp) {
+          load_row32(e.partial + (size_t)sp * e.M * e.N + (size_t)m * e.N + nb, nvalid, pr[0]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += pr[0][j];
         }
       }
       if (!split_out) {
@@ -362,6 +359,196 @@ __device__ __forceinline__ void tc_epilogue(const TileCtx& ctx, const int m0, co
     }
   }
   tc_fence_before();                    // TMEM reads ordered before whatever lets the next MMA reuse the buffer
+}
+
+// ---- coalesced epilogue (step kernel) -------------------------------------------------------------------
+// The epilogue above gives every lane one accumulator ROW: each of its memory instructions touches 32 different
+// 128 B lines, i.e. 32 LSU cycles per instruction -- 2 us per plain tile and 20-45 us for the tiles whose epilogue
+// reads several auxiliary operands (measured: step trace, relation-discriminator data gradient).  Here a warp stages
+// its 32 x 32 accumulator chunk in shared memory ([32][36] floats, conflict-free for the 16 B accesses of both
+// passes) and re-reads it with lanes along the COLUMNS: lane = (row quarter rq, column quad cq), every global access
+// is a 16 B piece of a 128 B row segment, 4 rows per instruction.  Auxiliary operands of four rows are requested
+// together before the first is used.
+constexpr int TC_STAGE_LD = 36;
+constexpr int TC_EPI_STAGE_FLOATS = 32 * TC_STAGE_LD;      // per epilogue warp
+
+struct Quad {
+  float4 x[4];      // four rows (it*4 + rq for it in a batch of 4 ... see below), 4 consecutive columns each
+};
+
+template <int F>
+__device__ __forceinline__ void epi_apply_quads(const Group& g, const int mode, const int (&rows)[4],
+                                                const bool (&row_ok)[4], const int n, const bool full4,
+                                                float4 (&v)[4]) {
+  const int f = (F >= 0) ? F : g.flags;
+  auto ld4 = [&](const float* p) -> float4 {
+    if (full4 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) return __ldcg(reinterpret_cast<const float4*>(p));
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n + 0 < g.N) r.x = __ldcg(p);
+    if (n + 1 < g.N) r.y = __ldcg(p + 1);
+    if (n + 2 < g.N) r.z = __ldcg(p + 2);
+    if (n + 3 < g.N) r.w = __ldcg(p + 3);
+    return r;
+  };
+  // ---- every load of the batch first ----
+  float4 pr0[4], pr1[4], a_add[4], a_gate[4], a_c[4];
+  float rs[4];
+  float4 a_bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t plane = (size_t)g.M * g.N;
+  if (mode == TILE_OWNER) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (row_ok[u]) {
+        pr0[u] = ld4(g.partial + (size_t)rows[u] * g.N + n);
+        if (g.ksplit > 2) pr1[u] = ld4(g.partial + plane + (size_t)rows[u] * g.N + n);
+      }
+  }
+  if (mode != TILE_PARTIAL) {
+    if (f & EPI_BIAS) a_bias = ld4(g.bias + n);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!row_ok[u]) continue;
+      const size_t m = (size_t)rows[u];
+      if (f & EPI_ADDROW) {
+        rs[u] = g.rowscale ? __ldcg(g.rowscale + m * g.rs_stride) + g.rs_bias : 1.0f;
+        a_add[u] = ld4(g.add + m * g.ldadd + n);
+      }
+      if (f & (EPI_GATE | EPI_DPRE)) a_gate[u] = ld4(g.gate + m * g.ldgate + n);
+      if (f & EPI_ACCUM) a_c[u] = ld4(g.C + m * g.ldc + n);
+    }
+  }
+  // ---- arithmetic ----
+  if (mode == TILE_OWNER) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (row_ok[u]) {
+        v[u].x += pr0[u].x; v[u].y += pr0[u].y; v[u].z += pr0[u].z; v[u].w += pr0[u].w;
+        if (g.ksplit > 2) { v[u].x += pr1[u].x; v[u].y += pr1[u].y; v[u].z += pr1[u].z; v[u].w += pr1[u].w; }
+        for (int sp = 2; sp < g.ksplit - 1; ++sp) {
+          const float4 t = ld4(g.partial + (size_t)sp * plane + (size_t)rows[u] * g.N + n);
+          v[u].x += t.x; v[u].y += t.y; v[u].z += t.z; v[u].w += t.w;
+        }
+      }
+  }
+  if (mode == TILE_PARTIAL) return;
+  const float alpha = g.alpha_dev ? g.alpha * __ldg(g.alpha_dev) : g.alpha;
+  const uint64_t step = (f & EPI_DROP_RNG) ? (g.step_dev ? *g.step_dev : 0ull) : 0ull;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (!row_ok[u]) continue;
+    const size_t m = (size_t)rows[u];
+    float e[4] = {v[u].x * alpha, v[u].y * alpha, v[u].z * alpha, v[u].w * alpha};
+    if (f & EPI_BIAS) { e[0] += a_bias.x; e[1] += a_bias.y; e[2] += a_bias.z; e[3] += a_bias.w; }
+    if (f & EPI_RELU) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) e[i] = fmaxf(e[i], 0.f);
+    }
+    if (f & EPI_DROP_MASK) {
+      const uint8_t* k = g.keep + m * g.ldkeep + n;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (n + i < g.N) e[i] = k[i] ? e[i] * g.drop_scale : 0.f;
+    }
+    if (f & EPI_DROP_RNG) {
+      const uint64_t base = g.rng_offset + m * (uint64_t)g.N + (uint64_t)n;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) e[i] = rng_keep(g.seed, step, base + i, g.drop_p) ? e[i] * g.drop_scale : 0.f;
+    }
+    if (f & EPI_ADDROW) {
+      e[0] = fmaf(rs[u], a_add[u].x, e[0]); e[1] = fmaf(rs[u], a_add[u].y, e[1]);
+      e[2] = fmaf(rs[u], a_add[u].z, e[2]); e[3] = fmaf(rs[u], a_add[u].w, e[3]);
+    }
+    if (f & EPI_GATE) {
+      e[0] = a_gate[u].x > 0.f ? e[0] : 0.f; e[1] = a_gate[u].y > 0.f ? e[1] : 0.f;
+      e[2] = a_gate[u].z > 0.f ? e[2] : 0.f; e[3] = a_gate[u].w > 0.f ? e[3] : 0.f;
+    }
+    if (f & EPI_ACCUM) { e[0] += a_c[u].x; e[1] += a_c[u].y; e[2] += a_c[u].z; e[3] += a_c[u].w; }
+    if (f & EPI_DPRE) {
+      e[0] = a_gate[u].x > 0.f ? e[0] * g.drop_scale : 0.f; e[1] = a_gate[u].y > 0.f ? e[1] * g.drop_scale : 0.f;
+      e[2] = a_gate[u].z > 0.f ? e[2] * g.drop_scale : 0.f; e[3] = a_gate[u].w > 0.f ? e[3] * g.drop_scale : 0.f;
+    }
+    v[u] = make_float4(e[0], e[1], e[2], e[3]);
+  }
+}
+
+template <int kEpiWarps>
+__device__ __forceinline__ void tc_epilogue_coalesced(const TileCtx& ctx, const int m0, const int n0, const int split,
+                                                      const int n_iter, const int mode, const uint32_t tmem_base,
+                                                      const int acc, const int ew, float* __restrict__ stage) {
+  const int lane = threadIdx.x & 31;
+  const int lq = (ew + 2) & 3;          // TMEM lane quarter this warp may access
+  const Group e = ctx.g;                // register copy
+  const bool split_out = mode == TILE_PARTIAL;
+  float* const obase = split_out ? e.partial + (size_t)split * e.M * e.N : e.C;
+  const int ldo = split_out ? e.N : e.ldc;
+  constexpr int kColChunks = (TC_BN / 32) * 4 / kEpiWarps;
+  const int c0 = (ew / 4) * kColChunks;
+  const int rq = lane >> 3, cq = lane & 7;
+#pragma unroll 1
+  for (int c = c0; c < c0 + kColChunks; ++c) {
+    {  // accumulator chunk -> registers (lane = row) -> shared memory
+      float v[32];
+      if (n_iter > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      __syncwarp();                     // the previous chunk's readers are done with the staging tile
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stage + lane * TC_STAGE_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
+    }
+    const int nb = n0 + c * 32;
+    const int n = nb + cq * 4;
+    if (nb >= e.N) continue;
+    const bool full4 = n + 3 < e.N;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {                 // 2 batches of 4 x (4 rows per instruction) = 32 rows
+      int rows[4];
+      bool ok[4];
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = (half * 4 + u) * 4 + rq;            // row of the chunk
+        rows[u] = m0 + lq * 32 + r;
+        ok[u] = rows[u] < e.M && n < e.N;
+        q[u] = *reinterpret_cast<const float4*>(stage + r * TC_STAGE_LD + cq * 4);
+      }
+      TA3N_EPI_DISPATCH(e.flags, { epi_apply_quads<EPI_F>(e, mode, rows, ok, n, full4, q); })
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        float* o = obase + (size_t)rows[u] * ldo + n;
+        if (full4 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+          *reinterpret_cast<float4*>(o) = q[u];
+        } else {
+          if (n + 0 < e.N) o[0] = q[u].x;
+          if (n + 1 < e.N) o[1] = q[u].y;
+          if (n + 2 < e.N) o[2] = q[u].z;
+          if (n + 3 < e.N) o[3] = q[u].w;
+        }
+      }
+      if (!split_out && (e.flags & EPI_MULTI)) {            // dZ planes: the gates of all planes of the batch in flight
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          if (p >= e.n_multi) break;
+          float4 gt[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (ok[u]) gt[u] = __ldcg(reinterpret_cast<const float4*>(e.multi_gate[p] + (size_t)rows[u] * e.ldmulti + n));
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (ok[u])
+              *reinterpret_cast<float4*>(e.multi_out[p] + (size_t)rows[u] * e.ldmulti + n) =
+                  make_float4(gt[u].x > 0.f ? q[u].x : 0.f, gt[u].y > 0.f ? q[u].y : 0.f, gt[u].z > 0.f ? q[u].z : 0.f,
+                              gt[u].w > 0.f ? q[u].w : 0.f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
 }
 
 // chunk range [c_begin, c_begin + n_iter) of split `split` of the group staged in ctx

@@ -27,6 +27,7 @@ constexpr int kStepThreads = 352;     // warp 0 TMA producer, 1 MMA issuer, 2..9
 constexpr int kStepStages = 5;        // operand ring: 5 x 32 KB
 constexpr int kStepSlots = 3;         // tasks a CTA holds at once (scheduled ahead of the one being finished)
 constexpr int kStepScratchBytes = 40 * 1024;      // shared memory of the row tasks (outside the operand ring)
+static_assert(8 * TC_EPI_STAGE_FLOATS * 4 <= kStepScratchBytes, "epilogue staging tiles live in the scratch area");
 constexpr int kStepSmemBytes = kStepStages * TC_STAGE_BYTES + kStepScratchBytes + 1024;
 constexpr int kStepTmemCols = 256;    // two 128-column accumulators
 
@@ -238,7 +239,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
           tc_fence_after();
         }
         if (hd.trace && rt == 0) t_acc = global_ns();
-        tc_epilogue<8>(sl.ctx, sl.task.m0, sl.task.n0, sl.task.split, sl.n_iter, sl.task.mode, tmem_base, acc, ew);
+        tc_epilogue_coalesced<8>(sl.ctx, sl.task.m0, sl.task.n0, sl.task.split, sl.n_iter, sl.task.mode, tmem_base, acc,
+                                 ew, scratch + ew * TC_EPI_STAGE_FLOATS);
         if (sl.n_iter > 0) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&sh.tmem_empty_bar[acc]);      // this warp's TMEM reads are done
@@ -261,10 +263,10 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
       const int sig = sl.task.signal, sig2 = sl.task.signal2, index = sl.index;
       const unsigned long long tag = ((unsigned long long)type << 16) | ((unsigned long long)(unsigned)sl.task.group << 24) |
                                      ((unsigned long long)sl.task.mode << 48) | ((unsigned long long)(unsigned)sl.n_iter << 52);
-      __threadfence();
-      row_sync();
+      row_sync();                        // every warp's stores are issued (CTA-scope order) ...
       if (rt == 0) {
         if (sig >= 0 || sig2 >= 0) {
+          __threadfence();               // ... one cumulative gpu-scope fence publishes them with the release below
           fence_proxy_async_all();
           if (sig >= 0) red_release(hd.counters + sig, 1);
           if (sig2 >= 0) red_release(hd.counters + sig2, 1);

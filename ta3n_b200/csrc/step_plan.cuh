@@ -664,7 +664,10 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
     append(v);
   }
   // ================= S2: frame-discriminator hidden + TRN relations =================
+  // the longest relation tiles (scale 0: 80 K slabs at cfg2) set this stage's critical path: halve them
   std::vector<int> ones2(P.g2.groups.size(), 1);
+  if (step_split_enabled())
+    for (size_t gi = 1; gi < P.g2.groups.size(); ++gi) ones2[gi] = std::min(4, std::max(1, (step_slabs(P.g2, P.g2.groups[gi]) + 39) / 40));
   const int g2 = add_groups(P.g2, ones2);
   if (g2 < 0) return TA3N_ERR_UNSUPPORTED;
   const int c2f = counters(nfb);                        // hid_f row blocks

@@ -69,6 +69,7 @@ struct TailArgs {
   float* G;                          // [M, H]     d loss / d feat_video
   float* dHid;                       // [R, M, H]
   float* dHf;                        // [M*T, F]
+  unsigned long long* dbg;           // optional [tasks][16] phase timestamps (development)
 };
 
 // dot of a row held in shared memory (len floats) with a global row, distributed over a warp
@@ -92,10 +93,63 @@ __host__ __device__ constexpr int tail_smem_floats(int vp, int R, int H, int T, 
 }
 
 // vp = videos the shared-memory layout is sized for (nv <= vp <= kTailVideos)
-__device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const int nv, const int vp, float* sm,
-                                       const int tid) {
+// NOTE: force-inlined, and every scalar / pointer of the argument block is copied into a local first.  As an
+// out-of-line function taking `const TailArgs&`, each field access was a GENERIC load (the block lives in parameter
+// or shared memory) that the compiler had to repeat after every store (possible aliasing): the task took 95 us.
+struct TailLocal {      // the pointer / scalar fields of TailArgs, as restrict-qualified locals
+  const float* __restrict__ hid_f;
+  const float* __restrict__ act;
+  const float* __restrict__ hid_r;
+  const float* __restrict__ W2f;
+  const float* __restrict__ b2f;
+  const float* __restrict__ Wc;
+  const float* __restrict__ bc;
+  const float* __restrict__ W1v;
+  const float* __restrict__ b1v;
+  const float* __restrict__ W2v;
+  const float* __restrict__ b2v;
+  const float* __restrict__ class_weight;
+  const long long* __restrict__ labels;
+  float* __restrict__ pred_frame;
+  float* __restrict__ feat_rel;
+  float* __restrict__ pred_rel;
+  float* __restrict__ attn;
+  float* __restrict__ feat_video;
+  float* __restrict__ dropped;
+  float* __restrict__ pred_video;
+  float* __restrict__ hid_v;
+  float* __restrict__ pred_dom;
+  float* __restrict__ row_loss;
+  float* __restrict__ g_video;
+  float* __restrict__ g_dom;
+  float* __restrict__ g_frame;
+  float* __restrict__ Pt;
+  float* __restrict__ dHv;
+  float* __restrict__ G;
+  float* __restrict__ dHid;
+  float* __restrict__ dHf;
+  DropArgs drop_v;
+  int use_attn, loss_flags, Bs;
+  float gamma, dom_w0, dom_w1;
+};
+
+__device__ __forceinline__ void tail_task(const TailArgs& args, const int v0, const int nv, const int vp,
+                                          float* __restrict__ sm, const int tid) {
   const int lane = tid & 31, warp = tid >> 5;
-  const int M = a.M, T = a.T, R = a.R, H = a.H, F = a.F, C = a.C;
+  const int M = args.M, T = args.T, R = args.R, H = args.H, F = args.F, C = args.C;
+  TailLocal a;
+  a.hid_f = args.hid_f; a.act = args.act; a.hid_r = args.hid_r; a.W2f = args.W2f; a.b2f = args.b2f; a.Wc = args.Wc;
+  a.bc = args.bc; a.W1v = args.W1v; a.b1v = args.b1v; a.W2v = args.W2v; a.b2v = args.b2v;
+  a.class_weight = args.class_weight; a.labels = args.labels; a.pred_frame = args.pred_frame;
+  a.feat_rel = args.feat_rel; a.pred_rel = args.pred_rel; a.attn = args.attn; a.feat_video = args.feat_video;
+  a.dropped = args.dropped; a.pred_video = args.pred_video; a.hid_v = args.hid_v; a.pred_dom = args.pred_dom;
+  a.row_loss = args.row_loss; a.g_video = args.g_video; a.g_dom = args.g_dom; a.g_frame = args.g_frame; a.Pt = args.Pt;
+  a.dHv = args.dHv; a.G = args.G; a.dHid = args.dHid; a.dHf = args.dHf; a.drop_v = args.drop_v;
+  a.use_attn = args.use_attn; a.loss_flags = args.loss_flags; a.Bs = args.Bs; a.gamma = args.gamma;
+  a.dom_w0 = args.dom_w0; a.dom_w1 = args.dom_w1;
+  const int vs_in = args.valid_rows ? args.valid_rows[0] : args.Bs;
+  const int vt_in = args.valid_rows ? args.valid_rows[1] : args.M - args.Bs;
+  unsigned long long* const dbg = args.dbg;
   constexpr int V = kTailVideos;                  // register arrays; smem strides use vp
   float* s_fr = sm;                               // [vp][R][H]  feat_rel
   float* s_drop = s_fr + vp * R * H;              // [vp][H]     dropped features
@@ -112,7 +166,18 @@ __device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const in
   float* s_gv = s_gr + vp * 2 * R;
   float* s_gd = s_gv + vp * C;
   float* s_w = s_gd + vp * 2;                     // [vp][R]     attention weight + 1
-  const float beta1 = a.beta_dev ? __ldg(a.beta_dev + 1) : 0.f;
+  const float beta1 = args.beta_dev ? __ldg(args.beta_dev + 1) : 0.f;
+  int dbg_i = 0;
+#define TAIL_MARK()                                                                          \
+  do {                                                                                       \
+    if (dbg && tid == 0) {                                                                   \
+      unsigned long long t_;                                                                 \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                  \
+      dbg[(size_t)(v0 / kTailVideos) * 16 + dbg_i] = t_;                                     \
+    }                                                                                        \
+    ++dbg_i;                                                                                 \
+  } while (0)
+  TAIL_MARK();
 
   // ---- phase 1: frame logits, relation sums + relation logits ---------------------------------------
   for (int it = warp; it < nv * T; it += 8) {               // warp per frame row: 2 dots of length F
@@ -141,7 +206,7 @@ __device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const in
     for (int e = tid; e < nv * R * H4; e += kRowThreads) {
       const int h4 = e % H4, vi = e / H4, i = vi % R, v = vi / R;
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = a.map.rel_begin[i]; q < a.map.rel_begin[i + 1]; ++q) {
+      for (int q = args.map.rel_begin[i]; q < args.map.rel_begin[i + 1]; ++q) {
         const float4 x = __ldcg(reinterpret_cast<const float4*>(a.act + q * plane + (size_t)(v0 + v) * H) + h4);
         s.x += x.x;
         s.y += x.y;
@@ -155,7 +220,7 @@ __device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const in
   for (int it = warp; it < nv * R; it += 8) {               // relation logits: hid_r[i][v,:] . W2r_i  (models.py:479)
     const int v = it / R, i = it - v * R;
     const float* hr = a.hid_r + ((size_t)i * M + (v0 + v)) * H;
-    const float* w0 = a.W2r.p[i];
+    const float* w0 = args.W2r.p[i];
     float s0 = 0.f, s1 = 0.f;
     for (int k = lane * 4; k < H; k += 128) {
       const float4 h = __ldcg(reinterpret_cast<const float4*>(hr + k));
@@ -164,8 +229,8 @@ __device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const in
       s0 = fmaf(h.x, x0.x, fmaf(h.y, x0.y, fmaf(h.z, x0.z, fmaf(h.w, x0.w, s0))));
       s1 = fmaf(h.x, x1.x, fmaf(h.y, x1.y, fmaf(h.z, x1.z, fmaf(h.w, x1.w, s1))));
     }
-    s0 = warp_sum(s0) + __ldg(a.b2r.p[i]);
-    s1 = warp_sum(s1) + __ldg(a.b2r.p[i] + 1);
+    s0 = warp_sum(s0) + __ldg(args.b2r.p[i]);
+    s1 = warp_sum(s1) + __ldg(args.b2r.p[i] + 1);
     if (lane == 0) {
       const size_t o = (size_t)(v0 + v) * R + i;
       s_pr[(v * R + i) * 2] = s0;
@@ -178,6 +243,7 @@ __device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const in
     }
   }
   row_sync();
+  TAIL_MARK();
   // ---- phase 2: attentive pooling + dropout                         models.py:379-388, 651-652, 679-680 ----
   for (int e = tid; e < nv * H; e += kRowThreads) {
     const int v = e / H, h = e - v * H;
@@ -193,40 +259,102 @@ __device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const in
   if (!a.use_attn)                                          // models.py:647 placeholder output
     for (int e = tid; e < nv * R; e += kRowThreads) a.attn[(size_t)v0 * R + e] = s_fr[e * H];
   row_sync();
+  TAIL_MARK();
   // ---- phase 3: classifier logits, video-discriminator hidden layer        models.py:681-687, 464-468 ----
-  for (int it = warp; it < nv * C; it += 8) {
-    const int v = it / C, c = it - v * C;
-    const float s = warp_dot_sg(s_drop + v * H, a.Wc + (size_t)c * H, H, lane) + __ldg(a.bc + c);
-    if (lane == 0) {
-      s_pv[v * C + c] = s;
-      a.pred_video[(size_t)(v0 + v) * C + c] = s;
+  // Both are latency-bound walks over weights in L2: every warp issues the loads of a whole batch of rows before it
+  // touches the first one (8 rows = 16 independent 16 B loads per lane in flight).
+  {
+    const int n_items = nv * C;
+    for (int base = warp; base < n_items; base += 8 * 8) {
+      float4 w[8][2];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int it = base + 8 * u;
+        const int c = it < n_items ? it % C : 0;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const int k = lane * 4 + 128 * kk;
+          w[u][kk] = (it < n_items && k < H) ? __ldg(reinterpret_cast<const float4*>(a.Wc + (size_t)c * H + k))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int it = base + 8 * u;
+        if (it >= n_items) break;
+        const int v = it / C, c = it - v * C;
+        float acc = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const int k = lane * 4 + 128 * kk;
+          if (k < H) {
+            const float4 d = *reinterpret_cast<const float4*>(s_drop + v * H + k);
+            acc = fmaf(d.x, w[u][kk].x, fmaf(d.y, w[u][kk].y, fmaf(d.z, w[u][kk].z, fmaf(d.w, w[u][kk].w, acc))));
+          }
+        }
+        for (int k = lane * 4 + 256; k < H; k += 128) {          // H > 256: the rest of the row, plainly
+          const float4 d = *reinterpret_cast<const float4*>(s_drop + v * H + k);
+          const float4 x = __ldg(reinterpret_cast<const float4*>(a.Wc + (size_t)c * H + k));
+          acc = fmaf(d.x, x.x, fmaf(d.y, x.y, fmaf(d.z, x.z, fmaf(d.w, x.w, acc))));
+        }
+        const float sres = warp_sum(acc) + __ldg(a.bc + c);
+        if (lane == 0) {
+          s_pv[v * C + c] = sres;
+          a.pred_video[(size_t)(v0 + v) * C + c] = sres;
+        }
+      }
     }
   }
-  for (int h = warp; h < H; h += 8) {                       // warp per hidden unit, all videos of the task at once
-    const float* wr = a.W1v + (size_t)h * H;
-    float acc[V];
+  for (int h0 = warp * (H / 8); h0 < (warp + 1) * (H / 8); h0 += 8) {     // warp w owns hidden units [w H/8, (w+1) H/8)
+    float4 w[8][2];
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = 0.f;
-    for (int k = lane * 4; k < H; k += 128) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(wr + k));
+    for (int u = 0; u < 8; ++u)
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (v < nv) {
-          const float4 d = *reinterpret_cast<const float4*>(s_drop + v * H + k);
-          acc[v] = fmaf(d.x, w.x, fmaf(d.y, w.y, fmaf(d.z, w.z, fmaf(d.w, w.w, acc[v]))));
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = lane * 4 + 128 * kk;
+        w[u][kk] = k < H ? __ldg(reinterpret_cast<const float4*>(a.W1v + (size_t)(h0 + u) * H + k))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int h = h0 + u;
+      float acc[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = lane * 4 + 128 * kk;
+        if (k < H) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            if (v < nv) {
+              const float4 d = *reinterpret_cast<const float4*>(s_drop + v * H + k);
+              acc[v] = fmaf(d.x, w[u][kk].x, fmaf(d.y, w[u][kk].y, fmaf(d.z, w[u][kk].z, fmaf(d.w, w[u][kk].w, acc[v]))));
+            }
         }
-    }
-    const float b = __ldg(a.b1v + h);
+      }
+      for (int k = lane * 4 + 256; k < H; k += 128) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(a.W1v + (size_t)h * H + k));
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const float s = fmaxf(warp_sum(acc[v]) + b, 0.f);
-      if (lane == 0 && v < nv) {
-        s_hv[v * H + h] = s;
-        a.hid_v[(size_t)(v0 + v) * H + h] = s;
+        for (int v = 0; v < V; ++v)
+          if (v < nv) {
+            const float4 d = *reinterpret_cast<const float4*>(s_drop + v * H + k);
+            acc[v] = fmaf(d.x, x.x, fmaf(d.y, x.y, fmaf(d.z, x.z, fmaf(d.w, x.w, acc[v]))));
+          }
+      }
+      const float b = __ldg(a.b1v + h);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float sres = fmaxf(warp_sum(acc[v]) + b, 0.f);
+        if (lane == 0 && v < nv) {
+          s_hv[v * H + h] = sres;
+          a.hid_v[(size_t)(v0 + v) * H + h] = sres;
+        }
       }
     }
   }
   row_sync();
+  TAIL_MARK();
   // ---- phase 4: video-domain logits                                              models.py:469-470 ----
   for (int it = warp; it < nv * 2; it += 8) {
     const int v = it >> 1, j = it & 1;
@@ -237,11 +365,12 @@ __device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const in
     }
   }
   row_sync();
+  TAIL_MARK();
   // ---- phase 5: loss heads (one warp per video)          main.py:446, 508-538, 559-562; loss.py:15-25 ----
   {
     const int Bs = a.Bs;
-    const int vs = a.valid_rows ? min(a.valid_rows[0], Bs) : Bs;
-    const int vt = a.valid_rows ? min(a.valid_rows[1], M - Bs) : M - Bs;
+    const int vs = min(vs_in, Bs);
+    const int vt = min(vt_in, M - Bs);
     // normalisers of the (weighted) means: CrossEntropyLoss(weight=w) divides by the sum of the weights of the rows
     float n_cls = (float)max(vs, 1);
     if (a.class_weight) {                                   // main.py:160-163, 204: sum_m w[y_m] over the real source rows
@@ -338,6 +467,7 @@ __device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const in
     }
   }
   row_sync();
+  TAIL_MARK();
   // the head gradients are operands of the column sums (skinny weight gradients and bias gradients)
   for (int e = tid; e < nv * C; e += kRowThreads) a.g_video[(size_t)v0 * C + e] = s_gv[e];
   for (int e = tid; e < nv * 2; e += kRowThreads) a.g_dom[(size_t)v0 * 2 + e] = s_gd[e];
@@ -350,36 +480,80 @@ __device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const in
     a.dHv[(size_t)(v0 + v) * H + h] = s;
   }
   row_sync();
+  TAIL_MARK();
   // ---- phase 7: G = ((g_video Wc) - beta1 * (dHv W1v)) * keep/(1-p)      (disc dgrad + video_head_bwd) ----
-  for (int k = tid; k < H; k += kRowThreads) {              // thread per feature: W1v[h, k] is coalesced over k
-    float acc[V];
+  // d[v, k] = sum_h dHv[v, h] W1v[h, k]: lane = (kq, hg) -- 8 groups of 4 consecutive k per warp, the 4 lanes of a group
+  // split the h range, 16 independent 16 B loads in flight per lane, then two shuffles fold the h quarters.
+  for (int kbase = 0; kbase < H; kbase += 256) {
+    const int hg = lane & 3, kq = warp * 8 + (lane >> 2);
+    const int k = kbase + kq * 4;
+    float4 acc[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = 0.f;
-    for (int h = 0; h < H; ++h) {
-      const float w = __ldg(a.W1v + (size_t)h * H + k);
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int hq = H / 4;                                  // h range of this lane: [hg hq, (hg + 1) hq)
+    if (k < H) {
+      for (int hb = hg * hq; hb < (hg + 1) * hq; hb += 16) {
+        float4 w[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(a.W1v + (size_t)(hb + u) * H + k));
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            if (v < nv) {
+              const float dh = s_dhv[v * H + hb + u];
+              acc[v].x = fmaf(dh, w[u].x, acc[v].x);
+              acc[v].y = fmaf(dh, w[u].y, acc[v].y);
+              acc[v].z = fmaf(dh, w[u].z, acc[v].z);
+              acc[v].w = fmaf(dh, w[u].w, acc[v].w);
+            }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {                           // fold the four h quarters (lanes hg = 0..3 of the group)
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
+        acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+        acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
+        acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+      }
+    }
+    if (hg == 0 && k < H) {
 #pragma unroll
       for (int v = 0; v < V; ++v)
-        if (v < nv) acc[v] = fmaf(s_dhv[v * H + h], w, acc[v]);
+        if (v < nv) *reinterpret_cast<float4*>(s_fv + v * H + k) = acc[v];      // s_fv is free after phase 2
     }
+  }
+  row_sync();
+  TAIL_MARK();
+  for (int k = tid; k < H; k += kRowThreads) {              // thread per feature: classifier part, dropout, store
     float cls[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) cls[v] = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float w = __ldg(a.Wc + (size_t)c * H + k);
+    for (int c0 = 0; c0 < C; c0 += 16) {
+      float w[16];
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (v < nv) cls[v] = fmaf(s_gv[v * C + c], w, cls[v]);
+      for (int u = 0; u < 16; ++u) w[u] = (c0 + u < C) ? __ldg(a.Wc + (size_t)(c0 + u) * H + k) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (c0 + u < C) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            if (v < nv) cls[v] = fmaf(s_gv[v * C + c0 + u], w[u], cls[v]);
+        }
     }
 #pragma unroll
     for (int v = 0; v < V; ++v)
       if (v < nv) {
         const size_t ge = (size_t)(v0 + v) * H + k;
-        const float g = (cls[v] - beta1 * acc[v]) * drop_factor(a.drop_v, ge);
+        const float g = (cls[v] - beta1 * s_fv[v * H + k]) * drop_factor(a.drop_v, ge);
         s_G[v * H + k] = g;
         a.G[ge] = g;
       }
   }
   row_sync();
+  TAIL_MARK();
   // ---- phase 8: attention gradient, relation-discriminator hidden gradient, frame-discriminator hidden gradient
   for (int it = warp; it < nv * R; it += 8) {               // relattn_bwd_pre
     const int v = it / R, i = it - v * R;
@@ -399,7 +573,7 @@ __device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const in
       a.Pt[o * 2] = pt0;
       a.Pt[o * 2 + 1] = pt1;
     }
-    const float* w0 = a.W2r.p[i];
+    const float* w0 = args.W2r.p[i];
     const float* hr = a.hid_r + ((size_t)i * M + (v0 + v)) * H;
     float* dh = a.dHid + ((size_t)i * M + (v0 + v)) * H;
     for (int k = lane * 4; k < H; k += 128) {
@@ -432,6 +606,8 @@ __device__ __noinline__ void tail_task(const TailArgs& a, const int v0, const in
       *reinterpret_cast<float4*>(dh + k) = d;
     }
   }
+  TAIL_MARK();
+#undef TAIL_MARK
 }
 
 // ---- column sums as tasks --------------------------------------------------------------------------------
@@ -526,8 +702,9 @@ __device__ __forceinline__ void colsum_part_body(const WColsumJob& j, float4 (*r
   }
 }
 
-__device__ __noinline__ void colsum_part_task(const WColsumJob& j, float* sm, const int cb, const int split,
-                                              const int tid) {
+__device__ __forceinline__ void colsum_part_task(const WColsumJob& job_in, float* __restrict__ sm, const int cb,
+                                                 const int split, const int tid) {
+  const WColsumJob j = job_in;      // register copy: no generic reloads behind the stores
   float4(*red)[33] = reinterpret_cast<float4(*)[33]>(sm);
   const int lane = tid & 31, warp = tid >> 5;
   if (cb * 128 >= j.N || split >= j.nsplit) return;
@@ -551,7 +728,8 @@ __device__ __noinline__ void colsum_part_task(const WColsumJob& j, float* sm, co
 }
 
 // out[k, n] = sum_split partial[split, k, n] in split order (the whole job: N2*N outputs, 256 threads)
-__device__ __noinline__ void colsum_reduce_task(const WColsumJob& j, const int tid) {
+__device__ __forceinline__ void colsum_reduce_task(const WColsumJob& job_in, const int tid) {
+  const WColsumJob j = job_in;
   const int total = j.N2 * j.N;
   const int nsplit = j.nsplit;
   for (int e = tid; e < total; e += kRowThreads) {

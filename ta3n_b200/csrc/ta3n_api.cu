@@ -822,6 +822,10 @@ int ta3n_counter_inc(uint64_t* counter, ta3n_stream_t stream) {
 namespace {
 
 constexpr int kStepMagic = 0x7A3B5700;
+std::atomic<unsigned long long*>& tail_debug_ptr() {       // development: phase timestamps of the row task
+  static std::atomic<unsigned long long*> p{nullptr};
+  return p;
+}
 
 int step_kernel_config(int* sm_count) {          // per-device opt-in of the large dynamic shared memory
   std::lock_guard<std::mutex> lock(device_mu());
@@ -847,9 +851,12 @@ size_t ta3n_step_workspace_bytes(const ta3n_step_desc* desc) {
   return P.scratch_bytes + Arena::round(B.partial_floats * sizeof(float)) + 4096;
 }
 
+void ta3n_debug_set_tail_trace(unsigned long long* dev_buf) { tail_debug_ptr().store(dev_buf); }
+
 int ta3n_step_run_phased(const ta3n_step_desc* desc, ta3n_stream_t stream) {
   StepProgram P;
   TA3N_TRY(build_step_program(desc, &P));
+  P.tail.dbg = tail_debug_ptr().load();
   cudaStream_t st = S(stream);
   int sm_count = 148;
   TA3N_TRY(step_kernel_config(&sm_count));
