@@ -224,11 +224,12 @@ int ta3n_counter_inc(uint64_t* counter, ta3n_stream_t stream);
  *
  * Everything is described once by a ta3n_step_desc (device pointers unless noted).  Two executors give
  * bit-identical results:
- *   ta3n_step_run_phased : one launch per dependency level -- 6 grouped tcgen05 GEMM launches, 1 fused per-video
- *                          row kernel, 2 column-sum launches (9 launches; the round-1 sequence had 25);
- *   ta3n_step_build + ta3n_step_run : the same work as ONE persistent kernel (one CTA per SM) that pulls GEMM
- *                          tiles / row tasks / column-sum tasks from a queue and synchronises them through arrival
- *                          counters in global memory (csrc/step_kernel.cuh) -- plus one memset node for the counters.
+ *   ta3n_step_run_phased : one launch per dependency level -- 8 grouped GEMM launches (engine as selected), 4 row
+ *                          kernels (frame rows; per video: relation pooling, loss heads, relation backward) and
+ *                          2 column-sum launches (14 launches; the round-1 sequence had 25);
+ *   ta3n_step_build + ta3n_step_run : the same work as ONE persistent kernel (one CTA per SM) whose CTAs claim
+ *                          READY GEMM tiles / row tasks / column-sum tasks from priority queues and synchronise
+ *                          through arrival counters in global memory (csrc/step_kernel.cuh) -- plus one memset node.
  * Both are CUDA-graph capturable (ta3n_step_build itself is not: it copies the task graph to the device).        */
 typedef struct {
   int Bs, Bt;                 /* source / target videos of the mini-batch (M = Bs + Bt rows, source first)         */
@@ -295,13 +296,12 @@ size_t ta3n_step_plan_bytes(const ta3n_step_desc* desc);
 int ta3n_step_build(const ta3n_step_desc* desc, void* plan_dev, size_t plan_bytes, void* handle_host);
 int ta3n_step_run(const void* handle_host, ta3n_stream_t stream);
 /* Host-only summary of the task graph of `desc` (counts per task type, arrival counters, K slabs, and the number of
- * waits that earlier tasks cannot satisfy -- must be 0: the deadlock-freedom invariant).  No CUDA call.            */
+ * tasks a simulated scheduler can never run -- must be 0: the dependency graph is acyclic and every awaited count is
+ * reached).  No CUDA call.                                                                                          */
 size_t ta3n_step_describe(const ta3n_step_desc* desc, char* buf, size_t buf_bytes);
 /* Optional per-task trace: trace_dev (device, n_tasks * 4 uint64) receives {SM id, scheduled, accumulator ready, done}
  * (globaltimer ns) of every task of the following runs; NULL switches it off.  tools/step_trace.py reads it.        */
 int ta3n_step_set_trace(void* handle_host, unsigned long long* trace_dev);
-/* development: the stand-alone row kernel of ta3n_step_run_phased writes 16 phase timestamps per task to dev_buf (NULL: off) */
-void ta3n_debug_set_tail_trace(unsigned long long* dev_buf);
 /* number of tasks / arrival counters of a built plan (diagnostics) */
 int ta3n_step_info(const void* handle_host, int* n_tasks, int* n_counters, int* n_gemm_tiles);
 

@@ -100,7 +100,6 @@ SIGNATURES = {
     "ta3n_step_run": (_I, [_VP, _VP]),
     "ta3n_step_describe": (_SZ, [C.POINTER(StepDesc), C.c_char_p, _SZ]),
     "ta3n_step_set_trace": (_I, [_VP, _VP]),
-    "ta3n_debug_set_tail_trace": (None, [_VP]),
     "ta3n_step_info": (_I, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ta3n_allreduce_flag_bytes": (_SZ, [_I]),
     "ta3n_allreduce_mean": (_I, [_PP, _VP, _PP, _VP, _I, _I, C.c_longlong, _VP]),

@@ -369,106 +369,20 @@ __device__ __forceinline__ void tc_epilogue(const TileCtx& ctx, const int m0, co
 // passes) and re-reads it with lanes along the COLUMNS: lane = (row quarter rq, column quad cq), every global access
 // is a 16 B piece of a 128 B row segment, 4 rows per instruction.  Auxiliary operands of four rows are requested
 // together before the first is used.
+// ONE body with run-time flags (uniform branches), not one copy per flag set: the nine specialised copies of the
+// first version made the step kernel 42 k instructions (680 KB), far beyond the instruction cache.  The step planner
+// guarantees what keeps it small: N % 4 == 0, every leading dimension % 4 == 0, every pointer 16-byte aligned (no
+// scalar tails), ksplit <= 4, and no auxiliary operand on a split group (the three aux registers sets are shared
+// between {partials} and {add, gate, accumulate}).
 constexpr int TC_STAGE_LD = 36;
 constexpr int TC_EPI_STAGE_FLOATS = 32 * TC_STAGE_LD;      // per epilogue warp
 
-struct Quad {
-  float4 x[4];      // four rows (it*4 + rq for it in a batch of 4 ... see below), 4 consecutive columns each
-};
-
-template <int F>
-__device__ __forceinline__ void epi_apply_quads(const Group& g, const int mode, const int (&rows)[4],
-                                                const bool (&row_ok)[4], const int n, const bool full4,
-                                                float4 (&v)[4]) {
-  const int f = (F >= 0) ? F : g.flags;
-  auto ld4 = [&](const float* p) -> float4 {
-    if (full4 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) return __ldcg(reinterpret_cast<const float4*>(p));
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n + 0 < g.N) r.x = __ldcg(p);
-    if (n + 1 < g.N) r.y = __ldcg(p + 1);
-    if (n + 2 < g.N) r.z = __ldcg(p + 2);
-    if (n + 3 < g.N) r.w = __ldcg(p + 3);
-    return r;
-  };
-  // ---- every load of the batch first ----
-  float4 pr0[4], pr1[4], a_add[4], a_gate[4], a_c[4];
-  float rs[4];
-  float4 a_bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  const size_t plane = (size_t)g.M * g.N;
-  if (mode == TILE_OWNER) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (row_ok[u]) {
-        pr0[u] = ld4(g.partial + (size_t)rows[u] * g.N + n);
-        if (g.ksplit > 2) pr1[u] = ld4(g.partial + plane + (size_t)rows[u] * g.N + n);
-      }
-  }
-  if (mode != TILE_PARTIAL) {
-    if (f & EPI_BIAS) a_bias = ld4(g.bias + n);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (!row_ok[u]) continue;
-      const size_t m = (size_t)rows[u];
-      if (f & EPI_ADDROW) {
-        rs[u] = g.rowscale ? __ldcg(g.rowscale + m * g.rs_stride) + g.rs_bias : 1.0f;
-        a_add[u] = ld4(g.add + m * g.ldadd + n);
-      }
-      if (f & (EPI_GATE | EPI_DPRE)) a_gate[u] = ld4(g.gate + m * g.ldgate + n);
-      if (f & EPI_ACCUM) a_c[u] = ld4(g.C + m * g.ldc + n);
-    }
-  }
-  // ---- arithmetic ----
-  if (mode == TILE_OWNER) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (row_ok[u]) {
-        v[u].x += pr0[u].x; v[u].y += pr0[u].y; v[u].z += pr0[u].z; v[u].w += pr0[u].w;
-        if (g.ksplit > 2) { v[u].x += pr1[u].x; v[u].y += pr1[u].y; v[u].z += pr1[u].z; v[u].w += pr1[u].w; }
-        for (int sp = 2; sp < g.ksplit - 1; ++sp) {
-          const float4 t = ld4(g.partial + (size_t)sp * plane + (size_t)rows[u] * g.N + n);
-          v[u].x += t.x; v[u].y += t.y; v[u].z += t.z; v[u].w += t.w;
-        }
-      }
-  }
-  if (mode == TILE_PARTIAL) return;
-  const float alpha = g.alpha_dev ? g.alpha * __ldg(g.alpha_dev) : g.alpha;
-  const uint64_t step = (f & EPI_DROP_RNG) ? (g.step_dev ? *g.step_dev : 0ull) : 0ull;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    if (!row_ok[u]) continue;
-    const size_t m = (size_t)rows[u];
-    float e[4] = {v[u].x * alpha, v[u].y * alpha, v[u].z * alpha, v[u].w * alpha};
-    if (f & EPI_BIAS) { e[0] += a_bias.x; e[1] += a_bias.y; e[2] += a_bias.z; e[3] += a_bias.w; }
-    if (f & EPI_RELU) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) e[i] = fmaxf(e[i], 0.f);
-    }
-    if (f & EPI_DROP_MASK) {
-      const uint8_t* k = g.keep + m * g.ldkeep + n;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (n + i < g.N) e[i] = k[i] ? e[i] * g.drop_scale : 0.f;
-    }
-    if (f & EPI_DROP_RNG) {
-      const uint64_t base = g.rng_offset + m * (uint64_t)g.N + (uint64_t)n;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) e[i] = rng_keep(g.seed, step, base + i, g.drop_p) ? e[i] * g.drop_scale : 0.f;
-    }
-    if (f & EPI_ADDROW) {
-      e[0] = fmaf(rs[u], a_add[u].x, e[0]); e[1] = fmaf(rs[u], a_add[u].y, e[1]);
-      e[2] = fmaf(rs[u], a_add[u].z, e[2]); e[3] = fmaf(rs[u], a_add[u].w, e[3]);
-    }
-    if (f & EPI_GATE) {
-      e[0] = a_gate[u].x > 0.f ? e[0] : 0.f; e[1] = a_gate[u].y > 0.f ? e[1] : 0.f;
-      e[2] = a_gate[u].z > 0.f ? e[2] : 0.f; e[3] = a_gate[u].w > 0.f ? e[3] : 0.f;
-    }
-    if (f & EPI_ACCUM) { e[0] += a_c[u].x; e[1] += a_c[u].y; e[2] += a_c[u].z; e[3] += a_c[u].w; }
-    if (f & EPI_DPRE) {
-      e[0] = a_gate[u].x > 0.f ? e[0] * g.drop_scale : 0.f; e[1] = a_gate[u].y > 0.f ? e[1] * g.drop_scale : 0.f;
-      e[2] = a_gate[u].z > 0.f ? e[2] * g.drop_scale : 0.f; e[3] = a_gate[u].w > 0.f ? e[3] * g.drop_scale : 0.f;
-    }
-    v[u] = make_float4(e[0], e[1], e[2], e[3]);
-  }
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void add4(float4& a, const float4& b) {
+  a.x += b.x;
+  a.y += b.y;
+  a.z += b.z;
+  a.w += b.w;
 }
 
 template <int kEpiWarps>
@@ -477,13 +391,21 @@ __device__ __forceinline__ void tc_epilogue_coalesced(const TileCtx& ctx, const 
                                                       const int acc, const int ew, float* __restrict__ stage) {
   const int lane = threadIdx.x & 31;
   const int lq = (ew + 2) & 3;          // TMEM lane quarter this warp may access
-  const Group e = ctx.g;                // register copy
+  const Group& e = ctx.g;               // shared memory (the task slot)
+  const int f = mode == TILE_PARTIAL ? 0 : e.flags;
+  const int M = e.M, N = e.N;
   const bool split_out = mode == TILE_PARTIAL;
-  float* const obase = split_out ? e.partial + (size_t)split * e.M * e.N : e.C;
-  const int ldo = split_out ? e.N : e.ldc;
+  const size_t plane = (size_t)M * N;
+  float* const obase = split_out ? e.partial + (size_t)split * plane : e.C;
+  const int ldo = split_out ? N : e.ldc;
   constexpr int kColChunks = (TC_BN / 32) * 4 / kEpiWarps;
   const int c0 = (ew / 4) * kColChunks;
   const int rq = lane >> 3, cq = lane & 7;
+  const int n_part = mode == TILE_OWNER ? e.ksplit - 1 : 0;
+  const float alpha = split_out ? 1.0f : (e.alpha_dev ? e.alpha * __ldg(e.alpha_dev) : e.alpha);
+  const uint64_t step = (f & EPI_DROP_RNG) ? (e.step_dev ? *e.step_dev : 0ull) : 0ull;
+  const bool drop_early = (f & (EPI_DROP_MASK | EPI_DROP_RNG)) && !(f & EPI_DROP_LATE);
+  const bool drop_late = (f & (EPI_DROP_MASK | EPI_DROP_RNG)) && (f & EPI_DROP_LATE);
 #pragma unroll 1
   for (int c = c0; c < c0 + kColChunks; ++c) {
     {  // accumulator chunk -> registers (lane = row) -> shared memory
@@ -500,55 +422,152 @@ __device__ __forceinline__ void tc_epilogue_coalesced(const TileCtx& ctx, const 
         *reinterpret_cast<float4*>(stage + lane * TC_STAGE_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       __syncwarp();
     }
-    const int nb = n0 + c * 32;
-    const int n = nb + cq * 4;
-    if (nb >= e.N) continue;
-    const bool full4 = n + 3 < e.N;
+    const int n = n0 + c * 32 + cq * 4;
+    if (n >= N) continue;               // N % 4 == 0: a column quad is inside or outside as a whole
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f & EPI_BIAS) bias4 = ldcg4(e.bias + n);
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {                 // 2 batches of 4 x (4 rows per instruction) = 32 rows
       int rows[4];
       bool ok[4];
-      float4 q[4];
+      float4 q[4], x0[4], x1[4], x2[4];
+      float rs[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int r = (half * 4 + u) * 4 + rq;            // row of the chunk
         rows[u] = m0 + lq * 32 + r;
-        ok[u] = rows[u] < e.M && n < e.N;
+        ok[u] = rows[u] < M;
         q[u] = *reinterpret_cast<const float4*>(stage + r * TC_STAGE_LD + cq * 4);
       }
-      TA3N_EPI_DISPATCH(e.flags, { epi_apply_quads<EPI_F>(e, mode, rows, ok, n, full4, q); })
+      // ---- every load of the batch first ----
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (!ok[u]) continue;
-        float* o = obase + (size_t)rows[u] * ldo + n;
-        if (full4 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
-          *reinterpret_cast<float4*>(o) = q[u];
+        const size_t m = (size_t)rows[u];
+        if (n_part > 0) {
+          x0[u] = ldcg4(e.partial + m * N + n);
+          if (n_part > 1) x1[u] = ldcg4(e.partial + plane + m * N + n);
+          if (n_part > 2) x2[u] = ldcg4(e.partial + 2 * plane + m * N + n);
         } else {
-          if (n + 0 < e.N) o[0] = q[u].x;
-          if (n + 1 < e.N) o[1] = q[u].y;
-          if (n + 2 < e.N) o[2] = q[u].z;
-          if (n + 3 < e.N) o[3] = q[u].w;
+          if (f & EPI_ADDROW) {
+            rs[u] = e.rowscale ? __ldcg(e.rowscale + m * e.rs_stride) + e.rs_bias : 1.0f;
+            x0[u] = ldcg4(e.add + m * e.ldadd + n);
+          }
+          if (f & (EPI_GATE | EPI_DPRE)) x1[u] = ldcg4(e.gate + m * e.ldgate + n);
+          if (f & EPI_ACCUM) x2[u] = ldcg4(e.C + m * e.ldc + n);
         }
       }
-      if (!split_out && (e.flags & EPI_MULTI)) {            // dZ planes: the gates of all planes of the batch in flight
+      // ---- arithmetic + store ----
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          if (p >= e.n_multi) break;
-          float4 gt[4];
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        const size_t m = (size_t)rows[u];
+        float4 v = q[u];
+        if (n_part > 0) {
+          add4(v, x0[u]);
+          if (n_part > 1) add4(v, x1[u]);
+          if (n_part > 2) add4(v, x2[u]);
+        }
+        if (!split_out) {
+          float ev[4] = {v.x * alpha, v.y * alpha, v.z * alpha, v.w * alpha};
+          if (f & EPI_BIAS) {
+            ev[0] += bias4.x;
+            ev[1] += bias4.y;
+            ev[2] += bias4.z;
+            ev[3] += bias4.w;
+          }
+          if (f & EPI_RELU) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ev[i] = fmaxf(ev[i], 0.f);
+          }
+          if (drop_early || drop_late) {
+            float df[4];
+            if (f & EPI_DROP_MASK) {
+              const uchar4 k = *reinterpret_cast<const uchar4*>(e.keep + m * e.ldkeep + n);
+              df[0] = k.x ? e.drop_scale : 0.f;
+              df[1] = k.y ? e.drop_scale : 0.f;
+              df[2] = k.z ? e.drop_scale : 0.f;
+              df[3] = k.w ? e.drop_scale : 0.f;
+            } else {
+              const uint64_t base = e.rng_offset + m * (uint64_t)N + (uint64_t)n;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) df[i] = rng_keep(e.seed, step, base + i, e.drop_p) ? e.drop_scale : 0.f;
+            }
+            if (drop_late && (f & EPI_ADDROW)) {
+              ev[0] = fmaf(rs[u], x0[u].x, ev[0]);
+              ev[1] = fmaf(rs[u], x0[u].y, ev[1]);
+              ev[2] = fmaf(rs[u], x0[u].z, ev[2]);
+              ev[3] = fmaf(rs[u], x0[u].w, ev[3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ev[i] = df[i] != 0.f ? ev[i] * df[i] : 0.f;
+          }
+          if ((f & EPI_ADDROW) && !drop_late) {
+            ev[0] = fmaf(rs[u], x0[u].x, ev[0]);
+            ev[1] = fmaf(rs[u], x0[u].y, ev[1]);
+            ev[2] = fmaf(rs[u], x0[u].z, ev[2]);
+            ev[3] = fmaf(rs[u], x0[u].w, ev[3]);
+          }
+          if (f & EPI_GATE) {
+            ev[0] = x1[u].x > 0.f ? ev[0] : 0.f;
+            ev[1] = x1[u].y > 0.f ? ev[1] : 0.f;
+            ev[2] = x1[u].z > 0.f ? ev[2] : 0.f;
+            ev[3] = x1[u].w > 0.f ? ev[3] : 0.f;
+          }
+          if (f & EPI_ACCUM) {
+            ev[0] += x2[u].x;
+            ev[1] += x2[u].y;
+            ev[2] += x2[u].z;
+            ev[3] += x2[u].w;
+          }
+          if (f & EPI_DPRE) {
+            ev[0] = x1[u].x > 0.f ? ev[0] * e.drop_scale : 0.f;
+            ev[1] = x1[u].y > 0.f ? ev[1] * e.drop_scale : 0.f;
+            ev[2] = x1[u].z > 0.f ? ev[2] * e.drop_scale : 0.f;
+            ev[3] = x1[u].w > 0.f ? ev[3] * e.drop_scale : 0.f;
+          }
+          v = make_float4(ev[0], ev[1], ev[2], ev[3]);
+        }
+        q[u] = v;
+        *reinterpret_cast<float4*>(obase + m * ldo + n) = v;
+      }
+      if (f & EPI_MULTI) {            // dZ planes: the gates of all rows of the batch in flight per plane
+        const int n_multi = e.n_multi;
+#pragma unroll 1
+        for (int p = 0; p < n_multi; ++p) {
+          const float* gate = e.multi_gate[p];
+          float* out = e.multi_out[p];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (ok[u]) gt[u] = __ldcg(reinterpret_cast<const float4*>(e.multi_gate[p] + (size_t)rows[u] * e.ldmulti + n));
+            if (ok[u]) x1[u] = ldcg4(gate + (size_t)rows[u] * e.ldmulti + n);
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             if (ok[u])
-              *reinterpret_cast<float4*>(e.multi_out[p] + (size_t)rows[u] * e.ldmulti + n) =
-                  make_float4(gt[u].x > 0.f ? q[u].x : 0.f, gt[u].y > 0.f ? q[u].y : 0.f, gt[u].z > 0.f ? q[u].z : 0.f,
-                              gt[u].w > 0.f ? q[u].w : 0.f);
+              *reinterpret_cast<float4*>(out + (size_t)rows[u] * e.ldmulti + n) =
+                  make_float4(x1[u].x > 0.f ? q[u].x : 0.f, x1[u].y > 0.f ? q[u].y : 0.f, x1[u].z > 0.f ? q[u].z : 0.f,
+                              x1[u].w > 0.f ? q[u].w : 0.f);
         }
       }
     }
   }
   tc_fence_before();
+}
+
+// Can the step kernel's epilogue take this group?  (see tc_epilogue_coalesced)
+inline bool tc_step_group_ok(const Group& g) {
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (g.N % 4 != 0 || g.ldc % 4 != 0 || !a16(g.C) || g.ksplit > 4) return false;
+  if (g.ksplit > 1 && (g.flags & (EPI_ADDROW | EPI_GATE | EPI_ACCUM | EPI_DPRE | EPI_MULTI))) return false;
+  if ((g.flags & EPI_BIAS) && !a16(g.bias)) return false;
+  if ((g.flags & EPI_DROP_MASK) && (g.ldkeep % 4 != 0 || (reinterpret_cast<uintptr_t>(g.keep) & 3u) != 0)) return false;
+  if ((g.flags & EPI_ADDROW) && (g.ldadd % 4 != 0 || !a16(g.add))) return false;
+  if ((g.flags & (EPI_GATE | EPI_DPRE)) && (g.ldgate % 4 != 0 || !a16(g.gate))) return false;
+  if (g.flags & EPI_MULTI) {
+    if (g.ldmulti % 4 != 0 || g.n_multi > 3) return false;
+    for (int p = 0; p < g.n_multi; ++p)
+      if (!a16(g.multi_gate[p]) || !a16(g.multi_out[p])) return false;
+  }
+  return true;
 }
 
 // chunk range [c_begin, c_begin + n_iter) of split `split` of the group staged in ctx

@@ -42,6 +42,8 @@ enum : int {
   EPI_ACCUM = 64,      // v += C[m,n]
   EPI_DPRE = 128,      // LAST: v = gate[m*ldgate + n] > 0 ? v * drop_scale : 0   (ReLU + dropout backward of the shared
                        //       layer folded into the data-gradient GEMM that completes d_feat; rowops dpre_kernel)
+  EPI_DROP_LATE = 512, // modifier of EPI_DROP_MASK / EPI_DROP_RNG: the dropout factor is applied AFTER the row add
+                       //       (data gradient through dropout: G = (Gc - beta * acc) * keep / (1 - p); models.py:679-680)
   EPI_MULTI = 256      // additionally store v * 1[multi_gate[q][m*ldmulti + n] > 0] to multi_out[q], q < n_multi
                        //       (d_feat_rel -> the dZ planes of every relation of the scale; rowops dz_kernel)
 };
@@ -115,15 +117,18 @@ __device__ __forceinline__ float epilogue_t(const Group& g, int m, int n, float 
   float v = (g.alpha_dev ? g.alpha * __ldg(g.alpha_dev) : g.alpha) * acc;
   if (f & EPI_BIAS) v += g.bias[n];
   if (f & EPI_RELU) v = fmaxf(v, 0.0f);
-  if (f & EPI_DROP_MASK) v = g.keep[(size_t)m * g.ldkeep + n] ? v * g.drop_scale : 0.0f;
+  float dropf = 1.0f;
+  if (f & EPI_DROP_MASK) dropf = g.keep[(size_t)m * g.ldkeep + n] ? g.drop_scale : 0.0f;
   if (f & EPI_DROP_RNG) {
     uint64_t step = g.step_dev ? *g.step_dev : 0ull;
-    v = rng_keep(g.seed, step, g.rng_offset + (uint64_t)m * (uint64_t)g.N + (uint64_t)n, g.drop_p) ? v * g.drop_scale : 0.0f;
+    dropf = rng_keep(g.seed, step, g.rng_offset + (uint64_t)m * (uint64_t)g.N + (uint64_t)n, g.drop_p) ? g.drop_scale : 0.0f;
   }
+  if ((f & (EPI_DROP_MASK | EPI_DROP_RNG)) && !(f & EPI_DROP_LATE)) v = dropf != 0.0f ? v * dropf : 0.0f;
   if (f & EPI_ADDROW) {
     float rs = g.rowscale ? g.rowscale[(size_t)m * g.rs_stride] + g.rs_bias : 1.0f;
     v += rs * g.add[(size_t)m * g.ldadd + n];
   }
+  if ((f & (EPI_DROP_MASK | EPI_DROP_RNG)) && (f & EPI_DROP_LATE)) v = dropf != 0.0f ? v * dropf : 0.0f;
   if (f & EPI_GATE) v = g.gate[(size_t)m * g.ldgate + n] > 0.0f ? v : 0.0f;
   if (f & EPI_ACCUM) v += g.C[(size_t)m * g.ldc + n];
   if (f & EPI_DPRE) v = g.gate[(size_t)m * g.ldgate + n] > 0.0f ? v * g.drop_scale : 0.0f;
@@ -159,6 +164,22 @@ __device__ __forceinline__ void load_row32(const float* p, int nvalid, float (&r
   }
 }
 
+// dropout factor of the 32 elements (m, nb .. nb+31): mask bytes or the counter-based RNG
+__device__ __forceinline__ void drop_row32(const Group& g, const int f, int m, int nb, int nvalid, float (&v)[32]) {
+  if (f & EPI_DROP_MASK) {
+    const uint8_t* k = g.keep + (size_t)m * g.ldkeep + nb;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) v[j] = k[j] ? v[j] * g.drop_scale : 0.0f;
+  }
+  if (f & EPI_DROP_RNG) {
+    const uint64_t step = g.step_dev ? *g.step_dev : 0ull;
+    const uint64_t base = g.rng_offset + (uint64_t)m * (uint64_t)g.N + (uint64_t)nb;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = rng_keep(g.seed, step, base + j, g.drop_p) ? v[j] * g.drop_scale : 0.0f;
+  }
+}
+
 // The same epilogue applied to a 32-column segment (m, nb..nb+31) held by one thread (tcgen05 engine: one
 // accumulator row per lane).  Auxiliary operands (bias, add, gate, C) are fetched as whole 128 B row pieces
 // with vector loads up front instead of one dependent scalar load per element.
@@ -178,24 +199,14 @@ __device__ __forceinline__ void epilogue_row32_generic(const Group& g, int m, in
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
-  if (f & EPI_DROP_MASK) {
-    const uint8_t* k = g.keep + (size_t)m * g.ldkeep + nb;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) v[j] = k[j] ? v[j] * g.drop_scale : 0.0f;
-  }
-  if (f & EPI_DROP_RNG) {
-    const uint64_t step = g.step_dev ? *g.step_dev : 0ull;
-    const uint64_t base = g.rng_offset + (uint64_t)m * (uint64_t)g.N + (uint64_t)nb;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = rng_keep(g.seed, step, base + j, g.drop_p) ? v[j] * g.drop_scale : 0.0f;
-  }
+  if ((f & (EPI_DROP_MASK | EPI_DROP_RNG)) && !(f & EPI_DROP_LATE)) drop_row32(g, f, m, nb, nvalid, v);
   if (f & EPI_ADDROW) {
     const float rs = g.rowscale ? __ldcg(g.rowscale + (size_t)m * g.rs_stride) + g.rs_bias : 1.0f;
     load_row32(g.add + (size_t)m * g.ldadd + nb, nvalid, aux);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaf(rs, aux[j], v[j]);
   }
+  if ((f & (EPI_DROP_MASK | EPI_DROP_RNG)) && (f & EPI_DROP_LATE)) drop_row32(g, f, m, nb, nvalid, v);
   if (f & EPI_GATE) {
     load_row32(g.gate + (size_t)m * g.ldgate + nb, nvalid, aux);
 #pragma unroll
@@ -253,22 +264,12 @@ __device__ __forceinline__ void epilogue_row32(const Group& g, int m, int nb, in
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
-  if (f & EPI_DROP_MASK) {
-    const uint8_t* k = g.keep + (size_t)m * g.ldkeep + nb;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) v[j] = k[j] ? v[j] * g.drop_scale : 0.0f;
-  }
-  if (f & EPI_DROP_RNG) {
-    const uint64_t step = g.step_dev ? *g.step_dev : 0ull;
-    const uint64_t base = g.rng_offset + (uint64_t)m * (uint64_t)g.N + (uint64_t)nb;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = rng_keep(g.seed, step, base + j, g.drop_p) ? v[j] * g.drop_scale : 0.0f;
-  }
+  if ((f & (EPI_DROP_MASK | EPI_DROP_RNG)) && !(f & EPI_DROP_LATE)) drop_row32(g, f, m, nb, nvalid, v);
   if (f & EPI_ADDROW) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaf(rs, a_add[j], v[j]);
   }
+  if ((f & (EPI_DROP_MASK | EPI_DROP_RNG)) && (f & EPI_DROP_LATE)) drop_row32(g, f, m, nb, nvalid, v);
   if (f & EPI_GATE) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = a_gate[j] > 0.0f ? v[j] : 0.0f;
@@ -318,6 +319,7 @@ __device__ __forceinline__ void epilogue_row32(const Group& g, int m, int nb, in
     case EPI_ADDROW: { constexpr int EPI_F = EPI_ADDROW; __VA_ARGS__; } break;              \
     case EPI_ACCUM: { constexpr int EPI_F = EPI_ACCUM; __VA_ARGS__; } break;                \
     case (EPI_ACCUM | EPI_DPRE): { constexpr int EPI_F = EPI_ACCUM | EPI_DPRE; __VA_ARGS__; } break; \
+    case (EPI_ADDROW | EPI_DROP_RNG | EPI_DROP_LATE): { constexpr int EPI_F = EPI_ADDROW | EPI_DROP_RNG | EPI_DROP_LATE; __VA_ARGS__; } break; \
     case (EPI_ADDROW | EPI_MULTI): { constexpr int EPI_F = EPI_ADDROW | EPI_MULTI; __VA_ARGS__; } break; \
     default: { constexpr int EPI_F = -1; __VA_ARGS__; } break;                              \
   }

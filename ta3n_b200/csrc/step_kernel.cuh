@@ -4,16 +4,20 @@
 // backward to every parameter gradient) is a static graph of ~900 small tasks: 128x128 tcgen05 GEMM tiles
 // (gemm_tcgen05.cuh::tc_tile), per-video row tasks and column-sum tasks (step_rows.cuh).  Run as separate launches
 // (round 1: 25 kernels, every one sub-wave) the step is the SUM of per-launch critical paths plus a drain and a
-// pipeline fill at every kernel boundary: 0.27 ms for 20 us of HBM traffic.  Here one CTA per SM pulls tasks from a
-// queue in a fixed priority order; a task waits on arrival counters of the tasks that produce its inputs (release /
-// acquire through global memory), so
+// pipeline fill at every kernel boundary: 0.27 ms for 20 us of HBM traffic.  Here one CTA per SM pulls tasks from
+// priority queues; a task becomes eligible when the arrival counters of the tasks that produce its inputs have reached
+// their targets (release / acquire through global memory), so
 //   * dependent stages overlap at 128-row granularity instead of at kernel boundaries,
-//   * the weight-gradient tiles and column sums (a third of the work, needed by nobody until the end of the step)
-//     fill the SMs the latency-bound forward / data-gradient chain leaves idle,
+//   * the frame branch, the weight-gradient tiles and the column sums (half of the work, needed by nobody on the
+//     video-level chain) fill the SMs the latency-bound chain leaves idle,
 //   * split-K tiles are folded by an "owner" tile that depends on its partial tiles -- deterministic, no reduce pass.
-// Deadlock freedom: tasks are taken in queue order and only ever wait for tasks EARLIER in the queue, each of which
-// has been taken by a resident CTA that never waits on a later task; so the lowest-numbered unfinished task can always
-// run, whatever number of CTAs is resident.  A bounded spin turns any violation into a trap instead of a hang.
+// Scheduling: the tasks live in kStepQueues priority queues (0 = the forward / data-gradient spine, 1..6 = the
+// per-row-block chains between the TRN forward and the TRN data gradient, 7 = fillers: frame branch, weight gradients,
+// column sums).  A CTA's scheduler warp looks at the first unclaimed tasks of every queue at once (4 lanes per queue),
+// checks their arrival counters and claims the first one that is READY with a compare-and-swap.  A CTA therefore never
+// holds a task whose inputs are missing: there is nothing to deadlock on whatever the order inside a queue, and an
+// SM that cannot advance the critical chain takes a filler instead of waiting.  A bounded spin turns a task graph
+// that can never complete (a bug) into a trap instead of a hang.
 // Results do not depend on which CTA runs a task: every output element is produced by exactly one task with a fixed
 // summation order -> bit-identical reruns.
 #pragma once
@@ -31,13 +35,17 @@ static_assert(8 * TC_EPI_STAGE_FLOATS * 4 <= kStepScratchBytes, "epilogue stagin
 constexpr int kStepSmemBytes = kStepStages * TC_STAGE_BYTES + kStepScratchBytes + 1024;
 constexpr int kStepTmemCols = 256;    // two 128-column accumulators
 
-enum : int { TASK_GEMM = 0, TASK_TAIL = 1, TASK_COLSUM_PART = 2, TASK_COLSUM_REDUCE = 3, TASK_FINISH = 4, TASK_STOP = 5 };
+constexpr int kStepQueues = 8;        // 4 scheduler lanes each
+constexpr int kQueueLanes = 32 / kStepQueues;
+
+enum : int { TASK_GEMM = 0, TASK_ROW = 1, TASK_COLSUM_PART = 2, TASK_COLSUM_REDUCE = 3, TASK_FINISH = 4, TASK_STOP = 5,
+             TASK_FRAME = 6 };
 
 struct StepTask {
   int type;
   int group;              // GEMM: group index; COLSUM_*: job index
-  int m0, n0;             // GEMM: tile origin; TAIL: first video, video count; COLSUM_PART: column block, row split
-  int split, mode;        // GEMM: split index, TILE_* mode
+  int m0, n0;             // GEMM: tile origin; ROW / FRAME: first video / frame row, count; COLSUM_PART: column block, row split
+  int split, mode;        // GEMM: split index, TILE_* mode; ROW: ROW_* kind
   int wait_begin[2], wait_end[2], wait_val[2];     // wait until counters[i] >= val for i in [begin, end)
   int signal;             // counter bumped on completion (-1: none)
   int signal2;            // second counter (the stage total; -1: none)
@@ -57,11 +65,11 @@ struct StepHeader {
   const CUtensorMap* maps;
   const WColsumJob* jobs;
   const TailArgs* tail;
-  int* counters;                 // [n_counters]; counters[n_counters - 1] is the queue cursor
+  int* counters;                 // [n_counters] arrival counters, then [n_tasks] claim flags, then [kStepQueues] queue
+                                 // heads (index of the first task of the queue that may still be unclaimed)
+  int queue_begin[kStepQueues + 1];   // tasks of queue q are [queue_begin[q], queue_begin[q + 1])
   unsigned long long* step_counter;   // dropout step counter, advanced by the FINISH task (may be null)
   unsigned long long* trace;     // optional [n_tasks][4]: {sm id, scheduled, accumulator ready, done} (globaltimer ns)
-  int tail_videos;               // videos per row task
-  int pad_;
 };
 
 struct StepSlot {                // one scheduled task: descriptor + (GEMM) the group and its segments
@@ -92,6 +100,64 @@ __device__ __forceinline__ unsigned sm_id() {
   return v;
 }
 
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Scheduler warp: claim the next READY task.  `allow_rows`: row / column-sum tasks may be claimed (only when this CTA
+// has nothing else in flight: a row task claimed behind another one would wait for it while other SMs idle).
+// Returns the task index, or -1 when every task of every queue has been claimed.
+__device__ __forceinline__ int step_claim(const StepHeader& hd, int* const claim, int* const heads, const int lane,
+                                          const volatile int* done_count, const uint32_t issued) {
+  const int q = lane / kQueueLanes, w = lane % kQueueLanes;
+  const int q_end = hd.queue_begin[q + 1];
+  unsigned spins = 0;
+  for (;;) {
+    const bool allow_rows = (uint32_t)(*done_count) == issued;
+    const int head = max(ld_relaxed(heads + q), hd.queue_begin[q]);
+    const int idx = head + w;
+    const bool in_range = idx < q_end;
+    bool claimed = true, ready = false;
+    if (in_range) {
+      claimed = ld_relaxed(claim + idx) != 0;
+      if (!claimed) {
+        const StepTask* t = hd.tasks + idx;
+        const int type = __ldg(&t->type);
+        ready = allow_rows || type == TASK_GEMM;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int cb = __ldg(&t->wait_begin[r]), ce = __ldg(&t->wait_end[r]), val = __ldg(&t->wait_val[r]);
+          for (int c = cb; c < ce && ready; ++c) ready = ld_acquire(hd.counters + c) >= val;
+        }
+      }
+    }
+    // queue heads: skip the leading claimed entries of each window
+    const unsigned cl = __ballot_sync(0xffffffffu, claimed);
+    {
+      const unsigned mine = (cl >> (q * kQueueLanes)) & ((1u << kQueueLanes) - 1u);
+      const int lead = __ffs(~mine) - 1;                    // leading claimed entries (kQueueLanes when all are)
+      if (w == 0 && lead > 0 && head < q_end) atomicMax(heads + q, min(head + lead, q_end));
+    }
+    const unsigned rm = __ballot_sync(0xffffffffu, ready);
+    if (rm != 0u) {
+      const int pick = __ffs(rm) - 1;
+      int ok = 0;
+      if (lane == pick) ok = atomicCAS(claim + idx, 0, 1) == 0 ? 1 : 0;
+      ok = __shfl_sync(0xffffffffu, ok, pick);
+      const int t = __shfl_sync(0xffffffffu, idx, pick);
+      if (ok) return t;
+      continue;
+    }
+    // nothing ready: finished?  (every queue's head at its end)
+    const unsigned open = __ballot_sync(0xffffffffu, head < q_end);
+    if (open == 0u) return -1;
+    __nanosleep(64);
+    if (++spins > (1u << 24)) __trap();                     // ~ seconds: a task graph that cannot complete
+  }
+}
+
 __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid_constant__ StepHeader hd) {
   extern __shared__ uint8_t step_smem_raw[];
   __shared__ __align__(8) TcShared sh;
@@ -100,11 +166,13 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
   __shared__ StepSlot slots[kStepSlots];
   __shared__ TailArgs tail;
   __shared__ WColsumJob job;
+  __shared__ int done_count;            // tasks this CTA has completed (scheduler: is anything still in flight?)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(step_smem_raw) + 1023) & ~uintptr_t(1023));
   float* scratch = reinterpret_cast<float*>(smem + kStepStages * TC_STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tid = threadIdx.x;
-  int* const cursor = hd.counters + hd.n_counters - 1;
+  int* const claim = hd.counters + hd.n_counters;
+  int* const heads = claim + hd.n_tasks;
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -113,6 +181,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
       mbar_init(&slot_full[s], 1);
       mbar_init(&slot_empty[s], 10);       // producer + MMA issuer + 8 epilogue warps
     }
+    done_count = 0;
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&sh.tmem_slot, kStepTmemCols);
@@ -126,15 +195,13 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
   //  and must not release its dependents before it has finished)
 
   if (warp == 10) {
-    // =========================== scheduler: take tasks, stage them, wait for their inputs ===========================
+    // =========================== scheduler: claim ready tasks, stage them ===========================
     for (uint32_t k = 0;; ++k) {
       const int s = (int)(k % kStepSlots);
       mbar_wait(&slot_empty[s], ((k / kStepSlots) & 1u) ^ 1u);
       StepSlot& sl = slots[s];
-      int t = 0;
-      if (lane == 0) t = atomicAdd(cursor, 1);
-      t = __shfl_sync(0xffffffffu, t, 0);
-      if (t >= hd.n_tasks) {
+      const int t = step_claim(hd, claim, heads, lane, &done_count, k);
+      if (t < 0) {
         if (lane == 0) {
           sl.task.type = TASK_STOP;
           mbar_arrive(&slot_full[s]);
@@ -161,21 +228,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
         }
       }
       if (lane == 0) sl.index = t;
-      // dependencies: every lane polls its own counters of the two ranges (acquire)
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int val = sl.task.wait_val[r];
-        for (int c = sl.task.wait_begin[r] + lane; c < sl.task.wait_end[r]; c += 32) {
-          unsigned spins = 0;
-          while (ld_acquire(hd.counters + c) < val) {
-            __nanosleep(40);
-            if (++spins > (1u << 25)) __trap();        // ~ seconds: a scheduling bug becomes an error, not a hung GPU
-          }
-        }
-      }
       __syncwarp();
       if (lane == 0) {
-        __threadfence();
+        __threadfence();                   // the acquire loads of the claim, cumulatively, before the consumers' reads
         mbar_arrive(&slot_full[s]);
       }
     }
@@ -246,8 +301,10 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
           if (lane == 0) mbar_arrive(&sh.tmem_empty_bar[acc]);      // this warp's TMEM reads are done
           ++tiles;
         }
-      } else if (type == TASK_TAIL) {
-        tail_task(tail, sl.task.m0, sl.task.n0, hd.tail_videos, scratch, rt);
+      } else if (type == TASK_FRAME) {
+        frame_task(tail, sl.task.m0, sl.task.n0, rt);
+      } else if (type == TASK_ROW) {
+        video_row_task(sl.task.mode, tail, sl.task.m0, sl.task.n0, rt);
       } else if (type == TASK_COLSUM_PART || type == TASK_COLSUM_REDUCE) {
         for (int i = rt; i < (int)(sizeof(WColsumJob) / sizeof(int)); i += kRowThreads)
           reinterpret_cast<int*>(&job)[i] = __ldg(reinterpret_cast<const int*>(hd.jobs + sl.task.group) + i);
@@ -271,6 +328,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
           if (sig >= 0) red_release(hd.counters + sig, 1);
           if (sig2 >= 0) red_release(hd.counters + sig2, 1);
         }
+        *reinterpret_cast<volatile int*>(&done_count) = (int)(k + 1);
         if (hd.trace) {
           unsigned long long* tr = hd.trace + (size_t)index * 4;
           tr[0] = (unsigned long long)sm_id() | tag;
@@ -292,12 +350,18 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
 }
 
 // ---- stand-alone row kernels of the phased executor --------------------------------------------------------
-__global__ void __launch_bounds__(kRowThreads) tail_kernel(const __grid_constant__ TailArgs a) {
-  extern __shared__ __align__(16) float tail_sm[];
+__global__ void __launch_bounds__(kRowThreads) frame_row_kernel(const __grid_constant__ TailArgs a) {
   pdl_wait();
-  const int v0 = blockIdx.x * kTailVideos;
-  const int nv = min(kTailVideos, a.M - v0);
-  if (nv > 0) tail_task(a, v0, nv, kTailVideos, tail_sm, threadIdx.x);
+  const int r0 = blockIdx.x * kRowFrames;
+  const int nr = min(kRowFrames, a.M * a.T - r0);
+  if (nr > 0) frame_task(a, r0, nr, threadIdx.x);
+}
+
+__global__ void __launch_bounds__(kRowThreads) video_row_kernel(const __grid_constant__ TailArgs a, const int kind) {
+  pdl_wait();
+  const int v0 = blockIdx.x * kRowVideos;
+  const int nv = min(kRowVideos, a.M - v0);
+  if (nv > 0) video_row_task(kind, a, v0, nv, threadIdx.x);
 }
 
 // column sums of the phased executor: the same task functions, (job, column block, row split) from the block index

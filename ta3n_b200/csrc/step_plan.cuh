@@ -47,22 +47,24 @@ inline int step_parse_table(const ta3n_relation_table* tab, StepRelLayout* L) {
 
 // scratch tensors carved from desc->workspace (fixed order: identical addresses on every call)
 struct StepScratch {
-  float *g_video, *g_dom, *g_frame, *Pt, *dHv, *G, *dHid, *dHf, *d_feat, *d_feat_rel, *dz, *row_loss;
+  float *g_video, *g_dom, *g_frame, *g_rel, *Pt, *dHv, *Gc, *G, *dHid, *dHf, *d_feat, *d_feat_rel, *dz, *row_loss, *frame_loss;
 };
 
-struct StepJob {        // a column-sum job and the stage whose outputs it reads
+// stages whose completion a weight-gradient group / column-sum job waits for
+enum : int { DEP_FRAME = 1, DEP_HEADS = 2, DEP_RELBWD = 4, DEP_DZ = 8, DEP_DFEAT = 16 };
+struct StepJob {        // a column-sum job and the stages whose outputs it reads (DEP_* mask, at most two bits)
   WColsumJob job;
-  int dep;              // 4: after the row tasks, 5: after the relation dgrad, 6: after the TRN dgrad
+  int dep;
 };
 
 struct StepProgram {
   StepRelLayout L;
   int M, MT, Rs, Rt;
   StepScratch sc;
-  GemmPlan g1, g2, g3, g5, g6, g7;
+  GemmPlan g1, g2, g3, g4a, g4b, g5, g6, g7;
   int g2_frame_group;                 // index of the frame-discriminator hidden group inside g2 (TRN groups follow)
   int g5_frame_group;                 // index of the frame dgrad group inside g5 (relation groups come first)
-  std::vector<int> g7_dep;            // per group of g7: 4, 5 or 6 (stage that completes its operands)
+  std::vector<int> g7_dep;            // per group of g7: DEP_* mask of the stages that complete its operands
   TailArgs tail;
   std::vector<StepJob> jobs;
   size_t scratch_bytes;               // bytes of the fixed scratch tensors at the start of the workspace
@@ -71,8 +73,8 @@ struct StepProgram {
 inline size_t step_fixed_scratch_floats(int M, int T, int F, int H, int C, int R, int n_rel) {
   auto r = [](size_t n) { return (n + 63) & ~size_t(63); };
   const size_t MT = (size_t)M * T;
-  return r((size_t)M * C) + r((size_t)M * 2) + r(MT * 2) + r((size_t)M * R * 2) + r((size_t)M * H) + r((size_t)M * H) +
-         r((size_t)R * M * H) + r(MT * F) + r(MT * F) + r((size_t)M * R * H) + r((size_t)n_rel * M * H) + r((size_t)M);
+  return r((size_t)M * C) + r((size_t)M * 2) + r(MT * 2) + 2 * r((size_t)M * R * 2) + 3 * r((size_t)M * H) +
+         r((size_t)R * M * H) + r(MT * F) + r(MT * F) + r((size_t)M * R * H) + r((size_t)n_rel * M * H) + r((size_t)M) + r(MT);
 }
 
 // dry: only sizes are wanted (workspace query) -- scratch pointers are placeholders that are never dereferenced
@@ -82,7 +84,8 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
   const StepRelLayout& L = P->L;
   const int T = d->T, D = d->D, F = d->F, H = d->H, C = d->C, R = L.R;
   TA3N_REQUIRE(d->Bs >= 1 && d->Bt >= 0 && T == L.T && D > 0 && F > 0 && H > 0 && C >= 1, "bad sizes");
-  TA3N_REQUIRE(H % 128 == 0 && F % 4 == 0 && D % 4 == 0, "fused step needs H % 128 == 0, F % 4 == 0, D % 4 == 0");
+  TA3N_REQUIRE((H == 128 || H == 256) && F % 4 == 0 && D % 4 == 0, "fused step needs H in {128, 256}, F % 4 == 0, D % 4 == 0");
+  TA3N_REQUIRE(L.R <= 32, "fused step: at most 32 relation scales");
   TA3N_REQUIRE(T <= kTailMaxT && C <= kTailMaxC, "fused step: T <= 32, C <= 128");
   TA3N_REQUIRE(d->x_src && (d->Bt == 0 || d->x_tgt) && d->labels && d->beta_dev && d->loss, "null input");
   TA3N_REQUIRE(d->W_sh && d->b_sh && d->W1f && d->b1f && d->W2f && d->b2f && d->Wc && d->bc && d->W1v && d->b1v &&
@@ -106,8 +109,10 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
   sc.g_video = take((size_t)M * C);
   sc.g_dom = take((size_t)M * 2);
   sc.g_frame = take((size_t)MT * 2);
+  sc.g_rel = take((size_t)M * R * 2);
   sc.Pt = take((size_t)M * R * 2);
   sc.dHv = take((size_t)M * H);
+  sc.Gc = take((size_t)M * H);
   sc.G = take((size_t)M * H);
   sc.dHid = take((size_t)R * M * H);
   sc.dHf = take((size_t)MT * F);
@@ -115,7 +120,8 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
   sc.d_feat_rel = take((size_t)M * R * H);
   sc.dz = take((size_t)L.n_rel * M * H);
   sc.row_loss = take((size_t)M);
-  if (!sc.row_loss) return fail(TA3N_ERR_WORKSPACE, "fused step: workspace too small (%zu bytes)", d->workspace_bytes);
+  sc.frame_loss = take((size_t)MT);
+  if (!sc.frame_loss) return fail(TA3N_ERR_WORKSPACE, "fused step: workspace too small (%zu bytes)", d->workspace_bytes);
   P->scratch_bytes = arena.used;
 
   const DropArgs di = make_drop(&d->drop_i), dv = make_drop(&d->drop_v);
@@ -226,8 +232,6 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
     }
     a.Wc = d->Wc;
     a.bc = d->bc;
-    a.W1v = d->W1v;
-    a.b1v = d->b1v;
     a.W2v = d->W2v;
     a.b2v = d->b2v;
     a.drop_v = dv;
@@ -241,14 +245,58 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
     a.hid_v = d->hid_v;
     a.pred_dom = d->pred_dom;
     a.row_loss = sc.row_loss;
+    a.frame_loss = sc.frame_loss;
     a.g_video = sc.g_video;
     a.g_dom = sc.g_dom;
     a.g_frame = sc.g_frame;
+    a.g_rel = sc.g_rel;
     a.Pt = sc.Pt;
     a.dHv = sc.dHv;
+    a.Gc = sc.Gc;
     a.G = sc.G;
     a.dHid = sc.dHid;
     a.dHf = sc.dHf;
+  }
+  // ---- G4a: hidden layer of the video discriminator on the dropped pooled feature           models.py:464-468 ----
+  {
+    GemmPlan& p = P->g4a;
+    p = GemmPlan();
+    p.label = "step_vid_hidden";
+    Group& g = p.add_group(M, H, d->hid_v, H);
+    g.flags = EPI_BIAS | EPI_RELU;
+    g.bias = d->b1v;
+    p.add_seg(d->dropped, H, d->W1v, H, H);
+  }
+  // ---- G4b: its data gradient, completing G = d loss / d feat_video = (Gc - beta1 * dHv W1v) * keep / (1 - p)
+  //           (GradReverse models.py:20-29 as alpha = -beta1; dropout backward models.py:679-680 in the epilogue) ----
+  {
+    GemmPlan& p = P->g4b;
+    p = GemmPlan();
+    p.label = "step_vid_dgrad";
+    p.a_kmaj = true;
+    p.b_kmaj = false;
+    Group& g = p.add_group(M, H, sc.G, H);
+    g.alpha = -1.0f;
+    g.alpha_dev = d->beta_dev + 1;
+    g.flags = EPI_ADDROW;
+    g.add = sc.Gc;
+    g.ldadd = H;
+    if (dv.mode != 0) {
+      g.flags |= EPI_DROP_LATE;
+      g.drop_scale = dv.scale;
+      g.drop_p = dv.p;
+      if (dv.mode == 1) {
+        g.flags |= EPI_DROP_MASK;
+        g.keep = dv.keep;
+        g.ldkeep = H;
+      } else {
+        g.flags |= EPI_DROP_RNG;
+        g.seed = dv.seed;
+        g.step_dev = dv.step_dev;
+        g.rng_offset = 0;
+      }
+    }
+    p.add_seg(sc.dHv, H, d->W1v, H, H);
   }
   // ---- G5: data gradients of the relation discriminators (-> dZ of every relation) and of the frame
   //          discriminator (-> d_feat)                                              models.py:20-29, 472-488 ----
@@ -319,10 +367,10 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
     p.add_group(F, D, d->dW_sh, D);                                     // shared layer: d_pre^T x
     if (Rs > 0) p.add_seg(sc.d_feat, F, d->x_src, D, Rs);
     if (Rt > 0) p.add_seg(sc.d_feat + (size_t)Rs * F, F, d->x_tgt, D, Rt);
-    P->g7_dep.push_back(6);
+    P->g7_dep.push_back(DEP_DFEAT);
     p.add_group(F, F, d->dW1f, F);                                      // frame discriminator layer 1
     p.add_seg(sc.dHf, F, d->feat, F, MT);
-    P->g7_dep.push_back(4);
+    P->g7_dep.push_back(DEP_FRAME);
     for (int i = 0; i < R; ++i) {                                       // TRN: dW_i[:, jF:(j+1)F] = sum_r dZ^T x[tau[j]]
       const int s = L.scale_size[i];
       TA3N_REQUIRE(d->dW_trn_host[i] && d->db_trn_host[i], "null TRN gradient");
@@ -330,18 +378,18 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
         p.add_group(H, F, d->dW_trn_host[i] + (size_t)j * F, s * F);
         for (int q = L.rel_begin[i]; q < L.rel_begin[i + 1]; ++q)
           p.add_seg(sc.dz + (size_t)q * plane, H, d->feat + (size_t)L.frames[L.slot_begin[q] + j] * F, ldx, M);
-        P->g7_dep.push_back(5);
+        P->g7_dep.push_back(DEP_DZ);
       }
     }
     for (int i = 0; i < R; ++i) {                                       // relation discriminators layer 1
       TA3N_REQUIRE(d->dW1r_host[i] && d->db1r_host[i] && d->dW2r_host[i] && d->db2r_host[i], "null relation gradient");
       p.add_group(H, H, d->dW1r_host[i], H);
       p.add_seg(sc.dHid + (size_t)i * plane, H, d->feat_rel + (size_t)i * H, R * H, M);
-      P->g7_dep.push_back(4);
+      P->g7_dep.push_back(DEP_RELBWD);
     }
     p.add_group(H, H, d->dW1v, H);                                      // video discriminator layer 1
     p.add_seg(sc.dHv, H, d->dropped, H, M);
-    P->g7_dep.push_back(4);
+    P->g7_dep.push_back(DEP_HEADS);
     // (the classifier's weight gradient dWc [C, H] is a skinny reduction over the videos: a weighted column sum below)
   }
   // ---- column sums: bias gradients, skinny head weight gradients, the scalar loss ----
@@ -356,50 +404,51 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
     };
     cs.add(d->db_sh, F, F);
     cs.seg(sc.d_feat, MT);
-    push(6);
+    push(DEP_DFEAT);
     cs.add(d->db1f, F, F);
     cs.seg(sc.dHf, MT);
-    push(4);
+    push(DEP_FRAME);
     cs.add_weighted(d->dW2f, F, 2, F, F, 2);
     cs.seg(d->hid_f, MT, sc.g_frame);
-    push(4);
+    push(DEP_FRAME);
     cs.add(d->db2f, 2, 2);
     cs.seg(sc.g_frame, MT);
-    push(4);
+    push(DEP_FRAME);
     for (int i = 0; i < R; ++i) {
       cs.add(d->db_trn_host[i], H, H);
       for (int q = L.rel_begin[i]; q < L.rel_begin[i + 1]; ++q) cs.seg(sc.dz + (size_t)q * plane, M);
-      push(5);
+      push(DEP_DZ);
     }
     for (int i = 0; i < R; ++i) {
       cs.add_weighted(d->dW2r_host[i], H, 2, H, H, R * 2);
       cs.seg(d->hid_r + (size_t)i * plane, M, sc.Pt + (size_t)i * 2);
-      push(4);
+      push(DEP_RELBWD);
       cs.add(d->db2r_host[i], 2, R * 2);
       cs.seg(sc.Pt + (size_t)i * 2, M);
-      push(4);
+      push(DEP_RELBWD);
       cs.add(d->db1r_host[i], H, H);
       cs.seg(sc.dHid + (size_t)i * plane, M);
-      push(4);
+      push(DEP_RELBWD);
     }
     cs.add_weighted(d->dWc, H, C, H, H, C);
     cs.seg(d->dropped, M, sc.g_video);
-    push(4);
+    push(DEP_HEADS);
     cs.add(d->dbc, C, C);
     cs.seg(sc.g_video, M);
-    push(4);
+    push(DEP_HEADS);
     cs.add_weighted(d->dW2v, H, 2, H, H, 2);
     cs.seg(d->hid_v, M, sc.g_dom);
-    push(4);
+    push(DEP_HEADS);
     cs.add(d->db2v, 2, 2);
     cs.seg(sc.g_dom, M);
-    push(4);
+    push(DEP_HEADS);
     cs.add(d->db1v, H, H);
     cs.seg(sc.dHv, M);
-    push(4);
-    cs.add(d->loss, 1, 1);
+    push(DEP_HEADS);
+    cs.add(d->loss, 1, 1);                 // the scalar loss: video / relation level terms + frame level terms
     cs.seg(sc.row_loss, M);
-    push(4);
+    cs.seg(sc.frame_loss, MT);
+    push(DEP_HEADS | DEP_FRAME);
   }
   return TA3N_OK;
 }
@@ -453,14 +502,14 @@ inline int step_split_filler(int slabs) {
 }
 
 struct BuiltPlan {
-  std::vector<StepTask> tasks;
+  std::vector<StepTask> tasks;    // queue 0's tasks, then queue 1's, ...
+  int queue_begin[kStepQueues + 1];
   std::vector<StepGroup> groups;
   std::vector<SegLite> segs;
   std::vector<CUtensorMap> maps;
   std::vector<WColsumJob> jobs;
   int n_counters = 0;
   int n_gemm_tiles = 0;
-  int tail_videos = kTailVideos;  // videos per row task (what fits the step kernel's scratch shared memory)
   size_t partial_floats = 0;      // split-K partials + column-sum partials (carved after the fixed scratch)
 };
 
@@ -521,6 +570,11 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
       sg.g.ksplit = ksplit[gi];
       sg.g.fix_slot = -1;
       sg.g.partial = sg.g.ksplit > 1 ? carve((size_t)(sg.g.ksplit - 1) * sg.g.M * sg.g.N) : nullptr;
+      if (!tc_step_group_ok(sg.g)) {
+        fail(TA3N_ERR_UNSUPPORTED, "fused step: a group of %s breaks the epilogue's alignment rules (N %d, ldc %d, flags %d)",
+             p.label, sg.g.N, sg.g.ldc, sg.g.flags);
+        return -1;
+      }
       for (int k = 0; k < sg.g.seg_count; ++k) {
         const Seg& s = p.segs[p.groups[gi].seg_begin + k];
         if (!tc_operand_ok(s.A, s.lda) || !tc_operand_ok(s.B, s.ldb) || s.len <= 0) {
@@ -614,11 +668,22 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
       return sa > sb;
     });
   };
-  auto append = [&](const std::vector<StepTask>& v) { B->tasks.insert(B->tasks.end(), v.begin(), v.end()); };
+  // the queues: 0 = spine, 1 .. kStepQueues-2 = row-block chains, kStepQueues-1 = fillers
+  std::vector<StepTask> queue[kStepQueues];
+  constexpr int kFill = kStepQueues - 1;
+  auto chain_q = [&](int mb) { return 1 + mb % (kStepQueues - 2); };
+  auto append = [&](int q, const std::vector<StepTask>& v) { queue[q].insert(queue[q].end(), v.begin(), v.end()); };
   const int nmb = (M + TC_BM - 1) / TC_BM;              // row blocks of a [videos] operand
   const int nfb = (MT + TC_BM - 1) / TC_BM;             // row blocks of a [frames] operand
+  auto one = [](int c, int v) {
+    Dep d;
+    d.b = c;
+    d.e = c + 1;
+    d.v = v;
+    return d;
+  };
 
-  // ================= S1: shared layer =================
+  // ================= S1: shared layer (spine) =================
   std::vector<int> ks1;
   for (const Group& g : P.g1.groups) ks1.push_back(step_split_critical(step_tiles(P.g1.groups[0]) + (P.g1.groups.size() > 1 ? step_tiles(P.g1.groups[1]) : 0), step_slabs(P.g1, g), sm_count));
   const int g1 = add_groups(P.g1, ks1);
@@ -654,17 +719,14 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
     if (d.e < 0) d.b = d.e = 0;
     return d;
   };
-  {
+  for (size_t gi = 0; gi < P.g1.groups.size(); ++gi) {
     std::vector<StepTask> v;
-    for (size_t gi = 0; gi < P.g1.groups.size(); ++gi) {
-      const int cb = g1_cbase[gi];
-      if (emit_group(&v, g1 + (int)gi, Dep(), nullptr, [cb](int mb) { return cb + mb; }) != 0) return TA3N_ERR_INVALID;
-    }
-    sort_by_slabs(&v);
-    append(v);
+    const int cb = g1_cbase[gi];
+    if (emit_group(&v, g1 + (int)gi, Dep(), nullptr, [cb](int mb) { return cb + mb; }) != 0) return TA3N_ERR_INVALID;
+    append(0, v);       // row block after row block: the consumers of the first rows start while the last are computed
   }
-  // ================= S2: frame-discriminator hidden + TRN relations =================
-  // the longest relation tiles (scale 0: 80 K slabs at cfg2) set this stage's critical path: halve them
+  // ================= S2: TRN relations (spine) + frame-discriminator hidden layer (filler) =================
+  // the longest relation tiles (scale 0: 80 K slabs at cfg2) set this stage's critical path: split them
   std::vector<int> ones2(P.g2.groups.size(), 1);
   if (step_split_enabled())
     for (size_t gi = 1; gi < P.g2.groups.size(); ++gi) ones2[gi] = std::min(4, std::max(1, (step_slabs(P.g2, P.g2.groups[gi]) + 39) / 40));
@@ -680,22 +742,94 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
       if (emit_group(&v, g2 + 1 + q, Dep(), [&](int m0) { return feat_rows(T * m0, T * std::min(m0 + TC_BM, M)); },
                      [=](int mb) { return c2t + mb * L.n_rel + q; }) != 0)
         return TA3N_ERR_INVALID;
-    if (emit_group(&v, g2 + 0, Dep(), [&](int m0) { return feat_rows(m0, std::min(m0 + TC_BM, MT)); },
+    sort_by_slabs(&v);
+    std::stable_sort(v.begin(), v.end(), [](const StepTask& a, const StepTask& b) { return a.m0 < b.m0; });   // block-major
+    append(0, v);
+    std::vector<StepTask> vf;
+    if (emit_group(&vf, g2 + 0, Dep(), [&](int m0) { return feat_rows(m0, std::min(m0 + TC_BM, MT)); },
                    [=](int mb) { return c2f + mb; }) != 0)
       return TA3N_ERR_INVALID;
-    sort_by_slabs(&v);
-    append(v);
+    append(kFill, vf);
   }
-  // ================= S3: relation-discriminator hidden layers =================
+  // ================= frame branch (filler): frame rows -> frame dgrad =================
+  // frame row tasks never straddle a 128-row block
+  const int c4f = counters(nfb);
+  const int c4f_total = counters(1);
+  std::vector<int> frame_tasks_of(nfb, 0);
+  int n_frame_tasks = 0;
+  for (int fb = 0; fb < nfb; ++fb)
+    for (int r0 = fb * TC_BM; r0 < std::min((fb + 1) * TC_BM, MT); r0 += kRowFrames) {
+      StepTask t;
+      memset(&t, 0, sizeof(t));
+      t.type = TASK_FRAME;
+      t.m0 = r0;
+      t.n0 = std::min(kRowFrames, std::min((fb + 1) * TC_BM, MT) - r0);
+      t.wait_begin[0] = c2f + fb;
+      t.wait_end[0] = c2f + fb + 1;
+      t.wait_val[0] = need2f;
+      t.signal = c4f + fb;
+      t.signal2 = c4f_total;
+      queue[kFill].push_back(t);
+      frame_tasks_of[fb]++;
+      n_frame_tasks++;
+    }
+  // ================= S3 .. S5: the video-level chains, one per row block =================
   std::vector<int> ones3(P.g3.groups.size(), 1);
   const int g3 = add_groups(P.g3, ones3);
   if (g3 < 0) return TA3N_ERR_UNSUPPORTED;
+  const int g4a = add_groups(P.g4a, std::vector<int>(1, 1));
+  const int g4b = add_groups(P.g4b, std::vector<int>(1, 1));
+  std::vector<int> ones5(P.g5.groups.size(), 1);
+  const int g5 = add_groups(P.g5, ones5);
+  if (g4a < 0 || g4b < 0 || g5 < 0) return TA3N_ERR_UNSUPPORTED;
   const int c3 = counters(nmb * R);                     // hid_r: [row block][scale]
   const int need3 = (P.g3.groups[0].N + TC_BN - 1) / TC_BN;
+  const int c4a = counters(nmb);                        // relpool tasks of a row block
+  const int c4b = counters(nmb);                        // hid_v tiles
+  const int c4c = counters(nmb);                        // heads tasks
+  const int c4c_total = counters(1);
+  const int c4d = counters(nmb);                        // G tiles
+  const int c4e = counters(nmb);                        // relbwd tasks
+  const int c4e_total = counters(1);
+  const int c5r = counters(nmb * R);
+  const int c5r_total = counters(1);
+  const int need5r = (P.g5.groups[0].N + TC_BN - 1) / TC_BN;
+  const int c5f = counters(nfb);
+  const int need5f = (P.g5.groups[P.g5_frame_group].N + TC_BN - 1) / TC_BN;
+  const int need4 = (P.g4a.groups[0].N + TC_BN - 1) / TC_BN;
+  std::vector<int> row_tasks_of(nmb, 0);
+  int n_row_tasks = 0;
+  for (int mb = 0; mb < nmb; ++mb) {
+    row_tasks_of[mb] = (std::min((mb + 1) * TC_BM, M) - mb * TC_BM + kRowVideos - 1) / kRowVideos;
+    n_row_tasks += row_tasks_of[mb];
+  }
+  auto emit_rows = [&](int kind, int mb, const Dep& d, int sig, int sig_total) {
+    for (int v0 = mb * TC_BM; v0 < std::min((mb + 1) * TC_BM, M); v0 += kRowVideos) {
+      StepTask t;
+      memset(&t, 0, sizeof(t));
+      t.type = TASK_ROW;
+      t.mode = kind;
+      t.m0 = v0;
+      t.n0 = std::min(kRowVideos, std::min((mb + 1) * TC_BM, M) - v0);
+      t.wait_begin[0] = d.b;
+      t.wait_end[0] = d.e;
+      t.wait_val[0] = d.v;
+      t.signal = sig;
+      t.signal2 = sig_total;
+      queue[chain_q(mb)].push_back(t);
+    }
+  };
+  // tiles of one row block of a group (emit_group emits all blocks: filter)
+  auto block_tiles = [&](const std::vector<StepTask>& v, int mb) {
+    std::vector<StepTask> o;
+    for (const StepTask& t : v)
+      if (t.m0 / TC_BM == mb) o.push_back(t);
+    return o;
+  };
   {
-    std::vector<StepTask> v;
+    std::vector<StepTask> v3, v4a, v4b, v5;
     for (int i = 0; i < R; ++i)
-      if (emit_group(&v, g3 + i, Dep(),
+      if (emit_group(&v3, g3 + i, Dep(),
                      [&, i](int m0) {
                        Dep d;
                        d.b = c2t + (m0 / TC_BM) * L.n_rel + L.rel_begin[i];
@@ -705,88 +839,45 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
                      },
                      [=](int mb) { return c3 + mb * R + i; }) != 0)
         return TA3N_ERR_INVALID;
-    sort_by_slabs(&v);
-    append(v);
-  }
-  // ================= S4: per-video row tasks =================
-  // videos per row task: what fits the scratch shared memory of the step kernel (4 on the path's shapes)
-  int vpt = kTailVideos;
-  while (vpt > 1 && (size_t)tail_smem_floats(vpt, R, P.tail.H, T, P.tail.C) * sizeof(float) > (size_t)kStepScratchBytes) --vpt;
-  if ((size_t)tail_smem_floats(vpt, R, P.tail.H, T, P.tail.C) * sizeof(float) > (size_t)kStepScratchBytes)
-    return fail(TA3N_ERR_UNSUPPORTED, "fused step: one video does not fit the row task's shared memory (T=%d, C=%d)", T, P.tail.C);
-  B->tail_videos = vpt;
-  const int n_tail = (M + vpt - 1) / vpt;
-  const int c4 = counters(n_tail);
-  const int c4_total = counters(1);
-  auto hidf_rows = [&](int r0, int r1) {                // S2 blocks producing hid_f rows [r0, r1)
-    Dep d;
-    d.b = c2f + r0 / TC_BM;
-    d.e = c2f + (r1 + TC_BM - 1) / TC_BM;
-    d.v = need2f;
-    return d;
-  };
-  for (int k = 0; k < n_tail; ++k) {
-    StepTask t;
-    memset(&t, 0, sizeof(t));
-    t.signal = t.signal2 = -1;
-    t.type = TASK_TAIL;
-    t.m0 = k * vpt;
-    t.n0 = std::min(vpt, M - t.m0);
-    const int mb = t.m0 / TC_BM;
-    t.wait_begin[0] = c3 + mb * R;
-    t.wait_end[0] = c3 + (mb + 1) * R;
-    t.wait_val[0] = need3;
-    const Dep hf = hidf_rows(T * t.m0, T * (t.m0 + t.n0));
-    t.wait_begin[1] = hf.b;
-    t.wait_end[1] = hf.e;
-    t.wait_val[1] = hf.v;
-    t.signal = c4 + k;
-    t.signal2 = c4_total;
-    B->tasks.push_back(t);
-  }
-  auto tail_videos = [&](int v0, int v1) {              // row tasks covering videos [v0, v1)
-    Dep d;
-    d.b = c4 + v0 / vpt;
-    d.e = c4 + (v1 + vpt - 1) / vpt;
-    d.v = 1;
-    return d;
-  };
-  Dep all4;                                             // "every row task is done": one counter
-  all4.b = c4_total;
-  all4.e = c4_total + 1;
-  all4.v = n_tail;
-  // ================= S5: dgrad of the relation discriminators (-> dZ) and of the frame discriminator =================
-  std::vector<int> ones5(P.g5.groups.size(), 1);
-  const int g5 = add_groups(P.g5, ones5);
-  if (g5 < 0) return TA3N_ERR_UNSUPPORTED;
-  const int c5r = counters(nmb * R);
-  const int c5r_total = counters(1);
-  const int need5r = (P.g5.groups[0].N + TC_BN - 1) / TC_BN;
-  const int c5f = counters(nfb);
-  const int need5f = (P.g5.groups[P.g5_frame_group].N + TC_BN - 1) / TC_BN;
-  {
-    std::vector<StepTask> v;
+    sort_by_slabs(&v3);
+    if (emit_group(&v4a, g4a, Dep(), [&](int m0) { return one(c4a + m0 / TC_BM, row_tasks_of[m0 / TC_BM]); },
+                   [=](int mb) { return c4b + mb; }) != 0)
+      return TA3N_ERR_INVALID;
+    if (emit_group(&v4b, g4b, Dep(), [&](int m0) { return one(c4c + m0 / TC_BM, row_tasks_of[m0 / TC_BM]); },
+                   [=](int mb) { return c4d + mb; }) != 0)
+      return TA3N_ERR_INVALID;
     for (int i = 0; i < R; ++i)
-      if (emit_group(&v, g5 + i, Dep(), [&](int m0) { return tail_videos(m0, std::min(m0 + TC_BM, M)); },
+      if (emit_group(&v5, g5 + i, Dep(), [&](int m0) { return one(c4e + m0 / TC_BM, row_tasks_of[m0 / TC_BM]); },
                      [=](int mb) { return c5r + mb * R + i; }, c5r_total) != 0)
         return TA3N_ERR_INVALID;
+    for (int mb = 0; mb < nmb; ++mb) {
+      const int q = chain_q(mb);
+      append(q, block_tiles(v3, mb));
+      Dep d3;
+      d3.b = c3 + mb * R;
+      d3.e = c3 + (mb + 1) * R;
+      d3.v = need3;
+      emit_rows(ROW_RELPOOL, mb, d3, c4a + mb, -1);
+      append(q, block_tiles(v4a, mb));
+      emit_rows(ROW_HEADS, mb, one(c4b + mb, need4), c4c + mb, c4c_total);
+      append(q, block_tiles(v4b, mb));
+      emit_rows(ROW_RELBWD, mb, one(c4d + mb, need4), c4e + mb, c4e_total);
+      append(q, block_tiles(v5, mb));
+    }
+    // frame dgrad (filler): its A operand dHf comes from the frame row tasks of the same 128-row block
     std::vector<StepTask> vf;
-    if (emit_group(&vf, g5 + P.g5_frame_group, Dep(),
-                   [&](int m0) { return tail_videos(m0 / T, (std::min(m0 + TC_BM, MT) + T - 1) / T); },
+    if (emit_group(&vf, g5 + P.g5_frame_group, Dep(), [&](int m0) { return one(c4f + m0 / TC_BM, frame_tasks_of[m0 / TC_BM]); },
                    [=](int mb) { return c5f + mb; }) != 0)
       return TA3N_ERR_INVALID;
-    append(v);          // the relation tiles gate S6: first
-    append(vf);
+    append(kFill, vf);
   }
-  // ================= fillers that only need the row tasks =================
-  // (G7 groups with dep 4, column sums with dep 4)
+  // ================= weight gradients and column sums =================
   std::vector<int> ks7;
   for (size_t gi = 0; gi < P.g7.groups.size(); ++gi) ks7.push_back(step_split_filler(step_slabs(P.g7, P.g7.groups[gi])));
   // the shared-layer weight gradient closes the step: balance it over the whole machine
   ks7[0] = std::max(ks7[0], step_split_critical(step_tiles(P.g7.groups[0]), step_slabs(P.g7, P.g7.groups[0]), sm_count));
   const int g7 = add_groups(P.g7, ks7);
   if (g7 < 0) return TA3N_ERR_UNSUPPORTED;
-  // column-sum jobs
   const int job0 = (int)B->jobs.size();
   const int cj = counters((int)P.jobs.size());
   std::vector<int> job_parts(P.jobs.size(), 0);
@@ -797,52 +888,7 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
     job_parts[ji] = ((j.N + 127) / 128) * j.nsplit;
     B->jobs.push_back(j);
   }
-  auto emit_jobs = [&](int dep, const Dep& d) {
-    for (size_t ji = 0; ji < P.jobs.size(); ++ji) {
-      if (P.jobs[ji].dep != dep) continue;
-      const WColsumJob& j = B->jobs[job0 + ji];
-      for (int cb = 0; cb < (j.N + 127) / 128; ++cb)
-        for (int sp = 0; sp < j.nsplit; ++sp) {
-          StepTask t;
-          memset(&t, 0, sizeof(t));
-    t.signal = t.signal2 = -1;
-          t.type = TASK_COLSUM_PART;
-          t.group = job0 + (int)ji;
-          t.m0 = cb;
-          t.n0 = sp;
-          t.wait_begin[0] = d.b;
-          t.wait_end[0] = d.e;
-          t.wait_val[0] = d.v;
-          t.signal = cj + (int)ji;
-          B->tasks.push_back(t);
-        }
-    }
-    for (size_t ji = 0; ji < P.jobs.size(); ++ji) {
-      if (P.jobs[ji].dep != dep) continue;
-      StepTask t;
-      memset(&t, 0, sizeof(t));
-    t.signal = t.signal2 = -1;
-      t.type = TASK_COLSUM_REDUCE;
-      t.group = job0 + (int)ji;
-      t.wait_begin[0] = cj + (int)ji;
-      t.wait_end[0] = cj + (int)ji + 1;
-      t.wait_val[0] = job_parts[ji];
-      t.signal = -1;
-      B->tasks.push_back(t);
-    }
-  };
-  auto emit_wgrad = [&](int dep, const Dep& d) {
-    std::vector<StepTask> v;
-    for (size_t gi = 0; gi < P.g7.groups.size(); ++gi)
-      if (P.g7_dep[gi] == dep)
-        if (emit_group(&v, g7 + (int)gi, d, nullptr, nullptr) != 0) return -1;
-    sort_by_slabs(&v);
-    append(v);
-    return 0;
-  };
-  if (emit_wgrad(4, all4) != 0) return TA3N_ERR_INVALID;
-  emit_jobs(4, all4);
-  // ================= S6: TRN dgrad per frame (+ frame-disc gradient, ReLU/dropout backward) =================
+  // ================= S6: TRN dgrad per frame (+ frame-disc gradient, ReLU/dropout backward) (spine) =================
   std::vector<int> ones6(P.g6.groups.size(), 1);
   const int g6 = add_groups(P.g6, ones6);
   if (g6 < 0) return TA3N_ERR_UNSUPPORTED;
@@ -873,32 +919,100 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
       }
     }
     sort_by_slabs(&v);
-    append(v);
+    std::stable_sort(v.begin(), v.end(), [](const StepTask& a, const StepTask& b) { return a.m0 < b.m0; });   // block-major
+    append(0, v);
   }
-  Dep all5;                                             // every dZ plane is complete
-  all5.b = c5r_total;
-  all5.e = c5r_total + 1;
-  all5.v = nmb * R * need5r;
-  if (emit_wgrad(5, all5) != 0) return TA3N_ERR_INVALID;
-  emit_jobs(5, all5);
-  Dep all6;                                             // d(pre-activation) of the shared layer is complete
-  all6.b = c6_total;
-  all6.e = c6_total + 1;
-  all6.v = nmb * T * need6;
-  if (emit_wgrad(6, all6) != 0) return TA3N_ERR_INVALID;
-  emit_jobs(6, all6);
-  {  // advance the dropout step counter once every reader (S1 epilogues, row tasks) is done
+  // stage-complete conditions
+  auto dep_of = [&](int bit) {
+    switch (bit) {
+      case DEP_FRAME: return one(c4f_total, n_frame_tasks);
+      case DEP_HEADS: return one(c4c_total, n_row_tasks);
+      case DEP_RELBWD: return one(c4e_total, n_row_tasks);
+      case DEP_DZ: return one(c5r_total, nmb * R * need5r);
+      default: return one(c6_total, nmb * T * need6);
+    }
+  };
+  auto set_deps = [&](StepTask* t, int mask) {
+    int r = 0;
+    for (int bit = 1; bit <= DEP_DFEAT; bit <<= 1)
+      if (mask & bit) {
+        if (r >= 2) return -1;
+        const Dep d = dep_of(bit);
+        t->wait_begin[r] = d.b;
+        t->wait_end[r] = d.e;
+        t->wait_val[r] = d.v;
+        ++r;
+      }
+    return 0;
+  };
+  auto emit_jobs = [&](int q, int mask) {
+    for (size_t ji = 0; ji < P.jobs.size(); ++ji) {
+      if (P.jobs[ji].dep != mask) continue;
+      const WColsumJob& j = B->jobs[job0 + ji];
+      for (int cb = 0; cb < (j.N + 127) / 128; ++cb)
+        for (int sp = 0; sp < j.nsplit; ++sp) {
+          StepTask t;
+          memset(&t, 0, sizeof(t));
+          t.signal2 = -1;
+          t.type = TASK_COLSUM_PART;
+          t.group = job0 + (int)ji;
+          t.m0 = cb;
+          t.n0 = sp;
+          if (set_deps(&t, mask) != 0) return -1;
+          t.signal = cj + (int)ji;
+          queue[q].push_back(t);
+        }
+    }
+    for (size_t ji = 0; ji < P.jobs.size(); ++ji) {
+      if (P.jobs[ji].dep != mask) continue;
+      StepTask t;
+      memset(&t, 0, sizeof(t));
+      t.signal = t.signal2 = -1;
+      t.type = TASK_COLSUM_REDUCE;
+      t.group = job0 + (int)ji;
+      t.wait_begin[0] = cj + (int)ji;
+      t.wait_end[0] = cj + (int)ji + 1;
+      t.wait_val[0] = job_parts[ji];
+      queue[q].push_back(t);
+    }
+    return 0;
+  };
+  auto emit_wgrad = [&](int q, int mask) {
+    std::vector<StepTask> v;
+    for (size_t gi = 0; gi < P.g7.groups.size(); ++gi)
+      if (P.g7_dep[gi] == mask) {
+        const Dep d = dep_of(mask);
+        if (emit_group(&v, g7 + (int)gi, d, nullptr, nullptr) != 0) return -1;
+      }
+    sort_by_slabs(&v);
+    append(q, v);
+    return 0;
+  };
+  // fillers in the order their operands complete; the shared layer's gradients close the spine
+  for (int mask : {(int)DEP_FRAME, (int)DEP_HEADS, (int)(DEP_HEADS | DEP_FRAME), (int)DEP_RELBWD, (int)DEP_DZ}) {
+    if ((mask & (mask - 1)) == 0 && emit_wgrad(kFill, mask) != 0) return TA3N_ERR_INVALID;
+    if (emit_jobs(kFill, mask) != 0) return TA3N_ERR_INVALID;
+  }
+  if (emit_wgrad(0, DEP_DFEAT) != 0) return TA3N_ERR_INVALID;
+  if (emit_jobs(0, DEP_DFEAT) != 0) return TA3N_ERR_INVALID;
+  {  // advance the dropout step counter once every reader (S1 epilogues, relpool tasks, the G tiles) is done
     StepTask t;
     memset(&t, 0, sizeof(t));
     t.signal = t.signal2 = -1;
     t.type = TASK_FINISH;
-    t.wait_begin[0] = all4.b;
-    t.wait_end[0] = all4.e;
-    t.wait_val[0] = all4.v;
-    t.signal = -1;
-    B->tasks.push_back(t);
+    const Dep d = dep_of(DEP_DZ);
+    t.wait_begin[0] = d.b;
+    t.wait_end[0] = d.e;
+    t.wait_val[0] = d.v;
+    queue[kFill].push_back(t);
   }
-  B->n_counters = nc + 1;          // + the queue cursor
+  B->tasks.clear();
+  for (int q = 0; q < kStepQueues; ++q) {
+    B->queue_begin[q] = (int)B->tasks.size();
+    B->tasks.insert(B->tasks.end(), queue[q].begin(), queue[q].end());
+  }
+  B->queue_begin[kStepQueues] = (int)B->tasks.size();
+  B->n_counters = nc;
   B->partial_floats = pused;
   if (partial_base && pused > partial_cap_floats) return fail(TA3N_ERR_WORKSPACE, "fused step: partial workspace too small");
   return TA3N_OK;

@@ -822,18 +822,12 @@ int ta3n_counter_inc(uint64_t* counter, ta3n_stream_t stream) {
 namespace {
 
 constexpr int kStepMagic = 0x7A3B5700;
-std::atomic<unsigned long long*>& tail_debug_ptr() {       // development: phase timestamps of the row task
-  static std::atomic<unsigned long long*> p{nullptr};
-  return p;
-}
-
 int step_kernel_config(int* sm_count) {          // per-device opt-in of the large dynamic shared memory
   std::lock_guard<std::mutex> lock(device_mu());
   DeviceInfo* d = device_info();
   if (!d) return fail(TA3N_ERR_CUDA, "cudaGetDevice failed");
   if (!d->step_configured) {
     TA3N_CUDA(cudaFuncSetAttribute(ta3n_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBytes));
-    TA3N_CUDA(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     d->step_configured = true;
   }
   *sm_count = d->sm_count;
@@ -851,26 +845,29 @@ size_t ta3n_step_workspace_bytes(const ta3n_step_desc* desc) {
   return P.scratch_bytes + Arena::round(B.partial_floats * sizeof(float)) + 4096;
 }
 
-void ta3n_debug_set_tail_trace(unsigned long long* dev_buf) { tail_debug_ptr().store(dev_buf); }
-
 int ta3n_step_run_phased(const ta3n_step_desc* desc, ta3n_stream_t stream) {
   StepProgram P;
   TA3N_TRY(build_step_program(desc, &P));
-  P.tail.dbg = tail_debug_ptr().load();
   cudaStream_t st = S(stream);
   int sm_count = 148;
   TA3N_TRY(step_kernel_config(&sm_count));
+  const int n_row = (P.M + kRowVideos - 1) / kRowVideos;
+  auto rows = [&](const char* label, int kind) {
+    pre_launch(label, st);
+    launch_kernel(video_row_kernel, n_row, kRowThreads, 0, st, P.tail, kind);
+    return after_launch();
+  };
   TA3N_TRY(run_gemm(P.g1, st));
   TA3N_TRY(run_gemm(P.g2, st));
+  pre_launch("step_frame_rows", st);
+  launch_kernel(frame_row_kernel, (P.MT + kRowFrames - 1) / kRowFrames, kRowThreads, 0, st, P.tail);
+  TA3N_TRY(after_launch());
   TA3N_TRY(run_gemm(P.g3, st));
-  {
-    const int n_tail = (P.M + kTailVideos - 1) / kTailVideos;
-    const size_t smem = (size_t)tail_smem_floats(kTailVideos, P.L.R, desc->H, desc->T, desc->C) * sizeof(float);
-    TA3N_REQUIRE(smem <= 160 * 1024, "row task: shared memory (T, C too large)");
-    pre_launch("step_tail", st);
-    launch_kernel(tail_kernel, n_tail, kRowThreads, smem, st, P.tail);
-    TA3N_TRY(after_launch());
-  }
+  TA3N_TRY(rows("step_relpool", ROW_RELPOOL));
+  TA3N_TRY(run_gemm(P.g4a, st));
+  TA3N_TRY(rows("step_heads", ROW_HEADS));
+  TA3N_TRY(run_gemm(P.g4b, st));
+  TA3N_TRY(rows("step_relbwd", ROW_RELBWD));
   TA3N_TRY(run_gemm(P.g5, st));
   TA3N_TRY(run_gemm(P.g6, st));
   TA3N_TRY(run_gemm(P.g7, st));
@@ -923,7 +920,7 @@ PlanLayout plan_layout(const BuiltPlan& B) {
   l.segs = put(B.segs.size() * sizeof(SegLite));
   l.jobs = put(B.jobs.size() * sizeof(WColsumJob));
   l.tail = put(sizeof(TailArgs));
-  l.counters = put((size_t)B.n_counters * sizeof(int));
+  l.counters = put((size_t)(B.n_counters + B.tasks.size() + kStepQueues) * sizeof(int));
   l.total = off;
   return l;
 }
@@ -973,7 +970,7 @@ int ta3n_step_build(const ta3n_step_desc* desc, void* plan_dev, size_t plan_byte
   h.hd.tail = reinterpret_cast<const TailArgs*>(base + l.tail);
   h.hd.counters = reinterpret_cast<int*>(base + l.counters);
   h.hd.step_counter = reinterpret_cast<unsigned long long*>(desc->step_counter);
-  h.hd.tail_videos = B.tail_videos;
+  for (int q = 0; q <= kStepQueues; ++q) h.hd.queue_begin[q] = B.queue_begin[q];
   h.magic = kStepMagic;
   h.n_gemm_tiles = B.n_gemm_tiles;
   h.smem_bytes = kStepSmemBytes;
@@ -989,7 +986,8 @@ int ta3n_step_run(const void* handle_host, ta3n_stream_t stream) {
   memcpy(&h, handle_host, sizeof(h));
   TA3N_REQUIRE(h.magic == kStepMagic, "not a handle filled by ta3n_step_build");
   cudaStream_t st = S(stream);
-  TA3N_CUDA(cudaMemsetAsync(h.hd.counters, 0, (size_t)h.hd.n_counters * sizeof(int), st));
+  // arrival counters, claim flags and queue heads
+  TA3N_CUDA(cudaMemsetAsync(h.hd.counters, 0, (size_t)(h.hd.n_counters + h.hd.n_tasks + kStepQueues) * sizeof(int), st));
   pre_launch("step_kernel", st);
   ta3n_step_kernel<<<h.grid, kStepThreads, h.smem_bytes, st>>>(h.hd);
   return after_launch();
@@ -1002,12 +1000,13 @@ size_t ta3n_step_describe(const ta3n_step_desc* desc, char* buf, size_t buf_byte
   if (build_step_program(desc, &P, /*dry=*/true) != TA3N_OK) return 0;
   BuiltPlan B;
   if (build_task_graph(P, 148, nullptr, 0, &B) != TA3N_OK) return 0;
-  int n_type[5] = {0, 0, 0, 0, 0};
+  int n_type[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long slabs = 0;
-  int bad_order = 0;
-  std::vector<int> signalled_before(B.n_counters, 0);
-  for (size_t i = 0; i < B.tasks.size(); ++i) {
-    const StepTask& t = B.tasks[i];
+  int bad = 0;
+  // every wait must be satisfiable: the counter's total number of signals reaches the awaited value, and the
+  // dependency graph is acyclic (checked by simulating the scheduler: run whatever is ready until nothing is left)
+  std::vector<int> total(B.n_counters, 0);
+  for (const StepTask& t : B.tasks) {
     n_type[t.type]++;
     if (t.type == TASK_GEMM) {
       const StepGroup& sg = B.groups[t.group];
@@ -1015,18 +1014,42 @@ size_t ta3n_step_describe(const ta3n_step_desc* desc, char* buf, size_t buf_byte
       for (int k = 0; k < sg.g.seg_count; ++k) n += (B.segs[sg.seg_begin + k].len + TC_BK - 1) / TC_BK;
       slabs += (n + sg.g.ksplit - 1) / sg.g.ksplit;
     }
-    // every wait must be satisfiable by signals of EARLIER tasks (the deadlock-freedom invariant)
-    for (int r = 0; r < 2; ++r)
-      for (int c = t.wait_begin[r]; c < t.wait_end[r]; ++c)
-        if (c < 0 || c >= B.n_counters - 1 || signalled_before[c] < t.wait_val[r]) ++bad_order;
-    if (t.signal >= 0) signalled_before[t.signal]++;
+    if (t.signal >= 0) total[t.signal]++;
+    if (t.signal2 >= 0) total[t.signal2]++;
+  }
+  {
+    std::vector<int> cnt(B.n_counters, 0);
+    std::vector<char> done(B.tasks.size(), 0);
+    size_t left = B.tasks.size();
+    bool progress = true;
+    while (left > 0 && progress) {
+      progress = false;
+      for (size_t i = 0; i < B.tasks.size(); ++i) {
+        if (done[i]) continue;
+        const StepTask& t = B.tasks[i];
+        bool ready = true;
+        for (int r = 0; r < 2 && ready; ++r)
+          for (int c = t.wait_begin[r]; c < t.wait_end[r]; ++c)
+            if (c < 0 || c >= B.n_counters || cnt[c] < t.wait_val[r]) {
+              ready = false;
+              break;
+            }
+        if (!ready) continue;
+        done[i] = 1;
+        --left;
+        progress = true;
+        if (t.signal >= 0) cnt[t.signal]++;
+        if (t.signal2 >= 0) cnt[t.signal2]++;
+      }
+    }
+    bad = (int)left;
   }
   char line[512];
   snprintf(line, sizeof(line),
-           "tasks %zu gemm_tiles %d tail %d colsum_parts %d colsum_reduces %d counters %d maps %zu groups %zu slabs %ld "
+           "tasks %zu gemm_tiles %d row %d frame %d colsum_parts %d colsum_reduces %d counters %d maps %zu groups %zu slabs %ld "
            "partial_floats %zu unsatisfiable_waits %d",
-           B.tasks.size(), n_type[TASK_GEMM], n_type[TASK_TAIL], n_type[TASK_COLSUM_PART], n_type[TASK_COLSUM_REDUCE],
-           B.n_counters, B.maps.size(), B.groups.size(), slabs, B.partial_floats, bad_order);
+           B.tasks.size(), n_type[TASK_GEMM], n_type[TASK_ROW], n_type[TASK_FRAME], n_type[TASK_COLSUM_PART],
+           n_type[TASK_COLSUM_REDUCE], B.n_counters, B.maps.size(), B.groups.size(), slabs, B.partial_floats, bad);
   const size_t n = strlen(line);
   if (buf && buf_bytes > 0) {
     const size_t c = n < buf_bytes - 1 ? n : buf_bytes - 1;

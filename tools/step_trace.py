@@ -42,7 +42,7 @@ nit = (tag >> 52) & 0xFFF
 t0 = int(sched[sched > 0].min())
 span = (int(done.max()) - t0) / 1e3
 print(f"tasks {len(t)}  span {span:.1f} us  SMs used {len(set(sm.tolist()))}")
-names = {0: "gemm", 1: "tail", 2: "colsum_part", 3: "colsum_reduce", 4: "finish"}
+names = {0: "gemm", 1: "row", 6: "frame", 2: "colsum_part", 3: "colsum_reduce", 4: "finish"}
 busy_total = 0.0
 for k, nm in names.items():
     sel = typ == k
@@ -58,12 +58,24 @@ for k, nm in names.items():
     print(f"  {nm:14s} n={int(sel.sum()):5d}  busy {dur.sum():9.1f} us  avg {dur.mean():6.2f}  max {dur.max():6.2f}{extra}")
 print(f"  epilogue-warp busy fraction: {busy_total / (span * len(set(sm.tolist()))):.2f}")
 # per GEMM group: when did it start / end (relative), tiles, avg duration
-print("  group  tiles  slabs/tile  first_start  last_end   avg_dur (us)")
+print("  group  tiles  slabs/tile  first_start  last_end   avg_dur  acc_wait  epilogue (us)")
 for gidx in sorted(set(grp[typ == 0].tolist())):
     sel = (typ == 0) & (grp == gidx)
     print(f"  {gidx:5d}  {int(sel.sum()):5d}  {float(nit[sel].double().mean()):9.1f}  {(int(sched[sel].min()) - t0) / 1e3:10.1f}  "
-          f"{(int(done[sel].max()) - t0) / 1e3:9.1f}  {float((done[sel] - sched[sel]).double().mean()) / 1e3:8.2f}")
-for k in (1, 2, 3):
+          f"{(int(done[sel].max()) - t0) / 1e3:9.1f}  {float((done[sel] - sched[sel]).double().mean()) / 1e3:8.2f}"
+          f"  {float((acc[sel] - sched[sel]).double().mean()) / 1e3:8.2f}  {float((done[sel] - acc[sel]).double().mean()) / 1e3:8.2f}")
+for k in (6, 2, 3):
     sel = typ == k
     if sel.sum():
         print(f"  {names[k]:14s} first_start {(int(sched[sel].min()) - t0) / 1e3:8.1f}  last_end {(int(done[sel].max()) - t0) / 1e3:8.1f}")
+for kind, nm in ((0, "relpool"), (1, "heads"), (2, "relbwd")):
+    sel = (typ == 1) & (mode == kind)
+    if sel.sum():
+        d = (done[sel] - sched[sel]).double() / 1e3
+        print(f"  row:{nm:9s} n={int(sel.sum()):4d} first_start {(int(sched[sel].min()) - t0) / 1e3:8.1f}  last_end {(int(done[sel].max()) - t0) / 1e3:8.1f}"
+              f"  avg {d.mean():6.2f} max {d.max():6.2f}")
+# idle time: per SM, span minus busy
+busy = {}
+for i in range(len(t)):
+    busy[int(sm[i])] = busy.get(int(sm[i]), 0.0) + (int(done[i]) - int(sched[i])) / 1e3
+print(f"  per-SM busy: min {min(busy.values()):.1f} max {max(busy.values()):.1f} mean {sum(busy.values()) / len(busy):.1f} us of {span:.1f}")
