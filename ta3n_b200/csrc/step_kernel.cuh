@@ -11,13 +11,14 @@
 //   * the frame branch, the weight-gradient tiles and the column sums (half of the work, needed by nobody on the
 //     video-level chain) fill the SMs the latency-bound chain leaves idle,
 //   * split-K tiles are folded by an "owner" tile that depends on its partial tiles -- deterministic, no reduce pass.
-// Scheduling: the tasks live in kStepQueues priority queues (0 = the forward / data-gradient spine, 1..6 = the
-// per-row-block chains between the TRN forward and the TRN data gradient, 7 = fillers: frame branch, weight gradients,
-// column sums).  A CTA's scheduler warp looks at the first unclaimed tasks of every queue at once (4 lanes per queue),
-// checks their arrival counters and claims the first one that is READY with a compare-and-swap.  A CTA therefore never
-// holds a task whose inputs are missing: there is nothing to deadlock on whatever the order inside a queue, and an
-// SM that cannot advance the critical chain takes a filler instead of waiting.  A bounded spin turns a task graph
-// that can never complete (a bug) into a trap instead of a hang.
+// Scheduling: the tasks live in kStepQueues queues (0 = the forward / data-gradient spine, 1..6 = the per-row-block
+// chains between the TRN forward and the TRN data gradient, 7 = fillers: frame branch, weight gradients, column sums),
+// each with a ticket cursor.  A CTA's scheduler warp looks at the head of every queue at once, and draws a ticket
+// from the first queue whose head task is READY (arrival counters reached).  A CTA never blocks on a task: a ticket
+// drawn in a race for a task that is not ready yet is parked and polled, while the CTA keeps taking other work -- an
+// SM that cannot advance the critical chain takes a filler instead of waiting.  Progress needs the queue orders to be
+// consistent with the dependencies (a head-only scheduler must be able to finish: checked by ta3n_step_describe and
+// tests/test_step_plan.py); a bounded spin turns a violation into a trap instead of a hang.
 // Results do not depend on which CTA runs a task: every output element is produced by exactly one task with a fixed
 // summation order -> bit-identical reruns.
 #pragma once
@@ -35,8 +36,7 @@ static_assert(8 * TC_EPI_STAGE_FLOATS * 4 <= kStepScratchBytes, "epilogue stagin
 constexpr int kStepSmemBytes = kStepStages * TC_STAGE_BYTES + kStepScratchBytes + 1024;
 constexpr int kStepTmemCols = 256;    // two 128-column accumulators
 
-constexpr int kStepQueues = 8;        // 4 scheduler lanes each
-constexpr int kQueueLanes = 32 / kStepQueues;
+constexpr int kStepQueues = 8;
 
 enum : int { TASK_GEMM = 0, TASK_ROW = 1, TASK_COLSUM_PART = 2, TASK_COLSUM_REDUCE = 3, TASK_FINISH = 4, TASK_STOP = 5,
              TASK_FRAME = 6 };
@@ -65,8 +65,7 @@ struct StepHeader {
   const CUtensorMap* maps;
   const WColsumJob* jobs;
   const TailArgs* tail;
-  int* counters;                 // [n_counters] arrival counters, then [n_tasks] claim flags, then [kStepQueues] queue
-                                 // heads (index of the first task of the queue that may still be unclaimed)
+  int* counters;                 // [n_counters] arrival counters, then [kStepQueues] ticket cursors of the queues
   int queue_begin[kStepQueues + 1];   // tasks of queue q are [queue_begin[q], queue_begin[q + 1])
   unsigned long long* step_counter;   // dropout step counter, advanced by the FINISH task (may be null)
   unsigned long long* trace;     // optional [n_tasks][4]: {sm id, scheduled, accumulator ready, done} (globaltimer ns)
@@ -106,54 +105,74 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
   return v;
 }
 
-// Scheduler warp: claim the next READY task.  `allow_rows`: row / column-sum tasks may be claimed (only when this CTA
-// has nothing else in flight: a row task claimed behind another one would wait for it while other SMs idle).
-// Returns the task index, or -1 when every task of every queue has been claimed.
-__device__ __forceinline__ int step_claim(const StepHeader& hd, int* const claim, int* const heads, const int lane,
-                                          const volatile int* done_count, const uint32_t issued) {
-  const int q = lane / kQueueLanes, w = lane % kQueueLanes;
-  const int q_end = hd.queue_begin[q + 1];
+// Is task `idx` runnable by this CTA now?  (arrival counters reached; row-type tasks only when `allow_rows`)
+__device__ __forceinline__ bool step_task_ready(const StepHeader& hd, const int idx, const bool allow_rows) {
+  const StepTask* t = hd.tasks + idx;
+  if (!allow_rows && __ldg(&t->type) != TASK_GEMM) return false;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int cb = __ldg(&t->wait_begin[r]), ce = __ldg(&t->wait_end[r]), val = __ldg(&t->wait_val[r]);
+    for (int c = cb; c < ce; ++c)
+      if (ld_acquire(hd.counters + c) < val) return false;
+  }
+  return true;
+}
+
+constexpr int kStepDeferred = 8;      // tickets a CTA may hold for tasks that were not ready when it drew them
+
+// Scheduler warp: the next task for this CTA.  Every queue has a ticket cursor; a CTA draws a ticket (atomicAdd: no two
+// CTAs ever contend for the same task) only after seeing that the task at the cursor is READY.  When several CTAs draw
+// at once the later tickets belong to tasks nobody has checked: such a task, if not ready, is parked in the CTA's
+// deferred list and polled with the queue heads -- the CTA never blocks on it and keeps taking other work.
+// `allow_rows`: row / column-sum tasks run only when the CTA has nothing else in flight (a row task queued behind
+// another task would wait for it while other SMs idle).  Returns the task index, or -1 when every queue is drained.
+__device__ __forceinline__ int step_next_task(const StepHeader& hd, int* const cursors, const int lane,
+                                              const volatile int* done_count, const uint32_t issued, int* deferred,
+                                              int& n_def) {
   unsigned spins = 0;
   for (;;) {
     const bool allow_rows = (uint32_t)(*done_count) == issued;
-    const int head = max(ld_relaxed(heads + q), hd.queue_begin[q]);
-    const int idx = head + w;
-    const bool in_range = idx < q_end;
-    bool claimed = true, ready = false;
-    if (in_range) {
-      claimed = ld_relaxed(claim + idx) != 0;
-      if (!claimed) {
-        const StepTask* t = hd.tasks + idx;
-        const int type = __ldg(&t->type);
-        ready = allow_rows || type == TASK_GEMM;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int cb = __ldg(&t->wait_begin[r]), ce = __ldg(&t->wait_end[r]), val = __ldg(&t->wait_val[r]);
-          for (int c = cb; c < ce && ready; ++c) ready = ld_acquire(hd.counters + c) >= val;
-        }
-      }
+    int cand = -1;
+    bool ready = false;
+    if (lane < kStepQueues) {
+      const int c = ld_relaxed(cursors + lane);
+      if (c < hd.queue_begin[lane + 1] - hd.queue_begin[lane]) cand = hd.queue_begin[lane] + c;
+    } else if (lane < kStepQueues + kStepDeferred) {
+      if (lane - kStepQueues < n_def) cand = deferred[lane - kStepQueues];
     }
-    // queue heads: skip the leading claimed entries of each window
-    const unsigned cl = __ballot_sync(0xffffffffu, claimed);
-    {
-      const unsigned mine = (cl >> (q * kQueueLanes)) & ((1u << kQueueLanes) - 1u);
-      const int lead = __ffs(~mine) - 1;                    // leading claimed entries (kQueueLanes when all are)
-      if (w == 0 && lead > 0 && head < q_end) atomicMax(heads + q, min(head + lead, q_end));
-    }
+    if (cand >= 0) ready = step_task_ready(hd, cand, allow_rows);
+    const unsigned open = __ballot_sync(0xffffffffu, cand >= 0);
     const unsigned rm = __ballot_sync(0xffffffffu, ready);
-    if (rm != 0u) {
-      const int pick = __ffs(rm) - 1;
-      int ok = 0;
-      if (lane == pick) ok = atomicCAS(claim + idx, 0, 1) == 0 ? 1 : 0;
-      ok = __shfl_sync(0xffffffffu, ok, pick);
-      const int t = __shfl_sync(0xffffffffu, idx, pick);
+    const unsigned rdef = rm >> kStepQueues;
+    if (rdef != 0u) {                                       // a parked task has become ready: oldest commitment first
+      const int k = __ffs(rdef) - 1;
+      const int t = deferred[k];
+      __syncwarp();
+      if (lane == 0) deferred[k] = deferred[n_def - 1];
+      --n_def;
+      __syncwarp();
+      return t;
+    }
+    const unsigned rq = rm & ((1u << kStepQueues) - 1u);
+    if (rq != 0u && n_def < kStepDeferred) {
+      const int q = __ffs(rq) - 1;
+      const int seen = __shfl_sync(0xffffffffu, cand, q);
+      int t = 0;
+      if (lane == 0) t = hd.queue_begin[q] + atomicAdd(cursors + q, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= hd.queue_begin[q + 1]) continue;             // the queue ran out between the look and the draw
+      if (t == seen) return t;
+      bool ok = false;
+      if (lane == 0) ok = step_task_ready(hd, t, allow_rows);
+      ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
       if (ok) return t;
+      if (lane == 0) deferred[n_def] = t;
+      ++n_def;
+      __syncwarp();
       continue;
     }
-    // nothing ready: finished?  (every queue's head at its end)
-    const unsigned open = __ballot_sync(0xffffffffu, head < q_end);
-    if (open == 0u) return -1;
-    __nanosleep(64);
+    if (open == 0u) return -1;                              // every queue drained, nothing parked
+    __nanosleep(32);
     if (++spins > (1u << 24)) __trap();                     // ~ seconds: a task graph that cannot complete
   }
 }
@@ -171,8 +190,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
   float* scratch = reinterpret_cast<float*>(smem + kStepStages * TC_STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tid = threadIdx.x;
-  int* const claim = hd.counters + hd.n_counters;
-  int* const heads = claim + hd.n_tasks;
+  int* const cursors = hd.counters + hd.n_counters;
+  __shared__ int deferred[kStepDeferred];
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -196,11 +215,12 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
 
   if (warp == 10) {
     // =========================== scheduler: claim ready tasks, stage them ===========================
+    int n_def = 0;
     for (uint32_t k = 0;; ++k) {
       const int s = (int)(k % kStepSlots);
       mbar_wait(&slot_empty[s], ((k / kStepSlots) & 1u) ^ 1u);
       StepSlot& sl = slots[s];
-      const int t = step_claim(hd, claim, heads, lane, &done_count, k);
+      const int t = step_next_task(hd, cursors, lane, &done_count, k, deferred, n_def);
       if (t < 0) {
         if (lane == 0) {
           sl.task.type = TASK_STOP;

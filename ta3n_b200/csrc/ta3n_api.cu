@@ -920,7 +920,7 @@ PlanLayout plan_layout(const BuiltPlan& B) {
   l.segs = put(B.segs.size() * sizeof(SegLite));
   l.jobs = put(B.jobs.size() * sizeof(WColsumJob));
   l.tail = put(sizeof(TailArgs));
-  l.counters = put((size_t)(B.n_counters + B.tasks.size() + kStepQueues) * sizeof(int));
+  l.counters = put((size_t)(B.n_counters + kStepQueues) * sizeof(int));
   l.total = off;
   return l;
 }
@@ -986,8 +986,8 @@ int ta3n_step_run(const void* handle_host, ta3n_stream_t stream) {
   memcpy(&h, handle_host, sizeof(h));
   TA3N_REQUIRE(h.magic == kStepMagic, "not a handle filled by ta3n_step_build");
   cudaStream_t st = S(stream);
-  // arrival counters, claim flags and queue heads
-  TA3N_CUDA(cudaMemsetAsync(h.hd.counters, 0, (size_t)(h.hd.n_counters + h.hd.n_tasks + kStepQueues) * sizeof(int), st));
+  // arrival counters and the queues' ticket cursors
+  TA3N_CUDA(cudaMemsetAsync(h.hd.counters, 0, (size_t)(h.hd.n_counters + kStepQueues) * sizeof(int), st));
   pre_launch("step_kernel", st);
   ta3n_step_kernel<<<h.grid, kStepThreads, h.smem_bytes, st>>>(h.hd);
   return after_launch();
@@ -1003,8 +1003,8 @@ size_t ta3n_step_describe(const ta3n_step_desc* desc, char* buf, size_t buf_byte
   int n_type[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long slabs = 0;
   int bad = 0;
-  // every wait must be satisfiable: the counter's total number of signals reaches the awaited value, and the
-  // dependency graph is acyclic (checked by simulating the scheduler: run whatever is ready until nothing is left)
+  // The queue orders must be consistent with the dependencies: a scheduler that only sees the head of every queue has
+  // to be able to finish (also proves that every awaited count is reached and the graph is acyclic).
   std::vector<int> total(B.n_counters, 0);
   for (const StepTask& t : B.tasks) {
     n_type[t.type]++;
@@ -1019,27 +1019,29 @@ size_t ta3n_step_describe(const ta3n_step_desc* desc, char* buf, size_t buf_byte
   }
   {
     std::vector<int> cnt(B.n_counters, 0);
-    std::vector<char> done(B.tasks.size(), 0);
+    int cur[kStepQueues];
+    for (int q = 0; q < kStepQueues; ++q) cur[q] = B.queue_begin[q];
     size_t left = B.tasks.size();
     bool progress = true;
-    while (left > 0 && progress) {
+    while (left > 0 && progress) {      // a scheduler that only ever sees the head of each queue
       progress = false;
-      for (size_t i = 0; i < B.tasks.size(); ++i) {
-        if (done[i]) continue;
-        const StepTask& t = B.tasks[i];
-        bool ready = true;
-        for (int r = 0; r < 2 && ready; ++r)
-          for (int c = t.wait_begin[r]; c < t.wait_end[r]; ++c)
-            if (c < 0 || c >= B.n_counters || cnt[c] < t.wait_val[r]) {
-              ready = false;
-              break;
-            }
-        if (!ready) continue;
-        done[i] = 1;
-        --left;
-        progress = true;
-        if (t.signal >= 0) cnt[t.signal]++;
-        if (t.signal2 >= 0) cnt[t.signal2]++;
+      for (int q = 0; q < kStepQueues; ++q) {
+        while (cur[q] < B.queue_begin[q + 1]) {
+          const StepTask& t = B.tasks[cur[q]];
+          bool ready = true;
+          for (int r = 0; r < 2 && ready; ++r)
+            for (int c = t.wait_begin[r]; c < t.wait_end[r]; ++c)
+              if (c < 0 || c >= B.n_counters || cnt[c] < t.wait_val[r]) {
+                ready = false;
+                break;
+              }
+          if (!ready) break;
+          ++cur[q];
+          --left;
+          progress = true;
+          if (t.signal >= 0) cnt[t.signal]++;
+          if (t.signal2 >= 0) cnt[t.signal2]++;
+        }
       }
     }
     bad = (int)left;

@@ -459,16 +459,17 @@ def test_fused_step_stream_options_do_not_change_results():
     params = orc.init_params(cfg, seed=1234)
     model = build_model(cfg, params, train=True)
     xs, xt, labels = orc.synthetic_batch(40, cfg)
-    base = TrainStep(model, 40, 40, (0.75, 0.75, 0.5), use_graph=True)
+    base = TrainStep(model, 40, 40, (0.75, 0.75, 0.5), use_graph=True, mode="legacy")
     l0 = base(xs, xt, labels).clone()
     g0 = base.flat_grad.clone()
-    alt = TrainStep(model, 40, 40, (0.75, 0.75, 0.5), use_graph=True, overlap_wgrad=True, parallel_branches=True)
+    alt = TrainStep(model, 40, 40, (0.75, 0.75, 0.5), use_graph=True, overlap_wgrad=True, parallel_branches=True,
+                    mode="legacy")
     l1 = alt(xs, xt, labels).clone()
     torch.cuda.synchronize()
     assert torch.equal(l0, l1)
     assert_close(alt.flat_grad, g0, 1e-6, "gradients with forked streams")
     # two-graph split used to overlap the early-bucket all-reduce under data parallelism
-    split = TrainStep(model, 40, 40, (0.75, 0.75, 0.5), use_graph=True, overlap_allreduce=True)
+    split = TrainStep(model, 40, 40, (0.75, 0.75, 0.5), use_graph=True, overlap_allreduce=True, mode="legacy")
     assert split.graphs[0][1] is not None
     l2 = split(xs, xt, labels).clone()
     l2 = split(xs, xt, labels).clone()
