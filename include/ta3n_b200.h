@@ -299,8 +299,9 @@ int ta3n_step_run(const void* handle_host, ta3n_stream_t stream);
  * tasks a simulated scheduler can never run -- must be 0: the dependency graph is acyclic and every awaited count is
  * reached).  No CUDA call.                                                                                          */
 size_t ta3n_step_describe(const ta3n_step_desc* desc, char* buf, size_t buf_bytes);
-/* Optional per-task trace: trace_dev (device, n_tasks * 4 uint64) receives {SM id, scheduled, accumulator ready, done}
- * (globaltimer ns) of every task of the following runs; NULL switches it off.  tools/step_trace.py reads it.        */
+/* Optional per-task trace: trace_dev (device, n_tasks * 8 uint64) receives {SM id | tag, started, accumulator ready,
+ * done, body done, CTA synced, 0, 0} (globaltimer ns) of every task of the following runs; NULL switches it off.
+ * tools/step_trace.py reads it.                                                                                     */
 int ta3n_step_set_trace(void* handle_host, unsigned long long* trace_dev);
 /* number of tasks / arrival counters of a built plan (diagnostics) */
 int ta3n_step_info(const void* handle_host, int* n_tasks, int* n_counters, int* n_gemm_tiles);

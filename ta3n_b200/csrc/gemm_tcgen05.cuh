@@ -385,14 +385,30 @@ __device__ __forceinline__ void add4(float4& a, const float4& b) {
   a.w += b.w;
 }
 
-template <int kEpiWarps>
-__device__ __forceinline__ void tc_epilogue_coalesced(const TileCtx& ctx, const int m0, const int n0, const int split,
-                                                      const int n_iter, const int mode, const uint32_t tmem_base,
-                                                      const int acc, const int ew, float* __restrict__ stage) {
+// CLS selects how much of the body exists (three copies instead of one per flag set):
+//   0 = plain: alpha * accumulator (+ split-K partials)          weight gradients, partial tiles, frame dgrad
+//   1 = forward: + bias, ReLU, dropout                            every forward layer
+//   2 = everything (run-time flags)                               the data-gradient tiles with auxiliary operands
+// The per-element work of the plain class is one multiply: with run-time flag tests inside the row loops it was
+// 1300 instructions per warp and tile (5 us at 2 warps per scheduler); the lean copies are ~250.
+enum : int { EPI_CLS_PLAIN = 0, EPI_CLS_FORWARD = 1, EPI_CLS_ALL = 2 };
+__device__ __forceinline__ int epi_class(const int mode, const int flags) {
+  if (mode == TILE_PARTIAL || flags == 0) return EPI_CLS_PLAIN;
+  if ((flags & ~(EPI_BIAS | EPI_RELU | EPI_DROP_MASK | EPI_DROP_RNG)) == 0) return EPI_CLS_FORWARD;
+  return EPI_CLS_ALL;
+}
+
+template <int kEpiWarps, int CLS>
+__device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0, const int n0, const int split,
+                                                const int n_iter, const int mode, const uint32_t tmem_base,
+                                                const int acc, const int ew, float* __restrict__ stage) {
   const int lane = threadIdx.x & 31;
   const int lq = (ew + 2) & 3;          // TMEM lane quarter this warp may access
   const Group& e = ctx.g;               // shared memory (the task slot)
-  const int f = mode == TILE_PARTIAL ? 0 : e.flags;
+  constexpr int kMask = CLS == EPI_CLS_PLAIN ? 0
+                        : CLS == EPI_CLS_FORWARD ? (EPI_BIAS | EPI_RELU | EPI_DROP_MASK | EPI_DROP_RNG)
+                                                 : ~0;
+  const int f = (mode == TILE_PARTIAL ? 0 : e.flags) & kMask;
   const int M = e.M, N = e.N;
   const bool split_out = mode == TILE_PARTIAL;
   const size_t plane = (size_t)M * N;
@@ -401,7 +417,7 @@ __device__ __forceinline__ void tc_epilogue_coalesced(const TileCtx& ctx, const 
   constexpr int kColChunks = (TC_BN / 32) * 4 / kEpiWarps;
   const int c0 = (ew / 4) * kColChunks;
   const int rq = lane >> 3, cq = lane & 7;
-  const int n_part = mode == TILE_OWNER ? e.ksplit - 1 : 0;
+  const int n_part = (CLS != EPI_CLS_ALL && mode == TILE_OWNER) ? e.ksplit - 1 : 0;      // no aux operands on split groups
   const float alpha = split_out ? 1.0f : (e.alpha_dev ? e.alpha * __ldg(e.alpha_dev) : e.alpha);
   const uint64_t step = (f & EPI_DROP_RNG) ? (e.step_dev ? *e.step_dev : 0ull) : 0ull;
   const bool drop_early = (f & (EPI_DROP_MASK | EPI_DROP_RNG)) && !(f & EPI_DROP_LATE);
@@ -551,6 +567,19 @@ __device__ __forceinline__ void tc_epilogue_coalesced(const TileCtx& ctx, const 
     }
   }
   tc_fence_before();
+}
+
+template <int kEpiWarps>
+__device__ __forceinline__ void tc_epilogue_coalesced(const TileCtx& ctx, const int m0, const int n0, const int split,
+                                                      const int n_iter, const int mode, const uint32_t tmem_base,
+                                                      const int acc, const int ew, float* __restrict__ stage) {
+  const int cls = epi_class(mode, ctx.g.flags);
+  if (cls == EPI_CLS_PLAIN)
+    tc_epilogue_cls<kEpiWarps, EPI_CLS_PLAIN>(ctx, m0, n0, split, n_iter, mode, tmem_base, acc, ew, stage);
+  else if (cls == EPI_CLS_FORWARD)
+    tc_epilogue_cls<kEpiWarps, EPI_CLS_FORWARD>(ctx, m0, n0, split, n_iter, mode, tmem_base, acc, ew, stage);
+  else
+    tc_epilogue_cls<kEpiWarps, EPI_CLS_ALL>(ctx, m0, n0, split, n_iter, mode, tmem_base, acc, ew, stage);
 }
 
 // Can the step kernel's epilogue take this group?  (see tc_epilogue_coalesced)

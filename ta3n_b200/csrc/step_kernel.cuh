@@ -68,7 +68,8 @@ struct StepHeader {
   int* counters;                 // [n_counters] arrival counters, then [kStepQueues] ticket cursors of the queues
   int queue_begin[kStepQueues + 1];   // tasks of queue q are [queue_begin[q], queue_begin[q + 1])
   unsigned long long* step_counter;   // dropout step counter, advanced by the FINISH task (may be null)
-  unsigned long long* trace;     // optional [n_tasks][4]: {sm id, scheduled, accumulator ready, done} (globaltimer ns)
+  unsigned long long* trace;     // optional [n_tasks][8]: {sm id | tag, started, accumulator ready, done, body done,
+                                 // CTA synced, -, -} (globaltimer ns)
 };
 
 struct StepSlot {                // one scheduled task: descriptor + (GEMM) the group and its segments
@@ -177,7 +178,7 @@ __device__ __forceinline__ int step_next_task(const StepHeader& hd, int* const c
   }
 }
 
-__global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid_constant__ StepHeader hd) {
+__global__ void __maxnreg__(184) ta3n_step_kernel(const __grid_constant__ StepHeader hd) {
   extern __shared__ uint8_t step_smem_raw[];
   __shared__ __align__(8) TcShared sh;
   __shared__ __align__(8) uint64_t slot_full[kStepSlots];
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
       const StepSlot& sl = slots[s];
       const int type = sl.task.type;
       if (type == TASK_STOP) break;
-      unsigned long long t_sched = 0, t_acc = 0;
+      unsigned long long t_sched = 0, t_acc = 0, t_body = 0, t_sync = 0;
       if (hd.trace && rt == 0) t_sched = global_ns();
       if (type == TASK_GEMM) {
         const int acc = (int)(tiles & 1u);
@@ -336,11 +337,13 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
       } else if (type == TASK_FINISH) {
         if (rt == 0 && hd.step_counter) hd.step_counter[0] += 1ull;
       }
+      if (hd.trace && rt == 0) t_body = global_ns();
       // ---- completion: every store of the task issued -> release its arrival counters ----
       const int sig = sl.task.signal, sig2 = sl.task.signal2, index = sl.index;
       const unsigned long long tag = ((unsigned long long)type << 16) | ((unsigned long long)(unsigned)sl.task.group << 24) |
                                      ((unsigned long long)sl.task.mode << 48) | ((unsigned long long)(unsigned)sl.n_iter << 52);
       row_sync();                        // every warp's stores are issued (CTA-scope order) ...
+      if (hd.trace && rt == 0) t_sync = global_ns();
       if (rt == 0) {
         if (sig >= 0 || sig2 >= 0) {
           __threadfence();               // ... one cumulative gpu-scope fence publishes them with the release below
@@ -350,11 +353,13 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
         }
         *reinterpret_cast<volatile int*>(&done_count) = (int)(k + 1);
         if (hd.trace) {
-          unsigned long long* tr = hd.trace + (size_t)index * 4;
+          unsigned long long* tr = hd.trace + (size_t)index * 8;
           tr[0] = (unsigned long long)sm_id() | tag;
           tr[1] = t_sched;
           tr[2] = t_acc;
           tr[3] = global_ns();
+          tr[4] = t_body;
+          tr[5] = t_sync;
         }
       }
       __syncwarp();

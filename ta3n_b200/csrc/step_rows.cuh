@@ -98,7 +98,94 @@ __device__ __forceinline__ LossNorm loss_norm(const TailArgs& a) {
 // frame logits (models.py:461), frame-level domain loss + its gradient (main.py:513-538), data gradient of the head
 // through the ReLU of the hidden layer: dHf = (g_frame W2f) * 1[hid_f > 0].  Depends on hid_f alone, so the whole frame
 // branch runs beside the video-level chain.
-__device__ __forceinline__ void frame_task(const TailArgs& a, const int r0, const int nr, const int tid) {
+template <int FV>      // F <= 128 * FV
+__device__ __forceinline__ void frame_task_t(const TailArgs& a, const int r0, const int nr, const int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int T = a.T, F = a.F, Bs = a.Bs;
+  const float* __restrict__ W2f = a.W2f;
+  const LossNorm ln = loss_norm(a);
+  const float b0 = __ldg(a.b2f), b1 = __ldg(a.b2f + 1);
+  constexpr int RW = kRowFrames / 8;                        // rows per warp, all in flight at once
+  float4 h[RW][FV];
+#pragma unroll
+  for (int j = 0; j < RW; ++j) {
+    const int it = warp + 8 * j;
+#pragma unroll
+    for (int kk = 0; kk < FV; ++kk) {
+      const int k = lane * 4 + 128 * kk;
+      h[j][kk] = (it < nr && k < F) ? __ldcg(reinterpret_cast<const float4*>(a.hid_f + ((size_t)r0 + it) * F + k))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float4 w0[FV], w1[FV];
+#pragma unroll
+  for (int kk = 0; kk < FV; ++kk) {
+    const int k = lane * 4 + 128 * kk;
+    w0[kk] = k < F ? __ldg(reinterpret_cast<const float4*>(W2f + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    w1[kk] = k < F ? __ldg(reinterpret_cast<const float4*>(W2f + F + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float s0[RW], s1[RW];
+#pragma unroll
+  for (int j = 0; j < RW; ++j) {
+    float x0 = 0.f, x1 = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < FV; ++kk) {
+      x0 = fmaf(h[j][kk].x, w0[kk].x, fmaf(h[j][kk].y, w0[kk].y, fmaf(h[j][kk].z, w0[kk].z, fmaf(h[j][kk].w, w0[kk].w, x0))));
+      x1 = fmaf(h[j][kk].x, w1[kk].x, fmaf(h[j][kk].y, w1[kk].y, fmaf(h[j][kk].z, w1[kk].z, fmaf(h[j][kk].w, w1[kk].w, x1))));
+    }
+    s0[j] = x0;
+    s1[j] = x1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < RW; ++j) {
+      s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], o);
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < RW; ++j) {
+    const int it = warp + 8 * j;
+    if (it >= nr) break;
+    const size_t row = (size_t)r0 + it;
+    const float p0 = s0[j] + b0, p1 = s1[j] + b1;
+    const int m = (int)(row / T);
+    const int dom = m >= Bs ? 1 : 0;
+    const bool real = dom ? (m - Bs < ln.vt) : (m < ln.vs);
+    float g0 = 0.f, g1 = 0.f, l = 0.f;
+    if (real && (a.loss_flags & LOSS_ADV_FRAME)) {
+      const float wd = dom ? a.dom_w1 : a.dom_w0;
+      const Attn2 x = attn_from_logits(p0, p1);
+      const float inv = wd / (ln.n_dom * (float)T);
+      l = -(dom ? x.lq1 : x.lq0) * inv;
+      g0 = (x.q0 - (dom ? 0.f : 1.f)) * inv;
+      g1 = (x.q1 - (dom ? 1.f : 0.f)) * inv;
+    }
+    if (lane == 0) {
+      a.pred_frame[row * 2] = p0;
+      a.pred_frame[row * 2 + 1] = p1;
+      a.g_frame[row * 2] = g0;
+      a.g_frame[row * 2 + 1] = g1;
+      a.frame_loss[row] = l;
+    }
+    float* __restrict__ dh = a.dHf + row * F;
+#pragma unroll
+    for (int kk = 0; kk < FV; ++kk) {
+      const int k = lane * 4 + 128 * kk;
+      if (k < F) {
+        float4 d;
+        d.x = h[j][kk].x > 0.f ? fmaf(g0, w0[kk].x, g1 * w1[kk].x) : 0.f;
+        d.y = h[j][kk].y > 0.f ? fmaf(g0, w0[kk].y, g1 * w1[kk].y) : 0.f;
+        d.z = h[j][kk].z > 0.f ? fmaf(g0, w0[kk].z, g1 * w1[kk].z) : 0.f;
+        d.w = h[j][kk].w > 0.f ? fmaf(g0, w0[kk].w, g1 * w1[kk].w) : 0.f;
+        *reinterpret_cast<float4*>(dh + k) = d;
+      }
+    }
+  }
+}
+// any F % 4 == 0, one row at a time (F > 512: fc_dim = 2048 runs)
+__device__ __forceinline__ void frame_task_any(const TailArgs& a, const int r0, const int nr, const int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   const int T = a.T, F = a.F, Bs = a.Bs;
   const float* __restrict__ W2f = a.W2f;
@@ -150,6 +237,13 @@ __device__ __forceinline__ void frame_task(const TailArgs& a, const int r0, cons
     }
   }
 }
+// the path has F = 512: all four rows of a warp in flight; wider layers take the row-at-a-time form
+__device__ __forceinline__ void frame_task(const TailArgs& a, const int r0, const int nr, const int tid) {
+  if (a.F <= 512)
+    frame_task_t<4>(a, r0, nr, tid);
+  else
+    frame_task_any(a, r0, nr, tid);
+}
 
 // The video-level row tasks give every video to ONE warp: lane l holds the feature elements 4l .. 4l+3 of each
 // 128-wide chunk of a length-H row (HV = H / 128 chunks), so the tasks need no shared memory and no block barrier.
@@ -194,52 +288,95 @@ __device__ __forceinline__ void relpool_task_t(const TailArgs& a, const int v0, 
   const size_t plane = (size_t)M * H;
   for (int v = warp; v < nv; v += 8) {
     const int m = v0 + v;
-    // relation logits from the discriminators' hidden layer -> attention weights; lane i keeps w_i + 1 of scale i
+    // relation logits from the discriminators' hidden layer -> attention weights; lane i keeps w_i + 1 of scale i.
+    // Four scales per round: their hidden rows are requested together (the task is a chain of L2 round trips otherwise)
     float wp1 = 1.0f;
-    for (int i = 0; i < R; ++i) {
-      const RowVec<HV> h = row_load_cg<HV>(a.hid_r + ((size_t)i * M + m) * H, lane);
-      const float* w = a.W2r.p[i];
-      const float s0 = row_dot<HV>(h, row_load_ro<HV>(w, lane)) + __ldg(a.b2r.p[i]);
-      const float s1 = row_dot<HV>(h, row_load_ro<HV>(w + H, lane)) + __ldg(a.b2r.p[i] + 1);
-      const float wi = a.use_attn ? attn_from_logits(s0, s1).w : 0.f;
-      const size_t o = (size_t)m * R + i;
-      if (lane == 0) {
-        a.pred_rel[o * 2] = s0;
-        a.pred_rel[o * 2 + 1] = s1;
-        if (a.use_attn) a.attn[o] = wi;
+    for (int i0 = 0; i0 < R; i0 += 4) {
+      RowVec<HV> h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (i0 + j < R) h[j] = row_load_cg<HV>(a.hid_r + ((size_t)(i0 + j) * M + m) * H, lane);
+      float s0[4], s1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s0[j] = s1[j] = 0.f;
+        if (i0 + j < R) {
+          const float* w = a.W2r.p[i0 + j];
+          const RowVec<HV> x0 = row_load_ro<HV>(w, lane), x1 = row_load_ro<HV>(w + H, lane);
+#pragma unroll
+          for (int kk = 0; kk < HV; ++kk) {
+            s0[j] = fmaf(h[j].c[kk].x, x0.c[kk].x, fmaf(h[j].c[kk].y, x0.c[kk].y, fmaf(h[j].c[kk].z, x0.c[kk].z, fmaf(h[j].c[kk].w, x0.c[kk].w, s0[j]))));
+            s1[j] = fmaf(h[j].c[kk].x, x1.c[kk].x, fmaf(h[j].c[kk].y, x1.c[kk].y, fmaf(h[j].c[kk].z, x1.c[kk].z, fmaf(h[j].c[kk].w, x1.c[kk].w, s1[j]))));
+          }
+        }
       }
-      if ((i & 31) == lane) wp1 = wi + 1.0f;      // R <= 32
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], o);
+          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j;
+        if (i >= R) break;
+        const float p0 = s0[j] + __ldg(a.b2r.p[i]), p1 = s1[j] + __ldg(a.b2r.p[i] + 1);
+        const float wi = a.use_attn ? attn_from_logits(p0, p1).w : 0.f;
+        const size_t o = (size_t)m * R + i;
+        if (lane == 0) {
+          a.pred_rel[o * 2] = p0;
+          a.pred_rel[o * 2 + 1] = p1;
+          if (a.use_attn) a.attn[o] = wi;
+        }
+        if ((i & 31) == lane) wp1 = wi + 1.0f;    // R <= 32
+      }
     }
     RowVec<HV> y;
 #pragma unroll
     for (int kk = 0; kk < HV; ++kk) y.c[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float first = 0.f;                            // feat_rel[m, i, 0] (placeholder attention output)
-    for (int i = 0; i < R; ++i) {
-      RowVec<HV> f;
+    for (int i0 = 0; i0 < R; i0 += 2) {           // two scales (up to six relation rows) in flight
+      RowVec<HV> x[2][3];
 #pragma unroll
-      for (int kk = 0; kk < HV; ++kk) f.c[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = a.map.rel_begin[i]; q < a.map.rel_begin[i + 1]; ++q) {
-        const RowVec<HV> x = row_load_cg<HV>(a.act + q * plane + (size_t)m * H, lane);
+      for (int j = 0; j < 2; ++j) {
+        const int i = i0 + j;
+        if (i >= R) break;
+        const int qb = a.map.rel_begin[i], qn = a.map.rel_begin[i + 1] - qb;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          if (r < qn) x[j][r] = row_load_cg<HV>(a.act + (qb + r) * plane + (size_t)m * H, lane);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int i = i0 + j;
+        if (i >= R) break;
+        const int qn = a.map.rel_begin[i + 1] - a.map.rel_begin[i];
+        RowVec<HV> f = x[j][0];
+#pragma unroll
+        for (int r = 1; r < 3; ++r)
+          if (r < qn) {
+#pragma unroll
+            for (int kk = 0; kk < HV; ++kk) {
+              f.c[kk].x += x[j][r].c[kk].x;
+              f.c[kk].y += x[j][r].c[kk].y;
+              f.c[kk].z += x[j][r].c[kk].z;
+              f.c[kk].w += x[j][r].c[kk].w;
+            }
+          }
+        row_store<HV>(a.feat_rel + ((size_t)m * R + i) * H, lane, f);
+        const float wi = __shfl_sync(0xffffffffu, wp1, i & 31);
 #pragma unroll
         for (int kk = 0; kk < HV; ++kk) {
-          f.c[kk].x += x.c[kk].x;
-          f.c[kk].y += x.c[kk].y;
-          f.c[kk].z += x.c[kk].z;
-          f.c[kk].w += x.c[kk].w;
+          y.c[kk].x = fmaf(wi, f.c[kk].x, y.c[kk].x);
+          y.c[kk].y = fmaf(wi, f.c[kk].y, y.c[kk].y);
+          y.c[kk].z = fmaf(wi, f.c[kk].z, y.c[kk].z);
+          y.c[kk].w = fmaf(wi, f.c[kk].w, y.c[kk].w);
         }
-      }
-      row_store<HV>(a.feat_rel + ((size_t)m * R + i) * H, lane, f);
-      const float wi = __shfl_sync(0xffffffffu, wp1, i & 31);
-#pragma unroll
-      for (int kk = 0; kk < HV; ++kk) {
-        y.c[kk].x = fmaf(wi, f.c[kk].x, y.c[kk].x);
-        y.c[kk].y = fmaf(wi, f.c[kk].y, y.c[kk].y);
-        y.c[kk].z = fmaf(wi, f.c[kk].z, y.c[kk].z);
-        y.c[kk].w = fmaf(wi, f.c[kk].w, y.c[kk].w);
-      }
-      if (!a.use_attn) {                          // models.py:647 placeholder output: feat_rel[:, :, 0]
-        first = __shfl_sync(0xffffffffu, f.c[0].x, 0);
-        if (lane == 0) a.attn[(size_t)m * R + i] = first;
+        if (!a.use_attn) {                        // models.py:647 placeholder output: feat_rel[:, :, 0]
+          const float first = __shfl_sync(0xffffffffu, f.c[0].x, 0);
+          if (lane == 0) a.attn[(size_t)m * R + i] = first;
+        }
       }
     }
     row_store<HV>(a.feat_video + (size_t)m * H, lane, y);
@@ -276,15 +413,36 @@ __device__ __forceinline__ void heads_task_t(const TailArgs& a, const int v0, co
     const bool real = dom ? (m - Bs < ln.vt) : (m < ln.vs);
     const RowVec<HV> d = row_load_cg<HV>(a.dropped + (size_t)m * H, lane);
     const RowVec<HV> hv = row_load_cg<HV>(a.hid_v + (size_t)m * H, lane);
+    const int y_lab = (m < Bs) ? (int)a.labels[m] : -1;    // requested early: off the critical chain below
     float pv[CV];
 #pragma unroll
     for (int j = 0; j < CV; ++j) pv[j] = -INFINITY;
-    for (int c = 0; c < C; ++c) {
-      const float s = row_dot<HV>(d, row_load_ro<HV>(a.Wc + (size_t)c * H, lane)) + __ldg(a.bc + c);
-      if ((c & 31) == lane) {
+    for (int c0 = 0; c0 < C; c0 += 4) {                     // four classes per round: their reductions interleave
+      float part[4];
 #pragma unroll
-        for (int j = 0; j < CV; ++j)
-          if (j == (c >> 5)) pv[j] = s;
+      for (int j = 0; j < 4; ++j) {
+        part[j] = 0.f;
+        if (c0 + j < C) {
+          const RowVec<HV> w = row_load_ro<HV>(a.Wc + (size_t)(c0 + j) * H, lane);
+#pragma unroll
+          for (int kk = 0; kk < HV; ++kk)
+            part[j] = fmaf(d.c[kk].x, w.c[kk].x, fmaf(d.c[kk].y, w.c[kk].y, fmaf(d.c[kk].z, w.c[kk].z, fmaf(d.c[kk].w, w.c[kk].w, part[j]))));
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) part[j] += __shfl_xor_sync(0xffffffffu, part[j], o);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j;
+        if (c < C && (c & 31) == lane) {
+          const float sres = part[j] + __ldg(a.bc + c);
+#pragma unroll
+          for (int jj = 0; jj < CV; ++jj)
+            if (jj == (c >> 5)) pv[jj] = sres;
+        }
       }
     }
     const RowVec<HV> w2v0 = row_load_ro<HV>(a.W2v, lane), w2v1 = row_load_ro<HV>(a.W2v + H, lane);
@@ -327,7 +485,7 @@ __device__ __forceinline__ void heads_task_t(const TailArgs& a, const int v0, co
       const Attn2 dv = attn_from_logits(pd0, pd1);
       const bool att = (a.loss_flags & LOSS_ATT_ENT) != 0;
       const float att_scale = att ? a.gamma / ln.n_all : 0.f;
-      const int y = (m < Bs) ? (int)a.labels[m] : -1;
+      const int y = y_lab;
       const float wy = (m < Bs) ? (a.class_weight ? __ldg(a.class_weight + y) : 1.f) : 0.f;
 #pragma unroll
       for (int j = 0; j < CV; ++j) {
@@ -416,31 +574,49 @@ __device__ __forceinline__ void relbwd_task_t(const TailArgs& a, const int v0, c
   for (int v = warp; v < nv; v += 8) {
     const int m = v0 + v;
     const RowVec<HV> G = row_load_cg<HV>(a.G + (size_t)m * H, lane);
-    for (int i = 0; i < R; ++i) {
-      const size_t o = (size_t)m * R + i;
-      float pt0 = __ldcg(a.g_rel + o * 2), pt1 = __ldcg(a.g_rel + o * 2 + 1);
-      if (a.use_attn) {
-        const float dw = row_dot<HV>(G, row_load_cg<HV>(a.feat_rel + o * H, lane));
-        const Attn2 x = attn_from_logits(__ldcg(a.pred_rel + o * 2), __ldcg(a.pred_rel + o * 2 + 1));
-        pt0 += dw * x.q0 * (x.lq0 + x.ent);
-        pt1 += dw * x.q1 * (x.lq1 + x.ent);
-      }
-      if (lane == 0) {
-        a.Pt[o * 2] = pt0;
-        a.Pt[o * 2 + 1] = pt1;
-      }
-      const float* w = a.W2r.p[i];
-      const RowVec<HV> h = row_load_cg<HV>(a.hid_r + ((size_t)i * M + m) * H, lane);
-      const RowVec<HV> x0 = row_load_ro<HV>(w, lane), x1 = row_load_ro<HV>(w + H, lane);
-      RowVec<HV> d;
+    for (int i0 = 0; i0 < R; i0 += 2) {             // two scales in flight: every load of the pair before the first use
+      RowVec<HV> fr[2], h[2];
+      float gr0[2], gr1[2], pr0[2], pr1[2];
 #pragma unroll
-      for (int kk = 0; kk < HV; ++kk) {
-        d.c[kk].x = h.c[kk].x > 0.f ? fmaf(pt0, x0.c[kk].x, pt1 * x1.c[kk].x) : 0.f;
-        d.c[kk].y = h.c[kk].y > 0.f ? fmaf(pt0, x0.c[kk].y, pt1 * x1.c[kk].y) : 0.f;
-        d.c[kk].z = h.c[kk].z > 0.f ? fmaf(pt0, x0.c[kk].z, pt1 * x1.c[kk].z) : 0.f;
-        d.c[kk].w = h.c[kk].w > 0.f ? fmaf(pt0, x0.c[kk].w, pt1 * x1.c[kk].w) : 0.f;
+      for (int j = 0; j < 2; ++j) {
+        const int i = i0 + j;
+        if (i >= R) break;
+        const size_t o = (size_t)m * R + i;
+        gr0[j] = __ldcg(a.g_rel + o * 2);
+        gr1[j] = __ldcg(a.g_rel + o * 2 + 1);
+        pr0[j] = __ldcg(a.pred_rel + o * 2);
+        pr1[j] = __ldcg(a.pred_rel + o * 2 + 1);
+        if (a.use_attn) fr[j] = row_load_cg<HV>(a.feat_rel + o * H, lane);
+        h[j] = row_load_cg<HV>(a.hid_r + ((size_t)i * M + m) * H, lane);
       }
-      row_store<HV>(a.dHid + ((size_t)i * M + m) * H, lane, d);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int i = i0 + j;
+        if (i >= R) break;
+        const size_t o = (size_t)m * R + i;
+        float pt0 = gr0[j], pt1 = gr1[j];
+        if (a.use_attn) {
+          const float dw = row_dot<HV>(G, fr[j]);
+          const Attn2 x = attn_from_logits(pr0[j], pr1[j]);
+          pt0 += dw * x.q0 * (x.lq0 + x.ent);
+          pt1 += dw * x.q1 * (x.lq1 + x.ent);
+        }
+        if (lane == 0) {
+          a.Pt[o * 2] = pt0;
+          a.Pt[o * 2 + 1] = pt1;
+        }
+        const float* w = a.W2r.p[i];
+        const RowVec<HV> x0 = row_load_ro<HV>(w, lane), x1 = row_load_ro<HV>(w + H, lane);
+        RowVec<HV> d;
+#pragma unroll
+        for (int kk = 0; kk < HV; ++kk) {
+          d.c[kk].x = h[j].c[kk].x > 0.f ? fmaf(pt0, x0.c[kk].x, pt1 * x1.c[kk].x) : 0.f;
+          d.c[kk].y = h[j].c[kk].y > 0.f ? fmaf(pt0, x0.c[kk].y, pt1 * x1.c[kk].y) : 0.f;
+          d.c[kk].z = h[j].c[kk].z > 0.f ? fmaf(pt0, x0.c[kk].z, pt1 * x1.c[kk].z) : 0.f;
+          d.c[kk].w = h[j].c[kk].w > 0.f ? fmaf(pt0, x0.c[kk].w, pt1 * x1.c[kk].w) : 0.f;
+        }
+        row_store<HV>(a.dHid + ((size_t)i * M + m) * H, lane, d);
+      }
     }
   }
 }

@@ -370,11 +370,11 @@ class TrainStep:
 
     def trace(self, enable: bool = True):
         """Fused mode, eager or before capture: record {SM, scheduled, accumulator ready, done} per task of the step
-        kernel (ta3n_step_set_trace).  Returns the device tensor (n_tasks, 4) int64 the kernel fills."""
+        kernel (ta3n_step_set_trace).  Returns the device tensor (n_tasks, 8) int64 the kernel fills."""
         lib = _lib.load()
         n_tasks = self.step_info()[0]
         if not hasattr(self, "_trace_buf"):
-            self._trace_buf = torch.zeros(n_tasks, 4, device=self.device, dtype=torch.int64)
+            self._trace_buf = torch.zeros(n_tasks, 8, device=self.device, dtype=torch.int64)
         for h in self.step_handles:
             if h is not None:
                 check(lib.ta3n_step_set_trace(h, _P(self._trace_buf) if enable else None))

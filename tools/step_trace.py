@@ -33,7 +33,7 @@ flush.fill_(1)
 step.run()
 torch.cuda.synchronize()
 t = tr.cpu()
-tag, sched, acc, done = t[:, 0], t[:, 1], t[:, 2], t[:, 3]
+tag, sched, acc, done, body, synced = t[:, 0], t[:, 1], t[:, 2], t[:, 3], t[:, 4], t[:, 5]
 sm = tag & 0xFFFF
 typ = (tag >> 16) & 0xFF
 grp = (tag >> 24) & 0xFFFFFF
@@ -58,12 +58,14 @@ for k, nm in names.items():
     print(f"  {nm:14s} n={int(sel.sum()):5d}  busy {dur.sum():9.1f} us  avg {dur.mean():6.2f}  max {dur.max():6.2f}{extra}")
 print(f"  epilogue-warp busy fraction: {busy_total / (span * len(set(sm.tolist()))):.2f}")
 # per GEMM group: when did it start / end (relative), tiles, avg duration
-print("  group  tiles  slabs/tile  first_start  last_end   avg_dur  acc_wait  epilogue (us)")
+print("  group  tiles  slabs/tile  first_start  last_end   avg_dur  acc_wait  epilogue = body + sync + publish (us)")
 for gidx in sorted(set(grp[typ == 0].tolist())):
     sel = (typ == 0) & (grp == gidx)
     print(f"  {gidx:5d}  {int(sel.sum()):5d}  {float(nit[sel].double().mean()):9.1f}  {(int(sched[sel].min()) - t0) / 1e3:10.1f}  "
           f"{(int(done[sel].max()) - t0) / 1e3:9.1f}  {float((done[sel] - sched[sel]).double().mean()) / 1e3:8.2f}"
-          f"  {float((acc[sel] - sched[sel]).double().mean()) / 1e3:8.2f}  {float((done[sel] - acc[sel]).double().mean()) / 1e3:8.2f}")
+          f"  {float((acc[sel] - sched[sel]).double().mean()) / 1e3:8.2f}  {float((done[sel] - acc[sel]).double().mean()) / 1e3:8.2f}"
+          f"  {float((body[sel] - acc[sel]).double().mean()) / 1e3:6.2f} {float((synced[sel] - body[sel]).double().mean()) / 1e3:6.2f}"
+          f" {float((done[sel] - synced[sel]).double().mean()) / 1e3:6.2f}")
 for k in (6, 2, 3):
     sel = typ == k
     if sel.sum():
