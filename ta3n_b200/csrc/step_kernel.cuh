@@ -178,7 +178,7 @@ __device__ __forceinline__ int step_next_task(const StepHeader& hd, int* const c
   }
 }
 
-__global__ void __maxnreg__(184) ta3n_step_kernel(const __grid_constant__ StepHeader hd) {
+__global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid_constant__ StepHeader hd) {
   extern __shared__ uint8_t step_smem_raw[];
   __shared__ __align__(8) TcShared sh;
   __shared__ __align__(8) uint64_t slot_full[kStepSlots];
