@@ -377,6 +377,14 @@ __device__ __forceinline__ void tc_epilogue(const TileCtx& ctx, const int m0, co
 constexpr int TC_STAGE_LD = 36;
 constexpr int TC_EPI_STAGE_FLOATS = 32 * TC_STAGE_LD;      // per epilogue warp
 
+__device__ __forceinline__ void sts4(uint32_t saddr, const float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void add4(float4& a, const float4& b) {
   a.x += b.x;
@@ -401,7 +409,7 @@ __device__ __forceinline__ int epi_class(const int mode, const int flags) {
 template <int kEpiWarps, int CLS>
 __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0, const int n0, const int split,
                                                 const int n_iter, const int mode, const uint32_t tmem_base,
-                                                const int acc, const int ew, float* __restrict__ stage) {
+                                                const int acc, const int ew, const uint32_t stage) {
   const int lane = threadIdx.x & 31;
   const int lq = (ew + 2) & 3;          // TMEM lane quarter this warp may access
   const Group& e = ctx.g;               // shared memory (the task slot)
@@ -435,7 +443,7 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
       __syncwarp();                     // the previous chunk's readers are done with the staging tile
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(stage + lane * TC_STAGE_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        sts4(stage + (uint32_t)(lane * TC_STAGE_LD + j) * 4u, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
       __syncwarp();
     }
     const int n = n0 + c * 32 + cq * 4;
@@ -453,7 +461,7 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
         const int r = (half * 4 + u) * 4 + rq;            // row of the chunk
         rows[u] = m0 + lq * 32 + r;
         ok[u] = rows[u] < M;
-        q[u] = *reinterpret_cast<const float4*>(stage + r * TC_STAGE_LD + cq * 4);
+        q[u] = lds4(stage + (uint32_t)(r * TC_STAGE_LD + cq * 4) * 4u);
       }
       // ---- every load of the batch first ----
 #pragma unroll
@@ -506,8 +514,15 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
               df[3] = k.w ? e.drop_scale : 0.f;
             } else {
               const uint64_t base = e.rng_offset + m * (uint64_t)N + (uint64_t)n;
+              if ((base & 3ull) == 0) {                     // the quad shares one hash (always, on the path's shapes)
+                const uint64_t hsh = rng_hash4(e.seed, step, base >> 2);
+                const uint32_t thr = rng_threshold(e.drop_p);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) df[i] = rng_keep(e.seed, step, base + i, e.drop_p) ? e.drop_scale : 0.f;
+                for (int i = 0; i < 4; ++i) df[i] = rng_keep_bits(hsh, i, thr) ? e.drop_scale : 0.f;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) df[i] = rng_keep(e.seed, step, base + i, e.drop_p) ? e.drop_scale : 0.f;
+              }
             }
             if (drop_late && (f & EPI_ADDROW)) {
               ev[0] = fmaf(rs[u], x0[u].x, ev[0]);
@@ -567,19 +582,6 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
     }
   }
   tc_fence_before();
-}
-
-template <int kEpiWarps>
-__device__ __forceinline__ void tc_epilogue_coalesced(const TileCtx& ctx, const int m0, const int n0, const int split,
-                                                      const int n_iter, const int mode, const uint32_t tmem_base,
-                                                      const int acc, const int ew, float* __restrict__ stage) {
-  const int cls = epi_class(mode, ctx.g.flags);
-  if (cls == EPI_CLS_PLAIN)
-    tc_epilogue_cls<kEpiWarps, EPI_CLS_PLAIN>(ctx, m0, n0, split, n_iter, mode, tmem_base, acc, ew, stage);
-  else if (cls == EPI_CLS_FORWARD)
-    tc_epilogue_cls<kEpiWarps, EPI_CLS_FORWARD>(ctx, m0, n0, split, n_iter, mode, tmem_base, acc, ew, stage);
-  else
-    tc_epilogue_cls<kEpiWarps, EPI_CLS_ALL>(ctx, m0, n0, split, n_iter, mode, tmem_base, acc, ew, stage);
 }
 
 // Can the step kernel's epilogue take this group?  (see tc_epilogue_coalesced)

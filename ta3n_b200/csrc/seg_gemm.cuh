@@ -175,8 +175,18 @@ __device__ __forceinline__ void drop_row32(const Group& g, const int f, int m, i
   if (f & EPI_DROP_RNG) {
     const uint64_t step = g.step_dev ? *g.step_dev : 0ull;
     const uint64_t base = g.rng_offset + (uint64_t)m * (uint64_t)g.N + (uint64_t)nb;
+    if ((base & 3ull) == 0) {
+      const uint32_t thr = rng_threshold(g.drop_p);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = rng_keep(g.seed, step, base + j, g.drop_p) ? v[j] * g.drop_scale : 0.0f;
+      for (int j = 0; j < 32; j += 4) {
+        const uint64_t hsh = rng_hash4(g.seed, step, (base + j) >> 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[j + i] = rng_keep_bits(hsh, i, thr) ? v[j + i] * g.drop_scale : 0.0f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = rng_keep(g.seed, step, base + j, g.drop_p) ? v[j] * g.drop_scale : 0.0f;
+    }
   }
 }
 

@@ -49,6 +49,8 @@ struct StepTask {
   int wait_begin[2], wait_end[2], wait_val[2];     // wait until counters[i] >= val for i in [begin, end)
   int signal;             // counter bumped on completion (-1: none)
   int signal2;            // second counter (the stage total; -1: none)
+  int urgent;             // on the latency-critical chain: only an otherwise idle CTA may take it (no queueing behind
+                          // tiles the CTA has already committed to)
 };
 static_assert(sizeof(StepTask) % 4 == 0 && sizeof(StepTask) / 4 <= 32, "staged by one warp");
 
@@ -100,16 +102,38 @@ __device__ __forceinline__ unsigned sm_id() {
   return v;
 }
 
+// Task slots in file-scope shared memory, so that the out-of-line epilogue below reads its group with LDS
+__shared__ StepSlot g_slots[kStepSlots];
+
+// The tile epilogue of slot s, one out-of-line copy per class (own register allocation, see step_rows.cuh)
+template <int CLS>
+__device__ __noinline__ void step_epilogue_cls(const int s, const uint32_t tmem_base, const int acc, const int ew,
+                                               const uint32_t stage) {
+  const StepSlot& sl = g_slots[s];
+  tc_epilogue_cls<8, CLS>(sl.ctx, sl.task.m0, sl.task.n0, sl.task.split, sl.n_iter, sl.task.mode, tmem_base, acc, ew, stage);
+}
+__device__ __forceinline__ void step_epilogue(const int s, const uint32_t tmem_base, const int acc, const int ew,
+                                              const uint32_t stage) {
+  const int cls = epi_class(g_slots[s].task.mode, g_slots[s].ctx.g.flags);
+  if (cls == EPI_CLS_PLAIN)
+    step_epilogue_cls<EPI_CLS_PLAIN>(s, tmem_base, acc, ew, stage);
+  else if (cls == EPI_CLS_FORWARD)
+    step_epilogue_cls<EPI_CLS_FORWARD>(s, tmem_base, acc, ew, stage);
+  else
+    step_epilogue_cls<EPI_CLS_ALL>(s, tmem_base, acc, ew, stage);
+}
+
 __device__ __forceinline__ int ld_relaxed(const int* p) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
-// Is task `idx` runnable by this CTA now?  (arrival counters reached; row-type tasks only when `allow_rows`)
-__device__ __forceinline__ bool step_task_ready(const StepHeader& hd, const int idx, const bool allow_rows) {
+// Is task `idx` runnable by this CTA now?  (arrival counters reached; row-type and urgent tasks only when the CTA is
+// idle: they must not queue behind tiles it has already committed to)
+__device__ __forceinline__ bool step_task_ready(const StepHeader& hd, const int idx, const bool idle) {
   const StepTask* t = hd.tasks + idx;
-  if (!allow_rows && __ldg(&t->type) != TASK_GEMM) return false;
+  if (!idle && (__ldg(&t->type) != TASK_GEMM || __ldg(&t->urgent) != 0)) return false;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int cb = __ldg(&t->wait_begin[r]), ce = __ldg(&t->wait_end[r]), val = __ldg(&t->wait_val[r]);
@@ -125,14 +149,18 @@ constexpr int kStepDeferred = 8;      // tickets a CTA may hold for tasks that w
 // CTAs ever contend for the same task) only after seeing that the task at the cursor is READY.  When several CTAs draw
 // at once the later tickets belong to tasks nobody has checked: such a task, if not ready, is parked in the CTA's
 // deferred list and polled with the queue heads -- the CTA never blocks on it and keeps taking other work.
-// `allow_rows`: row / column-sum tasks run only when the CTA has nothing else in flight (a row task queued behind
-// another task would wait for it while other SMs idle).  Returns the task index, or -1 when every queue is drained.
+// Row / column-sum tasks and the GEMM tiles of the latency-critical chains (`urgent`) are taken only by a CTA with
+// nothing else in flight: queued behind tiles a CTA has committed to they would wait while other SMs idle.  One CTA
+// in four is RESERVED for the spine and the chains: it ignores the filler queue until every other queue is drained,
+// so that a chain task that becomes ready finds an idle SM instead of waiting for a filler tile to finish.
+// Returns the task index, or -1 when every queue is drained.
 __device__ __forceinline__ int step_next_task(const StepHeader& hd, int* const cursors, const int lane,
                                               const volatile int* done_count, const uint32_t issued, int* deferred,
                                               int& n_def) {
   unsigned spins = 0;
   for (;;) {
     const bool allow_rows = (uint32_t)(*done_count) == issued;
+    const bool reserved = (blockIdx.x & 3u) == 0u;
     int cand = -1;
     bool ready = false;
     if (lane < kStepQueues) {
@@ -141,8 +169,9 @@ __device__ __forceinline__ int step_next_task(const StepHeader& hd, int* const c
     } else if (lane < kStepQueues + kStepDeferred) {
       if (lane - kStepQueues < n_def) cand = deferred[lane - kStepQueues];
     }
-    if (cand >= 0) ready = step_task_ready(hd, cand, allow_rows);
     const unsigned open = __ballot_sync(0xffffffffu, cand >= 0);
+    if (reserved && lane == kStepQueues - 1 && (open & ((1u << (kStepQueues - 1)) - 1u)) != 0u) cand = -1;
+    if (cand >= 0) ready = step_task_ready(hd, cand, allow_rows);
     const unsigned rm = __ballot_sync(0xffffffffu, ready);
     const unsigned rdef = rm >> kStepQueues;
     if (rdef != 0u) {                                       // a parked task has become ready: oldest commitment first
@@ -183,9 +212,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
   __shared__ __align__(8) TcShared sh;
   __shared__ __align__(8) uint64_t slot_full[kStepSlots];
   __shared__ __align__(8) uint64_t slot_empty[kStepSlots];
-  __shared__ StepSlot slots[kStepSlots];
-  __shared__ TailArgs tail;
-  __shared__ WColsumJob job;
+  StepSlot* const slots = g_slots;
   __shared__ int done_count;            // tasks this CTA has completed (scheduler: is anything still in flight?)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(step_smem_raw) + 1023) & ~uintptr_t(1023));
   float* scratch = reinterpret_cast<float*>(smem + kStepStages * TC_STAGE_BYTES);
@@ -206,7 +233,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
   }
   if (warp == 1) tmem_alloc(&sh.tmem_slot, kStepTmemCols);
   for (int i = tid; i < (int)(sizeof(TailArgs) / sizeof(int)); i += kStepThreads)
-    reinterpret_cast<int*>(&tail)[i] = reinterpret_cast<const int*>(hd.tail)[i];
+    reinterpret_cast<int*>(&g_tail)[i] = reinterpret_cast<const int*>(hd.tail)[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -315,25 +342,24 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
           tc_fence_after();
         }
         if (hd.trace && rt == 0) t_acc = global_ns();
-        tc_epilogue_coalesced<8>(sl.ctx, sl.task.m0, sl.task.n0, sl.task.split, sl.n_iter, sl.task.mode, tmem_base, acc,
-                                 ew, scratch + ew * TC_EPI_STAGE_FLOATS);
+        step_epilogue(s, tmem_base, acc, ew, smem_u32(scratch + ew * TC_EPI_STAGE_FLOATS));
         if (sl.n_iter > 0) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&sh.tmem_empty_bar[acc]);      // this warp's TMEM reads are done
           ++tiles;
         }
       } else if (type == TASK_FRAME) {
-        frame_task(tail, sl.task.m0, sl.task.n0, rt);
+        frame_task(sl.task.m0, sl.task.n0, rt);
       } else if (type == TASK_ROW) {
-        video_row_task(sl.task.mode, tail, sl.task.m0, sl.task.n0, rt);
+        video_row_task(sl.task.mode, sl.task.m0, sl.task.n0, rt);
       } else if (type == TASK_COLSUM_PART || type == TASK_COLSUM_REDUCE) {
         for (int i = rt; i < (int)(sizeof(WColsumJob) / sizeof(int)); i += kRowThreads)
-          reinterpret_cast<int*>(&job)[i] = __ldg(reinterpret_cast<const int*>(hd.jobs + sl.task.group) + i);
+          reinterpret_cast<int*>(&g_job)[i] = __ldg(reinterpret_cast<const int*>(hd.jobs + sl.task.group) + i);
         row_sync();
         if (type == TASK_COLSUM_PART)
-          colsum_part_task(job, scratch, sl.task.m0, sl.task.n0, rt);
+          colsum_part_task(scratch, sl.task.m0, sl.task.n0, rt);
         else
-          colsum_reduce_task(job, rt);
+          colsum_reduce_task(rt);
       } else if (type == TASK_FINISH) {
         if (rt == 0 && hd.step_counter) hd.step_counter[0] += 1ull;
       }
@@ -376,38 +402,42 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
 
 // ---- stand-alone row kernels of the phased executor --------------------------------------------------------
 __global__ void __launch_bounds__(kRowThreads) frame_row_kernel(const __grid_constant__ TailArgs a) {
+  for (int i = threadIdx.x; i < (int)(sizeof(TailArgs) / sizeof(int)); i += kRowThreads)
+    reinterpret_cast<int*>(&g_tail)[i] = reinterpret_cast<const int*>(&a)[i];
+  __syncthreads();
   pdl_wait();
   const int r0 = blockIdx.x * kRowFrames;
   const int nr = min(kRowFrames, a.M * a.T - r0);
-  if (nr > 0) frame_task(a, r0, nr, threadIdx.x);
+  if (nr > 0) frame_task(r0, nr, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(kRowThreads) video_row_kernel(const __grid_constant__ TailArgs a, const int kind) {
+  for (int i = threadIdx.x; i < (int)(sizeof(TailArgs) / sizeof(int)); i += kRowThreads)
+    reinterpret_cast<int*>(&g_tail)[i] = reinterpret_cast<const int*>(&a)[i];
+  __syncthreads();
   pdl_wait();
   const int v0 = blockIdx.x * kRowVideos;
   const int nv = min(kRowVideos, a.M - v0);
-  if (nv > 0) video_row_task(kind, a, v0, nv, threadIdx.x);
+  if (nv > 0) video_row_task(kind, v0, nv, threadIdx.x);
 }
 
 // column sums of the phased executor: the same task functions, (job, column block, row split) from the block index
 __global__ void __launch_bounds__(kRowThreads) step_colsum_part_kernel(const __grid_constant__ WColsumTable tab) {
   __shared__ __align__(16) float red_sm[8 * 33 * 4];
-  __shared__ WColsumJob j;
   pdl_wait();
   for (int i = threadIdx.x; i < (int)(sizeof(WColsumJob) / sizeof(int)); i += kRowThreads)
-    reinterpret_cast<int*>(&j)[i] = reinterpret_cast<const int*>(&tab.job[blockIdx.y])[i];
+    reinterpret_cast<int*>(&g_job)[i] = reinterpret_cast<const int*>(&tab.job[blockIdx.y])[i];
   __syncthreads();
-  colsum_part_task(j, red_sm, blockIdx.x, blockIdx.z, threadIdx.x);
+  colsum_part_task(red_sm, blockIdx.x, blockIdx.z, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(kRowThreads)
 step_colsum_reduce_kernel(const __grid_constant__ WColsumTable tab, unsigned long long* step_counter) {
-  __shared__ WColsumJob j;
   pdl_wait();
   for (int i = threadIdx.x; i < (int)(sizeof(WColsumJob) / sizeof(int)); i += kRowThreads)
-    reinterpret_cast<int*>(&j)[i] = reinterpret_cast<const int*>(&tab.job[blockIdx.x])[i];
+    reinterpret_cast<int*>(&g_job)[i] = reinterpret_cast<const int*>(&tab.job[blockIdx.x])[i];
   __syncthreads();
-  colsum_reduce_task(j, threadIdx.x);
+  colsum_reduce_task(threadIdx.x);
   if (step_counter && blockIdx.x == 0 && threadIdx.x == 0) step_counter[0] += 1ull;   // last launch of the step
 }
 

@@ -1009,6 +1009,7 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
   B->tasks.clear();
   for (int q = 0; q < kStepQueues; ++q) {
     B->queue_begin[q] = (int)B->tasks.size();
+    for (StepTask& t : queue[q]) t.urgent = (q >= 1 && q <= kStepQueues - 2) ? 1 : 0;      // the row-block chains
     B->tasks.insert(B->tasks.end(), queue[q].begin(), queue[q].end());
   }
   B->queue_begin[kStepQueues] = (int)B->tasks.size();

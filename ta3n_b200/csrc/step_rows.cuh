@@ -75,6 +75,13 @@ struct TailArgs {
   float* dHf;                        // [M*T, F]
 };
 
+// The argument blocks of the row tasks live in file-scope shared memory: the tasks are compiled OUT OF LINE (their
+// register allocation stays separate from the GEMM roles of the step kernel, whose 168-register budget they blew as
+// inlined code: 1.6 KB of spills), and a reference to a known __shared__ object keeps every field access an LDS that
+// global stores cannot alias -- passed as `const TailArgs&` the block became generic loads repeated after every store.
+__shared__ TailArgs g_tail;
+__shared__ WColsumJob g_job;
+
 // normalisers of the (weighted) means shared by the loss tasks: CrossEntropyLoss(weight=w) divides by the sum of the
 // weights of the rows it sees (main.py:160-167, 204-206); padding rows of a short last batch are excluded
 // (main.py:354-372, 421-422)
@@ -99,7 +106,8 @@ __device__ __forceinline__ LossNorm loss_norm(const TailArgs& a) {
 // through the ReLU of the hidden layer: dHf = (g_frame W2f) * 1[hid_f > 0].  Depends on hid_f alone, so the whole frame
 // branch runs beside the video-level chain.
 template <int FV>      // F <= 128 * FV
-__device__ __forceinline__ void frame_task_t(const TailArgs& a, const int r0, const int nr, const int tid) {
+__device__ __noinline__ void frame_task_t(const int r0, const int nr, const int tid) {
+  const TailArgs& a = g_tail;
   const int lane = tid & 31, warp = tid >> 5;
   const int T = a.T, F = a.F, Bs = a.Bs;
   const float* __restrict__ W2f = a.W2f;
@@ -185,7 +193,8 @@ __device__ __forceinline__ void frame_task_t(const TailArgs& a, const int r0, co
   }
 }
 // any F % 4 == 0, one row at a time (F > 512: fc_dim = 2048 runs)
-__device__ __forceinline__ void frame_task_any(const TailArgs& a, const int r0, const int nr, const int tid) {
+__device__ __noinline__ void frame_task_any(const int r0, const int nr, const int tid) {
+  const TailArgs& a = g_tail;
   const int lane = tid & 31, warp = tid >> 5;
   const int T = a.T, F = a.F, Bs = a.Bs;
   const float* __restrict__ W2f = a.W2f;
@@ -238,11 +247,11 @@ __device__ __forceinline__ void frame_task_any(const TailArgs& a, const int r0, 
   }
 }
 // the path has F = 512: all four rows of a warp in flight; wider layers take the row-at-a-time form
-__device__ __forceinline__ void frame_task(const TailArgs& a, const int r0, const int nr, const int tid) {
-  if (a.F <= 512)
-    frame_task_t<4>(a, r0, nr, tid);
+__device__ __forceinline__ void frame_task(const int r0, const int nr, const int tid) {
+  if (g_tail.F <= 512)
+    frame_task_t<4>(r0, nr, tid);
   else
-    frame_task_any(a, r0, nr, tid);
+    frame_task_any(r0, nr, tid);
 }
 
 // The video-level row tasks give every video to ONE warp: lane l holds the feature elements 4l .. 4l+3 of each
@@ -282,7 +291,8 @@ __device__ __forceinline__ float row_dot(const RowVec<HV>& a, const RowVec<HV>& 
 // ---- relpool task: videos [v0, v0 + nv): relation sums, relation logits, entropy attention, attentive pooling,
 // dropout of the pooled feature              TRNmodule.py:79, models.py:479, 351-357, 379-388, 651-652, 679-680 ----
 template <int HV>
-__device__ __forceinline__ void relpool_task_t(const TailArgs& a, const int v0, const int nv, const int tid) {
+__device__ __noinline__ void relpool_task_t(const int v0, const int nv, const int tid) {
+  const TailArgs& a = g_tail;
   const int lane = tid & 31, warp = tid >> 5;
   const int M = a.M, R = a.R, H = a.H;
   const size_t plane = (size_t)M * H;
@@ -382,11 +392,20 @@ __device__ __forceinline__ void relpool_task_t(const TailArgs& a, const int v0, 
     row_store<HV>(a.feat_video + (size_t)m * H, lane, y);
 #pragma unroll
     for (int kk = 0; kk < HV; ++kk) {
-      const size_t ge = (size_t)m * H + lane * 4 + 128 * kk;
-      y.c[kk].x *= drop_factor(a.drop_v, ge);
-      y.c[kk].y *= drop_factor(a.drop_v, ge + 1);
-      y.c[kk].z *= drop_factor(a.drop_v, ge + 2);
-      y.c[kk].w *= drop_factor(a.drop_v, ge + 3);
+      const size_t ge = (size_t)m * H + lane * 4 + 128 * kk;      // a multiple of 4: one hash for the quad
+      if (a.drop_v.mode == 2) {
+        const uint64_t hsh = rng_hash4(a.drop_v.seed, a.drop_v.step_dev ? *a.drop_v.step_dev : 0ull, ge >> 2);
+        const uint32_t thr = rng_threshold(a.drop_v.p);
+        y.c[kk].x = rng_keep_bits(hsh, 0, thr) ? y.c[kk].x * a.drop_v.scale : 0.f;
+        y.c[kk].y = rng_keep_bits(hsh, 1, thr) ? y.c[kk].y * a.drop_v.scale : 0.f;
+        y.c[kk].z = rng_keep_bits(hsh, 2, thr) ? y.c[kk].z * a.drop_v.scale : 0.f;
+        y.c[kk].w = rng_keep_bits(hsh, 3, thr) ? y.c[kk].w * a.drop_v.scale : 0.f;
+      } else {
+        y.c[kk].x *= drop_factor(a.drop_v, ge);
+        y.c[kk].y *= drop_factor(a.drop_v, ge + 1);
+        y.c[kk].z *= drop_factor(a.drop_v, ge + 2);
+        y.c[kk].w *= drop_factor(a.drop_v, ge + 3);
+      }
     }
     row_store<HV>(a.dropped + (size_t)m * H, lane, y);
   }
@@ -396,7 +415,8 @@ __device__ __forceinline__ void relpool_task_t(const TailArgs& a, const int v0, 
 // then the first backward step of both video heads: dHv = (g_dom W2v) * 1[hid_v > 0], Gc = g_video Wc
 //                              models.py:681-687, 469-470; main.py:446, 508-538, 559-562; loss.py:15-25 ----
 template <int HV>
-__device__ __forceinline__ void heads_task_t(const TailArgs& a, const int v0, const int nv, const int tid) {
+__device__ __noinline__ void heads_task_t(const int v0, const int nv, const int tid) {
+  const TailArgs& a = g_tail;
   const int lane = tid & 31, warp = tid >> 5;
   const int R = a.R, H = a.H, C = a.C, Bs = a.Bs;
   const LossNorm ln = loss_norm(a);
@@ -568,7 +588,8 @@ __device__ __forceinline__ void heads_task_t(const TailArgs& a, const int v0, co
 // relation heads receive, and their data gradient through the hidden ReLU: dHid_i = (Pt_i W2r_i) * 1[hid_r_i > 0]
 //                                                                     backward of models.py:379-388, 479 ----
 template <int HV>
-__device__ __forceinline__ void relbwd_task_t(const TailArgs& a, const int v0, const int nv, const int tid) {
+__device__ __noinline__ void relbwd_task_t(const int v0, const int nv, const int tid) {
+  const TailArgs& a = g_tail;
   const int lane = tid & 31, warp = tid >> 5;
   const int M = a.M, R = a.R, H = a.H;
   for (int v = warp; v < nv; v += 8) {
@@ -623,12 +644,12 @@ __device__ __forceinline__ void relbwd_task_t(const TailArgs& a, const int v0, c
 
 // H = 128 * HV with HV in {1, 2} (checked by build_step_program): the path has H = 256 (models.py:223)
 enum : int { ROW_RELPOOL = 0, ROW_HEADS = 1, ROW_RELBWD = 2 };
-__device__ __forceinline__ void video_row_task(const int kind, const TailArgs& a, const int v0, const int nv, const int tid) {
-#define TA3N_ROW_DISPATCH(HVV)                                   \
-  if (kind == ROW_RELPOOL) relpool_task_t<HVV>(a, v0, nv, tid);  \
-  else if (kind == ROW_HEADS) heads_task_t<HVV>(a, v0, nv, tid); \
-  else relbwd_task_t<HVV>(a, v0, nv, tid);
-  if (a.H == 256) {
+__device__ __forceinline__ void video_row_task(const int kind, const int v0, const int nv, const int tid) {
+#define TA3N_ROW_DISPATCH(HVV)                                \
+  if (kind == ROW_RELPOOL) relpool_task_t<HVV>(v0, nv, tid);  \
+  else if (kind == ROW_HEADS) heads_task_t<HVV>(v0, nv, tid); \
+  else relbwd_task_t<HVV>(v0, nv, tid);
+  if (g_tail.H == 256) {
     TA3N_ROW_DISPATCH(2)
   } else {
     TA3N_ROW_DISPATCH(1)
@@ -728,9 +749,8 @@ __device__ __forceinline__ void colsum_part_body(const WColsumJob& j, float4 (*r
   }
 }
 
-__device__ __forceinline__ void colsum_part_task(const WColsumJob& job_in, float* __restrict__ sm, const int cb,
-                                                 const int split, const int tid) {
-  const WColsumJob j = job_in;      // register copy: no generic reloads behind the stores
+__device__ __noinline__ void colsum_part_task(float* __restrict__ sm, const int cb, const int split, const int tid) {
+  const WColsumJob& j = g_job;      // file-scope shared memory: LDS, never aliased by the global stores
   float4(*red)[33] = reinterpret_cast<float4(*)[33]>(sm);
   const int lane = tid & 31, warp = tid >> 5;
   if (cb * 128 >= j.N || split >= j.nsplit) return;
@@ -754,8 +774,8 @@ __device__ __forceinline__ void colsum_part_task(const WColsumJob& job_in, float
 }
 
 // out[k, n] = sum_split partial[split, k, n] in split order (the whole job: N2*N outputs, 256 threads)
-__device__ __forceinline__ void colsum_reduce_task(const WColsumJob& job_in, const int tid) {
-  const WColsumJob j = job_in;
+__device__ __noinline__ void colsum_reduce_task(const int tid) {
+  const WColsumJob& j = g_job;
   const int total = j.N2 * j.N;
   const int nsplit = j.nsplit;
   for (int e = tid; e < total; e += kRowThreads) {
