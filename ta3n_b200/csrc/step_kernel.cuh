@@ -82,11 +82,9 @@ struct StepSlot {                // one scheduled task: descriptor + (GEMM) the 
   TileCtx ctx;
 };
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
+// NOTE: polls use ld.relaxed, never ld.acquire: ptxas implements a gpu-scope acquire as load + CCTL.IVALL, i.e. every
+// poll invalidated the SM's whole L1 (187 k times per step, one every 0.4 us per SM: measured with ncu, profiles/).
+// The acquire is one fence after the poll has succeeded.
 __device__ __forceinline__ void red_release(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -138,7 +136,7 @@ __device__ __forceinline__ bool step_task_ready(const StepHeader& hd, const int 
   for (int r = 0; r < 2; ++r) {
     const int cb = __ldg(&t->wait_begin[r]), ce = __ldg(&t->wait_end[r]), val = __ldg(&t->wait_val[r]);
     for (int c = cb; c < ce; ++c)
-      if (ld_acquire(hd.counters + c) < val) return false;
+      if (ld_relaxed(hd.counters + c) < val) return false;      // relaxed: the caller fences ONCE after the claim
   }
   return true;
 }
@@ -249,6 +247,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
       mbar_wait(&slot_empty[s], ((k / kStepSlots) & 1u) ^ 1u);
       StepSlot& sl = slots[s];
       const int t = step_next_task(hd, cursors, lane, &done_count, k, deferred, n_def);
+      __threadfence();                     // acquire side of the arrival counters (relaxed polls above), once per task
       if (t < 0) {
         if (lane == 0) {
           sl.task.type = TASK_STOP;
@@ -277,10 +276,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
       }
       if (lane == 0) sl.index = t;
       __syncwarp();
-      if (lane == 0) {
-        __threadfence();                   // the acquire loads of the claim, cumulatively, before the consumers' reads
-        mbar_arrive(&slot_full[s]);
-      }
+      if (lane == 0) mbar_arrive(&slot_full[s]);
     }
   } else if (warp == 0) {
     // =========================== TMA producer ===========================
