@@ -464,17 +464,22 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
         q[u] = lds4(stage + (uint32_t)(r * TC_STAGE_LD + cq * 4) * 4u);
       }
       // ---- every load of the batch first ----
+      // (every element of the auxiliary arrays is written, under a select rather than a branch: left partly
+      //  uninitialised behind `continue`s the compiler kept them in LOCAL memory and stored each load result to the
+      //  stack as it arrived -- one load in flight at a time; measured with ncu, profiles/README.md)
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (!ok[u]) continue;
-        const size_t m = (size_t)rows[u];
+        const size_t m = (size_t)(ok[u] ? rows[u] : m0);        // a safe row for the masked-off lanes
+        x0[u] = x1[u] = x2[u] = zero4;
+        rs[u] = 1.0f;
         if (n_part > 0) {
           x0[u] = ldcg4(e.partial + m * N + n);
           if (n_part > 1) x1[u] = ldcg4(e.partial + plane + m * N + n);
           if (n_part > 2) x2[u] = ldcg4(e.partial + 2 * plane + m * N + n);
-        } else {
+        } else if (CLS == EPI_CLS_ALL) {
           if (f & EPI_ADDROW) {
-            rs[u] = e.rowscale ? __ldcg(e.rowscale + m * e.rs_stride) + e.rs_bias : 1.0f;
+            if (e.rowscale) rs[u] = __ldcg(e.rowscale + m * e.rs_stride) + e.rs_bias;
             x0[u] = ldcg4(e.add + m * e.ldadd + n);
           }
           if (f & (EPI_GATE | EPI_DPRE)) x1[u] = ldcg4(e.gate + m * e.ldgate + n);
@@ -484,8 +489,7 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
       // ---- arithmetic + store ----
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (!ok[u]) continue;
-        const size_t m = (size_t)rows[u];
+        const size_t m = (size_t)(ok[u] ? rows[u] : m0);
         float4 v = q[u];
         if (n_part > 0) {
           add4(v, x0[u]);
@@ -560,7 +564,7 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
           v = make_float4(ev[0], ev[1], ev[2], ev[3]);
         }
         q[u] = v;
-        *reinterpret_cast<float4*>(obase + m * ldo + n) = v;
+        if (ok[u]) *reinterpret_cast<float4*>(obase + m * ldo + n) = v;
       }
       if (f & EPI_MULTI) {            // dZ planes: the gates of all rows of the batch in flight per plane
         const int n_multi = e.n_multi;

@@ -117,20 +117,21 @@ __device__ __noinline__ void frame_task_t(const int r0, const int nr, const int 
   float4 h[RW][FV];
 #pragma unroll
   for (int j = 0; j < RW; ++j) {
-    const int it = warp + 8 * j;
+    const int it = min(warp + 8 * j, nr - 1);               // clamped: every element is loaded (no branches)
 #pragma unroll
     for (int kk = 0; kk < FV; ++kk) {
-      const int k = lane * 4 + 128 * kk;
-      h[j][kk] = (it < nr && k < F) ? __ldcg(reinterpret_cast<const float4*>(a.hid_f + ((size_t)r0 + it) * F + k))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int k = min(lane * 4 + 128 * kk, F - 4);
+      h[j][kk] = __ldcg(reinterpret_cast<const float4*>(a.hid_f + ((size_t)r0 + it) * F + k));
+      if (lane * 4 + 128 * kk >= F) h[j][kk] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   float4 w0[FV], w1[FV];
 #pragma unroll
   for (int kk = 0; kk < FV; ++kk) {
-    const int k = lane * 4 + 128 * kk;
-    w0[kk] = k < F ? __ldg(reinterpret_cast<const float4*>(W2f + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    w1[kk] = k < F ? __ldg(reinterpret_cast<const float4*>(W2f + F + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k = min(lane * 4 + 128 * kk, F - 4);
+    w0[kk] = __ldg(reinterpret_cast<const float4*>(W2f + k));
+    w1[kk] = __ldg(reinterpret_cast<const float4*>(W2f + F + k));
+    if (lane * 4 + 128 * kk >= F) w0[kk] = w1[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float s0[RW], s1[RW];
 #pragma unroll
@@ -155,8 +156,8 @@ __device__ __noinline__ void frame_task_t(const int r0, const int nr, const int 
 #pragma unroll
   for (int j = 0; j < RW; ++j) {
     const int it = warp + 8 * j;
-    if (it >= nr) break;
-    const size_t row = (size_t)r0 + it;
+    const bool live = it < nr;
+    const size_t row = (size_t)r0 + (live ? it : 0);
     const float p0 = s0[j] + b0, p1 = s1[j] + b1;
     const int m = (int)(row / T);
     const int dom = m >= Bs ? 1 : 0;
@@ -170,7 +171,7 @@ __device__ __noinline__ void frame_task_t(const int r0, const int nr, const int 
       g0 = (x.q0 - (dom ? 0.f : 1.f)) * inv;
       g1 = (x.q1 - (dom ? 1.f : 0.f)) * inv;
     }
-    if (lane == 0) {
+    if (lane == 0 && live) {
       a.pred_frame[row * 2] = p0;
       a.pred_frame[row * 2 + 1] = p1;
       a.g_frame[row * 2] = g0;
@@ -181,7 +182,7 @@ __device__ __noinline__ void frame_task_t(const int r0, const int nr, const int 
 #pragma unroll
     for (int kk = 0; kk < FV; ++kk) {
       const int k = lane * 4 + 128 * kk;
-      if (k < F) {
+      if (k < F && live) {
         float4 d;
         d.x = h[j][kk].x > 0.f ? fmaf(g0, w0[kk].x, g1 * w1[kk].x) : 0.f;
         d.y = h[j][kk].y > 0.f ? fmaf(g0, w0[kk].y, g1 * w1[kk].y) : 0.f;
@@ -304,14 +305,14 @@ __device__ __noinline__ void relpool_task_t(const int v0, const int nv, const in
     for (int i0 = 0; i0 < R; i0 += 4) {
       RowVec<HV> h[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (i0 + j < R) h[j] = row_load_cg<HV>(a.hid_r + ((size_t)(i0 + j) * M + m) * H, lane);
+      for (int j = 0; j < 4; ++j)                  // clamped index: every register of the array is written (no branches)
+        h[j] = row_load_cg<HV>(a.hid_r + ((size_t)min(i0 + j, R - 1) * M + m) * H, lane);
       float s0[4], s1[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         s0[j] = s1[j] = 0.f;
-        if (i0 + j < R) {
-          const float* w = a.W2r.p[i0 + j];
+        {
+          const float* w = a.W2r.p[min(i0 + j, R - 1)];
           const RowVec<HV> x0 = row_load_ro<HV>(w, lane), x1 = row_load_ro<HV>(w + H, lane);
 #pragma unroll
           for (int kk = 0; kk < HV; ++kk) {
@@ -330,17 +331,17 @@ __device__ __noinline__ void relpool_task_t(const int v0, const int nv, const in
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int i = i0 + j;
-        if (i >= R) break;
+        const bool live = i0 + j < R;
+        const int i = min(i0 + j, R - 1);
         const float p0 = s0[j] + __ldg(a.b2r.p[i]), p1 = s1[j] + __ldg(a.b2r.p[i] + 1);
         const float wi = a.use_attn ? attn_from_logits(p0, p1).w : 0.f;
         const size_t o = (size_t)m * R + i;
-        if (lane == 0) {
+        if (lane == 0 && live) {
           a.pred_rel[o * 2] = p0;
           a.pred_rel[o * 2 + 1] = p1;
           if (a.use_attn) a.attn[o] = wi;
         }
-        if ((i & 31) == lane) wp1 = wi + 1.0f;    // R <= 32
+        if (live && (i & 31) == lane) wp1 = wi + 1.0f;    // R <= 32
       }
     }
     RowVec<HV> y;
@@ -350,17 +351,16 @@ __device__ __noinline__ void relpool_task_t(const int v0, const int nv, const in
       RowVec<HV> x[2][3];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int i = i0 + j;
-        if (i >= R) break;
+        const int i = min(i0 + j, R - 1);
         const int qb = a.map.rel_begin[i], qn = a.map.rel_begin[i + 1] - qb;
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
-          if (r < qn) x[j][r] = row_load_cg<HV>(a.act + (qb + r) * plane + (size_t)m * H, lane);
+        for (int r = 0; r < 3; ++r)               // clamped relation: the duplicate load is cheaper than a branch
+          x[j][r] = row_load_cg<HV>(a.act + (qb + min(r, qn - 1)) * plane + (size_t)m * H, lane);
       }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int i = i0 + j;
-        if (i >= R) break;
+        if (i < R) {
         const int qn = a.map.rel_begin[i + 1] - a.map.rel_begin[i];
         RowVec<HV> f = x[j][0];
 #pragma unroll
@@ -386,6 +386,7 @@ __device__ __noinline__ void relpool_task_t(const int v0, const int nv, const in
         if (!a.use_attn) {                        // models.py:647 placeholder output: feat_rel[:, :, 0]
           const float first = __shfl_sync(0xffffffffu, f.c[0].x, 0);
           if (lane == 0) a.attn[(size_t)m * R + i] = first;
+        }
         }
       }
     }
@@ -600,20 +601,19 @@ __device__ __noinline__ void relbwd_task_t(const int v0, const int nv, const int
       float gr0[2], gr1[2], pr0[2], pr1[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int i = i0 + j;
-        if (i >= R) break;
+        const int i = min(i0 + j, R - 1);           // clamped: every register of the arrays is written
         const size_t o = (size_t)m * R + i;
         gr0[j] = __ldcg(a.g_rel + o * 2);
         gr1[j] = __ldcg(a.g_rel + o * 2 + 1);
         pr0[j] = __ldcg(a.pred_rel + o * 2);
         pr1[j] = __ldcg(a.pred_rel + o * 2 + 1);
-        if (a.use_attn) fr[j] = row_load_cg<HV>(a.feat_rel + o * H, lane);
+        fr[j] = row_load_cg<HV>(a.feat_rel + o * H, lane);
         h[j] = row_load_cg<HV>(a.hid_r + ((size_t)i * M + m) * H, lane);
       }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int i = i0 + j;
-        if (i >= R) break;
+        if (i < R) {
         const size_t o = (size_t)m * R + i;
         float pt0 = gr0[j], pt1 = gr1[j];
         if (a.use_attn) {
@@ -637,6 +637,7 @@ __device__ __noinline__ void relbwd_task_t(const int v0, const int nv, const int
           d.c[kk].w = h[j].c[kk].w > 0.f ? fmaf(pt0, x0.c[kk].w, pt1 * x1.c[kk].w) : 0.f;
         }
         row_store<HV>(a.dHid + ((size_t)i * M + m) * H, lane, d);
+        }
       }
     }
   }
