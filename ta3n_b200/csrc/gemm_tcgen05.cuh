@@ -213,7 +213,10 @@ __device__ __forceinline__ void tc_pipe_init(TcShared* sh, int epi_warps) {
 //   TILE_PARTIAL : raw accumulator -> partial[split]         (separate reduce pass, or an owner tile below)
 //   TILE_OWNER   : adds partial[0 .. ksplit-2] in a fixed order, then fused epilogue -> C.  The caller guarantees
 //                  those partials are complete and visible (step kernel: task dependency).
-enum : int { TILE_FINAL = 0, TILE_PARTIAL = 1, TILE_OWNER = 2 };
+//   TILE_SPLIT   : (step kernel) raw accumulator -> partial[split]; the LAST split of the tile to arrive (arrival counter)
+//                  then runs a TILE_REDUCE pass: partial[0 .. ksplit-1] summed in split order + fused epilogue -> C.
+//                  No split ever waits for another one, and the result does not depend on which one came last.
+enum : int { TILE_FINAL = 0, TILE_PARTIAL = 1, TILE_OWNER = 2, TILE_SPLIT = 3, TILE_REDUCE = 4 };
 
 // TMA producer (ONE thread): the n_iter K slabs [c_begin, c_begin + n_iter) of tile (m0, n0) into the ring.
 // `slabs` = slabs this CTA has pushed so far (advanced by the caller).
@@ -401,7 +404,7 @@ __device__ __forceinline__ void add4(float4& a, const float4& b) {
 // 1300 instructions per warp and tile (5 us at 2 warps per scheduler); the lean copies are ~250.
 enum : int { EPI_CLS_PLAIN = 0, EPI_CLS_FORWARD = 1, EPI_CLS_ALL = 2 };
 __device__ __forceinline__ int epi_class(const int mode, const int flags) {
-  if (mode == TILE_PARTIAL || flags == 0) return EPI_CLS_PLAIN;
+  if (mode == TILE_PARTIAL || mode == TILE_SPLIT || flags == 0) return EPI_CLS_PLAIN;
   if ((flags & ~(EPI_BIAS | EPI_RELU | EPI_DROP_MASK | EPI_DROP_RNG)) == 0) return EPI_CLS_FORWARD;
   return EPI_CLS_ALL;
 }
@@ -416,16 +419,17 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
   constexpr int kMask = CLS == EPI_CLS_PLAIN ? 0
                         : CLS == EPI_CLS_FORWARD ? (EPI_BIAS | EPI_RELU | EPI_DROP_MASK | EPI_DROP_RNG)
                                                  : ~0;
-  const int f = (mode == TILE_PARTIAL ? 0 : e.flags) & kMask;
+  const bool split_out = mode == TILE_PARTIAL || mode == TILE_SPLIT;
+  const int f = (split_out ? 0 : e.flags) & kMask;
   const int M = e.M, N = e.N;
-  const bool split_out = mode == TILE_PARTIAL;
   const size_t plane = (size_t)M * N;
   float* const obase = split_out ? e.partial + (size_t)split * plane : e.C;
   const int ldo = split_out ? N : e.ldc;
   constexpr int kColChunks = (TC_BN / 32) * 4 / kEpiWarps;
   const int c0 = (ew / 4) * kColChunks;
   const int rq = lane >> 3, cq = lane & 7;
-  const int n_part = (CLS != EPI_CLS_ALL && mode == TILE_OWNER) ? e.ksplit - 1 : 0;      // no aux operands on split groups
+  // planes of raw partial sums folded in (no aux operands on split groups: the register sets are shared)
+  const int n_part = CLS == EPI_CLS_ALL ? 0 : (mode == TILE_OWNER ? e.ksplit - 1 : (mode == TILE_REDUCE ? e.ksplit : 0));
   const float alpha = split_out ? 1.0f : (e.alpha_dev ? e.alpha * __ldg(e.alpha_dev) : e.alpha);
   const uint64_t step = (f & EPI_DROP_RNG) ? (e.step_dev ? *e.step_dev : 0ull) : 0ull;
   const bool drop_early = (f & (EPI_DROP_MASK | EPI_DROP_RNG)) && !(f & EPI_DROP_LATE);
@@ -454,7 +458,7 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
     for (int half = 0; half < 2; ++half) {                 // 2 batches of 4 x (4 rows per instruction) = 32 rows
       int rows[4];
       bool ok[4];
-      float4 q[4], x0[4], x1[4], x2[4];
+      float4 q[4], x0[4], x1[4], x2[4], x3[4];
       float rs[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -477,6 +481,7 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
           x0[u] = ldcg4(e.partial + m * N + n);
           if (n_part > 1) x1[u] = ldcg4(e.partial + plane + m * N + n);
           if (n_part > 2) x2[u] = ldcg4(e.partial + 2 * plane + m * N + n);
+          x3[u] = n_part > 3 ? ldcg4(e.partial + 3 * plane + m * N + n) : zero4;
         } else if (CLS == EPI_CLS_ALL) {
           if (f & EPI_ADDROW) {
             if (e.rowscale) rs[u] = __ldcg(e.rowscale + m * e.rs_stride) + e.rs_bias;
@@ -484,6 +489,11 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
           }
           if (f & (EPI_GATE | EPI_DPRE)) x1[u] = ldcg4(e.gate + m * e.ldgate + n);
           if (f & EPI_ACCUM) x2[u] = ldcg4(e.C + m * e.ldc + n);
+          if (f & EPI_MULTI) {          // the gates of every dZ plane ride with the first round of loads
+            x1[u] = ldcg4(e.multi_gate[0] + m * e.ldmulti + n);           // (a MULTI group has no gate / accumulate)
+            if (e.n_multi > 1) x2[u] = ldcg4(e.multi_gate[1] + m * e.ldmulti + n);
+            x3[u] = e.n_multi > 2 ? ldcg4(e.multi_gate[2] + m * e.ldmulti + n) : zero4;
+          }
         }
       }
       // ---- arithmetic + store ----
@@ -495,6 +505,7 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
           add4(v, x0[u]);
           if (n_part > 1) add4(v, x1[u]);
           if (n_part > 2) add4(v, x2[u]);
+          if (n_part > 3) add4(v, x3[u]);
         }
         if (!split_out) {
           float ev[4] = {v.x * alpha, v.y * alpha, v.z * alpha, v.w * alpha};
@@ -566,22 +577,24 @@ __device__ __forceinline__ void tc_epilogue_cls(const TileCtx& ctx, const int m0
         q[u] = v;
         if (ok[u]) *reinterpret_cast<float4*>(obase + m * ldo + n) = v;
       }
-      if (f & EPI_MULTI) {            // dZ planes: the gates of all rows of the batch in flight per plane
+      if (CLS == EPI_CLS_ALL && (f & EPI_MULTI)) {      // dZ planes (gates already in x1 .. x3)
         const int n_multi = e.n_multi;
-#pragma unroll 1
-        for (int p = 0; p < n_multi; ++p) {
-          const float* gate = e.multi_gate[p];
-          float* out = e.multi_out[p];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (ok[u]) x1[u] = ldcg4(gate + (size_t)rows[u] * e.ldmulti + n);
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (ok[u])
-              *reinterpret_cast<float4*>(out + (size_t)rows[u] * e.ldmulti + n) =
-                  make_float4(x1[u].x > 0.f ? q[u].x : 0.f, x1[u].y > 0.f ? q[u].y : 0.f, x1[u].z > 0.f ? q[u].z : 0.f,
-                              x1[u].w > 0.f ? q[u].w : 0.f);
-        }
+        for (int u = 0; u < 4; ++u)
+          if (ok[u]) {
+            const size_t off = (size_t)rows[u] * e.ldmulti + n;
+            *reinterpret_cast<float4*>(e.multi_out[0] + off) =
+                make_float4(x1[u].x > 0.f ? q[u].x : 0.f, x1[u].y > 0.f ? q[u].y : 0.f, x1[u].z > 0.f ? q[u].z : 0.f,
+                            x1[u].w > 0.f ? q[u].w : 0.f);
+            if (n_multi > 1)
+              *reinterpret_cast<float4*>(e.multi_out[1] + off) =
+                  make_float4(x2[u].x > 0.f ? q[u].x : 0.f, x2[u].y > 0.f ? q[u].y : 0.f, x2[u].z > 0.f ? q[u].z : 0.f,
+                              x2[u].w > 0.f ? q[u].w : 0.f);
+            if (n_multi > 2)
+              *reinterpret_cast<float4*>(e.multi_out[2] + off) =
+                  make_float4(x3[u].x > 0.f ? q[u].x : 0.f, x3[u].y > 0.f ? q[u].y : 0.f, x3[u].z > 0.f ? q[u].z : 0.f,
+                              x3[u].w > 0.f ? q[u].w : 0.f);
+          }
       }
     }
   }
@@ -598,7 +611,8 @@ inline bool tc_step_group_ok(const Group& g) {
   if ((g.flags & EPI_ADDROW) && (g.ldadd % 4 != 0 || !a16(g.add))) return false;
   if ((g.flags & (EPI_GATE | EPI_DPRE)) && (g.ldgate % 4 != 0 || !a16(g.gate))) return false;
   if (g.flags & EPI_MULTI) {
-    if (g.ldmulti % 4 != 0 || g.n_multi > 3) return false;
+    if (g.ldmulti % 4 != 0 || g.n_multi < 1 || g.n_multi > 3) return false;
+    if (g.flags & (EPI_GATE | EPI_DPRE | EPI_ACCUM)) return false;      // their registers carry the plane gates
     for (int p = 0; p < g.n_multi; ++p)
       if (!a16(g.multi_gate[p]) || !a16(g.multi_out[p])) return false;
   }

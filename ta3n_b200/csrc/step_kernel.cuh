@@ -49,6 +49,7 @@ struct StepTask {
   int wait_begin[2], wait_end[2], wait_val[2];     // wait until counters[i] >= val for i in [begin, end)
   int signal;             // counter bumped on completion (-1: none)
   int signal2;            // second counter (the stage total; -1: none)
+  int split_counter;      // GEMM, TILE_SPLIT: arrival counter of the output tile (the last split to arrive reduces)
   int urgent;             // on the latency-critical chain: only an otherwise idle CTA may take it (no queueing behind
                           // tiles the CTA has already committed to)
 };
@@ -71,7 +72,7 @@ struct StepHeader {
   int queue_begin[kStepQueues + 1];   // tasks of queue q are [queue_begin[q], queue_begin[q + 1])
   unsigned long long* step_counter;   // dropout step counter, advanced by the FINISH task (may be null)
   unsigned long long* trace;     // optional [n_tasks][8]: {sm id | tag, started, accumulator ready, done, body done,
-                                 // CTA synced, -, -} (globaltimer ns)
+                                 // CTA synced, -, -} (globaltimer ns), followed by [M / 8][8] phase marks of the row tasks
 };
 
 struct StepSlot {                // one scheduled task: descriptor + (GEMM) the group and its segments
@@ -109,6 +110,18 @@ __device__ __noinline__ void step_epilogue_cls(const int s, const uint32_t tmem_
                                                const uint32_t stage) {
   const StepSlot& sl = g_slots[s];
   tc_epilogue_cls<8, CLS>(sl.ctx, sl.task.m0, sl.task.n0, sl.task.split, sl.n_iter, sl.task.mode, tmem_base, acc, ew, stage);
+}
+// TILE_REDUCE pass of slot s: the split-K partials of the tile, summed in split order, through the fused epilogue
+template <int CLS>
+__device__ __noinline__ void step_reduce_cls(const int s, const int ew, const uint32_t stage) {
+  const StepSlot& sl = g_slots[s];
+  tc_epilogue_cls<8, CLS>(sl.ctx, sl.task.m0, sl.task.n0, 0, 0, TILE_REDUCE, 0u, 0, ew, stage);
+}
+__device__ __forceinline__ void step_reduce(const int s, const int ew, const uint32_t stage) {
+  if (epi_class(TILE_REDUCE, g_slots[s].ctx.g.flags) == EPI_CLS_PLAIN)
+    step_reduce_cls<EPI_CLS_PLAIN>(s, ew, stage);
+  else
+    step_reduce_cls<EPI_CLS_FORWARD>(s, ew, stage);      // split groups never carry auxiliary operands
 }
 __device__ __forceinline__ void step_epilogue(const int s, const uint32_t tmem_base, const int acc, const int ew,
                                               const uint32_t stage) {
@@ -212,6 +225,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
   __shared__ __align__(8) uint64_t slot_empty[kStepSlots];
   StepSlot* const slots = g_slots;
   __shared__ int done_count;            // tasks this CTA has completed (scheduler: is anything still in flight?)
+  __shared__ int split_rank;            // TILE_SPLIT: how many splits of the tile had arrived before this one
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(step_smem_raw) + 1023) & ~uintptr_t(1023));
   float* scratch = reinterpret_cast<float*>(smem + kStepStages * TC_STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,6 +246,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
   if (warp == 1) tmem_alloc(&sh.tmem_slot, kStepTmemCols);
   for (int i = tid; i < (int)(sizeof(TailArgs) / sizeof(int)); i += kStepThreads)
     reinterpret_cast<int*>(&g_tail)[i] = reinterpret_cast<const int*>(hd.tail)[i];
+  __syncthreads();
+  if (tid == 0) g_tail.dbg = hd.trace ? hd.trace + (size_t)hd.n_tasks * 8 : nullptr;      // row-task phase marks
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -330,6 +346,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
       const int type = sl.task.type;
       if (type == TASK_STOP) break;
       unsigned long long t_sched = 0, t_acc = 0, t_body = 0, t_sync = 0;
+      bool publish = true;                 // a split-K tile that was not the last to arrive has nothing to announce
       if (hd.trace && rt == 0) t_sched = global_ns();
       if (type == TASK_GEMM) {
         const int acc = (int)(tiles & 1u);
@@ -343,6 +360,22 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
           __syncwarp();
           if (lane == 0) mbar_arrive(&sh.tmem_empty_bar[acc]);      // this warp's TMEM reads are done
           ++tiles;
+        }
+        if (sl.task.mode == TILE_SPLIT) {      // raw partial written: am I the last split of this tile?
+          row_sync();
+          if (rt == 0) {
+            __threadfence();                   // release my partial (cumulative over the CTA: bar above) ...
+            const int before = atomicAdd(hd.counters + sl.task.split_counter, 1);
+            __threadfence();                   // ... acquire the others'
+            split_rank = before;
+          }
+          row_sync();
+          if (split_rank == sl.ctx.g.ksplit - 1) {
+            step_reduce(s, ew, smem_u32(scratch + ew * TC_EPI_STAGE_FLOATS));
+            publish = true;
+          } else {
+            publish = false;
+          }
         }
       } else if (type == TASK_FRAME) {
         frame_task(sl.task.m0, sl.task.n0, rt);
@@ -367,7 +400,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ta3n_step_kernel(const __grid
       row_sync();                        // every warp's stores are issued (CTA-scope order) ...
       if (hd.trace && rt == 0) t_sync = global_ns();
       if (rt == 0) {
-        if (sig >= 0 || sig2 >= 0) {
+        if (publish && (sig >= 0 || sig2 >= 0)) {
           __threadfence();               // ... one cumulative gpu-scope fence publishes them with the release below
           fence_proxy_async_all();
           if (sig >= 0) red_release(hd.counters + sig, 1);

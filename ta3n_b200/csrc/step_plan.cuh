@@ -569,7 +569,7 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
       sg.g.tiles_n = (sg.g.N + TC_BN - 1) / TC_BN;
       sg.g.ksplit = ksplit[gi];
       sg.g.fix_slot = -1;
-      sg.g.partial = sg.g.ksplit > 1 ? carve((size_t)(sg.g.ksplit - 1) * sg.g.M * sg.g.N) : nullptr;
+      sg.g.partial = sg.g.ksplit > 1 ? carve((size_t)sg.g.ksplit * sg.g.M * sg.g.N) : nullptr;
       if (!tc_step_group_ok(sg.g)) {
         fail(TA3N_ERR_UNSUPPORTED, "fused step: a group of %s breaks the epilogue's alignment rules (N %d, ldc %d, flags %d)",
              p.label, sg.g.N, sg.g.ldc, sg.g.flags);
@@ -609,50 +609,34 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
                         const std::function<int(int mb)>& sig, int sig_total = -1) {
     const Group& g = B->groups[gidx].g;
     const int pc = g.ksplit > 1 ? counters(g.tiles_m * g.tiles_n) : -1;
-    // partial tiles first (nobody waits on the queue position of an owner before its partials)
-    for (int pass = 0; pass < 2; ++pass)
-      for (int tm = 0; tm < g.tiles_m; ++tm)
-        for (int tn = 0; tn < g.tiles_n; ++tn)
-          for (int sp = 0; sp < g.ksplit; ++sp) {
-            const bool owner = sp == g.ksplit - 1;
-            if ((pass == 0) == owner && g.ksplit > 1) continue;
-            if (g.ksplit == 1 && pass == 0) continue;
-            StepTask t;
-            memset(&t, 0, sizeof(t));
-    t.signal = t.signal2 = -1;
-            t.type = TASK_GEMM;
-            t.group = gidx;
-            t.m0 = tm * TC_BM;
-            t.n0 = tn * TC_BN;
-            t.split = sp;
-            t.mode = g.ksplit == 1 ? TILE_FINAL : (owner ? TILE_OWNER : TILE_PARTIAL);
-            Dep dr = dep_of_rows ? dep_of_rows(t.m0) : d0;
-            t.wait_begin[0] = dr.b;
-            t.wait_end[0] = dr.e;
-            t.wait_val[0] = dr.v;
-            if (dep_of_rows && d0.e > d0.b) {       // second static range
-              t.wait_begin[1] = d0.b;
-              t.wait_end[1] = d0.e;
-              t.wait_val[1] = d0.v;
-            }
-            if (g.ksplit > 1) {
-              const int pidx = pc + tm * g.tiles_n + tn;
-              if (owner) {
-                if (t.wait_end[1] > t.wait_begin[1]) return -1;      // both ranges taken: not needed by any stage here
-                t.wait_begin[1] = pidx;
-                t.wait_end[1] = pidx + 1;
-                t.wait_val[1] = g.ksplit - 1;
-              } else {
-                t.signal = pidx;
-              }
-            }
-            if (g.ksplit == 1 || owner) {
-              t.signal = sig ? sig(tm) : -1;
-              t.signal2 = sig_total;
-            }
-            out->push_back(t);
-            ++B->n_gemm_tiles;
+    for (int tm = 0; tm < g.tiles_m; ++tm)
+      for (int tn = 0; tn < g.tiles_n; ++tn)
+        for (int sp = 0; sp < g.ksplit; ++sp) {
+          StepTask t;
+          memset(&t, 0, sizeof(t));
+          t.type = TASK_GEMM;
+          t.group = gidx;
+          t.m0 = tm * TC_BM;
+          t.n0 = tn * TC_BN;
+          t.split = sp;
+          // split-K: every split writes its raw partial; the last one to arrive at the tile's counter reduces them
+          // in split order and announces the tile (TILE_SPLIT, step_kernel.cuh) -- no split waits for another
+          t.mode = g.ksplit == 1 ? TILE_FINAL : TILE_SPLIT;
+          t.split_counter = g.ksplit > 1 ? pc + tm * g.tiles_n + tn : -1;
+          Dep dr = dep_of_rows ? dep_of_rows(t.m0) : d0;
+          t.wait_begin[0] = dr.b;
+          t.wait_end[0] = dr.e;
+          t.wait_val[0] = dr.v;
+          if (dep_of_rows && d0.e > d0.b) {       // second static range
+            t.wait_begin[1] = d0.b;
+            t.wait_end[1] = d0.e;
+            t.wait_val[1] = d0.v;
           }
+          t.signal = sig ? sig(tm) : -1;
+          t.signal2 = sig_total;
+          out->push_back(t);
+          ++B->n_gemm_tiles;
+        }
     return 0;
   };
   auto sort_by_slabs = [&](std::vector<StepTask>* v) {
@@ -664,7 +648,6 @@ inline int build_task_graph(const StepProgram& P, int sm_count, float* partial_b
       for (int k = 0; k < gb.seg_count; ++k) sb += (B->segs[B->groups[b.group].seg_begin + k].len + TC_BK - 1) / TC_BK;
       sa = (sa + ga.ksplit - 1) / ga.ksplit;
       sb = (sb + gb.ksplit - 1) / gb.ksplit;
-      if ((a.mode == TILE_OWNER) != (b.mode == TILE_OWNER)) return b.mode == TILE_OWNER;     // owners last
       return sa > sb;
     });
   };

@@ -73,7 +73,16 @@ struct TailArgs {
   const float* G;                    // [M, H]     d loss / d feat_video (completed by the video-discriminator dgrad GEMM)
   float* dHid;                       // [R, M, H]
   float* dHf;                        // [M*T, F]
+  unsigned long long* dbg;           // development: [M / 8][8] phase timestamps of the relpool / heads tasks (or null)
 };
+
+__device__ __forceinline__ void row_mark(const TailArgs& a, int task, int slot, int warp, int lane) {
+  if (a.dbg && warp == 0 && lane == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.dbg[(size_t)task * 8 + slot] = t;
+  }
+}
 
 // The argument blocks of the row tasks live in file-scope shared memory: the tasks are compiled OUT OF LINE (their
 // register allocation stays separate from the GEMM roles of the step kernel, whose 168-register budget they blew as
@@ -297,6 +306,7 @@ __device__ __noinline__ void relpool_task_t(const int v0, const int nv, const in
   const int lane = tid & 31, warp = tid >> 5;
   const int M = a.M, R = a.R, H = a.H;
   const size_t plane = (size_t)M * H;
+  row_mark(a, v0 / kRowVideos, 0, warp, lane);
   for (int v = warp; v < nv; v += 8) {
     const int m = v0 + v;
     // relation logits from the discriminators' hidden layer -> attention weights; lane i keeps w_i + 1 of scale i.
@@ -344,6 +354,7 @@ __device__ __noinline__ void relpool_task_t(const int v0, const int nv, const in
         if (live && (i & 31) == lane) wp1 = wi + 1.0f;    // R <= 32
       }
     }
+    row_mark(a, v0 / kRowVideos, 1, warp, lane);
     RowVec<HV> y;
 #pragma unroll
     for (int kk = 0; kk < HV; ++kk) y.c[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -390,6 +401,7 @@ __device__ __noinline__ void relpool_task_t(const int v0, const int nv, const in
         }
       }
     }
+    row_mark(a, v0 / kRowVideos, 2, warp, lane);
     row_store<HV>(a.feat_video + (size_t)m * H, lane, y);
 #pragma unroll
     for (int kk = 0; kk < HV; ++kk) {
@@ -409,6 +421,7 @@ __device__ __noinline__ void relpool_task_t(const int v0, const int nv, const in
       }
     }
     row_store<HV>(a.dropped + (size_t)m * H, lane, y);
+    row_mark(a, v0 / kRowVideos, 3, warp, lane);
   }
 }
 
@@ -432,6 +445,7 @@ __device__ __noinline__ void heads_task_t(const int v0, const int nv, const int 
     const int m = v0 + v;
     const int dom = m >= Bs ? 1 : 0;
     const bool real = dom ? (m - Bs < ln.vt) : (m < ln.vs);
+    row_mark(a, v0 / kRowVideos, 4, warp, lane);
     const RowVec<HV> d = row_load_cg<HV>(a.dropped + (size_t)m * H, lane);
     const RowVec<HV> hv = row_load_cg<HV>(a.hid_v + (size_t)m * H, lane);
     const int y_lab = (m < Bs) ? (int)a.labels[m] : -1;    // requested early: off the critical chain below
@@ -476,6 +490,7 @@ __device__ __noinline__ void heads_task_t(const int v0, const int nv, const int 
       a.pred_dom[(size_t)m * 2] = pd0;
       a.pred_dom[(size_t)m * 2 + 1] = pd1;
     }
+    row_mark(a, v0 / kRowVideos, 5, warp, lane);
     // ---- loss heads ----
     float gv[CV];
     float g0 = 0.f, g1 = 0.f, loss = 0.f;
@@ -553,6 +568,7 @@ __device__ __noinline__ void heads_task_t(const int v0, const int nv, const int 
       a.g_dom[(size_t)m * 2 + 1] = g1;
       a.row_loss[m] = loss;
     }
+    row_mark(a, v0 / kRowVideos, 6, warp, lane);
     // ---- dHv = (g_dom W2v) * 1[hid_v > 0]                                                  (head_bwd_data) ----
     RowVec<HV> o;
 #pragma unroll
@@ -582,6 +598,7 @@ __device__ __noinline__ void heads_task_t(const int v0, const int nv, const int 
       }
     }
     row_store<HV>(a.Gc + (size_t)m * H, lane, o);
+    row_mark(a, v0 / kRowVideos, 7, warp, lane);
   }
 }
 

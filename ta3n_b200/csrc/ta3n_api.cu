@@ -1039,8 +1039,11 @@ size_t ta3n_step_describe(const ta3n_step_desc* desc, char* buf, size_t buf_byte
           ++cur[q];
           --left;
           progress = true;
-          if (t.signal >= 0) cnt[t.signal]++;
-          if (t.signal2 >= 0) cnt[t.signal2]++;
+          bool publish = true;
+          if (t.type == TASK_GEMM && t.mode == TILE_SPLIT)      // only the last split to arrive announces the tile
+            publish = ++cnt[t.split_counter] == B.groups[t.group].g.ksplit;
+          if (publish && t.signal >= 0) cnt[t.signal]++;
+          if (publish && t.signal2 >= 0) cnt[t.signal2]++;
         }
       }
     }

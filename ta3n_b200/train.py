@@ -113,7 +113,7 @@ class TrainStep:
         allreduce (world > 1): 'peer' = this library's one-kernel all-reduce over NVLink peer / NVSwitch multicast
         memory (csrc/allreduce.cuh; the gradient bucket then lives in symmetric memory and the whole iteration --
         step, all-reduce, optimizer -- is one CUDA graph), 'nccl' = torch.distributed all_reduce between graphs;
-        default: 'peer' in fused / phased mode when symmetric memory can be set up, else 'nccl'."""
+        default: 'peer' when symmetric memory can be set up (and no NCCL overlap option was asked for), else 'nccl'."""
         if not model.training:
             raise ValueError("TrainStep needs model.train() (dropout state is fixed at construction)")
         self.model = model
@@ -156,6 +156,7 @@ class TrainStep:
                              "legacy sequence bakes beta into the captured graph")
         if class_weight is not None and mode == "legacy":
             raise ValueError("class_weight needs mode='fused' or 'phased'")
+        self._overlap_requested = bool(overlap_allreduce)
         self.split = (self.world > 1) if overlap_allreduce is None else bool(overlap_allreduce)
         if model.use_attn_frame != "none" or mode != "legacy":
             self.split = False     # frame attention couples the TRN and frame-discriminator gradients
@@ -172,6 +173,8 @@ class TrainStep:
         self.flat_param = flatten_parameters(model)
         order, offs, n, self.early_numel = bucket_layout(self.params)
         self.flat_grad = self._alloc_gradient_bucket(n, allreduce)
+        if self.ar is not None and overlap_allreduce is None:
+            self.split = False      # the library's own all-reduce runs inside the one graph: nothing to split around
         self.grad_views: List[Optional[torch.Tensor]] = [None] * len(self.params)
         for idx in order:
             p = self.params[idx]
@@ -257,7 +260,8 @@ class TrainStep:
         all-reduce kernel can read and write every rank's copy (ta3n_allreduce_mean)."""
         import os
         self.ar = None
-        want = allreduce or os.environ.get("TA3N_ALLREDUCE") or ("peer" if self.mode != "legacy" else "nccl")
+        legacy_nccl = self.mode == "legacy" and (self._overlap_requested or self.graph_collectives)
+        want = allreduce or os.environ.get("TA3N_ALLREDUCE") or ("nccl" if legacy_nccl else "peer")
         if want not in ("peer", "nccl"):
             raise ValueError(f"allreduce must be 'peer' or 'nccl', got {want!r}")
         if self.world == 1 or want == "nccl":
@@ -374,7 +378,7 @@ class TrainStep:
         lib = _lib.load()
         n_tasks = self.step_info()[0]
         if not hasattr(self, "_trace_buf"):
-            self._trace_buf = torch.zeros(n_tasks, 8, device=self.device, dtype=torch.int64)
+            self._trace_buf = torch.zeros(n_tasks + (self.M + 7) // 8, 8, device=self.device, dtype=torch.int64)
         for h in self.step_handles:
             if h is not None:
                 check(lib.ta3n_step_set_trace(h, _P(self._trace_buf) if enable else None))
@@ -487,6 +491,8 @@ class TrainStep:
                          stage_done=stage_done, side_stream=self.branch_stream)
         if self.overlap_wgrad:
             main.wait_stream(side)            # join
+        if self.ar is not None and at_split is None:
+            self._enqueue_allreduce()         # same stream, same graph: step -> all-reduce -> optimizer
         if optimizer and self.opt is not None:
             self._enqueue_optimizer()
 

@@ -452,6 +452,71 @@ def test_fused_train_step_matches_oracle(T, attn_frame, bs, bt, C, use_graph, en
     assert model.fc_feature_source.weight.grad is None       # off-path parameters stay untouched
 
 
+def test_train_step_loss_weights_and_beta_schedule(engine):
+    """criterion(weight=class weights) / criterion_domain(weight=domain weights) (main.py:160-167, 204-206) and the
+    per-step DANN beta (main.py:350-352: negative --beta entries take 2/(1+exp(-10p))-1) inside the captured step."""
+    from ta3n_b200.train import TrainStep, beta_dann
+    C, T, bs, bt = 7, 5, 20, 13
+    cfg = orc.PathConfig(num_class=C, num_segments=T, fc_dim=512, dropout_i=0.0, dropout_v=0.0)
+    params = orc.init_params(cfg, seed=5)
+    g = torch.Generator().manual_seed(6)
+    for k in params:
+        if params[k].dtype.is_floating_point and k.startswith(orc.USED_PARAM_PREFIXES) and "weight" in k:
+            params[k] = params[k] + 0.02 * torch.randn(params[k].shape, generator=g)
+    xs = torch.randn(bs, T, orc.FEATURE_DIM, generator=g)
+    xt = torch.randn(bt, T, orc.FEATURE_DIM, generator=g) + 0.1
+    labels = torch.randint(0, C, (bs,), generator=g)
+    cw = torch.rand(C, generator=g) + 0.25
+    dw = (0.6, 1.7)
+    model = build_model(cfg, params, train=True)
+    step = TrainStep(model, bs, bt, (-1.0, 0.6, -1.0), gamma=0.003, use_graph=True, class_weight=cw, domain_weight=dw)
+    named = dict(model.named_parameters())
+    for p in (0.1, 0.8):                          # two points of the schedule through the SAME captured graph
+        step.set_progress(p)
+        loss = step(xs, xt, labels)
+        torch.cuda.synchronize()
+        b = beta_dann(p)
+        p64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in params.items()}
+        l64, _, g64 = orc.train_step(p64, xs.double(), xt.double(), labels, (b, 0.6, b), cfg, 0.003, train=True,
+                                     class_weight=cw.double(), domain_weight=torch.tensor(dw).double())
+        _, _, g32 = orc.train_step(params, xs, xt, labels, (b, 0.6, b), cfg, 0.003, train=True, class_weight=cw,
+                                   domain_weight=torch.tensor(dw))
+        assert_close(loss.cpu()[0], l64, TOL[engine], f"weighted loss p={p}", noise=1e-6)
+        for name, go in g64.items():
+            assert_close(named[name].grad, go, GRAD_TOL[engine], f"weighted grad {name} p={p}",
+                         noise=abs_err(g32[name], go) * NOISE_SCALE[engine])
+
+
+FULL_SIZE = {"cfg2": dict(B=256, T=5, C=12, attn_frame="none"),            # BASELINE.json configs[1]
+             "cfg3": dict(B=128, T=9, C=12, attn_frame="TransAttn"),       # configs[2]
+             "cfg5": dict(B=512, T=5, C=30, attn_frame="none")}            # configs[4], per GPU
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE))
+def test_full_size_train_step_matches_oracle(name, engine):
+    """Loss and EVERY parameter gradient of one training step at the full size of BASELINE.json's configurations
+    (synthetic inputs of SURVEY 8d, default initialisation) against the fp64 oracle."""
+    from ta3n_b200.train import TrainStep
+    c = FULL_SIZE[name]
+    cfg = orc.PathConfig(num_class=c["C"], num_segments=c["T"], fc_dim=512, dropout_i=0.0, dropout_v=0.0,
+                         use_attn="TransAttn", use_attn_frame=c["attn_frame"])
+    params = orc.init_params(cfg, seed=1234)
+    xs, xt, labels = orc.synthetic_batch(c["B"], cfg)
+    beta = (0.75, 0.75, 0.5)
+    loss_o, _, grads_o, n_loss, _, n_grad = oracle_truth(params, xs, xt, labels, beta, cfg, 0.003, True, None)
+    model = build_model(cfg, params, train=True)
+    step = TrainStep(model, c["B"], c["B"], beta, gamma=0.003, use_graph=True)
+    loss = step(xs.pin_memory(), xt.pin_memory(), labels)
+    torch.cuda.synchronize()
+    assert_close(loss.cpu()[0], loss_o, TOL[engine], f"{name} loss", noise=n_loss)
+    named = dict(model.named_parameters())
+    worst = 0.0
+    for pname, go in grads_o.items():
+        worst = max(worst, assert_close(named[pname].grad, go, GRAD_TOL[engine], f"{name} grad {pname}",
+                                        noise=n_grad[pname] * NOISE_SCALE[engine]))
+    print(f"{name}/{engine}/{step.mode}: worst gradient error {worst:.2e}")
+
+
 def test_fused_step_stream_options_do_not_change_results():
     """overlap_wgrad / parallel_branches only re-order independent work across forked streams."""
     from ta3n_b200.train import TrainStep

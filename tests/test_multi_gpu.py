@@ -36,7 +36,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q):
+VARIANTS = {"nccl-legacy": dict(mode="legacy", allreduce="nccl"),      # two graphs, NCCL overlapping the second
+            "peer-legacy": dict(mode="legacy", allreduce="peer"),      # one graph: step + library all-reduce + optimizer
+            "peer-phased": dict(mode="phased", allreduce="peer")}
+
+
+def _worker(rank, world, port, q, variant):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -49,8 +54,10 @@ def _worker(rank, world, port, q):
         xs, xt, labels = orc.synthetic_batch(world * B_LOCAL, _cfg())
         sl = shard_rows(world * B_LOCAL, rank, world)
         model = _build(dev)
-        step = TrainStep(model, B_LOCAL, B_LOCAL, (0.75, 0.75, 0.5), gamma=0.0, use_graph=True)   # split graphs
-        assert step.graphs[0][1] is not None
+        kw = VARIANTS[variant]
+        step = TrainStep(model, B_LOCAL, B_LOCAL, (0.75, 0.75, 0.5), gamma=0.0, use_graph=True, **kw)
+        assert (step.graphs[0][1] is not None) == (variant == "nccl-legacy")      # split graphs only around NCCL
+        assert (step.ar is not None) == (kw["allreduce"] == "peer")
         for _ in range(2):
             step(xs[sl], xt[sl], labels[sl])
         torch.cuda.synchronize()
@@ -59,7 +66,7 @@ def _worker(rank, world, port, q):
         # the same with the fused optimizer: 3 iterations, then all ranks must hold identical parameters
         model2 = _build(dev)
         opt_step = TrainStep(model2, B_LOCAL, B_LOCAL, (0.75, 0.75, 0.5), gamma=0.0, use_graph=True,
-                             optimizer=SGDNesterov(lr=0.05, clip_gradient=0.02))
+                             optimizer=SGDNesterov(lr=0.05, clip_gradient=0.02), **kw)
         for _ in range(3):
             opt_step(xs[sl], xt[sl], labels[sl])
         torch.cuda.synchronize()
@@ -73,14 +80,15 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_gpu_trainstep_matches_global_batch():
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_two_gpu_trainstep_matches_global_batch(variant):
     import ta3n_b200
     from ta3n_b200.train import SGDNesterov, TrainStep, flatten_parameters
     ta3n_b200.set_gemm_engine("fp32")
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, variant)) for r in range(world)]
     for p in procs:
         p.start()
     got = torch.from_numpy(q.get(timeout=300))
@@ -93,7 +101,7 @@ def test_two_gpu_trainstep_matches_global_batch():
     model = _build(dev)
     # gamma=0: every loss term is a plain mean over rows, so mean-of-shard-means == global mean exactly
     ref = TrainStep(model, world * B_LOCAL, world * B_LOCAL, (0.75, 0.75, 0.5), gamma=0.0, use_graph=True,
-                    overlap_allreduce=True)          # same bucket layout as the 2-rank run
+                    mode="legacy")                   # same bucket layout as the 2-rank run
     ref(xs, xt, labels)
     torch.cuda.synchronize()
     want = ref.flat_grad.cpu()
@@ -103,7 +111,7 @@ def test_two_gpu_trainstep_matches_global_batch():
     model2 = _build(dev)
     p0 = flatten_parameters(model2).clone()                    # initial values in bucket order
     ref2 = TrainStep(model2, world * B_LOCAL, world * B_LOCAL, (0.75, 0.75, 0.5), gamma=0.0, use_graph=True,
-                     overlap_allreduce=True, optimizer=SGDNesterov(lr=0.05, clip_gradient=0.02))
+                     mode="legacy", optimizer=SGDNesterov(lr=0.05, clip_gradient=0.02))
     for _ in range(3):
         ref2(xs, xt, labels)
     torch.cuda.synchronize()

@@ -32,7 +32,10 @@ tr = step.trace(True)
 flush.fill_(1)
 step.run()
 torch.cuda.synchronize()
-t = tr.cpu()
+t_all = tr.cpu()
+n_tasks = step.step_info()[0]
+t = t_all[:n_tasks]
+marks = t_all[n_tasks:].double()
 tag, sched, acc, done, body, synced = t[:, 0], t[:, 1], t[:, 2], t[:, 3], t[:, 4], t[:, 5]
 sm = tag & 0xFFFF
 typ = (tag >> 16) & 0xFF
@@ -81,3 +84,12 @@ busy = {}
 for i in range(len(t)):
     busy[int(sm[i])] = busy.get(int(sm[i]), 0.0) + (int(done[i]) - int(sched[i])) / 1e3
 print(f"  per-SM busy: min {min(busy.values()):.1f} max {max(busy.values()):.1f} mean {sum(busy.values()) / len(busy):.1f} us of {span:.1f}")
+
+# phase marks of the row tasks (warp 0 of each task): relpool [start, logits done, pooled, end], heads [start, logits, loss, end]
+ok = (marks[:, 0] > 0) & (marks[:, 3] > 0)
+if ok.any():
+    m = marks[ok]
+    print("  relpool phases (us): logits %.2f  pool %.2f  dropout+store %.2f" % (
+        float((m[:, 1] - m[:, 0]).mean()) / 1e3, float((m[:, 2] - m[:, 1]).mean()) / 1e3, float((m[:, 3] - m[:, 2]).mean()) / 1e3))
+    print("  heads phases (us): logits %.2f  loss %.2f  backward %.2f" % (
+        float((m[:, 5] - m[:, 4]).mean()) / 1e3, float((m[:, 6] - m[:, 5]).mean()) / 1e3, float((m[:, 7] - m[:, 6]).mean()) / 1e3))
