@@ -151,7 +151,7 @@ def measured_peaks():
 def pick_engine(requested):
     import ta3n_b200
     if requested == "auto":
-        requested = os.environ.get("TA3N_DEFAULT_ENGINE", "tf32")
+        requested = os.environ.get("TA3N_DEFAULT_ENGINE", "tf32x3")      # the library default = the parity-tested engine
     ta3n_b200.set_gemm_engine(requested)
     return requested
 

@@ -13,6 +13,7 @@ from . import build as _build
 
 TA3N_GEMM_FP32_SIMT = 0
 TA3N_GEMM_TF32_TCGEN05 = 1
+TA3N_GEMM_TF32X3_TCGEN05 = 2
 
 
 class RelationTable(C.Structure):
@@ -157,12 +158,12 @@ def ptr_array(ptrs):
 
 def set_gemm_engine(engine) -> None:
     """'tf32' (tcgen05 tensor cores; the library default) or 'fp32' (exact SIMT tiles)."""
-    code = {"fp32": TA3N_GEMM_FP32_SIMT, "tf32": TA3N_GEMM_TF32_TCGEN05}.get(engine, engine)
+    code = {"fp32": TA3N_GEMM_FP32_SIMT, "tf32": TA3N_GEMM_TF32_TCGEN05, "tf32x3": TA3N_GEMM_TF32X3_TCGEN05}.get(engine, engine)
     check(load().ta3n_set_gemm_engine(int(code)))
 
 
 def get_gemm_engine() -> str:
-    return {0: "fp32", 1: "tf32"}[load().ta3n_get_gemm_engine()]
+    return {0: "fp32", 1: "tf32", 2: "tf32x3"}[load().ta3n_get_gemm_engine()]
 
 
 def launch_count() -> int:

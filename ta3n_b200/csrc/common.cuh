@@ -114,7 +114,7 @@ inline int after_launch() {
 }
 
 inline std::atomic<int>& gemm_engine() {
-  static std::atomic<int> e{TA3N_GEMM_TF32_TCGEN05};   // the product engine; 'fp32' is the exact parity engine
+  static std::atomic<int> e{TA3N_GEMM_TF32X3_TCGEN05};   // the product engine; 'fp32' is the exact parity engine
   return e;
 }
 

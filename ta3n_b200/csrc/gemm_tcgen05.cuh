@@ -688,6 +688,247 @@ seg_gemm_tc_kernel(const __grid_constant__ GemmTable tab, const __grid_constant_
   }
 }
 
+// ---- the precise forward kernel ("tf32x3"): fp32-grade products from the tensor cores -------------------------
+// kind::tf32 keeps 10 mantissa bits of each operand: every forward GEMM is accurate to ~3e-4, and ~1.3e-4 of the
+// ReLU units behind them (pre-activation within that error of zero) come out with the wrong on/off state.  Each flip
+// moves a gradient entry by O(1), which is where the 1-2 % gradient deviation of the plain tf32 engine comes from
+// (tools/parity_report.py; with the pattern pinned the same gradients agree to 4e-4).  The forward layers therefore
+// run here with the operands split in two tf32 pieces (a = hi + lo, hi = the 10 mantissa bits the tensor core reads
+// from the raw fp32 word, lo = a - hi, exact):     a b ~= hi_a hi_b + lo_a hi_b + hi_a lo_b      (three MMAs per K step)
+// Two more things are needed for fp32 grade (measured, tools/x3_probe.py, profiles/README.md):
+//   * K is accumulated in CHUNKS of 256 inside the tensor core and the chunks are added in fp32 registers: over the
+//     full K = 2048 the tensor core's own accumulation limits the result to 5e-6 whatever the operands (three and four
+//     products give the same error); chunked, 6e-7 -- the error of an fp32 FFMA loop -- and no sign flips;
+//   * the tensor maps deliver the RAW fp32 words (no TMA rounding), so that hi + lo = a exactly.
+// The eight warps that wait for the accumulator in the plain kernel do the work: they compute the lo tiles of each
+// stage (shared memory -> shared memory, layout-agnostic: lo has the swizzle of its source), and drain a finished chunk
+// from TMEM (two accumulator buffers: the MMAs of chunk c+1 run while chunk c is added to the 64 running sums a thread
+// keeps), then run the usual fused epilogue on those registers.
+constexpr int X3_STAGES = 3;
+constexpr int X3_STAGE_BYTES = 2 * TC_STAGE_BYTES;            // [A | B | A_lo | B_lo]
+constexpr int X3_CHUNK = 8;                                   // slabs (256 K columns) per tensor-core accumulation
+constexpr int X3_THREADS = 320;                               // warp 0 TMA, warp 1 MMA, 8 worker warps
+constexpr int X3_TMEM_COLS = 256;
+constexpr int x3_smem_bytes() { return X3_STAGES * X3_STAGE_BYTES + 1024; }
+
+struct X3Shared {
+  uint64_t full_bar[X3_STAGES];      // TMA landed
+  uint64_t split_bar[X3_STAGES];     // the 8 worker warps have written the lo tiles
+  uint64_t empty_bar[X3_STAGES];     // the MMAs have read the stage
+  uint64_t chunk_full[2];            // accumulator buffer complete
+  uint64_t chunk_empty[2];           // ... drained by the 8 worker warps
+  uint32_t tmem_slot;
+};
+
+template <bool A_KMAJ, bool B_KMAJ>
+__global__ void __launch_bounds__(X3_THREADS, 1)
+seg_gemm_tc_x3_kernel(const __grid_constant__ GemmTable tab, const __grid_constant__ TcMaps maps,
+                      const __grid_constant__ TcSegMaps segmaps) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  __shared__ __align__(8) X3Shared sh;
+  __shared__ TileCtx ctx;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int tile = blockIdx.x;
+  load_tile_ctx(tab, tile, &ctx, segmaps.a, segmaps.b);
+  const Group& g = ctx.g;
+  int local = tile - g.tile_begin;
+  const int per_split = g.tiles_m * g.tiles_n;
+  const int split = local / per_split;
+  local -= split * per_split;
+  const int m0 = (local / g.tiles_n) * TC_BM;
+  const int n0 = (local % g.tiles_n) * TC_BN;
+  int c_begin, n_iter;
+  tc_chunk_range(ctx, split, &c_begin, &n_iter);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < X3_STAGES; ++s) {
+      mbar_init(&sh.full_bar[s], 1);
+      mbar_init(&sh.split_bar[s], 8);
+      mbar_init(&sh.empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sh.chunk_full[b], 1);
+      mbar_init(&sh.chunk_empty[b], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&sh.tmem_slot, X3_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh.tmem_slot;
+  pdl_wait();
+
+  const int n_chunks = (n_iter + X3_CHUNK - 1) / X3_CHUNK;
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0 && n_iter > 0) {
+      int seg = 0, k0 = 0;
+      {
+        int skip = c_begin;
+        while (seg < g.seg_count) {
+          const int nch = (ctx.seg[seg].len + TC_BK - 1) / TC_BK;
+          if (skip < nch) {
+            k0 = skip * TC_BK;
+            break;
+          }
+          skip -= nch;
+          ++seg;
+        }
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int stage = it % X3_STAGES;
+        const uint32_t phase = (uint32_t)(it / X3_STAGES) & 1u;
+        mbar_wait(&sh.empty_bar[stage], phase ^ 1u);
+        mbar_expect_tx(&sh.full_bar[stage], TC_STAGE_BYTES);
+        uint8_t* sA = smem + stage * X3_STAGE_BYTES;
+        uint8_t* sB = sA + TC_A_BYTES;
+        const CUtensorMap* ma = &maps.m[ctx.seg[seg].amap];
+        const CUtensorMap* mb = &maps.m[ctx.seg[seg].bmap];
+        if (A_KMAJ) {
+          tma_load_2d(sA, ma, &sh.full_bar[stage], k0, m0);
+        } else if (tab.pad_ & 1) {
+          tma_load_3d(sA, ma, &sh.full_bar[stage], 0, k0, m0 >> 5);
+        } else {
+#pragma unroll
+          for (int q = 0; q < TC_BM / 32; ++q) tma_load_2d(sA + q * 4096, ma, &sh.full_bar[stage], m0 + 32 * q, k0);
+        }
+        if (B_KMAJ) {
+          tma_load_2d(sB, mb, &sh.full_bar[stage], k0, n0);
+        } else if (tab.pad_ & 2) {
+          tma_load_3d(sB, mb, &sh.full_bar[stage], 0, k0, n0 >> 5);
+        } else {
+#pragma unroll
+          for (int q = 0; q < TC_BN / 32; ++q) tma_load_2d(sB + q * 4096, mb, &sh.full_bar[stage], n0 + 32 * q, k0);
+        }
+        k0 += TC_BK;
+        if (k0 >= ctx.seg[seg].len) {
+          ++seg;
+          k0 = 0;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: three products per K step, a fresh accumulator per chunk ----------------
+    if (lane == 0 && n_iter > 0) {
+      const uint32_t idesc = umma_idesc_tf32(A_KMAJ, B_KMAJ, TC_BM, TC_BN);
+      for (int it = 0; it < n_iter; ++it) {
+        const int stage = it % X3_STAGES;
+        const uint32_t phase = (uint32_t)(it / X3_STAGES) & 1u;
+        const int chunk = it / X3_CHUNK, cbuf = chunk & 1;
+        const bool chunk_first = it % X3_CHUNK == 0;
+        if (chunk_first) {
+          mbar_wait(&sh.chunk_empty[cbuf], ((uint32_t)(chunk >> 1) & 1u) ^ 1u);      // drained two chunks ago
+          tc_fence_after();
+        }
+        mbar_wait(&sh.split_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + stage * X3_STAGE_BYTES);
+        const uint32_t b_hi = a_hi + TC_A_BYTES;
+        const uint32_t a_lo = a_hi + TC_STAGE_BYTES, b_lo = b_hi + TC_STAGE_BYTES;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(cbuf * TC_BN);
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+          const uint64_t dah = A_KMAJ ? umma_desc_kmajor(a_hi, ks) : umma_desc_mnmajor(a_hi, ks);
+          const uint64_t dbh = B_KMAJ ? umma_desc_kmajor(b_hi, ks) : umma_desc_mnmajor(b_hi, ks);
+          const uint64_t dal = A_KMAJ ? umma_desc_kmajor(a_lo, ks) : umma_desc_mnmajor(a_lo, ks);
+          const uint64_t dbl = B_KMAJ ? umma_desc_kmajor(b_lo, ks) : umma_desc_mnmajor(b_lo, ks);
+          umma_tf32(tmem_d, dal, dbh, idesc, (chunk_first && ks == 0) ? 0u : 1u);      // small terms first
+          umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+          umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+        }
+        umma_commit(&sh.empty_bar[stage]);
+        if (it % X3_CHUNK == X3_CHUNK - 1 || it == n_iter - 1) umma_commit(&sh.chunk_full[cbuf]);
+      }
+    }
+  } else {
+    // ---------------- worker warps: lo tiles, chunk accumulation, epilogue ----------------
+    const int ew = warp - 2;
+    const int wt = ew * 32 + lane;                      // 0 .. 255
+    const int lq = (ew + 2) & 3;                        // TMEM lane quarter of this warp
+    const int chalf = ew / 4;                           // which 64 columns of the tile
+    float sum[2][32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum[c][j] = 0.f;
+    int drained = 0;
+    auto drain = [&](int chunk) {
+      const int cbuf = chunk & 1;
+      mbar_wait(&sh.chunk_full[cbuf], (uint32_t)(chunk >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(cbuf * TC_BN + (chalf * 2 + c) * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[c][j] += v[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.chunk_empty[cbuf]);
+    };
+    for (int it = 0; it < n_iter; ++it) {
+      const int stage = it % X3_STAGES;
+      const uint32_t phase = (uint32_t)(it / X3_STAGES) & 1u;
+      mbar_wait(&sh.full_bar[stage], phase);
+      const uint32_t hi = smem_u32(smem + stage * X3_STAGE_BYTES);
+#pragma unroll
+      for (int i = 0; i < TC_STAGE_BYTES / 16 / 256; ++i) {       // 8 float4 per thread: A and B tiles alike
+        const uint32_t off = (uint32_t)(wt + 256 * i) * 16u;
+        const float4 a = lds4(hi + off);
+        float4 l;
+        l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+        l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+        l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+        l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+        sts4(hi + TC_STAGE_BYTES + off, l);
+      }
+      fence_proxy_async();                              // generic-proxy writes -> the tensor core's reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.split_bar[stage]);
+      // a chunk is drained one slab into the next one (its MMAs have had time to finish: no bubble)
+      if (drained < n_chunks - 1 && it >= (drained + 1) * X3_CHUNK) drain(drained++);
+    }
+    while (drained < n_chunks) drain(drained++);
+
+    // ---- fused epilogue on the running sums (same code as tc_epilogue, accumulators already in registers) ----
+    const Group e = ctx.g;
+    const int m = m0 + lq * 32 + lane;
+    const int mode = e.ksplit > 1 ? TILE_PARTIAL : TILE_FINAL;
+    float* const obase = mode == TILE_PARTIAL ? e.partial + (size_t)split * e.M * e.N : e.C;
+    const int ldo = mode == TILE_PARTIAL ? e.N : e.ldc;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int nb = n0 + (chalf * 2 + c) * 32;
+      if (m < e.M && nb < e.N) {
+        float* orow = obase + (size_t)m * ldo + nb;
+        const int nvalid = min(32, e.N - nb);
+        if (mode == TILE_FINAL) {
+          TA3N_EPI_DISPATCH(e.flags, { epilogue_row32<EPI_F>(e, m, nb, nvalid, sum[c]); })
+        }
+        if (nb + 32 <= e.N && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(orow + j) = make_float4(sum[c][j], sum[c][j + 1], sum[c][j + 2], sum[c][j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < e.N) orow[j] = sum[c][j];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, X3_TMEM_COLS);
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -711,6 +952,7 @@ struct DeviceInfo {
   int sm_count = 0;
   bool configured[8] = {false, false, false, false, false, false, false, false};
   bool step_configured = false;      // step_kernel.cuh kernels (ta3n_api.cu)
+  bool x3_configured = false;        // seg_gemm_tc_x3_kernel
 };
 inline std::mutex& device_mu() {
   static std::mutex mu;
@@ -739,9 +981,10 @@ struct MapKey {
   int box_inner, box_outer;
   int atom32;   // 1: SWIZZLE_128B_ATOM_32B (MN-major operands), 0: SWIZZLE_128B
   int rank3;    // 1: MN-major operand as {32 floats, outer rows, inner/32 groups}, box {32, box_outer, 4}
+  int raw;      // 1: FLOAT32 (the raw words, precise kernel); 0: TFLOAT32 (TMA rounds to tf32)
   bool operator<(const MapKey& o) const {
-    return std::tie(ptr, inner, outer, ld, box_inner, box_outer, atom32, rank3) <
-           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer, o.atom32, o.rank3);
+    return std::tie(ptr, inner, outer, ld, box_inner, box_outer, atom32, rank3, raw) <
+           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer, o.atom32, o.rank3, o.raw);
   }
 };
 
@@ -766,7 +1009,7 @@ inline int encode_map(const MapKey& k, CUtensorMap* out) {
   // TFLOAT32: the TMA unit rounds fp32 -> tf32 (round to nearest) while filling shared memory, so the
   // tensor core never sees the truncation bias (-2^-11 relative per operand) it would apply to raw fp32
   // bit patterns (measured in round 1: a -7e-4 bias per GEMM with FLOAT32 maps).
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, k.rank3 ? 3 : 2,
+  CUresult r = fn(out, k.raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, k.rank3 ? 3 : 2,
                   const_cast<void*>(k.ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   k.atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -796,9 +1039,10 @@ inline bool tc_group_ok(const GemmPlan& plan, const Group& g) {
 
 // tensor-map keys of one segment of a group (shared by the per-launch and the step-kernel planners)
 inline void tc_seg_keys(const Seg& s, const Group& g, bool a_kmaj, bool b_kmaj, bool a3d, bool b3d, MapKey* ka,
-                        MapKey* kb) {
-  *ka = a_kmaj ? MapKey{s.A, s.len, g.M, s.lda, TC_BK, TC_BM, 0, 0} : MapKey{s.A, g.M, s.len, s.lda, 32, TC_BK, 1, a3d ? 1 : 0};
-  *kb = b_kmaj ? MapKey{s.B, s.len, g.N, s.ldb, TC_BK, TC_BN, 0, 0} : MapKey{s.B, g.N, s.len, s.ldb, 32, TC_BK, 1, b3d ? 1 : 0};
+                        MapKey* kb, bool raw = false) {
+  const int rw = raw ? 1 : 0;
+  *ka = a_kmaj ? MapKey{s.A, s.len, g.M, s.lda, TC_BK, TC_BM, 0, 0, rw} : MapKey{s.A, g.M, s.len, s.lda, 32, TC_BK, 1, a3d ? 1 : 0, rw};
+  *kb = b_kmaj ? MapKey{s.B, s.len, g.N, s.ldb, TC_BK, TC_BN, 0, 0, rw} : MapKey{s.B, g.N, s.len, s.ldb, 32, TC_BK, 1, b3d ? 1 : 0, rw};
 }
 
 template <bool A_KMAJ, bool B_KMAJ, int STAGES>
@@ -820,6 +1064,23 @@ inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSe
   pre_launch(label, stream);
   launch_kernel(seg_gemm_tc_kernel<A_KMAJ, B_KMAJ, STAGES>, tab.total_tiles, tc_threads(STAGES),
                 tc_smem_bytes(STAGES), stream, tab, maps, sm, first_wave);
+  return after_launch();
+}
+
+// the precise forward kernel (K-major x K-major: every forward layer)
+inline int tc_launch_x3(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream, const char* label) {
+  {
+    std::lock_guard<std::mutex> lock(device_mu());
+    DeviceInfo* d = device_info();
+    if (!d) return fail(TA3N_ERR_CUDA, "cudaGetDevice failed");
+    if (!d->x3_configured) {
+      TA3N_CUDA(cudaFuncSetAttribute(seg_gemm_tc_x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     x3_smem_bytes()));
+      d->x3_configured = true;
+    }
+  }
+  pre_launch(label, stream);
+  launch_kernel(seg_gemm_tc_x3_kernel<true, true>, tab.total_tiles, X3_THREADS, x3_smem_bytes(), stream, tab, maps, sm);
   return after_launch();
 }
 
@@ -859,7 +1120,7 @@ inline void tc_rank3_flags(const GemmPlan& plan, bool* a3d, bool* b3d) {
 }
 
 // Launch `plan` (all groups eligible) on the tcgen05 engine.
-inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
+inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool precise = false) {
   // longest-K groups first (see the tile remap in the kernel): LPT-style balance of the tensor pipe
   std::vector<int> order(plan_in.groups.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
@@ -889,7 +1150,7 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
       std::map<MapKey, int> trial = local;
       for (int i = 0; i < src.seg_count; ++i) {
         MapKey ka, kb;
-        tc_seg_keys(plan.segs[src.seg_begin + i], src, plan.a_kmaj, plan.b_kmaj, a3d, b3d, &ka, &kb);
+        tc_seg_keys(plan.segs[src.seg_begin + i], src, plan.a_kmaj, plan.b_kmaj, a3d, b3d, &ka, &kb, precise);
         for (const MapKey& k : {ka, kb})
           if (!trial.count(k)) trial[k] = nmaps + fresh++;
         keys.push_back({ka, kb});
@@ -925,7 +1186,9 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream) {
     tab.total_tiles = tiles;
     tab.pad_ = (a3d ? 1 : 0) | (b3d ? 2 : 0);
     if (tiles > 0) {
-      if (plan.a_kmaj && plan.b_kmaj)
+      if (precise)
+        TA3N_TRY(tc_launch_x3(tab, maps, sm, stream, plan.label));
+      else if (plan.a_kmaj && plan.b_kmaj)
         TA3N_TRY((tc_launch_one<true, true>(tab, maps, sm, stream, plan.label)));
       else if (plan.a_kmaj && !plan.b_kmaj)
         TA3N_TRY((tc_launch_one<true, false>(tab, maps, sm, stream, plan.label)));
@@ -953,13 +1216,15 @@ inline int run_gemm(GemmPlan& plan, cudaStream_t stream, Arena* splitk_arena = n
     if (g.M <= 0 || g.N <= 0 || g.seg_count <= 0)
       return fail(TA3N_ERR_INVALID, "seg_gemm: empty group M=%d N=%d segs=%d", g.M, g.N, g.seg_count);
   const int engine = gemm_engine().load();
-  if (engine == TA3N_GEMM_TF32_TCGEN05) {
+  if (engine == TA3N_GEMM_TF32_TCGEN05 || engine == TA3N_GEMM_TF32X3_TCGEN05) {
+    // the precise kernel for the forward layers of the x3 engine (K-major operands); everything else plain tf32
+    const bool precise = engine == TA3N_GEMM_TF32X3_TCGEN05 && plan.precise && plan.a_kmaj && plan.b_kmaj;
     std::vector<int> tc_idx, simt_idx;
     for (int i = 0; i < (int)plan.groups.size(); ++i) (tc_group_ok(plan, plan.groups[i]) ? tc_idx : simt_idx).push_back(i);
     if (!tc_idx.empty()) {
       GemmPlan tc = sub_plan(plan, tc_idx);
       plan_splitk(tc, splitk_arena, TC_BM, TC_BN, TC_BK, 4);
-      TA3N_TRY(launch_tc(tc, stream));
+      TA3N_TRY(launch_tc(tc, stream, precise));
     }
     if (!simt_idx.empty()) {
       GemmPlan rest = sub_plan(plan, simt_idx);

@@ -133,6 +133,7 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
     GemmPlan& p = P->g1;
     p = GemmPlan();
     p.label = "step_shared_fc_fwd";
+    p.precise = true;
     const float* xs[2] = {d->x_src, d->x_tgt};
     const int rows[2] = {Rs, Rt};
     size_t row0 = 0;
@@ -165,6 +166,7 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
     GemmPlan& p = P->g2;
     p = GemmPlan();
     p.label = "step_fwd_batch";
+    p.precise = true;
     P->g2_frame_group = 0;
     Group& gf = p.add_group(MT, F, d->hid_f, F);
     gf.flags = EPI_BIAS | EPI_RELU;
@@ -188,6 +190,7 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
     GemmPlan& p = P->g3;
     p = GemmPlan();
     p.label = "step_rel_hidden";
+    p.precise = true;
     for (int i = 0; i < R; ++i) {
       TA3N_REQUIRE(d->W1r_host[i] && d->b1r_host[i] && d->W2r_host[i] && d->b2r_host[i], "null relation weight");
       Group& g = p.add_group(M, H, d->hid_r + (size_t)i * plane, H);
@@ -262,6 +265,7 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
     GemmPlan& p = P->g4a;
     p = GemmPlan();
     p.label = "step_vid_hidden";
+    p.precise = true;
     Group& g = p.add_group(M, H, d->hid_v, H);
     g.flags = EPI_BIAS | EPI_RELU;
     g.bias = d->b1v;

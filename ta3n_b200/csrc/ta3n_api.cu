@@ -133,6 +133,7 @@ struct FwdBatch {
   void reset() {
     plan = GemmPlan();
     plan.label = "fwd_batch";
+    plan.precise = true;
     post.clear();
   }
 };
@@ -218,7 +219,7 @@ const char* ta3n_last_error(void) { return last_error_buf(); }
 uint64_t ta3n_launch_count(void) { return launch_counter().load(); }
 void ta3n_reset_launch_count(void) { launch_counter().store(0); }
 int ta3n_set_gemm_engine(int engine) {
-  if (engine != TA3N_GEMM_FP32_SIMT && engine != TA3N_GEMM_TF32_TCGEN05)
+  if (engine != TA3N_GEMM_FP32_SIMT && engine != TA3N_GEMM_TF32_TCGEN05 && engine != TA3N_GEMM_TF32X3_TCGEN05)
     return fail(TA3N_ERR_INVALID, "unknown GEMM engine %d", engine);
   gemm_engine().store(engine);
   return TA3N_OK;
@@ -284,6 +285,7 @@ int ta3n_shared_fc_fwd(const float* x_src, int rows_src, const float* x_tgt, int
   const DropArgs d = make_drop(drop);
   GemmPlan plan;
     plan.label = "shared_fc_fwd";
+    plan.precise = true;
   const float* xs[2] = {x_src, x_tgt};
   const int rows[2] = {rows_src, rows_tgt};
   size_t row0 = 0;
@@ -348,6 +350,7 @@ int ta3n_disc_fwd(const float* x, int rows, int K, int Kh, const float* W1, cons
   TA3N_REQUIRE(x && W1 && b1 && W2 && b2 && hidden && logits, "null pointer");
   GemmPlan plan;
     plan.label = "disc_fwd";
+    plan.precise = true;
   Group& g = plan.add_group(rows, Kh, hidden, Kh);
   g.flags = EPI_BIAS | EPI_RELU;
   g.bias = b1;
@@ -466,6 +469,7 @@ int ta3n_trn_fwd(const float* x, int M, int F, int H, const ta3n_relation_table*
   const int ldx = L.T * F;
   GemmPlan plan;
     plan.label = "trn_fwd";
+    plan.precise = true;
   plan.load_flags = relu_input ? LD_RELU_A : 0;
   for (int q = 0; q < L.n_rel; ++q) {
     const int i = L.rel_scale[q], s = L.scale_size[i];
@@ -608,6 +612,7 @@ int ta3n_relattn_fwd(const float* feat_rel, int M, int R, int H, const float* co
                "null pointer");
   GemmPlan plan;
     plan.label = "relattn_fwd";
+    plan.precise = true;
   PtrTable w2, b2;
   memset(&w2, 0, sizeof(w2));
   memset(&b2, 0, sizeof(b2));
@@ -1141,6 +1146,7 @@ int ta3n_gemm_tn(const float* A, const float* B, float* C, int M, int N, int K, 
   TA3N_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bad arguments");
   GemmPlan plan;
     plan.label = "gemm_tn";
+    plan.precise = true;
   plan.add_group(M, N, C, N);
   plan.add_seg(A, K, B, K, K);
   return run_gemm(plan, S(stream));

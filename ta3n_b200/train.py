@@ -19,6 +19,7 @@ discriminator + shared layer backward) computes; only the second, smaller all-re
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
@@ -104,10 +105,10 @@ class TrainStep:
                  optimizer: Optional[SGDNesterov] = None, mode: Optional[str] = None,
                  class_weight: Optional[torch.Tensor] = None, domain_weight: Sequence[float] = (1.0, 1.0),
                  allreduce: Optional[str] = None):
-        """mode: 'fused' (default when the model has no frame attention) = the whole forward + loss + backward as ONE
-        persistent kernel (C ABI ta3n_step_build / ta3n_step_run); 'phased' = the same work as 9 launches
-        (ta3n_step_run_phased); 'legacy' = the round-1 per-operator sequence (25 launches; the only mode that
-        supports use_attn_frame).  class_weight / domain_weight: the weights of criterion / criterion_domain
+        """mode: 'legacy' (default) = the per-operator sequence (25 launches in one CUDA graph; the only mode that
+        supports use_attn_frame); 'phased' = the step program as 14 launches (ta3n_step_run_phased; default when class /
+        domain weights or a scheduled beta are given); 'fused' = the same program as ONE persistent kernel (C ABI
+        ta3n_step_build / ta3n_step_run; plain tf32 tiles whatever engine is selected).  class_weight / domain_weight: the weights of criterion / criterion_domain
         (main.py:160-167, 204-205; fused and phased modes).  A negative beta entry selects the DANN schedule for that
         level (main.py:350-352): call set_progress(p) every step.
         allreduce (world > 1): 'peer' = this library's one-kernel all-reduce over NVLink peer / NVSwitch multicast
@@ -138,10 +139,14 @@ class TrainStep:
             self.flags |= 8
         # split the step in two graphs around the first gradient bucket only when there is something to overlap
         if mode is None:
-            # the fused kernel is a tcgen05 kernel; with the exact fp32 engine selected the same step runs phased
-            # (its grouped GEMM launches honour the engine), so engine-parametrised callers get what they selected
-            mode = "legacy" if model.use_attn_frame != "none" else \
-                ("fused" if _lib.get_gemm_engine() == "tf32" else "phased")
+            # 'legacy' (the per-operator sequence) is the fastest executor measured so far and honours the selected
+            # GEMM engine; the features only the step program has (class / domain weights, the DANN beta
+            # schedule) select 'phased', which honours the engine too.  'fused' (one persistent kernel, plain tf32
+            # tiles only) is opt-in.
+            needs_step = class_weight is not None or any(float(b) < 0 for b in beta) or \
+                tuple(float(w) for w in domain_weight) != (1.0, 1.0)
+            mode = "phased" if (needs_step and model.use_attn_frame == "none") else "legacy"
+            mode = os.environ.get("TA3N_STEP_MODE", mode)
         if mode not in ("fused", "phased", "legacy"):
             raise ValueError(f"unknown TrainStep mode {mode!r}")
         if mode != "legacy" and model.use_attn_frame != "none":

@@ -26,11 +26,11 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(autouse=True)
 def _exact_engine_unless_parametrised(request):
     """GPU tests that do not ask for the ``engine`` fixture were written against the exact fp32 engine; the library
-    default is the product engine (tf32), so select fp32 for them explicitly and restore the default afterwards."""
+    default is the product engine (tf32x3), so select fp32 for them explicitly and restore the default afterwards."""
     if "gpu" not in request.keywords:
         yield
         return
     import ta3n_b200
     ta3n_b200.set_gemm_engine("fp32")
     yield
-    ta3n_b200.set_gemm_engine("tf32")
+    ta3n_b200.set_gemm_engine("tf32x3")

@@ -39,13 +39,14 @@ def test_every_declared_symbol_is_exported(lib):
 def test_abi_version_and_engine_switch(lib):
     from ta3n_b200 import _lib
     assert lib.ta3n_abi_version() == 2
+    assert _lib.get_gemm_engine() == "tf32x3"          # the library default: the parity-tested product engine
     _lib.set_gemm_engine("tf32")
     assert _lib.get_gemm_engine() == "tf32"
     _lib.set_gemm_engine("fp32")
     assert _lib.get_gemm_engine() == "fp32"
     assert lib.ta3n_set_gemm_engine(7) != 0
     assert b"unknown GEMM engine" in lib.ta3n_last_error()
-    _lib.set_gemm_engine("tf32")          # the library default
+    _lib.set_gemm_engine("tf32x3")          # the library default
 
 
 def test_argument_validation_needs_no_gpu(lib):

@@ -17,21 +17,19 @@ from tests.golden_util import (TOL_PATH, abs_err, assert_close, check_grads_agai
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = ["fp32", "tf32"]
-TOL = {"fp32": 2e-4, "tf32": TOL_PATH}
-if os.environ.get("TA3N_TEST_TF32X3") == "1":     # experimental engine: held to the fp32 bounds
-    ENGINES.append("tf32x3")
-    TOL["tf32x3"] = 2e-4
-# Gradients under the tf32 engine, compared with the fp64 network WITHOUT pinning the activation
-# pattern: every product is accurate to ~3e-4, but ~2e-4 of the ReLU units sit within rounding error
-# of zero and flip, and each flip moves a gradient entry by O(1) -> normwise ~sqrt(2e-4) ~ 1-2.5e-2
-# (measured, tools/parity_report.py).  Inherent to ANY reduced-precision forward (cuBLAS TF32 and bf16
-# included).  With the realised pattern pinned the gradients agree to 2e-3 again
-# (test_tf32_gradients_match_oracle_on_realised_activation_pattern).
-GRAD_TOL = {"fp32": 2 * 2e-4, "tf32": 5e-2, "tf32x3": 2 * 2e-4}
+# Engines: "fp32" = exact SIMT tiles; "tf32x3" = the PRODUCT engine (tcgen05; forward layers at fp32 grade, backward
+# GEMMs plain tf32); "tf32" = plain tf32 everywhere (fastest; its forward error flips ~1e-4 of the ReLU units, which
+# costs 1-2 % of gradient accuracy -- kept as an option, held to a documented looser bound).
+ENGINES = ["fp32", "tf32x3", "tf32"]
+TOL = {"fp32": 2e-4, "tf32x3": 2e-4, "tf32": TOL_PATH}
+# Gradients: the product engine is held to the path's 1e-3 (north_star) with the same 8x noise-floor allowance as the
+# exact engine.  Plain tf32, compared with the fp64 network WITHOUT pinning the activation pattern, carries the ReLU
+# flips of its forward: normwise ~sqrt(2e-4) ~ 1-2.5e-2 (tools/parity_report.py); with the realised pattern pinned it
+# agrees to 2e-3 again (test_tf32_gradients_match_oracle_on_realised_activation_pattern).
+GRAD_TOL = {"fp32": 2 * 2e-4, "tf32x3": 1e-3, "tf32": 5e-2}
 # Rounding-noise floor of sums that cancel (bias gradients of the domain heads): measured as
-# ||ref_fp32 - ref_fp64|| for the fp32 engine; tf32 carries 13 fewer mantissa bits.
-NOISE_SCALE = {"fp32": 1.0, "tf32": 2.0 ** 13, "tf32x3": 8.0}
+# ||ref_fp32 - ref_fp64|| per tensor; the allowance is 8 x NOISE_SCALE x floor.
+NOISE_SCALE = {"fp32": 1.0, "tf32x3": 1.0, "tf32": 2.0 ** 13}
 
 
 def _dev():
@@ -43,7 +41,7 @@ def engine(request):
     import ta3n_b200
     ta3n_b200.set_gemm_engine(request.param)
     yield request.param
-    ta3n_b200.set_gemm_engine("fp32")
+    ta3n_b200.set_gemm_engine("tf32x3")      # back to the library default
 
 
 def build_model(cfg: orc.PathConfig, params, train: bool):
@@ -333,7 +331,7 @@ def test_full_size_gradient_shards_sum_to_full_batch(engine):
 
     full = grads_of(slice(0, 256))
     h0, h1 = grads_of(slice(0, 128)), grads_of(slice(128, 256))
-    tol = 5e-4 if engine == "fp32" else GRAD_TOL["tf32"]
+    tol = 5e-4 if engine == "fp32" else GRAD_TOL[engine]
     for k in full:
         # noise floor: the domain-head bias gradients are sums of opposite-sign halves (~1e-7 left)
         assert_close(0.5 * (h0[k] + h1[k]), full[k], tol, f"shard-sum {k}", noise=2e-8)

@@ -62,6 +62,10 @@ def report(tag, loss, grads, ref_loss, ref):
 
 l_leg, g_leg, _, _ = run("legacy", "fp32")
 report("legacy fp32 vs oracle", l_leg, g_leg, l64, g64)
+l_x3, g_x3, _, _ = run("legacy", "tf32x3")
+report("legacy tf32x3 vs oracle", l_x3, g_x3, l64, g64)
+l_x3p, g_x3p, _, _ = run("phased", "tf32x3")
+report("phased tf32x3 vs oracle", l_x3p, g_x3p, l64, g64)
 l_ph, g_ph, _, _ = run("phased", "fp32")
 report("phased fp32 vs oracle", l_ph, g_ph, l64, g64)
 l_pt, g_pt, _, _ = run("phased", "tf32")
@@ -91,7 +95,7 @@ rep = _lib.timing_report()
 _lib.timing_enable(False)
 print("phased per launch (us):", {k: round(v[1] / 10 * 1e3, 1) for k, v in rep.items()}, flush=True)
 # timing
-for mode, eng in (("legacy", "tf32"), ("phased", "tf32"), ("fused", "tf32")):
+for mode, eng in (("legacy", "tf32"), ("legacy", "tf32x3"), ("phased", "tf32"), ("phased", "tf32x3"), ("fused", "tf32")):
     ta3n_b200.set_gemm_engine(eng)
     m = build()
     step = TrainStep(m, bs, bt, beta, gamma=0.003, use_graph=True, mode=mode)

@@ -63,4 +63,5 @@ for (M, N, K, wscale, relu_in) in [(2560, 512, 2048, 0.001, False), (512, 256, 2
         Cc += gemm(Ah[:, s].contiguous(), Bh[:, s].contiguous(), "tf32") + gemm(Al[:, s].contiguous(), Bh[:, s].contiguous(), "tf32") + \
             gemm(Ah[:, s].contiguous(), Bl[:, s].contiguous(), "tf32")
     report("x3, K by 256", Cc)
+    report("engine tf32x3", gemm(A, B, "tf32x3"))
     report("torch fp32", (A @ B.t()))
