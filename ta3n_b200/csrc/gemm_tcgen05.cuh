@@ -952,7 +952,7 @@ struct DeviceInfo {
   int sm_count = 0;
   bool configured[8] = {false, false, false, false, false, false, false, false};
   bool step_configured = false;      // step_kernel.cuh kernels (ta3n_api.cu)
-  bool x3_configured = false;        // seg_gemm_tc_x3_kernel
+  bool x3_configured[4] = {false, false, false, false};      // seg_gemm_tc_x3_kernel, per operand layout
 };
 inline std::mutex& device_mu() {
   static std::mutex mu;
@@ -1067,20 +1067,22 @@ inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSe
   return after_launch();
 }
 
-// the precise forward kernel (K-major x K-major: every forward layer)
+// the precise kernel, per operand layout
+template <bool A_KMAJ, bool B_KMAJ>
 inline int tc_launch_x3(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream, const char* label) {
+  constexpr int slot = (A_KMAJ ? 0 : 1) + (B_KMAJ ? 0 : 2);
   {
     std::lock_guard<std::mutex> lock(device_mu());
     DeviceInfo* d = device_info();
     if (!d) return fail(TA3N_ERR_CUDA, "cudaGetDevice failed");
-    if (!d->x3_configured) {
-      TA3N_CUDA(cudaFuncSetAttribute(seg_gemm_tc_x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (!d->x3_configured[slot]) {
+      TA3N_CUDA(cudaFuncSetAttribute(seg_gemm_tc_x3_kernel<A_KMAJ, B_KMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      x3_smem_bytes()));
-      d->x3_configured = true;
+      d->x3_configured[slot] = true;
     }
   }
   pre_launch(label, stream);
-  launch_kernel(seg_gemm_tc_x3_kernel<true, true>, tab.total_tiles, X3_THREADS, x3_smem_bytes(), stream, tab, maps, sm);
+  launch_kernel(seg_gemm_tc_x3_kernel<A_KMAJ, B_KMAJ>, tab.total_tiles, X3_THREADS, x3_smem_bytes(), stream, tab, maps, sm);
   return after_launch();
 }
 
@@ -1186,8 +1188,14 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool precise 
     tab.total_tiles = tiles;
     tab.pad_ = (a3d ? 1 : 0) | (b3d ? 2 : 0);
     if (tiles > 0) {
-      if (precise)
-        TA3N_TRY(tc_launch_x3(tab, maps, sm, stream, plan.label));
+      if (precise && plan.a_kmaj && plan.b_kmaj)
+        TA3N_TRY((tc_launch_x3<true, true>(tab, maps, sm, stream, plan.label)));
+      else if (precise && plan.a_kmaj && !plan.b_kmaj)
+        TA3N_TRY((tc_launch_x3<true, false>(tab, maps, sm, stream, plan.label)));
+      else if (precise && !plan.a_kmaj && !plan.b_kmaj)
+        TA3N_TRY((tc_launch_x3<false, false>(tab, maps, sm, stream, plan.label)));
+      else if (precise)
+        TA3N_TRY((tc_launch_x3<false, true>(tab, maps, sm, stream, plan.label)));
       else if (plan.a_kmaj && plan.b_kmaj)
         TA3N_TRY((tc_launch_one<true, true>(tab, maps, sm, stream, plan.label)));
       else if (plan.a_kmaj && !plan.b_kmaj)
@@ -1207,6 +1215,14 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool precise 
   return TA3N_OK;
 }
 
+inline bool x3_dgrad_enabled() {      // TA3N_X3_DGRAD=0: data-gradient GEMMs of the x3 engine as plain tf32 (A/B measurements)
+  static const bool on = []() {
+    const char* e = getenv("TA3N_X3_DGRAD");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // Run a plan.  With the tf32 engine selected, every group the tensor-core kernel can take runs
 // there; the rest (tiny heads, unaligned operands, ReLU-on-load) runs on the fp32 SIMT engine --
 // still CUDA, never the CPU.
@@ -1218,7 +1234,7 @@ inline int run_gemm(GemmPlan& plan, cudaStream_t stream, Arena* splitk_arena = n
   const int engine = gemm_engine().load();
   if (engine == TA3N_GEMM_TF32_TCGEN05 || engine == TA3N_GEMM_TF32X3_TCGEN05) {
     // the precise kernel for the forward layers of the x3 engine (K-major operands); everything else plain tf32
-    const bool precise = engine == TA3N_GEMM_TF32X3_TCGEN05 && plan.precise && plan.a_kmaj && plan.b_kmaj;
+    const bool precise = engine == TA3N_GEMM_TF32X3_TCGEN05 && (plan.precise || (plan.precise_dgrad && x3_dgrad_enabled()));
     std::vector<int> tc_idx, simt_idx;
     for (int i = 0; i < (int)plan.groups.size(); ++i) (tc_group_ok(plan, plan.groups[i]) ? tc_idx : simt_idx).push_back(i);
     if (!tc_idx.empty()) {

@@ -277,6 +277,7 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
     GemmPlan& p = P->g4b;
     p = GemmPlan();
     p.label = "step_vid_dgrad";
+    p.precise_dgrad = true;
     p.a_kmaj = true;
     p.b_kmaj = false;
     Group& g = p.add_group(M, H, sc.G, H);
@@ -308,6 +309,7 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
     GemmPlan& p = P->g5;
     p = GemmPlan();
     p.label = "step_dgrad_a";
+    p.precise_dgrad = true;
     p.a_kmaj = true;
     p.b_kmaj = false;
     for (int i = 0; i < R; ++i) {
@@ -343,6 +345,7 @@ inline int build_step_program(const ta3n_step_desc* d, StepProgram* P, bool dry 
     GemmPlan& p = P->g6;
     p = GemmPlan();
     p.label = "step_dgrad_b";
+    p.precise_dgrad = true;
     p.a_kmaj = true;
     p.b_kmaj = false;
     for (int t = 0; t < T; ++t) {

@@ -412,6 +412,7 @@ int ta3n_disc_bwd(const float* x, int rows, int K, int Kh, const float* W1, cons
   if (dx) {  // dx (+)= -beta * dH W1
     GemmPlan plan;
     plan.label = "disc_dgrad";
+    plan.precise_dgrad = true;
     plan.a_kmaj = true;
     plan.b_kmaj = false;
     Group& g = plan.add_group(rows, K, dx, K);
@@ -566,6 +567,7 @@ int ta3n_trn_bwd(const float* x, int M, int F, int H, const ta3n_relation_table*
   if (dx) {  // dgrad, deterministic per frame: dx[:, t, :] = sum_{(q,j): tau_q[j]=t} dz_q W_i[:, jF:(j+1)F]
     GemmPlan plan;
     plan.label = "trn_dgrad";
+    plan.precise_dgrad = true;
     plan.a_kmaj = true;
     plan.b_kmaj = false;
     std::vector<int> untouched;
@@ -698,6 +700,7 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
   {  // d_feat_rel[:, i, :] = (w_i + 1) G - beta * dHid_i W1_i
     GemmPlan plan;
     plan.label = "relattn_dgrad";
+    plan.precise_dgrad = true;
     plan.a_kmaj = true;
     plan.b_kmaj = false;
     for (int i = 0; i < R; ++i) {
