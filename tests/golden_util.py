@@ -76,7 +76,7 @@ def check_outputs_against_golden(z, case: str, outs, tol: float, stride: int):
     return worst
 
 
-def check_grads_against_golden(z, case: str, grads: dict, used: list, tol: float, stride: int):
+def check_grads_against_golden(z, case: str, grads: dict, used: list, tol: float, stride: int, noise_scale: float = 1.0):
     worst = 0.0
     for name in used:
         g = grads[name]
@@ -85,11 +85,11 @@ def check_grads_against_golden(z, case: str, grads: dict, used: list, tol: float
         # rounding-noise floor of this gradient: the reference's own |fp32 - fp64|, but never below a few
         # fp32 ulps of the O(1e-2) summands of the domain-head bias sums (their opposite-sign halves cancel
         # to ~1e-7, and ONE sample of |fp32 - fp64| can come out luckily small)
-        noise = max(float(z[f"{case}/grad_noise/{name}"]), 4e-9)
+        noise = max(float(z[f"{case}/grad_noise/{name}"]), 4e-9) * noise_scale
         got_norm = g.detach().double().norm().item()
         assert abs(got_norm - ref_norm) <= tol * ref_norm + 8 * noise, \
             f"{case}: grad norm {name}: {got_norm:.6e} vs {ref_norm:.6e} (noise {noise:.2e})"
         worst = max(worst, assert_close(sample(g, stride), z[f"{case}/grad_sample/{name}"], tol * 4,
                                         f"{case}:grad_sample:{name}",
-                                        noise=max(float(z[f"{case}/grad_sample_noise/{name}"]), 4e-9)))
+                                        noise=max(float(z[f"{case}/grad_sample_noise/{name}"]), 4e-9) * noise_scale))
     return worst
