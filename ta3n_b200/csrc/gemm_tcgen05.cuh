@@ -1241,13 +1241,13 @@ inline int run_gemm(GemmPlan& plan, cudaStream_t stream, Arena* splitk_arena = n
     const bool precise = engine == TA3N_GEMM_TF32X3_TCGEN05 && (plan.precise || (plan.precise_dgrad && x3_dgrad_enabled()));
     std::vector<int> tc_idx, simt_idx;
     // x3 engine: the small weight-gradient GEMMs (the 256 x 256 layers of the video / relation discriminators,
-    // <= 0.15 GFLOP each) run on the exact SIMT engine.  Near the adversarial equilibrium their source and target
+    // <= 0.3 GFLOP each) run on the exact SIMT engine.  Near the adversarial equilibrium their source and target
     // halves cancel, which amplifies the 3e-4 of a tf32 product to 4e-3 of the net gradient (cfg3, measured); as
     // exact tiles they cost one small launch (~6 us per step).
     const bool small_exact = engine == TA3N_GEMM_TF32X3_TCGEN05 && !plan.a_kmaj && !plan.b_kmaj;
     for (int i = 0; i < (int)plan.groups.size(); ++i) {
       const Group& g = plan.groups[i];
-      const bool tiny = small_exact && 2.0 * g.M * g.N * (double)plan.k_total(g) <= 1.5e8;
+      const bool tiny = small_exact && (long)g.M * g.N <= 256L * 256L && 2.0 * g.M * g.N * (double)plan.k_total(g) <= 3e8;
       ((tc_group_ok(plan, g) && !tiny) ? tc_idx : simt_idx).push_back(i);
     }
     if (!tc_idx.empty()) {
