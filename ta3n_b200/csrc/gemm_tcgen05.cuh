@@ -1241,14 +1241,23 @@ inline int run_gemm(GemmPlan& plan, cudaStream_t stream, Arena* splitk_arena = n
     const bool precise = engine == TA3N_GEMM_TF32X3_TCGEN05 && (plan.precise || (plan.precise_dgrad && x3_dgrad_enabled()));
     std::vector<int> tc_idx, simt_idx;
     // x3 engine: the small weight-gradient GEMMs (the 256 x 256 layers of the video / relation discriminators,
-    // <= 0.3 GFLOP each) run on the exact SIMT engine.  Near the adversarial equilibrium their source and target
-    // halves cancel, which amplifies the 3e-4 of a tf32 product to 4e-3 of the net gradient (cfg3, measured); as
-    // exact tiles they cost one small launch (~6 us per step).
-    const bool small_exact = engine == TA3N_GEMM_TF32X3_TCGEN05 && !plan.a_kmaj && !plan.b_kmaj;
+    // <= 0.3 GFLOP each) run on the precise kernel.  Near the adversarial equilibrium their source and target
+    // halves cancel, which amplifies the 3e-4 of a tf32 product to 4e-3 of the net gradient (cfg3, measured).
+    // (On the exact SIMT engine the same five groups cost 64 us; as one 20-tile launch of the x3 kernel ~15 us.)
+    const bool small_exact = engine == TA3N_GEMM_TF32X3_TCGEN05 && !plan.a_kmaj && !plan.b_kmaj && !precise;
+    std::vector<int> fine_idx;
     for (int i = 0; i < (int)plan.groups.size(); ++i) {
       const Group& g = plan.groups[i];
       const bool tiny = small_exact && (long)g.M * g.N <= 256L * 256L && 2.0 * g.M * g.N * (double)plan.k_total(g) <= 3e8;
-      ((tc_group_ok(plan, g) && !tiny) ? tc_idx : simt_idx).push_back(i);
+      if (!tc_group_ok(plan, g))
+        simt_idx.push_back(i);
+      else
+        (tiny ? fine_idx : tc_idx).push_back(i);
+    }
+    if (!fine_idx.empty()) {
+      GemmPlan fine = sub_plan(plan, fine_idx);
+      fine.label = "wgrad_small_x3";
+      TA3N_TRY(launch_tc(fine, stream, true));
     }
     if (!tc_idx.empty()) {
       GemmPlan tc = sub_plan(plan, tc_idx);
