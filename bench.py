@@ -527,6 +527,12 @@ def run_b200(args):
                 "kernels of this library), D2H of every step's loss (read by the host one step behind)"},
         "gpu_launches": int(launches), "launches_per_step": int(step.launches_per_step),
         "cuda_graph": not args.no_graph, "autograd_api_ms_per_step": autograd_ms, "clocks": clocks,
+        "step_mode": step.mode,
+        "allreduce": None if world == 1 else (
+            {"kind": "library kernel over " + ("NVSwitch multicast (multimem.ld_reduce / multimem.st)" if step.ar["mc"]
+                                               else "NVLink peer memory"),
+             "bytes": int(step.flat_grad.numel() * 4), "where": "inside the step's CUDA graph, before the optimizer"}
+            if step.ar is not None else {"kind": "NCCL all_reduce (AVG) between two graphs", "bytes": int(step.flat_grad.numel() * 4)}),
     }
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, 1000, 2, budget_s=args.cpu_seconds)

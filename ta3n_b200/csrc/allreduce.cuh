@@ -20,8 +20,9 @@
 namespace ta3n {
 
 constexpr int kArMaxWorld = 16;
-constexpr int kArBlocks = 64;
-constexpr int kArThreads = 1024;
+constexpr int kArBlocks = 128;
+constexpr int kArThreads = 512;
+constexpr int kArUnroll = 4;          // independent 16 B reductions a thread keeps in flight (the loop is latency-bound)
 
 struct ArPeers {
   float* buf[kArMaxWorld];          // peer mappings of the bucket ([rank] = local)
@@ -76,31 +77,55 @@ allreduce_mean_kernel(const __grid_constant__ ArPeers P, float* __restrict__ mc,
   const size_t s0 = n4 * (size_t)rank / world, s1 = n4 * (size_t)(rank + 1) / world;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   if (mc != nullptr) {
-    for (size_t i = s0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += stride) {
-      float4 v = multimem_ld_reduce_add(mc + 4 * i);
-      v.x *= scale;
-      v.y *= scale;
-      v.z *= scale;
-      v.w *= scale;
-      multimem_st(mc + 4 * i, v);
+    for (size_t i0 = s0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < s1; i0 += stride * kArUnroll) {
+      float4 v[kArUnroll];
+#pragma unroll
+      for (int u = 0; u < kArUnroll; ++u) {
+        const size_t i = i0 + (size_t)u * stride;
+        if (i < s1) v[u] = multimem_ld_reduce_add(mc + 4 * i);
+      }
+#pragma unroll
+      for (int u = 0; u < kArUnroll; ++u) {
+        const size_t i = i0 + (size_t)u * stride;
+        if (i < s1) {
+          v[u].x *= scale;
+          v[u].y *= scale;
+          v[u].z *= scale;
+          v[u].w *= scale;
+          multimem_st(mc + 4 * i, v[u]);
+        }
+      }
     }
   } else {
-    for (size_t i = s0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += stride) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i0 = s0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < s1; i0 += stride * 2) {
+      float4 acc[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const size_t i = i0 + (size_t)u * stride;
+        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < s1) {
 #pragma unroll 8
-      for (int p = 0; p < world; ++p) {       // fixed rank order; `world` independent loads in flight
-        const float4 x = __ldcg(reinterpret_cast<const float4*>(P.buf[p]) + i);
-        acc.x += x.x;
-        acc.y += x.y;
-        acc.z += x.z;
-        acc.w += x.w;
+          for (int p = 0; p < world; ++p) {       // fixed rank order; `world` independent loads in flight
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(P.buf[p]) + i);
+            acc[u].x += x.x;
+            acc[u].y += x.y;
+            acc[u].z += x.z;
+            acc[u].w += x.w;
+          }
+        }
       }
-      acc.x *= scale;
-      acc.y *= scale;
-      acc.z *= scale;
-      acc.w *= scale;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const size_t i = i0 + (size_t)u * stride;
+        if (i < s1) {
+          acc[u].x *= scale;
+          acc[u].y *= scale;
+          acc[u].z *= scale;
+          acc[u].w *= scale;
 #pragma unroll 8
-      for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(P.buf[p])[i] = acc;
+          for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(P.buf[p])[i] = acc[u];
+        }
+      }
     }
   }
   ar_barrier(P, rank, world, 1, seq);
