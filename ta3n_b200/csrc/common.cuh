@@ -87,6 +87,11 @@ inline PendingTimer& pending_timer() {
 inline void pre_launch(const char* label, cudaStream_t stream) {
   TimingRegistry& t = timing();
   if (!t.enabled.load(std::memory_order_relaxed)) return;
+  static const bool log_launches = []() {      // TA3N_LAUNCH_LOG=1: call-site label of every launch, in order, on stderr
+    const char* e = getenv("TA3N_LAUNCH_LOG");
+    return e && e[0] == '1';
+  }();
+  if (log_launches) fprintf(stderr, "ta3n-launch %s\n", label);
   TimingRegistry::Rec r;
   r.label = label;
   if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;

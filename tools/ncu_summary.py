@@ -13,6 +13,7 @@ import subprocess
 import sys
 
 WANT = {                                   # exact column names of `--page raw`
+    "l2_rd": "lts__t_bytes_op_read.sum" ,
     "dur": "gpu__time_duration.sum",
     "dram_rd": "dram__bytes_read.sum",
     "dram_wr": "dram__bytes_write.sum",
@@ -63,8 +64,10 @@ def main():
 
         site = sites[k] if k < len(sites) else r[name_i].split("(")[0][-28:]
         rd, wr = val("dram_rd"), val("dram_wr")
-        print(f"{site:16s} grid={r[grid_i]:>12s} block={r[block_i]:>11s} dur={val('dur'):7.2f} us  "
-              f"dram_rd={rd / 1e6:7.2f} MB dram_wr={wr / 1e6:6.2f} MB  tensor_pipe_active={val('tensor_pct'):5.1f}%  "
+        kname = r[name_i].split("(")[0].split("::")[-1][:26]
+        gbs = (rd + wr) / max(val('dur'), 1e-9) / 1e3          # bytes / us = MB/s -> GB/s
+        print(f"{site:18s} {kname:26s} grid={r[grid_i]:>12s} block={r[block_i]:>11s} dur={val('dur'):7.2f} us  "
+              f"dram_rd={rd / 1e6:7.2f} MB dram_wr={wr / 1e6:6.2f} MB ({gbs:6.0f} GB/s)  tensor_pipe_active={val('tensor_pct'):5.1f}%  "
               f"lts_throughput={val('lts_pct'):5.2f}%  regs={int(val('regs')) if val('regs') == val('regs') else -1}")
         traffic[site] = traffic.get(site, 0.0) + rd + wr
         k += 1
