@@ -494,13 +494,14 @@ def run_b200(args):
         ach = tm["sites"][dom] / (per_step_ms * 1e-3) / 1e9
         traffic = None
         try:   # DRAM bytes of this call site from the committed `ncu --set full` capture (profiles/)
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
                 traffic = json.load(f)["dram_bytes_per_step"].get(dom) if (B, T, F, C) == (256, 5, 512, 12) else None
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic,
-                "traffic_source": "profiles/r1_prof_tc_gemm.ncu-rep (dram__bytes_read+write of the launch)",
+                "traffic_source": "profiles/r2_step_full.txt (ncu --set full of one step of this binary, tf32x3 engine: "
+                                  "dram__bytes_read+write of the launch)",
                 "peak_kind": peak_kind,
                 "algorithmic_bytes_per_step": tm["sites"][dom], "kernel_ms_per_step": per_step_ms,
                 "share_of_library_time": ms / total_site_ms, "launches_per_step": cnt / n_prof}

@@ -43,10 +43,13 @@ def main():
     ap.add_argument("--sites", default="", help="comma-separated call-site names of the kept launches, in order")
     ap.add_argument("--json", default="", help="write {dram_bytes_per_step: {site: bytes}} here")
     a = ap.parse_args()
-    raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True)
-    if raw.returncode != 0:
-        sys.exit(raw.stderr[-2000:])
-    rows = list(csv.reader(io.StringIO(raw.stdout)))
+    if a.report.endswith(".csv"):          # an exported `ncu -i rep --page raw --csv` (reports above 64 MiB do not travel)
+        rows = list(csv.reader(open(a.report)))
+    else:
+        raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True)
+        if raw.returncode != 0:
+            sys.exit(raw.stderr[-2000:])
+        rows = list(csv.reader(io.StringIO(raw.stdout)))
     header, units, body = rows[0], rows[1], rows[2:]
     col = {k: find(header, v) for k, v in WANT.items()}
     name_i, grid_i, block_i = header.index("Kernel Name"), header.index("Grid Size"), header.index("Block Size")
