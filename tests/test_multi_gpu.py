@@ -120,3 +120,33 @@ def test_two_gpu_trainstep_matches_global_batch(variant):
     got_delta = got_param.double() - p0.double().cpu()
     err = ((got_delta - want_delta).norm() / want_delta.norm()).item()
     assert err < 1e-3, err
+
+
+def test_nn_dataparallel_replicas_match_single_gpu():
+    """The reference's own multi-GPU mode (main.py:79: nn.DataParallel, one host thread per replica): forward outputs and
+    the gradients reduced onto GPU 0 equal the single-GPU ones.  Exercises the per-device kernel configuration and the
+    per-thread tensor-map caches of the library with two devices driven from one process."""
+    import ta3n_b200
+    from ta3n_b200.loss import ta3n_loss
+    ta3n_b200.set_gemm_engine("tf32x3")
+    cfg = _cfg()
+    xs, xt, labels = orc.synthetic_batch(2 * B_LOCAL, cfg)
+    dev0 = torch.device("cuda", 0)
+
+    def run(parallel):
+        model = _build(dev0)
+        net = torch.nn.DataParallel(model, [0, 1]) if parallel else model
+        outs = net(xs.to(dev0), xt.to(dev0), [0.75, 0.75, 0.5], 0, is_train=True, reverse=False)
+        loss = ta3n_loss(outs, labels.to(dev0), 0.003)
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss.detach().cpu(), outs[1].detach().cpu(), {k: p.grad.detach().cpu() for k, p in model.named_parameters()
+                                                             if p.grad is not None}
+
+    l1, o1, g1 = run(False)
+    l2, o2, g2 = run(True)
+    assert abs(l1.item() - l2.item()) <= 1e-5 * abs(l1.item())
+    assert ((o1 - o2).norm() / o1.norm()).item() < 1e-4
+    for k in g1:
+        err = ((g1[k].double() - g2[k].double()).norm() / g1[k].double().norm().clamp_min(1e-30)).item()
+        assert err < 2e-3 or (g1[k] - g2[k]).abs().max().item() < 1e-7, (k, err)
