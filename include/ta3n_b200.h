@@ -334,6 +334,13 @@ int ta3n_sgd_nesterov_step(float* params, const float* grads, float* momentum_bu
                            const float* lr_dev, float momentum, float weight_decay, float max_norm,
                            void* workspace, size_t workspace_bytes, float* stats,
                            ta3n_stream_t stream);
+/* The same with an optional per-element mask (n floats, device; 0 = leave parameter and momentum untouched): parameters
+ * the configured losses give no gradient -- torch.optim.SGD skips parameters whose .grad is None (main.py:83), it does
+ * not weight-decay them.  The mask must be constant over each aligned group of four elements.                         */
+int ta3n_sgd_nesterov_step_masked(float* params, const float* grads, float* momentum_buf, long long n,
+                                  const float* lr_dev, float momentum, float weight_decay, float max_norm,
+                                  void* workspace, size_t workspace_bytes, float* stats, const float* active,
+                                  ta3n_stream_t stream);
 
 /* ---- self test of the tensor-core GEMM engine (used by tests; device buffers) ------ */
 /* C[M,N] = A[M,K] * B[N,K]^T with the selected engine; A, B, C row-major fp32.           */

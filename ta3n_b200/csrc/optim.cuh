@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kOptThreads) sqnorm_partial_kernel(const float
 __global__ void __launch_bounds__(kOptThreads) sgd_nesterov_kernel(
     float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, long long n,
     const float* __restrict__ lr_dev, float mu, float wd, float max_norm, const float* __restrict__ partial,
-    int n_partial, float* __restrict__ stats) {
+    int n_partial, float* __restrict__ stats, const float* __restrict__ active) {
   pdl_wait();
   __shared__ float red[32];
   __shared__ float coef_s;
@@ -90,7 +90,10 @@ __global__ void __launch_bounds__(kOptThreads) sgd_nesterov_kernel(
     (M) = mm;                               \
     (P) = (P) - lr * fmaf(mu, mm, d);       \
   }
+  // `active` (optional, one float per element, 0 = skip): parameters the configured losses give no gradient --
+  // torch.optim.SGD leaves a parameter whose .grad is None untouched (no weight decay, no momentum), main.py:83
   for (long long i = static_cast<long long>(blockIdx.x) * kOptThreads + threadIdx.x; i < n4; i += stride) {
+    if (active != nullptr && reinterpret_cast<const float4*>(active)[i].x == 0.f) continue;      // slots are 64-float aligned
     float4 pv = p4[i], gv = g4[i], mv = m4[i];
     TA3N_SGD_ELEM(pv.x, gv.x, mv.x)
     TA3N_SGD_ELEM(pv.y, gv.y, mv.y)
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(kOptThreads) sgd_nesterov_kernel(
     p4[i] = pv;
     m4[i] = mv;
   }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3) && (active == nullptr || active[(n4 << 2) + threadIdx.x] != 0.f)) {
     long long i = (n4 << 2) + threadIdx.x;
     float pv = p[i], gv = g[i], mv = m[i];
     TA3N_SGD_ELEM(pv, gv, mv)

@@ -1121,13 +1121,14 @@ int ta3n_allreduce_mean(float* const* peer_bufs_host, float* multicast_buf, uint
 // ---- optimizer step: clip_grad_norm_ + SGD-Nesterov over flat buffers (main.py:83, 578-583) ----
 size_t ta3n_sgd_workspace_bytes(void) { return Arena::round(kSqnormBlocks * sizeof(float)); }
 
-int ta3n_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf, long long n, const float* lr_dev,
-                           float momentum, float weight_decay, float max_norm, void* workspace,
-                           size_t workspace_bytes, float* stats, ta3n_stream_t stream) {
+int ta3n_sgd_nesterov_step_masked(float* params, const float* grads, float* momentum_buf, long long n, const float* lr_dev,
+                                  float momentum, float weight_decay, float max_norm, void* workspace,
+                                  size_t workspace_bytes, float* stats, const float* active, ta3n_stream_t stream) {
   TA3N_REQUIRE(params && grads && momentum_buf && lr_dev && n > 0, "bad arguments");
   TA3N_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
                  reinterpret_cast<uintptr_t>(momentum_buf)) & 15) == 0, "flat buffers must be 16-byte aligned");
   TA3N_REQUIRE(momentum >= 0.f && weight_decay >= 0.f, "negative momentum / weight decay");
+  TA3N_REQUIRE(active == nullptr || (reinterpret_cast<uintptr_t>(active) & 15) == 0, "active mask must be 16-byte aligned");
   float* partial = nullptr;
   if (max_norm > 0.f) {
     TA3N_REQUIRE(workspace != nullptr && workspace_bytes >= ta3n_sgd_workspace_bytes(), "workspace too small");
@@ -1140,8 +1141,15 @@ int ta3n_sgd_nesterov_step(float* params, const float* grads, float* momentum_bu
   int blocks = static_cast<int>(std::min<long long>((n4 + kOptThreads - 1) / kOptThreads, 148 * 8));
   pre_launch("sgd_nesterov", S(stream));
   launch_kernel(sgd_nesterov_kernel, blocks, kOptThreads, 0, S(stream), params, grads, momentum_buf, n, lr_dev,
-                momentum, weight_decay, max_norm, static_cast<const float*>(partial), kSqnormBlocks, stats);
+                momentum, weight_decay, max_norm, static_cast<const float*>(partial), kSqnormBlocks, stats, active);
   return after_launch();
+}
+
+int ta3n_sgd_nesterov_step(float* params, const float* grads, float* momentum_buf, long long n, const float* lr_dev,
+                           float momentum, float weight_decay, float max_norm, void* workspace,
+                           size_t workspace_bytes, float* stats, ta3n_stream_t stream) {
+  return ta3n_sgd_nesterov_step_masked(params, grads, momentum_buf, n, lr_dev, momentum, weight_decay, max_norm, workspace,
+                                       workspace_bytes, stats, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

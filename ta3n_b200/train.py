@@ -197,6 +197,21 @@ class TrainStep:
             self.grad_stats = torch.zeros(2, device=dev, dtype=torch.float32)     # [total_norm, clip_coef]
             self.opt_ws = torch.zeros(max(1, _lib.load().ta3n_sgd_workspace_bytes() // 4), device=dev,
                                       dtype=torch.float32)
+            # parameters the configured losses never reach keep grad = None in the reference, and torch.optim.SGD then
+            # leaves them alone (no weight decay, no momentum; main.py:83): mask their slots out of the fused update
+            R = self.R
+            idle = []
+            if not (self.flags & 4) and model.use_attn_frame == "none":
+                idle += [2, 3, 4, 5]                                  # frame discriminator
+            if not (self.flags & 1) and model.use_attn == "none":
+                idle += list(range(6 + 2 * R, 6 + 6 * R))             # relation discriminators
+            if not (self.flags & 2) and not (self.flags & 8):
+                idle += list(range(len(self.params) - 4, len(self.params)))     # video discriminator
+            self.active_mask = None
+            if idle:
+                self.active_mask = torch.ones_like(self.flat_grad)
+                for idx in idle:
+                    self.active_mask[offs[idx]:offs[idx] + -(-self.params[idx].numel() // _ALIGN) * _ALIGN] = 0.0
 
         f32 = dict(device=dev, dtype=torch.float32)
         # input slots: one, or two for prefetching the next mini-batch while this one computes
@@ -421,10 +436,10 @@ class TrainStep:
         """clip_grad_norm_ + SGD-Nesterov over the flat buffers (main.py:578-583): two launches."""
         o = self.opt
         clip = float(o.clip_gradient) if o.clip_gradient is not None else 0.0
-        check(_lib.load().ta3n_sgd_nesterov_step(
+        check(_lib.load().ta3n_sgd_nesterov_step_masked(
             _P(self.flat_param), _P(self.flat_grad), _P(self.momentum_buf), self.flat_grad.numel(),
             _P(self.lr_dev), float(o.momentum), float(o.weight_decay), clip, _P(self.opt_ws),
-            self.opt_ws.numel() * 4, _P(self.grad_stats), TF._stream()))
+            self.opt_ws.numel() * 4, _P(self.grad_stats), _P(self.active_mask), TF._stream()))
 
     def set_lr(self, lr: float):
         """Per-step learning-rate schedules (main.py:800-802): one 4-byte async copy, no re-capture."""

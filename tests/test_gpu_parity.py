@@ -574,6 +574,29 @@ def test_fused_step_stream_options_do_not_change_results():
         assert view.data_ptr() % 256 == 0 and prm.data_ptr() % 256 == 0    # vector stores / TMA operands
 
 
+def test_optimizer_leaves_parameters_without_gradient_alone():
+    """torch.optim.SGD skips parameters whose .grad is None (main.py:83): with the frame-level adversarial loss off
+    (place_adv[2] = 'N', main.py:513-538) the frame discriminator gets no gradient in the reference and must not be
+    weight-decayed by the fused update either; the other parameters move."""
+    from ta3n_b200.train import SGDNesterov, TrainStep
+    cfg = orc.PathConfig(num_class=12, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0)
+    params = orc.init_params(cfg, seed=3)
+    xs, xt, labels = orc.synthetic_batch(16, cfg)
+    model = build_model(cfg, params, train=True)
+    step = TrainStep(model, 16, 16, (0.75, 0.75, 0.5), gamma=0.003, use_graph=True, place_adv=("Y", "Y", "N"),
+                     optimizer=SGDNesterov(lr=0.1, weight_decay=0.1, clip_gradient=None))
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    for _ in range(3):
+        step(xs, xt, labels)
+    torch.cuda.synchronize()
+    after = dict(model.named_parameters())
+    for name in ("fc_feature_domain.weight", "fc_feature_domain.bias", "fc_classifier_domain.weight",
+                 "fc_classifier_domain.bias"):
+        assert torch.equal(after[name].detach(), before[name]), name
+    assert not torch.equal(after["fc_feature_shared_source.weight"].detach(), before["fc_feature_shared_source.weight"])
+    assert not torch.equal(after["fc_feature_domain_video.weight"].detach(), before["fc_feature_domain_video.weight"])
+
+
 @pytest.mark.parametrize("n,max_norm", [(1000003, 0.5), (4096, 0.0), (7, 1e9)])
 def test_sgd_nesterov_kernel_matches_torch_optim(n, max_norm):
     """ta3n_sgd_nesterov_step vs torch.optim.SGD(nesterov) + clip_grad_norm_ (main.py:83, 578-583) run in fp64 on
