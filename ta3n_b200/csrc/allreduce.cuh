@@ -51,19 +51,28 @@ __device__ __forceinline__ void multimem_st(float* mc, const float4 v) {
                : "memory");
 }
 
-// all blocks `b` of all ranks meet: slot = (phase, b); one flag per source rank
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// all blocks `b` of all ranks meet: slot = (phase, b); one flag per source rank.
+// Only the `world` signalling threads of a block fence (a system-scope fence by each of the 65 k threads of the grid
+// cost ~15 us per barrier: measured, tools/allreduce_probe.py), cumulatively for the block through the CTA barrier;
+// polls are relaxed loads (an acquire load is a load + L1 invalidate on this part) with one fence after the wait.
 __device__ __forceinline__ void ar_barrier(const ArPeers& P, int rank, int world, int phase, unsigned seq) {
-  __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < world) {
     const int p = threadIdx.x;
     const size_t slot = ((size_t)phase * kArBlocks + blockIdx.x) * world;
+    __threadfence_system();                       // this block's writes, then the flag
     st_release_sys(P.flags[p] + slot + rank, seq);
     unsigned spins = 0;
-    while ((int)(ld_acquire_sys(P.flags[rank] + slot + p) - seq) < 0) {
-      __nanosleep(32);
-      if (++spins > (1u << 25)) __trap();     // a missing peer becomes an error, not a hung GPU
+    while ((int)(ld_relaxed_sys(P.flags[rank] + slot + p) - seq) < 0) {
+      if (++spins > (1u << 26)) __trap();         // a missing peer becomes an error, not a hung GPU
     }
+    __threadfence_system();                       // acquire side
   }
   __syncthreads();
 }
