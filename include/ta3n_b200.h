@@ -85,6 +85,11 @@ void ta3n_reset_launch_count(void);
 /* select the GEMM engine used by subsequent calls (process-wide). */
 int ta3n_set_gemm_engine(int engine);
 int ta3n_get_gemm_engine(void);
+/* Optional device scratch (caller-owned, 256-byte aligned; NULL / 0 removes it) for the calling THREAD's forward
+ * launches under the tf32x3 engine: with it the precise kernel balances its one-CTA-per-SM grid by splitting K
+ * (deterministic partials + fixed-order reduce).  The forward entry points take no workspace argument, hence this
+ * registration; the launches that use it are stream-ordered, so one buffer serves them all.  48 MB cover cfg5.      */
+int ta3n_set_forward_scratch(void* scratch, size_t bytes);
 /* Per-call-site device timing (CUDA events on the launching stream, eager mode only; not for use
  * under graph capture).  ta3n_timing_report synchronises the recorded events, writes lines
  * "label count total_ms\n" to buf, clears the registry and returns the bytes needed.           */

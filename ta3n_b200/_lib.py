@@ -63,6 +63,7 @@ SIGNATURES = {
     "ta3n_reset_launch_count": (None, []),
     "ta3n_set_gemm_engine": (_I, [_I]),
     "ta3n_get_gemm_engine": (_I, []),
+    "ta3n_set_forward_scratch": (_I, [_VP, _SZ]),
     "ta3n_timing_enable": (None, [_I]),
     "ta3n_timing_report": (_SZ, [C.c_char_p, _SZ]),
     "ta3n_shared_fc_fwd": (_I, [_VP, _I, _VP, _I, _I, _VP, _VP, _I, _DRP, _VP, _VP]),

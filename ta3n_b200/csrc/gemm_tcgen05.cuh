@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cmath>
 #include <functional>
 #include <map>
 #include <tuple>
@@ -1218,6 +1219,73 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool precise 
   return TA3N_OK;
 }
 
+// ---- balanced split-K for the precise forward launches ------------------------------------------------------
+// The precise kernel holds one CTA per SM and is bound by shared-memory bandwidth (~0.9 us per K slab), so a launch
+// costs what its longest CTA queue costs: the shared layer has 80 tiles of 64 slabs for 148 SMs, the forward batch 80
+// tiles of 16 slabs next to tiles of up to 80.  Split factors per group are chosen by simulating the greedy (LPT)
+// assignment of the resulting tasks to the SMs for a few target task lengths; partials go to the caller's scratch
+// (ta3n_set_forward_scratch) and a fixed-order reduce pass applies the epilogue.  Deterministic.
+struct ForwardScratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+inline ForwardScratch& forward_scratch() {
+  static thread_local ForwardScratch s;
+  return s;
+}
+inline int x3_plan_slabs(const GemmPlan& plan, const Group& g) {
+  int n = 0;
+  for (int k = 0; k < g.seg_count; ++k) n += (plan.segs[g.seg_begin + k].len + TC_BK - 1) / TC_BK;
+  return n;
+}
+inline double x3_makespan(const GemmPlan& plan, const std::vector<int>& ks, int sms) {
+  std::vector<double> tasks;
+  for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
+    const Group& g = plan.groups[gi];
+    const int tiles = ((g.M + TC_BM - 1) / TC_BM) * ((g.N + TC_BN - 1) / TC_BN);
+    const double len = (double)x3_plan_slabs(plan, g) / ks[gi] + 4.0;      // + prologue / epilogue, in slab units
+    for (int t = 0; t < tiles * ks[gi]; ++t) tasks.push_back(len);
+  }
+  std::sort(tasks.begin(), tasks.end(), std::greater<double>());
+  std::vector<double> load(sms, 0.0);
+  for (double t : tasks) *std::min_element(load.begin(), load.end()) += t;
+  return *std::max_element(load.begin(), load.end());
+}
+inline void plan_splitk_balanced(GemmPlan& plan, Arena* arena, int sms) {
+  if (!arena) return;
+  double total = 0;
+  for (const Group& g : plan.groups)
+    total += (double)x3_plan_slabs(plan, g) * ((g.M + TC_BM - 1) / TC_BM) * ((g.N + TC_BN - 1) / TC_BN);
+  std::vector<int> best(plan.groups.size(), 1);
+  double best_cost = x3_makespan(plan, best, sms);
+  for (double c : {1.1, 1.25, 1.5, 2.0}) {
+    const double target = std::max(8.0, total / sms * c);
+    std::vector<int> ks(plan.groups.size(), 1);
+    for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
+      const int slabs = x3_plan_slabs(plan, plan.groups[gi]);
+      int k = (int)std::ceil(slabs / target);
+      k = std::max(1, std::min(k, 8));
+      while (k > 1 && slabs / k < 8) --k;
+      ks[gi] = k;
+    }
+    bool any = false;
+    for (int k : ks) any |= k > 1;
+    const double cost = x3_makespan(plan, ks, sms) + (any ? 8.0 : 0.0);      // the reduce pass
+    if (cost < best_cost * 0.92) {
+      best_cost = cost;
+      best = ks;
+    }
+  }
+  for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
+    Group& g = plan.groups[gi];
+    if (best[gi] < 2) continue;
+    float* p = arena->floats((size_t)best[gi] * g.M * g.N);
+    if (!p) continue;                      // scratch too small: stay unsplit (still correct)
+    g.ksplit = best[gi];
+    g.partial = p;
+  }
+}
+
 // TA3N_X3_DGRAD=1: the data-gradient GEMMs of the x3 engine at fp32 grade as well.  Measured at cfg2 (profiles/
 // r2_x3_ab.txt): +36 us per step (340 -> 376) for TRN bias gradients at 2e-6 instead of 2.4e-4 and no change of the
 // worst tensors (shared-layer gradients 1.24e-3 vs 1.29e-3 unpinned: those are set by ReLU-pattern differences and by
@@ -1264,7 +1332,12 @@ inline int run_gemm(GemmPlan& plan, cudaStream_t stream, Arena* splitk_arena = n
     }
     if (!tc_idx.empty()) {
       GemmPlan tc = sub_plan(plan, tc_idx);
-      plan_splitk(tc, splitk_arena, TC_BM, TC_BN, TC_BK, 4);
+      if (precise && splitk_arena == nullptr && forward_scratch().ptr != nullptr) {
+        Arena scratch(forward_scratch().ptr, forward_scratch().bytes);
+        plan_splitk_balanced(tc, &scratch, device_sm_count());
+      } else {
+        plan_splitk(tc, splitk_arena, TC_BM, TC_BN, TC_BK, 4);
+      }
       TA3N_TRY(launch_tc(tc, stream, precise));
     }
     if (!simt_idx.empty()) {

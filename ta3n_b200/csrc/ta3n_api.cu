@@ -226,6 +226,13 @@ int ta3n_set_gemm_engine(int engine) {
 }
 int ta3n_get_gemm_engine(void) { return gemm_engine().load(); }
 
+int ta3n_set_forward_scratch(void* scratch, size_t bytes) {
+  TA3N_REQUIRE(scratch == nullptr || (reinterpret_cast<uintptr_t>(scratch) & 255u) == 0, "scratch must be 256-byte aligned");
+  forward_scratch().ptr = bytes > 0 ? scratch : nullptr;
+  forward_scratch().bytes = scratch ? bytes : 0;
+  return TA3N_OK;
+}
+
 void ta3n_timing_enable(int on) { timing().enabled.store(on != 0); }
 
 // Synchronises the recorded events, aggregates device time per call-site label and writes lines

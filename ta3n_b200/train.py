@@ -456,6 +456,16 @@ class TrainStep:
         all-reduce instead)."""
         lib = _lib.load()
         st = TF._stream()
+        # scratch for the balanced split-K of the precise forward launches (tf32x3 engine); registered only while this
+        # step is being enqueued (the captured kernels keep the address, the buffer lives as long as the TrainStep)
+        scratch = self.bufs.workspace("forward_scratch", 48 << 20)
+        check(lib.ta3n_set_forward_scratch(_P(scratch), scratch.numel()))
+        try:
+            self._enqueue_body(lib, st, at_split, optimizer)
+        finally:
+            check(lib.ta3n_set_forward_scratch(None, 0))
+
+    def _enqueue_body(self, lib, st, at_split, optimizer):
         if self.mode != "legacy":
             if self.mode == "fused":
                 check(lib.ta3n_step_run(self.step_handles[self.active], st))
