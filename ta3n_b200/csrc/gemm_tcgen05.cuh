@@ -1209,9 +1209,30 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool precise 
       else
         TA3N_TRY((tc_launch_one<false, true>(tab, maps, sm, stream, plan.label)));
       if (any_split) {
-        dim3 grid(splitk_reduce_blocks(tab), ng);
-        pre_launch("splitk_reduce", stream);
-        launch_kernel(splitk_reduce_kernel, grid, 256, 0, stream, tab);
+        // vectorised reduce when every split group allows it (the forward layers), blocks for split groups only
+        SplitGroups sgs;
+        sgs.n = 0;
+        bool vec = true;
+        size_t mx4 = 0;
+        for (int i = 0; i < ng; ++i) {
+          const Group& g = tab.g[i];
+          if (g.ksplit <= 1) continue;
+          sgs.idx[sgs.n++] = (unsigned char)i;
+          const bool ok = g.N % 4 == 0 && g.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15u) == 0 &&
+                          (reinterpret_cast<uintptr_t>(g.partial) & 15u) == 0 &&
+                          (g.flags & ~(EPI_BIAS | EPI_RELU | EPI_DROP_RNG)) == 0 && g.ksplit <= 8;
+          vec = vec && ok;
+          mx4 = std::max(mx4, (size_t)g.M * g.N / 4);
+        }
+        if (vec && sgs.n > 0) {
+          dim3 grid((unsigned)std::min<size_t>((mx4 + 255) / 256, 1024), sgs.n);
+          pre_launch("splitk_reduce", stream);
+          launch_kernel(splitk_reduce_v4_kernel, grid, 256, 0, stream, tab, sgs);
+        } else {
+          dim3 grid(splitk_reduce_blocks(tab), ng);
+          pre_launch("splitk_reduce", stream);
+          launch_kernel(splitk_reduce_kernel, grid, 256, 0, stream, tab);
+        }
         TA3N_TRY(after_launch());
       }
     }
@@ -1258,12 +1279,12 @@ inline void plan_splitk_balanced(GemmPlan& plan, Arena* arena, int sms) {
     total += (double)x3_plan_slabs(plan, g) * ((g.M + TC_BM - 1) / TC_BM) * ((g.N + TC_BN - 1) / TC_BN);
   std::vector<int> best(plan.groups.size(), 1);
   double best_cost = x3_makespan(plan, best, sms);
-  for (double c : {1.1, 1.25, 1.5, 2.0}) {
+  for (double c : {1.1, 1.25, 1.5, 2.0, -2.0, -3.0, -4.0}) {      // negative: the same factor for every group
     const double target = std::max(8.0, total / sms * c);
     std::vector<int> ks(plan.groups.size(), 1);
     for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
       const int slabs = x3_plan_slabs(plan, plan.groups[gi]);
-      int k = (int)std::ceil(slabs / target);
+      int k = c > 0 ? (int)std::ceil(slabs / target) : (int)(-c);
       k = std::max(1, std::min(k, 8));
       while (k > 1 && slabs / k < 8) --k;
       ks[gi] = k;

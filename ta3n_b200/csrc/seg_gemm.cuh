@@ -603,6 +603,53 @@ inline unsigned splitk_reduce_blocks(const GemmTable& tab) {
   return (unsigned)(b ? b : 1);
 }
 
+// The same reduction, four consecutive columns per thread (N % 4 == 0, aligned C / partial / bias: the forward layers):
+// 16 B loads of every partial in flight together, one pass of the epilogue per quad, blocks only for split groups
+// (blockIdx.y indexes `split_groups`).
+struct SplitGroups {
+  int n;
+  unsigned char idx[kMaxGroups];
+};
+__global__ void __launch_bounds__(256) splitk_reduce_v4_kernel(const __grid_constant__ GemmTable tab,
+                                                               const __grid_constant__ SplitGroups sg) {
+  pdl_wait();
+  __shared__ Group g;
+  {
+    const int* src = reinterpret_cast<const int*>(&tab.g[sg.idx[blockIdx.y]]);
+    int* dst = reinterpret_cast<int*>(&g);
+    for (int i = threadIdx.x; i < (int)(sizeof(Group) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+  const size_t total4 = (size_t)g.M * g.N / 4;
+  const int N4 = g.N / 4;
+  const Group gr = g;
+  const float4* part = reinterpret_cast<const float4*>(gr.partial);
+  TA3N_EPI_DISPATCH(gr.flags, {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += (size_t)gridDim.x * blockDim.x) {
+      float4 p[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < gr.ksplit) p[k] = __ldcg(part + (size_t)k * total4 + e);
+      float4 s = p[0];
+#pragma unroll
+      for (int k = 1; k < 8; ++k)
+        if (k < gr.ksplit) {
+          s.x += p[k].x;
+          s.y += p[k].y;
+          s.z += p[k].z;
+          s.w += p[k].w;
+        }
+      const int m = (int)(e / N4), n = (int)(e % N4) * 4;
+      float4 o;
+      o.x = epilogue_t<EPI_F>(gr, m, n, s.x);
+      o.y = epilogue_t<EPI_F>(gr, m, n + 1, s.y);
+      o.z = epilogue_t<EPI_F>(gr, m, n + 2, s.z);
+      o.w = epilogue_t<EPI_F>(gr, m, n + 3, s.w);
+      *reinterpret_cast<float4*>(gr.C + (size_t)m * gr.ldc + n) = o;
+    }
+  })
+}
+
 // =============================================================================================
 // host side: table builder + launcher
 // =============================================================================================
