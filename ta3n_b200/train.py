@@ -100,7 +100,7 @@ class TrainStep:
     def __init__(self, model, batch_source: int, batch_target: int, beta: Sequence[float], gamma: float = 0.003,
                  place_adv: Sequence[str] = ("Y", "Y", "Y"), add_loss_DA: str = "attentive_entropy",
                  use_graph: bool = True, process_group=None, seed: int = 0x5EED, double_buffer: bool = False,
-                 overlap_wgrad: bool = False, parallel_branches: bool = False,
+                 overlap_wgrad: Optional[bool] = None, parallel_branches: bool = False,
                  overlap_allreduce: Optional[bool] = None, graph_collectives: Optional[bool] = None,
                  optimizer: Optional[SGDNesterov] = None, mode: Optional[str] = None,
                  class_weight: Optional[torch.Tensor] = None, domain_weight: Sequence[float] = (1.0, 1.0),
@@ -151,6 +151,11 @@ class TrainStep:
             raise ValueError(f"unknown TrainStep mode {mode!r}")
         if mode != "legacy" and model.use_attn_frame != "none":
             raise NotImplementedError("the fused step does not cover use_attn_frame; use mode='legacy'")
+        if overlap_wgrad is None:
+            # measured at cfg2 (tools/legacy_options.py): the weight-gradient launches on a forked stream of the graph
+            # gain 12 us per step under the tf32x3 engine (its small precise launch overlaps the data-gradient chain)
+            # and lose 16 us under plain tf32
+            overlap_wgrad = mode == "legacy" and _lib.get_gemm_engine() == "tf32x3" and not overlap_allreduce
         if mode != "legacy" and (overlap_wgrad or parallel_branches or overlap_allreduce or graph_collectives):
             raise ValueError("overlap_wgrad / parallel_branches / overlap_allreduce / graph_collectives are options "
                              "of mode='legacy' (the fused step is a single kernel)")
