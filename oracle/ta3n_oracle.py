@@ -56,6 +56,7 @@ class PathConfig:
     dropout_v: float = 0.5
     use_attn: str = "TransAttn"    # or 'none'
     use_attn_frame: str = "none"   # or 'TransAttn'
+    ens_DA: str = "none"           # or 'MCD': a second video-level classifier (models.py:276-279, 716-720)
 
     @property
     def shared_dim(self) -> int:   # models.py:129
@@ -136,6 +137,8 @@ def init_params(cfg: PathConfig, seed: Optional[int] = None) -> "OrderedDict[str
     put("fc_feature_video_source_2", _std_linear(H, H))         # unused
     put("fc_feature_domain_video", _std_linear(H, H))
     put("fc_classifier_video_source", _std_linear(H, C))
+    if cfg.ens_DA == "MCD":                                     # models.py:276-279
+        put("fc_classifier_video_source_2", _std_linear(H, C))
     put("fc_classifier_domain_video", _std_linear(H, 2))
     for i in range(T - 1):
         put(f"relation_domain_classifier_all.{i}.0", _default_linear(H, H))
@@ -145,7 +148,7 @@ def init_params(cfg: PathConfig, seed: Optional[int] = None) -> "OrderedDict[str
 
 USED_PARAM_PREFIXES = (
     "fc_feature_shared_source", "fc_feature_domain.", "fc_classifier_domain.",
-    "TRN.", "fc_feature_domain_video", "fc_classifier_video_source",
+    "TRN.", "fc_feature_domain_video", "fc_classifier_video_source",      # (also ..._source_2 under MCD)
     "fc_classifier_domain_video", "relation_domain_classifier_all",
 )
 
@@ -340,7 +343,10 @@ def _forward_domain(p: Dict[str, torch.Tensor], x: torch.Tensor, beta: Sequence[
 
     pred_domain = [pred_rel, pred_dom_video, pred_frame.view(batch, T, 2)]            # reversed list, :722
     feats = [pred_video, feat_video, feat_frames]                                      # reversed list, :722
-    return attn, pred_video, pred_video, pred_domain, feats                            # :713 out_2 = out
+    pred_video_2 = pred_video                                                          # :713 out_2 = out
+    if cfg.ens_DA == "MCD":                                                            # :716-720 (share_params == 'Y')
+        pred_video_2 = F.linear(vid, p["fc_classifier_video_source_2.weight"], p["fc_classifier_video_source_2.bias"])
+    return attn, pred_video, pred_video_2, pred_domain, feats
 
 
 def split_gates(gates: Optional[Dict[str, torch.Tensor]], bs: int, T: int):
@@ -387,6 +393,11 @@ def attentive_entropy(pred: torch.Tensor, pred_domain: torch.Tensor) -> torch.Te
     q = F.softmax(pred, dim=1)
     lq = F.log_softmax(pred, dim=1)
     return torch.mean(weights * torch.sum(-q * lq, 1))
+
+
+def dis_MCD(out1: torch.Tensor, out2: torch.Tensor) -> torch.Tensor:
+    """loss.py:29-30: the classifier discrepancy of MCD (main.py:548-556)."""
+    return torch.mean(torch.abs(F.softmax(out1, dim=1) - F.softmax(out2, dim=1)))
 
 
 def compose_loss(outputs, label_source: torch.Tensor, gamma: float = 0.003,

@@ -287,7 +287,7 @@ def path_forward(spec: PathSpec, xs, xt, params, bufs: Buffers, batch_gemms: boo
     saved = dict(feat=feat, hid_f=hid_f, pred_frame=pred_frame, feat_in=feat_in, act=act, feat_rel=feat_rel,
                  hid_r=hid_r, pred_rel=pred_rel, attn=attn, dropped=dropped, hid_v=hid_v)
     outputs = (feat.view(M, T, F), pred_frame.view(M, T, 2), attn, pred_rel, feat_video, pred_video,
-               pred_dom_video)
+               pred_dom_video, dropped)
     return saved, outputs, (Bs, Bt, D, T, F, H, Cn)
 
 
@@ -339,12 +339,16 @@ def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: 
         frame_done = torch.cuda.Event()
         frame_done.record(side_stream)
 
-    # 6'. video discriminator: d_dropped = -beta1 * dgrad
+    # 6'. video discriminator: d_dropped = -beta1 * dgrad  (+ what other consumers of `dropped` sent back: the second
+    #     classifier of MCD, models.py:716-720 -- it sits behind GRL_mu like the first one, so its gradient joins here)
     d_dropped = new("d_dropped", M, H)
+    g_dropped = g("dropped")
+    if g_dropped is not None:
+        d_dropped.copy_(g_dropped.reshape(M, H))
     ws = wsp("disc_v", lib.ta3n_disc_bwd_workspace_bytes(M, H, H))
     check(lib.ta3n_disc_bwd(_p(dropped), M, H, H, _p(w1v), _p(w2v), _p(hid_v), _p(g("pred_dom_video")),
-                            float(spec.beta[1]), _p(d_dropped), 0, _p(dw1v), _p(db1v), _p(dw2v), _p(db2v),
-                            _p(ws), ws.numel(), st))
+                            float(spec.beta[1]), _p(d_dropped), 1 if g_dropped is not None else 0, _p(dw1v), _p(db1v),
+                            _p(dw2v), _p(db2v), _p(ws), ws.numel(), st))
     # 5'. classifier + dropout_v (+ optional GRL_mu around both heads, models.py:682-684)
     G = new("G", M, H)
     ws = wsp("vhead", lib.ta3n_video_head_bwd_workspace_bytes(M, H, Cn))
@@ -393,7 +397,7 @@ def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: 
     stage_done("shared")
 
 
-_OUT_NAMES = ("feat", "pred_frame", "attn", "pred_rel", "feat_video", "pred_video", "pred_dom_video")
+_OUT_NAMES = ("feat", "pred_frame", "attn", "pred_rel", "feat_video", "pred_video", "pred_dom_video", "dropped")
 
 
 class _VideoPathFunction(torch.autograd.Function):
@@ -401,7 +405,7 @@ class _VideoPathFunction(torch.autograd.Function):
 
     Outputs (all for M = Bs + Bt rows, source rows first):
       feat_fc (M,T,F) | pred_frame (M,T,2) | attn (M,R) | pred_rel (M,R,2) | feat_video (M,H) |
-      pred_video (M,C) | pred_dom_video (M,2)
+      pred_video (M,C) | pred_dom_video (M,2) | dropped (M,H): the video feature after dropout_v, for further heads
     """
 
     @staticmethod
@@ -434,3 +438,39 @@ class _VideoPathFunction(torch.autograd.Function):
 
 def video_path(spec: PathSpec, xs: torch.Tensor, xt: torch.Tensor, params: Sequence[torch.Tensor]):
     return _VideoPathFunction.apply(spec, xs, xt, *params)
+
+
+class _VideoHead2Function(torch.autograd.Function):
+    """A further classifier on the dropped video feature: ``fc_classifier_video_source_2`` of the MCD variant
+    (models.py:276-279, 716-720).  Forward and backward are the library's video-head operators without dropout
+    (ta3n_video_head_fwd / _bwd with drop = NULL): logits, weight / bias gradient, data gradient."""
+
+    @staticmethod
+    def forward(ctx, dropped, weight, bias):
+        dropped, weight, bias = _chk(dropped, "dropped"), _chk(weight, "weight"), _chk(bias, "bias")
+        lib = _lib.load()
+        M, H = dropped.shape
+        Cn = weight.shape[0]
+        pred = torch.empty(M, Cn, device=dropped.device, dtype=torch.float32)
+        same = torch.empty_like(dropped)            # the operator also returns its (here: identical) dropped input
+        check(lib.ta3n_video_head_fwd(_p(dropped), M, H, Cn, _p(weight), _p(bias), None, _p(same), _p(pred), _stream()))
+        ctx.save_for_backward(dropped, weight)
+        return pred
+
+    @staticmethod
+    def backward(ctx, g_pred):
+        dropped, weight = ctx.saved_tensors
+        lib = _lib.load()
+        M, H = dropped.shape
+        Cn = weight.shape[0]
+        g_pred = _chk(g_pred, "grad")
+        d_in = torch.empty_like(dropped)
+        dw, db = torch.empty_like(weight), torch.empty(Cn, device=weight.device, dtype=torch.float32)
+        ws = _ws(lib.ta3n_video_head_bwd_workspace_bytes(M, H, Cn), dropped)
+        check(lib.ta3n_video_head_bwd(_p(dropped), M, H, Cn, _p(weight), None, _p(g_pred), None, None, 1.0, _p(d_in),
+                                      _p(dw), _p(db), _p(ws), ws.numel(), _stream()))
+        return d_in, dw, db
+
+
+def video_head2(dropped: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor):
+    return _VideoHead2Function.apply(dropped, weight, bias)

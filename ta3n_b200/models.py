@@ -59,8 +59,8 @@ class VideoModel(nn.Module):
             _unsupported('add_fc', add_fc, [1])
         if use_bn != 'none':
             _unsupported('use_bn', use_bn, ['none'])
-        if ens_DA != 'none':
-            _unsupported('ens_DA', ens_DA, ['none'])
+        if ens_DA not in ('none', 'MCD'):
+            _unsupported('ens_DA', ens_DA, ['none', 'MCD'])
         if share_params != 'Y':
             _unsupported('share_params', share_params, ['Y'])
         if use_attn not in ('TransAttn', 'none'):
@@ -140,6 +140,8 @@ class VideoModel(nn.Module):
         self.fc_feature_video_source_2 = std_linear(feat_video_dim, feat_video_dim)     # :262 (unused)
         self.fc_feature_domain_video = std_linear(feat_aggregated_dim, feat_video_dim)  # :267
         self.fc_classifier_video_source = std_linear(feat_video_dim, num_class)         # :272
+        if self.ens_DA == 'MCD':                                                        # :276-279 second classifier
+            self.fc_classifier_video_source_2 = std_linear(feat_video_dim, num_class)
         self.fc_classifier_domain_video = std_linear(feat_video_dim, 2)                 # :281
 
         self.relation_domain_classifier_all = nn.ModuleList(                             # :286-294
@@ -213,16 +215,23 @@ class VideoModel(nn.Module):
         spec = TF.PathSpec(num_segments=num_segments, beta=(float(beta[0]), float(beta[1]), float(beta[2])),
                            mu=float(mu), reverse=bool(reverse), use_attn=self.use_attn != 'none',
                            use_attn_frame=self.use_attn_frame != 'none', drop_i=drop_i, drop_v=drop_v)
-        feat_fc, pred_frame, attn, pred_rel, feat_video, pred_video, pred_dom_video = TF.video_path(
+        feat_fc, pred_frame, attn, pred_rel, feat_video, pred_video, pred_dom_video, dropped = TF.video_path(
             spec, xs, xt, self.path_parameters())
+        pred_video_2 = pred_video                                                     # :713-714 out_2 = out
+        if self.ens_DA == 'MCD':                                                      # :716-720 (share_params == 'Y')
+            # the second classifier reads the same dropped (and, under `reverse`, gradient-reversed) feature as the
+            # first: its data gradient re-enters the path node through the `dropped` output, in front of GRL_mu
+            pred_video_2 = TF.video_head2(dropped, self.fc_classifier_video_source_2.weight,
+                                          self.fc_classifier_video_source_2.bias)
 
         def halves(t):
             return t[:Bs], t[Bs:]
 
         (attn_s, attn_t), (out_s, out_t) = halves(attn), halves(pred_video)
+        out2_s, out2_t = halves(pred_video_2)
         (ff_s, ff_t), (fv_s, fv_t) = halves(feat_fc), halves(feat_video)
         (pf_s, pf_t), (pv_s, pv_t), (pr_s, pr_t) = halves(pred_frame), halves(pred_dom_video), halves(pred_rel)
         # lists are returned reversed, as the reference does (models.py:722):
         #   pred_domain = [relation (B,R,2), video (B,2), frame (B,T,2)];  feat = [pred (B,C), video (B,H), fc (B,T,F)]
-        return (attn_s, out_s, out_s, [pr_s, pv_s, pf_s], [out_s, fv_s, ff_s],
-                attn_t, out_t, out_t, [pr_t, pv_t, pf_t], [out_t, fv_t, ff_t])
+        return (attn_s, out_s, out2_s, [pr_s, pv_s, pf_s], [out_s, fv_s, ff_s],
+                attn_t, out_t, out2_t, [pr_t, pv_t, pf_t], [out_t, fv_t, ff_t])

@@ -484,7 +484,7 @@ class TrainStep:
         check(lib.ta3n_counter_inc(_P(self.step_counter), st))          # fresh dropout masks per step
         saved, outputs, dims = TF.path_forward(self.spec, self.xs, self.xt, self.params, self.bufs, batch_gemms=True)
         self.outputs = outputs
-        _, pred_frame, _, pred_rel, _, pred_video, pred_dom = outputs
+        _, pred_frame, _, pred_rel, _, pred_video, pred_dom, _ = outputs
         check(lib.ta3n_loss_fwd_bwd(_P(pred_video), _P(self.labels), _P(pred_rel), _P(pred_dom), _P(pred_frame),
                                     self.Bs, self.Bt, self.T, self.R, self.C, self.gamma, self.flags,
                                     _P(self.valid), _P(self.loss), _P(self.g_video), _P(self.g_rel), _P(self.g_dom),

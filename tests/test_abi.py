@@ -85,7 +85,7 @@ def test_no_cpu_fallback_in_product_package():
 
 def test_unsupported_options_raise():
     from ta3n_b200.models import VideoModel
-    for kw in (dict(frame_aggregation="avgpool"), dict(use_bn="AdaBN"), dict(ens_DA="MCD"),
+    for kw in (dict(frame_aggregation="avgpool"), dict(use_bn="AdaBN"), dict(ens_DA="AutoDIAL"),
                dict(share_params="N"), dict(use_attn="general"), dict(baseline_type="tsn")):
         args = dict(num_class=5, baseline_type="video", frame_aggregation="trn-m", modality="RGB", verbose=False)
         args.update(kw)

@@ -48,7 +48,7 @@ def build_model(cfg: orc.PathConfig, params, train: bool):
     from ta3n_b200.models import VideoModel
     m = VideoModel(cfg.num_class, "video", "trn-m", "RGB", train_segments=cfg.num_segments,
                    val_segments=cfg.num_segments, add_fc=1, fc_dim=cfg.fc_dim, dropout_i=cfg.dropout_i,
-                   dropout_v=cfg.dropout_v, partial_bn=False, use_bn="none", ens_DA="none",
+                   dropout_v=cfg.dropout_v, partial_bn=False, use_bn="none", ens_DA=cfg.ens_DA,
                    use_attn=cfg.use_attn, use_attn_frame=cfg.use_attn_frame, share_params="Y", verbose=False)
     m.load_state_dict(params)
     m = m.to(_dev())
@@ -450,6 +450,58 @@ def test_fused_train_step_matches_oracle(T, attn_frame, bs, bt, C, use_graph, en
         assert_close(named[name].grad, go, GRAD_TOL[engine], f"fused grad {name}",
                      noise=n_grad[name] * NOISE_SCALE[engine])
     assert model.fc_feature_source.weight.grad is None       # off-path parameters stay untouched
+
+
+@pytest.mark.parametrize("reverse,mu", [(False, 0.0), (True, 0.7)])
+def test_mcd_variant_matches_oracle(reverse, mu, engine):
+    """SURVEY 8f n4, ens_DA='MCD' (models.py:276-279, 716-720; main.py:447, 548-556): second video-level classifier on the
+    dropped (and, in the `reverse=True` pass, gradient-reversed) feature.  Outputs and every gradient of
+       CE(out_s) + CE(out_s_2) - dis_MCD(out_t, out_t_2) + the three domain losses     against the fp64 oracle
+    (the oracle's MCD branch is pinned to the live reference in tests/test_oracle_vs_reference.py)."""
+    cfg = orc.PathConfig(num_class=9, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0, ens_DA="MCD")
+    params = orc.init_params(cfg, seed=17)
+    g = torch.Generator().manual_seed(18)
+    for k in params:
+        if params[k].dtype.is_floating_point and "weight" in k and \
+                (k.startswith(orc.USED_PARAM_PREFIXES) or k.startswith("fc_classifier_video_source_2")):
+            params[k] = params[k] + 0.02 * torch.randn(params[k].shape, generator=g)
+    bs, bt = 21, 13
+    xs, xt = torch.randn(bs, 5, orc.FEATURE_DIM, generator=g), torch.randn(bt, 5, orc.FEATURE_DIM, generator=g)
+    labels = torch.randint(0, 9, (bs,), generator=g)
+    beta = [0.75, 0.6, 0.5]
+
+    def mcd_loss(outs, lab, F=torch.nn.functional):
+        dom = 0.0
+        for ps, pt in zip(outs[3], outs[8]):
+            both = torch.cat([ps.reshape(-1, 2), pt.reshape(-1, 2)], 0)
+            tgt = torch.cat([torch.zeros(ps.numel() // 2, dtype=torch.long, device=both.device),
+                             torch.ones(pt.numel() // 2, dtype=torch.long, device=both.device)])
+            dom = dom + F.cross_entropy(both, tgt)
+        return F.cross_entropy(outs[1], lab) + F.cross_entropy(outs[2], lab) - orc.dis_MCD(outs[6], outs[7]) + dom
+
+    def oracle(dtype):
+        p = {k: (v.to(dtype).requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in params.items()}
+        o = orc.forward(p, xs.to(dtype), xt.to(dtype), beta, mu, cfg, train=True, reverse=reverse)
+        loss = mcd_loss(o, labels)
+        loss.backward()
+        return loss.detach(), o, {k: v.grad for k, v in p.items() if v.dtype.is_floating_point and v.grad is not None}
+
+    l64, o64, g64 = oracle(torch.float64)
+    _, _, g32 = oracle(torch.float32)
+    model = build_model(cfg, params, train=True)
+    outs = model(xs.to(_dev()), xt.to(_dev()), beta, mu, is_train=True, reverse=reverse)
+    loss = mcd_loss(outs, labels.to(_dev()))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert_close(loss.detach().cpu(), l64, TOL[engine], "MCD loss", noise=1e-7)
+    for i in (1, 2, 6, 7):
+        assert_close(outs[i].detach().cpu(), o64[i].detach(), TOL[engine], f"MCD output {i}", noise=1e-9)
+    assert "fc_classifier_video_source_2.weight" in g64
+    named = dict(model.named_parameters())
+    for name, go in g64.items():
+        assert named[name].grad is not None, name
+        assert_close(named[name].grad, go, GRAD_TOL[engine], f"MCD grad {name}",
+                     noise=abs_err(g32[name], go) * NOISE_SCALE[engine])
 
 
 def test_train_step_loss_weights_and_beta_schedule(engine):

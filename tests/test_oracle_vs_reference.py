@@ -100,3 +100,46 @@ def test_weighted_losses_match_the_reference_criteria():
     ref = ref + gen_golden.GAMMA * ref_loss.attentive_entropy(torch.cat((out_s, out_t), 0), alls[1])
     got = orc.compose_loss(outs_ref, labels, gen_golden.GAMMA, class_weight=cw, domain_weight=dw)
     assert_close(got.detach(), ref.detach(), 1e-6, "weighted loss")
+
+
+@pytest.mark.parametrize("reverse,mu", [(False, 0.0), (True, 0.7)])
+def test_oracle_mcd_variant_equals_live_reference(reverse, mu):
+    """ens_DA='MCD' (models.py:276-279, 716-720; main.py:447, 548-556): the second video-level classifier, the
+    `reverse=True` pass and the discrepancy loss dis_MCD (loss.py:29-30) -- outputs and every gradient of
+       CE(out_s) + CE(out_s_2) - dis_MCD(out_t, out_t_2)  on the live reference vs the oracle."""
+    ref_models, _, ref_loss = ref_shims.load()
+    torch.manual_seed(11)
+    m = ref_models.VideoModel(7, "video", "trn-m", "RGB", train_segments=5, val_segments=5, add_fc=1, fc_dim=512,
+                              dropout_i=0.0, dropout_v=0.0, partial_bn=False, use_bn="none", ens_DA="MCD",
+                              use_attn="TransAttn", share_params="Y", verbose=False)
+    m.train()                                  # (the reference's train() override returns None)
+    cfg = orc.PathConfig(num_class=7, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0, ens_DA="MCD")
+    p_init = orc.init_params(cfg, seed=11)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(p_init.keys())
+    for k in sd:
+        assert torch.equal(sd[k], p_init[k]), k
+    g = torch.Generator().manual_seed(12)
+    with torch.no_grad():                      # away from the degenerate 0.001 init
+        for k, v in m.named_parameters():
+            if "weight" in k:
+                v.add_(0.02 * torch.randn(v.shape, generator=g))
+    xs, xt = torch.randn(6, 5, 2048, generator=g), torch.randn(4, 5, 2048, generator=g)
+    labels = torch.randint(0, 7, (6,), generator=g)
+    beta = [0.75, 0.75, 0.5]
+    outs = m(xs, xt, beta, mu, is_train=True, reverse=reverse)
+    ce = torch.nn.CrossEntropyLoss()
+    loss_ref = ce(outs[1], labels) + ce(outs[2], labels) - ref_loss.dis_MCD(outs[6], outs[7])
+    loss_ref.backward()
+    params = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in m.state_dict().items()}
+    o = orc.forward(params, xs, xt, beta, mu, cfg, train=True, reverse=reverse)
+    loss = torch.nn.functional.cross_entropy(o[1], labels) + torch.nn.functional.cross_entropy(o[2], labels) - \
+        orc.dis_MCD(o[6], o[7])
+    loss.backward()
+    assert_close(loss.detach(), loss_ref.detach(), TOL_FP32, "MCD loss")
+    for i in (1, 2, 6, 7):
+        assert_close(o[i].detach(), outs[i].detach(), TOL_FP32, f"MCD output {i}")
+    assert not torch.equal(o[1], o[2])
+    for name, prm in m.named_parameters():
+        if prm.grad is not None:
+            assert_close(params[name].grad, prm.grad, 2e-4, f"MCD grad {name}")
