@@ -724,11 +724,10 @@ struct X3Shared {
 template <bool A_KMAJ, bool B_KMAJ>
 __global__ void __launch_bounds__(X3_THREADS, 1)
 seg_gemm_tc_x3_kernel(const __grid_constant__ GemmTable tab, const __grid_constant__ TcMaps maps,
-                      const __grid_constant__ TcSegMaps segmaps, int* __restrict__ fix_counters) {
+                      const __grid_constant__ TcSegMaps segmaps) {
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ __align__(8) X3Shared sh;
   __shared__ TileCtx ctx;
-  __shared__ int s_last;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -899,74 +898,26 @@ seg_gemm_tc_x3_kernel(const __grid_constant__ GemmTable tab, const __grid_consta
     // ---- fused epilogue on the running sums (same code as tc_epilogue, accumulators already in registers) ----
     const Group e = ctx.g;
     const int m = m0 + lq * 32 + lane;
-    const size_t plane = (size_t)e.M * e.N;
-    // split-K inside the kernel (fix_slot >= 0): every split stores its raw partial; the LAST one to arrive at the
-    // tile's counter sums all of them in split order and applies the epilogue -- no reduce launch, no waiting, and
-    // the result does not depend on which split came last.  Otherwise (separate reduce kernel) partial only.
-    bool finish = e.ksplit <= 1;
-    if (e.ksplit > 1) {
+    const int mode = e.ksplit > 1 ? TILE_PARTIAL : TILE_FINAL;
+    float* const obase = mode == TILE_PARTIAL ? e.partial + (size_t)split * e.M * e.N : e.C;
+    const int ldo = mode == TILE_PARTIAL ? e.N : e.ldc;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int nb = n0 + (chalf * 2 + c) * 32;
-        if (m < e.M && nb < e.N) {
-          float* orow = e.partial + (size_t)split * plane + (size_t)m * e.N + nb;
-          if (nb + 32 <= e.N && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(orow + j) = make_float4(sum[c][j], sum[c][j + 1], sum[c][j + 2], sum[c][j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < e.N) orow[j] = sum[c][j];
-          }
-        }
-      }
-      if (e.fix_slot >= 0 && fix_counters != nullptr) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight worker warps: all partial stores issued
-        if (wt == 0) {
-          __threadfence();                                      // release (cumulative over the CTA through the barrier)
-          const int before = atomicAdd(fix_counters + e.fix_slot + (m0 / TC_BM) * e.tiles_n + n0 / TC_BN, 1);
-          __threadfence();                                      // acquire the other splits' partials
-          s_last = before == e.ksplit - 1 ? 1 : 0;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        finish = s_last != 0;
-        if (finish) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int nb = n0 + (chalf * 2 + c) * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum[c][j] = 0.f;
-            if (m < e.M && nb < e.N) {
-              const int nvalid = min(32, e.N - nb);
-              for (int k = 0; k < e.ksplit; ++k) {
-                float pr[32];
-                load_row32(e.partial + (size_t)k * plane + (size_t)m * e.N + nb, nvalid, pr);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sum[c][j] += pr[j];
-              }
-            }
-          }
-        }
-      }
-    }
-    if (finish) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int nb = n0 + (chalf * 2 + c) * 32;
-        if (m < e.M && nb < e.N) {
-          float* orow = e.C + (size_t)m * e.ldc + nb;
-          const int nvalid = min(32, e.N - nb);
+    for (int c = 0; c < 2; ++c) {
+      const int nb = n0 + (chalf * 2 + c) * 32;
+      if (m < e.M && nb < e.N) {
+        float* orow = obase + (size_t)m * ldo + nb;
+        const int nvalid = min(32, e.N - nb);
+        if (mode == TILE_FINAL) {
           TA3N_EPI_DISPATCH(e.flags, { epilogue_row32<EPI_F>(e, m, nb, nvalid, sum[c]); })
-          if (nb + 32 <= e.N && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
+        }
+        if (nb + 32 <= e.N && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(orow + j) = make_float4(sum[c][j], sum[c][j + 1], sum[c][j + 2], sum[c][j + 3]);
-          } else {
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(orow + j) = make_float4(sum[c][j], sum[c][j + 1], sum[c][j + 2], sum[c][j + 3]);
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < e.N) orow[j] = sum[c][j];
-          }
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < e.N) orow[j] = sum[c][j];
         }
       }
     }
@@ -1122,8 +1073,7 @@ inline int tc_launch_stages(const GemmTable& tab, const TcMaps& maps, const TcSe
 
 // the precise kernel, per operand layout
 template <bool A_KMAJ, bool B_KMAJ>
-inline int tc_launch_x3(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream, const char* label,
-                        int* fix_counters) {
+inline int tc_launch_x3(const GemmTable& tab, const TcMaps& maps, const TcSegMaps& sm, cudaStream_t stream, const char* label) {
   constexpr int slot = (A_KMAJ ? 0 : 1) + (B_KMAJ ? 0 : 2);
   {
     std::lock_guard<std::mutex> lock(device_mu());
@@ -1136,8 +1086,7 @@ inline int tc_launch_x3(const GemmTable& tab, const TcMaps& maps, const TcSegMap
     }
   }
   pre_launch(label, stream);
-  launch_kernel(seg_gemm_tc_x3_kernel<A_KMAJ, B_KMAJ>, tab.total_tiles, X3_THREADS, x3_smem_bytes(), stream, tab, maps, sm,
-                fix_counters);
+  launch_kernel(seg_gemm_tc_x3_kernel<A_KMAJ, B_KMAJ>, tab.total_tiles, X3_THREADS, x3_smem_bytes(), stream, tab, maps, sm);
   return after_launch();
 }
 
@@ -1234,7 +1183,7 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool precise 
       g.tiles_n = (g.N + TC_BN - 1) / TC_BN;
       g.tile_begin = tiles;
       tiles += g.tiles_m * g.tiles_n * g.ksplit;
-      if (!(precise && plan_in.fix_counters != nullptr)) g.fix_slot = -1;
+      g.fix_slot = -1;
       any_split |= g.ksplit > 1;
       tab.g[ng++] = g;
       ++gi;
@@ -1243,17 +1192,14 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool precise 
     tab.total_tiles = tiles;
     tab.pad_ = (a3d ? 1 : 0) | (b3d ? 2 : 0);
     if (tiles > 0) {
-      int* fixc = precise ? plan_in.fix_counters : nullptr;
-      if (fixc != nullptr && any_split)       // arrival counters of the in-kernel split-K reduction
-        TA3N_CUDA(cudaMemsetAsync(fixc, 0, (size_t)plan_in.fix_count * sizeof(int), stream));
       if (precise && plan.a_kmaj && plan.b_kmaj)
-        TA3N_TRY((tc_launch_x3<true, true>(tab, maps, sm, stream, plan.label, fixc)));
+        TA3N_TRY((tc_launch_x3<true, true>(tab, maps, sm, stream, plan.label)));
       else if (precise && plan.a_kmaj && !plan.b_kmaj)
-        TA3N_TRY((tc_launch_x3<true, false>(tab, maps, sm, stream, plan.label, fixc)));
+        TA3N_TRY((tc_launch_x3<true, false>(tab, maps, sm, stream, plan.label)));
       else if (precise && !plan.a_kmaj && !plan.b_kmaj)
-        TA3N_TRY((tc_launch_x3<false, false>(tab, maps, sm, stream, plan.label, fixc)));
+        TA3N_TRY((tc_launch_x3<false, false>(tab, maps, sm, stream, plan.label)));
       else if (precise)
-        TA3N_TRY((tc_launch_x3<false, true>(tab, maps, sm, stream, plan.label, fixc)));
+        TA3N_TRY((tc_launch_x3<false, true>(tab, maps, sm, stream, plan.label)));
       else if (plan.a_kmaj && plan.b_kmaj)
         TA3N_TRY((tc_launch_one<true, true>(tab, maps, sm, stream, plan.label)));
       else if (plan.a_kmaj && !plan.b_kmaj)
@@ -1270,7 +1216,7 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool precise 
         size_t mx4 = 0;
         for (int i = 0; i < ng; ++i) {
           const Group& g = tab.g[i];
-          if (g.ksplit <= 1 || g.fix_slot >= 0) continue;
+          if (g.ksplit <= 1) continue;
           sgs.idx[sgs.n++] = (unsigned char)i;
           const bool ok = g.N % 4 == 0 && g.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15u) == 0 &&
                           (reinterpret_cast<uintptr_t>(g.partial) & 15u) == 0 &&
@@ -1278,9 +1224,7 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool precise 
           vec = vec && ok;
           mx4 = std::max(mx4, (size_t)g.M * g.N / 4);
         }
-        if (sgs.n == 0) {
-          // every split group is finished inside the GEMM kernel
-        } else if (vec) {
+        if (vec && sgs.n > 0) {
           dim3 grid((unsigned)std::min<size_t>((mx4 + 255) / 256, 1024), sgs.n);
           pre_launch("splitk_reduce", stream);
           launch_kernel(splitk_reduce_v4_kernel, grid, 256, 0, stream, tab, sgs);
@@ -1289,7 +1233,7 @@ inline int launch_tc(const GemmPlan& plan_in, cudaStream_t stream, bool precise 
           pre_launch("splitk_reduce", stream);
           launch_kernel(splitk_reduce_kernel, grid, 256, 0, stream, tab);
         }
-        if (sgs.n > 0) TA3N_TRY(after_launch());
+        TA3N_TRY(after_launch());
       }
     }
   }
@@ -1353,7 +1297,6 @@ inline void plan_splitk_balanced(GemmPlan& plan, Arena* arena, int sms) {
       best = ks;
     }
   }
-  int n_counters = 0;
   for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
     Group& g = plan.groups[gi];
     if (best[gi] < 2) continue;
@@ -1361,14 +1304,6 @@ inline void plan_splitk_balanced(GemmPlan& plan, Arena* arena, int sms) {
     if (!p) continue;                      // scratch too small: stay unsplit (still correct)
     g.ksplit = best[gi];
     g.partial = p;
-    g.fix_slot = n_counters;               // arrival counters of its tiles (in-kernel reduction by the last split)
-    n_counters += ((g.M + TC_BM - 1) / TC_BM) * ((g.N + TC_BN - 1) / TC_BN);
-  }
-  if (n_counters > 0) {
-    plan.fix_counters = reinterpret_cast<int*>(arena->floats((size_t)n_counters));
-    plan.fix_count = n_counters;
-    if (!plan.fix_counters)
-      for (Group& g : plan.groups) g.fix_slot = -1;       // no room: separate reduce pass
   }
 }
 

@@ -660,8 +660,6 @@ struct GemmPlan {
   int load_flags = 0;
   bool precise = false;             // a forward layer: the x3 engine runs it at fp32 grade (gemm_tcgen05.cuh)
   bool precise_dgrad = false;       // a data-gradient GEMM (feeds further GEMMs): x3 engine, fp32 grade as well
-  int* fix_counters = nullptr;      // precise launches: arrival counters of the in-kernel split-K reduction
-  int fix_count = 0;
   const char* label = "seg_gemm";   // call-site name used by the timing registry
 
   // add a group; its segments must be pushed right after with add_seg
