@@ -418,13 +418,19 @@ def test_cpu_tensors_are_moved_not_computed_on_cpu():
 # ------------------------------------------------------------------------------------------------
 # fused loss heads and the fused / graph-captured training step
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["legacy", "phased", "fused"])
 @pytest.mark.parametrize("use_graph", [False, True])
 @pytest.mark.parametrize("T,attn_frame,bs,bt,C", [(5, "none", 24, 24, 12), (4, "TransAttn", 9, 5, 30),
                                                    (3, "none", 60, 11, 51)])     # C > 32: chunked class head
-def test_fused_train_step_matches_oracle(T, attn_frame, bs, bt, C, use_graph, engine):
+def test_fused_train_step_matches_oracle(T, attn_frame, bs, bt, C, use_graph, engine, mode):
     """TrainStep (forward + fused loss heads + backward, no autograd) vs the fp64 oracle's
-    loss and parameter gradients; dropout off so both see the same function."""
+    loss and parameter gradients; dropout off so both see the same function.  All three executors: the per-operator
+    sequence, the step program as launches, the step program as one persistent kernel (plain tf32 tiles only)."""
     from ta3n_b200.train import TrainStep
+    if mode != "legacy" and attn_frame != "none":
+        pytest.skip("frame attention is covered by the per-operator sequence only")
+    if mode == "fused" and engine != "tf32":
+        pytest.skip("the persistent kernel runs plain tf32 tiles")
     cfg = orc.PathConfig(num_class=C, num_segments=T, fc_dim=512, dropout_i=0.0, dropout_v=0.0,
                          use_attn="TransAttn", use_attn_frame=attn_frame)
     params = orc.init_params(cfg, seed=21)
@@ -438,7 +444,7 @@ def test_fused_train_step_matches_oracle(T, attn_frame, bs, bt, C, use_graph, en
     beta = (0.75, 0.6, 0.5)
     loss_o, _, grads_o, n_loss, _, n_grad = oracle_truth(params, xs, xt, labels, beta, cfg, 0.003, True, None)
     model = build_model(cfg, params, train=True)
-    step = TrainStep(model, bs, bt, beta, gamma=0.003, use_graph=use_graph)
+    step = TrainStep(model, bs, bt, beta, gamma=0.003, use_graph=use_graph, mode=mode)
     for _ in range(2):                                       # replays are idempotent
         loss = step(xs.pin_memory(), xt.pin_memory(), labels)
     torch.cuda.synchronize()
