@@ -295,13 +295,16 @@ def run_reference(args):
 
 
 def workload_config(args, world, engine):
-    return {"workload": f"cfg2: B={args.batch} source + {args.batch} target videos per GPU, T={args.segments}, "
+    name = {(256, 5, 12, 512): "cfg2", (512, 5, 30, 512): "cfg5 per GPU", (8, 5, 5, 512): "cfg1",
+            (128, 9, 12, 512): "cfg3 without frame attention"}.get((args.batch, args.segments, args.classes, args.fc_dim),
+                                                                   "custom")
+    return {"workload": f"{name}: B={args.batch} source + {args.batch} target videos per GPU, T={args.segments}, "
                         f"D={D}, fc_dim={args.fc_dim}, {args.classes} classes, TRN-M + TransAttn + RevGrad "
                         f"discriminators (frame/video/relation)",
             "global_batch": 2 * args.batch * world, "per_gpu_clips": 2 * args.batch,
             "api": "ta3n_b200.train.TrainStep (forward + fused loss heads + backward, one CUDA graph)",
             "step": "forward + composed loss + backward to all parameter gradients"
-                    + (" + flat NCCL gradient all-reduce" if world > 1 else ""),
+                    + (" + gradient all-reduce (see `allreduce`)" if world > 1 else ""),
             "optimizer": "excluded from value (metric is fwd+bwd); included in e2e",
             "dropout": "0.5/0.5 (product arm: in-kernel counter RNG; reference arm: nn.Dropout)",
             "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) before every timed step",
