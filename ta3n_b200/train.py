@@ -262,6 +262,8 @@ class TrainStep:
         self.branch_stream = torch.cuda.Stream(device=dev) if parallel_branches else None
         self.overlap_wgrad = bool(overlap_wgrad)
         self.side_stream = torch.cuda.Stream(device=dev) if self.overlap_wgrad else None
+        self.early_ar = os.environ.get("TA3N_EARLY_ALLREDUCE", "1") != "0"
+        self.ar_stream = torch.cuda.Stream(device=dev) if (self.overlap_wgrad and self.ar is not None) else None
         self.launches_per_step = 0               # kernels of libta3n_sm100.so per step (counted at capture)
         self.use_graph = bool(use_graph)
         self.graphs = [None] * self.n_slots      # per input slot: (graph_a, graph_b or None)
@@ -298,7 +300,8 @@ class TrainStep:
             flat = symm.empty(n, dtype=torch.float32, device=self.device)
             flat.zero_()
             hdl = symm.rendezvous(flat, group)
-            flags = symm.empty(lib.ta3n_allreduce_flag_bytes(self.world) // 4, dtype=torch.int32, device=self.device)
+            self._ar_flag_bytes = lib.ta3n_allreduce_flag_bytes(self.world)
+            flags = symm.empty(2 * self._ar_flag_bytes // 4, dtype=torch.int32, device=self.device)      # two call slots
             flags.zero_()
             fh = symm.rendezvous(flags, group)
             torch.cuda.synchronize()
@@ -317,12 +320,16 @@ class TrainStep:
             self.ar = None
             return torch.zeros(n, device=self.device, dtype=torch.float32)
 
-    def _enqueue_allreduce(self):
-        """Mean of the gradient bucket over the ranks on the current stream (graph-capturable)."""
+    def _enqueue_allreduce(self, lo=0, hi=None, slot=0, stream=None):
+        """Mean over the ranks of floats [lo, hi) of the gradient bucket on `stream` (default: the current one;
+        graph-capturable).  `slot` selects one of the two flag regions, so that two calls of one step -- the early
+        bucket on a forked stream, the late one behind the backward -- never share a barrier flag."""
         a = self.ar
+        hi = self.flat_grad.numel() if hi is None else hi
         check(_lib.load().ta3n_allreduce_mean(
-            _lib.ptr_array(a["bufs"]), a["mc"] or None, _lib.ptr_array(a["flags"]), _P(self.step_counter),
-            a["rank"], a["world"], self.flat_grad.numel(), TF._stream()))
+            _lib.ptr_array([p + 4 * lo for p in a["bufs"]]), (a["mc"] + 4 * lo) if a["mc"] else None,
+            _lib.ptr_array([p + slot * self._ar_flag_bytes for p in a["flags"]]), _P(self.step_counter),
+            a["rank"], a["world"], hi - lo, stream if stream is not None else TF._stream()))
 
     # -- the fused step (C ABI ta3n_step_*) ------------------------------------------------------------
     def _build_step(self, slot):
@@ -503,6 +510,8 @@ class TrainStep:
         else:
             flush_after = {"shared": 0}
 
+        early_ar = self.ar is not None and at_split is None and self.overlap_wgrad and self.early_ar
+
         def stage_done(name):
             if name not in flush_after:
                 return
@@ -512,6 +521,13 @@ class TrainStep:
                 ev.record(main)
                 side.wait_event(ev)
                 check(lib.ta3n_wgrad_defer_flush(_P(ws), ws.numel(), side.cuda_stream))
+                if name == "trn" and early_ar:
+                    # the video / relation / TRN gradients (62 % of the bucket) are complete on the side stream:
+                    # reduce them now, on a third stream, under the frame-discriminator / shared-layer backward
+                    done = torch.cuda.Event()
+                    done.record(side)
+                    self.ar_stream.wait_event(done)
+                    self._enqueue_allreduce(0, self.early_numel, slot=0, stream=self.ar_stream.cuda_stream)
             else:
                 check(lib.ta3n_wgrad_defer_flush(_P(ws), ws.numel(), TF._stream()))
             if name == "trn" and at_split is not None:
@@ -526,7 +542,10 @@ class TrainStep:
                          stage_done=stage_done, side_stream=self.branch_stream)
         if self.overlap_wgrad:
             main.wait_stream(side)            # join
-        if self.ar is not None and at_split is None:
+        if early_ar:
+            main.wait_stream(self.ar_stream)
+            self._enqueue_allreduce(self.early_numel, None, slot=1)      # the late 38 %: the only exposed part
+        elif self.ar is not None and at_split is None:
             self._enqueue_allreduce()         # same stream, same graph: step -> all-reduce -> optimizer
         if optimizer and self.opt is not None:
             self._enqueue_optimizer()

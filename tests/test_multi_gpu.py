@@ -38,7 +38,8 @@ def _free_port():
 
 VARIANTS = {"nccl-legacy": dict(mode="legacy", allreduce="nccl"),      # two graphs, NCCL overlapping the second
             "peer-legacy": dict(mode="legacy", allreduce="peer"),      # one graph: step + library all-reduce + optimizer
-            "peer-phased": dict(mode="phased", allreduce="peer")}
+            "peer-legacy-early": dict(mode="legacy", allreduce="peer", overlap_wgrad=True),   # + early bucket reduced
+            "peer-phased": dict(mode="phased", allreduce="peer")}                             #   on a forked stream
 
 
 def _worker(rank, world, port, q, variant):
