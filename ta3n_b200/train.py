@@ -262,7 +262,10 @@ class TrainStep:
         self.branch_stream = torch.cuda.Stream(device=dev) if parallel_branches else None
         self.overlap_wgrad = bool(overlap_wgrad)
         self.side_stream = torch.cuda.Stream(device=dev) if self.overlap_wgrad else None
-        self.early_ar = os.environ.get("TA3N_EARLY_ALLREDUCE", "1") != "0"
+        # measured at N=2 (profiles/r2_bench_n2_early_allreduce.txt): 0.448 ms/step with the early bucket reduced on a
+        # forked stream against 0.432 with one all-reduce behind the step -- the collective is latency / rank-skew bound
+        # (a second kernel pays the fixed ~25 us again and competes for SMs), so the split is opt-in
+        self.early_ar = os.environ.get("TA3N_EARLY_ALLREDUCE", "0") == "1"
         self.ar_stream = torch.cuda.Stream(device=dev) if (self.overlap_wgrad and self.ar is not None) else None
         self.launches_per_step = 0               # kernels of libta3n_sm100.so per step (counted at capture)
         self.use_graph = bool(use_graph)
@@ -307,7 +310,10 @@ class TrainStep:
             torch.cuda.synchronize()
             dist.barrier(group=self.group)              # every rank's flags are zero before anybody signals
             mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
-            if os.environ.get("TA3N_ALLREDUCE_NO_MULTICAST") == "1":
+            # two ranks: plain peer loads / stores are faster than the switch reduction (50 vs 61 us back to back,
+            # 13.9 MB; at eight ranks 80 vs 67: tools/allreduce_probe.py, profiles/r2_allreduce_probe_n*.txt)
+            if os.environ.get("TA3N_ALLREDUCE_NO_MULTICAST") == "1" or (self.world <= 2 and
+                                                                         os.environ.get("TA3N_ALLREDUCE_MULTICAST") != "1"):
                 mc = 0
             self.ar = dict(bufs=[int(p) for p in hdl.buffer_ptrs], flags=[int(p) for p in fh.buffer_ptrs],
                            mc=mc, rank=int(hdl.rank), world=int(hdl.world_size), keep=(flat, flags, hdl, fh))
