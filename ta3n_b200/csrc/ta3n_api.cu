@@ -1120,7 +1120,16 @@ int ta3n_allreduce_mean(float* const* peer_bufs_host, float* multicast_buf, uint
   }
   TA3N_REQUIRE((reinterpret_cast<uintptr_t>(multicast_buf) & 15u) == 0, "multicast mapping must be 16-byte aligned");
   pre_launch("allreduce_mean", S(stream));
-  launch_kernel(allreduce_mean_kernel, kArBlocks, kArThreads, 0, S(stream), P, multicast_buf,
+  // CTAs of the kernel (each one is a participant of the two flag barriers): TA3N_AR_BLOCKS overrides the default
+  static const int env_blocks = []() {
+    const char* e = getenv("TA3N_AR_BLOCKS");
+    return e ? atoi(e) : 0;
+  }();
+  // measured at N=4 (cfg2 step, profiles/r2_allreduce_blocks.txt): 64 CTAs 0.411 ms/step, 32: 0.423, 128: 0.425 --
+  // fewer barrier participants, still enough loads in flight; two ranks use the peer path and want all 128
+  int blocks = env_blocks > 0 ? env_blocks : (world > 2 ? 64 : kArBlocks);
+  blocks = std::max(1, std::min(blocks, kArBlocks));
+  launch_kernel(allreduce_mean_kernel, blocks, kArThreads, 0, S(stream), P, multicast_buf,
                 reinterpret_cast<const unsigned long long*>(seq_dev), rank, world, (size_t)(n / 4), 1.0f / (float)world);
   return after_launch();
 }
