@@ -90,6 +90,11 @@ int ta3n_get_gemm_engine(void);
  * (deterministic partials + fixed-order reduce).  The forward entry points take no workspace argument, hence this
  * registration; the launches that use it are stream-ordered, so one buffer serves them all.  48 MB cover cfg5.      */
 int ta3n_set_forward_scratch(void* scratch, size_t bytes);
+/* Host-only (no CUDA call): the split-K factors that balancing would choose for one precise forward launch of
+ * n_groups GEMMs C[M,N] = A[M,K] B[N,K]^T on `sms` SMs with scratch_bytes of forward scratch -> ksplit_out[n_groups];
+ * makespan_out (optional, 2 doubles) = {unsplit, chosen} longest per-SM queue of the planner's model, in K-slab units. */
+int ta3n_plan_forward_splits(int n_groups, const int* M, const int* N, const int* K, int sms, size_t scratch_bytes,
+                             int* ksplit_out, double* makespan_out);
 /* Per-call-site device timing (CUDA events on the launching stream, eager mode only; not for use
  * under graph capture).  ta3n_timing_report synchronises the recorded events, writes lines
  * "label count total_ms\n" to buf, clears the registry and returns the bytes needed.           */

@@ -51,6 +51,7 @@ class StepDesc(C.Structure):
 STEP_HANDLE_BYTES = 256
 
 _VP, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_IP = C.POINTER(C.c_int)
 _PP = C.POINTER(C.c_void_p)
 _TAB = C.POINTER(RelationTable)
 _DRP = C.POINTER(Dropout)
@@ -64,6 +65,7 @@ SIGNATURES = {
     "ta3n_set_gemm_engine": (_I, [_I]),
     "ta3n_get_gemm_engine": (_I, []),
     "ta3n_set_forward_scratch": (_I, [_VP, _SZ]),
+    "ta3n_plan_forward_splits": (_I, [_I, _IP, _IP, _IP, _I, _SZ, _IP, C.POINTER(C.c_double)]),
     "ta3n_timing_enable": (None, [_I]),
     "ta3n_timing_report": (_SZ, [C.c_char_p, _SZ]),
     "ta3n_shared_fc_fwd": (_I, [_VP, _I, _VP, _I, _I, _VP, _VP, _I, _DRP, _VP, _VP]),
@@ -159,13 +161,24 @@ def ptr_array(ptrs):
 
 
 def set_gemm_engine(engine) -> None:
-    """'tf32' (tcgen05 tensor cores; the library default) or 'fp32' (exact SIMT tiles)."""
+    """'tf32x3' (tcgen05, error-compensated tf32: fp32-grade forward; the library default), 'tf32' (plain tcgen05
+    tf32) or 'fp32' (exact SIMT tiles)."""
     code = {"fp32": TA3N_GEMM_FP32_SIMT, "tf32": TA3N_GEMM_TF32_TCGEN05, "tf32x3": TA3N_GEMM_TF32X3_TCGEN05}.get(engine, engine)
     check(load().ta3n_set_gemm_engine(int(code)))
 
 
 def get_gemm_engine() -> str:
     return {0: "fp32", 1: "tf32", 2: "tf32x3"}[load().ta3n_get_gemm_engine()]
+
+
+def plan_forward_splits(shapes, sms: int = 148, scratch_bytes: int = 48 << 20):
+    """Split-K factors the tf32x3 engine's balanced planner picks for one forward launch of GEMMs [(M, N, K), ...]
+    (host-only, C ABI ta3n_plan_forward_splits).  Returns (ksplit list, unsplit makespan, chosen makespan)."""
+    n = len(shapes)
+    arr = lambda col: (C.c_int * n)(*[int(s[col]) for s in shapes])
+    ks, span = (C.c_int * n)(), (C.c_double * 2)()
+    check(load().ta3n_plan_forward_splits(n, arr(0), arr(1), arr(2), int(sms), int(scratch_bytes), ks, span))
+    return list(ks), span[0], span[1]
 
 
 def launch_count() -> int:

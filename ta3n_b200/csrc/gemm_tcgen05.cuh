@@ -1353,7 +1353,9 @@ inline int run_gemm(GemmPlan& plan, cudaStream_t stream, Arena* splitk_arena = n
     }
     if (!tc_idx.empty()) {
       GemmPlan tc = sub_plan(plan, tc_idx);
-      if (precise && splitk_arena == nullptr && forward_scratch().ptr != nullptr) {
+      // only the forward plans: they run on ONE stream, in order, so they can share the scratch; precise data-gradient
+      // plans (TA3N_X3_DGRAD=1) may run on forked streams (parallel_branches) and stay unsplit
+      if (precise && plan.precise && splitk_arena == nullptr && forward_scratch().ptr != nullptr) {
         Arena scratch(forward_scratch().ptr, forward_scratch().bytes);
         plan_splitk_balanced(tc, &scratch, device_sm_count());
       } else {

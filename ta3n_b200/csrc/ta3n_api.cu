@@ -1008,6 +1008,35 @@ int ta3n_step_run(const void* handle_host, ta3n_stream_t stream) {
   return after_launch();
 }
 
+// Host-only: the split-K factors the balanced planner (gemm_tcgen05.cuh: plan_splitk_balanced) would choose for a
+// precise forward launch of n_groups GEMMs C[M,N] += A[M,K] B[N,K]^T on `sms` SMs with `scratch_bytes` of forward
+// scratch; ksplit_out[n_groups] receives them, makespan_out[2] = {unsplit, chosen} makespan of the LPT model in K-slab
+// units.  No CUDA call: the planner's policy is testable on a machine without a GPU.
+int ta3n_plan_forward_splits(int n_groups, const int* M, const int* N, const int* K, int sms, size_t scratch_bytes,
+                             int* ksplit_out, double* makespan_out) {
+  if (n_groups <= 0 || !M || !N || !K || !ksplit_out || sms <= 0)
+    return fail(TA3N_ERR_INVALID, "ta3n_plan_forward_splits: bad arguments");
+  GemmPlan plan;
+  for (int i = 0; i < n_groups; ++i) {
+    if (M[i] <= 0 || N[i] <= 0 || K[i] <= 0)
+      return fail(TA3N_ERR_INVALID, "ta3n_plan_forward_splits: group %d has M=%d N=%d K=%d", i, M[i], N[i], K[i]);
+    plan.add_group(M[i], N[i], nullptr, N[i]);
+    plan.add_seg(nullptr, K[i], nullptr, K[i], K[i]);
+  }
+  std::vector<int> ones(n_groups, 1);
+  const double before = x3_makespan(plan, ones, sms);
+  // the arena only hands out addresses here (nothing is dereferenced); any non-null base will do
+  Arena scratch(reinterpret_cast<void*>(uintptr_t(256)), scratch_bytes);
+  plan_splitk_balanced(plan, &scratch, sms);
+  std::vector<int> ks(n_groups);
+  for (int i = 0; i < n_groups; ++i) ks[i] = ksplit_out[i] = plan.groups[i].ksplit;
+  if (makespan_out) {
+    makespan_out[0] = before;
+    makespan_out[1] = x3_makespan(plan, ks, sms);
+  }
+  return TA3N_OK;
+}
+
 // Host-only description of the task graph the fused step would run for `desc` (no CUDA call; pointers in desc only
 // need to be non-null): "tasks T gemm_tiles G tail R colsum_parts P colsum_reduces Q counters N maps K slabs S".
 size_t ta3n_step_describe(const ta3n_step_desc* desc, char* buf, size_t buf_bytes) {

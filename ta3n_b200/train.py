@@ -11,10 +11,13 @@ Gradients land directly in a flat fp32 bucket whose views are installed as ``par
 ``grad=None``, as in the reference).
 
 Data parallelism (one process per GPU, videos sharded, weights replicated) replaces the reference's
-``nn.DataParallel`` (main.py:79) by NCCL all-reduces over that bucket.  With more than one rank the step is
-captured as TWO graphs split where the backward has produced the gradients of the video / relation / TRN
-layers (62 % of the bytes): their all-reduce runs on NCCL's stream while the second graph (frame
-discriminator + shared layer backward) computes; only the second, smaller all-reduce is exposed.
+``nn.DataParallel`` (main.py:79) by an all-reduce (mean) over that bucket.  Default with several ranks: the bucket
+lives in symmetric memory and the library's own one-kernel all-reduce (csrc/allreduce.cuh: NVLink peer loads / NVSwitch
+multicast reduction) follows the backward inside the SAME CUDA graph, then the optimizer -- one graph replay per
+iteration.  ``allreduce='nccl'`` (or a system without symmetric memory) falls back to NCCL: the step is then captured
+as TWO graphs split where the backward has produced the gradients of the video / relation / TRN layers (62 % of the
+bytes); their all-reduce runs on NCCL's stream while the second graph (frame discriminator + shared layer backward)
+computes, and only the second, smaller all-reduce is exposed.
 """
 from __future__ import annotations
 
@@ -93,9 +96,10 @@ def flatten_parameters(model) -> torch.Tensor:
 
 class TrainStep:
     """Options ``overlap_wgrad`` / ``parallel_branches`` put independent parts of the backward on forked streams
-    inside the captured graph.  Measured on B200 (tools/concurrency_probe.py): forked sub-wave tcgen05 GEMM nodes
-    of one graph do not overlap (49.9 us forked vs 50.4 us sequential for two 80-tile launches), so both are off
-    by default; they stay available and tested for correctness."""
+    inside the captured graph.  Measured on B200: forked sub-wave tcgen05 GEMM nodes of one graph do not overlap under
+    plain tf32 (tools/concurrency_probe.py: 49.9 us forked vs 50.4 us sequential for two 80-tile launches), so
+    ``parallel_branches`` is off by default; ``overlap_wgrad`` defaults to on only under the tf32x3 engine, where the
+    small precise weight-gradient launch hides behind the data-gradient chain (tools/legacy_options.py: -12 us)."""
 
     def __init__(self, model, batch_source: int, batch_target: int, beta: Sequence[float], gamma: float = 0.003,
                  place_adv: Sequence[str] = ("Y", "Y", "Y"), add_loss_DA: str = "attentive_entropy",
