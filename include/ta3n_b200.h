@@ -166,7 +166,9 @@ int ta3n_relattn_fwd(const float* feat_rel, int M, int R, int H, const float* co
                      float* attn, float* feat_video, ta3n_stream_t stream);
 size_t ta3n_relattn_bwd_workspace_bytes(int M, int R, int H);
 /* g_feat_video [M,H], g_pred_rel [M,R,2] (may be NULL), g_attn [M,R] (may be NULL)
- * -> d_feat_rel [M,R,H] and the discriminator gradients; beta = beta[0].                 */
+ * -> d_feat_rel [M,R,H] and the discriminator gradients; beta = beta[0].
+ * use_attn == 2: the weights in attn [M,R] were produced by ta3n_general_attn_fwd: G is scaled by (attn + 1) as for
+ * TransAttn, but no gradient flows from the weights into pred_rel (g_attn is ignored; ta3n_general_attn_bwd owns it). */
 int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* const* W1_host,
                      const float* const* W2_host, int use_attn, const float* hidden,
                      const float* pred_rel, const float* attn, const float* g_feat_video,
@@ -174,6 +176,24 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
                      float* d_feat_rel, float* const* dW1_host, float* const* db1_host,
                      float* const* dW2_host, float* const* db2_host, void* workspace,
                      size_t workspace_bytes, ta3n_stream_t stream);
+
+/* ---- 'general' attention over the relation features (use_attn='general') ----------- */
+/* models.py:320-325 (attn_layer = Linear(H,H), Tanh, Linear(H,1)), :359-366 (softmax over the R relations),
+ * :379-388 (re-weighting by attn + 1), :651 (sum).  Call after ta3n_relattn_fwd(use_attn = 0), which leaves the
+ * plain sum in feat_video:
+ *   hidden [M*R,H] <- tanh(feat_rel W1^T + b1) (saved);  attn [M,R] <- softmax_r(hidden w2 + b2);
+ *   feat_video [M,H] += sum_r attn[:,r] feat_rel[:,r,:].      W1 [H,H], b1 [H], w2 [1,H], b2 [1]               */
+int ta3n_general_attn_fwd(const float* feat_rel, int M, int R, int H, const float* W1, const float* b1,
+                          const float* w2, const float* b2, float* hidden, float* attn, float* feat_video,
+                          ta3n_stream_t stream);
+size_t ta3n_general_attn_bwd_workspace_bytes(int M, int R, int H);
+/* Call after ta3n_relattn_bwd(use_attn = 2), which has written d_feat_rel = (attn + 1) G + discriminator part:
+ * g_feat_video = G [M,H], g_attn [M,R] (may be NULL) -> d_feat_rel [M,R,H] += gradient through the weights;
+ * dW1 [H,H], db1 [H], dw2 [1,H], db2 [1] are written.                                                            */
+int ta3n_general_attn_bwd(const float* feat_rel, int M, int R, int H, const float* W1, const float* w2,
+                          const float* hidden, const float* attn, const float* g_feat_video, const float* g_attn,
+                          float* d_feat_rel, float* dW1, float* db1, float* dw2, float* db2, void* workspace,
+                          size_t workspace_bytes, ta3n_stream_t stream);
 
 /* ---- video head: Dropout -> [GRL_mu] -> Linear(H -> C)  (models.py:679-687) -------- */
 /* feat_video [M,H] -> dropped [M,H] (saved; equals feat_video when no dropout),

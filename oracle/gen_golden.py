@@ -38,6 +38,7 @@ CASES = {
     "t9_attnframe": dict(bs=4, bt=4, T=9, C=12, F=512, train=True, use_attn="TransAttn", attn_frame="TransAttn"),
     "noattn_f256": dict(bs=5, bt=5, T=5, C=12, F=256, train=False, use_attn="none", attn_frame="none"),
     "t3_f2048": dict(bs=2, bt=2, T=3, C=6, F=2048, train=True, use_attn="TransAttn", attn_frame="none"),
+    "general_attn": dict(bs=7, bt=5, T=5, C=12, F=512, train=True, use_attn="general", attn_frame="none"),
 }
 BETA = (0.75, 0.75, 0.5)
 GAMMA = 0.003

@@ -9,7 +9,7 @@ one code path of cmhungsteve/TA3N that this repo accelerates:
 
     VideoModel.forward with frame_aggregation='trn-m', baseline_type='video',
     add_fc=1, use_bn='none', ens_DA='none', share_params='Y',
-    use_attn in {'TransAttn','none'}, use_attn_frame in {'none','TransAttn'}
+    use_attn in {'TransAttn','general','none'}, use_attn_frame in {'none','TransAttn'}
 
 plus the loss composition that main.py applies right after it.  Each function
 cites the reference file:line it follows (paths relative to /root/reference).
@@ -54,7 +54,7 @@ class PathConfig:
     fc_dim: int = 512
     dropout_i: float = 0.5
     dropout_v: float = 0.5
-    use_attn: str = "TransAttn"    # or 'none'
+    use_attn: str = "TransAttn"    # or 'general' / 'none'
     use_attn_frame: str = "none"   # or 'TransAttn'
     ens_DA: str = "none"           # or 'MCD': a second video-level classifier (models.py:276-279, 716-720)
 
@@ -143,13 +143,16 @@ def init_params(cfg: PathConfig, seed: Optional[int] = None) -> "OrderedDict[str
     for i in range(T - 1):
         put(f"relation_domain_classifier_all.{i}.0", _default_linear(H, H))
         put(f"relation_domain_classifier_all.{i}.2", _default_linear(H, 2))
+    if cfg.use_attn == "general":                               # models.py:320-325: attn_layer, PyTorch default init
+        put("attn_layer.0", _default_linear(H, H))
+        put("attn_layer.2", _default_linear(H, 1))
     return p
 
 
 USED_PARAM_PREFIXES = (
     "fc_feature_shared_source", "fc_feature_domain.", "fc_classifier_domain.",
     "TRN.", "fc_feature_domain_video", "fc_classifier_video_source",      # (also ..._source_2 under MCD)
-    "fc_classifier_domain_video", "relation_domain_classifier_all",
+    "fc_classifier_domain_video", "relation_domain_classifier_all", "attn_layer",
 )
 
 
@@ -177,6 +180,14 @@ class _FlipGrad(torch.autograd.Function):
 
 def grad_reverse(x: torch.Tensor, beta: float) -> torch.Tensor:
     return _FlipGrad.apply(x, beta)
+
+
+def general_attention(p: Dict[str, torch.Tensor], feat: torch.Tensor) -> torch.Tensor:
+    """get_general_attn (models.py:359-366): feat (B, n, H) -> softmax over the n segments of attn_layer(feat), (B, n)."""
+    n = feat.size(1)
+    hid = torch.tanh(F.linear(feat.reshape(-1, feat.size(-1)), p["attn_layer.0.weight"], p["attn_layer.0.bias"]))
+    s = F.linear(hid, p["attn_layer.2.weight"], p["attn_layer.2.bias"]).view(-1, n, 1)
+    return F.softmax(s, dim=1).view(-1, n)
 
 
 def entropy_attention(logits: torch.Tensor) -> torch.Tensor:
@@ -237,7 +248,9 @@ def activation_pattern(params, xs, xt, beta, cfg: "PathConfig") -> Dict[str, tor
                    p[f"relation_domain_classifier_all.{i}.0.bias"]) for i in range(R)]
     g["rel_disc"] = [h > 0 for h in hr]
     relf = torch.stack(rel, 1)
-    if cfg.use_attn != "none":
+    if cfg.use_attn == "general":
+        relf = (general_attention(p, relf).unsqueeze(-1) + 1) * relf
+    elif cfg.use_attn != "none":
         pr = torch.stack([F.linear(F.relu(hr[i]), p[f"relation_domain_classifier_all.{i}.2.weight"],
                                    p[f"relation_domain_classifier_all.{i}.2.bias"]) for i in range(R)], 1)
         w = entropy_attention(pr.reshape(-1, 2)).view(M, R)
@@ -322,7 +335,10 @@ def _forward_domain(p: Dict[str, torch.Tensor], x: torch.Tensor, beta: Sequence[
          for i in range(R)], 1)                                                        # :472-488 -> (B,R,2)
 
     if cfg.use_attn != "none":                                                         # :643-645, :379-388
-        w_rel = entropy_attention(pred_rel.reshape(-1, 2)).view(batch, R)
+        if cfg.use_attn == "general":                                                  # :382-383, :359-366
+            w_rel = general_attention(p, rel)
+        else:
+            w_rel = entropy_attention(pred_rel.reshape(-1, 2)).view(batch, R)
         rel_att = (w_rel.unsqueeze(-1) + 1) * rel
         attn = w_rel
     else:                                                                              # :647

@@ -84,6 +84,9 @@ SIGNATURES = {
     "ta3n_relattn_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ta3n_relattn_bwd": (_I, [_VP, _I, _I, _I, _PP, _PP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP,
                               _PP, _PP, _PP, _PP, _VP, _SZ, _VP]),
+    "ta3n_general_attn_fwd": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "ta3n_general_attn_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ta3n_general_attn_bwd": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "ta3n_video_head_fwd": (_I, [_VP, _I, _I, _I, _VP, _VP, _DRP, _VP, _VP, _VP]),
     "ta3n_video_head_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ta3n_video_head_bwd": (_I, [_VP, _I, _I, _I, _VP, _DRP, _VP, _VP, _VP, _F, _VP, _VP, _VP, _VP, _SZ, _VP]),

@@ -382,6 +382,86 @@ __global__ void attn_placeholder_bwd_kernel(const float* __restrict__ g_attn, fl
     d_feat_rel[(size_t)e * H] += g_attn[e];
 }
 
+// ---- 'general' attention over the relation features              models.py:320-325, 359-366, 379-388 ----
+// attn_layer = Linear(H,H) -> Tanh -> Linear(H,1); the first Linear (+ bias) has been applied by a GEMM and sits in
+// `hidden` [M*R, H] (row m*R + r).  Block per video, warp per relation:
+//   hidden <- tanh(hidden);  s_r = <w2, hidden_r> + b2;  a = softmax_r(s);  attn[m,:] = a
+//   feat_video[m,:] += sum_r a_r feat_rel[m,r,:]          (it already holds the plain sum: (a_r + 1) in total)
+__global__ void __launch_bounds__(kRelWarps * 32)
+general_attn_fwd_kernel(const float* __restrict__ feat_rel, float* __restrict__ hidden, int M, int R, int H,
+                        const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ attn,
+                        float* __restrict__ feat_video) {
+  pdl_wait();
+  __shared__ float ssh[kMaxScales];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int m = blockIdx.x;
+  for (int r = warp; r < R; r += nwarp) {
+    float* hr = hidden + ((size_t)m * R + r) * H;
+    float s = 0.f;
+    for (int h = lane; h < H; h += 32) {
+      const float t = tanhf(hr[h]);
+      hr[h] = t;
+      s = fmaf(t, __ldg(w2 + h), s);
+    }
+    s = warp_sum(s) + __ldg(b2);
+    if (lane == 0) ssh[r] = s;
+  }
+  __syncthreads();
+  float mx = ssh[0];
+  for (int r = 1; r < R; ++r) mx = fmaxf(mx, ssh[r]);
+  float den = 0.f;
+  for (int r = 0; r < R; ++r) den += expf(ssh[r] - mx);
+  const float inv = 1.0f / den;
+  if ((int)threadIdx.x < R) attn[(size_t)m * R + threadIdx.x] = expf(ssh[threadIdx.x] - mx) * inv;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float y = feat_video[(size_t)m * H + h];
+    for (int r = 0; r < R; ++r) y = fmaf(expf(ssh[r] - mx) * inv, feat_rel[((size_t)m * R + r) * H + h], y);
+    feat_video[(size_t)m * H + h] = y;
+  }
+}
+
+// backward of the above up to the pre-activation of the first Linear (block per video, warp per relation):
+//   da_r = <G[m], feat_rel[m,r]> + g_attn[m,r];  ds_r = a_r (da_r - sum_q a_q da_q)
+//   d_pre[m,r,:] = ds_r * w2 * (1 - hidden[m,r,:]^2);  d_s[m,r] = ds_r
+__global__ void __launch_bounds__(kRelWarps * 32)
+general_attn_bwd_kernel(const float* __restrict__ feat_rel, const float* __restrict__ hidden,
+                        const float* __restrict__ attn, const float* __restrict__ G, const float* __restrict__ g_attn,
+                        int M, int R, int H, const float* __restrict__ w2, float* __restrict__ d_s,
+                        float* __restrict__ d_pre) {
+  pdl_wait();
+  __shared__ float da[kMaxScales];
+  __shared__ float ds[kMaxScales];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int m = blockIdx.x;
+  for (int r = warp; r < R; r += nwarp) {
+    const float* fr = feat_rel + ((size_t)m * R + r) * H;
+    const float* gr = G + (size_t)m * H;
+    float dot = 0.f;
+    for (int h = lane; h < H; h += 32) dot = fmaf(gr[h], fr[h], dot);
+    dot = warp_sum(dot);
+    if (g_attn) dot += g_attn[(size_t)m * R + r];
+    if (lane == 0) da[r] = dot;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < R) {
+    float mean = 0.f;
+    for (int q = 0; q < R; ++q) mean = fmaf(attn[(size_t)m * R + q], da[q], mean);
+    const float v = attn[(size_t)m * R + threadIdx.x] * (da[threadIdx.x] - mean);
+    ds[threadIdx.x] = v;
+    d_s[(size_t)m * R + threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = warp; r < R; r += nwarp) {
+    const float* hr = hidden + ((size_t)m * R + r) * H;
+    float* dp = d_pre + ((size_t)m * R + r) * H;
+    const float v = ds[r];
+    for (int h = lane; h < H; h += 32) {
+      const float t = hr[h];
+      dp[h] = v * __ldg(w2 + h) * (1.0f - t * t);
+    }
+  }
+}
+
 // ---- frame-level attention                                         models.py:368-377 ----------
 __global__ void __launch_bounds__(256) frame_attn_fwd_kernel(const float* __restrict__ feat,
                                                              const float* __restrict__ logits, int rows, int F,

@@ -655,6 +655,10 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
                      ta3n_stream_t stream) {
   TA3N_REQUIRE(M >= 0 && R >= 1 && R <= kMaxScales && H > 0, "bad sizes");
   TA3N_REQUIRE(dW1_host && db1_host && dW2_host && db2_host, "null gradient tables");
+  // use_attn: 0 = plain sum, 1 = TransAttn (weights derived from pred_rel; their gradient flows into the logits),
+  //           2 = the weights in `attn` come from elsewhere ('general' attention): only the (w + 1) scaling of G here,
+  //               the weights' own gradient is ta3n_general_attn_bwd's business (g_attn is ignored)
+  TA3N_REQUIRE(use_attn >= 0 && use_attn <= 2, "use_attn must be 0, 1 or 2");
   cudaStream_t st = S(stream);
   if (M == 0) {
     for (int i = 0; i < R; ++i) {
@@ -678,7 +682,7 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
   for (int i = 0; i < R; ++i) w2.p[i] = W2_host[i];
   pre_launch("relattn_bwd_pre", st);
   launch_kernel(relattn_bwd_pre_kernel, M, 32 * (R < kRelWarps ? R : kRelWarps), 0, st, 
-      feat_rel, hidden, pred_rel, g_feat_video, g_pred_rel, g_attn, M, R, H, w2, use_attn, Pt, dHid);
+      feat_rel, hidden, pred_rel, g_feat_video, g_pred_rel, g_attn, M, R, H, w2, use_attn == 1 ? 1 : 0, Pt, dHid);
   TA3N_TRY(after_launch());
 
   {  // weight gradients of both layers of every relation discriminator
@@ -729,6 +733,93 @@ int ta3n_relattn_bwd(const float* feat_rel, int M, int R, int H, const float* co
     pre_launch("attn_placeholder_bwd", st);
     launch_kernel(attn_placeholder_bwd_kernel, blocks_for((size_t)M * R, 256), 256, 0, st, g_attn, d_feat_rel, M, R, H);
     TA3N_TRY(after_launch());
+  }
+  return TA3N_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 'general' attention over the relation features          models.py:320-325, 359-366, 379-388, 651
+// ------------------------------------------------------------------------------------------------
+int ta3n_general_attn_fwd(const float* feat_rel, int M, int R, int H, const float* W1, const float* b1,
+                          const float* w2, const float* b2, float* hidden, float* attn, float* feat_video,
+                          ta3n_stream_t stream) {
+  TA3N_REQUIRE(M >= 0 && R >= 1 && R <= kMaxScales && H > 0, "bad sizes");
+  if (M == 0) return TA3N_OK;
+  TA3N_REQUIRE(feat_rel && W1 && b1 && w2 && b2 && hidden && attn && feat_video, "null pointer");
+  {  // hidden [M*R, H] = feat_rel W1^T + b1   (tanh is applied by the row kernel)
+    GemmPlan plan;
+    plan.label = "general_attn_fwd";
+    plan.precise = true;
+    Group& g = plan.add_group(M * R, H, hidden, H);
+    g.flags = EPI_BIAS;
+    g.bias = b1;
+    plan.add_seg(feat_rel, H, W1, H, H);
+    TA3N_TRY(run_gemm(plan, S(stream)));
+  }
+  pre_launch("general_attn_rows", S(stream));
+  launch_kernel(general_attn_fwd_kernel, M, 32 * (R < kRelWarps ? R : kRelWarps), 0, S(stream), feat_rel, hidden, M, R,
+                H, w2, b2, attn, feat_video);
+  return after_launch();
+}
+
+size_t ta3n_general_attn_bwd_workspace_bytes(int M, int R, int H) {
+  return Arena::round((size_t)M * R * H * sizeof(float)) + Arena::round((size_t)M * R * sizeof(float)) +
+         splitk_bytes(1) + colsum_bytes((size_t)2 * H + 1);
+}
+
+int ta3n_general_attn_bwd(const float* feat_rel, int M, int R, int H, const float* W1, const float* w2,
+                          const float* hidden, const float* attn, const float* g_feat_video, const float* g_attn,
+                          float* d_feat_rel, float* dW1, float* db1, float* dw2, float* db2, void* workspace,
+                          size_t workspace_bytes, ta3n_stream_t stream) {
+  TA3N_REQUIRE(M >= 0 && R >= 1 && R <= kMaxScales && H > 0, "bad sizes");
+  TA3N_REQUIRE(dW1 && db1 && dw2 && db2, "null gradient pointer");
+  cudaStream_t st = S(stream);
+  if (M == 0) {
+    TA3N_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * H * H, st));
+    TA3N_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * H, st));
+    TA3N_CUDA(cudaMemsetAsync(dw2, 0, sizeof(float) * H, st));
+    TA3N_CUDA(cudaMemsetAsync(db2, 0, sizeof(float), st));
+    return TA3N_OK;
+  }
+  TA3N_REQUIRE(feat_rel && W1 && w2 && hidden && attn && g_feat_video && d_feat_rel, "null pointer");
+  Arena arena(workspace, workspace_bytes);
+  float* d_pre = arena.floats((size_t)M * R * H);
+  float* d_s = arena.floats((size_t)M * R);
+  if (!d_pre || !d_s)
+    return fail(TA3N_ERR_WORKSPACE, "ta3n_general_attn_bwd: workspace too small (%zu bytes)", workspace_bytes);
+  pre_launch("general_attn_bwd_rows", st);
+  launch_kernel(general_attn_bwd_kernel, M, 32 * (R < kRelWarps ? R : kRelWarps), 0, st, feat_rel, hidden, attn,
+                g_feat_video, g_attn, M, R, H, w2, d_s, d_pre);
+  TA3N_TRY(after_launch());
+  {  // dW1 [H,H] = d_pre^T feat_rel
+    GemmPlan plan;
+    plan.label = "general_attn_wgrad";
+    plan.a_kmaj = false;
+    plan.b_kmaj = false;
+    plan.add_group(H, H, dW1, H);
+    plan.add_seg(d_pre, H, feat_rel, H, M * R);
+    TA3N_TRY(submit_wgrad(plan, st, &arena));
+  }
+  {  // dw2 [1,H] = d_s^T hidden, db2 = sum d_s, db1 = column sums of d_pre
+    ColsumPlan cs;
+    cs.add_weighted(dw2, H, 1, H, H, 1);
+    cs.seg(hidden, M * R, d_s);
+    cs.add(db2, 1, 1);
+    cs.seg(d_s, M * R);
+    cs.add(db1, H, H);
+    cs.seg(d_pre, M * R);
+    TA3N_TRY(submit_colsum(cs, st, &arena));
+  }
+  {  // d_feat_rel += d_pre W1
+    GemmPlan plan;
+    plan.label = "general_attn_dgrad";
+    plan.precise_dgrad = true;
+    plan.a_kmaj = true;
+    plan.b_kmaj = false;
+    Group& g = plan.add_group(M * R, H, d_feat_rel, H);
+    g.flags = EPI_ACCUM;
+    plan.add_seg(d_pre, H, W1, H, H);
+    TA3N_TRY(run_gemm(plan, st));
   }
   return TA3N_OK;
 }

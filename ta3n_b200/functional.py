@@ -182,6 +182,7 @@ class PathSpec:
     mu: float = 0.0
     reverse: bool = False
     use_attn: bool = True                     # 'TransAttn' vs 'none'
+    general_attn: bool = False                # use_attn='general': attn_layer weights over the relation features
     use_attn_frame: bool = False
     drop_i: DropSpec = field(default_factory=DropSpec)
     drop_v: DropSpec = field(default_factory=DropSpec)
@@ -190,6 +191,15 @@ class PathSpec:
 # parameter order expected by _VideoPathFunction (R = T-1):
 #   shared W,b | frame-disc W1,b1,W2,b2 | TRN W_0..W_{R-1} | TRN b_0..b_{R-1} |
 #   rel-disc W1_i | b1_i | W2_i | b2_i (each R long) | classifier W,b | video-disc W1,b1,W2,b2
+#   [ | attn_layer W1,b1,w2,b2  -- only with PathSpec.general_attn ]
+def _attn_layer_params(params, R):
+    """The four trailing tensors of the 'general' attention layer (models.py:320-325)."""
+    n = 6 + 6 * R + 6
+    if len(params) != n + 4:
+        raise _lib.Ta3nError(f"general attention expects {n + 4} parameter tensors, got {len(params)}")
+    return params[n:n + 4]
+
+
 def _split_params(params, R):
     it = iter(params)
     take = lambda n: [next(it) for _ in range(n)]   # noqa: E731
@@ -273,8 +283,15 @@ def path_forward(spec: PathSpec, xs, xt, params, bufs: Buffers, batch_gemms: boo
     attn, feat_video = new("attn", M, R), new("feat_video", M, H)
     check(lib.ta3n_relattn_fwd(_p(feat_rel), M, R, H, ptr_array([_p(w) for w in r_w1]),
                                ptr_array([_p(b) for b in r_b1]), ptr_array([_p(w) for w in r_w2]),
-                               ptr_array([_p(b) for b in r_b2]), int(spec.use_attn), _p(hid_r), _p(pred_rel),
-                               _p(attn), _p(feat_video), st))
+                               ptr_array([_p(b) for b in r_b2]), int(spec.use_attn and not spec.general_attn),
+                               _p(hid_r), _p(pred_rel), _p(attn), _p(feat_video), st))
+    # 4b. 'general' attention (models.py:359-366, 379-388): the plain sum above + sum_r softmax_r(MLP(feat_rel)) feat_rel
+    hid_a = None
+    if spec.general_attn:
+        wa1, ba1, wa2, ba2 = _attn_layer_params(params, R)
+        hid_a = new("hid_a", M * R, H)
+        check(lib.ta3n_general_attn_fwd(_p(feat_rel), M, R, H, _p(wa1), _p(ba1), _p(wa2), _p(ba2), _p(hid_a), _p(attn),
+                                        _p(feat_video), st))
     # 5. video head  (models.py:679-687)
     dropped, pred_video = new("dropped", M, H), new("pred_video", M, Cn)
     check(lib.ta3n_video_head_fwd(_p(feat_video), M, H, Cn, _p(w_c), _p(b_c), _dref(d_v), _p(dropped),
@@ -286,6 +303,8 @@ def path_forward(spec: PathSpec, xs, xt, params, bufs: Buffers, batch_gemms: boo
 
     saved = dict(feat=feat, hid_f=hid_f, pred_frame=pred_frame, feat_in=feat_in, act=act, feat_rel=feat_rel,
                  hid_r=hid_r, pred_rel=pred_rel, attn=attn, dropped=dropped, hid_v=hid_v)
+    if hid_a is not None:
+        saved["hid_a"] = hid_a
     outputs = (feat.view(M, T, F), pred_frame.view(M, T, 2), attn, pred_rel, feat_video, pred_video,
                pred_dom_video, dropped)
     return saved, outputs, (Bs, Bt, D, T, F, H, Cn)
@@ -360,11 +379,20 @@ def path_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: 
     d_feat_rel = new("d_feat_rel", M, R, H)
     ws = wsp("relattn", lib.ta3n_relattn_bwd_workspace_bytes(M, R, H))
     check(lib.ta3n_relattn_bwd(_p(feat_rel), M, R, H, ptr_array([_p(w) for w in r_w1]),
-                               ptr_array([_p(w) for w in r_w2]), int(spec.use_attn), _p(hid_r), _p(pred_rel),
+                               ptr_array([_p(w) for w in r_w2]), 2 if spec.general_attn else int(spec.use_attn),
+                               _p(hid_r), _p(pred_rel),
                                _p(attn), _p(G), _p(g("pred_rel")), _p(g("attn")), float(spec.beta[0]),
                                _p(d_feat_rel), ptr_array([_p(t) for t in dr_w1]),
                                ptr_array([_p(t) for t in dr_b1]), ptr_array([_p(t) for t in dr_w2]),
                                ptr_array([_p(t) for t in dr_b2]), _p(ws), ws.numel(), st))
+    if spec.general_attn:
+        # 4b'. the attention weights' own gradient: through softmax and the tanh MLP back into feat_rel
+        wa1, _, wa2, _ = _attn_layer_params(params, R)
+        dwa1, dba1, dwa2, dba2 = _attn_layer_params(gout, R)
+        ws = wsp("general_attn", lib.ta3n_general_attn_bwd_workspace_bytes(M, R, H))
+        check(lib.ta3n_general_attn_bwd(_p(feat_rel), M, R, H, _p(wa1), _p(wa2), _p(saved["hid_a"]), _p(attn), _p(G),
+                                        _p(g("attn")), _p(d_feat_rel), _p(dwa1), _p(dba1), _p(dwa2), _p(dba2),
+                                        _p(ws), ws.numel(), st))
     stage_done("relation")
     # 3'. TRN
     if frame_done is not None:

@@ -63,8 +63,8 @@ class VideoModel(nn.Module):
             _unsupported('ens_DA', ens_DA, ['none', 'MCD'])
         if share_params != 'Y':
             _unsupported('share_params', share_params, ['Y'])
-        if use_attn not in ('TransAttn', 'none'):
-            _unsupported('use_attn', use_attn, ['TransAttn', 'none'])
+        if use_attn not in ('TransAttn', 'general', 'none'):
+            _unsupported('use_attn', use_attn, ['TransAttn', 'general', 'none'])
         if use_attn_frame not in ('none', 'TransAttn'):
             _unsupported('use_attn_frame', use_attn_frame, ['none', 'TransAttn'])
         if use_attn_frame != 'none' and use_attn != 'TransAttn':
@@ -149,6 +149,9 @@ class VideoModel(nn.Module):
             for _ in range(self.train_segments - 1))
 
         self.alpha = torch.ones(1)                                                       # :314
+        if self.use_attn == 'general':                                                   # :320-325, PyTorch default init
+            self.attn_layer = nn.Sequential(nn.Linear(feat_aggregated_dim, feat_aggregated_dim), nn.Tanh(),
+                                            nn.Linear(feat_aggregated_dim, 1))
 
     def partialBN(self, enable):
         self._enable_pbn = enable
@@ -160,6 +163,12 @@ class VideoModel(nn.Module):
         return super().train(mode)
 
     # ---- helpers kept for API parity ---------------------------------------------------------------
+    def get_general_attn(self, feat):
+        """softmax over the segments of attn_layer(feat) (models.py:359-366); torch ops, utility only."""
+        n = feat.size(1)
+        w = self.attn_layer(feat.reshape(-1, feat.size(-1))).view(-1, n, 1)
+        return torch.softmax(w, dim=1)
+
     def get_trans_attn(self, pred_domain):
         """w = 1 - H(softmax(pred_domain))  (models.py:351-357); torch ops, utility only."""
         q = torch.softmax(pred_domain, dim=1)
@@ -170,6 +179,12 @@ class VideoModel(nn.Module):
         R = self.train_segments - 1
         trn_w, trn_b = self.TRN.relation_weights()
         rel = self.relation_domain_classifier_all
+        extra = []
+        if self.use_attn == 'general':
+            extra = [self.attn_layer[0].weight, self.attn_layer[0].bias, self.attn_layer[2].weight, self.attn_layer[2].bias]
+        return self._core_parameters(R, trn_w, trn_b, rel) + extra
+
+    def _core_parameters(self, R, trn_w, trn_b, rel):
         return [self.fc_feature_shared_source.weight, self.fc_feature_shared_source.bias,
                 self.fc_feature_domain.weight, self.fc_feature_domain.bias,
                 self.fc_classifier_domain.weight, self.fc_classifier_domain.bias,
@@ -214,7 +229,7 @@ class VideoModel(nn.Module):
         drop_i, drop_v = self._drop_specs(dev)
         spec = TF.PathSpec(num_segments=num_segments, beta=(float(beta[0]), float(beta[1]), float(beta[2])),
                            mu=float(mu), reverse=bool(reverse), use_attn=self.use_attn != 'none',
-                           use_attn_frame=self.use_attn_frame != 'none', drop_i=drop_i, drop_v=drop_v)
+                           general_attn=self.use_attn == 'general', use_attn_frame=self.use_attn_frame != 'none', drop_i=drop_i, drop_v=drop_v)
         feat_fc, pred_frame, attn, pred_rel, feat_video, pred_video, pred_dom_video, dropped = TF.video_path(
             spec, xs, xt, self.path_parameters())
         pred_video_2 = pred_video                                                     # :713-714 out_2 = out

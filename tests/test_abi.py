@@ -62,6 +62,16 @@ def test_argument_validation_needs_no_gpu(lib):
     assert b"16-byte aligned" in lib.ta3n_last_error()
     assert lib.ta3n_sgd_nesterov_step(16, 32, 48, 10, 64, -0.1, 1e-4, 0.0, None, 0, None, None) == 1
     assert lib.ta3n_sgd_workspace_bytes() >= 296 * 4
+    # general attention: bad sizes / null pointers, and an empty batch is a no-op
+    assert lib.ta3n_general_attn_fwd(None, 4, 0, 256, None, None, None, None, None, None, None, None) == 1
+    assert lib.ta3n_general_attn_fwd(None, 4, 4, 256, None, None, None, None, None, None, None, None) == 1
+    assert b"ta3n_general_attn_fwd" in lib.ta3n_last_error()
+    assert lib.ta3n_general_attn_fwd(None, 0, 4, 256, None, None, None, None, None, None, None, None) == 0
+    assert lib.ta3n_general_attn_bwd(None, 4, 4, 256, None, None, None, None, None, None, None, None, None, None, None,
+                                     None, 0, None) == 1
+    assert lib.ta3n_general_attn_bwd_workspace_bytes(256, 4, 256) >= 256 * 4 * 256 * 4
+    assert lib.ta3n_relattn_bwd(None, 4, 4, 256, None, None, 3, None, None, None, None, None, None, 0.5, None, None,
+                                None, None, None, None, 0, None) == 1
     # loss heads: a class count / batch of zero is rejected before anything is launched
     assert lib.ta3n_loss_fwd_bwd(None, None, None, None, None, 0, 0, 5, 4, 12, 0.003, 15, None, None, None, None,
                                  None, None, None, 0, None) == 1
@@ -86,13 +96,33 @@ def test_no_cpu_fallback_in_product_package():
 def test_unsupported_options_raise():
     from ta3n_b200.models import VideoModel
     for kw in (dict(frame_aggregation="avgpool"), dict(use_bn="AdaBN"), dict(ens_DA="AutoDIAL"),
-               dict(share_params="N"), dict(use_attn="general"), dict(baseline_type="tsn")):
+               dict(share_params="N"), dict(use_attn="general", use_attn_frame="TransAttn"), dict(baseline_type="tsn")):
         args = dict(num_class=5, baseline_type="video", frame_aggregation="trn-m", modality="RGB", verbose=False)
         args.update(kw)
         with pytest.raises(NotImplementedError):
             VideoModel(**args)
     with pytest.raises(ValueError):
         VideoModel(5, "video", "trn-m", "RGB", add_fc=0, verbose=False)
+
+
+def test_general_attention_model_has_the_reference_parameters():
+    """use_attn='general' (models.py:320-325): attn_layer = Linear(H,H), Tanh, Linear(H,1), appended to the operator's
+    parameter list; TrainStep (the captured step of the shipped configuration) refuses the variant."""
+    import torch
+
+    from ta3n_b200.models import VideoModel
+    from ta3n_b200.train import TrainStep
+    m = VideoModel(5, "video", "trn-m", "RGB", train_segments=5, val_segments=5, fc_dim=64, use_attn="general",
+                   verbose=False)
+    sd = m.state_dict()
+    assert sd["attn_layer.0.weight"].shape == (256, 256) and sd["attn_layer.2.weight"].shape == (1, 256)
+    assert sd["attn_layer.0.bias"].shape == (256,) and sd["attn_layer.2.bias"].shape == (1,)
+    pp = m.path_parameters()
+    assert len(pp) == 6 + 6 * 4 + 6 + 4 and pp[-4] is m.attn_layer[0].weight and pp[-1] is m.attn_layer[2].bias
+    w = m.get_general_attn(torch.randn(3, 4, 256))
+    assert w.shape == (3, 4, 1) and torch.allclose(w.sum(1), torch.ones(3, 1))
+    with pytest.raises(NotImplementedError):
+        TrainStep(m, 4, 4, beta=[0.75, 0.75, 0.5])
 
 
 def test_relation_table_matches_survey_appendix_a():

@@ -143,6 +143,66 @@ def test_model_matches_oracle_mid_size(T, attn_frame, bs, bt, engine):
         assert_close(grads[name], go, GRAD_TOL[engine], f"grad {name}", noise=n_grad[name] * NOISE_SCALE[engine])
 
 
+@pytest.mark.parametrize("T,bs,bt,drop", [(5, 21, 13, 0.0), (7, 9, 12, 0.5), (2, 3, 2, 0.0)])
+def test_general_attention_variant_matches_oracle(T, bs, bt, drop, engine):
+    """SURVEY 8f n4, use_attn='general' (models.py:320-325 attn_layer, :359-366 softmax over the relations, :379-388
+    re-weighting by attn + 1): outputs and every gradient -- including attn_layer's own and the part of the trunk
+    gradient that flows through the attention weights -- against the fp64 oracle, with trained-like weights and a loss
+    that also reads the returned attention weights (exercises g_attn).  The oracle's branch is pinned to the live
+    reference in tests/test_oracle_vs_reference.py and by the 'general_attn' golden case."""
+    cfg = orc.PathConfig(num_class=9, num_segments=T, fc_dim=512, dropout_i=drop, dropout_v=drop, use_attn="general")
+    params = orc.init_params(cfg, seed=23)
+    g = torch.Generator().manual_seed(24)
+    for k in params:
+        if params[k].dtype.is_floating_point and k.startswith(orc.USED_PARAM_PREFIXES) and "weight" in k:
+            params[k] = params[k] + 0.02 * torch.randn(params[k].shape, generator=g)
+    xs = torch.randn(bs, T, orc.FEATURE_DIM, generator=g)
+    xt = torch.randn(bt, T, orc.FEATURE_DIM, generator=g) + 0.3
+    labels = torch.randint(0, 9, (bs,), generator=g)
+    keep = lambda *s: (torch.rand(*s, generator=g) < 0.5).to(torch.uint8)   # noqa: E731
+    masks = None if drop == 0 else {"i_source": keep(bs * T, 512), "i_target": keep(bt * T, 512),
+                                    "v_source": keep(bs, 256), "v_target": keep(bt, 256)}
+    beta = [0.75, 0.6, 0.5]
+
+    def loss_of(outs, lab, compose):
+        return compose(outs, lab) + 0.5 * (outs[0] ** 2).sum() + 0.25 * (outs[5] ** 2).sum()
+
+    def oracle(dtype):
+        p = {k: (v.to(dtype).requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in params.items()}
+        o = orc.forward(p, xs.to(dtype), xt.to(dtype), beta, 0.0, cfg, train=True, reverse=False, masks=masks)
+        loss = loss_of(o, labels, lambda oo, ll: orc.compose_loss(oo, ll, 0.003, use_attn="general"))
+        loss.backward()
+        return loss.detach(), o, {k: v.grad for k, v in p.items() if v.dtype.is_floating_point and v.grad is not None}
+
+    l64, o64, g64 = oracle(torch.float64)
+    l32, o32, g32 = oracle(torch.float32)
+    from ta3n_b200.loss import ta3n_loss
+    model = build_model(cfg, params, train=True)
+    model.dropout_masks = cat_masks(masks)
+    outs = model(xs.to(_dev()), xt.to(_dev()), beta, 0.0, is_train=True, reverse=False)
+    loss = loss_of(outs, labels.to(_dev()), lambda oo, ll: ta3n_loss(oo, ll, 0.003, use_attn="general"))
+    loss.backward()
+    torch.cuda.synchronize()
+    tol = TOL[engine]
+    assert_close(loss.detach().cpu(), l64, tol, "loss", noise=abs(l32.item() - l64.item()))
+    for i, (a, b, c32) in enumerate(zip(flat_outputs(outs), flat_outputs(o64), flat_outputs(o32))):
+        assert a.shape == b.shape
+        assert_close(a.detach().cpu(), b.detach(), tol, f"output {i}", noise=abs_err(c32.detach(), b.detach()))
+    if T > 2:
+        assert float(outs[0].detach().std()) > 1e-3, "the attention weights should not be uniform in this test"
+    else:                                           # one relation: softmax over a single logit
+        assert torch.equal(outs[0].detach().cpu(), torch.ones(bs, 1))
+    named = dict(model.named_parameters())
+    assert "attn_layer.0.weight" in g64
+    for name, go in g64.items():
+        assert named[name].grad is not None, name
+        if name == "attn_layer.2.bias":             # zero by construction (softmax shift invariance)
+            assert float(named[name].grad.norm()) <= 1e-5 * max(1.0, float(named["attn_layer.2.weight"].grad.norm()))
+            continue
+        assert_close(named[name].grad, go, GRAD_TOL[engine], f"grad {name}",
+                     noise=abs_err(g32[name], go) * NOISE_SCALE[engine])
+
+
 @pytest.mark.parametrize("T,attn_frame,bs,bt", [(5, "none", 48, 40), (6, "TransAttn", 12, 20)])
 def test_tf32_gradients_match_oracle_on_realised_activation_pattern(T, attn_frame, bs, bt):
     """tf32 engine: with the ReLU on/off pattern of the CUDA forward pinned in the fp64 oracle, the loss

@@ -6,12 +6,12 @@ import torch
 
 from oracle import gen_golden, ref_shims
 from oracle import ta3n_oracle as orc
-from tests.golden_util import TOL_FP32, assert_close
+from tests.golden_util import STRUCTURAL_ZERO_GRADS, TOL_FP32, assert_close
 
 pytestmark = pytest.mark.skipif(not ref_shims.available(), reason="/root/reference not present")
 
 
-@pytest.mark.parametrize("case", ["cfg1_train_masked", "t9_attnframe", "noattn_f256"])
+@pytest.mark.parametrize("case", ["cfg1_train_masked", "t9_attnframe", "noattn_f256", "general_attn"])
 def test_oracle_equals_live_reference(case):
     c = gen_golden.CASES[case]
     model, outs_ref, loss_ref, _ = gen_golden.run_reference(c)
@@ -28,6 +28,8 @@ def test_oracle_equals_live_reference(case):
     for name, prm in model.named_parameters():
         if prm.grad is None:
             assert name not in grads
+        elif name in STRUCTURAL_ZERO_GRADS:
+            assert float(prm.grad.norm()) < 1e-6 and float(grads[name].norm()) < 1e-6
         else:
             assert_close(grads[name], prm.grad, 2e-4, f"grad {name}")
 
@@ -143,3 +145,50 @@ def test_oracle_mcd_variant_equals_live_reference(reverse, mu):
     for name, prm in m.named_parameters():
         if prm.grad is not None:
             assert_close(params[name].grad, prm.grad, 2e-4, f"MCD grad {name}")
+
+
+def test_oracle_general_attention_equals_live_reference():
+    """use_attn='general' (models.py:320-325 attn_layer, :359-366 softmax over the relations, :379-388 re-weighting) with
+    trained-like weights and a loss that also reads the attention weights themselves: outputs and every gradient."""
+    ref_models, _, _ = ref_shims.load()
+    torch.manual_seed(21)
+    m = ref_models.VideoModel(9, "video", "trn-m", "RGB", train_segments=5, val_segments=5, add_fc=1, fc_dim=512,
+                              dropout_i=0.0, dropout_v=0.0, partial_bn=False, use_bn="none", ens_DA="none",
+                              use_attn="general", share_params="Y", verbose=False)
+    m.train()
+    cfg = orc.PathConfig(num_class=9, num_segments=5, fc_dim=512, dropout_i=0.0, dropout_v=0.0, use_attn="general")
+    p_init = orc.init_params(cfg, seed=21)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(p_init.keys())
+    for k in sd:
+        assert torch.equal(sd[k], p_init[k]), k
+    g = torch.Generator().manual_seed(22)
+    with torch.no_grad():
+        for k, v in m.named_parameters():
+            if "weight" in k:
+                v.add_(0.02 * torch.randn(v.shape, generator=g))
+    xs, xt = torch.randn(6, 5, 2048, generator=g), torch.randn(4, 5, 2048, generator=g)
+    labels = torch.randint(0, 9, (6,), generator=g)
+    beta = [0.75, 0.6, 0.5]
+
+    def loss_of(outs):
+        return orc.compose_loss(outs, labels, 0.003, use_attn="general") + 0.5 * (outs[0] ** 2).sum() + \
+            0.25 * (outs[5] ** 2).sum()
+
+    outs = m(xs, xt, beta, 0, is_train=True, reverse=False)
+    loss_ref = loss_of(outs)
+    loss_ref.backward()
+    params = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in m.state_dict().items()}
+    o = orc.forward(params, xs, xt, beta, 0, cfg, train=True, reverse=False)
+    loss = loss_of(o)
+    loss.backward()
+    assert_close(loss.detach(), loss_ref.detach(), TOL_FP32, "loss")
+    for i in (0, 1, 5, 6):
+        assert_close(o[i].detach(), outs[i].detach(), TOL_FP32, f"output {i}")
+    assert float(outs[0].detach().std()) > 1e-3, "attention weights should not be uniform in this test"
+    for name, prm in m.named_parameters():
+        if name in STRUCTURAL_ZERO_GRADS:
+            assert float(prm.grad.norm()) < 1e-6 and float(params[name].grad.norm()) < 1e-6
+        elif prm.grad is not None:
+            assert_close(params[name].grad, prm.grad, 2e-4, f"grad {name}")
+    assert m.attn_layer[0].weight.grad is not None and float(m.attn_layer[0].weight.grad.norm()) > 0
