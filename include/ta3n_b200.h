@@ -137,6 +137,11 @@ int ta3n_frame_attn_fwd(const float* feat, const float* logits, int rows, int F,
 int ta3n_frame_attn_bwd(const float* feat, const float* logits, int rows, int F, float* d_out,
                         float* g_logits, ta3n_stream_t stream);
 
+/* ---- average over the segments (frame_aggregation='avgpool', models.py:425-433) ---- */
+/* x [M,T,F] -> out [M,F] = sum_t x / T (nn.AvgPool2d([T, 1]));  backward: g [M,F] -> dx [M,T,F] = g / T        */
+int ta3n_segment_mean_fwd(const float* x, int M, int T, int F, float* out, ta3n_stream_t stream);
+int ta3n_segment_mean_bwd(const float* g, int M, int T, int F, float* dx, ta3n_stream_t stream);
+
 /* ---- multi-scale temporal relation module (TRNmodule.py:58-82) --------------------- */
 /* x [M, T, F];  W_host[i] -> device [H, scale_size[i]*F];  b_host[i] -> device [H]
  * act [n_rel_total, M, H] : relu'd relation activations (saved for backward)

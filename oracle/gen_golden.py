@@ -39,6 +39,11 @@ CASES = {
     "noattn_f256": dict(bs=5, bt=5, T=5, C=12, F=256, train=False, use_attn="none", attn_frame="none"),
     "t3_f2048": dict(bs=2, bt=2, T=3, C=6, F=2048, train=True, use_attn="TransAttn", attn_frame="none"),
     "general_attn": dict(bs=7, bt=5, T=5, C=12, F=512, train=True, use_attn="general", attn_frame="none"),
+    # frame_aggregation='avgpool' (key "agg"; default 'trn-m'): the paper's baseline aggregation, with / without attention
+    "avgpool_transattn": dict(bs=6, bt=5, T=5, C=12, F=512, train=True, use_attn="TransAttn", attn_frame="none",
+                              agg="avgpool"),
+    "avgpool_noattn_f256": dict(bs=4, bt=7, T=3, C=7, F=256, train=False, use_attn="none", attn_frame="none",
+                                agg="avgpool"),
 }
 BETA = (0.75, 0.75, 0.5)
 GAMMA = 0.003
@@ -50,7 +55,8 @@ DROPOUT = 0.5
 
 def case_config(c) -> orc.PathConfig:
     return orc.PathConfig(num_class=c["C"], num_segments=c["T"], fc_dim=c["F"], dropout_i=DROPOUT,
-                          dropout_v=DROPOUT, use_attn=c["use_attn"], use_attn_frame=c["attn_frame"])
+                          dropout_v=DROPOUT, use_attn=c["use_attn"], use_attn_frame=c["attn_frame"],
+                          frame_aggregation=c.get("agg", "trn-m"))
 
 
 def case_inputs(c):
@@ -67,8 +73,8 @@ def case_inputs(c):
         masks = {
             "i_source": (torch.rand(c["bs"] * c["T"], cfg.shared_dim, generator=gm) < keep).to(torch.uint8),
             "i_target": (torch.rand(c["bt"] * c["T"], cfg.shared_dim, generator=gm) < keep).to(torch.uint8),
-            "v_source": (torch.rand(c["bs"], orc.NUM_BOTTLENECK, generator=gm) < keep).to(torch.uint8),
-            "v_target": (torch.rand(c["bt"], orc.NUM_BOTTLENECK, generator=gm) < keep).to(torch.uint8),
+            "v_source": (torch.rand(c["bs"], cfg.video_dim, generator=gm) < keep).to(torch.uint8),
+            "v_target": (torch.rand(c["bt"], cfg.video_dim, generator=gm) < keep).to(torch.uint8),
         }
     return cfg, xs, xt, labels, masks
 
@@ -108,7 +114,7 @@ def run_reference(c, dtype=torch.float32):
     cfg, xs, xt, labels, masks = case_inputs(c)
     xs, xt = xs.to(dtype), xt.to(dtype)
     torch.manual_seed(MODEL_SEED)
-    model = ref_models.VideoModel(c["C"], "video", "trn-m", "RGB", train_segments=c["T"], val_segments=c["T"],
+    model = ref_models.VideoModel(c["C"], "video", c.get("agg", "trn-m"), "RGB", train_segments=c["T"], val_segments=c["T"],
                                   add_fc=1, fc_dim=c["F"], dropout_i=DROPOUT, dropout_v=DROPOUT,
                                   partial_bn=False, use_bn="none", ens_DA="none", use_attn=c["use_attn"],
                                   n_attn=1, use_attn_frame=c["attn_frame"], share_params="Y", verbose=False)

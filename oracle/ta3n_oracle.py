@@ -7,7 +7,8 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 What it is: a functional, eager-PyTorch (CPU, fp32 or fp64) restatement of the
 one code path of cmhungsteve/TA3N that this repo accelerates:
 
-    VideoModel.forward with frame_aggregation='trn-m', baseline_type='video',
+    VideoModel.forward with frame_aggregation='trn-m' (the hot path; 'avgpool', the paper's baseline aggregation,
+    as an off-path variant), baseline_type='video',
     add_fc=1, use_bn='none', ens_DA='none', share_params='Y',
     use_attn in {'TransAttn','general','none'}, use_attn_frame in {'none','TransAttn'}
 
@@ -57,6 +58,11 @@ class PathConfig:
     use_attn: str = "TransAttn"    # or 'general' / 'none'
     use_attn_frame: str = "none"   # or 'TransAttn'
     ens_DA: str = "none"           # or 'MCD': a second video-level classifier (models.py:276-279, 716-720)
+    frame_aggregation: str = "trn-m"   # or 'avgpool' (models.py:240-241, 425-433, 620-626): no relation level
+
+    @property
+    def video_dim(self) -> int:    # feat_aggregated_dim = feat_video_dim, models.py:240-250
+        return self.shared_dim if self.frame_aggregation == "avgpool" else NUM_BOTTLENECK
 
     @property
     def shared_dim(self) -> int:   # models.py:129
@@ -114,7 +120,8 @@ def init_params(cfg: PathConfig, seed: Optional[int] = None) -> "OrderedDict[str
     """
     if seed is not None:
         torch.manual_seed(seed)
-    Fd, H, C, T = cfg.shared_dim, NUM_BOTTLENECK, cfg.num_class, cfg.num_segments
+    Fd, H, C, T = cfg.shared_dim, cfg.video_dim, cfg.num_class, cfg.num_segments
+    trn = cfg.frame_aggregation == "trn-m"
     p: "OrderedDict[str, torch.Tensor]" = OrderedDict()
 
     def put(name, wb):
@@ -125,9 +132,9 @@ def init_params(cfg: PathConfig, seed: Optional[int] = None) -> "OrderedDict[str
     put("fc_feature_domain", _std_linear(Fd, Fd))
     put("fc_classifier_source", _std_linear(Fd, C))             # executed, output dropped
     put("fc_classifier_domain", _std_linear(Fd, 2))
-    for i, scale in enumerate(range(T, 1, -1)):
+    for i, scale in enumerate(range(T, 1, -1) if trn else ()):
         put(f"TRN.fc_fusion_scales.{i}.1", _default_linear(scale * Fd, H))
-    for dom in ("S", "T"):                                      # BatchNorm1d(256), unused here
+    for dom in ("S", "T") if trn else ():                       # BatchNorm1d(256), unused here
         p[f"bn_trn_{dom}.weight"] = torch.ones(H)
         p[f"bn_trn_{dom}.bias"] = torch.zeros(H)
         p[f"bn_trn_{dom}.running_mean"] = torch.zeros(H)
@@ -140,10 +147,11 @@ def init_params(cfg: PathConfig, seed: Optional[int] = None) -> "OrderedDict[str
     if cfg.ens_DA == "MCD":                                     # models.py:276-279
         put("fc_classifier_video_source_2", _std_linear(H, C))
     put("fc_classifier_domain_video", _std_linear(H, 2))
-    for i in range(T - 1):
+    for i in range(T - 1) if trn else ():                       # models.py:285-294: trn-m only
         put(f"relation_domain_classifier_all.{i}.0", _default_linear(H, H))
         put(f"relation_domain_classifier_all.{i}.2", _default_linear(H, 2))
     if cfg.use_attn == "general":                               # models.py:320-325: attn_layer, PyTorch default init
+        assert trn, "general attention is defined over the relation features"
         put("attn_layer.0", _default_linear(H, H))
         put("attn_layer.2", _default_linear(H, 1))
     return p
@@ -320,6 +328,9 @@ def _forward_domain(p: Dict[str, torch.Tensor], x: torch.Tensor, beta: Sequence[
     # fc_classifier_source (:617) is executed by the reference but its output is
     # dropped for baseline_type='video' (:437-441); it has no effect on any output.
 
+    if cfg.frame_aggregation == "avgpool":
+        return _forward_domain_avgpool(p, feat, feat_frames, pred_frame, beta, mu, cfg, train, reverse, mask_v, gates)
+
     rel = trn_multiscale(feat.view(batch, T, Fd),
                          [p[f"TRN.fc_fusion_scales.{i}.1.weight"] for i in range(R)],
                          [p[f"TRN.fc_fusion_scales.{i}.1.bias"] for i in range(R)],
@@ -361,6 +372,33 @@ def _forward_domain(p: Dict[str, torch.Tensor], x: torch.Tensor, beta: Sequence[
     feats = [pred_video, feat_video, feat_frames]                                      # reversed list, :722
     pred_video_2 = pred_video                                                          # :713 out_2 = out
     if cfg.ens_DA == "MCD":                                                            # :716-720 (share_params == 'Y')
+        pred_video_2 = F.linear(vid, p["fc_classifier_video_source_2.weight"], p["fc_classifier_video_source_2.bias"])
+    return attn, pred_video, pred_video_2, pred_domain, feats
+
+
+def _forward_domain_avgpool(p, feat, feat_frames, pred_frame, beta, mu, cfg: PathConfig, train: bool, reverse: bool,
+                            mask_v, gates):
+    """frame_aggregation='avgpool' behind the frame level (models.py:620-626, 425-433, 679-706): the frame features,
+    re-weighted by the frame-level domain attention under use_attn='TransAttn' (:427-430), are averaged over the segments
+    (:432); the video-level layers are shared_dim wide (:240-241, 250); there is no relation level -- the reference puts
+    the video-level domain prediction into that slot of pred_domain (:703-706) and the first feature of every video into
+    the attention output (:624-626)."""
+    batch, T, Fd = feat_frames.size(0), cfg.num_segments, cfg.shared_dim
+    if cfg.use_attn == "TransAttn":                                                     # :427-430
+        feat = (entropy_attention(pred_frame).view(-1, 1) + 1) * feat
+    feat_video = feat.view(batch, T, Fd).sum(1) / T                                     # :432 AvgPool2d([T, 1])
+    attn = feat_video[:, 0]                                                             # :625-626
+    vid = _apply_dropout(feat_video, cfg.dropout_v, train, mask_v)                      # :679
+    if reverse:                                                                         # :682-684
+        vid = grad_reverse(vid, mu)
+    pred_video = F.linear(vid, p["fc_classifier_video_source.weight"], p["fc_classifier_video_source.bias"])   # :686
+    pred_dom_video = two_layer_disc(vid, p["fc_feature_domain_video.weight"], p["fc_feature_domain_video.bias"],
+                                    p["fc_classifier_domain_video.weight"], p["fc_classifier_domain_video.bias"],
+                                    beta[1], gates.get("video_disc"))                   # :694
+    pred_domain = [pred_dom_video, pred_dom_video, pred_frame.view(batch, T, 2)]        # :705-706 dummy relation slot
+    feats = [pred_video, feat_video, feat_frames]
+    pred_video_2 = pred_video
+    if cfg.ens_DA == "MCD":
         pred_video_2 = F.linear(vid, p["fc_classifier_video_source_2.weight"], p["fc_classifier_video_source_2.bias"])
     return attn, pred_video, pred_video_2, pred_domain, feats
 

@@ -77,6 +77,8 @@ SIGNATURES = {
     "ta3n_grl_bwd": (_I, [_VP, _F, _VP, _SZ, _VP]),
     "ta3n_frame_attn_fwd": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
     "ta3n_frame_attn_bwd": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
+    "ta3n_segment_mean_fwd": (_I, [_VP, _I, _I, _I, _VP, _VP]),
+    "ta3n_segment_mean_bwd": (_I, [_VP, _I, _I, _I, _VP, _VP]),
     "ta3n_trn_fwd": (_I, [_VP, _I, _I, _I, _TAB, _PP, _PP, _I, _VP, _VP, _VP]),
     "ta3n_trn_bwd_workspace_bytes": (_SZ, [_I, _I, _I, _TAB]),
     "ta3n_trn_bwd": (_I, [_VP, _I, _I, _I, _TAB, _PP, _I, _VP, _VP, _PP, _PP, _VP, _I, _VP, _SZ, _VP]),

@@ -462,6 +462,32 @@ general_attn_bwd_kernel(const float* __restrict__ feat_rel, const float* __restr
   }
 }
 
+// ---- average over the segments (frame_aggregation='avgpool')        models.py:425-433 (AvgPool2d([T, 1])) ----
+// out[m, f] = (sum_t x[m, t, f]) / T ; consecutive threads take consecutive f: coalesced, each x element read once.
+__global__ void __launch_bounds__(256) segment_mean_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                               int M, int T, int F) {
+  pdl_wait();
+  const size_t total = (size_t)M * F;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = e / F, f = e % F;
+    const float* p = x + m * T * F + f;
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += p[(size_t)t * F];
+    out[e] = s / (float)T;
+  }
+}
+// dx[m, t, f] = g[m, f] / T
+__global__ void __launch_bounds__(256) segment_mean_bwd_kernel(const float* __restrict__ g, float* __restrict__ dx,
+                                                               int M, int T, int F) {
+  pdl_wait();
+  const size_t total = (size_t)M * T * F;
+  const size_t tf = (size_t)T * F;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = e / tf, f = e % F;
+    dx[e] = g[m * F + f] / (float)T;
+  }
+}
+
 // ---- frame-level attention                                         models.py:368-377 ----------
 __global__ void __launch_bounds__(256) frame_attn_fwd_kernel(const float* __restrict__ feat,
                                                              const float* __restrict__ logits, int rows, int F,

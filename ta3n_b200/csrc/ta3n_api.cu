@@ -464,6 +464,27 @@ int ta3n_frame_attn_bwd(const float* feat, const float* logits, int rows, int F,
 }
 
 // ------------------------------------------------------------------------------------------------
+// average over the segments (frame_aggregation='avgpool')                   models.py:425-433
+// ------------------------------------------------------------------------------------------------
+int ta3n_segment_mean_fwd(const float* x, int M, int T, int F, float* out, ta3n_stream_t stream) {
+  TA3N_REQUIRE(M >= 0 && T > 0 && F > 0, "bad sizes");
+  if (M == 0) return TA3N_OK;
+  TA3N_REQUIRE(x && out, "null pointer");
+  pre_launch("segment_mean_fwd", S(stream));
+  launch_kernel(segment_mean_fwd_kernel, blocks_for((size_t)M * F, 256), 256, 0, S(stream), x, out, M, T, F);
+  return after_launch();
+}
+
+int ta3n_segment_mean_bwd(const float* g, int M, int T, int F, float* dx, ta3n_stream_t stream) {
+  TA3N_REQUIRE(M >= 0 && T > 0 && F > 0, "bad sizes");
+  if (M == 0) return TA3N_OK;
+  TA3N_REQUIRE(g && dx, "null pointer");
+  pre_launch("segment_mean_bwd", S(stream));
+  launch_kernel(segment_mean_bwd_kernel, blocks_for((size_t)M * T * F, 256), 256, 0, S(stream), g, dx, M, T, F);
+  return after_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
 // multi-scale temporal relation module                                   TRNmodule.py:58-82
 // ------------------------------------------------------------------------------------------------
 int ta3n_trn_fwd(const float* x, int M, int F, int H, const ta3n_relation_table* tab,

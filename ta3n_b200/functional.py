@@ -468,6 +468,142 @@ def video_path(spec: PathSpec, xs: torch.Tensor, xt: torch.Tensor, params: Seque
     return _VideoPathFunction.apply(spec, xs, xt, *params)
 
 
+# ----------------------------------------------------------------------------------------------
+# frame_aggregation='avgpool' (SURVEY 8f n4): the same frame level, then the average over the segments
+# ----------------------------------------------------------------------------------------------
+# parameter order: shared W,b | frame-disc W1,b1,W2,b2 | classifier W,b | video-disc W1,b1,W2,b2   (F-wide video level)
+_AVG_OUT_NAMES = ("feat", "pred_frame", "feat_video", "pred_video", "pred_dom_video", "dropped")
+
+
+def avgpool_forward(spec: PathSpec, xs, xt, params, bufs: Buffers):
+    """models.py:557-610 (shared layer, frame discriminator), :427-432 (attention re-weighting + AvgPool2d([T,1])),
+    :679-698 (dropout_v, classifier, video discriminator) as seven C calls.  ``spec.use_attn`` = use_attn='TransAttn':
+    the frame features are re-weighted by (1 - H(softmax(pred_frame)) + 1) before the average."""
+    lib = _lib.load()
+    st = _stream()
+    T = spec.num_segments
+    if xs.dim() != 3 or xt.dim() != 3 or xs.shape[1] != T or xt.shape[1] != T or xs.shape[2] != xt.shape[2]:
+        raise _lib.Ta3nError(f"inputs must be (B,{T},D); got {tuple(xs.shape)} and {tuple(xt.shape)}")
+    if len(params) != 12:
+        raise _lib.Ta3nError(f"the avgpool path takes 12 parameter tensors, got {len(params)}")
+    Bs, Bt, D = xs.shape[0], xt.shape[0], xs.shape[2]
+    M = Bs + Bt
+    w_sh, b_sh, w1f, b1f, w2f, b2f, w_c, b_c, w1v, b1v, w2v, b2v = params
+    F, Cn = w_sh.shape[0], w_c.shape[0]
+    if tuple(w_c.shape) != (Cn, F) or tuple(w1v.shape) != (F, F) or tuple(w2v.shape) != (2, F):
+        raise _lib.Ta3nError("avgpool: the video-level layers must be shared_dim wide (models.py:240-250)")
+    new = bufs.get
+    d_i, d_v = spec.drop_i.cstruct(), spec.drop_v.cstruct()
+    feat = new("feat", M * T, F)
+    check(lib.ta3n_shared_fc_fwd(_p(xs), Bs * T, _p(xt), Bt * T, D, _p(w_sh), _p(b_sh), F, _dref(d_i), _p(feat), st))
+    hid_f, pred_frame = new("hid_f", M * T, F), new("pred_frame", M * T, 2)
+    check(lib.ta3n_disc_fwd(_p(feat), M * T, F, F, _p(w1f), _p(b1f), _p(w2f), _p(b2f), _p(hid_f), _p(pred_frame), st))
+    if spec.use_attn:
+        feat_att = new("feat_att", M * T, F)
+        check(lib.ta3n_frame_attn_fwd(_p(feat), _p(pred_frame), M * T, F, _p(feat_att), st))
+    else:
+        feat_att = feat
+    feat_video = new("feat_video", M, F)
+    check(lib.ta3n_segment_mean_fwd(_p(feat_att), M, T, F, _p(feat_video), st))
+    dropped, pred_video = new("dropped", M, F), new("pred_video", M, Cn)
+    check(lib.ta3n_video_head_fwd(_p(feat_video), M, F, Cn, _p(w_c), _p(b_c), _dref(d_v), _p(dropped), _p(pred_video), st))
+    hid_v, pred_dom_video = new("hid_v", M, F), new("pred_dom_video", M, 2)
+    check(lib.ta3n_disc_fwd(_p(dropped), M, F, F, _p(w1v), _p(b1v), _p(w2v), _p(b2v), _p(hid_v), _p(pred_dom_video), st))
+    saved = dict(feat=feat, hid_f=hid_f, pred_frame=pred_frame, dropped=dropped, hid_v=hid_v)
+    outputs = (feat.view(M, T, F), pred_frame.view(M, T, 2), feat_video, pred_video, pred_dom_video, dropped)
+    return saved, outputs, (Bs, Bt, D, T, F, Cn)
+
+
+def avgpool_backward(spec: PathSpec, dims, xs, xt, params, saved, gin, gout, bufs: Buffers):
+    """The backward C calls of avgpool_forward in reverse order; ``gin`` / ``gout`` as in path_backward."""
+    lib = _lib.load()
+    st = _stream()
+    Bs, Bt, D, T, F, Cn = dims
+    M = Bs + Bt
+    w_sh, b_sh, w1f, b1f, w2f, b2f, w_c, b_c, w1v, b1v, w2v, b2v = params
+    dw_sh, db_sh, dw1f, db1f, dw2f, db2f, dw_c, db_c, dw1v, db1v, dw2v, db2v = gout
+    g = lambda k: gin.get(k)   # noqa: E731
+    new, wsp = bufs.get, bufs.workspace
+    d_v = spec.drop_v.cstruct()
+    feat, hid_f, pred_frame = saved["feat"], saved["hid_f"], saved["pred_frame"]
+    dropped, hid_v = saved["dropped"], saved["hid_v"]
+    # video discriminator: d_dropped = -beta1 * dgrad (+ gradients of further heads on `dropped`, e.g. MCD's second one)
+    d_dropped = new("d_dropped", M, F)
+    g_dropped = g("dropped")
+    if g_dropped is not None:
+        d_dropped.copy_(g_dropped.reshape(M, F))
+    ws = wsp("disc_v", lib.ta3n_disc_bwd_workspace_bytes(M, F, F))
+    check(lib.ta3n_disc_bwd(_p(dropped), M, F, F, _p(w1v), _p(w2v), _p(hid_v), _p(g("pred_dom_video")),
+                            float(spec.beta[1]), _p(d_dropped), 1 if g_dropped is not None else 0, _p(dw1v), _p(db1v),
+                            _p(dw2v), _p(db2v), _p(ws), ws.numel(), st))
+    # classifier + dropout_v (+ GRL_mu under `reverse`)
+    G = new("G", M, F)
+    ws = wsp("vhead", lib.ta3n_video_head_bwd_workspace_bytes(M, F, Cn))
+    check(lib.ta3n_video_head_bwd(_p(dropped), M, F, Cn, _p(w_c), _dref(d_v), _p(g("pred_video")), _p(d_dropped),
+                                  _p(g("feat_video")), float(-spec.mu) if spec.reverse else 1.0, _p(G),
+                                  _p(dw_c), _p(db_c), _p(ws), ws.numel(), st))
+    # average over the segments, then the attention re-weighting (its weights' gradient goes into the frame logits)
+    d_feat = new("d_feat", M * T, F)
+    check(lib.ta3n_segment_mean_bwd(_p(G), M, T, F, _p(d_feat), st))
+    g_pf = g("pred_frame")
+    if g_pf is not None:
+        g_pf = g_pf.reshape(M * T, 2)
+    if spec.use_attn:
+        acc = new("g_pf_acc", M * T, 2)
+        if g_pf is not None:
+            acc.copy_(g_pf)
+        else:
+            acc.zero_()
+        g_pf = acc
+        check(lib.ta3n_frame_attn_bwd(_p(feat), _p(pred_frame), M * T, F, _p(d_feat), _p(g_pf), st))
+    # frame discriminator: d_feat += -beta2 * dgrad
+    ws = wsp("disc_f", lib.ta3n_disc_bwd_workspace_bytes(M * T, F, F))
+    check(lib.ta3n_disc_bwd(_p(feat), M * T, F, F, _p(w1f), _p(w2f), _p(hid_f), _p(g_pf), float(spec.beta[2]),
+                            _p(d_feat), 1, _p(dw1f), _p(db1f), _p(dw2f), _p(db2f), _p(ws), ws.numel(), st))
+    # shared layer (weight gradient only)
+    ws = wsp("shared", lib.ta3n_shared_fc_bwd_workspace_bytes(M * T, D, F))
+    g_feat = g("feat")
+    g_feat_flat = None if g_feat is None else g_feat.reshape(M * T, F)
+    check(lib.ta3n_shared_fc_bwd(_p(xs), Bs * T, _p(xt), Bt * T, D, F, _p(feat), _p(d_feat), _p(g_feat_flat),
+                                 float(spec.drop_i.p), _p(dw_sh), _p(db_sh), _p(ws), ws.numel(), st))
+
+
+class _AvgPoolPathFunction(torch.autograd.Function):
+    """VideoModel.forward with frame_aggregation='avgpool', source and target rows together, as ONE autograd node.
+    Outputs (M = Bs + Bt rows, source first): feat_fc (M,T,F) | pred_frame (M,T,2) | feat_video (M,F) |
+    pred_video (M,C) | pred_dom_video (M,2) | dropped (M,F)."""
+
+    @staticmethod
+    def forward(ctx, spec: PathSpec, xs, xt, *params):
+        xs, xt = _chk(xs, "input_source"), _chk(xt, "input_target")
+        params = [_chk(p, "parameter") for p in params]
+        saved, outputs, dims = avgpool_forward(spec, xs, xt, params, Buffers(xs.device))
+        ctx.spec, ctx.dims = spec, dims
+        ctx.saved_names = list(saved)
+        ctx.drop_keepalive = (spec.drop_i.keep, spec.drop_v.keep, spec.drop_i.step, spec.drop_v.step)
+        ctx.save_for_backward(xs, xt, *[saved[k] for k in ctx.saved_names], *params)
+        ctx.set_materialize_grads(False)
+        return outputs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise _lib.Ta3nError("gradients w.r.t. the input features are not part of this path")
+        tensors = ctx.saved_tensors
+        xs, xt = tensors[0], tensors[1]
+        n = len(ctx.saved_names)
+        saved = dict(zip(ctx.saved_names, tensors[2:2 + n]))
+        params = list(tensors[2 + n:])
+        gin = {k: _chk(g, "grad") for k, g in zip(_AVG_OUT_NAMES, grads) if g is not None}
+        gout = [torch.empty_like(p) for p in params]
+        avgpool_backward(ctx.spec, ctx.dims, xs, xt, params, saved, gin, gout, Buffers(xs.device))
+        return (None, None, None, *gout)
+
+
+def avgpool_path(spec: PathSpec, xs: torch.Tensor, xt: torch.Tensor, params: Sequence[torch.Tensor]):
+    return _AvgPoolPathFunction.apply(spec, xs, xt, *params)
+
+
 class _VideoHead2Function(torch.autograd.Function):
     """A further classifier on the dropped video feature: ``fc_classifier_video_source_2`` of the MCD variant
     (models.py:276-279, 716-720).  Forward and backward are the library's video-head operators without dropout

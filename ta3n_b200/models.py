@@ -51,8 +51,12 @@ class VideoModel(nn.Module):
         super().__init__()
         if add_fc < 1:
             raise ValueError('add at least one fc layer')                 # models.py:137-138
-        if frame_aggregation != 'trn-m':
-            _unsupported('frame_aggregation', frame_aggregation, ['trn-m'])
+        if frame_aggregation not in ('trn-m', 'avgpool'):
+            _unsupported('frame_aggregation', frame_aggregation, ['trn-m', 'avgpool'])
+        if frame_aggregation == 'avgpool' and (use_attn == 'general' or use_attn_frame != 'none'):
+            # models.py:427: aggregate_frames only knows TransAttn; general attention is defined over relation features
+            _unsupported('frame_aggregation with (use_attn, use_attn_frame)', (frame_aggregation, use_attn, use_attn_frame),
+                         [('avgpool', 'TransAttn', 'none'), ('avgpool', 'none', 'none')])
         if baseline_type != 'video':
             _unsupported('baseline_type', baseline_type, ['video'])
         if add_fc != 1:
@@ -129,12 +133,16 @@ class VideoModel(nn.Module):
         self.fc_classifier_source = std_linear(feat_frame_dim, num_class)               # :166 (output dropped)
         self.fc_classifier_domain = std_linear(feat_frame_dim, 2)                       # :170
 
-        self.num_bottleneck = 256                                                        # :223
-        self.TRN = TRNmodule.RelationModuleMultiScale(feat_shared_dim, self.num_bottleneck,
-                                                      self.train_segments, nonneg_input=True)
-        self.bn_trn_S = nn.BatchNorm1d(self.num_bottleneck)                              # :225 (unused)
-        self.bn_trn_T = nn.BatchNorm1d(self.num_bottleneck)
-        feat_aggregated_dim = feat_video_dim = self.num_bottleneck
+        trn = self.frame_aggregation == 'trn-m'
+        if trn:
+            self.num_bottleneck = 256                                                    # :223
+            self.TRN = TRNmodule.RelationModuleMultiScale(feat_shared_dim, self.num_bottleneck,
+                                                          self.train_segments, nonneg_input=True)
+            self.bn_trn_S = nn.BatchNorm1d(self.num_bottleneck)                          # :225 (unused)
+            self.bn_trn_T = nn.BatchNorm1d(self.num_bottleneck)
+            feat_aggregated_dim = feat_video_dim = self.num_bottleneck
+        else:                                                                            # avgpool, :240-241, :250
+            feat_aggregated_dim = feat_video_dim = feat_shared_dim
 
         self.fc_feature_video_source = std_linear(feat_aggregated_dim, feat_video_dim)  # :258 (unused)
         self.fc_feature_video_source_2 = std_linear(feat_video_dim, feat_video_dim)     # :262 (unused)
@@ -144,9 +152,10 @@ class VideoModel(nn.Module):
             self.fc_classifier_video_source_2 = std_linear(feat_video_dim, num_class)
         self.fc_classifier_domain_video = std_linear(feat_video_dim, 2)                 # :281
 
-        self.relation_domain_classifier_all = nn.ModuleList(                             # :286-294
-            nn.Sequential(nn.Linear(feat_aggregated_dim, feat_video_dim), nn.ReLU(), nn.Linear(feat_video_dim, 2))
-            for _ in range(self.train_segments - 1))
+        if trn:
+            self.relation_domain_classifier_all = nn.ModuleList(                         # :285-294 (trn-m only)
+                nn.Sequential(nn.Linear(feat_aggregated_dim, feat_video_dim), nn.ReLU(), nn.Linear(feat_video_dim, 2))
+                for _ in range(self.train_segments - 1))
 
         self.alpha = torch.ones(1)                                                       # :314
         if self.use_attn == 'general':                                                   # :320-325, PyTorch default init
@@ -176,6 +185,13 @@ class VideoModel(nn.Module):
 
     def path_parameters(self):
         """Parameters consumed by the fused operator, in its expected order."""
+        if self.frame_aggregation == 'avgpool':
+            return [self.fc_feature_shared_source.weight, self.fc_feature_shared_source.bias,
+                    self.fc_feature_domain.weight, self.fc_feature_domain.bias,
+                    self.fc_classifier_domain.weight, self.fc_classifier_domain.bias,
+                    self.fc_classifier_video_source.weight, self.fc_classifier_video_source.bias,
+                    self.fc_feature_domain_video.weight, self.fc_feature_domain_video.bias,
+                    self.fc_classifier_domain_video.weight, self.fc_classifier_domain_video.bias]
         R = self.train_segments - 1
         trn_w, trn_b = self.TRN.relation_weights()
         rel = self.relation_domain_classifier_all
@@ -215,6 +231,8 @@ class VideoModel(nn.Module):
     # ---- forward (models.py:545-722) -----------------------------------------------------------------
     def forward(self, input_source, input_target, beta, mu, is_train, reverse):
         num_segments = self.train_segments if is_train else self.val_segments        # :548
+        if self.frame_aggregation == 'avgpool':
+            return self._forward_avgpool(input_source, input_target, beta, mu, num_segments, reverse)
         if num_segments != self.train_segments:
             raise RuntimeError(f"trn-m is built for train_segments={self.train_segments}; got "
                                f"num_segments={num_segments} (the reference fails here too, SURVEY App. D Q3)")
@@ -250,3 +268,35 @@ class VideoModel(nn.Module):
         #   pred_domain = [relation (B,R,2), video (B,2), frame (B,T,2)];  feat = [pred (B,C), video (B,H), fc (B,T,F)]
         return (attn_s, out_s, out2_s, [pr_s, pv_s, pf_s], [out_s, fv_s, ff_s],
                 attn_t, out_t, out2_t, [pr_t, pv_t, pf_t], [out_t, fv_t, ff_t])
+
+    def _forward_avgpool(self, input_source, input_target, beta, mu, num_segments, reverse):
+        """frame_aggregation='avgpool' (models.py:620-626, 425-433): no relation level.  The reference fills the relation
+        slot of pred_domain with the video-level prediction (:703-706) and the attention output with the first feature of
+        every video (:624-626); both are reproduced so that main.py's loss loop sees the same tensors."""
+        dev = self.fc_feature_shared_source.weight.device
+        if dev.type != 'cuda':
+            raise TF._lib.Ta3nError("VideoModel must live on a CUDA device (model.cuda()); there is no CPU path")
+        xs = input_source.to(device=dev, dtype=torch.float32, non_blocking=True)
+        xt = input_target.to(device=dev, dtype=torch.float32, non_blocking=True)
+        xs = xs.reshape(-1, num_segments, xs.size(-1))
+        xt = xt.reshape(-1, num_segments, xt.size(-1))
+        Bs = xs.size(0)
+        drop_i, drop_v = self._drop_specs(dev)
+        spec = TF.PathSpec(num_segments=num_segments, beta=(float(beta[0]), float(beta[1]), float(beta[2])),
+                           mu=float(mu), reverse=bool(reverse), use_attn=self.use_attn == 'TransAttn',
+                           drop_i=drop_i, drop_v=drop_v)
+        feat_fc, pred_frame, feat_video, pred_video, pred_dom_video, dropped = TF.avgpool_path(
+            spec, xs, xt, self.path_parameters())
+        pred_video_2 = pred_video
+        if self.ens_DA == 'MCD':
+            pred_video_2 = TF.video_head2(dropped, self.fc_classifier_video_source_2.weight,
+                                          self.fc_classifier_video_source_2.bias)
+
+        def halves(t):
+            return t[:Bs], t[Bs:]
+
+        (out_s, out_t), (out2_s, out2_t) = halves(pred_video), halves(pred_video_2)
+        (ff_s, ff_t), (fv_s, fv_t) = halves(feat_fc), halves(feat_video)
+        (pf_s, pf_t), (pv_s, pv_t) = halves(pred_frame), halves(pred_dom_video)
+        return (fv_s[:, 0], out_s, out2_s, [pv_s, pv_s, pf_s], [out_s, fv_s, ff_s],
+                fv_t[:, 0], out_t, out2_t, [pv_t, pv_t, pf_t], [out_t, fv_t, ff_t])

@@ -121,11 +121,12 @@ class TrainStep:
         default: 'peer' when symmetric memory can be set up (and no NCCL overlap option was asked for), else 'nccl'."""
         if not model.training:
             raise ValueError("TrainStep needs model.train() (dropout state is fixed at construction)")
-        if model.use_attn == "general" or getattr(model, "ens_DA", "none") != "none":
+        if model.use_attn == "general" or getattr(model, "ens_DA", "none") != "none" or \
+                model.frame_aggregation != "trn-m":
             # the off-path variants (SURVEY 8f n4) run through VideoModel.forward + autograd; the captured step covers
             # the shipped configurations (use_attn 'TransAttn' / 'none', one classifier)
-            raise NotImplementedError("TrainStep covers use_attn in ('TransAttn', 'none') and ens_DA='none'; train "
-                                      "use_attn='general' / ens_DA='MCD' models with model(...) + loss.backward()")
+            raise NotImplementedError("TrainStep covers frame_aggregation='trn-m', use_attn in ('TransAttn', 'none') and "
+                                      "ens_DA='none'; train the other variants with model(...) + loss.backward()")
         self.model = model
         self.params = model.path_parameters()
         dev = self.params[0].device

@@ -72,6 +72,11 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.ta3n_general_attn_bwd_workspace_bytes(256, 4, 256) >= 256 * 4 * 256 * 4
     assert lib.ta3n_relattn_bwd(None, 4, 4, 256, None, None, 3, None, None, None, None, None, None, 0.5, None, None,
                                 None, None, None, None, 0, None) == 1
+    # segment mean (avgpool): bad sizes / null pointers; an empty batch is a no-op
+    assert lib.ta3n_segment_mean_fwd(None, 4, 0, 8, None, None) == 1
+    assert lib.ta3n_segment_mean_fwd(None, 4, 5, 8, None, None) == 1
+    assert lib.ta3n_segment_mean_bwd(None, 4, 5, 8, None, None) == 1
+    assert lib.ta3n_segment_mean_fwd(None, 0, 5, 8, None, None) == 0
     # loss heads: a class count / batch of zero is rejected before anything is launched
     assert lib.ta3n_loss_fwd_bwd(None, None, None, None, None, 0, 0, 5, 4, 12, 0.003, 15, None, None, None, None,
                                  None, None, None, 0, None) == 1
@@ -95,7 +100,7 @@ def test_no_cpu_fallback_in_product_package():
 
 def test_unsupported_options_raise():
     from ta3n_b200.models import VideoModel
-    for kw in (dict(frame_aggregation="avgpool"), dict(use_bn="AdaBN"), dict(ens_DA="AutoDIAL"),
+    for kw in (dict(frame_aggregation="rnn"), dict(frame_aggregation="avgpool", use_attn="general"), dict(use_bn="AdaBN"), dict(ens_DA="AutoDIAL"),
                dict(share_params="N"), dict(use_attn="general", use_attn_frame="TransAttn"), dict(baseline_type="tsn")):
         args = dict(num_class=5, baseline_type="video", frame_aggregation="trn-m", modality="RGB", verbose=False)
         args.update(kw)
@@ -103,6 +108,19 @@ def test_unsupported_options_raise():
             VideoModel(**args)
     with pytest.raises(ValueError):
         VideoModel(5, "video", "trn-m", "RGB", add_fc=0, verbose=False)
+
+
+def test_avgpool_model_has_the_reference_parameters():
+    """frame_aggregation='avgpool' (models.py:240-250, 285): shared_dim-wide video level, no TRN / relation layers."""
+    from ta3n_b200.models import VideoModel
+    from ta3n_b200.train import TrainStep
+    m = VideoModel(5, "video", "avgpool", "RGB", train_segments=5, val_segments=5, fc_dim=128, verbose=False)
+    sd = m.state_dict()
+    assert not any(k.startswith(("TRN", "relation_domain_classifier_all", "bn_trn")) for k in sd)
+    assert sd["fc_feature_domain_video.weight"].shape == (128, 128) and sd["fc_classifier_video_source.weight"].shape == (5, 128)
+    assert len(m.path_parameters()) == 12
+    with pytest.raises(NotImplementedError):
+        TrainStep(m, 4, 4, beta=[0.75, 0.75, 0.5])
 
 
 def test_general_attention_model_has_the_reference_parameters():

@@ -46,7 +46,7 @@ def engine(request):
 
 def build_model(cfg: orc.PathConfig, params, train: bool):
     from ta3n_b200.models import VideoModel
-    m = VideoModel(cfg.num_class, "video", "trn-m", "RGB", train_segments=cfg.num_segments,
+    m = VideoModel(cfg.num_class, "video", cfg.frame_aggregation, "RGB", train_segments=cfg.num_segments,
                    val_segments=cfg.num_segments, add_fc=1, fc_dim=cfg.fc_dim, dropout_i=cfg.dropout_i,
                    dropout_v=cfg.dropout_v, partial_bn=False, use_bn="none", ens_DA=cfg.ens_DA,
                    use_attn=cfg.use_attn, use_attn_frame=cfg.use_attn_frame, share_params="Y", verbose=False)
@@ -201,6 +201,72 @@ def test_general_attention_variant_matches_oracle(T, bs, bt, drop, engine):
             continue
         assert_close(named[name].grad, go, GRAD_TOL[engine], f"grad {name}",
                      noise=abs_err(g32[name], go) * NOISE_SCALE[engine])
+
+
+@pytest.mark.parametrize("T,fc_dim,bs,bt,use_attn,ens", [(5, 512, 19, 14, "TransAttn", "none"), (3, 256, 8, 11, "none", "none"),
+                                                          (4, 512, 10, 6, "TransAttn", "MCD")])
+def test_avgpool_variant_matches_oracle(T, fc_dim, bs, bt, use_attn, ens, engine):
+    """SURVEY 8f n4, frame_aggregation='avgpool' (models.py:425-433, 620-626, 703-706): frame level as on the path, the
+    frame features (re-weighted by the frame-level domain attention under TransAttn) averaged over the segments,
+    shared_dim-wide video-level layers, the video-level domain prediction doubling as the relation slot.  Outputs and
+    every gradient against the fp64 oracle with trained-like weights and dropout masks (the oracle's branch is pinned to
+    the live reference in tests/test_oracle_vs_reference.py and by two golden cases); with ens='MCD' the loss also
+    carries the second classifier and the discrepancy term."""
+    cfg = orc.PathConfig(num_class=9, num_segments=T, fc_dim=fc_dim, dropout_i=0.5, dropout_v=0.5, use_attn=use_attn,
+                         ens_DA=ens, frame_aggregation="avgpool")
+    params = orc.init_params(cfg, seed=31)
+    g = torch.Generator().manual_seed(32)
+    for k in params:
+        if params[k].dtype.is_floating_point and "weight" in k and \
+                (k.startswith(orc.USED_PARAM_PREFIXES) or k.startswith("fc_classifier_video_source_2")):
+            params[k] = params[k] + 0.02 * torch.randn(params[k].shape, generator=g)
+    xs = torch.randn(bs, T, orc.FEATURE_DIM, generator=g)
+    xt = torch.randn(bt, T, orc.FEATURE_DIM, generator=g) + 0.3
+    labels = torch.randint(0, 9, (bs,), generator=g)
+    keep = lambda *s: (torch.rand(*s, generator=g) < 0.5).to(torch.uint8)   # noqa: E731
+    masks = {"i_source": keep(bs * T, fc_dim), "i_target": keep(bt * T, fc_dim),
+             "v_source": keep(bs, fc_dim), "v_target": keep(bt, fc_dim)}
+    beta = [0.75, 0.6, 0.5]
+
+    def loss_of(outs, lab, compose):
+        loss = compose(outs, lab) + 0.5 * (outs[0] ** 2).sum()              # also through the attention placeholder
+        if ens == "MCD":
+            loss = loss + torch.nn.functional.cross_entropy(outs[2], lab) - orc.dis_MCD(outs[6], outs[7])
+        return loss
+
+    def oracle(dtype):
+        p = {k: (v.to(dtype).requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in params.items()}
+        o = orc.forward(p, xs.to(dtype), xt.to(dtype), beta, 0.0, cfg, train=True, reverse=False, masks=masks)
+        loss = loss_of(o, labels, lambda oo, ll: orc.compose_loss(oo, ll, 0.003, use_attn=use_attn))
+        loss.backward()
+        return loss.detach(), o, {k: v.grad for k, v in p.items() if v.dtype.is_floating_point and v.grad is not None}
+
+    l64, o64, g64 = oracle(torch.float64)
+    l32, o32, g32 = oracle(torch.float32)
+    from ta3n_b200.loss import ta3n_loss
+    model = build_model(cfg, params, train=True)
+    model.dropout_masks = cat_masks(masks)
+    outs = model(xs.to(_dev()), xt.to(_dev()), beta, 0.0, is_train=True, reverse=False)
+    loss = loss_of(outs, labels.to(_dev()), lambda oo, ll: ta3n_loss(oo, ll, 0.003, use_attn=use_attn))
+    loss.backward()
+    torch.cuda.synchronize()
+    tol = TOL[engine]
+    assert_close(loss.detach().cpu(), l64, tol, "loss", noise=abs(l32.item() - l64.item()))
+    assert outs[0].shape == (bs,) and outs[5].shape == (bt,) and outs[3][0].shape == (bs, 2)
+    assert outs[3][0] is outs[3][1]                     # the relation slot IS the video-level prediction (:705-706)
+    for i, (a, b, c32) in enumerate(zip(flat_outputs(outs) + [outs[2], outs[7]], flat_outputs(o64) + [o64[2], o64[7]],
+                                        flat_outputs(o32) + [o32[2], o32[7]])):
+        assert a.shape == b.shape
+        assert_close(a.detach().cpu(), b.detach(), tol, f"output {i}", noise=abs_err(c32.detach(), b.detach()))
+    named = dict(model.named_parameters())
+    assert len(g64) == (14 if ens == "MCD" else 12)
+    for name, go in g64.items():
+        assert named[name].grad is not None, name
+        assert_close(named[name].grad, go, GRAD_TOL[engine], f"grad {name}",
+                     noise=abs_err(g32[name], go) * NOISE_SCALE[engine])
+    for name, prm in named.items():                      # parameters off the path stay without gradient
+        if name not in g64:
+            assert prm.grad is None, name
 
 
 @pytest.mark.parametrize("T,attn_frame,bs,bt", [(5, "none", 48, 40), (6, "TransAttn", 12, 20)])

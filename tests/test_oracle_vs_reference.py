@@ -11,7 +11,8 @@ from tests.golden_util import STRUCTURAL_ZERO_GRADS, TOL_FP32, assert_close
 pytestmark = pytest.mark.skipif(not ref_shims.available(), reason="/root/reference not present")
 
 
-@pytest.mark.parametrize("case", ["cfg1_train_masked", "t9_attnframe", "noattn_f256", "general_attn"])
+@pytest.mark.parametrize("case", ["cfg1_train_masked", "t9_attnframe", "noattn_f256", "general_attn", "avgpool_transattn",
+                                  "avgpool_noattn_f256"])
 def test_oracle_equals_live_reference(case):
     c = gen_golden.CASES[case]
     model, outs_ref, loss_ref, _ = gen_golden.run_reference(c)
