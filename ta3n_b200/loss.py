@@ -21,6 +21,11 @@ def attentive_entropy(pred, pred_domain):
     return torch.mean((1 + dom_ent) * cls_ent)
 
 
+def dis_MCD(out1, out2):
+    """loss.py:29-30 -- classifier discrepancy of the MCD variant (main.py:548-556): mean |softmax(out1) - softmax(out2)|."""
+    return torch.mean(torch.abs(F.softmax(out1, dim=1) - F.softmax(out2, dim=1)))
+
+
 def ta3n_loss(outputs, label_source, gamma=0.003, place_adv=('Y', 'Y', 'Y'), use_attn='TransAttn',
               add_loss_DA='attentive_entropy'):
     """Loss of the shipped configuration (use_target='uSv', adv_DA='RevGrad'):

@@ -60,3 +60,18 @@ def test_learning_rate_schedule_matches_oracle_restatement_of_main_py():
     assert T.lr_dann(3e-2, 0.0) == 3e-2
     cfg = T.SGDNesterov(lr=3e-2)
     assert (cfg.momentum, cfg.weight_decay, cfg.clip_gradient) == (0.9, 1e-4, 20.0)   # opts.py defaults
+
+
+def test_loss_helpers_match_the_oracle_statements():
+    """ta3n_b200.loss (torch-op heads next to the path, loss.py:8-30) against the oracle's restatements, which are
+    pinned to the live reference in tests/test_oracle_vs_reference.py."""
+    import torch
+
+    from oracle import ta3n_oracle as orc
+    from ta3n_b200 import loss as L
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.randn(11, 7, generator=g), torch.randn(11, 7, generator=g)
+    d = torch.randn(11, 2, generator=g)
+    assert torch.allclose(L.dis_MCD(a, b), orc.dis_MCD(a, b), rtol=0, atol=1e-7)
+    assert torch.allclose(L.attentive_entropy(a, d), orc.attentive_entropy(a, d), rtol=0, atol=1e-6)
+    assert float(L.dis_MCD(a, a)) == 0.0
