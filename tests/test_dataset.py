@@ -85,6 +85,24 @@ def test_packed_shard_serves_the_same_items(tmp_path):
         D.pack_list(lst, shard, num_segments=5, rule="random")
 
 
+def test_gather_fills_the_staging_buffer_in_batch_order(tmp_path):
+    lst = _make_tree(str(tmp_path))
+    shard = os.path.join(str(tmp_path), "g.npy")
+    D.pack_list(lst, shard, num_segments=5)
+    packed = D.PackedTSNDataSet(shard, num_dataload=11)
+    out, lab = torch.full((6, 5, 16), -1.0), torch.full((6,), -1, dtype=torch.int64)
+    idx = np.array([10, 0, 7, 3])                       # unsorted, with a repeated underlying row (10 -> row 3)
+    packed.gather(idx, out, lab)
+    for k, i in enumerate(idx):
+        x, y = packed[int(i)]
+        assert torch.equal(out[k], x) and int(lab[k]) == y
+    assert torch.all(out[4:] == -1) and torch.all(lab[4:] == -1)        # a short batch leaves the tail alone
+    with pytest.raises(IndexError):
+        packed.gather(np.array([11]), out, lab)
+    packed.gather(np.array([], dtype=np.int64), out, lab)               # empty batch: no-op
+    assert torch.all(out[4:] == -1)
+
+
 def test_paired_loader_covers_each_epoch_like_zip_of_random_samplers(tmp_path):
     src_root, tgt_root = os.path.join(str(tmp_path), "s"), os.path.join(str(tmp_path), "t")
     os.makedirs(src_root), os.makedirs(tgt_root)
