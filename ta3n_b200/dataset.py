@@ -194,6 +194,9 @@ class PackedTSNDataSet(data.Dataset):
             self.meta = json.load(f)
         if len(self.meta["labels"]) != self.features.shape[0]:
             raise ValueError("shard and metadata disagree on the number of videos")
+        if self.features.dtype != np.float32 or self.features.ndim != 3:
+            raise ValueError(f"{packed_path}: expected a (videos, frames, feat_dim) float32 shard as written by pack_list, "
+                             f"got {self.features.dtype} {self.features.shape}")
         n = self.features.shape[0]
         # plain-ndarray view of the same mapping, one row per video: indexing a np.memmap builds a new memmap object per
         # access (3-4 us each, under the GIL), which was most of the time of a 512-row gather
